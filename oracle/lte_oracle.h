@@ -1,0 +1,122 @@
+/*
+ * lte_oracle.h -- CPU ORACLE for the srsUE downlink PDSCH receive chain.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked into, imported by or
+ * executed from the product (libsrsue_gpu / srsue_b200).  Only tests/, the smoke
+ * check in __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs
+ * may use it, and only as the checker.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in srsLTE (github.com/srsLTE/srsLTE,
+ * pinned only as ">= 1.0.0" by /root/reference/ue/hdr/srslte_version_check.h:30-41 and
+ * /root/reference/CMakeLists.txt:101), which is neither vendored in the reference tree nor
+ * installable offline, and the reference holds no golden vector for this path
+ * (ue/test/phy/CMakeLists.txt:20-24).  This file restates the chain from 3GPP TS 36.211 /
+ * 36.212 (Rel-8) plus the srsLTE-flavoured fixed-point conventions frozen in oracle/SPEC.md;
+ * behaviour at the API boundary follows the reference call sites
+ * (ue/src/phy/phch_worker.cc:246-374, ue/src/mac/dl_harq.cc:191-259).
+ */
+#ifndef LTE_ORACLE_H
+#define LTE_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float re, im; } lteo_cf_t;
+typedef struct { double re, im; } lteo_cd_t;
+
+#define LTEO_CRC24A 0x1864CFBu
+#define LTEO_CRC24B 0x1800063u
+#define LTEO_CRC16  0x11021u
+
+/* fixed-point turbo decoder constants (SPEC.md section 7) */
+#define LTEO_TD_C     511     /* clamp on channel LLRs at the decoder input          */
+#define LTEO_TD_E     2047    /* clamp on the extrinsic / a-priori LLR              */
+#define LTEO_TD_INF   10000   /* finite "minus infinity" for known trellis states   */
+#define LTEO_TD_NORM  4       /* state metrics re-normalised when k % 4 == 0        */
+#define LTEO_MAX_K    6144
+#define LTEO_LLR_MAX  32767   /* symmetric int16 saturation of LLRs / soft buffer   */
+#define LTEO_FILLER_LLR (-32767)
+
+typedef struct {
+  int nof_prb;      /* 6,15,25,50,75,100 */
+  int nof_ports;    /* 1 or 2 */
+  int cell_id;      /* 0..503, normal CP */
+} lteo_cell_t;
+
+typedef struct {
+  int sf_idx;       /* 0..9 */
+  int cfi;          /* 1..3 */
+  int rnti;
+  int qm;           /* 2,4,6 */
+  int tbs;          /* transport block size in bits */
+  int rv;           /* 0..3 */
+  int tm;           /* 1 = single port, 2 = transmit diversity (needs nof_ports == 2) */
+  int nof_prb_alloc;
+  uint8_t prb_mask[110]; /* 1 = PRB allocated (same PRBs in both slots) */
+} lteo_pdsch_cfg_t;
+
+typedef struct { int tbs, B, C, Kp, Km, Cp, Cm, F; } lteo_cbsegm_t;
+
+/* ---- tables / small helpers ------------------------------------------------------------ */
+int      lteo_qpp_params(int K, int *f1, int *f2);         /* 0 = ok, -1 = K not in table      */
+int      lteo_qpp_table_size(void);
+int      lteo_qpp_K(int idx);
+void     lteo_qpp_perm(int K, uint16_t *pi);                 /* pi[i] = (f1 i + f2 i^2) mod K   */
+int      lteo_window_len(int K);                             /* W(K), SPEC.md 7.3               */
+int      lteo_symbol_sz(int nof_prb);
+int      lteo_cp_len(int nfft, int symbol_in_slot);
+uint32_t lteo_crc_bits(const uint8_t *bits, int n, uint32_t poly, int order);
+void     lteo_gold(uint32_t c_init, int n, uint8_t *c);
+int      lteo_cbsegm(int tbs, lteo_cbsegm_t *s);
+int      lteo_cb_len(const lteo_cbsegm_t *s, int r);
+int      lteo_cb_E(const lteo_cbsegm_t *s, int G, int qm, int nl, int r);
+int      lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int32_t *re_idx);
+int      lteo_crs_positions(const lteo_cell_t *cell, int port, int l, int32_t *k_out);
+void     lteo_crs_values(const lteo_cell_t *cell, int sf_idx, int l, int8_t *re_sign, int8_t *im_sign);
+void     lteo_fft_twiddles(int n, lteo_cf_t *tw);           /* tw[k] = exp(-2 pi i k / n), k < n/2 */
+
+/* ---- TX side (test-vector generator; double precision) ---------------------------------- */
+void lteo_turbo_encode(const uint8_t *c, int K, uint8_t *d);            /* d: 3*(K+4) triples   */
+int  lteo_rm_sequence(int K, int F, int rv, int32_t *seq);              /* returns N_nd         */
+int  lteo_rm_tx(const uint8_t *d, int K, int F, int E, int rv, uint8_t *e);
+int  lteo_pdsch_encode_bits(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
+                            const uint8_t *tb_bytes, uint8_t *e_bits, int *G_out);
+int  lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
+                        const uint8_t *tb_bytes, lteo_cd_t *grid /* [ports][14][12*nof_prb] */);
+void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq /* 15*nfft samples */);
+
+/* ---- RX side (the restated hot path) ---------------------------------------------------- */
+void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n);
+void lteo_ofdm_rx(int nof_prb, const lteo_cf_t *iq, lteo_cf_t *sf_symbols);
+/* meas[5] = noise, rsrp, rssi, rsrq, snr */
+void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf_symbols,
+                lteo_cf_t *ce /* [ports][14*nsc] */, float *meas);
+void lteo_equalize(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, const lteo_cf_t *sf_symbols,
+                   const lteo_cf_t *ce, float noise_est, lteo_cf_t *d, int *nof_re);
+void lteo_demod(const lteo_cf_t *d, int nof_re, int qm, int16_t *llr);
+void lteo_descramble(int16_t *llr, int n, uint32_t c_init);
+void lteo_rm_rx(const int16_t *e, int E, int K, int F, int rv, int16_t *w /* 3K+12 triples */);
+/* crc_type: 0 none, 1 CRC24A, 2 CRC24B.  returns iterations run.  bits: K hard bits.        */
+int  lteo_tdec(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok);
+/* Debug variant: also returns ext/La after the last iteration and per-iteration bits        */
+int  lteo_tdec_dbg(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok,
+                   int16_t *la_out, int window_override);
+/* softbuf: [C][3*6144+12] int16 (srsLTE triples order), accumulated in place (caller resets
+ * for a new transmission).  Outputs (optional, may be NULL): d, e (descrambled LLRs), cb_iters,
+ * cb_crc.  Returns 0 iff TB CRC passes (srslte_pdsch_decode_rnti convention), -1 otherwise.  */
+int  lteo_pdsch_decode(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
+                       const lteo_cf_t *sf_symbols, const lteo_cf_t *ce, float noise_est,
+                       int max_iter, int16_t *softbuf, uint8_t *payload,
+                       lteo_cf_t *d_out, int16_t *e_out, int *cb_iters, int *cb_crc);
+/* whole chain from time-domain IQ: srslte_ue_dl_decode-like with the grant supplied.
+ * noise_mode: 0 = use noise_est argument, 1 = use channel-estimator noise.                    */
+int  lteo_ue_dl_decode(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, const lteo_cf_t *iq,
+                       float noise_est, int noise_mode, int max_iter, int16_t *softbuf,
+                       uint8_t *payload, float *meas, int *avg_iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

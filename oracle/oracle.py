@@ -1,0 +1,314 @@
+"""ctypes binding of the CPU oracle (oracle/liblteoracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/lte_oracle.h.  Imported by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs; never by the
+product package srsue_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblteoracle.so")
+
+MAX_K = 6144
+SB_STRIDE = 3 * MAX_K + 12
+CRC24A, CRC24B, CRC16 = 0x1864CFB, 0x1800063, 0x11021
+TD_C, TD_E, TD_INF = 511, 2047, 10000
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if (not force and os.path.exists(_SO)
+            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
+        return _SO
+    subprocess.check_call(["make", "-B", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class Cell(C.Structure):
+    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int)]
+
+
+class PdschCfg(C.Structure):
+    _fields_ = [("sf_idx", C.c_int), ("cfi", C.c_int), ("rnti", C.c_int), ("qm", C.c_int),
+                ("tbs", C.c_int), ("rv", C.c_int), ("tm", C.c_int), ("nof_prb_alloc", C.c_int),
+                ("prb_mask", C.c_uint8 * 110)]
+
+
+class CbSegm(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("tbs", "B", "C", "Kp", "Km", "Cp", "Cm", "F")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        try:
+            _lib = C.CDLL(_SO)
+        except OSError:
+            build(force=True)
+            _lib = C.CDLL(_SO)
+        _lib.lteo_crc_bits.restype = C.c_uint32
+    return _lib
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+def make_cell(nof_prb, nof_ports=1, cell_id=1):
+    return Cell(nof_prb, nof_ports, cell_id)
+
+
+def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None):
+    cfg = PdschCfg()
+    cfg.sf_idx, cfg.cfi, cfg.rnti, cfg.qm, cfg.tbs, cfg.rv, cfg.tm = sf_idx, cfi, rnti, qm, tbs, rv, tm
+    prbs = range(cell.nof_prb) if prbs is None else prbs
+    n = 0
+    for p in prbs:
+        cfg.prb_mask[p] = 1
+        n += 1
+    cfg.nof_prb_alloc = n
+    return cfg
+
+
+# ---- small helpers -------------------------------------------------------------------------
+def qpp_Ks():
+    L = lib()
+    return [L.lteo_qpp_K(i) for i in range(L.lteo_qpp_table_size())]
+
+
+def qpp_params(K):
+    f1, f2 = C.c_int(), C.c_int()
+    if lib().lteo_qpp_params(K, C.byref(f1), C.byref(f2)):
+        raise ValueError(K)
+    return f1.value, f2.value
+
+
+def qpp_perm(K):
+    pi = np.zeros(K, np.uint16)
+    lib().lteo_qpp_perm(K, _p(pi))
+    return pi
+
+
+def window_len(K):
+    return lib().lteo_window_len(K)
+
+
+def crc_bits(bits, poly, order=24):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    return lib().lteo_crc_bits(_p(bits), len(bits), C.c_uint32(poly), order)
+
+
+def gold(c_init, n):
+    c = np.zeros(n, np.uint8)
+    lib().lteo_gold(C.c_uint32(c_init), n, _p(c))
+    return c
+
+
+def cbsegm(tbs):
+    s = CbSegm()
+    if lib().lteo_cbsegm(tbs, C.byref(s)):
+        raise ValueError(tbs)
+    return s
+
+
+def cb_len(s, r):
+    return lib().lteo_cb_len(C.byref(s), r)
+
+
+def cb_E(s, G, qm, nl, r):
+    return lib().lteo_cb_E(C.byref(s), G, qm, nl, r)
+
+
+def pdsch_re_list(cell, cfg):
+    nsc = 12 * cell.nof_prb
+    re = np.zeros(14 * nsc, np.int32)
+    n = lib().lteo_pdsch_re_list(C.byref(cell), C.byref(cfg), _p(re))
+    return re[:n].copy()
+
+
+def fft_twiddles(n):
+    tw = np.zeros(n // 2, np.complex64)
+    lib().lteo_fft_twiddles(n, _p(tw))
+    return tw
+
+
+def rm_sequence(K, F, rv):
+    seq = np.zeros(3 * (K + 4), np.int32)
+    n = lib().lteo_rm_sequence(K, F, rv, _p(seq))
+    return seq[:n].copy()
+
+
+# ---- TX ----------------------------------------------------------------------------------
+def turbo_encode(c):
+    c = np.ascontiguousarray(c, np.uint8)
+    d = np.zeros(3 * (len(c) + 4), np.uint8)
+    lib().lteo_turbo_encode(_p(c), len(c), _p(d))
+    return d
+
+
+def pdsch_tx_grid(cell, cfg, tb_bytes):
+    nsc = 12 * cell.nof_prb
+    grid = np.zeros((cell.nof_ports, 14, nsc), np.complex128)
+    tb = np.ascontiguousarray(tb_bytes, np.uint8)
+    rc = lib().lteo_pdsch_tx_grid(C.byref(cell), C.byref(cfg), _p(tb), _p(grid))
+    if rc:
+        raise RuntimeError("pdsch_tx_grid rc=%d" % rc)
+    return grid
+
+
+def ofdm_tx(nof_prb, grid):
+    n = lib().lteo_symbol_sz(nof_prb)
+    grid = np.ascontiguousarray(grid, np.complex128)
+    iq = np.zeros(15 * n, np.complex128)
+    lib().lteo_ofdm_tx(nof_prb, _p(grid), _p(iq))
+    return iq
+
+
+# ---- RX ----------------------------------------------------------------------------------
+def fft(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().lteo_fft(_p(x), _p(out), len(x))
+    return out
+
+
+def ofdm_rx(nof_prb, iq):
+    iq = np.ascontiguousarray(iq, np.complex64)
+    sf = np.zeros(14 * 12 * nof_prb, np.complex64)
+    lib().lteo_ofdm_rx(nof_prb, _p(iq), _p(sf))
+    return sf
+
+
+def chest(cell, sf_idx, sf):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.zeros((cell.nof_ports, 14 * 12 * cell.nof_prb), np.complex64)
+    meas = np.zeros(5, np.float32)
+    lib().lteo_chest(C.byref(cell), sf_idx, _p(sf), _p(ce), _p(meas))
+    return ce, meas
+
+
+def equalize(cell, cfg, sf, ce, n0):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    d = np.zeros(14 * 12 * cell.nof_prb, np.complex64)
+    n = C.c_int()
+    lib().lteo_equalize(C.byref(cell), C.byref(cfg), _p(sf), _p(ce), C.c_float(n0), _p(d), C.byref(n))
+    return d[:n.value].copy()
+
+
+def demod(d, qm):
+    d = np.ascontiguousarray(d, np.complex64)
+    llr = np.zeros(len(d) * qm, np.int16)
+    lib().lteo_demod(_p(d), len(d), qm, _p(llr))
+    return llr
+
+
+def descramble(llr, c_init):
+    llr = np.ascontiguousarray(llr, np.int16).copy()
+    lib().lteo_descramble(_p(llr), len(llr), C.c_uint32(c_init))
+    return llr
+
+
+def rm_rx(e, K, F, rv, w=None):
+    e = np.ascontiguousarray(e, np.int16)
+    if w is None:
+        w = np.zeros(3 * K + 12, np.int16)
+    lib().lteo_rm_rx(_p(e), len(e), K, F, rv, _p(w))
+    return w
+
+
+def tdec(inp, K, max_iter=4, crc_type=0, window=0):
+    inp = np.ascontiguousarray(inp, np.int16)
+    assert len(inp) >= 3 * K + 12
+    bits = np.zeros(K, np.uint8)
+    ok = C.c_int()
+    la = np.zeros(K, np.int16)
+    it = lib().lteo_tdec_dbg(_p(inp), K, max_iter, crc_type, _p(bits), C.byref(ok), _p(la), window)
+    return bits, it, ok.value, la
+
+
+def new_softbuf(ncb=13):
+    return np.zeros((ncb, SB_STRIDE), np.int16)
+
+
+def pdsch_decode(cell, cfg, sf, ce, noise_est, max_iter=4, softbuf=None, want=False):
+    s = cbsegm(cfg.tbs)
+    if softbuf is None:
+        softbuf = new_softbuf(s.C)
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    payload = np.zeros((cfg.tbs + 7) // 8, np.uint8)
+    nsc = 12 * cell.nof_prb
+    d = np.zeros(14 * nsc, np.complex64)
+    e = np.zeros(14 * nsc * cfg.qm, np.int16)
+    iters = np.zeros(s.C, np.int32)
+    crc = np.zeros(s.C, np.int32)
+    rc = lib().lteo_pdsch_decode(C.byref(cell), C.byref(cfg), _p(sf), _p(ce), C.c_float(noise_est), max_iter,
+                                 _p(softbuf), _p(payload), _p(d), _p(e), _p(iters), _p(crc))
+    if want:
+        return rc, payload, dict(d=d, e=e, iters=iters, crc=crc, softbuf=softbuf)
+    return rc, payload
+
+
+def ue_dl_decode(cell, cfg, iq, noise_est=0.01, noise_mode=0, max_iter=4, softbuf=None):
+    s = cbsegm(cfg.tbs)
+    if softbuf is None:
+        softbuf = new_softbuf(s.C)
+    iq = np.ascontiguousarray(iq, np.complex64)
+    payload = np.zeros((cfg.tbs + 7) // 8, np.uint8)
+    meas = np.zeros(5, np.float32)
+    avg = C.c_int()
+    rc = lib().lteo_ue_dl_decode(C.byref(cell), C.byref(cfg), _p(iq), C.c_float(noise_est), noise_mode, max_iter,
+                                 _p(softbuf), _p(payload), _p(meas), C.byref(avg))
+    return rc, payload, meas, avg.value
+
+
+# ---- synthetic subframes (SURVEY.md 8d seeds) ----------------------------------------------
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None):
+    """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
+
+    Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
+    optional [ports][ntaps] complex array of channel taps (sample-spaced, shorter than the CP)."""
+    rng = np.random.default_rng(seed)
+    tb = rng.integers(0, 256, (cfg.tbs + 7) // 8, dtype=np.uint8)
+    grid = pdsch_tx_grid(cell, cfg, tb)
+    n = lib().lteo_symbol_sz(cell.nof_prb)
+    nsc = 12 * cell.nof_prb
+    rx = np.zeros((14, nsc), np.complex128)
+    k = np.arange(nsc)
+    bins = np.where(k < nsc // 2, n - nsc // 2 + k, k - nsc // 2 + 1)
+    for p in range(cell.nof_ports):
+        if taps is None:
+            h = np.ones(nsc, np.complex128)
+        else:
+            t = np.asarray(taps[p], np.complex128)
+            h = (t[None, :] * np.exp(-2j * np.pi * np.outer(bins, np.arange(len(t))) / n)).sum(1)
+        rx += grid[p] * h[None, :]
+    iq = ofdm_tx(cell.nof_prb, rx)
+    # unitary (I)FFT on both sides: a unit-power RE stays unit power and the per-RE noise variance
+    # equals the per-sample one, so snr_db is Es/N0 per resource element
+    sigma2 = 10.0 ** (-snr_db / 10.0)
+    nrng = np.random.default_rng(seed + 5_000_000)
+    noise = (nrng.standard_normal(len(iq)) + 1j * nrng.standard_normal(len(iq))) * np.sqrt(sigma2 / 2)
+    return tb, (iq + noise).astype(np.complex64), sigma2
+
+
+def gen_turbo_llrs(K, seed, ebn0_db=None, scale=64.0):
+    """cfg4 input: K random info bits -> turbo encoder -> LLR int16 [3K+12] (srsLTE triples order)."""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, 2, K, dtype=np.uint8)
+    d = turbo_encode(c).astype(np.float64)
+    s = 2.0 * d - 1.0                                 # bit 1 -> +1 (positive LLR <=> bit 1)
+    if ebn0_db is not None:
+        sigma2 = 1.0 / (2.0 * (1.0 / 3.0) * 10.0 ** (ebn0_db / 10.0))
+        nrng = np.random.default_rng(seed + 5_000_000)
+        s = s + nrng.standard_normal(len(s)) * np.sqrt(sigma2)
+    llr = np.clip(np.trunc(scale * s), -2048, 2047).astype(np.int16)
+    return c, llr
