@@ -1,0 +1,203 @@
+/*
+ * srslte_compat.h -- the slice of the srsLTE C API that srsUE's downlink path uses, served by
+ * libsrsue_gpu.  A maintainer builds ue/src/phy/phch_worker.cc, ue/src/mac/dl_harq.cc and
+ * ue/src/mac/proc_ra.cc against this header instead of "srslte/srslte.h" for the symbols below
+ * (INTEGRATION.md shows the CMake change); names, argument meaning and return conventions are
+ * those of the call sites cited next to each declaration (paths under /root/reference).
+ *
+ * Struct layouts are NOT binary compatible with a stock libsrslte build: callers are recompiled
+ * against this header.  Fields the reference dereferences directly keep their names
+ * (ue_dl.pdsch.dl_sch, ue_dl.sf_symbols, ue_dl.ce, ue_dl.chest, ue_dl.pdsch_cfg.grant.mcs.{mod,tbs,idx},
+ * ue_dl.last_n_cce, ue_dl.last_location.{ncce,L}: phch_worker.cc:88,260,320,338,347-348,356-357,446).
+ */
+#ifndef SRSUE_GPU_SRSLTE_COMPAT_H
+#define SRSUE_GPU_SRSLTE_COMPAT_H
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "srsue_gpu/srsue_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef SRSLTE_API
+#define SRSLTE_API __attribute__((visibility("default")))
+#endif
+
+#define SRSLTE_SUCCESS 0
+#define SRSLTE_ERROR (-1)
+#define SRSLTE_ERROR_INVALID_INPUTS (-2)
+
+#define SRSLTE_MAX_PORTS 4
+#define SRSLTE_MAX_PRB 110
+#define SRSLTE_MAX_CODEBLOCKS 32
+#define SRSLTE_TCOD_MAX_LEN_CB 6144
+#define SRSLTE_TCOD_TOTALTAIL 12
+#define SRSLTE_SIRNTI 0xFFFF
+
+/* cf_t: srsLTE uses C99 `_Complex float`; {re, im} pairs have the same layout */
+#ifdef SRSUE_GPU_PLAIN_CF
+typedef srsue_gpu_cf_t cf_t;
+#else
+typedef _Complex float cf_t;
+#endif
+
+typedef enum { SRSLTE_CP_NORM = 0, SRSLTE_CP_EXT } srslte_cp_t;
+typedef enum { SRSLTE_PHICH_NORM = 0, SRSLTE_PHICH_EXT } srslte_phich_length_t;
+typedef enum { SRSLTE_PHICH_R_1_6 = 0, SRSLTE_PHICH_R_1_2, SRSLTE_PHICH_R_1, SRSLTE_PHICH_R_2 } srslte_phich_resources_t;
+typedef enum { SRSLTE_MOD_BPSK = 0, SRSLTE_MOD_QPSK, SRSLTE_MOD_16QAM, SRSLTE_MOD_64QAM } srslte_mod_t;
+typedef enum { SRSLTE_RNTI_USER = 0, SRSLTE_RNTI_SI, SRSLTE_RNTI_RAR, SRSLTE_RNTI_TEMP, SRSLTE_RNTI_SPS,
+               SRSLTE_RNTI_PCH, SRSLTE_RNTI_NOF_TYPES } srslte_rnti_type_t;
+
+typedef struct SRSLTE_API {
+  uint32_t nof_prb;
+  uint32_t nof_ports;
+  uint32_t bw_idx;
+  uint32_t id;
+  srslte_cp_t cp;
+  srslte_phich_length_t phich_length;
+  srslte_phich_resources_t phich_resources;
+} srslte_cell_t;
+
+typedef struct SRSLTE_API { srslte_mod_t mod; int tbs; uint32_t idx; } srslte_ra_mcs_t;
+
+typedef struct SRSLTE_API {
+  bool prb_idx[2][SRSLTE_MAX_PRB];
+  uint32_t nof_prb;
+  uint32_t Qm;
+  srslte_ra_mcs_t mcs;
+} srslte_ra_dl_grant_t;
+
+/* uplink grant: only present so that srslte_phy_grant_t keeps its shape (mac_interface.h:59) */
+typedef struct SRSLTE_API {
+  uint32_t n_prb[2], n_prb_tilde[2], L_prb, freq_hopping, M_sc, M_sc_init, Qm;
+  srslte_ra_mcs_t mcs;
+  uint32_t ncs_dmrs;
+} srslte_ra_ul_grant_t;
+
+typedef union { srslte_ra_dl_grant_t dl; srslte_ra_ul_grant_t ul; } srslte_phy_grant_t;
+
+typedef struct SRSLTE_API { uint32_t F, C, K1, K2, C1, C2, tbs; } srslte_cbsegm_t;
+typedef struct SRSLTE_API { uint32_t lstart, nof_symb, nof_bits, nof_re; } srslte_ra_nbits_t;
+
+typedef struct SRSLTE_API {
+  srslte_cbsegm_t cb_segm;
+  srslte_ra_dl_grant_t grant;
+  srslte_ra_nbits_t nbits;
+  uint32_t rv;
+  uint32_t sf_idx;
+} srslte_pdsch_cfg_t;
+
+/* HARQ soft buffer, owned by MAC (ue/hdr/mac/dl_harq.h:88).  buffer_f keeps srsLTE's shape (one
+ * int16 array of 3*6144+12 per code block, decoder-input order); the authoritative copy between a
+ * reset and the next reset lives on the device (gpu_shadow) and is only mirrored into buffer_f by
+ * srsue_gpu_softbuffer_rx_sync_host(). */
+typedef struct SRSLTE_API {
+  uint32_t max_cb;
+  int16_t **buffer_f;
+  void *gpu_shadow;
+} srslte_softbuffer_rx_t;
+
+typedef struct SRSLTE_API { uint32_t max_iterations; uint32_t nof_iterations; } srslte_sch_t;
+
+typedef struct SRSLTE_API {
+  srslte_cell_t cell;
+  uint16_t rnti;
+  srslte_sch_t dl_sch;
+  void *gpu;                 /* back pointer to the owning ue_dl device state */
+} srslte_pdsch_t;
+
+typedef struct SRSLTE_API {
+  srslte_cell_t cell;
+  float noise_estimate, rsrp, rssi, rsrq;
+  void *gpu;
+} srslte_chest_dl_t;
+
+typedef struct SRSLTE_API { int unused; } srslte_pdcch_t;     /* PDCCH decode: next row */
+typedef struct SRSLTE_API { uint32_t L; uint32_t ncce; } srslte_dci_location_t;
+
+typedef struct SRSLTE_API {
+  srslte_pdcch_t pdcch;
+  srslte_pdsch_t pdsch;
+  srslte_chest_dl_t chest;
+  srslte_pdsch_cfg_t pdsch_cfg;
+  srslte_softbuffer_rx_t softbuffer;      /* used by srslte_ue_dl_decode[_rnti] only */
+  srslte_cell_t cell;
+  cf_t *sf_symbols;                       /* host mirror, 14 * 12 * nof_prb */
+  cf_t *ce[SRSLTE_MAX_PORTS];             /* host mirrors, one per configured port */
+  uint16_t current_rnti;
+  srslte_dci_location_t last_location;
+  uint32_t last_n_cce;
+  uint64_t pkt_errors, pkts_total, nof_detected;
+  void *gpu;                              /* opaque device state */
+} srslte_ue_dl_t;
+
+typedef struct SRSLTE_API {
+  uint32_t max_long_cb;
+  uint32_t n_iter;                        /* iterations requested through srslte_tdec_iteration */
+  void *gpu;
+} srslte_tdec_t;
+
+/* ---- helpers the DL callers use ------------------------------------------------------------------ */
+SRSLTE_API int srslte_symbol_sz(uint32_t nof_prb);                       /* ue/src/phy/prach.cc:77 */
+#define SRSLTE_SF_LEN(symbol_sz) ((symbol_sz) * 15)
+#define SRSLTE_SF_LEN_PRB(nof_prb) (SRSLTE_SF_LEN(srslte_symbol_sz(nof_prb)))   /* phch_worker.cc:69 */
+SRSLTE_API void *srslte_vec_malloc(uint32_t size);                      /* phch_worker.cc:69 (pinned here) */
+SRSLTE_API void srslte_vec_free(void *p);
+
+/* ---- UE DL object (phch_worker.cc:74,104,127,254,337) -------------------------------------------- */
+SRSLTE_API int srslte_ue_dl_init(srslte_ue_dl_t *q, srslte_cell_t cell);
+SRSLTE_API void srslte_ue_dl_free(srslte_ue_dl_t *q);
+SRSLTE_API void srslte_ue_dl_set_rnti(srslte_ue_dl_t *q, uint16_t rnti);
+SRSLTE_API int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t *q, cf_t *input, uint32_t sf_idx, uint32_t *cfi);
+SRSLTE_API int srslte_ue_dl_cfg_grant(srslte_ue_dl_t *q, srslte_ra_dl_grant_t *grant, uint32_t cfi, uint32_t sf_idx,
+                                      uint32_t rvidx);
+/* wrappers the north star names; the DCI search is a "next" row, so the grant to use is the one last
+ * installed with srsue_gpu_ue_dl_set_grant().  Return decoded bits (tbs) / 0 (no grant) / < 0. */
+SRSLTE_API int srslte_ue_dl_decode(srslte_ue_dl_t *q, cf_t *input, uint8_t *data, uint32_t tti);
+SRSLTE_API int srslte_ue_dl_decode_rnti(srslte_ue_dl_t *q, cf_t *input, uint8_t *data, uint32_t tti, uint16_t rnti);
+
+/* ---- PDSCH / SCH (phch_worker.cc:88,347-348,360,848) -------------------------------------------- */
+SRSLTE_API int srslte_pdsch_decode_rnti(srslte_pdsch_t *q, srslte_pdsch_cfg_t *cfg, srslte_softbuffer_rx_t *softbuffer,
+                                        cf_t *sf_symbols, cf_t *ce[SRSLTE_MAX_PORTS], float noise_estimate, uint16_t rnti,
+                                        uint8_t *data);
+SRSLTE_API void srslte_sch_set_max_noi(srslte_sch_t *q, uint32_t max_iterations);
+SRSLTE_API uint32_t srslte_pdsch_last_noi(srslte_pdsch_t *q);
+
+/* ---- channel-estimate getters (phch_worker.cc:359,799,821-823,842,847) --------------------------- */
+SRSLTE_API float srslte_chest_dl_get_noise_estimate(srslte_chest_dl_t *q);
+SRSLTE_API float srslte_chest_dl_get_snr(srslte_chest_dl_t *q);
+SRSLTE_API float srslte_chest_dl_get_rssi(srslte_chest_dl_t *q);
+SRSLTE_API float srslte_chest_dl_get_rsrq(srslte_chest_dl_t *q);
+SRSLTE_API float srslte_chest_dl_get_rsrp(srslte_chest_dl_t *q);
+
+/* ---- soft buffer (dl_harq.cc:169,174,232; proc_ra.cc:60,254; ue_itf_test_sib1.cc:121,136) -------- */
+SRSLTE_API int srslte_softbuffer_rx_init(srslte_softbuffer_rx_t *q, uint32_t nof_prb);
+SRSLTE_API void srslte_softbuffer_rx_free(srslte_softbuffer_rx_t *q);
+SRSLTE_API void srslte_softbuffer_rx_reset(srslte_softbuffer_rx_t *q);
+SRSLTE_API void srslte_softbuffer_rx_reset_tbs(srslte_softbuffer_rx_t *q, uint32_t tbs);
+SRSLTE_API void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t *q, uint32_t nof_cb);
+
+/* ---- turbo decoder object (BASELINE config 4) ----------------------------------------------------- */
+SRSLTE_API int srslte_tdec_init(srslte_tdec_t *h, uint32_t max_long_cb);
+SRSLTE_API void srslte_tdec_free(srslte_tdec_t *h);
+SRSLTE_API int srslte_tdec_reset(srslte_tdec_t *h, uint32_t long_cb);
+SRSLTE_API void srslte_tdec_iteration(srslte_tdec_t *h, int16_t *input, uint32_t long_cb);
+SRSLTE_API void srslte_tdec_decision(srslte_tdec_t *h, uint8_t *output, uint32_t long_cb);       /* one bit per byte */
+SRSLTE_API void srslte_tdec_decision_byte(srslte_tdec_t *h, uint8_t *output, uint32_t long_cb);  /* packed, MSB first */
+SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *output, uint32_t nof_iterations,
+                                   uint32_t long_cb);
+
+/* ---- extensions (not in srsLTE) ------------------------------------------------------------------- */
+/* CFI / grant sources until PCFICH + PDCCH decode land on the device */
+SRSLTE_API void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t *q, uint32_t cfi);
+SRSLTE_API int srsue_gpu_ue_dl_set_grant(srslte_ue_dl_t *q, const srslte_ra_dl_grant_t *grant, uint32_t cfi, uint32_t rvidx);
+/* copy the device-resident soft buffer into buffer_f (srsLTE decoder-input order) for `tbs` bits */
+SRSLTE_API int srsue_gpu_softbuffer_rx_sync_host(srslte_softbuffer_rx_t *q, uint32_t tbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

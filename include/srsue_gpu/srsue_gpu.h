@@ -1,0 +1,136 @@
+/*
+ * srsue_gpu.h -- C ABI of libsrsue_gpu: the batched, device-resident form of srsUE's downlink PDSCH
+ * receive chain for NVIDIA B200 (sm_100a).  Plain pointers and sizes only; every function returns 0
+ * (SRSLTE_SUCCESS) or a negative error (SRSLTE_ERROR = -1, or -2 for invalid arguments) like the
+ * srsLTE calls it stands in for.  The per-subframe srsLTE-shaped entry points that phch_worker calls
+ * (include/srsue_gpu/srslte_compat.h) are thin wrappers over this API with a batch of one.
+ *
+ * What each group replaces in the reference (kevinmel2000/srsUE, paths under /root/reference):
+ *   srsue_gpu_ofdm_rx + srsue_gpu_chest   srslte_ue_dl_decode_fft_estimate   ue/src/phy/phch_worker.cc:254
+ *   srsue_gpu_pdsch_plan_create           srslte_ue_dl_init / srslte_ue_dl_cfg_grant   phch_worker.cc:74,337
+ *   srsue_gpu_pdsch_llr + _pdsch_turbo    srslte_pdsch_decode_rnti           phch_worker.cc:347-348
+ *   srsue_gpu_pdsch_decode_batch[_host]   srslte_ue_dl_decode (the wrapper the north star names) and the
+ *                                         thread_pool hand-off it replaces   ue/src/common/thread_pool.cc:72-82
+ *   srsue_gpu_tdec_*                      srslte_tdec_run_all & co (turbo sweep, BASELINE config 4)
+ *   tb_status / meas read-back            srslte_pdsch_last_noi, srslte_chest_dl_get_*  phch_worker.cc:359-360,799-848
+ *
+ * There is NO CPU fallback: every entry point fails (negative return, message in
+ * srsue_gpu_last_error) when no CUDA device is usable.
+ */
+#ifndef SRSUE_GPU_H
+#define SRSUE_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSUE_GPU_SUCCESS 0
+#define SRSUE_GPU_ERROR (-1)
+#define SRSUE_GPU_ERROR_INVALID_INPUTS (-2)
+
+typedef struct srsue_gpu_ctx srsue_gpu_ctx_t;           /* one per process and device */
+typedef struct srsue_gpu_pdsch_plan srsue_gpu_pdsch_plan_t; /* one per (cell, grant shape) */
+
+typedef struct { float re, im; } srsue_gpu_cf_t;        /* layout of srsLTE's cf_t (float _Complex) */
+
+typedef struct {
+  int nof_prb;      /* 6, 15, 25, 50, 100 (75 = 1536-point FFT: not supported yet) */
+  int nof_ports;    /* 1 or 2 */
+  int cell_id;      /* physical cell id, normal cyclic prefix */
+} srsue_gpu_cell_t;
+
+typedef struct {
+  int sf_idx;       /* subframe 0..9 (tti % 10) */
+  int cfi;          /* control format indicator 1..3 */
+  int rnti;
+  int qm;           /* bits per symbol: 2, 4, 6 */
+  int tbs;          /* transport block size in bits */
+  int rv;           /* redundancy version 0..3 */
+  int tm;           /* 1: single antenna port, 2: transmit diversity */
+  int nof_prb_alloc;
+  uint8_t prb_mask[110];  /* 1 = PRB allocated (same PRBs in both slots) */
+} srsue_gpu_pdsch_cfg_t;
+
+typedef struct {
+  int nfft, nsc, sf_len;          /* FFT size, 12*nof_prb, samples per subframe */
+  int nof_re, G;                  /* PDSCH resource elements and coded bits per subframe */
+  int C, Kp, Km, Cp, Cm, F;       /* code-block segmentation */
+  int sb_cb_stride;               /* int16 elements per code block in the device soft buffer */
+  int sb_sf_stride;               /* int16 elements per subframe (C * sb_cb_stride) */
+  int payload_stride;             /* bytes per subframe in payload arrays */
+  int max_batch;
+} srsue_gpu_plan_info_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int srsue_gpu_ctx_create(srsue_gpu_ctx_t **ctx, int device);
+void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t *ctx);
+const char *srsue_gpu_last_error(void);
+int srsue_gpu_version(void);
+
+/* ---- turbo decoder (device pointers; `stream` is a cudaStream_t passed as void*) ------------ */
+/* geometry of the windowed decoder for code-block size K: window length, windows, tcb elements */
+int srsue_gpu_tdec_geometry(int K, int *W, int *P, int *cb_elems);
+/* srsLTE decoder-input order [n_cb][3K+12] int16 -> device layout [n_cb][cb_elems], clamped to +-511 */
+int srsue_gpu_tdec_import(srsue_gpu_ctx_t *ctx, const int16_t *d_triples, int n_cb, int K, int16_t *d_tcb, void *stream);
+int srsue_gpu_tdec_export(srsue_gpu_ctx_t *ctx, const int16_t *d_tcb, int n_cb, int K, int16_t *d_triples, void *stream);
+/* decode n_cb code blocks of size K from the device layout.  crc_type: 0 none (run max_iter
+ * iterations), 1 CRC24A, 2 CRC24B (stop as soon as the remainder is zero).  d_bits: [n_cb][K/8]
+ * bytes, MSB first.  d_status[cb] = iterations | crc_ok << 8. */
+int srsue_gpu_tdec_decode(srsue_gpu_ctx_t *ctx, const int16_t *d_tcb, int n_cb, int K, int max_iter, int crc_type,
+                          uint8_t *d_bits, int32_t *d_status, void *stream);
+/* import + decode in one call (what srslte_tdec_run_all does for one block) */
+int srsue_gpu_tdec_run_all(srsue_gpu_ctx_t *ctx, const int16_t *d_triples, int n_cb, int K, int max_iter, int crc_type,
+                           uint8_t *d_bits, int32_t *d_status, void *stream);
+/* host-pointer convenience of the same (copies in and out, synchronises) */
+int srsue_gpu_tdec_run_all_host(srsue_gpu_ctx_t *ctx, const int16_t *h_triples, int n_cb, int K, int max_iter,
+                                int crc_type, uint8_t *h_bits, int32_t *h_status);
+/* launch statistics of the most recent decode on this context */
+int srsue_gpu_tdec_last_launch(srsue_gpu_ctx_t *ctx, int *grid, int *block, int *smem_bytes, int *cb_per_cta);
+
+/* ---- PDSCH plan ------------------------------------------------------------------------------ */
+int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t *ctx, const srsue_gpu_cell_t *cell, const srsue_gpu_pdsch_cfg_t *cfg,
+                                int max_batch, srsue_gpu_pdsch_plan_t **plan);
+void srsue_gpu_pdsch_plan_destroy(srsue_gpu_pdsch_plan_t *plan);
+int srsue_gpu_pdsch_plan_info(const srsue_gpu_pdsch_plan_t *plan, srsue_gpu_plan_info_t *info);
+
+/* ---- stages (device pointers) ---------------------------------------------------------------- */
+/* d_iq [n_sf][sf_len] -> d_sf_symbols [n_sf][14*nsc] */
+int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_iq, srsue_gpu_cf_t *d_sf_symbols,
+                      void *stream);
+/* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
+int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
+                    float *d_meas, void *stream);
+/* equalise + demap + descramble + rate-dematch into d_softbuf [n_sf][sb_sf_stride].  noise_mode 0: use
+ * noise_est (srsUE passes 0.01), 1: use d_meas[.][0].  accumulate 0: new transmission, 1: HARQ combine.
+ * d_dbg_d [n_sf][nof_re] / d_dbg_e [n_sf][G] optional taps of the equalised symbols / descrambled LLRs. */
+int srsue_gpu_pdsch_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                        const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int accumulate,
+                        int16_t *d_softbuf, srsue_gpu_cf_t *d_dbg_d, int16_t *d_dbg_e, void *stream);
+/* turbo decode + CRC + transport-block assembly.  d_payload [n_sf][payload_stride] bytes MSB first;
+ * d_tb_status [n_sf][4] = {crc_ok, sum of iterations, floor(avg iterations), C};
+ * d_cb_status optional [n_sf][C]. */
+int srsue_gpu_pdsch_turbo(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_softbuf, int max_iter,
+                          uint8_t *d_payload, int32_t *d_tb_status, int32_t *d_cb_status, void *stream);
+
+/* ---- whole chain ------------------------------------------------------------------------------ */
+/* d_softbuf may be NULL (plan-owned scratch, new transmission).  d_meas may be NULL. */
+int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_iq, float noise_est,
+                                 int noise_mode, int max_iter, int accumulate, int16_t *d_softbuf, uint8_t *d_payload,
+                                 int32_t *d_tb_status, float *d_meas, void *stream);
+/* same with HOST buffers (pinned or pageable): H2D of the IQ, the chain, D2H of payload/status/meas,
+ * synchronised on return.  This is the call the offline driver and the e2e benchmark make. */
+int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *h_iq, float noise_est,
+                                      int noise_mode, int max_iter, uint8_t *h_payload, int32_t *h_tb_status,
+                                      float *h_meas);
+/* number of kernels the most recent chain call launched (for the benchmark's gpu_launches) */
+int srsue_gpu_last_launch_count(srsue_gpu_ctx_t *ctx);
+
+/* ---- pinned host memory helpers (so callers need not link the CUDA runtime) ------------------- */
+void *srsue_gpu_host_alloc(uint64_t bytes);
+void srsue_gpu_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

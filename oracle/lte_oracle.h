@@ -36,8 +36,9 @@ typedef struct { double re, im; } lteo_cd_t;
 #define LTEO_TD_INF   10000   /* finite "minus infinity" for known trellis states   */
 #define LTEO_TD_NORM  4       /* state metrics re-normalised when k % 4 == 0        */
 #define LTEO_MAX_K    6144
-#define LTEO_LLR_MAX  32767   /* symmetric int16 saturation of LLRs / soft buffer   */
-#define LTEO_FILLER_LLR (-32767)
+#define LTEO_LLR_MAX  32767   /* symmetric int16 saturation of demapper LLRs           */
+#define LTEO_SB_MAX   LTEO_TD_C /* the soft buffer IS the decoder input: it saturates at +-C */
+#define LTEO_FILLER_LLR (-LTEO_TD_C)
 
 typedef struct {
   int nof_prb;      /* 6,15,25,50,75,100 */

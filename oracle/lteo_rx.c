@@ -264,8 +264,8 @@ void lteo_descramble(int16_t *llr, int n, uint32_t c_init) {
 
 static inline int16_t sat_add(int a, int b) {
   int s = a + b;
-  if (s > LTEO_LLR_MAX) s = LTEO_LLR_MAX;
-  if (s < -LTEO_LLR_MAX) s = -LTEO_LLR_MAX;
+  if (s > LTEO_SB_MAX) s = LTEO_SB_MAX;
+  if (s < -LTEO_SB_MAX) s = -LTEO_SB_MAX;
   return (int16_t)s;
 }
 

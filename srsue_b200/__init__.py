@@ -1,0 +1,175 @@
+"""srsue_b200 -- Python loader for libsrsue_gpu (the product is the C-ABI shared library built from
+srsue_b200/csrc; see include/srsue_gpu/*.h).  This module only loads the library with ctypes and
+offers thin helpers that pass torch CUDA tensors' device pointers through the C ABI, for the tests,
+the benchmark and the smoke check.  There is no Python or CPU fallback: if the library is missing
+or no GPU is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrsue_gpu.so")
+
+
+class Cell(C.Structure):
+    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int)]
+
+
+class PdschCfg(C.Structure):
+    _fields_ = [("sf_idx", C.c_int), ("cfi", C.c_int), ("rnti", C.c_int), ("qm", C.c_int),
+                ("tbs", C.c_int), ("rv", C.c_int), ("tm", C.c_int), ("nof_prb_alloc", C.c_int),
+                ("prb_mask", C.c_uint8 * 110)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nfft", "nsc", "sf_len", "nof_re", "G", "C", "Kp", "Km", "Cp", "Cm", "F",
+                                       "sb_cb_stride", "sb_sf_stride", "payload_stride", "max_batch")]
+
+
+class GpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libsrsue_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    import subprocess
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    """Load libsrsue_gpu.so (raises if it has not been built -- there is no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpuError("libsrsue_gpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.srsue_gpu_last_error.restype = C.c_char_p
+        L.srsue_gpu_host_alloc.restype = C.c_void_p
+        L.srsue_gpu_host_alloc.argtypes = [C.c_uint64]
+        L.srsue_gpu_host_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GpuError("%s failed (%d): %s" % (what, rc, lib().srsue_gpu_last_error().decode()))
+
+
+def _ptr(t):
+    """device (or host) pointer of a torch tensor / numpy array / None as c_void_p"""
+    if t is None:
+        return C.c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().srsue_gpu_ctx_create(C.byref(self.h), device), "srsue_gpu_ctx_create")
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().srsue_gpu_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # ---- turbo ----
+    @staticmethod
+    def tdec_geometry(K):
+        W, P, n = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().srsue_gpu_tdec_geometry(K, C.byref(W), C.byref(P), C.byref(n)), "srsue_gpu_tdec_geometry")
+        return W.value, P.value, n.value
+
+    def tdec_import(self, d_triples, n_cb, K, d_tcb):
+        _check(lib().srsue_gpu_tdec_import(self.h, _ptr(d_triples), n_cb, K, _ptr(d_tcb), _stream()), "tdec_import")
+
+    def tdec_export(self, d_tcb, n_cb, K, d_triples):
+        _check(lib().srsue_gpu_tdec_export(self.h, _ptr(d_tcb), n_cb, K, _ptr(d_triples), _stream()), "tdec_export")
+
+    def tdec_decode(self, d_tcb, n_cb, K, max_iter, crc_type, d_bits, d_status):
+        _check(lib().srsue_gpu_tdec_decode(self.h, _ptr(d_tcb), n_cb, K, max_iter, crc_type, _ptr(d_bits), _ptr(d_status),
+                                           _stream()), "tdec_decode")
+
+    def tdec_run_all(self, d_triples, n_cb, K, max_iter, crc_type, d_bits, d_status):
+        _check(lib().srsue_gpu_tdec_run_all(self.h, _ptr(d_triples), n_cb, K, max_iter, crc_type, _ptr(d_bits),
+                                            _ptr(d_status), _stream()), "tdec_run_all")
+
+    def tdec_run_all_host(self, h_triples, n_cb, K, max_iter, crc_type, h_bits, h_status):
+        _check(lib().srsue_gpu_tdec_run_all_host(self.h, _ptr(h_triples), n_cb, K, max_iter, crc_type, _ptr(h_bits),
+                                                 _ptr(h_status)), "tdec_run_all_host")
+
+    def tdec_last_launch(self):
+        g, b, s, n = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lib().srsue_gpu_tdec_last_launch(self.h, C.byref(g), C.byref(b), C.byref(s), C.byref(n))
+        return dict(grid=g.value, block=b.value, smem=s.value, cb_per_cta=n.value)
+
+    def last_launch_count(self):
+        return lib().srsue_gpu_last_launch_count(self.h)
+
+
+class PdschPlan:
+    def __init__(self, ctx, cell, cfg, max_batch):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _check(lib().srsue_gpu_pdsch_plan_create(ctx.h, C.byref(cell), C.byref(cfg), max_batch, C.byref(self.h)),
+               "srsue_gpu_pdsch_plan_create")
+        self.info = PlanInfo()
+        lib().srsue_gpu_pdsch_plan_info(self.h, C.byref(self.info))
+
+    def close(self):
+        if self.h:
+            lib().srsue_gpu_pdsch_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def ofdm_rx(self, n_sf, d_iq, d_sf):
+        _check(lib().srsue_gpu_ofdm_rx(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _stream()), "ofdm_rx")
+
+    def chest(self, n_sf, d_sf, d_ce, d_meas):
+        _check(lib().srsue_gpu_chest(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), _stream()), "chest")
+
+    def pdsch_llr(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, accumulate, d_softbuf, d_dbg_d=None, d_dbg_e=None):
+        _check(lib().srsue_gpu_pdsch_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
+                                         accumulate, _ptr(d_softbuf), _ptr(d_dbg_d), _ptr(d_dbg_e), _stream()), "pdsch_llr")
+
+    def pdsch_turbo(self, n_sf, d_softbuf, max_iter, d_payload, d_tb_status, d_cb_status=None):
+        _check(lib().srsue_gpu_pdsch_turbo(self.h, n_sf, _ptr(d_softbuf), max_iter, _ptr(d_payload), _ptr(d_tb_status),
+                                           _ptr(d_cb_status), _stream()), "pdsch_turbo")
+
+    def decode_batch(self, n_sf, d_iq, noise_est, noise_mode, max_iter, d_payload, d_tb_status, d_softbuf=None,
+                     accumulate=0, d_meas=None):
+        _check(lib().srsue_gpu_pdsch_decode_batch(self.h, n_sf, _ptr(d_iq), C.c_float(noise_est), noise_mode, max_iter,
+                                                  accumulate, _ptr(d_softbuf), _ptr(d_payload), _ptr(d_tb_status),
+                                                  _ptr(d_meas), _stream()), "pdsch_decode_batch")
+
+    def decode_batch_host(self, n_sf, h_iq, noise_est, noise_mode, max_iter, h_payload, h_tb_status, h_meas=None):
+        _check(lib().srsue_gpu_pdsch_decode_batch_host(self.h, n_sf, _ptr(h_iq), C.c_float(noise_est), noise_mode, max_iter,
+                                                       _ptr(h_payload), _ptr(h_tb_status), _ptr(h_meas)),
+               "pdsch_decode_batch_host")
+
+
+def make_cell(nof_prb, nof_ports=1, cell_id=1):
+    return Cell(nof_prb, nof_ports, cell_id)
+
+
+def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None):
+    cfg = PdschCfg()
+    cfg.sf_idx, cfg.cfi, cfg.rnti, cfg.qm, cfg.tbs, cfg.rv, cfg.tm = sf_idx, cfi, rnti, qm, tbs, rv, tm
+    n = 0
+    for p in (range(cell.nof_prb) if prbs is None else prbs):
+        cfg.prb_mask[p] = 1
+        n += 1
+    cfg.nof_prb_alloc = n
+    return cfg

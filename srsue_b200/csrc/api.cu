@@ -1,0 +1,607 @@
+// api.cu -- host side of libsrsue_gpu: context, per-K turbo tables, PDSCH plans and the C ABI declared in
+// include/srsue_gpu/srsue_gpu.h.  This file and srslte_shim.cc are the only host code that touches CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "srsue_gpu/srsue_gpu.h"
+
+using namespace srsue;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_CHECK(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return fail(SRSUE_GPU_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t upload(T** d, const std::vector<T>& h) {
+  cudaError_t e = cudaMalloc((void**)d, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+struct TurboTables {
+  TurboGeom g{};
+  uint16_t* d_perm = nullptr;
+  uint32_t* d_crcU[2] = {nullptr, nullptr};   // [0] CRC24A, [1] CRC24B
+  uint32_t* d_crcV[2] = {nullptr, nullptr};
+};
+
+struct Scratch {
+  int16_t* nii = nullptr; size_t nii_elems = 0;
+  uint8_t* bits = nullptr; size_t bits_bytes = 0;
+  int16_t* tcb = nullptr; size_t tcb_elems = 0;
+  void release() { cudaFree(nii); cudaFree(bits); cudaFree(tcb); nii = nullptr; bits = nullptr; tcb = nullptr; nii_elems = bits_bytes = tcb_elems = 0; }
+};
+
+}  // namespace
+
+struct srsue_gpu_ctx {
+  int device = 0, num_sms = 0, smem_optin = 0;
+  std::mutex mu;
+  std::map<int, TurboTables> turbo;
+  Scratch scratch;
+  int last_grid = 0, last_block = 0, last_smem = 0, last_ncb = 0;
+  int launch_count = 0;
+  bool attr_set = false;
+};
+
+namespace {
+
+int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->turbo.find(K);
+  if (it != ctx->turbo.end()) { *out = &it->second; return 0; }
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  TurboTables t;
+  t.g = turbo_geom(K);
+  std::vector<uint16_t> pos;
+  turbo_perm_pos(t.g, pos);
+  CU_CHECK(upload(&t.d_perm, pos));
+  const uint32_t polys[2] = {kCrc24A, kCrc24B};
+  for (int i = 0; i < 2; i++) {
+    std::vector<uint32_t> U, V;
+    turbo_crc_tables(t.g, polys[i], U, V);
+    CU_CHECK(upload(&t.d_crcU[i], U));
+    CU_CHECK(upload(&t.d_crcV[i], V));
+  }
+  auto ins = ctx->turbo.emplace(K, t);
+  *out = &ins.first->second;
+  return 0;
+}
+
+struct TurboLaunchCfg { int ncb, threads, grid, smem; };
+
+TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb) {
+  const int nsw = g.W / 8;
+  const int slot_bytes = g.plane * 2 + nsw * 8 * g.T * 4;
+  const int fixed = g.plane * 2 + 64;
+  int ncb = (ctx->smem_optin - fixed) / (slot_bytes + 4);
+  ncb = std::min(ncb, kTurboMaxThreads / g.T);
+  // spread small batches over all SMs rather than filling a few CTAs
+  ncb = std::min(ncb, std::max(1, (n_cb + ctx->num_sms - 1) / ctx->num_sms));
+  ncb = std::max(ncb, 1);
+  TurboLaunchCfg c;
+  c.ncb = ncb;
+  c.threads = ((ncb * g.T + 31) / 32) * 32;
+  c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms);
+  c.smem = g.plane * 2 + ((ncb + 3) & ~3) * 4 + ncb * slot_bytes;
+  return c;
+}
+
+int ensure_scratch(Scratch& s, size_t nii_elems, size_t bits_bytes, size_t tcb_elems) {
+  if (nii_elems > s.nii_elems) { cudaFree(s.nii); CU_CHECK(cudaMalloc((void**)&s.nii, nii_elems * 2)); s.nii_elems = nii_elems; }
+  if (bits_bytes > s.bits_bytes) { cudaFree(s.bits); CU_CHECK(cudaMalloc((void**)&s.bits, bits_bytes)); s.bits_bytes = bits_bytes; }
+  if (tcb_elems > s.tcb_elems) { cudaFree(s.tcb); CU_CHECK(cudaMalloc((void**)&s.tcb, tcb_elems * 2)); s.tcb_elems = tcb_elems; }
+  return 0;
+}
+
+// launches the decoder for n_cb code blocks of size K.  cb_list (device) may be null.
+int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long long in_stride, const int32_t* d_cb_list, int n_cb, int K,
+                 int max_iter, int crc_type, uint8_t* d_bits, int out_stride, int32_t* d_status, cudaStream_t st) {
+  if (n_cb <= 0) return 0;
+  if (max_iter < 1 || crc_type < 0 || crc_type > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "bad max_iter/crc_type");
+  const TurboTables* tt = nullptr;
+  int rc = get_turbo_tables(ctx, K, &tt);
+  if (rc) return rc;
+  const TurboGeom& g = tt->g;
+  const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb);
+  const size_t slots = (size_t)lc.grid * lc.ncb;
+  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), slots * (size_t)g.plane, 0);
+  if (rc) return rc;
+  if (!ctx->attr_set) {
+    CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    ctx->attr_set = true;
+  }
+  TurboArgs a{};
+  a.in = d_in; a.in_stride = in_stride; a.cb_list = d_cb_list; a.n_cb = n_cb;
+  a.out_bits = d_bits; a.out_stride = out_stride; a.out_status = d_status;
+  a.max_iter = max_iter; a.crc_type = crc_type;
+  a.crc_poly = (crc_type == 2) ? kCrc24B : kCrc24A;
+  a.K = g.K; a.W = g.W; a.P = g.P; a.Ppad = g.Ppad; a.T = g.T; a.plane = g.plane;
+  a.perm_pos = tt->d_perm;
+  a.crcU = tt->d_crcU[crc_type == 2 ? 1 : 0];
+  a.crcV = tt->d_crcV[crc_type == 2 ? 1 : 0];
+  a.ncb_cta = lc.ncb;
+  a.nii = scr.nii;
+  a.bits_scratch = scr.bits;
+  turbo_decode_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  CU_CHECK(cudaGetLastError());
+  ctx->last_grid = lc.grid; ctx->last_block = lc.threads; ctx->last_smem = lc.smem; ctx->last_ncb = lc.ncb;
+  ctx->launch_count++;
+  return 0;
+}
+
+TurboGeomDev to_dev(const TurboGeom& g) { return TurboGeomDev{g.K, g.W, g.P, g.Ppad, g.T, g.plane, g.cb_elems}; }
+
+}  // namespace
+
+struct srsue_gpu_pdsch_plan {
+  srsue_gpu_ctx* ctx = nullptr;
+  CellCfg cell{};
+  PdschCfg cfg{};
+  CbSegm seg{};
+  srsue_gpu_plan_info_t info{};
+  TurboGeom gp{}, gm{};
+  int crs_off[2][4]{};
+  int max_E = 0, gather_stride = 0;
+  // device tables
+  int32_t* d_re = nullptr; uint32_t* d_scr = nullptr; uint16_t* d_gather = nullptr;
+  int32_t* d_e_start = nullptr; int32_t* d_cb_geom = nullptr; int8_t* d_crs = nullptr; float* d_tw = nullptr;
+  int32_t* d_list_m = nullptr; int32_t* d_list_p = nullptr;
+  // device work buffers (max_batch)
+  float2* d_sf = nullptr; float2* d_ce = nullptr; float* d_meas = nullptr; int16_t* d_sb = nullptr;
+  uint8_t* d_cb_bits = nullptr; int32_t* d_cb_status = nullptr;
+  // staging for the host-pointer call
+  float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
+  cudaStream_t stream = nullptr;
+  Scratch scratch;             // decoder scratch of this plan (plans may run concurrently on different streams)
+};
+
+extern "C" {
+
+const char* srsue_gpu_last_error(void) { return g_err.c_str(); }
+int srsue_gpu_version(void) { return 100; }
+
+int srsue_gpu_ctx_create(srsue_gpu_ctx_t** out, int device) {
+  if (!out) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null ctx pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SRSUE_GPU_ERROR, "libsrsue_gpu needs a CUDA device and has no CPU fallback: %s",
+                e != cudaSuccess ? cudaGetErrorString(e) : "no device");
+  if (device < 0 || device >= n) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "device %d out of range (%d devices)", device, n);
+  CU_CHECK(cudaSetDevice(device));
+  cudaDeviceProp p;
+  CU_CHECK(cudaGetDeviceProperties(&p, device));
+  if (p.major < 10) return fail(SRSUE_GPU_ERROR, "device %s is sm_%d%d; libsrsue_gpu is built for sm_100a only", p.name, p.major, p.minor);
+  auto* ctx = new srsue_gpu_ctx();
+  ctx->device = device;
+  ctx->num_sms = p.multiProcessorCount;
+  ctx->smem_optin = (int)p.sharedMemPerBlockOptin;
+  *out = ctx;
+  return 0;
+}
+
+void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& kv : ctx->turbo) {
+    cudaFree(kv.second.d_perm);
+    for (int i = 0; i < 2; i++) { cudaFree(kv.second.d_crcU[i]); cudaFree(kv.second.d_crcV[i]); }
+  }
+  ctx->scratch.release();
+  delete ctx;
+}
+
+int srsue_gpu_tdec_geometry(int K, int* W, int* P, int* cb_elems) {
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  const TurboGeom g = turbo_geom(K);
+  if (W) *W = g.W;
+  if (P) *P = g.P;
+  if (cb_elems) *cb_elems = g.cb_elems;
+  return 0;
+}
+
+int srsue_gpu_tdec_import(srsue_gpu_ctx_t* ctx, const int16_t* d_triples, int n_cb, int K, int16_t* d_tcb, void* stream) {
+  if (!ctx || !d_triples || !d_tcb || n_cb < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tdec_import: bad arguments");
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  if (n_cb == 0) return 0;
+  const TurboGeom g = turbo_geom(K);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  for (int done = 0; done < n_cb; done += 65535) {
+    const int n = std::min(65535, n_cb - done);
+    dim3 grid((g.cb_elems + 255) / 256 > 8 ? 8 : (g.cb_elems + 255) / 256, n);
+    triples_to_tcb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_triples + (size_t)done * (3 * K + 12), 3 * K + 12,
+                                                                  d_tcb + (size_t)done * g.cb_elems, g.cb_elems, n, to_dev(g));
+    ctx->launch_count++;
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_tdec_export(srsue_gpu_ctx_t* ctx, const int16_t* d_tcb, int n_cb, int K, int16_t* d_triples, void* stream) {
+  if (!ctx || !d_triples || !d_tcb || n_cb < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tdec_export: bad arguments");
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  if (n_cb == 0) return 0;
+  const TurboGeom g = turbo_geom(K);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  for (int done = 0; done < n_cb; done += 65535) {
+    const int n = std::min(65535, n_cb - done);
+    dim3 grid(8, n);
+    tcb_to_triples_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_tcb + (size_t)done * g.cb_elems, g.cb_elems,
+                                                                  d_triples + (size_t)done * (3 * K + 12), 3 * K + 12, n, to_dev(g));
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_tdec_decode(srsue_gpu_ctx_t* ctx, const int16_t* d_tcb, int n_cb, int K, int max_iter, int crc_type,
+                          uint8_t* d_bits, int32_t* d_status, void* stream) {
+  if (!ctx || !d_tcb || !d_bits || !d_status || n_cb < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tdec_decode: bad arguments");
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  const TurboGeom g = turbo_geom(K);
+  return launch_turbo(ctx, ctx->scratch, d_tcb, g.cb_elems, nullptr, n_cb, K, max_iter, crc_type, d_bits, K / 8, d_status, (cudaStream_t)stream);
+}
+
+int srsue_gpu_tdec_run_all(srsue_gpu_ctx_t* ctx, const int16_t* d_triples, int n_cb, int K, int max_iter, int crc_type,
+                           uint8_t* d_bits, int32_t* d_status, void* stream) {
+  if (!ctx) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null ctx");
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  if (n_cb <= 0) return n_cb == 0 ? 0 : fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "negative n_cb");
+  const TurboGeom g = turbo_geom(K);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  int rc = ensure_scratch(ctx->scratch, 0, 0, (size_t)n_cb * g.cb_elems);
+  if (rc) return rc;
+  ctx->launch_count = 0;
+  rc = srsue_gpu_tdec_import(ctx, d_triples, n_cb, K, ctx->scratch.tcb, stream);
+  if (rc) return rc;
+  return srsue_gpu_tdec_decode(ctx, ctx->scratch.tcb, n_cb, K, max_iter, crc_type, d_bits, d_status, stream);
+}
+
+int srsue_gpu_tdec_run_all_host(srsue_gpu_ctx_t* ctx, const int16_t* h_triples, int n_cb, int K, int max_iter, int crc_type,
+                                uint8_t* h_bits, int32_t* h_status) {
+  if (!ctx || !h_triples || !h_bits || !h_status || n_cb < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tdec_run_all_host: bad arguments");
+  if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
+  if (n_cb == 0) return 0;
+  static std::mutex host_call_mu;     // the context-level decoder scratch is shared: one host call at a time
+  std::lock_guard<std::mutex> lk(host_call_mu);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  int16_t* d_in = nullptr; uint8_t* d_bits = nullptr; int32_t* d_st = nullptr;
+  const size_t in_bytes = (size_t)n_cb * (3 * K + 12) * 2, bits_bytes = (size_t)n_cb * (K / 8);
+  CU_CHECK(cudaMalloc((void**)&d_in, in_bytes));
+  CU_CHECK(cudaMalloc((void**)&d_bits, bits_bytes));
+  CU_CHECK(cudaMalloc((void**)&d_st, (size_t)n_cb * 4));
+  int rc = 0;
+  cudaError_t e = cudaMemcpy(d_in, h_triples, in_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) rc = srsue_gpu_tdec_run_all(ctx, d_in, n_cb, K, max_iter, crc_type, d_bits, d_st, nullptr);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(h_bits, d_bits, bits_bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpy(h_status, d_st, (size_t)n_cb * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_bits); cudaFree(d_st);
+  if (e != cudaSuccess) return fail(SRSUE_GPU_ERROR, "tdec_run_all_host: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+int srsue_gpu_tdec_last_launch(srsue_gpu_ctx_t* ctx, int* grid, int* block, int* smem_bytes, int* cb_per_cta) {
+  if (!ctx) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  if (grid) *grid = ctx->last_grid;
+  if (block) *block = ctx->last_block;
+  if (smem_bytes) *smem_bytes = ctx->last_smem;
+  if (cb_per_cta) *cb_per_cta = ctx->last_ncb;
+  return 0;
+}
+
+int srsue_gpu_last_launch_count(srsue_gpu_ctx_t* ctx) { return ctx ? ctx->launch_count : 0; }
+
+// ---- PDSCH plan -------------------------------------------------------------------------------------
+int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* cell, const srsue_gpu_pdsch_cfg_t* cfg,
+                                int max_batch, srsue_gpu_pdsch_plan_t** out) {
+  if (!ctx || !cell || !cfg || !out || max_batch < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "plan_create: bad arguments");
+  *out = nullptr;
+  const int nfft = symbol_sz(cell->nof_prb);
+  if (nfft < 0 || nfft == 1536) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_prb=%d not supported (1536-point FFT not implemented)", cell->nof_prb);
+  if (cell->nof_ports < 1 || cell->nof_ports > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_ports must be 1 or 2");
+  if (cfg->qm != 2 && cfg->qm != 4 && cfg->qm != 6) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "qm must be 2, 4 or 6");
+  if (cfg->tm == 2 && cell->nof_ports != 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "transmit diversity needs 2 ports");
+  if (cfg->tm != 1 && cfg->tm != 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tm must be 1 or 2");
+  if (cfg->rv < 0 || cfg->rv > 3 || cfg->sf_idx < 0 || cfg->sf_idx > 9 || cfg->cfi < 1 || cfg->cfi > 3)
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "rv/sf_idx/cfi out of range");
+  CU_CHECK(cudaSetDevice(ctx->device));
+  auto* p = new srsue_gpu_pdsch_plan();
+  p->ctx = ctx;
+  p->cell = CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id};
+  static_assert(sizeof(PdschCfg) == sizeof(srsue_gpu_pdsch_cfg_t), "config layouts must match");
+  std::memcpy(&p->cfg, cfg, sizeof(PdschCfg));
+  if (cfg->tbs == 0) {
+    // front-end-only plan: OFDM demodulation and channel estimation for (cell, sf_idx); no grant yet
+    // (what srslte_ue_dl_decode_fft_estimate needs before the DCI is known, phch_worker.cc:254)
+    const int nsc0 = 12 * cell->nof_prb;
+    p->info.nfft = nfft; p->info.nsc = nsc0; p->info.sf_len = 15 * nfft; p->info.max_batch = max_batch;
+    std::vector<int8_t> crs0(4 * 2 * 2 * cell->nof_prb), rs0, is0;
+    const int crs_l0[4] = {0, 4, 7, 11};
+    for (int si = 0; si < 4; si++) {
+      crs_signs(p->cell, cfg->sf_idx, crs_l0[si], rs0, is0);
+      const int M = 2 * cell->nof_prb;
+      std::copy(rs0.begin(), rs0.end(), crs0.begin() + (si * 2 + 0) * M);
+      std::copy(is0.begin(), is0.end(), crs0.begin() + (si * 2 + 1) * M);
+      for (int port = 0; port < 2; port++) p->crs_off[port][si] = crs_offset(p->cell, port, crs_l0[si]);
+    }
+    std::vector<float> tw0;
+    fft_twiddles(nfft, tw0);
+    if (upload(&p->d_crs, crs0) != cudaSuccess || upload(&p->d_tw, tw0) != cudaSuccess) {
+      srsue_gpu_pdsch_plan_destroy(p);
+      return fail(SRSUE_GPU_ERROR, "plan_create: device allocation failed");
+    }
+    *out = p;
+    return 0;
+  }
+  if (!cbsegm(cfg->tbs, &p->seg)) { delete p; return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tbs=%d cannot be segmented", cfg->tbs); }
+  const CbSegm& s = p->seg;
+  std::vector<int32_t> re;
+  pdsch_re_list(p->cell, p->cfg, re);
+  const int nre = (int)re.size(), G = nre * cfg->qm, nl = (cfg->tm == 2) ? 2 : 1;
+  if (nre == 0 || G / (nl * cfg->qm) < s.C) { delete p; return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "grant has too few resource elements"); }
+  p->gp = turbo_geom(s.Kp);
+  p->gm = s.Cm ? turbo_geom(s.Km) : p->gp;
+  const int nsc = 12 * cell->nof_prb;
+  srsue_gpu_plan_info_t& I = p->info;
+  I.nfft = nfft; I.nsc = nsc; I.sf_len = 15 * nfft; I.nof_re = nre; I.G = G;
+  I.C = s.C; I.Kp = s.Kp; I.Km = s.Km; I.Cp = s.Cp; I.Cm = s.Cm; I.F = s.F;
+  I.sb_cb_stride = std::max(p->gp.cb_elems, p->gm.cb_elems);
+  I.sb_sf_stride = I.sb_cb_stride * s.C;
+  I.payload_stride = (cfg->tbs + 7) / 8;
+  I.max_batch = max_batch;
+  // rate-dematching tables
+  p->gather_stride = I.sb_cb_stride;
+  std::vector<uint16_t> gather((size_t)s.C * p->gather_stride, 0xFFFF), tab;
+  std::vector<int32_t> e_start(s.C + 1, 0), geom(4 * s.C, 0);
+  for (int r = 0; r < s.C; r++) {
+    const int K = cb_len(s, r), F = (r == 0) ? s.F : 0;
+    const TurboGeom g = turbo_geom(K);
+    const int N = rm_gather_table(g, F, cfg->rv, tab);
+    std::copy(tab.begin(), tab.end(), gather.begin() + (size_t)r * p->gather_stride);
+    const int E = cb_E(s, G, cfg->qm, nl, r);
+    e_start[r + 1] = e_start[r] + E;
+    p->max_E = std::max(p->max_E, E);
+    geom[4 * r] = g.cb_elems; geom[4 * r + 1] = N; geom[4 * r + 2] = K;
+  }
+  if (e_start[s.C] != G) { delete p; return fail(SRSUE_GPU_ERROR, "internal: rate-matching sizes do not add up"); }
+  std::vector<uint32_t> scr;
+  gold_packed(((uint32_t)cfg->rnti << 14) | ((uint32_t)cfg->sf_idx << 9) | (uint32_t)cell->cell_id, G, scr);
+  std::vector<int8_t> crs(4 * 2 * 2 * cell->nof_prb), rs, is;
+  const int crs_l[4] = {0, 4, 7, 11};
+  for (int si = 0; si < 4; si++) {
+    crs_signs(p->cell, cfg->sf_idx, crs_l[si], rs, is);
+    const int M = 2 * cell->nof_prb;
+    std::copy(rs.begin(), rs.end(), crs.begin() + (si * 2 + 0) * M);
+    std::copy(is.begin(), is.end(), crs.begin() + (si * 2 + 1) * M);
+    for (int port = 0; port < 2; port++) p->crs_off[port][si] = crs_offset(p->cell, port, crs_l[si]);
+  }
+  std::vector<float> tw;
+  fft_twiddles(nfft, tw);
+  std::vector<int32_t> list_m((size_t)max_batch * s.Cm), list_p((size_t)max_batch * s.Cp);
+  for (int sf = 0; sf < max_batch; sf++) {
+    for (int r = 0; r < s.Cm; r++) list_m[(size_t)sf * s.Cm + r] = sf * s.C + r;
+    for (int r = 0; r < s.Cp; r++) list_p[(size_t)sf * s.Cp + r] = sf * s.C + s.Cm + r;
+  }
+  bool ok = upload(&p->d_re, re) == cudaSuccess && upload(&p->d_scr, scr) == cudaSuccess &&
+            upload(&p->d_gather, gather) == cudaSuccess && upload(&p->d_e_start, e_start) == cudaSuccess &&
+            upload(&p->d_cb_geom, geom) == cudaSuccess && upload(&p->d_crs, crs) == cudaSuccess &&
+            upload(&p->d_tw, tw) == cudaSuccess && upload(&p->d_list_m, list_m) == cudaSuccess &&
+            upload(&p->d_list_p, list_p) == cudaSuccess;
+  const size_t B = (size_t)max_batch;
+  ok = ok && cudaMalloc((void**)&p->d_sf, B * 14 * nsc * sizeof(float2)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_ce, B * cell->nof_ports * 14 * nsc * sizeof(float2)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_meas, B * 5 * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_sb, B * I.sb_sf_stride * sizeof(int16_t)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_cb_bits, B * s.C * (s.Kp / 8)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_cb_status, B * s.C * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    srsue_gpu_pdsch_plan_destroy(p);
+    return fail(SRSUE_GPU_ERROR, "plan_create: device allocation failed: %s", msg);
+  }
+  CU_CHECK(cudaFuncSetAttribute(pdsch_llr_dematch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+  *out = p;
+  return 0;
+}
+
+void srsue_gpu_pdsch_plan_destroy(srsue_gpu_pdsch_plan_t* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaFree(p->d_re); cudaFree(p->d_scr); cudaFree(p->d_gather); cudaFree(p->d_e_start); cudaFree(p->d_cb_geom);
+  cudaFree(p->d_crs); cudaFree(p->d_tw); cudaFree(p->d_list_m); cudaFree(p->d_list_p);
+  cudaFree(p->d_sf); cudaFree(p->d_ce); cudaFree(p->d_meas); cudaFree(p->d_sb); cudaFree(p->d_cb_bits);
+  cudaFree(p->d_cb_status); cudaFree(p->d_iq); cudaFree(p->d_payload); cudaFree(p->d_tb_status);
+  p->scratch.release();
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int srsue_gpu_pdsch_plan_info(const srsue_gpu_pdsch_plan_t* p, srsue_gpu_plan_info_t* info) {
+  if (!p || !info) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  *info = p->info;
+  return 0;
+}
+
+#define PLAN_CHECK(p, n)                                                                               \
+  do {                                                                                                 \
+    if (!(p)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");                                \
+    if ((n) < 0 || (n) > (p)->info.max_batch) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "n_sf=%d outside [0, max_batch=%d]", (n), (p)->info.max_batch); \
+    if ((n) == 0) return 0;                                                                            \
+    CU_CHECK(cudaSetDevice((p)->ctx->device));                                                         \
+  } while (0)
+
+int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, srsue_gpu_cf_t* d_sf, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_iq || !d_sf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx: null buffer");
+  OfdmArgs a{};
+  a.iq = reinterpret_cast<const float2*>(d_iq); a.sf_symbols = reinterpret_cast<float2*>(d_sf);
+  a.tw = reinterpret_cast<const float2*>(p->d_tw);
+  a.nfft = p->info.nfft; a.nsc = p->info.nsc; a.n_sf = n_sf;
+  a.log2n = 0; while ((1 << a.log2n) < a.nfft) a.log2n++;
+  a.scale = (float)(1.0 / std::sqrt((double)a.nfft));
+  const int threads = std::max(32, a.nfft / 8);
+  const int smem = 2 * (a.nfft + a.nfft / 16 + 8) * (int)sizeof(float2);
+  for (int done = 0; done < n_sf; done += 65535) {
+    const int n = std::min(65535, n_sf - done);
+    OfdmArgs b = a;
+    b.iq += (size_t)done * 15 * a.nfft; b.sf_symbols += (size_t)done * 14 * a.nsc; b.n_sf = n;
+    ofdm_rx_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+    p->ctx->launch_count++;
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_chest(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, srsue_gpu_cf_t* d_ce, float* d_meas, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "chest: null buffer");
+  ChestArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<float2*>(d_ce); a.meas = d_meas;
+  a.crs_sign = p->d_crs; a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_prb = p->cell.nof_prb; a.nof_ports = p->cell.nof_ports;
+  std::memcpy(a.crs_off, p->crs_off, sizeof(a.crs_off));
+  const int smem = 2 * p->cell.nof_ports * 4 * 2 * p->cell.nof_prb * (int)sizeof(float2);
+  chest_kernel<<<n_sf, 512, smem, (cudaStream_t)stream>>>(a);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_pdsch_llr(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, const srsue_gpu_cf_t* d_ce,
+                        const float* d_meas, float noise_est, int noise_mode, int accumulate, int16_t* d_softbuf,
+                        srsue_gpu_cf_t* d_dbg_d, int16_t* d_dbg_e, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce || !d_softbuf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: null buffer");
+  if (p->info.C == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: front-end-only plan (tbs == 0)");
+  if (noise_mode && !d_meas) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: noise_mode 1 needs d_meas");
+  DemodArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
+  a.softbuf = d_softbuf; a.re_idx = p->d_re; a.scramble = p->d_scr; a.gather = p->d_gather;
+  a.cb_e_start = p->d_e_start; a.cb_geom = p->d_cb_geom;
+  a.dbg_d = reinterpret_cast<float2*>(d_dbg_d); a.dbg_e = d_dbg_e;
+  a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.tm = p->cfg.tm; a.qm = p->cfg.qm;
+  a.nof_re = p->info.nof_re; a.C = p->info.C; a.gather_stride = p->gather_stride; a.sb_stride = p->info.sb_cb_stride;
+  a.noise_est = noise_est; a.noise_mode = noise_mode; a.accumulate = accumulate;
+  a.k_sqpsk = (float)(100.0 * std::sqrt(2.0));
+  a.k_c16 = (float)(2.0 * 400.0 / std::sqrt(10.0));
+  a.k_c64a = (float)(4.0 * 700.0 / std::sqrt(42.0));
+  a.k_c64b = (float)(2.0 * 700.0 / std::sqrt(42.0));
+  a.k_sq2 = (float)std::sqrt(2.0);
+  const int smem = ((p->max_E * 2 + 15) / 16) * 16;
+  if (smem > p->ctx->smem_optin) return fail(SRSUE_GPU_ERROR, "code block of %d LLRs does not fit in shared memory", p->max_E);
+  for (int done = 0; done < n_sf; done += 65535) {
+    const int n = std::min(65535, n_sf - done);
+    DemodArgs b = a;
+    b.sf_symbols += (size_t)done * 14 * a.nsc; b.ce += (size_t)done * a.nof_ports * 14 * a.nsc;
+    if (b.meas) b.meas += (size_t)done * 5;
+    b.softbuf += (size_t)done * p->info.sb_sf_stride;
+    if (b.dbg_d) b.dbg_d += (size_t)done * a.nof_re;
+    if (b.dbg_e) b.dbg_e += (size_t)done * p->info.G;
+    b.n_sf = n;
+    pdsch_llr_dematch_kernel<<<dim3(a.C, n), 512, smem, (cudaStream_t)stream>>>(b);
+    p->ctx->launch_count++;
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_pdsch_turbo(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_softbuf, int max_iter, uint8_t* d_payload,
+                          int32_t* d_tb_status, int32_t* d_cb_status, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_softbuf || !d_payload || !d_tb_status) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_turbo: null buffer");
+  if (p->info.C == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_turbo: front-end-only plan (tbs == 0)");
+  const CbSegm& s = p->seg;
+  int32_t* cbst = d_cb_status ? d_cb_status : p->d_cb_status;
+  const int crc_type = (s.C > 1) ? 2 : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (s.Cm) rc = launch_turbo(p->ctx, p->scratch, d_softbuf, p->info.sb_cb_stride, p->d_list_m, n_sf * s.Cm, s.Km, max_iter, crc_type,
+                              p->d_cb_bits, s.Kp / 8, cbst, st);
+  if (rc) return rc;
+  rc = launch_turbo(p->ctx, p->scratch, d_softbuf, p->info.sb_cb_stride, p->d_list_p, n_sf * s.Cp, s.Kp, max_iter, crc_type, p->d_cb_bits,
+                    s.Kp / 8, cbst, st);
+  if (rc) return rc;
+  TbArgs t{};
+  t.cb_bits = p->d_cb_bits; t.cb_status = cbst; t.payload = d_payload; t.tb_status = d_tb_status;
+  t.n_sf = n_sf; t.C = s.C; t.Cm = s.Cm; t.Km = s.Km; t.Kp = s.Kp; t.F = s.F; t.tbs = s.tbs;
+  t.cb_bits_stride = s.Kp / 8; t.payload_stride = p->info.payload_stride;
+  tb_assemble_kernel<<<n_sf, 256, 0, st>>>(t);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, float noise_est, int noise_mode,
+                                 int max_iter, int accumulate, int16_t* d_softbuf, uint8_t* d_payload, int32_t* d_tb_status,
+                                 float* d_meas, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (accumulate && !d_softbuf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "HARQ combining needs a caller-owned soft buffer");
+  p->ctx->launch_count = 0;
+  float* meas = d_meas ? d_meas : p->d_meas;
+  int16_t* sb = d_softbuf ? d_softbuf : p->d_sb;
+  int rc = srsue_gpu_ofdm_rx(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream);
+  if (!rc) rc = srsue_gpu_chest(p, n_sf, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), reinterpret_cast<srsue_gpu_cf_t*>(p->d_ce), meas, stream);
+  if (!rc) rc = srsue_gpu_pdsch_llr(p, n_sf, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), reinterpret_cast<srsue_gpu_cf_t*>(p->d_ce), meas,
+                                    noise_est, noise_mode, accumulate, sb, nullptr, nullptr, stream);
+  if (!rc) rc = srsue_gpu_pdsch_turbo(p, n_sf, sb, max_iter, d_payload, d_tb_status, nullptr, stream);
+  return rc;
+}
+
+int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* h_iq, float noise_est,
+                                      int noise_mode, int max_iter, uint8_t* h_payload, int32_t* h_tb_status, float* h_meas) {
+  PLAN_CHECK(p, n_sf);
+  if (!h_iq || !h_payload || !h_tb_status) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "decode_batch_host: null buffer");
+  const size_t B = (size_t)p->info.max_batch;
+  if (!p->d_iq) {
+    CU_CHECK(cudaMalloc((void**)&p->d_iq, B * p->info.sf_len * sizeof(float2)));
+    CU_CHECK(cudaMalloc((void**)&p->d_payload, B * p->info.payload_stride));
+    CU_CHECK(cudaMalloc((void**)&p->d_tb_status, B * 4 * sizeof(int32_t)));
+  }
+  cudaStream_t st = p->stream;
+  CU_CHECK(cudaMemcpyAsync(p->d_iq, h_iq, (size_t)n_sf * p->info.sf_len * sizeof(float2), cudaMemcpyHostToDevice, st));
+  int rc = srsue_gpu_pdsch_decode_batch(p, n_sf, reinterpret_cast<srsue_gpu_cf_t*>(p->d_iq), noise_est, noise_mode, max_iter, 0,
+                                        nullptr, p->d_payload, p->d_tb_status, p->d_meas, st);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpyAsync(h_payload, p->d_payload, (size_t)n_sf * p->info.payload_stride, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaMemcpyAsync(h_tb_status, p->d_tb_status, (size_t)n_sf * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (h_meas) CU_CHECK(cudaMemcpyAsync(h_meas, p->d_meas, (size_t)n_sf * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+void* srsue_gpu_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void srsue_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// chest.cu -- K2: CRS least-squares channel estimate, 3-tap smoothing, frequency + time linear
+// interpolation, and the noise / RSRP / RSSI / RSRQ / SNR measurements (sm_100a).
+//
+// Replaces srsLTE's srslte_chest_dl_estimate inside srslte_ue_dl_decode_fft_estimate
+// (/root/reference/ue/src/phy/phch_worker.cc:254) and feeds the getters srsUE reads afterwards
+// (phch_worker.cc:359,799,821-823,842,847).  Arithmetic contract: oracle/SPEC.md section 3; every float
+// operation is an explicit round-to-nearest intrinsic so that nothing is contracted into an FMA.
+// One CTA per subframe: pilots and their smoothed values live in shared memory, each thread then owns
+// subcarriers k = tid, tid + blockDim, ... and writes the 14 interpolated symbols coalesced.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace srsue {
+
+namespace {
+__device__ __forceinline__ float lerp_rn(float a, float b, float f) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), f)); }
+__device__ __forceinline__ float abs2_rn(float2 z) { return __fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)); }
+
+// SPEC 3.5 reduction order: lane l accumulates elements l, l+32, ... in ascending order, then xor-tree
+template <typename F>
+__device__ __forceinline__ float warp_sum_ordered(int n, int lane, F elem) {
+  float acc = 0.0f;
+  for (int i = lane; i < n; i += 32) acc = __fadd_rn(acc, elem(i));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, off));
+  return acc;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(512) chest_kernel(const ChestArgs a) {
+  extern __shared__ __align__(16) float2 s_ch[];
+  __shared__ float s_ftab[17];
+  __shared__ float s_ttab[14];
+  __shared__ float s_red[3];
+  const int sf = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int nsc = a.nsc, M = 2 * a.nof_prb, np = a.nof_ports;
+  float2* s_ls = s_ch;                    // [np][4][M]
+  float2* s_sm = s_ch + np * 4 * M;       // [np][4][M]
+  const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
+  const int crs_l[4] = {0, 4, 7, 11};
+  const float isq2 = (float)(1.0 / sqrt(2.0));
+
+  if (tid < 17) s_ftab[tid] = (float)((double)(tid - 5) / 6.0);
+  if (tid >= 32 && tid < 46) {
+    const int l = tid - 32;
+    const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+    s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
+  }
+  // ---- least squares at the pilots ------------------------------------------------------------------
+  for (int i = tid; i < np * 4 * M; i += nt) {
+    const int m = i % M, si = (i / M) % 4, p = i / (4 * M);
+    const float2 v = y[crs_l[si] * nsc + a.crs_off[p][si] + 6 * m];
+    const int rs = a.crs_sign[(si * 2 + 0) * M + m], is = a.crs_sign[(si * 2 + 1) * M + m];
+    const float tre = __fadd_rn(rs > 0 ? v.x : -v.x, is > 0 ? v.y : -v.y);
+    const float tim = __fsub_rn(rs > 0 ? v.y : -v.y, is > 0 ? v.x : -v.x);
+    s_ls[i] = make_float2(__fmul_rn(tre, isq2), __fmul_rn(tim, isq2));
+  }
+  __syncthreads();
+  // ---- 3-tap smoothing (edges unchanged) ------------------------------------------------------------
+  for (int i = tid; i < np * 4 * M; i += nt) {
+    const int m = i % M;
+    float2 o = s_ls[i];
+    if (m > 0 && m < M - 1) {
+      const float2 l = s_ls[i - 1], c = s_ls[i], r = s_ls[i + 1];
+      o.x = __fadd_rn(__fadd_rn(__fmul_rn(0.1f, l.x), __fmul_rn(0.8f, c.x)), __fmul_rn(0.1f, r.x));
+      o.y = __fadd_rn(__fadd_rn(__fmul_rn(0.1f, l.y), __fmul_rn(0.8f, c.y)), __fmul_rn(0.1f, r.y));
+    }
+    s_sm[i] = o;
+  }
+  __syncthreads();
+  // ---- frequency + time interpolation ---------------------------------------------------------------
+  for (int p = 0; p < np; p++) {
+    float2* ce = a.ce + ((size_t)sf * np + p) * 14 * nsc;
+    for (int k = tid; k < nsc; k += nt) {
+      float2 h[4];
+#pragma unroll
+      for (int si = 0; si < 4; si++) {
+        const int off = a.crs_off[p][si];
+        int m = (k >= off) ? (k - off) / 6 : 0;
+        if (m > M - 2) m = M - 2;
+        const float f = s_ftab[k - (6 * m + off) + 5];
+        const float2 v0 = s_sm[(p * 4 + si) * M + m], v1 = s_sm[(p * 4 + si) * M + m + 1];
+        h[si] = make_float2(lerp_rn(v0.x, v1.x, f), lerp_rn(v0.y, v1.y, f));
+      }
+#pragma unroll
+      for (int l = 0; l < 14; l++) {
+        const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+        float2 o;
+        if (l == 0 || l == 4 || l == 7 || l == 11) o = h[l == 0 ? 0 : l == 4 ? 1 : l == 7 ? 2 : 3];
+        else { const float f = s_ttab[l]; o = make_float2(lerp_rn(h[s0].x, h[s0 + 1].x, f), lerp_rn(h[s0].y, h[s0 + 1].y, f)); }
+        ce[l * nsc + k] = o;
+      }
+    }
+  }
+  // ---- measurements: three warps, one quantity each -------------------------------------------------
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_noise = np * 4 * (M - 2), n_rsrp = 4 * M, n_rssi = 4 * nsc;
+  if (warp == 0) {
+    const float s = warp_sum_ordered(n_noise, lane, [&](int i) {
+      const int m = i % (M - 2) + 1, q = i / (M - 2);       // q = p*4 + si
+      const float2 l = s_ls[q * M + m], t = s_sm[q * M + m];
+      const float dr = __fsub_rn(l.x, t.x), di = __fsub_rn(l.y, t.y);
+      return __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+    });
+    if (lane == 0) s_red[0] = __fdiv_rn(__fdiv_rn(s, (float)n_noise), 0.06f);
+  } else if (warp == 1) {
+    const float s = warp_sum_ordered(n_rsrp, lane, [&](int i) { return abs2_rn(s_ls[i]); });   // port 0 first
+    if (lane == 0) s_red[1] = __fdiv_rn(s, (float)n_rsrp);
+  } else if (warp == 2) {
+    const float s = warp_sum_ordered(n_rssi, lane, [&](int i) {
+      const int si = i / nsc, k = i - si * nsc;
+      return abs2_rn(y[crs_l[si] * nsc + k]);
+    });
+    if (lane == 0) s_red[2] = __fdiv_rn(s, (float)n_rssi);
+  }
+  __syncthreads();
+  if (tid == 0 && a.meas) {
+    float* o = a.meas + (size_t)sf * 5;
+    o[0] = s_red[0]; o[1] = s_red[1]; o[2] = s_red[2];
+    o[3] = __fdiv_rn(__fmul_rn((float)a.nof_prb, s_red[1]), s_red[2]);
+    o[4] = __fdiv_rn(s_red[1], s_red[0]);
+  }
+}
+
+}  // namespace srsue

@@ -1,0 +1,89 @@
+// kernels.h -- device-side argument structs and kernel declarations of libsrsue_gpu (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lte_tables.h"
+
+namespace srsue {
+
+constexpr int kTurboMaxThreads = 384;
+
+struct TurboGeomDev { int K, W, P, Ppad, T, plane, cb_elems; };
+
+struct TurboArgs {
+  const int16_t* in;         // code blocks in tcb layout
+  long long in_stride;       // int16 elements between consecutive code blocks
+  const int32_t* cb_list;    // optional indirection (nullptr: code block i is entry i)
+  int n_cb;
+  uint8_t* out_bits;         // [cb][out_stride] hard bits, packed MSB first
+  int out_stride;
+  int32_t* out_status;       // [cb] iterations | crc_ok << 8
+  int max_iter, crc_type;    // crc_type: 0 none, 1 CRC24A, 2 CRC24B
+  uint32_t crc_poly;
+  int K, W, P, Ppad, T, plane;
+  const uint16_t* perm_pos;  // [plane]
+  const uint32_t* crcU;      // [W]
+  const uint32_t* crcV;      // [Ppad]
+  int ncb_cta;               // code-block slots per CTA
+  int16_t* nii;              // [grid * ncb_cta][2][2][2][8][Ppad + 2]
+  uint8_t* bits_scratch;     // [grid * ncb_cta][plane]
+};
+
+__global__ void turbo_decode_kernel(const TurboArgs g);
+__global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
+                                      int n_cb, TurboGeomDev g);
+__global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
+                                      int n_cb, TurboGeomDev g);
+
+// ---- front end -------------------------------------------------------------------------------------
+struct OfdmArgs {
+  const float2* iq;          // [n_sf][15 * nfft]
+  float2* sf_symbols;        // [n_sf][14 * nsc]
+  const float2* tw;          // nfft/2 twiddles
+  int n_sf, nfft, log2n, nsc;
+  float scale;
+};
+__global__ void ofdm_rx_kernel(const OfdmArgs a);
+
+struct ChestArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc]
+  float2* ce;                // [n_sf][ports][14 * nsc]
+  float* meas;               // [n_sf][5]  noise, rsrp, rssi, rsrq, snr
+  const int8_t* crs_sign;    // [4 crs symbols][2 (re, im)][2 * nof_prb]
+  int n_sf, nsc, nof_prb, nof_ports;
+  int crs_off[2][4];         // first pilot subcarrier per port and CRS symbol
+};
+__global__ void chest_kernel(const ChestArgs a);
+
+struct DemodArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc]
+  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float* meas;         // [n_sf][5] (noise estimate when noise_mode == 1)
+  int16_t* softbuf;          // [n_sf][C][sb_stride] tcb layout
+  const int32_t* re_idx;     // [nof_re] grid index of every PDSCH RE
+  const uint32_t* scramble;  // packed Gold sequence, G bits
+  const uint16_t* gather;    // [C][gather_stride] per code block: tcb element -> LLR index in the CB's range
+  const int32_t* cb_e_start; // [C+1] first LLR index of each code block
+  const int32_t* cb_geom;    // [C][4]: cb_elems, N (non-null positions), K, unused
+  float2* dbg_d;             // optional [n_sf][nof_re] equalised symbols
+  int16_t* dbg_e;            // optional [n_sf][G] descrambled LLRs
+  int n_sf, nsc, nof_ports, tm, qm, nof_re, C, gather_stride;
+  long long sb_stride;       // elements per code block in softbuf
+  float noise_est;
+  float k_sqpsk, k_c16, k_c64a, k_c64b, k_sq2;   // demapper constants, rounded on the host (SPEC 5)
+  int noise_mode;            // 0: noise_est, 1: meas[0]
+  int accumulate;            // 0: new transmission (buffer overwritten), 1: add to existing
+};
+__global__ void pdsch_llr_dematch_kernel(const DemodArgs a);
+
+struct TbArgs {
+  const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
+  const int32_t* cb_status;  // [n_sf * C]
+  uint8_t* payload;          // [n_sf][payload_stride]
+  int32_t* tb_status;        // [n_sf][4]: crc_ok, sum of iterations, avg iterations, C
+  int n_sf, C, Cm, Km, Kp, F, tbs, cb_bits_stride, payload_stride;
+};
+__global__ void tb_assemble_kernel(const TbArgs a);
+
+}  // namespace srsue

@@ -1,0 +1,244 @@
+// lte_tables.cc -- host-side LTE tables for libsrsue_gpu (see lte_tables.h).
+// 3GPP TS 36.211 6.3.5 / 6.10.1 / 7.2 and TS 36.212 5.1.1-5.1.4; window rule per oracle/SPEC.md 7.3.
+#include "lte_tables.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace srsue {
+
+static const uint16_t kQpp[188][3] = {
+#include "qpp_table.inc"
+};
+
+int qpp_index(int K) {
+  int lo = 0, hi = 187;
+  while (lo <= hi) {
+    int mid = (lo + hi) / 2;
+    if (kQpp[mid][0] == K) return mid;
+    if (kQpp[mid][0] < K) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+int qpp_K(int idx) { return (idx >= 0 && idx < 188) ? kQpp[idx][0] : -1; }
+
+bool qpp_params(int K, int* f1, int* f2) {
+  int i = qpp_index(K);
+  if (i < 0) return false;
+  *f1 = kQpp[i][1]; *f2 = kQpp[i][2];
+  return true;
+}
+
+int window_len(int K) {
+  int even = 0, any = 0;
+  for (int w = 64; w <= 128 && w <= K; w += 8) {
+    if (K % w) continue;
+    any = w;
+    if ((K / w) % 2 == 0) even = w;
+  }
+  if (even) return even;
+  if (any) return any;
+  for (int w = 64; w <= K; w += 8)
+    if (K % w == 0) return w;
+  return K;
+}
+
+TurboGeom turbo_geom(int K) {
+  TurboGeom g{};
+  g.K = K;
+  g.W = window_len(K);
+  g.P = K / g.W;
+  g.Ppad = (g.P + 1) & ~1;
+  g.T = g.Ppad / 2;
+  g.plane = g.W * g.Ppad;
+  g.cb_elems = 3 * g.plane + 16;
+  return g;
+}
+
+int symbol_sz(int nof_prb) {
+  static const int lim[6] = {6, 15, 25, 50, 75, 110}, sz[6] = {128, 256, 512, 1024, 1536, 2048};
+  if (nof_prb <= 0) return -1;
+  for (int i = 0; i < 6; i++)
+    if (nof_prb <= lim[i]) return sz[i];
+  return -1;
+}
+
+uint32_t crc_bits(const uint8_t* bits, int n, uint32_t poly, int order) {
+  const uint32_t top = 1u << order;
+  uint32_t r = 0;
+  for (int i = 0; i < n + order; i++) {
+    r = (r << 1) | (i < n ? (bits[i] & 1u) : 0u);
+    if (r & top) r ^= poly;
+  }
+  return r & (top - 1);
+}
+
+static uint32_t gf_mul24(uint32_t a, uint32_t b, uint32_t poly) {
+  uint32_t r = 0;
+  for (int i = 23; i >= 0; i--) {
+    r <<= 1;
+    if (r & 0x1000000u) r ^= poly;
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r & 0xFFFFFFu;
+}
+
+uint32_t crc_xpow(uint32_t poly, uint64_t e) {
+  uint32_t result = 1, base = 2;    // polynomials "1" and "x"
+  while (e) {
+    if (e & 1) result = gf_mul24(result, base, poly);
+    base = gf_mul24(base, base, poly);
+    e >>= 1;
+  }
+  return result;
+}
+
+void gold_bits(uint32_t c_init, int n, uint8_t* c) {
+  // two 31-bit LFSRs advanced 1600 steps before the first output (36.211 7.2)
+  uint32_t x1 = 1, x2 = c_init & 0x7FFFFFFFu;
+  auto step = [&]() {
+    uint32_t n1 = ((x1 >> 3) ^ x1) & 1u;
+    uint32_t n2 = ((x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1) ^ x2) & 1u;
+    x1 = (x1 >> 1) | (n1 << 30);
+    x2 = (x2 >> 1) | (n2 << 30);
+  };
+  for (int i = 0; i < 1600; i++) step();
+  for (int i = 0; i < n; i++) {
+    c[i] = (uint8_t)((x1 ^ x2) & 1u);
+    step();
+  }
+}
+
+void gold_packed(uint32_t c_init, int n, std::vector<uint32_t>& w) {
+  std::vector<uint8_t> c(n);
+  gold_bits(c_init, n, c.data());
+  w.assign((n + 31) / 32, 0u);
+  for (int i = 0; i < n; i++) w[i >> 5] |= (uint32_t)c[i] << (i & 31);
+}
+
+bool cbsegm(int tbs, CbSegm* s) {
+  std::memset(s, 0, sizeof(*s));
+  if (tbs <= 0) return false;
+  const int B = tbs + 24;
+  int C = 1, Bp = B;
+  if (B > kMaxK) { C = (B + 6119) / 6120; Bp = B + 24 * C; }
+  const int need = (Bp + C - 1) / C;
+  int ip = 0;
+  while (ip < 188 && kQpp[ip][0] < need) ip++;
+  if (ip == 188) return false;
+  s->tbs = tbs; s->B = B; s->C = C; s->Kp = kQpp[ip][0]; s->Cp = C;
+  if (C > 1) {
+    if (ip == 0) return false;
+    s->Km = kQpp[ip - 1][0];
+    s->Cm = (C * s->Kp - Bp) / (s->Kp - s->Km);
+    s->Cp = C - s->Cm;
+  }
+  s->F = s->Cp * s->Kp + s->Cm * s->Km - Bp;
+  return true;
+}
+
+int cb_E(const CbSegm& s, int G, int qm, int nl, int r) {
+  const int Gp = G / (nl * qm), gamma = Gp % s.C;
+  return nl * qm * (r <= s.C - gamma - 1 ? Gp / s.C : (Gp + s.C - 1) / s.C);
+}
+
+int crs_offset(const CellCfg& cell, int port, int l) {
+  const int ls = l % 7;
+  if (ls != 0 && ls != 4) return -1;
+  const int v = ((ls == 0) == (port == 0)) ? 0 : 3;
+  return (v + cell.cell_id % 6) % 6;
+}
+
+void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_sign, std::vector<int8_t>& im_sign) {
+  const int ns = 2 * sf_idx + l / 7, ls = l % 7, M = 2 * cell.nof_prb;
+  const uint32_t c_init = 1024u * (7u * (ns + 1) + ls + 1) * (2u * cell.cell_id + 1) + 2u * cell.cell_id + 1u;
+  std::vector<uint8_t> c(440);
+  gold_bits(c_init, 440, c.data());
+  re_sign.resize(M); im_sign.resize(M);
+  for (int m = 0; m < M; m++) {
+    const int mp = m + 110 - cell.nof_prb;
+    re_sign[m] = c[2 * mp] ? -1 : 1;
+    im_sign[m] = c[2 * mp + 1] ? -1 : 1;
+  }
+}
+
+void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t>& re) {
+  re.clear();
+  const int nsc = 12 * cell.nof_prb;
+  const int first = cfg.cfi + (cell.nof_prb <= 10 ? 1 : 0);
+  const int mid_lo = nsc / 2 - 36, mid_hi = nsc / 2 + 36;
+  for (int l = first; l < 14; l++) {
+    const int o0 = crs_offset(cell, 0, l);
+    const int o1 = (cell.nof_ports > 1) ? crs_offset(cell, 1, l) : -1;
+    bool central_reserved = ((cfg.sf_idx == 0 || cfg.sf_idx == 5) && (l == 5 || l == 6)) ||
+                            (cfg.sf_idx == 0 && l >= 7 && l <= 10);
+    for (int prb = 0; prb < cell.nof_prb; prb++) {
+      if (!cfg.prb_mask[prb]) continue;
+      for (int k = 12 * prb; k < 12 * prb + 12; k++) {
+        if (o0 >= 0 && (k % 6 == o0 || k % 6 == o1)) continue;
+        if (central_reserved && k >= mid_lo && k < mid_hi) continue;
+        re.push_back(l * nsc + k);
+      }
+    }
+  }
+}
+
+void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos) {
+  int f1 = 0, f2 = 0;
+  qpp_params(g.K, &f1, &f2);
+  pos.assign(g.plane, 0);
+  for (int j = 0; j < g.Ppad; j++)
+    for (int i = 0; i < g.W; i++) {
+      const int e = i * g.Ppad + j;
+      if (j >= g.P) { pos[e] = (uint16_t)e; continue; }     // padding column maps onto itself
+      const int64_t k = (int64_t)j * g.W + i;
+      const int n = (int)((f1 * k + (int64_t)f2 * k * k) % g.K);
+      pos[e] = (uint16_t)((n % g.W) * g.Ppad + n / g.W);
+    }
+}
+
+void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& U, std::vector<uint32_t>& V) {
+  U.resize(g.W); V.assign(g.Ppad, 0);
+  for (int i = 0; i < g.W; i++) U[i] = crc_xpow(poly, (uint64_t)(g.W - 1 - i + 24));
+  for (int j = 0; j < g.P; j++) V[j] = crc_xpow(poly, (uint64_t)(g.P - 1 - j) * g.W);
+}
+
+int tcb_offset(const TurboGeom& g, int triple_index) {
+  const int k = triple_index / 3, stream = triple_index % 3;
+  if (k < g.K) return stream * g.plane + (k % g.W) * g.Ppad + k / g.W;
+  return 3 * g.plane + (triple_index - 3 * g.K);      // 12 tail values in srsLTE order
+}
+
+int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& tab) {
+  static const uint8_t colperm[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                      1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+  const int D = g.K + 4, R = (D + 31) / 32, Kpi = 32 * R, ND = Kpi - D, Kw = 3 * Kpi;
+  const int k0 = R * (2 * ((Kw + 8 * R - 1) / (8 * R)) * rv + 2);
+  tab.assign(g.cb_elems, 0xFFFF);
+  for (int k = 0; k < F; k++) { tab[tcb_offset(g, 3 * k)] = 0xFFFE; tab[tcb_offset(g, 3 * k + 1)] = 0xFFFE; }
+  int n = 0;
+  for (int step = 0; step < Kw; step++) {
+    const int j = (k0 + step) % Kw;
+    int stream, col_pos;
+    if (j < Kpi) { stream = 0; col_pos = j; } else { stream = 1 + ((j - Kpi) & 1); col_pos = (j - Kpi) >> 1; }
+    const int row = col_pos % R, col = col_pos / R;
+    const int y = (stream < 2) ? row * 32 + colperm[col] : (colperm[col] + 32 * row + 1) % Kpi;
+    const int d = y - ND;
+    if (d < 0 || (stream < 2 && d < F)) continue;
+    tab[tcb_offset(g, 3 * d + stream)] = (uint16_t)n++;
+  }
+  return n;
+}
+
+void fft_twiddles(int n, std::vector<float>& tw) {
+  tw.resize(n);
+  for (int k = 0; k < n / 2; k++) {
+    const double a = -2.0 * M_PI * (double)k / (double)n;
+    float re = (float)std::cos(a), im = (float)std::sin(a);
+    if ((4 * k) % n == 0) { re = (4 * k / n == 0) ? 1.0f : 0.0f; im = (4 * k / n == 0) ? 0.0f : -1.0f; }
+    tw[2 * k] = re; tw[2 * k + 1] = im;
+  }
+}
+
+}  // namespace srsue

@@ -1,0 +1,77 @@
+// lte_tables.h -- host-side LTE tables and derived look-up tables for libsrsue_gpu.
+//
+// Everything here is integer bookkeeping that srsLTE performs inside srslte_ue_dl_cfg_grant /
+// srslte_pdsch_init / srslte_tdec_init (called from /root/reference/ue/src/phy/phch_worker.cc:74,337);
+// the results are uploaded once per (cell, grant shape) or per code-block size and cached on the device.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace srsue {
+
+constexpr int kMaxK = 6144;
+constexpr int kTdC = 511;       // clamp of channel LLRs at the decoder input / soft-buffer saturation
+constexpr int kTdE = 2047;      // clamp of extrinsic LLRs
+constexpr int kTdInf = 10000;   // finite minus-infinity of known trellis states
+constexpr uint32_t kCrc24A = 0x1864CFBu, kCrc24B = 0x1800063u;
+
+struct CellCfg { int nof_prb, nof_ports, cell_id; };
+
+struct PdschCfg {
+  int sf_idx, cfi, rnti, qm, tbs, rv, tm, nof_prb_alloc;
+  uint8_t prb_mask[110];
+};
+
+struct CbSegm { int tbs, B, C, Kp, Km, Cp, Cm, F; };
+
+// Geometry of the windowed decoder for one code-block size (oracle/SPEC.md 7.3) and of the
+// device-native decoder-input layout ("tcb"): three planes sys/par1/par2 of W x Ppad int16, element
+// (window j, step i) at i*Ppad + j, followed by 16 int16 holding the 12 tail values.
+struct TurboGeom {
+  int K, W, P, Ppad, T;   // T = Ppad / 2 threads per code block
+  int plane;              // W * Ppad
+  int cb_elems;           // 3 * plane + 16
+};
+
+bool qpp_params(int K, int* f1, int* f2);
+int qpp_index(int K);                       // row in the table, -1 if K is not a valid size
+int qpp_K(int idx);
+int window_len(int K);
+TurboGeom turbo_geom(int K);
+int symbol_sz(int nof_prb);
+inline int cp_len(int nfft, int l) { return ((l % 7) == 0 ? 160 : 144) * nfft / 2048; }
+
+uint32_t crc_bits(const uint8_t* bits, int n, uint32_t poly, int order);
+// x^e mod g(x) for the 24-bit CRC polynomials
+uint32_t crc_xpow(uint32_t poly, uint64_t e);
+
+void gold_bits(uint32_t c_init, int n, uint8_t* c);
+// packed LSB-first: bit i of the sequence is (w[i/32] >> (i%32)) & 1
+void gold_packed(uint32_t c_init, int n, std::vector<uint32_t>& w);
+
+bool cbsegm(int tbs, CbSegm* s);
+inline int cb_len(const CbSegm& s, int r) { return r < s.Cm ? s.Km : s.Kp; }
+int cb_E(const CbSegm& s, int G, int qm, int nl, int r);
+
+// ordered PDSCH resource elements as indices l*nsc + k into the subframe grid
+void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t>& re);
+// CRS of one OFDM symbol: first pilot offset for `port` (-1 if none) and the +-1 signs of re/im
+int crs_offset(const CellCfg& cell, int port, int l);
+void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_sign, std::vector<int8_t>& im_sign);
+
+// DEC2 access table: for trellis step i of window j (entry i*Ppad + j) the tcb position of pi(j*W+i)
+void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos);
+// CRC helpers for the per-window parallel CRC: U[i] = x^(W-1-i+24) mod g, V[j] = x^((P-1-j)W) mod g
+void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& U, std::vector<uint32_t>& V);
+
+// Rate de-matching gather table for one (K, F, rv): for every element m of the tcb buffer
+// (cb_elems entries) the first circular-buffer read index n in [0, N) that lands on it, 0xFFFF if
+// none (padding), 0xFFFE for filler positions.  Returns N (number of non-null positions).
+int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& tab);
+
+// offset of decoder-input element (srsLTE triples index 3k+stream, k < K+4) inside the tcb buffer
+int tcb_offset(const TurboGeom& g, int triple_index);
+
+void fft_twiddles(int n, std::vector<float>& tw /* re,im pairs, n/2 entries */);
+
+}  // namespace srsue

@@ -1,0 +1,440 @@
+// srslte_shim.cc -- srsLTE-shaped C entry points (include/srsue_gpu/srslte_compat.h) over the batch API
+// with a batch of one subframe.  Mirrors the call sequence of phch_worker::work_imp
+// (/root/reference/ue/src/phy/phch_worker.cc:132-243): decode_fft_estimate -> cfg_grant ->
+// pdsch_decode_rnti, with MAC owning the soft buffer and the payload pointer
+// (/root/reference/ue/src/mac/dl_harq.cc:216-279).  All buffers crossing this boundary are caller-owned
+// HOST memory; device state is private.  No CPU fallback: without a usable GPU every call fails.
+#define SRSUE_GPU_PLAIN_CF 1
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lte_tables.h"
+#include "srsue_gpu/srslte_compat.h"
+
+using namespace srsue;
+
+namespace {
+
+std::mutex g_mu;
+srsue_gpu_ctx_t* g_ctx = nullptr;
+
+srsue_gpu_ctx_t* shared_ctx() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_ctx) {
+    const char* dev = getenv("SRSUE_GPU_DEVICE");
+    if (srsue_gpu_ctx_create(&g_ctx, dev ? atoi(dev) : 0) != 0) {
+      fprintf(stderr, "libsrsue_gpu: %s\n", srsue_gpu_last_error());
+      g_ctx = nullptr;
+    }
+  }
+  return g_ctx;
+}
+
+struct SbShadow {
+  int16_t* d_buf = nullptr;
+  size_t elems = 0;
+  int valid_tbs = 0;      // 0: empty (reset); otherwise the TBS whose LLRs are accumulated
+};
+
+struct UeDlGpu {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  srsue_gpu_cell_t cell{};
+  int nsc = 0, sf_len = 0;
+  uint32_t cfi = 1;
+  srsue_gpu_pdsch_plan_t* front[10] = {nullptr};
+  std::map<std::string, srsue_gpu_pdsch_plan_t*> plans;
+  srsue_gpu_cf_t *d_iq = nullptr, *d_sf = nullptr, *d_ce = nullptr;
+  float* d_meas = nullptr;
+  uint8_t* d_payload = nullptr;
+  int32_t* d_tb_status = nullptr;
+  bool dev_valid = false;           // d_sf/d_ce hold what q->sf_symbols/q->ce mirror
+  const void* h_sf = nullptr;       // addresses of those host mirrors
+  const void* h_ce[SRSLTE_MAX_PORTS] = {nullptr};
+  bool have_grant = false;
+  uint32_t grant_cfi = 1, grant_rv = 0;
+  srslte_ra_dl_grant_t grant{};
+  cudaStream_t stream = nullptr;
+};
+
+int to_gpu_cfg(const srslte_cell_t& cell, const srslte_pdsch_cfg_t* cfg, uint16_t rnti, srsue_gpu_pdsch_cfg_t* out) {
+  std::memset(out, 0, sizeof(*out));
+  out->sf_idx = (int)cfg->sf_idx;
+  out->cfi = (int)cfg->nbits.lstart - (cell.nof_prb <= 10 ? 1 : 0);
+  out->rnti = rnti;
+  out->qm = (int)cfg->grant.Qm;
+  out->tbs = cfg->grant.mcs.tbs;
+  out->rv = (int)cfg->rv;
+  out->tm = cell.nof_ports == 1 ? 1 : 2;      // srsLTE: single antenna port or transmit diversity
+  int n = 0;
+  for (uint32_t i = 0; i < cell.nof_prb; i++) {
+    if (cfg->grant.prb_idx[0][i] != cfg->grant.prb_idx[1][i]) return -1;   // slot hopping not supported
+    out->prb_mask[i] = cfg->grant.prb_idx[0][i] ? 1 : 0;
+    n += out->prb_mask[i];
+  }
+  out->nof_prb_alloc = n;
+  return 0;
+}
+
+srsue_gpu_pdsch_plan_t* get_plan(UeDlGpu* u, const srsue_gpu_pdsch_cfg_t& c) {
+  std::string key(reinterpret_cast<const char*>(&c), sizeof(c));
+  auto it = u->plans.find(key);
+  if (it != u->plans.end()) return it->second;
+  if (u->plans.size() >= 64) {               // bounded cache: grants repeat in practice
+    for (auto& kv : u->plans) srsue_gpu_pdsch_plan_destroy(kv.second);
+    u->plans.clear();
+  }
+  srsue_gpu_pdsch_plan_t* p = nullptr;
+  if (srsue_gpu_pdsch_plan_create(u->ctx, &u->cell, &c, 1, &p) != 0) return nullptr;
+  u->plans[key] = p;
+  return p;
+}
+
+int sb_total_elems(uint32_t max_cb) { return (int)max_cb * (3 * kMaxK + 16); }
+
+}  // namespace
+
+extern "C" {
+
+int srslte_symbol_sz(uint32_t nof_prb) { return symbol_sz((int)nof_prb); }
+
+void* srslte_vec_malloc(uint32_t size) {
+  void* p = nullptr;
+  if (posix_memalign(&p, 64, size ? size : 64)) return nullptr;
+  return p;
+}
+void srslte_vec_free(void* p) { free(p); }
+
+// ---- UE DL ------------------------------------------------------------------------------------------
+int srslte_ue_dl_init(srslte_ue_dl_t* q, srslte_cell_t cell) {
+  if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  if (symbol_sz((int)cell.nof_prb) < 0 || cell.nof_ports < 1 || cell.nof_ports > 2 || cell.cp != SRSLTE_CP_NORM)
+    return SRSLTE_ERROR_INVALID_INPUTS;
+  srsue_gpu_ctx_t* ctx = shared_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  auto* u = new UeDlGpu();
+  u->ctx = ctx;
+  u->cell = srsue_gpu_cell_t{(int)cell.nof_prb, (int)cell.nof_ports, (int)cell.id};
+  u->nsc = 12 * (int)cell.nof_prb;
+  u->sf_len = 15 * symbol_sz((int)cell.nof_prb);
+  const size_t grid = (size_t)14 * u->nsc;
+  bool ok = cudaMalloc((void**)&u->d_iq, u->sf_len * sizeof(srsue_gpu_cf_t)) == cudaSuccess &&
+            cudaMalloc((void**)&u->d_sf, grid * sizeof(srsue_gpu_cf_t)) == cudaSuccess &&
+            cudaMalloc((void**)&u->d_ce, grid * cell.nof_ports * sizeof(srsue_gpu_cf_t)) == cudaSuccess &&
+            cudaMalloc((void**)&u->d_meas, 5 * sizeof(float)) == cudaSuccess &&
+            cudaMalloc((void**)&u->d_payload, 19200) == cudaSuccess &&     /* demux.h:60: 150*1024/8 bytes */
+            cudaMalloc((void**)&u->d_tb_status, 4 * sizeof(int32_t)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking) == cudaSuccess;
+  q->gpu = u;
+  q->cell = cell;
+  q->pdsch.cell = cell; q->pdsch.gpu = u; q->pdsch.dl_sch.max_iterations = 4;   /* ue.conf.example:83 */
+  q->chest.cell = cell; q->chest.gpu = u;
+  q->sf_symbols = (cf_t*)srslte_vec_malloc((uint32_t)(grid * sizeof(cf_t)));
+  for (uint32_t p = 0; p < cell.nof_ports; p++) q->ce[p] = (cf_t*)srslte_vec_malloc((uint32_t)(grid * sizeof(cf_t)));
+  u->h_sf = q->sf_symbols;
+  for (uint32_t p = 0; p < cell.nof_ports; p++) u->h_ce[p] = q->ce[p];
+  ok = ok && q->sf_symbols && q->ce[0] && srslte_softbuffer_rx_init(&q->softbuffer, cell.nof_prb) == 0;
+  if (!ok) { srslte_ue_dl_free(q); return SRSLTE_ERROR; }
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_ue_dl_free(srslte_ue_dl_t* q) {
+  if (!q) return;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  if (u) {
+    for (auto& f : u->front) srsue_gpu_pdsch_plan_destroy(f);
+    for (auto& kv : u->plans) srsue_gpu_pdsch_plan_destroy(kv.second);
+    cudaFree(u->d_iq); cudaFree(u->d_sf); cudaFree(u->d_ce); cudaFree(u->d_meas); cudaFree(u->d_payload); cudaFree(u->d_tb_status);
+    if (u->stream) cudaStreamDestroy(u->stream);
+    delete u;
+  }
+  srslte_vec_free(q->sf_symbols);
+  for (int p = 0; p < SRSLTE_MAX_PORTS; p++) srslte_vec_free(q->ce[p]);
+  srslte_softbuffer_rx_free(&q->softbuffer);
+  std::memset(q, 0, sizeof(*q));
+}
+
+void srslte_ue_dl_set_rnti(srslte_ue_dl_t* q, uint16_t rnti) {
+  // called from the MAC thread while workers run (phy.cc:253-257): a plain field write; the scrambling
+  // sequence of the rnti is generated lazily when a plan for it is first built
+  if (q) { q->current_rnti = rnti; q->pdsch.rnti = rnti; }
+}
+
+void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t* q, uint32_t cfi) {
+  if (q && q->gpu && cfi >= 1 && cfi <= 3) static_cast<UeDlGpu*>(q->gpu)->cfi = cfi;
+}
+
+int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf_idx, uint32_t* cfi) {
+  if (!q || !q->gpu || !input || sf_idx > 9) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  if (!u->front[sf_idx]) {
+    srsue_gpu_pdsch_cfg_t c{};
+    c.sf_idx = (int)sf_idx; c.cfi = 1; c.qm = 2; c.tm = u->cell.nof_ports == 1 ? 1 : 2; c.tbs = 0;
+    if (srsue_gpu_pdsch_plan_create(u->ctx, &u->cell, &c, 1, &u->front[sf_idx]) != 0) return SRSLTE_ERROR;
+  }
+  srsue_gpu_pdsch_plan_t* fp = u->front[sf_idx];
+  const size_t grid = (size_t)14 * u->nsc;
+  // the IQ buffer is reused by the caller right after we return (phch_worker.cc:254 vs :559,610,641):
+  // it is fully consumed (H2D) before the synchronise below
+  if (cudaMemcpyAsync(u->d_iq, input, u->sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  if (srsue_gpu_ofdm_rx(fp, 1, u->d_iq, u->d_sf, u->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_chest(fp, 1, u->d_sf, u->d_ce, u->d_meas, u->stream)) return SRSLTE_ERROR;
+  float meas[5];
+  cudaMemcpyAsync(q->sf_symbols, u->d_sf, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
+  for (int p = 0; p < u->cell.nof_ports; p++)
+    cudaMemcpyAsync(q->ce[p], u->d_ce + (size_t)p * grid, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
+  cudaMemcpyAsync(meas, u->d_meas, sizeof(meas), cudaMemcpyDeviceToHost, u->stream);
+  if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  q->chest.noise_estimate = meas[0]; q->chest.rsrp = meas[1]; q->chest.rssi = meas[2]; q->chest.rsrq = meas[3];
+  u->dev_valid = true;
+  if (cfi) *cfi = u->cfi;
+  return SRSLTE_SUCCESS;
+}
+
+int srslte_ue_dl_cfg_grant(srslte_ue_dl_t* q, srslte_ra_dl_grant_t* grant, uint32_t cfi, uint32_t sf_idx, uint32_t rvidx) {
+  if (!q || !grant || cfi < 1 || cfi > 3 || sf_idx > 9 || rvidx > 3) return SRSLTE_ERROR_INVALID_INPUTS;
+  srslte_pdsch_cfg_t* c = &q->pdsch_cfg;
+  std::memset(c, 0, sizeof(*c));
+  c->grant = *grant;
+  c->rv = rvidx;
+  c->sf_idx = sf_idx;
+  c->nbits.lstart = cfi + (q->cell.nof_prb <= 10 ? 1 : 0);
+  c->nbits.nof_symb = 14 - c->nbits.lstart;
+  CellCfg cell{(int)q->cell.nof_prb, (int)q->cell.nof_ports, (int)q->cell.id};
+  PdschCfg pc{};
+  pc.sf_idx = (int)sf_idx; pc.cfi = (int)cfi;
+  for (uint32_t i = 0; i < q->cell.nof_prb; i++) pc.prb_mask[i] = grant->prb_idx[0][i] ? 1 : 0;
+  std::vector<int32_t> re;
+  pdsch_re_list(cell, pc, re);
+  c->nbits.nof_re = (uint32_t)re.size();
+  c->nbits.nof_bits = c->nbits.nof_re * grant->Qm;
+  if (grant->mcs.tbs > 0) {
+    CbSegm s;
+    if (!cbsegm(grant->mcs.tbs, &s)) return SRSLTE_ERROR;
+    c->cb_segm.F = s.F; c->cb_segm.C = s.C; c->cb_segm.K1 = s.Kp; c->cb_segm.K2 = s.Km;
+    c->cb_segm.C1 = s.Cp; c->cb_segm.C2 = s.Cm; c->cb_segm.tbs = s.tbs;
+  }
+  return SRSLTE_SUCCESS;
+}
+
+int srsue_gpu_ue_dl_set_grant(srslte_ue_dl_t* q, const srslte_ra_dl_grant_t* grant, uint32_t cfi, uint32_t rvidx) {
+  if (!q || !q->gpu || !grant) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  u->grant = *grant; u->grant_cfi = cfi; u->grant_rv = rvidx; u->have_grant = true; u->cfi = cfi;
+  return SRSLTE_SUCCESS;
+}
+
+int srslte_pdsch_decode_rnti(srslte_pdsch_t* q, srslte_pdsch_cfg_t* cfg, srslte_softbuffer_rx_t* softbuffer, cf_t* sf_symbols,
+                             cf_t* ce[SRSLTE_MAX_PORTS], float noise_estimate, uint16_t rnti, uint8_t* data) {
+  if (!q || !q->gpu || !cfg || !softbuffer || !sf_symbols || !ce || !data) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  auto* sh = static_cast<SbShadow*>(softbuffer->gpu_shadow);
+  if (!sh || cfg->grant.mcs.tbs <= 0) return SRSLTE_ERROR_INVALID_INPUTS;
+  srsue_gpu_pdsch_cfg_t c;
+  if (to_gpu_cfg(q->cell, cfg, rnti, &c)) return SRSLTE_ERROR_INVALID_INPUTS;
+  srsue_gpu_pdsch_plan_t* p = get_plan(u, c);
+  if (!p) return SRSLTE_ERROR;
+  srsue_gpu_plan_info_t info;
+  srsue_gpu_pdsch_plan_info(p, &info);
+  if ((size_t)info.sb_sf_stride > sh->elems || info.payload_stride > 19200) return SRSLTE_ERROR;
+  const size_t grid = (size_t)14 * u->nsc;
+  // reuse the device copies of this subframe's grid when the caller hands back our own mirrors
+  // (phch_worker.cc:347-348 passes ue_dl.sf_symbols / ue_dl.ce), otherwise upload what we were given
+  bool own = u->dev_valid && sf_symbols == u->h_sf;
+  for (int pt = 0; pt < u->cell.nof_ports; pt++) own = own && (ce[pt] == u->h_ce[pt]);
+  if (!own) {
+    u->dev_valid = false;
+    cudaMemcpyAsync(u->d_sf, sf_symbols, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+    for (int pt = 0; pt < u->cell.nof_ports; pt++)
+      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+  }
+  const int accumulate = (sh->valid_tbs == c.tbs) ? 1 : 0;
+  if (srsue_gpu_pdsch_llr(p, 1, u->d_sf, u->d_ce, u->d_meas, noise_estimate, 0, accumulate, sh->d_buf, nullptr, nullptr, u->stream))
+    return SRSLTE_ERROR;
+  sh->valid_tbs = c.tbs;
+  const int max_it = q->dl_sch.max_iterations ? (int)q->dl_sch.max_iterations : 4;
+  if (srsue_gpu_pdsch_turbo(p, 1, sh->d_buf, max_it, u->d_payload, u->d_tb_status, nullptr, u->stream)) return SRSLTE_ERROR;
+  int32_t st[4];
+  // payload must be complete before we return: MAC pushes it to the PDU queue next (dl_harq.cc:296-309)
+  cudaMemcpyAsync(data, u->d_payload, info.payload_stride, cudaMemcpyDeviceToHost, u->stream);
+  cudaMemcpyAsync(st, u->d_tb_status, sizeof(st), cudaMemcpyDeviceToHost, u->stream);
+  if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  q->dl_sch.nof_iterations = (uint32_t)st[2];
+  return st[0] ? SRSLTE_SUCCESS : SRSLTE_ERROR;
+}
+
+void srslte_sch_set_max_noi(srslte_sch_t* q, uint32_t max_iterations) { if (q) q->max_iterations = max_iterations; }
+uint32_t srslte_pdsch_last_noi(srslte_pdsch_t* q) { return q ? q->dl_sch.nof_iterations : 0; }
+
+int srslte_ue_dl_decode_rnti(srslte_ue_dl_t* q, cf_t* input, uint8_t* data, uint32_t tti, uint16_t rnti) {
+  if (!q || !q->gpu || !input || !data) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  uint32_t cfi = 0;
+  const uint32_t sf_idx = tti % 10;
+  int rc = srslte_ue_dl_decode_fft_estimate(q, input, sf_idx, &cfi);
+  if (rc < 0) return rc;
+  if (!u->have_grant) return 0;                       // no DCI for this rnti
+  rc = srslte_ue_dl_cfg_grant(q, &u->grant, u->grant_cfi, sf_idx, u->grant_rv);
+  if (rc) return rc;
+  if (u->grant_rv == 0) srslte_softbuffer_rx_reset(&q->softbuffer);
+  q->pkts_total++;
+  // srslte_ue_dl_decode uses the channel estimator's noise figure (srsUE's worker passes 0.01 instead)
+  rc = srslte_pdsch_decode_rnti(&q->pdsch, &q->pdsch_cfg, &q->softbuffer, q->sf_symbols, q->ce,
+                                srslte_chest_dl_get_noise_estimate(&q->chest), rnti, data);
+  if (rc == SRSLTE_SUCCESS) return q->pdsch_cfg.grant.mcs.tbs;
+  q->pkt_errors++;
+  return (rc == SRSLTE_ERROR) ? 0 : rc;
+}
+
+int srslte_ue_dl_decode(srslte_ue_dl_t* q, cf_t* input, uint8_t* data, uint32_t tti) {
+  return srslte_ue_dl_decode_rnti(q, input, data, tti, q ? q->current_rnti : 0);
+}
+
+// ---- channel estimator getters -----------------------------------------------------------------------
+float srslte_chest_dl_get_noise_estimate(srslte_chest_dl_t* q) { return q ? q->noise_estimate : 0.f; }
+float srslte_chest_dl_get_snr(srslte_chest_dl_t* q) { return (q && q->noise_estimate > 0.f) ? q->rsrp / q->noise_estimate : 0.f; }
+float srslte_chest_dl_get_rssi(srslte_chest_dl_t* q) { return q ? q->rssi : 0.f; }
+float srslte_chest_dl_get_rsrq(srslte_chest_dl_t* q) { return q ? q->rsrq : 0.f; }
+float srslte_chest_dl_get_rsrp(srslte_chest_dl_t* q) { return q ? q->rsrp : 0.f; }
+
+// ---- soft buffer ---------------------------------------------------------------------------------------
+int srslte_softbuffer_rx_init(srslte_softbuffer_rx_t* q, uint32_t nof_prb) {
+  if (!q || nof_prb == 0 || nof_prb > SRSLTE_MAX_PRB) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  if (!shared_ctx()) return SRSLTE_ERROR;
+  // largest transport block of the bandwidth: I_TBS 26 row of 36.213 Table 7.1.7.2.1-1 scales ~ 753.76 bits/PRB
+  const uint32_t max_tbs = (nof_prb >= 100) ? 75376u : (uint32_t)(nof_prb * 760u + 24u);
+  q->max_cb = (max_tbs + 24 + 6119) / 6120 + 1;
+  q->buffer_f = (int16_t**)calloc(q->max_cb, sizeof(int16_t*));
+  if (!q->buffer_f) return SRSLTE_ERROR;
+  for (uint32_t i = 0; i < q->max_cb; i++) {
+    q->buffer_f[i] = (int16_t*)srslte_vec_malloc(sizeof(int16_t) * (3 * kMaxK + 12));
+    if (!q->buffer_f[i]) { srslte_softbuffer_rx_free(q); return SRSLTE_ERROR; }
+    std::memset(q->buffer_f[i], 0, sizeof(int16_t) * (3 * kMaxK + 12));
+  }
+  auto* sh = new SbShadow();
+  sh->elems = (size_t)sb_total_elems(q->max_cb);
+  if (cudaMalloc((void**)&sh->d_buf, sh->elems * sizeof(int16_t)) != cudaSuccess) { delete sh; srslte_softbuffer_rx_free(q); return SRSLTE_ERROR; }
+  q->gpu_shadow = sh;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_softbuffer_rx_free(srslte_softbuffer_rx_t* q) {
+  if (!q) return;
+  if (q->buffer_f) {
+    for (uint32_t i = 0; i < q->max_cb; i++) srslte_vec_free(q->buffer_f[i]);
+    free(q->buffer_f);
+  }
+  auto* sh = static_cast<SbShadow*>(q->gpu_shadow);
+  if (sh) { cudaFree(sh->d_buf); delete sh; }
+  std::memset(q, 0, sizeof(*q));
+}
+
+void srslte_softbuffer_rx_reset(srslte_softbuffer_rx_t* q) {
+  // new data (dl_harq.cc:232): the next decode overwrites the device buffer instead of accumulating
+  if (!q) return;
+  auto* sh = static_cast<SbShadow*>(q->gpu_shadow);
+  if (sh) sh->valid_tbs = 0;
+  if (q->buffer_f)
+    for (uint32_t i = 0; i < q->max_cb; i++)
+      if (q->buffer_f[i]) std::memset(q->buffer_f[i], 0, sizeof(int16_t) * (3 * kMaxK + 12));
+}
+void srslte_softbuffer_rx_reset_tbs(srslte_softbuffer_rx_t* q, uint32_t) { srslte_softbuffer_rx_reset(q); }
+void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t) { srslte_softbuffer_rx_reset(q); }
+
+int srsue_gpu_softbuffer_rx_sync_host(srslte_softbuffer_rx_t* q, uint32_t tbs) {
+  if (!q || !q->gpu_shadow) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* sh = static_cast<SbShadow*>(q->gpu_shadow);
+  CbSegm s;
+  if (!cbsegm((int)tbs, &s) || (uint32_t)s.C > q->max_cb) return SRSLTE_ERROR_INVALID_INPUTS;
+  const int stride = std::max(turbo_geom(s.Kp).cb_elems, s.Cm ? turbo_geom(s.Km).cb_elems : 0);
+  srsue_gpu_ctx_t* ctx = shared_ctx();
+  int16_t* d_tmp = nullptr;
+  if (cudaMalloc((void**)&d_tmp, sizeof(int16_t) * (3 * kMaxK + 12)) != cudaSuccess) return SRSLTE_ERROR;
+  int rc = SRSLTE_SUCCESS;
+  for (int r = 0; r < s.C && rc == SRSLTE_SUCCESS; r++) {
+    const int K = cb_len(s, r);
+    if (srsue_gpu_tdec_export(ctx, sh->d_buf + (size_t)r * stride, 1, K, d_tmp, nullptr)) rc = SRSLTE_ERROR;
+    else if (cudaMemcpy(q->buffer_f[r], d_tmp, sizeof(int16_t) * (3 * K + 12), cudaMemcpyDeviceToHost) != cudaSuccess) rc = SRSLTE_ERROR;
+  }
+  cudaFree(d_tmp);
+  return rc;
+}
+
+// ---- turbo decoder object --------------------------------------------------------------------------------
+namespace {
+struct TdecGpu {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  std::vector<int16_t> input;     // copy of the block handed to srslte_tdec_iteration
+  uint32_t K = 0;
+};
+}
+
+int srslte_tdec_init(srslte_tdec_t* h, uint32_t max_long_cb) {
+  if (!h || max_long_cb == 0 || max_long_cb > kMaxK) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(h, 0, sizeof(*h));
+  srsue_gpu_ctx_t* ctx = shared_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  auto* g = new TdecGpu();
+  g->ctx = ctx;
+  h->gpu = g;
+  h->max_long_cb = max_long_cb;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_tdec_free(srslte_tdec_t* h) {
+  if (!h) return;
+  delete static_cast<TdecGpu*>(h->gpu);
+  std::memset(h, 0, sizeof(*h));
+}
+
+int srslte_tdec_reset(srslte_tdec_t* h, uint32_t long_cb) {
+  if (!h || !h->gpu || long_cb > h->max_long_cb || qpp_index((int)long_cb) < 0) return SRSLTE_ERROR_INVALID_INPUTS;
+  h->n_iter = 0;
+  static_cast<TdecGpu*>(h->gpu)->K = long_cb;
+  return SRSLTE_SUCCESS;
+}
+
+// The decoder state after n calls is a pure function of (input, n); the device decoder keeps no state
+// between launches, so iteration() records the request and decision*() runs the n iterations.
+void srslte_tdec_iteration(srslte_tdec_t* h, int16_t* input, uint32_t long_cb) {
+  if (!h || !h->gpu || !input) return;
+  auto* g = static_cast<TdecGpu*>(h->gpu);
+  g->K = long_cb;
+  g->input.assign(input, input + 3 * long_cb + 12);
+  h->n_iter++;
+}
+
+void srslte_tdec_decision_byte(srslte_tdec_t* h, uint8_t* output, uint32_t long_cb) {
+  if (!h || !h->gpu || !output) return;
+  auto* g = static_cast<TdecGpu*>(h->gpu);
+  if (g->input.empty() || g->K != long_cb || h->n_iter == 0) return;
+  int32_t st = 0;
+  if (srsue_gpu_tdec_run_all_host(g->ctx, g->input.data(), 1, (int)long_cb, (int)h->n_iter, 0, output, &st))
+    fprintf(stderr, "libsrsue_gpu: %s\n", srsue_gpu_last_error());
+}
+
+void srslte_tdec_decision(srslte_tdec_t* h, uint8_t* output, uint32_t long_cb) {
+  std::vector<uint8_t> packed(long_cb / 8);
+  srslte_tdec_decision_byte(h, packed.data(), long_cb);
+  for (uint32_t i = 0; i < long_cb; i++) output[i] = (packed[i >> 3] >> (7 - (i & 7))) & 1;
+}
+
+int srslte_tdec_run_all(srslte_tdec_t* h, int16_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb) {
+  if (!h || !h->gpu || !input || !output || nof_iterations == 0) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (srslte_tdec_reset(h, long_cb)) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* g = static_cast<TdecGpu*>(h->gpu);
+  int32_t st = 0;
+  if (srsue_gpu_tdec_run_all_host(g->ctx, input, 1, (int)long_cb, (int)nof_iterations, 0, output, &st)) return SRSLTE_ERROR;
+  h->n_iter = nof_iterations;
+  return SRSLTE_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+"""ctypes mirrors of include/srsue_gpu/srslte_compat.h for the tests (the C++ callers use the header)."""
+import ctypes as C
+
+
+class Cell(C.Structure):
+    _fields_ = [("nof_prb", C.c_uint32), ("nof_ports", C.c_uint32), ("bw_idx", C.c_uint32), ("id", C.c_uint32),
+                ("cp", C.c_int), ("phich_length", C.c_int), ("phich_resources", C.c_int)]
+
+
+class Mcs(C.Structure):
+    _fields_ = [("mod", C.c_int), ("tbs", C.c_int), ("idx", C.c_uint32)]
+
+
+class Grant(C.Structure):
+    _fields_ = [("prb_idx", (C.c_bool * 110) * 2), ("nof_prb", C.c_uint32), ("Qm", C.c_uint32), ("mcs", Mcs)]
+
+
+class CbSegm(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("F", "C", "K1", "K2", "C1", "C2", "tbs")]
+
+
+class NBits(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("lstart", "nof_symb", "nof_bits", "nof_re")]
+
+
+class PdschCfg(C.Structure):
+    _fields_ = [("cb_segm", CbSegm), ("grant", Grant), ("nbits", NBits), ("rv", C.c_uint32), ("sf_idx", C.c_uint32)]
+
+
+class SoftBuffer(C.Structure):
+    _fields_ = [("max_cb", C.c_uint32), ("buffer_f", C.POINTER(C.POINTER(C.c_int16))), ("gpu_shadow", C.c_void_p)]
+
+
+class Sch(C.Structure):
+    _fields_ = [("max_iterations", C.c_uint32), ("nof_iterations", C.c_uint32)]
+
+
+class Pdsch(C.Structure):
+    _fields_ = [("cell", Cell), ("rnti", C.c_uint16), ("dl_sch", Sch), ("gpu", C.c_void_p)]
+
+
+class Chest(C.Structure):
+    _fields_ = [("cell", Cell), ("noise_estimate", C.c_float), ("rsrp", C.c_float), ("rssi", C.c_float),
+                ("rsrq", C.c_float), ("gpu", C.c_void_p)]
+
+
+class Pdcch(C.Structure):
+    _fields_ = [("unused", C.c_int)]
+
+
+class DciLocation(C.Structure):
+    _fields_ = [("L", C.c_uint32), ("ncce", C.c_uint32)]
+
+
+class UeDl(C.Structure):
+    _fields_ = [("pdcch", Pdcch), ("pdsch", Pdsch), ("chest", Chest), ("pdsch_cfg", PdschCfg), ("softbuffer", SoftBuffer),
+                ("cell", Cell), ("sf_symbols", C.c_void_p), ("ce", C.c_void_p * 4), ("current_rnti", C.c_uint16),
+                ("last_location", DciLocation), ("last_n_cce", C.c_uint32), ("pkt_errors", C.c_uint64),
+                ("pkts_total", C.c_uint64), ("nof_detected", C.c_uint64), ("gpu", C.c_void_p)]
+
+
+class Tdec(C.Structure):
+    _fields_ = [("max_long_cb", C.c_uint32), ("n_iter", C.c_uint32), ("gpu", C.c_void_p)]
+
+
+def make_grant(nof_prb, qm, tbs, prbs=None):
+    g = Grant()
+    for p in (range(nof_prb) if prbs is None else prbs):
+        g.prb_idx[0][p] = True
+        g.prb_idx[1][p] = True
+    g.nof_prb = nof_prb if prbs is None else len(list(prbs))
+    g.Qm = qm
+    g.mcs.mod = {2: 1, 4: 2, 6: 3}[qm]
+    g.mcs.tbs = tbs
+    g.mcs.idx = 0
+    return g

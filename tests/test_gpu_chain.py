@@ -1,0 +1,120 @@
+"""Whole-chain parity through the C ABI: decoded transport blocks, CRC verdicts and iteration counts
+against the CPU oracle, for the PDSCH configs of BASELINE.json, device-resident and host-buffer calls."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _taps():
+    rng = np.random.default_rng(77)
+    taps = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    return taps / np.sqrt((abs(taps) ** 2).sum(1, keepdims=True))
+
+
+CASES = {
+    "cfg1_1.4MHz_mcs0": dict(prb=6, ports=1, qm=2, tbs=152, tm=1, snr=10.0, taps=False, n=4, noise_mode=1),
+    "cfg2_20MHz_mcs28": dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, snr=30.0, taps=False, n=4, noise_mode=0),
+    "cfg2_waterfall": dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, snr=19.0, taps=False, n=6, noise_mode=0),
+    "cfg3_tm2_mcs16": dict(prb=100, ports=2, qm=4, tbs=30576, tm=2, snr=15.0, taps=True, n=4, noise_mode=1),
+    "filler_and_two_K": dict(prb=50, ports=1, qm=4, tbs=6208, tm=1, snr=18.0, taps=False, n=3, noise_mode=0),
+    "low_snr_fail": dict(prb=25, ports=1, qm=6, tbs=11448, tm=1, snr=3.0, taps=False, n=3, noise_mode=0),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_chain_matches_oracle(gpu, oracle, name):
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    c = CASES[name]
+    taps = _taps() if c["taps"] else None
+    ocell = o.make_cell(c["prb"], c["ports"], 1)
+    ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=c["qm"], tbs=c["tbs"], tm=c["tm"])
+    n = c["n"]
+    iq = np.stack([o.gen_subframe(ocell, ocfg, 20000 + i, c["snr"], taps)[1] for i in range(n)])
+    sent = [o.gen_subframe(ocell, ocfg, 20000 + i, c["snr"], taps)[0] for i in range(n)]
+    cell = sg.make_cell(c["prb"], c["ports"], 1)
+    cfg = sg.make_cfg(cell, sf_idx=1, cfi=1, qm=c["qm"], tbs=c["tbs"], tm=c["tm"])
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+    d_pl = torch.zeros((n, I.payload_stride), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+    plan.decode_batch(n, d_iq, 0.01, c["noise_mode"], 4, d_pl, d_st, d_meas=d_meas)
+    torch.cuda.synchronize()
+    pl_g, st_g = d_pl.cpu().numpy(), d_st.cpu().numpy()
+    # host-buffer entry point (what the offline driver calls)
+    h_pl = np.zeros((n, I.payload_stride), np.uint8)
+    h_st = np.zeros((n, 4), np.int32)
+    h_meas = np.zeros((n, 5), np.float32)
+    plan.decode_batch_host(n, iq, 0.01, c["noise_mode"], 4, h_pl, h_st, h_meas)
+    assert np.array_equal(h_pl, pl_g) and np.array_equal(h_st, st_g)
+    n_ok = 0
+    for i in range(n):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, c["noise_mode"], 4)
+        assert (st_g[i, 0] == 1) == (rc == 0), "CRC verdict differs (sf %d)" % i
+        assert np.array_equal(pl_g[i], pl), "transport block differs from oracle (sf %d)" % i
+        assert st_g[i, 2] == avg
+        assert np.allclose(h_meas[i], meas, rtol=1e-4)
+        if rc == 0:
+            n_ok += 1
+            assert np.array_equal(pl, sent[i])
+    if name == "low_snr_fail":
+        assert n_ok == 0
+    elif name != "cfg2_waterfall":
+        assert n_ok == n
+    plan.close()
+
+
+def test_srslte_shaped_entry_points(gpu, oracle):
+    """phch_worker's call sequence through the srsLTE-compatible symbols (host buffers, batch of one)."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, Grant, SoftBuffer, make_grant
+    prb, qm, tbs = 25, 4, 4968
+    ocell = o.make_cell(prb, 1, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=qm, tbs=tbs)
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 321, 20.0)
+    q = UeDl()
+    cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=0)
+    assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+    L.srslte_ue_dl_set_rnti(C.byref(q), 0x1234)
+    L.srslte_sch_set_max_noi(C.byref(q.pdsch.dl_sch), 4)
+    sb = SoftBuffer()
+    assert L.srslte_softbuffer_rx_init(C.byref(sb), prb) == 0
+    L.srslte_softbuffer_rx_reset(C.byref(sb))
+    cfi = C.c_uint32(0)
+    assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), iq.ctypes.data_as(C.c_void_p), 1, C.byref(cfi)) == 0
+    assert cfi.value == 1
+    grant = make_grant(prb, qm, tbs)
+    assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), 1, 1, 0) == 0
+    assert q.pdsch_cfg.nbits.nof_re == len(o.pdsch_re_list(ocell, ocfg))
+    payload = np.zeros(tbs // 8, np.uint8)
+    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), q.sf_symbols, q.ce,
+                                     C.c_float(0.01), C.c_uint16(0x1234), payload.ctypes.data_as(C.c_void_p))
+    rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
+    assert ret == 0 and rc == 0
+    assert np.array_equal(payload, pl) and np.array_equal(payload, tb)
+    assert L.srslte_pdsch_last_noi(C.byref(q.pdsch)) == avg
+    L.srslte_chest_dl_get_snr.restype = C.c_float
+    assert abs(L.srslte_chest_dl_get_snr(C.byref(q.chest)) - meas[4]) <= 1e-4 * meas[4]
+    # host mirrors of the grid are what the oracle computes
+    nsc = 12 * prb
+    sf_h = np.ctypeslib.as_array(C.cast(q.sf_symbols, C.POINTER(C.c_float)), shape=(14 * nsc * 2,)).view(np.complex64)
+    assert np.array_equal(sf_h, o.ofdm_rx(prb, iq))
+    # srslte_tdec object
+    from tests.srslte_ctypes import Tdec
+    h = Tdec()
+    K = 1024
+    c, llr = o.gen_turbo_llrs(K, 5, ebn0_db=1.5)
+    assert L.srslte_tdec_init(C.byref(h), 6144) == 0
+    out = np.zeros(K // 8, np.uint8)
+    assert L.srslte_tdec_run_all(C.byref(h), llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 4, K) == 0
+    assert np.array_equal(np.unpackbits(out), o.tdec(llr, K, 4, 0)[0])
+    L.srslte_tdec_free(C.byref(h))
+    L.srslte_softbuffer_rx_free(C.byref(sb))
+    L.srslte_ue_dl_free(C.byref(q))
