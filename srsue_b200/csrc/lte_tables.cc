@@ -190,8 +190,10 @@ void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos) {
   pos.assign(g.plane, 0);
   for (int j = 0; j < g.Ppad; j++)
     for (int i = 0; i < g.W; i++) {
-      const int e = i * g.Ppad + j;
-      if (j >= g.P) { pos[e] = (uint16_t)e; continue; }     // padding column maps onto itself
+      // entry order follows the thread-private [group][thread][8 steps] x {window 2t, 2t+1} layout;
+      // the value is a position in the shared exchange array A, which is [W][Ppad]
+      const int e = ((((i / 8) * g.T + j / 2) * 8 + i % 8) * 2) + (j & 1);
+      if (j >= g.P) { pos[e] = (uint16_t)(i * g.Ppad + j); continue; }     // padding column maps onto itself
       const int64_t k = (int64_t)j * g.W + i;
       const int n = (int)((f1 * k + (int64_t)f2 * k * k) % g.K);
       pos[e] = (uint16_t)((n % g.W) * g.Ppad + n / g.W);
@@ -206,7 +208,10 @@ void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& 
 
 int tcb_offset(const TurboGeom& g, int triple_index) {
   const int k = triple_index / 3, stream = triple_index % 3;
-  if (k < g.K) return stream * g.plane + (k % g.W) * g.Ppad + k / g.W;
+  if (k < g.K) {
+    const int j = k / g.W, i = k % g.W;       // window, step
+    return stream * g.plane + ((((i / 8) * g.T + j / 2) * 8 + i % 8) * 2) + (j & 1);
+  }
   return 3 * g.plane + (triple_index - 3 * g.K);      // 12 tail values in srsLTE order
 }
 

@@ -25,8 +25,10 @@ struct PdschCfg {
 struct CbSegm { int tbs, B, C, Kp, Km, Cp, Cm, F; };
 
 // Geometry of the windowed decoder for one code-block size (oracle/SPEC.md 7.3) and of the
-// device-native decoder-input layout ("tcb"): three planes sys/par1/par2 of W x Ppad int16, element
-// (window j, step i) at i*Ppad + j, followed by 16 int16 holding the 12 tail values.
+// device-native decoder-input layout ("tcb"): three planes sys/par1/par2 of W x Ppad int16 followed by
+// 16 int16 holding the 12 tail values.  Inside a plane the element of (window j, step i) sits at
+// (((i/8)*T + j/2)*8 + i%8)*2 + j%2: the 8 steps x 2 windows that one decoder thread consumes per
+// sub-window are 32 contiguous bytes, and consecutive threads are contiguous (two coalesced LDG.128).
 struct TurboGeom {
   int K, W, P, Ppad, T;   // T = Ppad / 2 threads per code block
   int plane;              // W * Ppad
@@ -59,7 +61,8 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
 int crs_offset(const CellCfg& cell, int port, int l);
 void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_sign, std::vector<int8_t>& im_sign);
 
-// DEC2 access table: for trellis step i of window j (entry i*Ppad + j) the tcb position of pi(j*W+i)
+// DEC2 access table: for trellis step i of window j (entry in tcb plane order) the position of
+// pi(j*W+i) in the shared exchange array A, which is laid out [W][Ppad]
 void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos);
 // CRC helpers for the per-window parallel CRC: U[i] = x^(W-1-i+24) mod g, V[j] = x^((P-1-j)W) mod g
 void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& U, std::vector<uint32_t>& V);

@@ -85,6 +85,14 @@ __device__ __forceinline__ uint32_t ext_step(const uint32_t (&a)[8], const uint3
   return vsub(l1, l0);
 }
 
+// PRMT with the sign-replicate bit of every selector nibble set (__byte_perm masks that bit off)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t sign_fill(uint32_t w) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(SEL));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t gf_mul24(uint32_t a, uint32_t b, uint32_t poly) {
   uint32_t r = 0;
 #pragma unroll 1
@@ -97,20 +105,33 @@ __device__ __forceinline__ uint32_t gf_mul24(uint32_t a, uint32_t b, uint32_t po
 }
 
 struct SlotCtx {
-  const uint32_t* sysw;   // channel LLR planes as packed pairs (global)
-  const uint32_t* p1w;
-  const uint32_t* p2w;
+  const uint4* sys4;      // channel LLR planes (global), this thread's first 8-step group: 2 x uint4 per group
+  const uint4* p14;
+  const uint4* p24;
   const int16_t* tail;    // 12 tail LLRs (global)
-  uint32_t* Aw;           // shared: extrinsic exchange array, packed pairs
-  uint32_t* ckpt;         // shared: [nsw][8][T]
+  uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
+  uint4* ckpt4;           // shared: beta checkpoints [nsw][T][2 x uint4], this thread's entry of group 0
+  const uint4* perm4;     // shared: DEC2 position pairs [nsw][T][2 x uint4], this thread's entry of group 0
   int16_t* nii;           // global: [2 dec][2 pp][2 kind][8][NP]
-  uint8_t* bits;          // global: [plane] hard decisions as 0x00 / 0xFF
+  uint8_t* bits;          // global: [W][Ppad] hard decisions, bit 7 of each byte
 };
+
+__device__ __forceinline__ void ld8(const uint4* p, uint32_t (&v)[8]) {
+  const uint4 a = __ldg(p), b = __ldg(p + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const uint4* p, uint32_t (&v)[8]) {
+  const uint4 a = p[0], b = p[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void sts8(uint4* p, const uint32_t (&v)[8]) {
+  p[0] = make_uint4(v[0], v[1], v[2], v[3]);
+  p[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
 
 // One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.
 template <int DEC>
-__device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, const uint32_t* s_permw, int t, int it,
-                                         bool store_bits) {
+__device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, int t, int it, bool store_bits) {
   const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW;
   const int j0 = 2 * t, j1 = 2 * t + 1;
   const int rd = it & 1, wr = rd ^ 1;
@@ -118,8 +139,9 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, c
   const int16_t* nii_b_rd = c.nii + ((DEC * 2 + rd) * 2 + 1) * 8 * NP;
   uint32_t* nii_a_wr = reinterpret_cast<uint32_t*>(c.nii + ((DEC * 2 + wr) * 2 + 0) * 8 * NP);
   uint32_t* nii_b_wr = reinterpret_cast<uint32_t*>(c.nii + ((DEC * 2 + wr) * 2 + 1) * 8 * NP);
-  const uint32_t* yw = DEC ? c.p2w : c.p1w;
+  const uint4* yq = DEC ? c.p24 : c.p14;
   int16_t* A16 = reinterpret_cast<int16_t*>(c.Aw);
+  const int gstride = 2 * T;                       // uint4 per 8-step group
 
   uint32_t b[8];
   // ---- beta at the end of the two windows -------------------------------------------------------
@@ -155,7 +177,7 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, c
       for (int s = 0; s < 8; s++) b[s] = 0;
     }
   }
-  // ---- alpha at the start of the two windows (read before anybody overwrites the other slot) ----
+  // ---- alpha at the start of the two windows ------------------------------------------------------
   uint32_t a[8];
 #pragma unroll
   for (int s = 0; s < 8; s++) {
@@ -166,23 +188,29 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, c
   }
 
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
+  uint32_t ny[kSW], ns[kSW];                        // register prefetch of the next group's channel LLRs
+  ld8(yq + (nsw - 1) * gstride, ny);
+  if (DEC == 0) ld8(c.sys4 + (nsw - 1) * gstride, ns);
 #pragma unroll 1
   for (int sw = nsw - 1; sw >= 0; sw--) {
     uint32_t x[kSW], y[kSW];
-    const int base = sw * kSW * T + t;
 #pragma unroll
-    for (int i = 0; i < kSW; i++) {
-      y[i] = __ldg(yw + base + i * T);
-      if (DEC == 0) {
-        const uint32_t s = __ldg(c.sysw + base + i * T);
-        x[i] = it ? vadd(s, c.Aw[base + i * T]) : s;
-      } else {
-        const uint32_t pp = s_permw[base + i * T];
-        x[i] = pack16(A16[pp & 0xFFFFu], A16[pp >> 16]);
-      }
+    for (int i = 0; i < kSW; i++) y[i] = ny[i];
+    if (DEC == 0) {
+      const uint32_t* ap = c.Aw + sw * kSW * T + t;
+#pragma unroll
+      for (int i = 0; i < kSW; i++) x[i] = vadd(ns[i], ap[i * T]);
+    } else {
+      uint32_t pp[kSW];
+      lds8(c.perm4 + sw * gstride, pp);
+#pragma unroll
+      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pp[i] & 0xFFFFu], A16[pp[i] >> 16]);
     }
-#pragma unroll
-    for (int s = 0; s < 8; s++) c.ckpt[(sw * 8 + s) * T + t] = b[s];
+    if (sw > 0) {
+      ld8(yq + (sw - 1) * gstride, ny);
+      if (DEC == 0) ld8(c.sys4 + (sw - 1) * gstride, ns);
+    }
+    sts8(c.ckpt4 + sw * gstride, b);
 #pragma unroll
     for (int i = kSW - 1; i >= 0; i--) {
       uint32_t nb[8];
@@ -197,24 +225,28 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, c
   for (int s = 0; s < 8; s++) nii_b_wr[(s * NP + j0) >> 1] = b[s];
 
   // ---- pass 2: forward sweep ----------------------------------------------------------------------
+  ld8(yq, ny);
+  if (DEC == 0) ld8(c.sys4, ns);
 #pragma unroll 1
   for (int sw = 0; sw < nsw; sw++) {
     uint32_t x[kSW], y[kSW], aux[kSW];     // aux: DEC1 systematic LLRs, DEC2 position pairs
-    const int base = sw * kSW * T + t;
+    uint32_t* ap = c.Aw + sw * kSW * T + t;
 #pragma unroll
-    for (int i = 0; i < kSW; i++) {
-      y[i] = __ldg(yw + base + i * T);
-      if (DEC == 0) {
-        aux[i] = __ldg(c.sysw + base + i * T);
-        x[i] = it ? vadd(aux[i], c.Aw[base + i * T]) : aux[i];
-      } else {
-        aux[i] = s_permw[base + i * T];
-        x[i] = pack16(A16[aux[i] & 0xFFFFu], A16[aux[i] >> 16]);
-      }
+    for (int i = 0; i < kSW; i++) y[i] = ny[i];
+    if (DEC == 0) {
+#pragma unroll
+      for (int i = 0; i < kSW; i++) { aux[i] = ns[i]; x[i] = vadd(ns[i], ap[i * T]); }
+    } else {
+      lds8(c.perm4 + sw * gstride, aux);
+#pragma unroll
+      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[aux[i] & 0xFFFFu], A16[aux[i] >> 16]);
+    }
+    if (sw + 1 < nsw) {
+      ld8(yq + (sw + 1) * gstride, ny);
+      if (DEC == 0) ld8(c.sys4 + (sw + 1) * gstride, ns);
     }
     uint32_t B[kSW][8];                     // B[i] = beta_{i+1} of this sub-window
-#pragma unroll
-    for (int s = 0; s < 8; s++) B[kSW - 1][s] = c.ckpt[(sw * 8 + s) * T + t];
+    lds8(c.ckpt4 + sw * gstride, B[kSW - 1]);
 #pragma unroll
     for (int i = kSW - 1; i >= 1; i--) {
       beta_step(B[i], B[i - 1], x[i], y[i], vadd(x[i], y[i]));
@@ -225,15 +257,16 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, c
       const uint32_t ext = ext_step(a, B[i], y[i]);
       const uint32_t la = vclampE(ext);
       if (DEC == 0) {
-        c.Aw[base + i * T] = vadd(aux[i], la);
+        ap[i * T] = vadd(aux[i], la);
       } else {
         const uint32_t p0 = aux[i] & 0xFFFFu, p1 = aux[i] >> 16;
         A16[p0] = (int16_t)(la & 0xFFFFu);
         A16[p1] = (int16_t)(la >> 16);
         if (store_bits) {
-          const uint32_t d = vadd(x[i], ext);
-          c.bits[p0] = ((int16_t)(d & 0xFFFFu) > 0) ? 0xFF : 0x00;
-          c.bits[p1] = ((int16_t)(d >> 16) > 0) ? 0xFF : 0x00;
+          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext); the byte keeps it in bit 7
+          const uint32_t nd = vsub(0u, vadd(x[i], ext));
+          c.bits[p0] = (uint8_t)(nd >> 8);
+          c.bits[p1] = (uint8_t)(nd >> 24);
         }
       }
       alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
@@ -253,16 +286,17 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
   const int slot = tid / T, t = tid - slot * T;
   const bool valid = slot < g.ncb_cta;
 
-  uint32_t* s_permw = smem;                                  // plane/2 words
+  uint32_t* s_permw = smem;                                  // plane/2 words, [nsw][T][8]
   uint32_t* s_crc = s_permw + plane / 2;                     // ncb_cta words (rounded to 4)
   uint32_t* s_slots = s_crc + ((g.ncb_cta + 3) & ~3);
-  const int slot_words = plane / 2 + nsw * 8 * T;
+  const int slot_words = plane / 2 + nsw * 8 * T;            // A + checkpoints
 
   for (int i = tid; i < plane / 2; i += blockDim.x) s_permw[i] = reinterpret_cast<const uint32_t*>(g.perm_pos)[i];
 
   SlotCtx c;
   c.Aw = s_slots + (size_t)(valid ? slot : 0) * slot_words;
-  c.ckpt = c.Aw + plane / 2;
+  c.ckpt4 = reinterpret_cast<uint4*>(c.Aw + plane / 2) + 2 * t;
+  c.perm4 = reinterpret_cast<const uint4*>(s_permw) + 2 * t;
   const size_t gslot = (size_t)blockIdx.x * g.ncb_cta + (valid ? slot : 0);
   c.nii = g.nii + gslot * (size_t)(2 * 2 * 2 * 8 * NP);
   c.bits = g.bits_scratch + gslot * (size_t)plane;
@@ -274,19 +308,22 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
     const bool active = valid && cb < g.n_cb;
     const long long cbi = active ? (g.cb_list ? g.cb_list[cb] : cb) : 0;
     const int16_t* in_cb = g.in + cbi * g.in_stride;
-    c.sysw = reinterpret_cast<const uint32_t*>(in_cb);
-    c.p1w = c.sysw + plane / 2;
-    c.p2w = c.p1w + plane / 2;
+    c.sys4 = reinterpret_cast<const uint4*>(in_cb) + 2 * t;
+    c.p14 = c.sys4 + plane / 8;
+    c.p24 = c.p14 + plane / 8;
     c.tail = in_cb + 3 * plane;
+    // a-priori LLRs start at zero: each thread clears its own column of A
+    if (active)
+      for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
 
     bool done = !active;
     int n_iter = 0, crc_ok = 0;
     for (int it = 0; it < g.max_iter; it++) {
       if (valid && t == 0) s_crc[slot] = 0;
       const bool store_bits = (g.crc_type != 0) || (it == g.max_iter - 1);
-      if (!done) map_pass<0>(g, c, s_permw, t, it, store_bits);
+      if (!done) map_pass<0>(g, c, t, it, store_bits);
       __syncthreads();
-      if (!done) { map_pass<1>(g, c, s_permw, t, it, store_bits); n_iter = it + 1; }
+      if (!done) { map_pass<1>(g, c, t, it, store_bits); n_iter = it + 1; }
       __syncthreads();
       if (g.crc_type != 0) {
         if (!done) {
@@ -297,8 +334,8 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
           for (int i = 0; i < W; i++) {
             const uint32_t w = *reinterpret_cast<const uint16_t*>(bp + (size_t)i * g.Ppad);
             const uint32_t u = __ldg(g.crcU + i);
-            c0 ^= (uint32_t)(-(int)(w & 1u)) & u;
-            c1 ^= (uint32_t)(-(int)((w >> 8) & 1u)) & u;
+            c0 ^= sign_fill<0x8888>(w) & u;      // all-ones when bit 7 of byte 0 is set
+            c1 ^= sign_fill<0x9999>(w) & u;      // same for byte 1
           }
           const uint32_t contrib = gf_mul24(c0, __ldg(g.crcV + 2 * t), g.crc_poly) ^
                                    gf_mul24(c1, __ldg(g.crcV + 2 * t + 1), g.crc_poly);
@@ -321,7 +358,7 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
         for (int bb = 0; bb < wbytes; bb++) {
           uint32_t v = 0;
 #pragma unroll
-          for (int q = 0; q < 8; q++) v = (v << 1) | (c.bits[(size_t)(bb * 8 + q) * g.Ppad + j] & 1u);
+          for (int q = 0; q < 8; q++) v = (v << 1) | (c.bits[(size_t)(bb * 8 + q) * g.Ppad + j] >> 7);
           out[j * wbytes + bb] = (uint8_t)v;
         }
       }
@@ -342,8 +379,11 @@ __global__ void triples_to_tcb_kernel(const int16_t* __restrict__ in, long long 
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.cb_elems; e += gridDim.x * blockDim.x) {
     int v = 0;
     if (e < 3 * g.plane) {
+      // tcb element -> (stream, window j, step i): element ((sw*T + t)*8 + ii)*2 + h, j = 2t + h, i = 8sw + ii
       const int stream = e / g.plane, r = e - stream * g.plane;
-      const int i = r / g.Ppad, j = r - i * g.Ppad;
+      const int h = r & 1, ii = (r >> 1) & 7, q = r >> 4;
+      const int sw = q / g.T, t = q - sw * g.T;
+      const int i = sw * 8 + ii, j = 2 * t + h;
       if (j < g.P) v = src[3 * (j * g.W + i) + stream];
     } else if (e - 3 * g.plane < 12) {
       v = src[3 * g.K + (e - 3 * g.plane)];
@@ -363,7 +403,8 @@ __global__ void tcb_to_triples_kernel(const int16_t* __restrict__ in, long long 
     int off;
     if (e < 3 * g.K) {
       const int k = e / 3, stream = e - 3 * k;
-      off = stream * g.plane + (k % g.W) * g.Ppad + k / g.W;
+      const int j = k / g.W, i = k - j * g.W;
+      off = stream * g.plane + ((((i >> 3) * g.T + (j >> 1)) * 8 + (i & 7)) << 1) + (j & 1);
     } else {
       off = 3 * g.plane + (e - 3 * g.K);
     }
