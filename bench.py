@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- PDSCH decoded Mbit/s @ 20 MHz, MCS 28, TM1 (BASELINE.json configs[1]) on N B200.
+
+A "step" is one pass of the hot path (OFDM demod -> channel estimate -> equalise/demap/descramble/dematch ->
+turbo decode + CRC -> transport blocks) over one batch of synthetic subframes that is already resident in
+HBM.  `value` = CRC-passing transport-block bits of all ranks / max-over-ranks device time.  `e2e` is the
+same metric through the host-buffer C-ABI call (H2D of the IQ and D2H of payload/status inside the timed
+region).  Subframe batches are independent: ranks shard them, no collective on the data path (weak scaling).
+
+Synthetic inputs come from the oracle's TX-side generator (oracle/lteo_tx.c), which is test infrastructure
+and not on the measured path.  `--impl reference` times the CPU restatement of the srsLTE path (the
+reference's own implementation, srsLTE, is not available offline -- see DESIGN.md) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, cfi=1, sf_idx=1, rnti=0x1234, cell_id=1)
+METRIC = "pdsch_decoded_mbit_per_s_20mhz_mcs28_tm1"
+
+
+def gen_pool(o, pool, snr_db, seed0):
+    ocell = o.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"])
+    ocfg = o.make_cfg(ocell, sf_idx=WORKLOAD["sf_idx"], cfi=WORKLOAD["cfi"], rnti=WORKLOAD["rnti"], qm=WORKLOAD["qm"],
+                      tbs=WORKLOAD["tbs"], tm=WORKLOAD["tm"])
+    tbs, iqs = [], []
+    for i in range(pool):
+        # payload seed = 10000*cfg + unit index, noise seed = payload seed + 5e6 (inside gen_subframe)
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 20000 + seed0 + i, snr_db)
+        tbs.append(tb)
+        iqs.append(iq)
+    return ocell, ocfg, np.stack(tbs), np.stack(iqs)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.2)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("clock sampling unavailable: %s" % type(e).__name__)
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the restated srsLTE path on all host threads, one subframe per thread at a time."""
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    cores = os.cpu_count() or 1
+    ocell, ocfg, tbs, iqs = gen_pool(o, min(args.pool, 16), args.snr, 0)
+    per_step = max(cores * 4, 16)
+    idx = np.arange(per_step) % len(iqs)
+    iq = iqs[idx]
+    for _ in range(args.warmup):
+        o.ue_dl_decode_mt(ocell, ocfg, iq[:cores], cores, 0.01, 0, args.max_iter)
+    t0 = time.perf_counter()
+    ok_bits = 0
+    for _ in range(args.steps):
+        ok, payload, status = o.ue_dl_decode_mt(ocell, ocfg, iq, cores, 0.01, 0, args.max_iter)
+        ok_bits += ok * WORKLOAD["tbs"]
+    dt = time.perf_counter() - t0
+    val = ok_bits / dt / 1e6
+    sample = "%d subframes per step x %d steps, %d threads, scalar C (-O2), early stop on CRC" % (per_step, args.steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB" % args.snr, "subframes_per_step": per_step,
+                   "max_iter": args.max_iter},
+        "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "subframes_per_s": val * 1e6 / WORKLOAD["tbs"],
+        "note": "CPU restatement of the srsLTE path (oracle/); srsLTE itself is not installable offline",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="subframes per step and per GPU (device-resident)")
+    ap.add_argument("--e2e-batch", type=int, default=1024, help="subframes per step for the host-buffer measurement")
+    ap.add_argument("--pool", type=int, default=32, help="distinct synthetic subframes (tiled to the batch)")
+    ap.add_argument("--snr", type=float, default=30.0)
+    ap.add_argument("--max-iter", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import srsue_b200 as sg
+    from oracle import oracle as o   # input generator + cpu_baseline only
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsrsue_gpu has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- inputs -------------------------------------------------------------------------------------
+    ocell, ocfg, tbs, iqs = gen_pool(o, args.pool, args.snr, 1000 * rank)
+    B = args.batch
+    idx = np.arange(B) % args.pool
+    ctx = sg.Context(local_rank)
+    cell = sg.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"])
+    cfg = sg.make_cfg(cell, sf_idx=WORKLOAD["sf_idx"], cfi=WORKLOAD["cfi"], rnti=WORKLOAD["rnti"], qm=WORKLOAD["qm"],
+                      tbs=WORKLOAD["tbs"], tm=WORKLOAD["tm"])
+    plan = sg.PdschPlan(ctx, cell, cfg, B)
+    I = plan.info
+    d_pool = torch.from_numpy(iqs.view(np.float32).reshape(args.pool, -1)).cuda()
+    d_iq = d_pool[torch.from_numpy(idx).cuda()].contiguous()          # [B][sf_len*2] float32, 245 760 B per subframe
+    del d_pool
+    d_sf = torch.empty((B, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.empty((B, WORKLOAD["ports"] * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.empty((B, 5), dtype=torch.float32, device="cuda")
+    d_sb = torch.empty((B, I.sb_sf_stride), dtype=torch.int16, device="cuda")
+    d_pl = torch.zeros((B, I.payload_stride), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+
+    names = ["ofdm_fft", "chest", "equalise_demap_dematch", "turbo_crc_tb"]
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        plan.ofdm_rx(B, d_iq, d_sf)
+        if ev:
+            ev[1].record()
+        plan.chest(B, d_sf, d_ce, d_meas)
+        if ev:
+            ev[2].record()
+        plan.pdsch_llr(B, d_sf, d_ce, d_meas, 0.01, 0, 0, d_sb)        # srsUE passes noise_estimate = 0.01
+        if ev:
+            ev[3].record()
+        plan.pdsch_turbo(B, d_sb, args.max_iter, d_pl, d_st)
+        if ev:
+            ev[4].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # correctness of what is being timed: every transport block passes CRC and equals what was sent
+    st = d_st.cpu().numpy()
+    pl = d_pl.cpu().numpy()
+    verified = bool((st[:, 0] == 1).all() and np.array_equal(pl[:args.pool], tbs[idx[:args.pool]]))
+    avg_iter = float(st[:, 1].sum()) / (B * I.C)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    launches = 0
+    barrier()
+    for k in range(args.steps):
+        ctx_count0 = 0
+        step(evs[k])
+        launches += 5 + (1 if I.Cm else 0)
+    barrier()
+    total_ms = evs[0][0].elapsed_time(evs[-1][4])
+    stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(4)]
+    ok_bits = float((d_st[:, 0] == 1).sum().item()) * WORKLOAD["tbs"] * args.steps
+
+    # ---- end to end through the host-buffer call --------------------------------------------------------
+    EB = min(args.e2e_batch, B)
+    lib = sg.lib()
+    import ctypes as C
+    nbytes_iq = EB * I.sf_len * 8
+    p_iq = lib.srsue_gpu_host_alloc(nbytes_iq)
+    h_iq = np.ctypeslib.as_array(C.cast(p_iq, C.POINTER(C.c_float)), shape=(EB, I.sf_len * 2))
+    h_iq[:] = iqs.view(np.float32).reshape(args.pool, -1)[np.arange(EB) % args.pool]
+    p_pl = lib.srsue_gpu_host_alloc(EB * I.payload_stride)
+    h_pl = np.ctypeslib.as_array(C.cast(p_pl, C.POINTER(C.c_uint8)), shape=(EB, I.payload_stride))
+    h_st = np.zeros((EB, 4), np.int32)
+    eplan = sg.PdschPlan(ctx, cell, cfg, EB)
+    for _ in range(2):
+        eplan.decode_batch_host(EB, h_iq, 0.01, 0, args.max_iter, h_pl, h_st)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_bits = 0
+    for _ in range(args.steps):
+        eplan.decode_batch_host(EB, h_iq, 0.01, 0, args.max_iter, h_pl, h_st)
+        e2e_bits += int((h_st[:, 0] == 1).sum()) * WORKLOAD["tbs"]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    e2e_ok = bool(np.array_equal(h_pl[:args.pool], tbs[(np.arange(EB) % args.pool)[:args.pool]]))
+
+    # ---- reduce over ranks (max time, sum of units) ------------------------------------------------------
+    vals = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([ok_bits, float(e2e_bits), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_s_max = vals.tolist()
+    ok_bits_all, e2e_bits_all, launches_all = sums.tolist()
+
+    if rank == 0:
+        value = ok_bits_all / (total_ms_max * 1e-3) / 1e6
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        # dominant kernel: the turbo decoder.  Algorithmic work per SURVEY 8d: 168 * K * iterations int16 ops
+        # per code block.  Peak from the measured issue rates (tools/alu_peak.cu, profiles/alu_peak_r01.json):
+        # 64 lanes/clk/SM of VIADD.16x2 on the FMA pipe (2 ops) + 64 lanes/clk/SM of VIADDMNMX.S16x2 on the ALU
+        # pipe (4 ops) = 384 int16 ops/clk/SM.
+        n_cb = B * I.C
+        turbo_ops = 168.0 * I.Kp * avg_iter * n_cb
+        alu_peak_tops = 148 * 384 * sm_max * 1e6 / 1e12
+        turbo_tops = turbo_ops / (stage_ms[3] * 1e-3) / 1e12
+        alg_bytes = {"ofdm_fft": 380160, "chest": 268800, "equalise_demap_dematch": 574584 + 120000, "turbo_crc_tb": 464058}
+        stages = []
+        for i, n in enumerate(names):
+            gbs = alg_bytes[n] * B / (stage_ms[i] * 1e-3) / 1e9
+            stages.append({"kernel": n, "ms": stage_ms[i], "share": stage_ms[i] / sum(stage_ms), "algorithmic_gbs": gbs,
+                           "frac_of_measured_hbm": gbs / hbm_peak})
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB (BASELINE configs[1])" % args.snr,
+                       "subframes_per_step_per_gpu": B, "distinct_subframes": args.pool, "max_iter": args.max_iter,
+                       "early_stop": "CRC24B per code block", "avg_turbo_iterations": avg_iter,
+                       "l2_policy": "inputs larger than L2 (%.0f MB of IQ per step)" % (B * I.sf_len * 8 / 1e6),
+                       "parallelism": "independent subframe batches per GPU, no collective"},
+            "subframes_per_s": value * 1e6 / WORKLOAD["tbs"],
+            "verified_bit_exact_payload": verified and e2e_ok,
+            "e2e": {"value": e2e_bits_all / e2e_s_max / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": nbytes_iq,
+                    "d2h_bytes_per_step": EB * (I.payload_stride + 16), "subframes_per_step": EB},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "alu", "kernel": "turbo_decode_kernel", "achieved": turbo_tops, "peak": alu_peak_tops,
+                         "unit": "Tint16op/s", "frac": turbo_tops / alu_peak_tops, "traffic": None,
+                         "peak_source": "measured VIADD.16x2 + VIADDMNMX.S16x2 issue rates at %.0f MHz (profiles/alu_peak_r01.json)" % sm_max,
+                         "note": "integer-ALU bound (north star); HBM-bound front-end kernels are listed in `stages`"},
+            "stages": stages,
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = max(cores * 8, 32)
+            sub = iqs[np.arange(n) % args.pool]
+            t0 = time.perf_counter()
+            ok, _, _ = o.ue_dl_decode_mt(ocell, ocfg, sub, cores, 0.01, 0, args.max_iter)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ok * WORKLOAD["tbs"] / dt / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "port",
+                                   "sample": "%d subframes of the same workload, %d threads, scalar C restatement of the srsLTE path" % (n, cores)}
+        print(json.dumps(out))
+    lib.srsue_gpu_host_free(p_iq)
+    lib.srsue_gpu_host_free(p_pl)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -270,6 +270,26 @@ def ue_dl_decode(cell, cfg, iq, noise_est=0.01, noise_mode=0, max_iter=4, softbu
     return rc, payload, meas, avg.value
 
 
+def ue_dl_decode_mt(cell, cfg, iq, nthreads, noise_est=0.01, noise_mode=0, max_iter=4):
+    """batch of subframes on `nthreads` host threads (bench.py cpu_baseline / reference arm)"""
+    iq = np.ascontiguousarray(iq, np.complex64)
+    n = iq.shape[0]
+    payload = np.zeros((n, (cfg.tbs + 7) // 8), np.uint8)
+    status = np.zeros((n, 2), np.int32)
+    ok = lib().lteo_ue_dl_decode_mt(C.byref(cell), C.byref(cfg), _p(iq), n, C.c_float(noise_est), noise_mode, max_iter,
+                                    nthreads, _p(payload), _p(status))
+    return ok, payload, status
+
+
+def tdec_mt(llrs, K, nthreads, max_iter=4, crc_type=0):
+    llrs = np.ascontiguousarray(llrs, np.int16)
+    n = llrs.shape[0]
+    bits = np.zeros((n, K), np.uint8)
+    iters = np.zeros(n, np.int32)
+    lib().lteo_tdec_mt(_p(llrs), n, K, max_iter, crc_type, nthreads, _p(bits), _p(iters))
+    return bits, iters
+
+
 # ---- synthetic subframes (SURVEY.md 8d seeds) ----------------------------------------------
 def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).

@@ -131,7 +131,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   const TurboGeom& g = tt->g;
   const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb);
   const size_t slots = (size_t)lc.grid * lc.ncb;
-  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), slots * (size_t)g.plane, 0);
+  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), slots * (size_t)g.plane * 2, 0);
   if (rc) return rc;
   if (!ctx->attr_set) {
     CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
@@ -168,11 +168,11 @@ struct srsue_gpu_pdsch_plan {
   srsue_gpu_plan_info_t info{};
   TurboGeom gp{}, gm{};
   int crs_off[2][4]{};
-  int max_E = 0, gather_stride = 0;
+  int max_E = 0, gather_stride = 0, direct = 0;
   // device tables
   int32_t* d_re = nullptr; uint32_t* d_scr = nullptr; uint16_t* d_gather = nullptr;
   int32_t* d_e_start = nullptr; int32_t* d_cb_geom = nullptr; int8_t* d_crs = nullptr; float* d_tw = nullptr;
-  int32_t* d_list_m = nullptr; int32_t* d_list_p = nullptr;
+  int32_t* d_list_m = nullptr; int32_t* d_list_p = nullptr; int32_t* d_tbmap = nullptr; uint32_t* d_tbshift = nullptr;
   // device work buffers (max_batch)
   float2* d_sf = nullptr; float2* d_ce = nullptr; float* d_meas = nullptr; int16_t* d_sb = nullptr;
   uint8_t* d_cb_bits = nullptr; int32_t* d_cb_status = nullptr;
@@ -381,19 +381,43 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
   p->gather_stride = I.sb_cb_stride;
   std::vector<uint16_t> gather((size_t)s.C * p->gather_stride, 0xFFFF), tab;
   std::vector<int32_t> e_start(s.C + 1, 0), geom(4 * s.C, 0);
+  // "direct" tables (every soft-buffer element receives at most one LLR, E <= N for all code blocks): the
+  // entry is the index of that LLR inside the code block's range, E for "nothing" and E+1 for filler, so the
+  // kernel gathers branch-free from a shared array that ends in the two sentinels {0, -C}.
+  p->direct = 1;
+  for (int r = 0; r < s.C; r++) {
+    const TurboGeom g = turbo_geom(cb_len(s, r));
+    const int N = 3 * (g.K + 4) - ((r == 0) ? 2 * s.F : 0);
+    if (cb_E(s, G, cfg->qm, nl, r) > N) p->direct = 0;
+  }
+  // transport-block assembly: byte ranges of every code block's payload and CRC24A chunk shifts
+  std::vector<int32_t> tbmap(4 * s.C, 0);
+  std::vector<uint32_t> tbshift((size_t)s.C * 32, 0);
+  const int tb_bytes = (cfg->tbs + 24) / 8;
+  int tb_pos = 0;
   for (int r = 0; r < s.C; r++) {
     const int K = cb_len(s, r), F = (r == 0) ? s.F : 0;
     const TurboGeom g = turbo_geom(K);
     const int N = rm_gather_table(g, F, cfg->rv, tab);
-    std::copy(tab.begin(), tab.end(), gather.begin() + (size_t)r * p->gather_stride);
     const int E = cb_E(s, G, cfg->qm, nl, r);
+    if (p->direct)
+      for (auto& v : tab) v = (v == 0xFFFE) ? (uint16_t)(E + 1) : (v >= E ? (uint16_t)E : v);
+    std::copy(tab.begin(), tab.end(), gather.begin() + (size_t)r * p->gather_stride);
     e_start[r + 1] = e_start[r] + E;
     p->max_E = std::max(p->max_E, E);
     geom[4 * r] = g.cb_elems; geom[4 * r + 1] = N; geom[4 * r + 2] = K;
+    const int src_off = F / 8, nb = K / 8 - (s.C > 1 ? 3 : 0) - F / 8, chunk = (nb + 31) / 32;
+    tbmap[4 * r] = src_off; tbmap[4 * r + 1] = nb; tbmap[4 * r + 2] = tb_pos; tbmap[4 * r + 3] = chunk;
+    for (int l = 0; l < 32; l++) {
+      const int end = std::min(nb, (l + 1) * chunk);           // stream bytes after this lane's chunk
+      tbshift[(size_t)r * 32 + l] = crc_xpow(kCrc24A, (uint64_t)8 * (tb_bytes - (tb_pos + end)));
+    }
+    tb_pos += nb;
   }
-  if (e_start[s.C] != G) { delete p; return fail(SRSUE_GPU_ERROR, "internal: rate-matching sizes do not add up"); }
+  if (e_start[s.C] != G || tb_pos != tb_bytes) { delete p; return fail(SRSUE_GPU_ERROR, "internal: rate-matching sizes do not add up"); }
   std::vector<uint32_t> scr;
   gold_packed(((uint32_t)cfg->rnti << 14) | ((uint32_t)cfg->sf_idx << 9) | (uint32_t)cell->cell_id, G, scr);
+  scr.push_back(0u);      // the kernel reads bit groups with a two-word funnel shift
   std::vector<int8_t> crs(4 * 2 * 2 * cell->nof_prb), rs, is;
   const int crs_l[4] = {0, 4, 7, 11};
   for (int si = 0; si < 4; si++) {
@@ -414,7 +438,8 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
             upload(&p->d_gather, gather) == cudaSuccess && upload(&p->d_e_start, e_start) == cudaSuccess &&
             upload(&p->d_cb_geom, geom) == cudaSuccess && upload(&p->d_crs, crs) == cudaSuccess &&
             upload(&p->d_tw, tw) == cudaSuccess && upload(&p->d_list_m, list_m) == cudaSuccess &&
-            upload(&p->d_list_p, list_p) == cudaSuccess;
+            upload(&p->d_list_p, list_p) == cudaSuccess && upload(&p->d_tbmap, tbmap) == cudaSuccess &&
+            upload(&p->d_tbshift, tbshift) == cudaSuccess;
   const size_t B = (size_t)max_batch;
   ok = ok && cudaMalloc((void**)&p->d_sf, B * 14 * nsc * sizeof(float2)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&p->d_ce, B * cell->nof_ports * 14 * nsc * sizeof(float2)) == cudaSuccess;
@@ -437,7 +462,7 @@ void srsue_gpu_pdsch_plan_destroy(srsue_gpu_pdsch_plan_t* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaFree(p->d_re); cudaFree(p->d_scr); cudaFree(p->d_gather); cudaFree(p->d_e_start); cudaFree(p->d_cb_geom);
-  cudaFree(p->d_crs); cudaFree(p->d_tw); cudaFree(p->d_list_m); cudaFree(p->d_list_p);
+  cudaFree(p->d_crs); cudaFree(p->d_tw); cudaFree(p->d_list_m); cudaFree(p->d_list_p); cudaFree(p->d_tbmap); cudaFree(p->d_tbshift);
   cudaFree(p->d_sf); cudaFree(p->d_ce); cudaFree(p->d_meas); cudaFree(p->d_sb); cudaFree(p->d_cb_bits);
   cudaFree(p->d_cb_status); cudaFree(p->d_iq); cudaFree(p->d_payload); cudaFree(p->d_tb_status);
   p->scratch.release();
@@ -509,13 +534,13 @@ int srsue_gpu_pdsch_llr(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_
   a.dbg_d = reinterpret_cast<float2*>(d_dbg_d); a.dbg_e = d_dbg_e;
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.tm = p->cfg.tm; a.qm = p->cfg.qm;
   a.nof_re = p->info.nof_re; a.C = p->info.C; a.gather_stride = p->gather_stride; a.sb_stride = p->info.sb_cb_stride;
-  a.noise_est = noise_est; a.noise_mode = noise_mode; a.accumulate = accumulate;
+  a.noise_est = noise_est; a.noise_mode = noise_mode; a.accumulate = accumulate; a.direct = p->direct;
   a.k_sqpsk = (float)(100.0 * std::sqrt(2.0));
   a.k_c16 = (float)(2.0 * 400.0 / std::sqrt(10.0));
   a.k_c64a = (float)(4.0 * 700.0 / std::sqrt(42.0));
   a.k_c64b = (float)(2.0 * 700.0 / std::sqrt(42.0));
   a.k_sq2 = (float)std::sqrt(2.0);
-  const int smem = ((p->max_E * 2 + 15) / 16) * 16;
+  const int smem = (((p->max_E + 2) * 2 + 15) / 16) * 16;
   if (smem > p->ctx->smem_optin) return fail(SRSUE_GPU_ERROR, "code block of %d LLRs does not fit in shared memory", p->max_E);
   for (int done = 0; done < n_sf; done += 65535) {
     const int n = std::min(65535, n_sf - done);
@@ -552,8 +577,8 @@ int srsue_gpu_pdsch_turbo(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_
   TbArgs t{};
   t.cb_bits = p->d_cb_bits; t.cb_status = cbst; t.payload = d_payload; t.tb_status = d_tb_status;
   t.n_sf = n_sf; t.C = s.C; t.Cm = s.Cm; t.Km = s.Km; t.Kp = s.Kp; t.F = s.F; t.tbs = s.tbs;
-  t.cb_bits_stride = s.Kp / 8; t.payload_stride = p->info.payload_stride;
-  tb_assemble_kernel<<<n_sf, 256, 0, st>>>(t);
+  t.cb_bits_stride = s.Kp / 8; t.payload_stride = p->info.payload_stride; t.tbmap = p->d_tbmap; t.tbshift = p->d_tbshift;
+  tb_assemble_kernel<<<n_sf, 32 * s.C, 0, st>>>(t);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
   return 0;

@@ -7,7 +7,7 @@
 
 namespace srsue {
 
-constexpr int kTurboMaxThreads = 384;
+constexpr int kTurboMaxThreads = 256;
 
 struct TurboGeomDev { int K, W, P, Ppad, T, plane, cb_elems; };
 
@@ -74,6 +74,7 @@ struct DemodArgs {
   float k_sqpsk, k_c16, k_c64a, k_c64b, k_sq2;   // demapper constants, rounded on the host (SPEC 5)
   int noise_mode;            // 0: noise_est, 1: meas[0]
   int accumulate;            // 0: new transmission (buffer overwritten), 1: add to existing
+  int direct;                // gather tables hold direct LLR indices with sentinels E (zero) and E+1 (filler)
 };
 __global__ void pdsch_llr_dematch_kernel(const DemodArgs a);
 
@@ -82,6 +83,8 @@ struct TbArgs {
   const int32_t* cb_status;  // [n_sf * C]
   uint8_t* payload;          // [n_sf][payload_stride]
   int32_t* tb_status;        // [n_sf][4]: crc_ok, sum of iterations, avg iterations, C
+  const int32_t* tbmap;      // [C][4]: source byte offset, payload bytes, TB byte position, bytes per lane
+  const uint32_t* tbshift;   // [C][32]: x^(8 * bytes after the lane's chunk) mod CRC24A
   int n_sf, C, Cm, Km, Kp, F, tbs, cb_bits_stride, payload_stride;
 };
 __global__ void tb_assemble_kernel(const TbArgs a);

@@ -72,14 +72,13 @@ __device__ __forceinline__ void normalise(uint32_t (&m)[8]) {
 
 // extrinsic of one trellis step from alpha_k and beta_{k+1}: max(A10, A11 + y) - max(A00, A01 + y)
 __device__ __forceinline__ uint32_t ext_step(const uint32_t (&a)[8], const uint32_t (&bn)[8], uint32_t y) {
-  uint32_t a00 = vadd(a[0], bn[0]);
-  a00 = vaddmax(a[1], bn[4], a00); a00 = vaddmax(a[6], bn[7], a00); a00 = vaddmax(a[7], bn[3], a00);
-  uint32_t a11 = vadd(a[0], bn[4]);
-  a11 = vaddmax(a[1], bn[0], a11); a11 = vaddmax(a[6], bn[3], a11); a11 = vaddmax(a[7], bn[7], a11);
-  uint32_t a01 = vadd(a[2], bn[5]);
-  a01 = vaddmax(a[3], bn[1], a01); a01 = vaddmax(a[4], bn[2], a01); a01 = vaddmax(a[5], bn[6], a01);
-  uint32_t a10 = vadd(a[2], bn[1]);
-  a10 = vaddmax(a[3], bn[5], a10); a10 = vaddmax(a[4], bn[6], a10); a10 = vaddmax(a[5], bn[2], a10);
+  // Pipe balance (measured, profiles/alu_peak_r01.json): VIADD.16x2 issues on the FMA pipe, VIADDMNMX /
+  // VIMNMX3 on the ALU pipe, 64 lanes/clk/SM each.  Three plain adds + one 3-input max + one fused add-max
+  // per class puts 8 instructions on the ALU pipe instead of 12 (max of 4 sums is order-independent).
+  const uint32_t a00 = vaddmax(a[7], bn[3], __vimax3_s16x2(vadd(a[0], bn[0]), vadd(a[1], bn[4]), vadd(a[6], bn[7])));
+  const uint32_t a11 = vaddmax(a[7], bn[7], __vimax3_s16x2(vadd(a[0], bn[4]), vadd(a[1], bn[0]), vadd(a[6], bn[3])));
+  const uint32_t a01 = vaddmax(a[5], bn[6], __vimax3_s16x2(vadd(a[2], bn[5]), vadd(a[3], bn[1]), vadd(a[4], bn[2])));
+  const uint32_t a10 = vaddmax(a[5], bn[2], __vimax3_s16x2(vadd(a[2], bn[1]), vadd(a[3], bn[5]), vadd(a[4], bn[6])));
   const uint32_t l1 = vaddmax(a11, y, a10);
   const uint32_t l0 = vaddmax(a01, y, a00);
   return vsub(l1, l0);
@@ -111,9 +110,9 @@ struct SlotCtx {
   const int16_t* tail;    // 12 tail LLRs (global)
   uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
   uint4* ckpt4;           // shared: beta checkpoints [nsw][T][2 x uint4], this thread's entry of group 0
-  const uint4* perm4;     // shared: DEC2 position pairs [nsw][T][2 x uint4], this thread's entry of group 0
+  const uint16_t* perm16; // shared: DEC2 positions [nsw][T][8 steps][2 windows], this thread's entry of group 0
   int16_t* nii;           // global: [2 dec][2 pp][2 kind][8][NP]
-  uint8_t* bits;          // global: [W][Ppad] hard decisions, bit 7 of each byte
+  uint16_t* bits;         // global: [W][Ppad] hard decisions, sign bit of each 16-bit word
 };
 
 __device__ __forceinline__ void ld8(const uint4* p, uint32_t (&v)[8]) {
@@ -201,10 +200,10 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
 #pragma unroll
       for (int i = 0; i < kSW; i++) x[i] = vadd(ns[i], ap[i * T]);
     } else {
-      uint32_t pp[kSW];
-      lds8(c.perm4 + sw * gstride, pp);
+      // position table read as LDS.U16 (immediate offsets, LSU pipe) instead of unpacking pairs on the ALU pipe
+      const uint16_t* pq = c.perm16 + sw * (2 * kSW) * T;
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pp[i] & 0xFFFFu], A16[pp[i] >> 16]);
+      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pq[2 * i]], A16[pq[2 * i + 1]]);
     }
     if (sw > 0) {
       ld8(yq + (sw - 1) * gstride, ny);
@@ -229,17 +228,17 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
   if (DEC == 0) ld8(c.sys4, ns);
 #pragma unroll 1
   for (int sw = 0; sw < nsw; sw++) {
-    uint32_t x[kSW], y[kSW], aux[kSW];     // aux: DEC1 systematic LLRs, DEC2 position pairs
+    uint32_t x[kSW], y[kSW], aux[kSW];     // aux: DEC1 systematic LLRs
     uint32_t* ap = c.Aw + sw * kSW * T + t;
+    const uint16_t* pq = c.perm16 + sw * (2 * kSW) * T;
 #pragma unroll
     for (int i = 0; i < kSW; i++) y[i] = ny[i];
     if (DEC == 0) {
 #pragma unroll
       for (int i = 0; i < kSW; i++) { aux[i] = ns[i]; x[i] = vadd(ns[i], ap[i * T]); }
     } else {
-      lds8(c.perm4 + sw * gstride, aux);
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[aux[i] & 0xFFFFu], A16[aux[i] >> 16]);
+      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pq[2 * i]], A16[pq[2 * i + 1]]);
     }
     if (sw + 1 < nsw) {
       ld8(yq + (sw + 1) * gstride, ny);
@@ -259,14 +258,14 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
       if (DEC == 0) {
         ap[i * T] = vadd(aux[i], la);
       } else {
-        const uint32_t p0 = aux[i] & 0xFFFFu, p1 = aux[i] >> 16;
+        const uint32_t p0 = pq[2 * i], p1 = pq[2 * i + 1];
         A16[p0] = (int16_t)(la & 0xFFFFu);
         A16[p1] = (int16_t)(la >> 16);
         if (store_bits) {
-          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext); the byte keeps it in bit 7
+          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
           const uint32_t nd = vsub(0u, vadd(x[i], ext));
-          c.bits[p0] = (uint8_t)(nd >> 8);
-          c.bits[p1] = (uint8_t)(nd >> 24);
+          c.bits[p0] = (uint16_t)nd;
+          c.bits[p1] = (uint16_t)(nd >> 16);
         }
       }
       alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
@@ -296,10 +295,10 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
   SlotCtx c;
   c.Aw = s_slots + (size_t)(valid ? slot : 0) * slot_words;
   c.ckpt4 = reinterpret_cast<uint4*>(c.Aw + plane / 2) + 2 * t;
-  c.perm4 = reinterpret_cast<const uint4*>(s_permw) + 2 * t;
+  c.perm16 = reinterpret_cast<const uint16_t*>(s_permw) + 2 * kSW * t;
   const size_t gslot = (size_t)blockIdx.x * g.ncb_cta + (valid ? slot : 0);
   c.nii = g.nii + gslot * (size_t)(2 * 2 * 2 * 8 * NP);
-  c.bits = g.bits_scratch + gslot * (size_t)plane;
+  c.bits = reinterpret_cast<uint16_t*>(g.bits_scratch) + gslot * (size_t)plane;
   __syncthreads();
 
   const int n_groups = (g.n_cb + g.ncb_cta - 1) / g.ncb_cta;
@@ -315,6 +314,17 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
     // a-priori LLRs start at zero: each thread clears its own column of A
     if (active)
       for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
+    // pull the channel LLRs of this CTA's NEXT code blocks into L2 while the current ones are decoded,
+    // so that their first (otherwise HBM-latency) pass finds them on chip
+    {
+      const int ncb_next = (grp + (int)gridDim.x) * g.ncb_cta + slot;
+      if (valid && ncb_next < g.n_cb) {
+        const long long nbi = g.cb_list ? g.cb_list[ncb_next] : ncb_next;
+        const char* base = reinterpret_cast<const char*>(g.in + nbi * g.in_stride);
+        const int bytes = (3 * plane + 16) * 2;
+        for (int o = t * 128; o < bytes; o += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
 
     bool done = !active;
     int n_iter = 0, crc_ok = 0;
@@ -329,13 +339,13 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
         if (!done) {
           // per-window CRC: remainder of (window bits * x^24), then shifted to the window's place
           uint32_t c0 = 0, c1 = 0;
-          const uint8_t* bp = c.bits + 2 * t;
-#pragma unroll 4
+          const uint32_t* bp = reinterpret_cast<const uint32_t*>(c.bits) + t;
+#pragma unroll 16
           for (int i = 0; i < W; i++) {
-            const uint32_t w = *reinterpret_cast<const uint16_t*>(bp + (size_t)i * g.Ppad);
+            const uint32_t w = bp[i * T];
             const uint32_t u = __ldg(g.crcU + i);
-            c0 ^= sign_fill<0x8888>(w) & u;      // all-ones when bit 7 of byte 0 is set
-            c1 ^= sign_fill<0x9999>(w) & u;      // same for byte 1
+            c0 ^= sign_fill<0x9999>(w) & u;      // all-ones when the low half is negative (bit 15)
+            c1 ^= sign_fill<0xBBBB>(w) & u;      // same for the high half (bit 31)
           }
           const uint32_t contrib = gf_mul24(c0, __ldg(g.crcV + 2 * t), g.crc_poly) ^
                                    gf_mul24(c1, __ldg(g.crcV + 2 * t + 1), g.crc_poly);
@@ -350,17 +360,18 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
     if (active) {
       uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
       const int wbytes = W / 8;
-#pragma unroll 1
-      for (int h = 0; h < 2; h++) {
-        const int j = 2 * t + h;
-        if (j >= P) break;
-#pragma unroll 1
-        for (int bb = 0; bb < wbytes; bb++) {
-          uint32_t v = 0;
+      const uint32_t* bp = reinterpret_cast<const uint32_t*>(c.bits) + t;
+#pragma unroll 2
+      for (int bb = 0; bb < wbytes; bb++) {
+        uint32_t v0 = 0, v1 = 0;
 #pragma unroll
-          for (int q = 0; q < 8; q++) v = (v << 1) | (c.bits[(size_t)(bb * 8 + q) * g.Ppad + j] >> 7);
-          out[j * wbytes + bb] = (uint8_t)v;
+        for (int q = 0; q < 8; q++) {
+          const uint32_t w = bp[(bb * 8 + q) * T];
+          v0 = (v0 << 1) | ((w >> 15) & 1u);
+          v1 = (v1 << 1) | (w >> 31);
         }
+        out[(2 * t) * wbytes + bb] = (uint8_t)v0;
+        if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)v1;
       }
       if (t == 0) g.out_status[cbi] = n_iter | (crc_ok << 8);
     }
