@@ -47,15 +47,19 @@ cudaError_t upload(T** d, const std::vector<T>& h) {
 struct TurboTables {
   TurboGeom g{};
   uint16_t* d_perm = nullptr;
-  uint32_t* d_crcU[2] = {nullptr, nullptr};   // [0] CRC24A, [1] CRC24B
-  uint32_t* d_crcV[2] = {nullptr, nullptr};
+  uint32_t* d_tpos[2] = {nullptr, nullptr};   // [0] CRC24A, [1] CRC24B
 };
 
 struct Scratch {
   int16_t* nii = nullptr; size_t nii_elems = 0;
   uint8_t* bits = nullptr; size_t bits_bytes = 0;
   int16_t* tcb = nullptr; size_t tcb_elems = 0;
-  void release() { cudaFree(nii); cudaFree(bits); cudaFree(tcb); nii = nullptr; bits = nullptr; tcb = nullptr; nii_elems = bits_bytes = tcb_elems = 0; }
+  uint4* ckpt = nullptr; size_t ckpt_bytes = 0;
+  int* counter = nullptr;
+  void release() {
+    cudaFree(nii); cudaFree(bits); cudaFree(tcb); cudaFree(ckpt); cudaFree(counter); counter = nullptr;
+    nii = nullptr; bits = nullptr; tcb = nullptr; ckpt = nullptr; nii_elems = bits_bytes = tcb_elems = ckpt_bytes = 0;
+  }
 };
 
 }  // namespace
@@ -84,10 +88,9 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   CU_CHECK(upload(&t.d_perm, pos));
   const uint32_t polys[2] = {kCrc24A, kCrc24B};
   for (int i = 0; i < 2; i++) {
-    std::vector<uint32_t> U, V;
-    turbo_crc_tables(t.g, polys[i], U, V);
-    CU_CHECK(upload(&t.d_crcU[i], U));
-    CU_CHECK(upload(&t.d_crcV[i], V));
+    std::vector<uint32_t> tpos;
+    turbo_crc_table(t.g, polys[i], tpos);
+    CU_CHECK(upload(&t.d_tpos[i], tpos));
   }
   auto ins = ctx->turbo.emplace(K, t);
   *out = &ins.first->second;
@@ -96,11 +99,10 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
 
 struct TurboLaunchCfg { int ncb, threads, grid, smem; };
 
-TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb) {
-  const int nsw = g.W / 8;
-  const int slot_bytes = g.plane * 2 + nsw * 8 * g.T * 4;
-  const int fixed = g.plane * 2 + 64;
-  int ncb = (ctx->smem_optin - fixed) / (slot_bytes + 4);
+TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb, bool crc) {
+  const int slot_bytes = g.plane * 2;
+  const int fixed = g.plane * 2 + (crc ? g.plane * 4 : 0) + 64;     // position table (+ CRC table)
+  int ncb = (ctx->smem_optin - fixed) / (slot_bytes + 8);
   ncb = std::min(ncb, kTurboMaxThreads / g.T);
   // spread small batches over all SMs rather than filling a few CTAs
   ncb = std::min(ncb, std::max(1, (n_cb + ctx->num_sms - 1) / ctx->num_sms));
@@ -109,7 +111,7 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   c.ncb = ncb;
   c.threads = ((ncb * g.T + 31) / 32) * 32;
   c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms);
-  c.smem = g.plane * 2 + ((ncb + 3) & ~3) * 4 + ncb * slot_bytes;
+  c.smem = g.plane * 2 + (crc ? g.plane * 4 : 0) + 2 * ((ncb + 3) & ~3) * 4 + ncb * slot_bytes;
   return c;
 }
 
@@ -129,10 +131,12 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   int rc = get_turbo_tables(ctx, K, &tt);
   if (rc) return rc;
   const TurboGeom& g = tt->g;
-  const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb);
+  const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb, crc_type != 0);
   const size_t slots = (size_t)lc.grid * lc.ncb;
   rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), slots * (size_t)g.plane * 2, 0);
   if (rc) return rc;
+  const size_t ckpt_bytes = slots * (size_t)(g.W / 8) * g.T * 32;
+  if (ckpt_bytes > scr.ckpt_bytes) { cudaFree(scr.ckpt); CU_CHECK(cudaMalloc((void**)&scr.ckpt, ckpt_bytes)); scr.ckpt_bytes = ckpt_bytes; }
   if (!ctx->attr_set) {
     CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     ctx->attr_set = true;
@@ -144,11 +148,16 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   a.crc_poly = (crc_type == 2) ? kCrc24B : kCrc24A;
   a.K = g.K; a.W = g.W; a.P = g.P; a.Ppad = g.Ppad; a.T = g.T; a.plane = g.plane;
   a.perm_pos = tt->d_perm;
-  a.crcU = tt->d_crcU[crc_type == 2 ? 1 : 0];
-  a.crcV = tt->d_crcV[crc_type == 2 ? 1 : 0];
+  a.crc_tpos = tt->d_tpos[crc_type == 2 ? 1 : 0];
   a.ncb_cta = lc.ncb;
   a.nii = scr.nii;
   a.bits_scratch = scr.bits;
+  a.ckpt = scr.ckpt;
+  if (!scr.counter) CU_CHECK(cudaMalloc((void**)&scr.counter, 256));
+  // work counter of the persistent slots: the first grid * ncb code blocks are assigned statically
+  CU_CHECK(cudaMemsetAsync(scr.counter, 0, sizeof(int), st));
+  a.work_counter = scr.counter;
+  a.work_base = lc.grid * lc.ncb;
   turbo_decode_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   CU_CHECK(cudaGetLastError());
   ctx->last_grid = lc.grid; ctx->last_block = lc.threads; ctx->last_smem = lc.smem; ctx->last_ncb = lc.ncb;
@@ -213,7 +222,7 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->turbo) {
     cudaFree(kv.second.d_perm);
-    for (int i = 0; i < 2; i++) { cudaFree(kv.second.d_crcU[i]); cudaFree(kv.second.d_crcV[i]); }
+    for (int i = 0; i < 2; i++) cudaFree(kv.second.d_tpos[i]);
   }
   ctx->scratch.release();
   delete ctx;

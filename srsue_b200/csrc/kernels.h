@@ -7,7 +7,7 @@
 
 namespace srsue {
 
-constexpr int kTurboMaxThreads = 256;
+constexpr int kTurboMaxThreads = 384;
 
 struct TurboGeomDev { int K, W, P, Ppad, T, plane, cb_elems; };
 
@@ -23,11 +23,13 @@ struct TurboArgs {
   uint32_t crc_poly;
   int K, W, P, Ppad, T, plane;
   const uint16_t* perm_pos;  // [plane]
-  const uint32_t* crcU;      // [W]
-  const uint32_t* crcV;      // [Ppad]
+  const uint32_t* crc_tpos;  // [plane] x^(K-1-n+24) mod g at the A position of bit n (0 in padding columns)
   int ncb_cta;               // code-block slots per CTA
   int16_t* nii;              // [grid * ncb_cta][2][2][2][8][Ppad + 2]
-  uint8_t* bits_scratch;     // [grid * ncb_cta][plane]
+  uint8_t* bits_scratch;     // [grid * ncb_cta][plane] x 16 bit
+  uint4* ckpt;               // [grid * ncb_cta][W/8][T][2]  beta checkpoints
+  int* work_counter;         // dynamic work items handed out so far (zeroed before the launch)
+  int work_base;             // first dynamically assigned code block = grid * ncb_cta
 };
 
 __global__ void turbo_decode_kernel(const TurboArgs g);

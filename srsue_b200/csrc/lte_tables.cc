@@ -200,10 +200,14 @@ void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos) {
     }
 }
 
-void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& U, std::vector<uint32_t>& V) {
-  U.resize(g.W); V.assign(g.Ppad, 0);
-  for (int i = 0; i < g.W; i++) U[i] = crc_xpow(poly, (uint64_t)(g.W - 1 - i + 24));
-  for (int j = 0; j < g.P; j++) V[j] = crc_xpow(poly, (uint64_t)(g.P - 1 - j) * g.W);
+void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tpos) {
+  tpos.assign(g.plane, 0u);
+  uint32_t v = crc_xpow(poly, 24);                 // contribution of the last bit, n = K-1
+  for (int n = g.K - 1; n >= 0; n--) {
+    tpos[(n % g.W) * g.Ppad + n / g.W] = v;
+    v <<= 1;                                         // times x, reduced
+    if (v & 0x1000000u) v ^= poly;
+  }
 }
 
 int tcb_offset(const TurboGeom& g, int triple_index) {

@@ -64,8 +64,9 @@ void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_s
 // DEC2 access table: for trellis step i of window j (entry in tcb plane order) the position of
 // pi(j*W+i) in the shared exchange array A, which is laid out [W][Ppad]
 void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos);
-// CRC helpers for the per-window parallel CRC: U[i] = x^(W-1-i+24) mod g, V[j] = x^((P-1-j)W) mod g
-void turbo_crc_tables(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& U, std::vector<uint32_t>& V);
+// CRC contribution of a hard bit at every position of the exchange array A ([W][Ppad]): the CRC of the K
+// decoded bits is the XOR over the set bits n of x^(K-1-n+24) mod g (zero initial state, no final xor)
+void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tpos);
 
 // Rate de-matching gather table for one (K, F, rv): for every element m of the tcb buffer
 // (cb_elems entries) the first circular-buffer read index n in [0, N) that lands on it, 0xFFFF if

@@ -7,15 +7,19 @@
 //
 // Mapping.  One thread owns TWO adjacent windows of one code block: every 32-bit register holds the
 // same trellis state of both windows as packed int16x2, so the whole add-compare-select is
-// VIADD.16x2 / VIADDMNMX.S16x2 with no cross-lane traffic.  A CTA keeps `ncb_cta` code blocks resident:
-//   shared memory : the extrinsic exchange array A (window-transposed, so natural-order accesses are one
-//                   conflict-free LDS.32 per thread and QPP-interleaved accesses are conflict-free
-//                   LDS.U16 by the contention-free property), the beta checkpoints of the current pass
-//                   and the DEC2 position table of this K;
-//   L2 / HBM      : the channel LLRs (read-only, window-transposed "tcb" layout -> coalesced 32-bit
-//                   loads), the window-boundary metrics (NII) and the hard-decision bytes.
-// Each MAP pass is: backward sweep storing beta every 8 steps, then forward sweep that re-creates
-// beta for 8 steps in registers and produces alpha, the extrinsic and (DEC2) the hard decision.
+// VIADD.16x2 (FMA pipe) / VIADDMNMX.S16x2 (ALU pipe) with no cross-lane traffic.  A CTA is persistent and
+// keeps `ncb_cta` code-block SLOTS of T threads each; a slot that finishes a block (CRC passed or budget
+// spent) takes the next one from a global counter, so early stopping saves time per block.
+//   shared memory : the extrinsic exchange array A of every slot (window-transposed: natural-order
+//                   accesses are one conflict-free LDS.32 per thread, QPP-interleaved accesses conflict-free
+//                   LDS.U16 by the contention-free property), the DEC2 position table and the per-position
+//                   CRC contribution table of this K;
+//   L2 / HBM      : the channel LLRs (read-only, thread-contiguous "tcb" layout -> coalesced LDG.128,
+//                   register-prefetched), the thread-private beta checkpoints of the current pass, the
+//                   window-boundary metrics (NII) and the hard decisions.
+// Each MAP pass is: backward sweep storing beta every 8 steps, then forward sweep that re-creates beta
+// for 8 steps in registers and produces alpha, the extrinsic and (DEC2) the hard decision, whose CRC
+// contribution x^(position) mod g is accumulated on the fly (the CRC is linear over GF(2)).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,7 +39,8 @@ __device__ __forceinline__ uint32_t vsub(uint32_t a, uint32_t b) { return __vsub
 // max(a + b, c) per int16 half, the add wrapping (VIADDMNMX.S16x2)
 __device__ __forceinline__ uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t vclampE(uint32_t v) { return __vmins2(__vmaxs2(v, kNegEPair), kEPair); }
-__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu); }
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
+__device__ __forceinline__ uint32_t pack16s(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu); }
 
 // beta_k from beta_{k+1} (SPEC 7.4); branch labels follow the RSC trellis of 36.212 5.1.3.2.1
 __device__ __forceinline__ void beta_step(const uint32_t (&bn)[8], uint32_t (&b)[8], uint32_t x, uint32_t y, uint32_t xy) {
@@ -72,13 +77,14 @@ __device__ __forceinline__ void normalise(uint32_t (&m)[8]) {
 
 // extrinsic of one trellis step from alpha_k and beta_{k+1}: max(A10, A11 + y) - max(A00, A01 + y)
 __device__ __forceinline__ uint32_t ext_step(const uint32_t (&a)[8], const uint32_t (&bn)[8], uint32_t y) {
-  // Pipe balance (measured, profiles/alu_peak_r01.json): VIADD.16x2 issues on the FMA pipe, VIADDMNMX /
-  // VIMNMX3 on the ALU pipe, 64 lanes/clk/SM each.  Three plain adds + one 3-input max + one fused add-max
-  // per class puts 8 instructions on the ALU pipe instead of 12 (max of 4 sums is order-independent).
-  const uint32_t a00 = vaddmax(a[7], bn[3], __vimax3_s16x2(vadd(a[0], bn[0]), vadd(a[1], bn[4]), vadd(a[6], bn[7])));
-  const uint32_t a11 = vaddmax(a[7], bn[7], __vimax3_s16x2(vadd(a[0], bn[4]), vadd(a[1], bn[0]), vadd(a[6], bn[3])));
-  const uint32_t a01 = vaddmax(a[5], bn[6], __vimax3_s16x2(vadd(a[2], bn[5]), vadd(a[3], bn[1]), vadd(a[4], bn[2])));
-  const uint32_t a10 = vaddmax(a[5], bn[2], __vimax3_s16x2(vadd(a[2], bn[1]), vadd(a[3], bn[5]), vadd(a[4], bn[6])));
+  uint32_t a00 = vadd(a[0], bn[0]);
+  a00 = vaddmax(a[1], bn[4], a00); a00 = vaddmax(a[6], bn[7], a00); a00 = vaddmax(a[7], bn[3], a00);
+  uint32_t a11 = vadd(a[0], bn[4]);
+  a11 = vaddmax(a[1], bn[0], a11); a11 = vaddmax(a[6], bn[3], a11); a11 = vaddmax(a[7], bn[7], a11);
+  uint32_t a01 = vadd(a[2], bn[5]);
+  a01 = vaddmax(a[3], bn[1], a01); a01 = vaddmax(a[4], bn[2], a01); a01 = vaddmax(a[5], bn[6], a01);
+  uint32_t a10 = vadd(a[2], bn[1]);
+  a10 = vaddmax(a[3], bn[5], a10); a10 = vaddmax(a[4], bn[6], a10); a10 = vaddmax(a[5], bn[2], a10);
   const uint32_t l1 = vaddmax(a11, y, a10);
   const uint32_t l0 = vaddmax(a01, y, a00);
   return vsub(l1, l0);
@@ -92,55 +98,46 @@ __device__ __forceinline__ uint32_t sign_fill(uint32_t w) {
   return r;
 }
 
-__device__ __forceinline__ uint32_t gf_mul24(uint32_t a, uint32_t b, uint32_t poly) {
-  uint32_t r = 0;
-#pragma unroll 1
-  for (int i = 23; i >= 0; i--) {
-    r <<= 1;
-    if (r & 0x1000000u) r ^= poly;
-    if ((b >> i) & 1u) r ^= a;
-  }
-  return r & 0xFFFFFFu;
-}
-
-struct SlotCtx {
-  const uint4* sys4;      // channel LLR planes (global), this thread's first 8-step group: 2 x uint4 per group
-  const uint4* p14;
-  const uint4* p24;
-  const int16_t* tail;    // 12 tail LLRs (global)
-  uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
-  uint4* ckpt4;           // shared: beta checkpoints [nsw][T][2 x uint4], this thread's entry of group 0
-  const uint16_t* perm16; // shared: DEC2 positions [nsw][T][8 steps][2 windows], this thread's entry of group 0
-  int16_t* nii;           // global: [2 dec][2 pp][2 kind][8][NP]
-  uint16_t* bits;         // global: [W][Ppad] hard decisions, sign bit of each 16-bit word
-};
-
 __device__ __forceinline__ void ld8(const uint4* p, uint32_t (&v)[8]) {
   const uint4 a = __ldg(p), b = __ldg(p + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void lds8(const uint4* p, uint32_t (&v)[8]) {
+__device__ __forceinline__ void ldp8(const uint4* p, uint32_t (&v)[8]) {      // plain (coherent) load
   const uint4 a = p[0], b = p[1];
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void sts8(uint4* p, const uint32_t (&v)[8]) {
+__device__ __forceinline__ void st8(uint4* p, const uint32_t (&v)[8]) {
   p[0] = make_uint4(v[0], v[1], v[2], v[3]);
   p[1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 
-// One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.
+// What one slot thread needs to find its code block and its scratch; everything else is derived in place
+// (keeps the live state across the long unrolled sweeps small).
+struct SlotCtx {
+  const uint4* in4;       // code block in tcb layout (global)
+  uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
+  uint32_t gslot;         // global slot number: selects the NII / checkpoint / decision scratch
+};
+
+// One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.  Returns the
+// thread's CRC contribution of the hard decisions (DEC2 with crc_on), else 0.
 template <int DEC>
-__device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, int t, int it, bool store_bits) {
-  const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW;
+__device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm16,
+                                             const uint32_t* s_tpos, int t, int it, bool store_bits, bool crc_on) {
+  const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
   const int j0 = 2 * t, j1 = 2 * t + 1;
   const int rd = it & 1, wr = rd ^ 1;
-  const int16_t* nii_a_rd = c.nii + ((DEC * 2 + rd) * 2 + 0) * 8 * NP;
-  const int16_t* nii_b_rd = c.nii + ((DEC * 2 + rd) * 2 + 1) * 8 * NP;
-  uint32_t* nii_a_wr = reinterpret_cast<uint32_t*>(c.nii + ((DEC * 2 + wr) * 2 + 0) * 8 * NP);
-  uint32_t* nii_b_wr = reinterpret_cast<uint32_t*>(c.nii + ((DEC * 2 + wr) * 2 + 1) * 8 * NP);
-  const uint4* yq = DEC ? c.p24 : c.p14;
-  int16_t* A16 = reinterpret_cast<int16_t*>(c.Aw);
+  int16_t* nii = g.nii + (size_t)c.gslot * (size_t)(2 * 2 * 2 * 8 * NP);
+  const int16_t* nii_a_rd = nii + ((DEC * 2 + rd) * 2 + 0) * 8 * NP;
+  const int16_t* nii_b_rd = nii + ((DEC * 2 + rd) * 2 + 1) * 8 * NP;
+  uint32_t* nii_a_wr = reinterpret_cast<uint32_t*>(nii + ((DEC * 2 + wr) * 2 + 0) * 8 * NP);
+  uint32_t* nii_b_wr = reinterpret_cast<uint32_t*>(nii + ((DEC * 2 + wr) * 2 + 1) * 8 * NP);
   const int gstride = 2 * T;                       // uint4 per 8-step group
+  const uint4* sysq = c.in4 + 2 * t;
+  const uint4* yq = sysq + (DEC ? 2 : 1) * (plane / 8);
+  uint4* ckpt4 = g.ckpt + (size_t)c.gslot * (size_t)(nsw * gstride) + 2 * t;
+  uint16_t* bits = reinterpret_cast<uint16_t*>(g.bits_scratch) + (size_t)c.gslot * (size_t)plane;
+  int16_t* A16 = reinterpret_cast<int16_t*>(c.Aw);
 
   uint32_t b[8];
   // ---- beta at the end of the two windows -------------------------------------------------------
@@ -148,14 +145,15 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
     const bool last0 = (j0 == P - 1), last1 = (j1 == P - 1);
     if (last0 || last1) {
       // trellis termination: beta_{K+3} = (0, -INF, ...) and three ordinary steps over the tail
+      const int16_t* tail = reinterpret_cast<const int16_t*>(c.in4) + 3 * plane;
       uint32_t bt[8], bq[8];
       bt[0] = 0;
 #pragma unroll
       for (int s = 1; s < 8; s++) bt[s] = kNegInfPair;
 #pragma unroll
       for (int q = 2; q >= 0; q--) {
-        const int xv = c.tail[DEC * 6 + 2 * q], yv = c.tail[DEC * 6 + 2 * q + 1];
-        const uint32_t x = pack16(xv, xv), y = pack16(yv, yv);
+        const int xv = tail[DEC * 6 + 2 * q], yv = tail[DEC * 6 + 2 * q + 1];
+        const uint32_t x = pack16s(xv, xv), y = pack16s(yv, yv);
         beta_step(bt, bq, x, y, vadd(x, y));
 #pragma unroll
         for (int s = 0; s < 8; s++) bt[s] = bq[s];
@@ -166,11 +164,11 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
         int lo = 0, hi = 0;
         if (last0) lo = (int)(int16_t)(bt[s] & 0xFFFFu); else if (it) lo = nii_b_rd[s * NP + j0 + 1];
         if (last1) hi = (int)(int16_t)(bt[s] >> 16); else if (it) hi = nii_b_rd[s * NP + j1 + 1];
-        b[s] = pack16(lo, hi);
+        b[s] = pack16s(lo, hi);
       }
     } else if (it) {
 #pragma unroll
-      for (int s = 0; s < 8; s++) b[s] = pack16(nii_b_rd[s * NP + j0 + 1], nii_b_rd[s * NP + j1 + 1]);
+      for (int s = 0; s < 8; s++) b[s] = pack16s(nii_b_rd[s * NP + j0 + 1], nii_b_rd[s * NP + j1 + 1]);
     } else {
 #pragma unroll
       for (int s = 0; s < 8; s++) b[s] = 0;
@@ -183,40 +181,42 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
     int lo, hi;
     if (j0 == 0) lo = s ? -kTdInf : 0; else lo = it ? nii_a_rd[s * NP + j0 - 1] : 0;
     hi = it ? nii_a_rd[s * NP + j0] : 0;
-    a[s] = pack16(lo, hi);
+    a[s] = pack16s(lo, hi);
   }
 
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
-  uint32_t ny[kSW], ns[kSW];                        // register prefetch of the next group's channel LLRs
-  ld8(yq + (nsw - 1) * gstride, ny);
-  if (DEC == 0) ld8(c.sys4 + (nsw - 1) * gstride, ns);
+  {
+    uint32_t ny[kSW], ns[kSW];                      // register prefetch of the next group's channel LLRs
+    ld8(yq + (nsw - 1) * gstride, ny);
+    if (DEC == 0) ld8(sysq + (nsw - 1) * gstride, ns);
 #pragma unroll 1
-  for (int sw = nsw - 1; sw >= 0; sw--) {
-    uint32_t x[kSW], y[kSW];
+    for (int sw = nsw - 1; sw >= 0; sw--) {
+      uint32_t x[kSW], y[kSW];
 #pragma unroll
-    for (int i = 0; i < kSW; i++) y[i] = ny[i];
-    if (DEC == 0) {
-      const uint32_t* ap = c.Aw + sw * kSW * T + t;
+      for (int i = 0; i < kSW; i++) y[i] = ny[i];
+      if (DEC == 0) {
+        const uint32_t* ap = c.Aw + sw * kSW * T + t;
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = vadd(ns[i], ap[i * T]);
-    } else {
-      // position table read as LDS.U16 (immediate offsets, LSU pipe) instead of unpacking pairs on the ALU pipe
-      const uint16_t* pq = c.perm16 + sw * (2 * kSW) * T;
+        for (int i = 0; i < kSW; i++) x[i] = vadd(ns[i], ap[i * T]);
+      } else {
+        // position table read as LDS.U16 (immediate offsets, LSU pipe), not unpacked on the ALU pipe
+        const uint16_t* pq = perm16 + sw * (2 * kSW) * T;
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pq[2 * i]], A16[pq[2 * i + 1]]);
-    }
-    if (sw > 0) {
-      ld8(yq + (sw - 1) * gstride, ny);
-      if (DEC == 0) ld8(c.sys4 + (sw - 1) * gstride, ns);
-    }
-    sts8(c.ckpt4 + sw * gstride, b);
+        for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
+      }
+      if (sw > 0) {
+        ld8(yq + (sw - 1) * gstride, ny);
+        if (DEC == 0) ld8(sysq + (sw - 1) * gstride, ns);
+      }
+      st8(ckpt4 + sw * gstride, b);                 // thread-private scratch, read back in pass 2
 #pragma unroll
-    for (int i = kSW - 1; i >= 0; i--) {
-      uint32_t nb[8];
-      beta_step(b, nb, x[i], y[i], vadd(x[i], y[i]));
+      for (int i = kSW - 1; i >= 0; i--) {
+        uint32_t nb[8];
+        beta_step(b, nb, x[i], y[i], vadd(x[i], y[i]));
 #pragma unroll
-      for (int s = 0; s < 8; s++) b[s] = nb[s];
-      if ((i & 3) == 0) normalise(b);
+        for (int s = 0; s < 8; s++) b[s] = nb[s];
+        if ((i & 3) == 0) normalise(b);
+      }
     }
   }
   // beta at the window start feeds the previous window in the next iteration
@@ -224,143 +224,129 @@ __device__ __forceinline__ void map_pass(const TurboArgs& g, const SlotCtx& c, i
   for (int s = 0; s < 8; s++) nii_b_wr[(s * NP + j0) >> 1] = b[s];
 
   // ---- pass 2: forward sweep ----------------------------------------------------------------------
-  ld8(yq, ny);
-  if (DEC == 0) ld8(c.sys4, ns);
+  uint32_t crc = 0;
+  {
+    uint32_t ny[kSW], ns[kSW], nbeta[8];            // register prefetch: channel LLRs, next checkpoint
+    ld8(yq, ny);
+    if (DEC == 0) ld8(sysq, ns);
+    ldp8(ckpt4, nbeta);
 #pragma unroll 1
-  for (int sw = 0; sw < nsw; sw++) {
-    uint32_t x[kSW], y[kSW], aux[kSW];     // aux: DEC1 systematic LLRs
-    uint32_t* ap = c.Aw + sw * kSW * T + t;
-    const uint16_t* pq = c.perm16 + sw * (2 * kSW) * T;
+    for (int sw = 0; sw < nsw; sw++) {
+      uint32_t x[kSW], y[kSW], aux[kSW];            // aux: DEC1 systematic LLRs
+      uint32_t* ap = c.Aw + sw * kSW * T + t;
+      const uint16_t* pq = perm16 + sw * (2 * kSW) * T;
 #pragma unroll
-    for (int i = 0; i < kSW; i++) y[i] = ny[i];
-    if (DEC == 0) {
-#pragma unroll
-      for (int i = 0; i < kSW; i++) { aux[i] = ns[i]; x[i] = vadd(ns[i], ap[i * T]); }
-    } else {
-#pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = pack16(A16[pq[2 * i]], A16[pq[2 * i + 1]]);
-    }
-    if (sw + 1 < nsw) {
-      ld8(yq + (sw + 1) * gstride, ny);
-      if (DEC == 0) ld8(c.sys4 + (sw + 1) * gstride, ns);
-    }
-    uint32_t B[kSW][8];                     // B[i] = beta_{i+1} of this sub-window
-    lds8(c.ckpt4 + sw * gstride, B[kSW - 1]);
-#pragma unroll
-    for (int i = kSW - 1; i >= 1; i--) {
-      beta_step(B[i], B[i - 1], x[i], y[i], vadd(x[i], y[i]));
-      if ((i & 3) == 0) normalise(B[i - 1]);
-    }
-#pragma unroll
-    for (int i = 0; i < kSW; i++) {
-      const uint32_t ext = ext_step(a, B[i], y[i]);
-      const uint32_t la = vclampE(ext);
+      for (int i = 0; i < kSW; i++) y[i] = ny[i];
       if (DEC == 0) {
-        ap[i * T] = vadd(aux[i], la);
+#pragma unroll
+        for (int i = 0; i < kSW; i++) { aux[i] = ns[i]; x[i] = vadd(ns[i], ap[i * T]); }
       } else {
-        const uint32_t p0 = pq[2 * i], p1 = pq[2 * i + 1];
-        A16[p0] = (int16_t)(la & 0xFFFFu);
-        A16[p1] = (int16_t)(la >> 16);
-        if (store_bits) {
-          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
-          const uint32_t nd = vsub(0u, vadd(x[i], ext));
-          c.bits[p0] = (uint16_t)nd;
-          c.bits[p1] = (uint16_t)(nd >> 16);
-        }
+#pragma unroll
+        for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
       }
-      alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
-      if ((i & 3) == 3) normalise(a);
+      uint32_t B[kSW][8];                           // B[i] = beta_{i+1} of this sub-window
+#pragma unroll
+      for (int s = 0; s < 8; s++) B[kSW - 1][s] = nbeta[s];
+      if (sw + 1 < nsw) {
+        ld8(yq + (sw + 1) * gstride, ny);
+        if (DEC == 0) ld8(sysq + (sw + 1) * gstride, ns);
+        ldp8(ckpt4 + (sw + 1) * gstride, nbeta);
+      }
+#pragma unroll
+      for (int i = kSW - 1; i >= 1; i--) {
+        beta_step(B[i], B[i - 1], x[i], y[i], vadd(x[i], y[i]));
+        if ((i & 3) == 0) normalise(B[i - 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < kSW; i++) {
+        const uint32_t ext = ext_step(a, B[i], y[i]);
+        const uint32_t la = vclampE(ext);
+        if (DEC == 0) {
+          ap[i * T] = vadd(aux[i], la);
+        } else {
+          const uint32_t p0 = pq[2 * i], p1 = pq[2 * i + 1];
+          A16[p0] = (int16_t)(la & 0xFFFFu);
+          A16[p1] = (int16_t)(la >> 16);
+          if (store_bits) {
+            // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
+            const uint32_t nd = vsub(0u, vadd(x[i], ext));
+            bits[p0] = (uint16_t)nd;
+            bits[p1] = (uint16_t)(nd >> 16);
+            if (crc_on) crc ^= (sign_fill<0x9999>(nd) & s_tpos[p0]) ^ (sign_fill<0xBBBB>(nd) & s_tpos[p1]);
+          }
+        }
+        alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
+        if ((i & 3) == 3) normalise(a);
+      }
     }
   }
 #pragma unroll
   for (int s = 0; s < 8; s++) nii_a_wr[(s * NP + j0) >> 1] = a[s];
+  return crc;
 }
 
 }  // namespace
 
 __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int T = g.T, W = g.W, P = g.P, plane = g.plane, NP = g.Ppad + 2, nsw = W / kSW;
+  const int T = g.T, W = g.W, P = g.P, plane = g.plane;
   const int tid = threadIdx.x;
   const int slot = tid / T, t = tid - slot * T;
   const bool valid = slot < g.ncb_cta;
+  const bool crc_on = g.crc_type != 0;
+  const int nflag = (g.ncb_cta + 3) & ~3;
 
-  uint32_t* s_permw = smem;                                  // plane/2 words, [nsw][T][8]
-  uint32_t* s_crc = s_permw + plane / 2;                     // ncb_cta words (rounded to 4)
-  uint32_t* s_slots = s_crc + ((g.ncb_cta + 3) & ~3);
-  const int slot_words = plane / 2 + nsw * 8 * T;            // A + checkpoints
+  uint32_t* s_permw = smem;                                  // plane/2 words: DEC2 positions [W/8][T][8][2] x u16
+  uint32_t* s_tpos = s_permw + plane / 2;                    // plane words (0 without CRC): x^(pos) mod g per A position
+  uint32_t* s_crc = s_tpos + (crc_on ? plane : 0);           // per slot: CRC accumulator
+  int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item
+  uint32_t* s_slots = s_crc + 2 * nflag;                     // per slot: A, plane/2 words
 
   for (int i = tid; i < plane / 2; i += blockDim.x) s_permw[i] = reinterpret_cast<const uint32_t*>(g.perm_pos)[i];
+  if (crc_on)
+    for (int i = tid; i < plane; i += blockDim.x) s_tpos[i] = g.crc_tpos[i];
 
   SlotCtx c;
-  c.Aw = s_slots + (size_t)(valid ? slot : 0) * slot_words;
-  c.ckpt4 = reinterpret_cast<uint4*>(c.Aw + plane / 2) + 2 * t;
-  c.perm16 = reinterpret_cast<const uint16_t*>(s_permw) + 2 * kSW * t;
-  const size_t gslot = (size_t)blockIdx.x * g.ncb_cta + (valid ? slot : 0);
-  c.nii = g.nii + gslot * (size_t)(2 * 2 * 2 * 8 * NP);
-  c.bits = reinterpret_cast<uint16_t*>(g.bits_scratch) + gslot * (size_t)plane;
+  c.Aw = s_slots + (size_t)(valid ? slot : 0) * (plane / 2);
+  c.gslot = blockIdx.x * g.ncb_cta + (valid ? slot : 0);
+  c.in4 = nullptr;
+  const uint16_t* perm16 = reinterpret_cast<const uint16_t*>(s_permw) + 2 * kSW * t;
+
+  // ---- persistent slots ------------------------------------------------------------------------------
+  int cur = blockIdx.x * g.ncb_cta + slot;                    // the first assignment is static
+  bool have = valid && cur < g.n_cb;
+  long long cbi = 0;
+  int it = 0;
+  auto init_slot = [&]() {
+    cbi = g.cb_list ? g.cb_list[cur] : cur;
+    c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
+    // a-priori LLRs start at zero: each thread clears its own column of A
+    for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
+    // start pulling the second decoder's parity plane towards L2 (its first use is one pass away)
+    const uint4* p2 = c.in4 + 2 * (plane / 8) + 2 * t;
+    for (int sw = 0; sw < W / kSW; sw++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + sw * 2 * T));
+  };
+  if (have) init_slot();
   __syncthreads();
 
-  const int n_groups = (g.n_cb + g.ncb_cta - 1) / g.ncb_cta;
-  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int cb = grp * g.ncb_cta + slot;
-    const bool active = valid && cb < g.n_cb;
-    const long long cbi = active ? (g.cb_list ? g.cb_list[cb] : cb) : 0;
-    const int16_t* in_cb = g.in + cbi * g.in_stride;
-    c.sys4 = reinterpret_cast<const uint4*>(in_cb) + 2 * t;
-    c.p14 = c.sys4 + plane / 8;
-    c.p24 = c.p14 + plane / 8;
-    c.tail = in_cb + 3 * plane;
-    // a-priori LLRs start at zero: each thread clears its own column of A
-    if (active)
-      for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
-    // pull the channel LLRs of this CTA's NEXT code blocks into L2 while the current ones are decoded,
-    // so that their first (otherwise HBM-latency) pass finds them on chip
-    {
-      const int ncb_next = (grp + (int)gridDim.x) * g.ncb_cta + slot;
-      if (valid && ncb_next < g.n_cb) {
-        const long long nbi = g.cb_list ? g.cb_list[ncb_next] : ncb_next;
-        const char* base = reinterpret_cast<const char*>(g.in + nbi * g.in_stride);
-        const int bytes = (3 * plane + 16) * 2;
-        for (int o = t * 128; o < bytes; o += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
-      }
+  while (true) {
+    if (__syncthreads_and(!have)) break;
+    if (valid && t == 0) s_crc[slot] = 0;
+    const bool store_bits = crc_on || (it == g.max_iter - 1);
+    if (have) map_pass<0>(g, c, perm16, s_tpos, t, it, store_bits, crc_on);
+    __syncthreads();
+    if (have) {
+      const uint32_t part = map_pass<1>(g, c, perm16, s_tpos, t, it, store_bits, crc_on);
+      if (crc_on) atomicXor(&s_crc[slot], part);
     }
-
-    bool done = !active;
-    int n_iter = 0, crc_ok = 0;
-    for (int it = 0; it < g.max_iter; it++) {
-      if (valid && t == 0) s_crc[slot] = 0;
-      const bool store_bits = (g.crc_type != 0) || (it == g.max_iter - 1);
-      if (!done) map_pass<0>(g, c, t, it, store_bits);
-      __syncthreads();
-      if (!done) { map_pass<1>(g, c, t, it, store_bits); n_iter = it + 1; }
-      __syncthreads();
-      if (g.crc_type != 0) {
-        if (!done) {
-          // per-window CRC: remainder of (window bits * x^24), then shifted to the window's place
-          uint32_t c0 = 0, c1 = 0;
-          const uint32_t* bp = reinterpret_cast<const uint32_t*>(c.bits) + t;
-#pragma unroll 16
-          for (int i = 0; i < W; i++) {
-            const uint32_t w = bp[i * T];
-            const uint32_t u = __ldg(g.crcU + i);
-            c0 ^= sign_fill<0x9999>(w) & u;      // all-ones when the low half is negative (bit 15)
-            c1 ^= sign_fill<0xBBBB>(w) & u;      // same for the high half (bit 31)
-          }
-          const uint32_t contrib = gf_mul24(c0, __ldg(g.crcV + 2 * t), g.crc_poly) ^
-                                   gf_mul24(c1, __ldg(g.crcV + 2 * t + 1), g.crc_poly);
-          atomicXor(&s_crc[slot], contrib);
-        }
-        __syncthreads();
-        if (!done && s_crc[slot] == 0) { done = true; crc_ok = 1; }
-      }
-      if (__syncthreads_and(done)) break;
-    }
-    // ---- pack the hard decisions of the last iteration, MSB first, natural order ----------------
-    if (active) {
+    __syncthreads();
+    const bool crc_ok = crc_on && valid && s_crc[slot] == 0;
+    const bool fin = have && (crc_ok || it + 1 >= g.max_iter);
+    if (fin) {
+      // ---- pack the hard decisions of this iteration, MSB first, natural order --------------------
       uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
       const int wbytes = W / 8;
-      const uint32_t* bp = reinterpret_cast<const uint32_t*>(c.bits) + t;
+      const uint32_t* bp = reinterpret_cast<const uint32_t*>(g.bits_scratch) + ((size_t)c.gslot * plane) / 2 + t;
 #pragma unroll 2
       for (int bb = 0; bb < wbytes; bb++) {
         uint32_t v0 = 0, v1 = 0;
@@ -373,9 +359,20 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
         out[(2 * t) * wbytes + bb] = (uint8_t)v0;
         if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)v1;
       }
-      if (t == 0) g.out_status[cbi] = n_iter | (crc_ok << 8);
+      if (t == 0) {
+        g.out_status[cbi] = (it + 1) | ((crc_ok ? 1 : 0) << 8);
+        s_next[slot] = g.work_base + atomicAdd(g.work_counter, 1);
+      }
+    } else if (have) {
+      it++;
     }
     __syncthreads();
+    if (fin) {
+      cur = s_next[slot];
+      have = cur < g.n_cb;
+      it = 0;
+      if (have) init_slot();
+    }
   }
 }
 
