@@ -126,6 +126,20 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t *plan, int n_sf, co
 /* number of kernels the most recent chain call launched (for the benchmark's gpu_launches) */
 int srsue_gpu_last_launch_count(srsue_gpu_ctx_t *ctx);
 
+/* ---- host-side bookkeeping, usable without a GPU (what srslte_ue_dl_cfg_grant computes on the host,
+ * phch_worker.cc:337; exported so that the tables can be checked on a CPU-only machine) ------------- */
+/* code-block segmentation of a transport block: out[8] = tbs, B, C, K+, K-, C+, C-, F */
+int srsue_gpu_host_cbsegm(int tbs, int *out);
+/* number of PDSCH resource elements of a grant; re_idx (optional) receives l*nsc + k for each */
+int srsue_gpu_host_pdsch_re(const srsue_gpu_cell_t *cell, const srsue_gpu_pdsch_cfg_t *cfg, int32_t *re_idx);
+/* rate-matching read order for (K, F, rv): seq[n] = index 3k+stream of the n-th non-null circular-buffer
+ * position (srsLTE decoder-input order); returns the number of entries (<= 3K+12) */
+int srsue_gpu_host_rm_sequence(int K, int F, int rv, int32_t *seq);
+/* QPP interleaver pi(i) for code-block size K */
+int srsue_gpu_host_qpp(int K, uint16_t *pi);
+/* n bits of the Gold sequence with the given c_init, one per byte */
+int srsue_gpu_host_gold(uint32_t c_init, int n, uint8_t *c);
+
 /* ---- pinned host memory helpers (so callers need not link the CUDA runtime) ------------------- */
 void *srsue_gpu_host_alloc(uint64_t bytes);
 void srsue_gpu_host_free(void *p);

@@ -282,7 +282,14 @@ void lteo_rm_rx(const int16_t *e, int E, int K, int F, int rv, int16_t *w) {
 /* ------------------------------------------------------------------------------------------------
  * Turbo decoder (SPEC.md 7): int16 max-log-MAP, parallel windows with next-iteration initialisation
  * ---------------------------------------------------------------------------------------------- */
-static inline int16_t w16(int v) { return (int16_t)(uint16_t)v; }   /* two's-complement wrap */
+/* two's-complement wrap; every time the exact value does not fit is counted so that tests can check the
+ * no-wrap argument of SPEC.md 7.6 (the counter is diagnostic only, not thread safe) */
+static long g_wrap_events = 0;
+static inline int16_t w16(int v) {
+  if (v > 32767 || v < -32768) g_wrap_events++;
+  return (int16_t)(uint16_t)v;
+}
+long lteo_wrap_events(int reset) { long v = g_wrap_events; if (reset) g_wrap_events = 0; return v; }
 static inline int16_t clampi(int v, int lim) { return (int16_t)(v > lim ? lim : (v < -lim ? -lim : v)); }
 static inline int16_t max16(int16_t a, int16_t b) { return a > b ? a : b; }
 

@@ -631,6 +631,51 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t* p, int n_sf, const
   return 0;
 }
 
+int srsue_gpu_host_cbsegm(int tbs, int* out) {
+  CbSegm s;
+  if (!out || !cbsegm(tbs, &s)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tbs=%d cannot be segmented", tbs);
+  const int v[8] = {s.tbs, s.B, s.C, s.Kp, s.Km, s.Cp, s.Cm, s.F};
+  std::memcpy(out, v, sizeof(v));
+  return 0;
+}
+
+int srsue_gpu_host_pdsch_re(const srsue_gpu_cell_t* cell, const srsue_gpu_pdsch_cfg_t* cfg, int32_t* re_idx) {
+  if (!cell || !cfg) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  CellCfg c{cell->nof_prb, cell->nof_ports, cell->cell_id};
+  PdschCfg pc;
+  std::memcpy(&pc, cfg, sizeof(pc));
+  std::vector<int32_t> re;
+  pdsch_re_list(c, pc, re);
+  if (re_idx) std::copy(re.begin(), re.end(), re_idx);
+  return (int)re.size();
+}
+
+int srsue_gpu_host_rm_sequence(int K, int F, int rv, int32_t* seq) {
+  if (qpp_index(K) < 0 || !seq || rv < 0 || rv > 3 || F < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  // invert the gather table: tcb offset -> read index, back to srsLTE order
+  const TurboGeom g = turbo_geom(K);
+  std::vector<uint16_t> tab;
+  const int N = rm_gather_table(g, F, rv, tab);
+  for (int tri = 0; tri < 3 * (K + 4); tri++) {
+    const uint16_t n = tab[tcb_offset(g, tri)];
+    if (n < 0xFFFE) seq[n] = tri;
+  }
+  return N;
+}
+
+int srsue_gpu_host_qpp(int K, uint16_t* pi) {
+  int f1, f2;
+  if (!pi || !qpp_params(K, &f1, &f2)) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  for (int64_t i = 0; i < K; i++) pi[i] = (uint16_t)((f1 * i + (int64_t)f2 * i * i) % K);
+  return 0;
+}
+
+int srsue_gpu_host_gold(uint32_t c_init, int n, uint8_t* c) {
+  if (!c || n < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  gold_bits(c_init, n, c);
+  return 0;
+}
+
 void* srsue_gpu_host_alloc(uint64_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;

@@ -1,0 +1,72 @@
+"""Generates tests/golden/*.npz from the CPU oracle (run from the repo root: python tests/golden/make_golden.py).
+
+The reference has no fixture for this path and srsLTE cannot be run here, so these vectors do not pin the
+oracle to the reference; they freeze the oracle (= oracle/SPEC.md) so that neither it nor the CUDA kernels can
+drift silently.  Small on purpose (a few hundred KB)."""
+import os
+import sys
+import hashlib
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as o  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    # turbo decoder: a few code blocks per size, noisy, fixed iterations and CRC early stop
+    tv = {}
+    for K, ebn0 in ((40, 2.0), (512, 1.0), (1056, 1.0), (5824, 1.2)):
+        llrs, bits4, its = [], [], []
+        for i in range(3):
+            rng = np.random.default_rng(1000 * K + i)
+            c = rng.integers(0, 2, K, dtype=np.uint8)
+            crc = o.crc_bits(c[:K - 24], o.CRC24B)
+            c[K - 24:] = [(crc >> (23 - b)) & 1 for b in range(24)]
+            d = o.turbo_encode(c).astype(np.float64) * 2 - 1
+            sigma2 = 1.0 / (2.0 / 3.0 * 10 ** (ebn0 / 10))
+            d += np.random.default_rng(1000 * K + i + 5_000_000).standard_normal(len(d)) * np.sqrt(sigma2)
+            llr = np.clip(np.trunc(64 * d), -2048, 2047).astype(np.int16)
+            b, it, ok, _ = o.tdec(llr, K, 4, 0)
+            b2, it2, ok2, _ = o.tdec(llr, K, 6, 2)
+            llrs.append(llr); bits4.append(np.packbits(b)); its.append((it2, ok2, int(np.packbits(b2).sum())))
+        tv["llr_%d" % K] = np.stack(llrs)
+        tv["bits4_%d" % K] = np.stack(bits4)
+        tv["crcrun_%d" % K] = np.array(its, np.int32)
+    np.savez_compressed(os.path.join(OUT, "turbo.npz"), **tv)
+    # PDSCH chain: config 1 complete (IQ in, everything out), configs 2/3 as digests of the intermediates
+    pv = {}
+    cell = o.make_cell(6, 1, 1)
+    cfg = o.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152)
+    tb, iq, _ = o.gen_subframe(cell, cfg, 1, 10.0)
+    sf = o.ofdm_rx(6, iq); ce, meas = o.chest(cell, 1, sf)
+    rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, want=True)
+    pv.update(cfg1_iq=iq, cfg1_tb=tb, cfg1_sf=sf, cfg1_ce=ce, cfg1_meas=meas, cfg1_e=dbg["e"][:1656],
+              cfg1_softbuf=dbg["softbuf"][0, :3 * 176 + 12], cfg1_payload=pl, cfg1_rc=np.array([rc]))
+    digests = []
+    rng = np.random.default_rng(77)
+    taps = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    taps /= np.sqrt((abs(taps) ** 2).sum(1, keepdims=True))
+    for name, prb, ports, qm, tbs, tm, snr, tp in (("cfg2", 100, 1, 6, 75376, 1, 30.0, None), ("cfg3", 100, 2, 4, 30576, 2, 15.0, taps)):
+        cell = o.make_cell(prb, ports, 1)
+        cfg = o.make_cfg(cell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=tm)
+        tb, iq, _ = o.gen_subframe(cell, cfg, 20000, snr, tp)
+        sf = o.ofdm_rx(prb, iq); ce, meas = o.chest(cell, 1, sf)
+        rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, want=True)
+        s = o.cbsegm(tbs)
+        digests.append("%s iq=%s sf=%s ce=%s e=%s sb=%s payload=%s rc=%d iters=%s" % (
+            name, sha(iq), sha(sf), sha(ce), sha(dbg["e"][:len(o.pdsch_re_list(cell, cfg)) * qm]),
+            sha(dbg["softbuf"][:s.C, :3 * s.Kp + 12]), sha(pl), rc, ",".join(map(str, dbg["iters"]))))
+    pv["digests"] = np.array(digests)
+    np.savez_compressed(os.path.join(OUT, "pdsch.npz"), **pv)
+    print("\n".join(digests))
+
+
+if __name__ == "__main__":
+    main()

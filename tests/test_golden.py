@@ -1,0 +1,117 @@
+"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py): the oracle must reproduce them on
+the CPU, the CUDA kernels must reproduce them on the GPU.  Parity remains unpinned against srsLTE itself."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _taps():
+    rng = np.random.default_rng(77)
+    t = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    return t / np.sqrt((abs(t) ** 2).sum(1, keepdims=True))
+
+
+def test_oracle_reproduces_turbo_golden(oracle):
+    tv = np.load(os.path.join(G, "turbo.npz"))
+    for K in (40, 512, 1056, 5824):
+        for i, llr in enumerate(tv["llr_%d" % K]):
+            b, it, ok, _ = oracle.tdec(llr, K, 4, 0)
+            assert np.array_equal(np.packbits(b), tv["bits4_%d" % K][i])
+            b2, it2, ok2, _ = oracle.tdec(llr, K, 6, 2)
+            assert (it2, ok2, int(np.packbits(b2).sum())) == tuple(tv["crcrun_%d" % K][i])
+
+
+def test_oracle_reproduces_pdsch_golden(oracle):
+    pv = np.load(os.path.join(G, "pdsch.npz"))
+    cell = oracle.make_cell(6, 1, 1)
+    cfg = oracle.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152)
+    iq = pv["cfg1_iq"]
+    sf = oracle.ofdm_rx(6, iq)
+    ce, meas = oracle.chest(cell, 1, sf)
+    rc, pl, dbg = oracle.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, want=True)
+    assert np.array_equal(sf, pv["cfg1_sf"]) and np.array_equal(ce, pv["cfg1_ce"]) and np.array_equal(meas, pv["cfg1_meas"])
+    assert np.array_equal(dbg["e"][:1656], pv["cfg1_e"])
+    assert np.array_equal(dbg["softbuf"][0, :3 * 176 + 12], pv["cfg1_softbuf"])
+    assert np.array_equal(pl, pv["cfg1_payload"]) and np.array_equal(pl, pv["cfg1_tb"]) and rc == int(pv["cfg1_rc"][0])
+    # the generator itself is part of what the digests freeze
+    tb, iq2, _ = oracle.gen_subframe(cell, cfg, 1, 10.0)
+    assert np.array_equal(iq2, iq)
+
+
+@pytest.mark.parametrize("idx,name,prb,ports,qm,tbs,tm,snr", [(0, "cfg2", 100, 1, 6, 75376, 1, 30.0), (1, "cfg3", 100, 2, 4, 30576, 2, 15.0)])
+def test_oracle_reproduces_digests(oracle, idx, name, prb, ports, qm, tbs, tm, snr):
+    pv = np.load(os.path.join(G, "pdsch.npz"))
+    want = dict(kv.split("=") for kv in str(pv["digests"][idx]).split()[1:])
+    cell = oracle.make_cell(prb, ports, 1)
+    cfg = oracle.make_cfg(cell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=tm)
+    tb, iq, _ = oracle.gen_subframe(cell, cfg, 20000, snr, _taps() if ports == 2 else None)
+    sf = oracle.ofdm_rx(prb, iq)
+    ce, meas = oracle.chest(cell, 1, sf)
+    rc, pl, dbg = oracle.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, want=True)
+    s = oracle.cbsegm(tbs)
+    assert sha(iq) == want["iq"] and sha(sf) == want["sf"] and sha(ce) == want["ce"]
+    assert sha(dbg["softbuf"][:s.C, :3 * s.Kp + 12]) == want["sb"] and sha(pl) == want["payload"]
+    assert ",".join(map(str, dbg["iters"])) == want["iters"] and rc == int(want["rc"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_turbo_golden(gpu):
+    import torch
+    sg, ctx = gpu
+    tv = np.load(os.path.join(G, "turbo.npz"))
+    for K in (40, 512, 1056, 5824):
+        llrs = tv["llr_%d" % K]
+        n = len(llrs)
+        d_in = torch.from_numpy(llrs).cuda()
+        d_bits = torch.zeros((n, K // 8), dtype=torch.uint8, device="cuda")
+        d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ctx.tdec_run_all(d_in, n, K, 4, 0, d_bits, d_st)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_bits.cpu().numpy(), tv["bits4_%d" % K])
+        ctx.tdec_run_all(d_in, n, K, 6, 2, d_bits, d_st)
+        torch.cuda.synchronize()
+        st = d_st.cpu().numpy()
+        got = np.stack([st & 0xFF, (st >> 8) & 1, d_bits.cpu().numpy().astype(np.int64).sum(1)], 1)
+        assert np.array_equal(got, tv["crcrun_%d" % K])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_pdsch_golden(gpu):
+    import torch
+    sg, ctx = gpu
+    pv = np.load(os.path.join(G, "pdsch.npz"))
+    cell = sg.make_cell(6, 1, 1)
+    cfg = sg.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152)
+    plan = sg.PdschPlan(ctx, cell, cfg, 1)
+    I = plan.info
+    iq = pv["cfg1_iq"]
+    d_iq = torch.from_numpy(iq.view(np.float32).reshape(1, -1)).cuda()
+    d_sf = torch.zeros((1, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((1, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((1, 5), dtype=torch.float32, device="cuda")
+    d_sb = torch.zeros((1, I.sb_sf_stride), dtype=torch.int16, device="cuda")
+    d_e = torch.zeros((1, I.G), dtype=torch.int16, device="cuda")
+    d_pl = torch.zeros((1, I.payload_stride), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    plan.ofdm_rx(1, d_iq, d_sf)
+    plan.chest(1, d_sf, d_ce, d_meas)
+    plan.pdsch_llr(1, d_sf, d_ce, d_meas, 0.01, 0, 0, d_sb, None, d_e)
+    plan.pdsch_turbo(1, d_sb, 4, d_pl, d_st)
+    t = torch.zeros(3 * 176 + 12, dtype=torch.int16, device="cuda")
+    ctx.tdec_export(d_sb, 1, 176, t)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sf.cpu().numpy().view(np.complex64)[0], pv["cfg1_sf"])
+    assert np.array_equal(d_ce.cpu().numpy().view(np.complex64), pv["cfg1_ce"])
+    assert np.allclose(d_meas.cpu().numpy()[0], pv["cfg1_meas"], rtol=1e-5)
+    assert np.array_equal(d_e.cpu().numpy()[0], pv["cfg1_e"])
+    assert np.array_equal(t.cpu().numpy(), pv["cfg1_softbuf"])
+    assert np.array_equal(d_pl.cpu().numpy()[0], pv["cfg1_payload"]) and d_st.cpu().numpy()[0, 0] == 1
+    plan.close()

@@ -121,7 +121,7 @@ def test_harq_accumulate_matches_oracle(gpu, oracle):
     for rv, seed in ((0, 42), (2, 42)):
         ocfg = o.make_cfg(ocell, sf_idx=2, cfi=2, qm=qm, tbs=tbs, rv=rv)
         cfg = sg.make_cfg(cell, sf_idx=2, cfi=2, qm=qm, tbs=tbs, rv=rv)
-        tb, iq, _ = o.gen_subframe(ocell, ocfg, seed, 9.0)
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, seed, 11.0)
         plan = sg.PdschPlan(ctx, cell, cfg, 1)
         I = plan.info
         if d_sb is None:

@@ -1,0 +1,166 @@
+"""CPU-only checks that pin the oracle (oracle/SPEC.md): known-answer values, independent models, and
+TX->RX round trips for the BASELINE.json configs.  The reference's own tests hold no vector for this path
+(ue/test/phy/CMakeLists.txt:20-24), so these anchors are what "oracle checked" means here."""
+import numpy as np
+import pytest
+
+
+def test_crc_check_values(oracle):
+    # CRC catalogue check values over "123456789": CRC-24/LTE-A, CRC-24/LTE-B, CRC-16/XMODEM (36.212 5.1.1 polynomials)
+    msg = np.unpackbits(np.frombuffer(b"123456789", np.uint8))
+    assert oracle.crc_bits(msg, oracle.CRC24A) == 0xCDE703
+    assert oracle.crc_bits(msg, oracle.CRC24B) == 0x23EF52
+    assert oracle.crc_bits(msg, oracle.CRC16, 16) == 0x31C3
+    # CRC of (message || crc) is zero
+    rng = np.random.default_rng(1)
+    for poly in (oracle.CRC24A, oracle.CRC24B):
+        m = rng.integers(0, 2, 1000, dtype=np.uint8)
+        c = oracle.crc_bits(m, poly)
+        full = np.concatenate([m, [(c >> (23 - i)) & 1 for i in range(24)]]).astype(np.uint8)
+        assert oracle.crc_bits(full, poly) == 0
+
+
+def test_gold_sequence_against_numpy_model(oracle):
+    def gold_np(c_init, n):
+        x1 = np.zeros(n + 1600 + 31, np.uint8); x2 = np.zeros_like(x1)
+        x1[0] = 1
+        for i in range(31):
+            x2[i] = (c_init >> i) & 1
+        for i in range(n + 1600):
+            x1[i + 31] = x1[i + 3] ^ x1[i]
+            x2[i + 31] = x2[i + 3] ^ x2[i + 2] ^ x2[i + 1] ^ x2[i]
+        return x1[1600:1600 + n] ^ x2[1600:1600 + n]
+    for c_init in (0, 1, 0x1234 << 14 | 1 << 9 | 1, 0x7FFFFFFF):
+        assert np.array_equal(oracle.gold(c_init, 500), gold_np(c_init, 500))
+
+
+def test_qpp_all_188_are_permutations(oracle):
+    Ks = oracle.qpp_Ks()
+    assert len(Ks) == 188 and Ks[0] == 40 and Ks[-1] == 6144
+    for K in Ks:
+        assert np.array_equal(np.sort(oracle.qpp_perm(K)), np.arange(K)), K
+    # spot values of 36.212 Table 5.1.3-3
+    assert oracle.qpp_params(40) == (3, 10) and oracle.qpp_params(6144) == (263, 480) and oracle.qpp_params(5824) == (89, 182)
+
+
+def test_window_rule(oracle):
+    for K in oracle.qpp_Ks():
+        W = oracle.window_len(K)
+        assert K % W == 0 and W % 8 == 0
+        assert W >= min(K, 64)
+    assert oracle.window_len(5824) == 112 and oracle.window_len(6144) == 128 and oracle.window_len(40) == 40
+
+
+def test_segmentation_of_baseline_configs(oracle):
+    # C x K, filler
+    s = oracle.cbsegm(152);   assert (s.C, s.Kp, s.F) == (1, 176, 0)
+    s = oracle.cbsegm(75376); assert (s.C, s.Kp, s.Cm, s.F) == (13, 5824, 0, 0)
+    s = oracle.cbsegm(30576); assert (s.C, s.Kp, s.Cm, s.F) == (5, 6144, 0, 0)
+    s = oracle.cbsegm(6208);  assert (s.C, s.Kp, s.Km, s.Cp, s.Cm, s.F) == (2, 3200, 3136, 1, 1, 56)
+
+
+def test_pdsch_re_counts(oracle):
+    c6 = oracle.make_cell(6, 1, 1); c100 = oracle.make_cell(100, 1, 1); c100b = oracle.make_cell(100, 2, 1)
+    assert len(oracle.pdsch_re_list(c6, oracle.make_cfg(c6, sf_idx=1, cfi=1))) == 828
+    assert len(oracle.pdsch_re_list(c100, oracle.make_cfg(c100, sf_idx=1, cfi=1))) == 15000
+    assert len(oracle.pdsch_re_list(c100b, oracle.make_cfg(c100b, sf_idx=1, cfi=1, tm=2))) == 14400
+    # subframe 0 loses PSS/SSS/PBCH REs of the six central PRBs
+    n0 = len(oracle.pdsch_re_list(c100, oracle.make_cfg(c100, sf_idx=0, cfi=1)))
+    assert n0 == 15000 - 72 * 2 - (60 + 3 * 72)      # SSS+PSS symbols, PBCH symbols 7-10 (symbol 7 carries CRS: 10 data RE per PRB)
+
+
+def test_ofdm_against_numpy_fft(oracle):
+    rng = np.random.default_rng(5)
+    for prb, n in ((6, 128), (15, 256), (25, 512), (50, 1024), (75, 1536), (100, 2048)):
+        iq = (rng.standard_normal(15 * n) + 1j * rng.standard_normal(15 * n)).astype(np.complex64)
+        sf = oracle.ofdm_rx(prb, iq).reshape(14, -1)
+        pos, nsc = 0, 12 * prb
+        for l in range(14):
+            pos += (160 if l % 7 == 0 else 144) * n // 2048
+            X = np.fft.fft(iq[pos:pos + n].astype(np.complex128)) / np.sqrt(n)
+            pos += n
+            ref = np.concatenate([X[n - nsc // 2:], X[1:nsc // 2 + 1]])
+            assert np.max(np.abs(sf[l] - ref)) / np.sqrt(np.mean(abs(ref) ** 2)) < 1e-5
+
+
+def test_turbo_encoder_and_noiseless_decode_all_K(oracle):
+    rng = np.random.default_rng(3)
+    for K in oracle.qpp_Ks():
+        c = rng.integers(0, 2, K, dtype=np.uint8)
+        d = oracle.turbo_encode(c)
+        assert np.array_equal(d[0:3 * K:3], c)                    # systematic stream
+        llr = ((d.astype(np.int16) * 2 - 1) * 64).astype(np.int16)
+        bits, it, ok, _ = oracle.tdec(llr, K, 2, 0)
+        assert np.array_equal(bits, c), K
+
+
+def test_rate_matching_roundtrip_and_filler(oracle):
+    for K, F, rv, E in ((176, 0, 0, 1656), (5824, 0, 0, 6924), (1056, 24, 2, 3000), (6144, 0, 3, 11520)):
+        seq = oracle.rm_sequence(K, F, rv)
+        assert len(seq) == 3 * (K + 4) - 2 * F and len(set(seq.tolist())) == len(seq)
+        e = np.arange(E, dtype=np.int16) % 200 - 100
+        w = oracle.rm_rx(e, K, F, rv)
+        ref = np.zeros(3 * K + 12, np.int64)
+        for i in range(E):
+            ref[seq[i % len(seq)]] = np.clip(ref[seq[i % len(seq)]] + int(e[i]), -511, 511)
+        for k in range(F):
+            ref[3 * k] = ref[3 * k + 1] = -511
+        assert np.array_equal(w, ref)
+
+
+def test_no_wrap_in_decoder_even_for_extreme_inputs(oracle):
+    """SPEC.md 7.6: with the input clamp the wrapping adds never wrap, so wrapping == saturating."""
+    L = oracle.lib()
+    L.lteo_wrap_events.restype = __import__("ctypes").c_long
+    L.lteo_wrap_events(1)
+    rng = np.random.default_rng(9)
+    for K in (40, 512, 2048, 6144):
+        for mode in range(4):
+            if mode == 0: x = rng.integers(-32768, 32768, 3 * K + 12)
+            elif mode == 1: x = np.full(3 * K + 12, 32767)
+            elif mode == 2: x = np.full(3 * K + 12, -32768)
+            else: x = rng.integers(0, 2, 3 * K + 12) * 65535 - 32768
+            oracle.tdec(x.astype(np.int16), K, 6, 0)
+    assert L.lteo_wrap_events(0) == 0
+
+
+TAPS = None
+
+
+def _taps():
+    rng = np.random.default_rng(77)
+    t = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    return t / np.sqrt((abs(t) ** 2).sum(1, keepdims=True))
+
+
+@pytest.mark.parametrize("prb,ports,qm,tbs,tm,snr,sf", [
+    (6, 1, 2, 152, 1, 10.0, 1),          # BASELINE config 1
+    (100, 1, 6, 75376, 1, 30.0, 1),      # config 2
+    (100, 2, 4, 30576, 2, 15.0, 1),      # config 3 (frequency-selective channel)
+    (25, 1, 4, 4968, 1, 20.0, 5),
+    (50, 1, 4, 6208, 1, 18.0, 0),        # two code-block sizes + filler
+    (15, 1, 2, 1008, 1, 8.0, 3),
+])
+def test_tx_rx_round_trip(oracle, prb, ports, qm, tbs, tm, snr, sf):
+    cell = oracle.make_cell(prb, ports, 1)
+    cfg = oracle.make_cfg(cell, sf_idx=sf, cfi=1, qm=qm, tbs=tbs, tm=tm)
+    tb, iq, _ = oracle.gen_subframe(cell, cfg, 7, snr, _taps() if ports == 2 else None)
+    rc, pl, meas, it = oracle.ue_dl_decode(cell, cfg, iq, 0.01, 0, 4)
+    assert rc == 0 and np.array_equal(pl, tb)
+    assert 0.3 < meas[1] < 3.0 and meas[0] > 0       # rsrp around 1, positive noise estimate
+
+
+def test_harq_combining_improves(oracle):
+    """first transmission too noisy, soft combining with rv 2 decodes (dl_harq.cc:191-259 behaviour)"""
+    cell = oracle.make_cell(25, 1, 1)
+    tbs = 11448
+    sb = oracle.new_softbuf(2)
+    res = []
+    for rv in (0, 2):
+        cfg = oracle.make_cfg(cell, sf_idx=2, cfi=2, qm=6, tbs=tbs, rv=rv)
+        tb, iq, _ = oracle.gen_subframe(cell, cfg, 42, 11.0)
+        sf = oracle.ofdm_rx(25, iq)
+        ce, _ = oracle.chest(cell, 2, sf)
+        rc, pl = oracle.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, softbuf=sb)
+        res.append((rc, np.array_equal(pl, tb)))
+    assert res[0][0] != 0 and res[1] == (0, True)
