@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -65,7 +66,7 @@ struct Scratch {
 }  // namespace
 
 struct srsue_gpu_ctx {
-  int device = 0, num_sms = 0, smem_optin = 0;
+  int device = 0, num_sms = 0, smem_optin = 0, smem_sm = 0;
   std::mutex mu;
   std::map<int, TurboTables> turbo;
   Scratch scratch;
@@ -99,19 +100,40 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
 
 struct TurboLaunchCfg { int ncb, threads, grid, smem; };
 
+// words between the exchange arrays of consecutive slots: plane/2 plus the skew that lets a warp straddling
+// two slots keep hitting distinct shared-memory banks ((plane/2 + skew) mod 32 == T mod 32)
+int turbo_slot_words(const TurboGeom& g) {
+  const int base = g.plane / 2;
+  return base + ((g.T - base) % 32 + 32) % 32;
+}
+
+// CTAs per SM of the persistent decoder.  Two independent CTAs per SM drift out of phase, which spreads the
+// L2 demand of the load-dominated backward sweeps and halves the width of every barrier.
+int turbo_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRSUE_TURBO_CTAS_PER_SM");
+    v = e ? std::max(1, std::min(4, atoi(e))) : 2;
+  }
+  return v;
+}
+
 TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb, bool crc) {
-  const int slot_bytes = g.plane * 2;
-  const int fixed = g.plane * 2 + (crc ? g.plane * 4 : 0) + 64;     // position table (+ CRC table)
-  int ncb = (ctx->smem_optin - fixed) / (slot_bytes + 8);
-  ncb = std::min(ncb, kTurboMaxThreads / g.T);
+  const int per_sm = turbo_ctas_per_sm();
+  const int slot_bytes = turbo_slot_words(g) * 4;
+  const int fixed = g.plane * 2 + (crc ? g.plane * 4 : 0) + 96;     // position table (+ CRC table) + flags
+  const int smem_budget = (ctx->smem_sm - per_sm * 1024) / per_sm;  // 1 KB per CTA is reserved by the driver
+  int ncb = (std::min(smem_budget, ctx->smem_optin) - fixed) / (slot_bytes + 8);
+  ncb = std::min(ncb, (kTurboMaxThreads / per_sm) / g.T);
+  if (const char* e = getenv("SRSUE_TURBO_MAX_SLOTS")) ncb = std::min(ncb, std::max(1, atoi(e)));   // tuning knob
   // spread small batches over all SMs rather than filling a few CTAs
-  ncb = std::min(ncb, std::max(1, (n_cb + ctx->num_sms - 1) / ctx->num_sms));
+  ncb = std::min(ncb, std::max(1, (n_cb + ctx->num_sms * per_sm - 1) / (ctx->num_sms * per_sm)));
   ncb = std::max(ncb, 1);
   TurboLaunchCfg c;
   c.ncb = ncb;
   c.threads = ((ncb * g.T + 31) / 32) * 32;
-  c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms);
-  c.smem = g.plane * 2 + (crc ? g.plane * 4 : 0) + 2 * ((ncb + 3) & ~3) * 4 + ncb * slot_bytes;
+  c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms * per_sm);
+  c.smem = g.plane * 2 + (crc ? g.plane * 4 : 0) + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes;
   return c;
 }
 
@@ -139,6 +161,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   if (ckpt_bytes > scr.ckpt_bytes) { cudaFree(scr.ckpt); CU_CHECK(cudaMalloc((void**)&scr.ckpt, ckpt_bytes)); scr.ckpt_bytes = ckpt_bytes; }
   if (!ctx->attr_set) {
     CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    CU_CHECK(cudaFuncSetAttribute(turbo_decode_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     ctx->attr_set = true;
   }
   TurboArgs a{};
@@ -150,6 +173,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   a.perm_pos = tt->d_perm;
   a.crc_tpos = tt->d_tpos[crc_type == 2 ? 1 : 0];
   a.ncb_cta = lc.ncb;
+  a.slot_words = turbo_slot_words(g);
   a.nii = scr.nii;
   a.bits_scratch = scr.bits;
   a.ckpt = scr.ckpt;
@@ -158,7 +182,8 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   CU_CHECK(cudaMemsetAsync(scr.counter, 0, sizeof(int), st));
   a.work_counter = scr.counter;
   a.work_base = lc.grid * lc.ncb;
-  turbo_decode_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  if (crc_type) turbo_decode_crc_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  else turbo_decode_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   CU_CHECK(cudaGetLastError());
   ctx->last_grid = lc.grid; ctx->last_block = lc.threads; ctx->last_smem = lc.smem; ctx->last_ncb = lc.ncb;
   ctx->launch_count++;
@@ -213,6 +238,7 @@ int srsue_gpu_ctx_create(srsue_gpu_ctx_t** out, int device) {
   ctx->device = device;
   ctx->num_sms = p.multiProcessorCount;
   ctx->smem_optin = (int)p.sharedMemPerBlockOptin;
+  ctx->smem_sm = (int)p.sharedMemPerMultiprocessor;
   *out = ctx;
   return 0;
 }

@@ -25,6 +25,7 @@ struct TurboArgs {
   const uint16_t* perm_pos;  // [plane]
   const uint32_t* crc_tpos;  // [plane] x^(K-1-n+24) mod g at the A position of bit n (0 in padding columns)
   int ncb_cta;               // code-block slots per CTA
+  int slot_words;            // 32-bit words between the exchange arrays of consecutive slots (plane/2 + skew)
   int16_t* nii;              // [grid * ncb_cta][2][2][2][8][Ppad + 2]
   uint8_t* bits_scratch;     // [grid * ncb_cta][plane] x 16 bit
   uint4* ckpt;               // [grid * ncb_cta][W/8][T][2]  beta checkpoints
@@ -32,7 +33,8 @@ struct TurboArgs {
   int work_base;             // first dynamically assigned code block = grid * ncb_cta
 };
 
-__global__ void turbo_decode_kernel(const TurboArgs g);
+__global__ void turbo_decode_kernel(const TurboArgs g);        // fixed iteration count
+__global__ void turbo_decode_crc_kernel(const TurboArgs g);    // CRC accumulated on the fly, early stop
 __global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
                                       int n_cb, TurboGeomDev g);
 __global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,

@@ -39,7 +39,15 @@ __device__ __forceinline__ uint32_t vsub(uint32_t a, uint32_t b) { return __vsub
 // max(a + b, c) per int16 half, the add wrapping (VIADDMNMX.S16x2)
 __device__ __forceinline__ uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t vclampE(uint32_t v) { return __vmins2(__vmaxs2(v, kNegEPair), kEPair); }
-__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5410); }
+// lo + hi * 65536 with lo, hi zero-extended 16-bit loads: one IMAD on the FMA pipe (a PRMT would take an
+// ALU-pipe slot, and the ALU pipe is the one this kernel saturates)
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
+// store a 16-bit value at base[idx] with the address formed by one IMAD.WIDE (FMA pipe)
+__device__ __forceinline__ void st16_wide(uint16_t* base, uint32_t idx, uint32_t v) {
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"((uint16_t)v) : "memory");
+}
 __device__ __forceinline__ uint32_t pack16s(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu); }
 
 // beta_k from beta_{k+1} (SPEC 7.4); branch labels follow the RSC trellis of 36.212 5.1.3.2.1
@@ -121,9 +129,9 @@ struct SlotCtx {
 
 // One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.  Returns the
 // thread's CRC contribution of the hard decisions (DEC2 with crc_on), else 0.
-template <int DEC>
+template <int DEC, bool CRC>
 __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm16,
-                                             const uint32_t* s_tpos, int t, int it, bool store_bits, bool crc_on) {
+                                             const uint32_t* s_tpos, int t, int it) {
   const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
   const int j0 = 2 * t, j1 = 2 * t + 1;
   const int rd = it & 1, wr = rd ^ 1;
@@ -186,9 +194,15 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
   {
-    uint32_t ny[kSW], ns[kSW];                      // register prefetch of the next group's channel LLRs
+    // Register prefetch TWO groups ahead: all warps of the CTA run this short, load-dominated sweep at the
+    // same time (the passes are barrier-separated), so there is no other phase to hide the L2 latency behind.
+    uint32_t ny[kSW], ns[kSW], my[kSW], ms[kSW];
     ld8(yq + (nsw - 1) * gstride, ny);
     if (DEC == 0) ld8(sysq + (nsw - 1) * gstride, ns);
+    if (nsw > 1) {
+      ld8(yq + (nsw - 2) * gstride, my);
+      if (DEC == 0) ld8(sysq + (nsw - 2) * gstride, ms);
+    }
 #pragma unroll 1
     for (int sw = nsw - 1; sw >= 0; sw--) {
       uint32_t x[kSW], y[kSW];
@@ -204,9 +218,11 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 #pragma unroll
         for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
       }
-      if (sw > 0) {
-        ld8(yq + (sw - 1) * gstride, ny);
-        if (DEC == 0) ld8(sysq + (sw - 1) * gstride, ns);
+#pragma unroll
+      for (int i = 0; i < kSW; i++) { ny[i] = my[i]; if (DEC == 0) ns[i] = ms[i]; }
+      if (sw > 1) {
+        ld8(yq + (sw - 2) * gstride, my);
+        if (DEC == 0) ld8(sysq + (sw - 2) * gstride, ms);
       }
       st8(ckpt4 + sw * gstride, b);                 // thread-private scratch, read back in pass 2
 #pragma unroll
@@ -267,13 +283,11 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
           const uint32_t p0 = pq[2 * i], p1 = pq[2 * i + 1];
           A16[p0] = (int16_t)(la & 0xFFFFu);
           A16[p1] = (int16_t)(la >> 16);
-          if (store_bits) {
-            // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
-            const uint32_t nd = vsub(0u, vadd(x[i], ext));
-            bits[p0] = (uint16_t)nd;
-            bits[p1] = (uint16_t)(nd >> 16);
-            if (crc_on) crc ^= (sign_fill<0x9999>(nd) & s_tpos[p0]) ^ (sign_fill<0xBBBB>(nd) & s_tpos[p1]);
-          }
+          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
+          const uint32_t nd = vsub(0u, vadd(x[i], ext));
+          st16_wide(bits, p0, nd);
+          st16_wide(bits, p1, nd >> 16);
+          if (CRC) crc ^= (sign_fill<0x9999>(nd) & s_tpos[p0]) ^ (sign_fill<0xBBBB>(nd) & s_tpos[p1]);
         }
         alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
         if ((i & 3) == 3) normalise(a);
@@ -285,29 +299,31 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   return crc;
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) {
+template <bool CRC>
+__device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int T = g.T, W = g.W, P = g.P, plane = g.plane;
   const int tid = threadIdx.x;
   const int slot = tid / T, t = tid - slot * T;
   const bool valid = slot < g.ncb_cta;
-  const bool crc_on = g.crc_type != 0;
+  constexpr bool crc_on = CRC;
   const int nflag = (g.ncb_cta + 3) & ~3;
 
   uint32_t* s_permw = smem;                                  // plane/2 words: DEC2 positions [W/8][T][8][2] x u16
   uint32_t* s_tpos = s_permw + plane / 2;                    // plane words (0 without CRC): x^(pos) mod g per A position
   uint32_t* s_crc = s_tpos + (crc_on ? plane : 0);           // per slot: CRC accumulator
-  int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item
-  uint32_t* s_slots = s_crc + 2 * nflag;                     // per slot: A, plane/2 words
+  int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
+  uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words
+  int* s_active = s_next + nflag;
 
   for (int i = tid; i < plane / 2; i += blockDim.x) s_permw[i] = reinterpret_cast<const uint32_t*>(g.perm_pos)[i];
   if (crc_on)
     for (int i = tid; i < plane; i += blockDim.x) s_tpos[i] = g.crc_tpos[i];
 
   SlotCtx c;
-  c.Aw = s_slots + (size_t)(valid ? slot : 0) * (plane / 2);
+  // slot stride = plane/2 words plus a skew that makes consecutive slots continue the bank sequence
+  // (base(s+1) = base(s) + T mod 32): a warp that straddles two slots then stays conflict-free
+  c.Aw = s_slots + (size_t)(valid ? slot : 0) * g.slot_words;
   c.gslot = blockIdx.x * g.ncb_cta + (valid ? slot : 0);
   c.in4 = nullptr;
   const uint16_t* perm16 = reinterpret_cast<const uint16_t*>(s_permw) + 2 * kSW * t;
@@ -322,21 +338,27 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
     // a-priori LLRs start at zero: each thread clears its own column of A
     for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
-    // start pulling the second decoder's parity plane towards L2 (its first use is one pass away)
-    const uint4* p2 = c.in4 + 2 * (plane / 8) + 2 * t;
-    for (int sw = 0; sw < W / kSW; sw++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + sw * 2 * T));
+    // the block comes straight from HBM: request all three planes now (the groups the backward sweep needs
+    // first go first) so that only the first sub-window waits for DRAM
+    const uint4* p0 = c.in4 + 2 * t;
+    for (int sw = W / kSW - 1; sw >= 0; sw--) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + sw * 2 * T));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (plane / 8) + sw * 2 * T));
+    }
+    for (int sw = W / kSW - 1; sw >= 0; sw--) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 2 * (plane / 8) + sw * 2 * T));
   };
   if (have) init_slot();
+  if (tid == 0) *s_active = 0;
+  __syncthreads();
+  if (have && t == 0) atomicAdd(s_active, 1);
   __syncthreads();
 
-  while (true) {
-    if (__syncthreads_and(!have)) break;
+  while (*s_active > 0) {
     if (valid && t == 0) s_crc[slot] = 0;
-    const bool store_bits = crc_on || (it == g.max_iter - 1);
-    if (have) map_pass<0>(g, c, perm16, s_tpos, t, it, store_bits, crc_on);
+    if (have) map_pass<0, CRC>(g, c, perm16, s_tpos, t, it);
     __syncthreads();
     if (have) {
-      const uint32_t part = map_pass<1>(g, c, perm16, s_tpos, t, it, store_bits, crc_on);
+      const uint32_t part = map_pass<1, CRC>(g, c, perm16, s_tpos, t, it);
       if (crc_on) atomicXor(&s_crc[slot], part);
     }
     __syncthreads();
@@ -347,7 +369,7 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
       uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
       const int wbytes = W / 8;
       const uint32_t* bp = reinterpret_cast<const uint32_t*>(g.bits_scratch) + ((size_t)c.gslot * plane) / 2 + t;
-#pragma unroll 2
+#pragma unroll 4
       for (int bb = 0; bb < wbytes; bb++) {
         uint32_t v0 = 0, v1 = 0;
 #pragma unroll
@@ -361,7 +383,9 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
       }
       if (t == 0) {
         g.out_status[cbi] = (it + 1) | ((crc_ok ? 1 : 0) << 8);
-        s_next[slot] = g.work_base + atomicAdd(g.work_counter, 1);
+        const int nxt = g.work_base + atomicAdd(g.work_counter, 1);
+        s_next[slot] = nxt;
+        if (nxt >= g.n_cb) atomicSub(s_active, 1);      // this slot retires
       }
     } else if (have) {
       it++;
@@ -375,6 +399,11 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
     }
   }
 }
+
+}  // namespace
+
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true>(g); }
 
 // ---- layout conversion at the API edge -----------------------------------------------------------
 // srsLTE decoder-input order (3K+12 interleaved triples) -> tcb layout, clamping to +-C (SPEC 7.2)
