@@ -255,7 +255,10 @@ def main():
         turbo_ops = 168.0 * I.Kp * avg_iter * n_cb
         alu_peak_tops = 148 * 384 * sm_max * 1e6 / 1e12
         turbo_tops = turbo_ops / (stage_ms[3] * 1e-3) / 1e12
-        alg_bytes = {"ofdm_fft": 380160, "chest": 268800, "equalise_demap_dematch": 574584 + 120000, "turbo_crc_tb": 464058}
+        # algorithmic bytes per subframe: FFT 245 760 in + 134 400 out; channel estimate 134 400 in +
+        # 134 400 out; K3+K4 fused: PDSCH REs 120 000 + estimates 120 000 in, soft buffer 454 584 out; turbo: soft
+        # buffer in + transport block out
+        alg_bytes = {"ofdm_fft": 380160, "chest": 268800, "equalise_demap_dematch": 694584, "turbo_crc_tb": 464058}
         stages = []
         for i, n in enumerate(names):
             gbs = alg_bytes[n] * B / (stage_ms[i] * 1e-3) / 1e9

@@ -1,0 +1,147 @@
+// pdsch_offline.cc -- offline downlink decoder: the C++ host side above the C ABI.
+//
+// Mode "worker" replays, subframe by subframe, exactly the call sequence of srsUE's PHY worker
+// (/root/reference/ue/src/phy/phch_worker.cc:132-243: extract_fft_and_pdcch_llr -> new_grant_dl ->
+// decode_pdsch -> tb_decoded) through the srsLTE-shaped symbols of libsrsue_gpu, with a MAC stand-in that owns
+// the soft buffer and the payload buffer the way dl_harq does (/root/reference/ue/src/mac/dl_harq.cc:216-279;
+// the same minimal caller as ue/test/phy/ue_itf_test_sib1.cc:108-123).  Mode "batch" hands all subframes to
+// srsue_gpu_pdsch_decode_batch_host in one call -- the batching layer that replaces the one-subframe-per-
+// thread hand-off of thread_pool::start_worker (ue/src/common/thread_pool.cc:246-254).
+//
+//   pdsch_offline worker|batch <in.bin> <out.bin>
+// in.bin : 12 int32 {magic 0x53525355, nof_prb, nof_ports, cell_id, sf_idx, cfi, rnti, qm, tbs, rv, n_sf, max_iter}
+//          followed by n_sf * SRSLTE_SF_LEN_PRB(nof_prb) cf_t samples
+// out.bin: per subframe {int32 ack, int32 n_iter, float snr} followed by tbs/8 payload bytes
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "srsue_gpu/srslte_compat.h"
+
+namespace {
+
+struct Header { int32_t magic, nof_prb, nof_ports, cell_id, sf_idx, cfi, rnti, qm, tbs, rv, n_sf, max_iter; };
+
+// what mac->new_grant_dl() hands back to the worker (mac_interface.h:62-74), reduced to the fields the DL path reads
+struct tb_action_dl_t {
+  bool decode_enabled;
+  uint32_t rv;
+  uint16_t rnti;
+  uint8_t* payload_ptr;
+  srslte_softbuffer_rx_t* softbuffer;
+  srslte_ra_dl_grant_t phy_grant;
+};
+
+class mac_stub {   // one HARQ process: owns the soft buffer and the PDU buffer
+ public:
+  bool init(uint32_t nof_prb, uint32_t tbs) {
+    payload.assign(tbs / 8 + 8, 0);
+    return srslte_softbuffer_rx_init(&softbuffer, nof_prb) == SRSLTE_SUCCESS;
+  }
+  ~mac_stub() { srslte_softbuffer_rx_free(&softbuffer); }
+  void new_grant_dl(const srslte_ra_dl_grant_t& grant, uint32_t rv, uint16_t rnti, tb_action_dl_t* action) {
+    if (rv == 0) srslte_softbuffer_rx_reset_tbs(&softbuffer, (uint32_t)grant.mcs.tbs);   // new data: dl_harq.cc:232
+    action->decode_enabled = true;
+    action->rv = rv;
+    action->rnti = rnti;
+    action->payload_ptr = payload.data();
+    action->softbuffer = &softbuffer;
+    action->phy_grant = grant;
+  }
+  std::vector<uint8_t> payload;
+  srslte_softbuffer_rx_t softbuffer;
+};
+
+int run_worker(const Header& h, cf_t* iq, FILE* out) {
+  srslte_cell_t cell;
+  std::memset(&cell, 0, sizeof(cell));
+  cell.nof_prb = h.nof_prb; cell.nof_ports = h.nof_ports; cell.id = h.cell_id; cell.cp = SRSLTE_CP_NORM;
+  srslte_ue_dl_t ue_dl;
+  if (srslte_ue_dl_init(&ue_dl, cell)) { fprintf(stderr, "Initiating UE DL: %s\n", srsue_gpu_last_error()); return 1; }
+  srslte_ue_dl_set_rnti(&ue_dl, (uint16_t)h.rnti);
+  if (h.max_iter > 0) srslte_sch_set_max_noi(&ue_dl.pdsch.dl_sch, h.max_iter);     // phch_worker.cc:87-89
+  srsue_gpu_ue_dl_set_cfi(&ue_dl, h.cfi);                                          // until PCFICH runs on the device
+  mac_stub mac;
+  if (!mac.init(h.nof_prb, h.tbs)) return 1;
+  srslte_ra_dl_grant_t grant;
+  std::memset(&grant, 0, sizeof(grant));
+  for (int i = 0; i < h.nof_prb; i++) grant.prb_idx[0][i] = grant.prb_idx[1][i] = true;
+  grant.nof_prb = h.nof_prb; grant.Qm = h.qm; grant.mcs.tbs = h.tbs;
+  grant.mcs.mod = h.qm == 2 ? SRSLTE_MOD_QPSK : h.qm == 4 ? SRSLTE_MOD_16QAM : SRSLTE_MOD_64QAM;
+  const int sf_len = SRSLTE_SF_LEN_PRB(h.nof_prb);
+  for (int n = 0; n < h.n_sf; n++) {
+    cf_t* signal_buffer = iq + (size_t)n * sf_len;
+    uint32_t cfi = 0;
+    if (srslte_ue_dl_decode_fft_estimate(&ue_dl, signal_buffer, h.sf_idx, &cfi) < 0) { fprintf(stderr, "Getting PDCCH FFT estimate\n"); return 1; }
+    tb_action_dl_t dl_action;
+    mac.new_grant_dl(grant, h.rv, (uint16_t)h.rnti, &dl_action);
+    bool dl_ack = false;
+    if (dl_action.decode_enabled && !srslte_ue_dl_cfg_grant(&ue_dl, &dl_action.phy_grant, cfi, h.sf_idx, dl_action.rv)) {
+      if (ue_dl.pdsch_cfg.grant.mcs.mod > 0 && ue_dl.pdsch_cfg.grant.mcs.tbs >= 0) {
+        const float noise_estimate = 0.01f;                                        // phch_worker.cc:340
+        dl_ack = srslte_pdsch_decode_rnti(&ue_dl.pdsch, &ue_dl.pdsch_cfg, dl_action.softbuffer, ue_dl.sf_symbols, ue_dl.ce,
+                                          noise_estimate, dl_action.rnti, dl_action.payload_ptr) == 0;
+      }
+    }
+    const int32_t ack = dl_ack, n_iter = (int32_t)srslte_pdsch_last_noi(&ue_dl.pdsch);
+    const float snr = srslte_chest_dl_get_snr(&ue_dl.chest);
+    fwrite(&ack, 4, 1, out); fwrite(&n_iter, 4, 1, out); fwrite(&snr, 4, 1, out);
+    fwrite(dl_action.payload_ptr, 1, h.tbs / 8, out);
+  }
+  srslte_ue_dl_free(&ue_dl);
+  return 0;
+}
+
+int run_batch(const Header& h, cf_t* iq, FILE* out) {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  if (srsue_gpu_ctx_create(&ctx, 0)) { fprintf(stderr, "%s\n", srsue_gpu_last_error()); return 1; }
+  srsue_gpu_cell_t cell = {h.nof_prb, h.nof_ports, h.cell_id};
+  srsue_gpu_pdsch_cfg_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.sf_idx = h.sf_idx; cfg.cfi = h.cfi; cfg.rnti = h.rnti; cfg.qm = h.qm; cfg.tbs = h.tbs; cfg.rv = h.rv;
+  cfg.tm = h.nof_ports == 1 ? 1 : 2; cfg.nof_prb_alloc = h.nof_prb;
+  for (int i = 0; i < h.nof_prb; i++) cfg.prb_mask[i] = 1;
+  srsue_gpu_pdsch_plan_t* plan = nullptr;
+  if (srsue_gpu_pdsch_plan_create(ctx, &cell, &cfg, h.n_sf, &plan)) { fprintf(stderr, "%s\n", srsue_gpu_last_error()); return 1; }
+  srsue_gpu_plan_info_t info;
+  srsue_gpu_pdsch_plan_info(plan, &info);
+  std::vector<uint8_t> payload((size_t)h.n_sf * info.payload_stride);
+  std::vector<int32_t> status((size_t)h.n_sf * 4);
+  std::vector<float> meas((size_t)h.n_sf * 5);
+  if (srsue_gpu_pdsch_decode_batch_host(plan, h.n_sf, reinterpret_cast<const srsue_gpu_cf_t*>(iq), 0.01f, 0, h.max_iter > 0 ? h.max_iter : 4,
+                                        payload.data(), status.data(), meas.data())) {
+    fprintf(stderr, "%s\n", srsue_gpu_last_error());
+    return 1;
+  }
+  for (int n = 0; n < h.n_sf; n++) {
+    const int32_t ack = status[4 * n], n_iter = status[4 * n + 2];
+    const float snr = meas[5 * n + 4];
+    fwrite(&ack, 4, 1, out); fwrite(&n_iter, 4, 1, out); fwrite(&snr, 4, 1, out);
+    fwrite(payload.data() + (size_t)n * info.payload_stride, 1, h.tbs / 8, out);
+  }
+  srsue_gpu_pdsch_plan_destroy(plan);
+  srsue_gpu_ctx_destroy(ctx);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc != 4) { fprintf(stderr, "usage: %s worker|batch <in.bin> <out.bin>\n", argv[0]); return 2; }
+  FILE* in = fopen(argv[2], "rb");
+  if (!in) { perror(argv[2]); return 1; }
+  Header h;
+  if (fread(&h, sizeof(h), 1, in) != 1 || h.magic != 0x53525355) { fprintf(stderr, "bad header\n"); return 1; }
+  const size_t n = (size_t)h.n_sf * SRSLTE_SF_LEN_PRB(h.nof_prb);
+  cf_t* iq = (cf_t*)srslte_vec_malloc((uint32_t)(n * sizeof(cf_t)));
+  if (!iq || fread(iq, sizeof(cf_t), n, in) != n) { fprintf(stderr, "short read\n"); return 1; }
+  fclose(in);
+  FILE* out = fopen(argv[3], "wb");
+  if (!out) { perror(argv[3]); return 1; }
+  const int rc = std::strcmp(argv[1], "batch") == 0 ? run_batch(h, iq, out) : run_worker(h, iq, out);
+  fclose(out);
+  srslte_vec_free(iq);
+  return rc;
+}

@@ -107,6 +107,14 @@ int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t
 int srsue_gpu_pdsch_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
                         const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int accumulate,
                         int16_t *d_softbuf, srsue_gpu_cf_t *d_dbg_d, int16_t *d_dbg_e, void *stream);
+/* fused variants used by the whole-chain call: the channel-estimate grid is never written to HBM.
+ * srsue_gpu_chest_pilots leaves only the smoothed pilot estimates d_pilots [n_sf][ports][4][2*nof_prb] (and
+ * the measurements); srsue_gpu_pdsch_llr_fused interpolates them per resource element (same arithmetic). */
+int srsue_gpu_chest_pilots(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                           srsue_gpu_cf_t *d_pilots, float *d_meas, void *stream);
+int srsue_gpu_pdsch_llr_fused(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                              const srsue_gpu_cf_t *d_pilots, const float *d_meas, float noise_est, int noise_mode,
+                              int accumulate, int16_t *d_softbuf, void *stream);
 /* turbo decode + CRC + transport-block assembly.  d_payload [n_sf][payload_stride] bytes MSB first;
  * d_tb_status [n_sf][4] = {crc_ok, sum of iterations, floor(avg iterations), C};
  * d_cb_status optional [n_sf][C]. */

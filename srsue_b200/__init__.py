@@ -144,6 +144,13 @@ class PdschPlan:
         _check(lib().srsue_gpu_pdsch_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                          accumulate, _ptr(d_softbuf), _ptr(d_dbg_d), _ptr(d_dbg_e), _stream()), "pdsch_llr")
 
+    def chest_pilots(self, n_sf, d_sf, d_pilots, d_meas):
+        _check(lib().srsue_gpu_chest_pilots(self.h, n_sf, _ptr(d_sf), _ptr(d_pilots), _ptr(d_meas), _stream()), "chest_pilots")
+
+    def pdsch_llr_fused(self, n_sf, d_sf, d_pilots, d_meas, noise_est, noise_mode, accumulate, d_softbuf):
+        _check(lib().srsue_gpu_pdsch_llr_fused(self.h, n_sf, _ptr(d_sf), _ptr(d_pilots), _ptr(d_meas), C.c_float(noise_est),
+                                               noise_mode, accumulate, _ptr(d_softbuf), _stream()), "pdsch_llr_fused")
+
     def pdsch_turbo(self, n_sf, d_softbuf, max_iter, d_payload, d_tb_status, d_cb_status=None):
         _check(lib().srsue_gpu_pdsch_turbo(self.h, n_sf, _ptr(d_softbuf), max_iter, _ptr(d_payload), _ptr(d_tb_status),
                                            _ptr(d_cb_status), _stream()), "pdsch_turbo")

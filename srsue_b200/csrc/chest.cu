@@ -68,10 +68,11 @@ __global__ void __launch_bounds__(512) chest_kernel(const ChestArgs a) {
       o.y = __fadd_rn(__fadd_rn(__fmul_rn(0.1f, l.y), __fmul_rn(0.8f, c.y)), __fmul_rn(0.1f, r.y));
     }
     s_sm[i] = o;
+    if (a.pilots) a.pilots[(size_t)sf * np * 4 * M + i] = o;
   }
   __syncthreads();
   // ---- frequency + time interpolation ---------------------------------------------------------------
-  for (int p = 0; p < np; p++) {
+  for (int p = 0; p < np && a.ce != nullptr; p++) {
     float2* ce = a.ce + ((size_t)sf * np + p) * 14 * nsc;
     for (int k = tid; k < nsc; k += nt) {
       float2 h[4];

@@ -52,7 +52,8 @@ __global__ void ofdm_rx_kernel(const OfdmArgs a);
 
 struct ChestArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc]
-  float2* ce;                // [n_sf][ports][14 * nsc]
+  float2* ce;                // [n_sf][ports][14 * nsc]; nullptr: skip the interpolation (fused path)
+  float2* pilots;            // optional [n_sf][ports][4][2 * nof_prb] smoothed pilot estimates
   float* meas;               // [n_sf][5]  noise, rsrp, rssi, rsrq, snr
   const int8_t* crs_sign;    // [4 crs symbols][2 (re, im)][2 * nof_prb]
   int n_sf, nsc, nof_prb, nof_ports;
@@ -62,7 +63,10 @@ __global__ void chest_kernel(const ChestArgs a);
 
 struct DemodArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc]
-  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float2* ce;          // [n_sf][ports][14 * nsc] (unused when pilots != nullptr)
+  const float2* pilots;      // optional [n_sf][ports][4][2 * nof_prb]: interpolate the channel on the fly
+  int nof_prb;
+  int crs_off[2][4];         // first pilot subcarrier per port and CRS symbol
   const float* meas;         // [n_sf][5] (noise estimate when noise_mode == 1)
   int16_t* softbuf;          // [n_sf][C][sb_stride] tcb layout
   const int32_t* re_idx;     // [nof_re] grid index of every PDSCH RE

@@ -26,6 +26,18 @@ __device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
   a = make_float2(__fadd_rn(a0.x, t.x), __fadd_rn(a0.y, t.y));
   b = make_float2(__fsub_rn(a0.x, t.x), __fsub_rn(a0.y, t.y));
 }
+// butterflies with the exact twiddles 1 and -i (the table holds exactly (1,0) and (0,-1) there, SPEC.md 2):
+// w*b is then b resp. (b.im, -b.re) without any rounding, so the products can be skipped
+__device__ __forceinline__ void bfly_one(float2& a, float2& b) {
+  const float2 a0 = a, b0 = b;
+  a = make_float2(__fadd_rn(a0.x, b0.x), __fadd_rn(a0.y, b0.y));
+  b = make_float2(__fsub_rn(a0.x, b0.x), __fsub_rn(a0.y, b0.y));
+}
+__device__ __forceinline__ void bfly_mj(float2& a, float2& b) {
+  const float2 a0 = a, b0 = b;
+  a = make_float2(__fadd_rn(a0.x, b0.y), __fsub_rn(a0.y, b0.x));
+  b = make_float2(__fsub_rn(a0.x, b0.y), __fadd_rn(a0.y, b0.x));
+}
 // skew: one padding element per 16 float2 keeps strided exchanges off a single bank group
 __device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
 
@@ -85,6 +97,27 @@ __device__ __forceinline__ void combine(float2 (&v)[8], int k, int L, int N, con
   for (int u = 0; u < R; u++) v[u] = o[u];
 }
 
+// The first radix-8 pass (L = 1, k = 0): stage A uses w = 1, stage B w = 1 and -i, stage C w_8^0..3.
+__device__ __forceinline__ void combine_first8(float2 (&v)[8], int N, const float2* __restrict__ tw) {
+#pragma unroll
+  for (int r = 0; r < 4; r++) bfly_one(v[r], v[r + 4]);
+  bfly_one(v[0], v[2]); bfly_one(v[1], v[3]);
+  bfly_mj(v[4], v[6]); bfly_mj(v[5], v[7]);
+  bfly_one(v[0], v[1]);
+  bfly_mj(v[2], v[3]);
+  bfly(v[4], v[5], tw[N / 8]);
+  bfly(v[6], v[7], tw[3 * (N / 8)]);
+  float2 o[8];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) o[h + 2 * q + 4 * e] = v[h * 4 + q * 2 + e];
+#pragma unroll
+  for (int u = 0; u < 8; u++) v[u] = o[u];
+}
+
 // First pass (global -> shared) or last pass (shared -> global, bin selection + scaling) for all
 // butterflies of this thread.  Data before a pass sits at index k*(N/L) + n, after it at k'*(N/L') + n'.
 template <int LOGR, bool FIRST, bool LAST>
@@ -101,7 +134,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, float2
       const int idx = k * (N / L) + np + nsub * r;
       v[r] = FIRST ? __ldg(gsrc + idx) : sbuf[skew(idx)];
     }
-    combine<LOGR>(v, k, L, N, tw);
+    if (FIRST && LOGR == 3) combine_first8(v, N, tw); else combine<LOGR>(v, k, L, N, tw);
 #pragma unroll
     for (int u = 0; u < R; u++) {
       const int kp = k + u * L;

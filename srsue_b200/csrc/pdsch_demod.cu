@@ -71,18 +71,50 @@ __device__ __forceinline__ void emit_re(const DemodArgs& a, int sf, int re, int 
   }
 }
 
-template <int QM>
-__device__ __forceinline__ void llr_stage(const DemodArgs& a, int sf, int e0, int e1, int16_t* s_e, float n0) {
+__device__ __forceinline__ float lerp_rn(float a, float b, float f) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), f)); }
+
+// Channel estimate of port p at grid index g (= l*nsc + k) from the smoothed pilots in shared memory: the
+// same frequency and time interpolation, operation for operation, as chest_kernel (SPEC.md 3.3-3.4).
+struct ChanInterp {
+  const float2* s_pil;     // [ports][4][M]
+  const float* s_ftab;     // [17]
+  const float* s_ttab;     // [14]
+  int nsc, M;
+  int off[2][4];
+  __device__ __forceinline__ float2 freq(int p, int si, int k) const {
+    const int o = off[p][si];
+    int m = (k >= o) ? (k - o) / 6 : 0;
+    if (m > M - 2) m = M - 2;
+    const float f = s_ftab[k - (6 * m + o) + 5];
+    const float2 v0 = s_pil[(p * 4 + si) * M + m], v1 = s_pil[(p * 4 + si) * M + m + 1];
+    return make_float2(lerp_rn(v0.x, v1.x, f), lerp_rn(v0.y, v1.y, f));
+  }
+  __device__ __forceinline__ float2 at(int p, int g) const {
+    const int l = g / nsc, k = g - l * nsc;
+    if (l == 0) return freq(p, 0, k);
+    if (l == 4) return freq(p, 1, k);
+    if (l == 7) return freq(p, 2, k);
+    if (l == 11) return freq(p, 3, k);
+    const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+    const float2 h0 = freq(p, s0, k), h1 = freq(p, s0 + 1, k);
+    const float f = s_ttab[l];
+    return make_float2(lerp_rn(h0.x, h1.x, f), lerp_rn(h0.y, h1.y, f));
+  }
+};
+
+template <int QM, bool FUSED>
+__device__ __forceinline__ void llr_stage(const DemodArgs& a, const ChanInterp& ci, int sf, int e0, int e1, int16_t* s_e, float n0) {
   const int nsc = a.nsc;
   const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
-  const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * nsc;
+  const float2* h0p = FUSED ? nullptr : a.ce + (size_t)sf * a.nof_ports * 14 * nsc;
   const int re0 = e0 / QM, re1 = e1 / QM;
   if (a.tm == 2 && a.nof_ports == 2) {
-    const float2* h1p = h0p + 14 * nsc;
+    const float2* h1p = FUSED ? nullptr : h0p + 14 * nsc;
     const float sq2 = a.k_sq2;
     for (int i = re0 + 2 * threadIdx.x; i < re1; i += 2 * blockDim.x) {
       const int g0 = __ldg(a.re_idx + i), g1 = __ldg(a.re_idx + i + 1);
-      const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
+      const float2 r0 = y[g0], r1 = y[g1];
+      const float2 h0 = FUSED ? ci.at(0, g0) : h0p[g0], h1 = FUSED ? ci.at(1, g0) : h1p[g0];
       const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
       const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
       const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
@@ -96,7 +128,7 @@ __device__ __forceinline__ void llr_stage(const DemodArgs& a, int sf, int e0, in
   } else {
     for (int i = re0 + threadIdx.x; i < re1; i += blockDim.x) {
       const int g0 = __ldg(a.re_idx + i);
-      const float2 r = y[g0], h = h0p[g0];
+      const float2 r = y[g0], h = FUSED ? ci.at(0, g0) : h0p[g0];
       const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
       const float2 d = make_float2(__fdiv_rn(dot_rn(r.x, h.x, r.y, h.y), den), __fdiv_rn(det_rn(r.y, h.x, r.x, h.y), den));
       emit_re<QM>(a, sf, i, e0, d, s_e);
@@ -119,10 +151,40 @@ __global__ void __launch_bounds__(512) pdsch_llr_dematch_kernel(const DemodArgs 
   const int e0 = a.cb_e_start[r], e1 = a.cb_e_start[r + 1], E = e1 - e0;
   const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
   if (threadIdx.x == 0) { s_e[E] = 0; s_e[E + 1] = (int16_t)-kTdC; }      // sentinels of the direct tables
-  switch (a.qm) {
-    case 2: llr_stage<2>(a, sf, e0, e1, s_e, n0); break;
-    case 4: llr_stage<4>(a, sf, e0, e1, s_e, n0); break;
-    default: llr_stage<6>(a, sf, e0, e1, s_e, n0); break;
+  ChanInterp ci;
+  if (a.pilots) {
+    // fused channel interpolation: the smoothed pilots of this subframe (6.4 KB per port at 100 PRB) live in
+    // shared memory behind the LLR buffer; the full estimate grid never exists in HBM
+    __shared__ float s_ftab[17];
+    __shared__ float s_ttab[14];
+    const int M = 2 * a.nof_prb, np = a.nof_ports;
+    float2* s_pil = reinterpret_cast<float2*>(s_e + ((E + 2 + 7) & ~7));
+    const float2* src = a.pilots + (size_t)sf * np * 4 * M;
+    for (int i = threadIdx.x; i < np * 4 * M; i += blockDim.x) s_pil[i] = src[i];
+    if (threadIdx.x < 17) s_ftab[threadIdx.x] = (float)((double)((int)threadIdx.x - 5) / 6.0);
+    if (threadIdx.x >= 32 && threadIdx.x < 46) {
+      const int l = threadIdx.x - 32;
+      const int crs_l[4] = {0, 4, 7, 11};
+      const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+      s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
+    }
+    ci.s_pil = s_pil; ci.s_ftab = s_ftab; ci.s_ttab = s_ttab; ci.nsc = a.nsc; ci.M = M;
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int si = 0; si < 4; si++) ci.off[p][si] = a.crs_off[p][si];
+    __syncthreads();
+    switch (a.qm) {
+      case 2: llr_stage<2, true>(a, ci, sf, e0, e1, s_e, n0); break;
+      case 4: llr_stage<4, true>(a, ci, sf, e0, e1, s_e, n0); break;
+      default: llr_stage<6, true>(a, ci, sf, e0, e1, s_e, n0); break;
+    }
+  } else {
+    switch (a.qm) {
+      case 2: llr_stage<2, false>(a, ci, sf, e0, e1, s_e, n0); break;
+      case 4: llr_stage<4, false>(a, ci, sf, e0, e1, s_e, n0); break;
+      default: llr_stage<6, false>(a, ci, sf, e0, e1, s_e, n0); break;
+    }
   }
   __syncthreads();
   const int cb_elems = a.cb_geom[4 * r], N = a.cb_geom[4 * r + 1];

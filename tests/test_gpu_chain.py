@@ -118,3 +118,39 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     L.srslte_tdec_free(C.byref(h))
     L.srslte_softbuffer_rx_free(C.byref(sb))
     L.srslte_ue_dl_free(C.byref(q))
+
+
+def test_cpp_offline_driver_worker_and_batch(gpu, oracle, tmp_path):
+    """driver/pdsch_offline.cc: the C++ host side replaying phch_worker's call sequence (mode worker) and the
+    batched call (mode batch) must both reproduce the oracle's transport blocks, CRC verdicts and iterations."""
+    import os, struct, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "pdsch_offline")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe,
+                               os.path.join(root, "driver", "pdsch_offline.cc"), "-L" + os.path.join(root, "srsue_b200"),
+                               "-lsrsue_gpu", "-Wl,-rpath," + os.path.join(root, "srsue_b200")])
+    o = oracle
+    prb, qm, tbs, n = 50, 6, 21384, 5
+    ocell = o.make_cell(prb, 1, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=qm, tbs=tbs)
+    iq = np.stack([o.gen_subframe(ocell, ocfg, 600 + i, 18.0 if i != 2 else 2.0)[1] for i in range(n)])
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<12i", 0x53525355, prb, 1, 1, 1, 1, 0x1234, qm, tbs, 0, n, 4))
+        f.write(iq.tobytes())
+    ref = [o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 0, 4) for i in range(n)]
+    for mode in ("worker", "batch"):
+        outp = tmp_path / ("out_%s.bin" % mode)
+        subprocess.check_call([exe, mode, str(inp), str(outp)])
+        raw = open(outp, "rb").read()
+        rec = 12 + tbs // 8
+        assert len(raw) == n * rec
+        for i in range(n):
+            ack, n_iter, snr = struct.unpack_from("<iif", raw, i * rec)
+            payload = np.frombuffer(raw, np.uint8, tbs // 8, i * rec + 12)
+            rc, pl, meas, avg = ref[i]
+            assert ack == int(rc == 0) and n_iter == avg, (mode, i)
+            assert np.array_equal(payload, pl), (mode, i)
+            assert abs(snr - meas[4]) <= 1e-4 * meas[4]
+    assert ref[2][0] != 0 and ref[0][0] == 0      # the noisy subframe fails, the others decode

@@ -146,3 +146,38 @@ def test_harq_accumulate_matches_oracle(gpu, oracle):
             torch.cuda.synchronize()
             assert np.array_equal(t.cpu().numpy(), sb_o[r, :3 * K + 12])
         plan.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "bw50_2p"])
+def test_fused_channel_interpolation_is_bit_identical(gpu, oracle, name):
+    """The whole-chain call never materialises the estimate grid: the demapper interpolates the smoothed pilots
+    per resource element.  Soft buffers must equal the unfused stage path bit for bit."""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    c = _cfgs(o)[name]
+    ocell = o.make_cell(c["prb"], c["ports"], 1)
+    ocfg = o.make_cfg(ocell, sf_idx=c["sf"], cfi=1, qm=c["qm"], tbs=c["tbs"], tm=c["tm"])
+    n_sf = 2
+    iq = np.stack([o.gen_subframe(ocell, ocfg, 3000 + i, c["snr"], c["taps"])[1] for i in range(n_sf)])
+    cell = sg.make_cell(c["prb"], c["ports"], 1)
+    cfg = sg.make_cfg(cell, sf_idx=c["sf"], cfi=1, qm=c["qm"], tbs=c["tbs"], tm=c["tm"])
+    plan = sg.PdschPlan(ctx, cell, cfg, n_sf)
+    I = plan.info
+    d_iq = torch.from_numpy(iq.view(np.float32).reshape(n_sf, -1)).cuda()
+    d_sf = torch.zeros((n_sf, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((n_sf, c["ports"] * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_pil = torch.zeros((n_sf, c["ports"] * 4 * 2 * c["prb"] * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((n_sf, 5), dtype=torch.float32, device="cuda")
+    d_meas2 = torch.zeros((n_sf, 5), dtype=torch.float32, device="cuda")
+    d_sb = torch.zeros((n_sf, I.sb_sf_stride), dtype=torch.int16, device="cuda")
+    d_sb2 = torch.full((n_sf, I.sb_sf_stride), 77, dtype=torch.int16, device="cuda")
+    plan.ofdm_rx(n_sf, d_iq, d_sf)
+    plan.chest(n_sf, d_sf, d_ce, d_meas)
+    plan.pdsch_llr(n_sf, d_sf, d_ce, d_meas, 0.01, 1, 0, d_sb)
+    plan.chest_pilots(n_sf, d_sf, d_pil, d_meas2)
+    plan.pdsch_llr_fused(n_sf, d_sf, d_pil, d_meas2, 0.01, 1, 0, d_sb2)
+    torch.cuda.synchronize()
+    assert torch.equal(d_meas, d_meas2)
+    assert torch.equal(d_sb, d_sb2)
+    plan.close()
