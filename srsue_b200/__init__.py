@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrsue_gpu.so")
+LIB_PATH = os.environ.get("SRSUE_GPU_LIB", os.path.join(_HERE, "libsrsue_gpu.so"))
 
 
 class Cell(C.Structure):
