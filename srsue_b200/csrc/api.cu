@@ -121,7 +121,8 @@ int turbo_ctas_per_sm() {
 TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb, bool crc) {
   const int per_sm = turbo_ctas_per_sm();
   const int slot_bytes = turbo_slot_words(g) * 4;
-  const int fixed = g.plane * 2 + (crc ? g.plane * 4 : 0) + 96;     // position table (+ CRC table) + flags
+  (void)crc;
+  const int fixed = g.plane * 2 + 96;                               // position table + flags
   const int smem_budget = (ctx->smem_sm - per_sm * 1024) / per_sm;  // 1 KB per CTA is reserved by the driver
   int ncb = (std::min(smem_budget, ctx->smem_optin) - fixed) / (slot_bytes + 8);
   ncb = std::min(ncb, (kTurboMaxThreads / per_sm) / g.T);
@@ -133,7 +134,7 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   c.ncb = ncb;
   c.threads = ((ncb * g.T + 31) / 32) * 32;
   c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms * per_sm);
-  c.smem = g.plane * 2 + (crc ? g.plane * 4 : 0) + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes;
+  c.smem = g.plane * 2 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes;
   return c;
 }
 

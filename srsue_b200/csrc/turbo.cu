@@ -287,7 +287,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
           const uint32_t nd = vsub(0u, vadd(x[i], ext));
           st16_wide(bits, p0, nd);
           st16_wide(bits, p1, nd >> 16);
-          if (CRC) crc ^= (sign_fill<0x9999>(nd) & s_tpos[p0]) ^ (sign_fill<0xBBBB>(nd) & s_tpos[p1]);
+          if (CRC) crc ^= (sign_fill<0x9999>(nd) & __ldg(s_tpos + p0)) ^ (sign_fill<0xBBBB>(nd) & __ldg(s_tpos + p1));
         }
         alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
         if ((i & 3) == 3) normalise(a);
@@ -310,15 +310,13 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   const int nflag = (g.ncb_cta + 3) & ~3;
 
   uint32_t* s_permw = smem;                                  // plane/2 words: DEC2 positions [W/8][T][8][2] x u16
-  uint32_t* s_tpos = s_permw + plane / 2;                    // plane words (0 without CRC): x^(pos) mod g per A position
-  uint32_t* s_crc = s_tpos + (crc_on ? plane : 0);           // per slot: CRC accumulator
+  const uint32_t* s_tpos = g.crc_tpos;                       // x^(pos) mod g per A position: 23 KB, read through L1
+  uint32_t* s_crc = s_permw + plane / 2;                     // per slot: CRC accumulator
   int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
   uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words
   int* s_active = s_next + nflag;
 
   for (int i = tid; i < plane / 2; i += blockDim.x) s_permw[i] = reinterpret_cast<const uint32_t*>(g.perm_pos)[i];
-  if (crc_on)
-    for (int i = tid; i < plane; i += blockDim.x) s_tpos[i] = g.crc_tpos[i];
 
   SlotCtx c;
   // slot stride = plane/2 words plus a skew that makes consecutive slots continue the bank sequence
