@@ -5,8 +5,12 @@
 // radix-2 decimation-in-time butterflies t = w*b, a' = a + t, b' = a - t, every float operation rounded
 // once (this file is compiled with -fmad=false), twiddles from the shared table.  The schedule is free:
 // each thread keeps 8 points in registers and performs three radix-2 stages per pass; passes exchange
-// data through (skewed) shared memory.  One CTA transforms one OFDM symbol; only the 12*N_PRB used bins
-// are written back, coalesced, already scaled.
+// data through skewed shared memory (ping-pong, one barrier per pass).  One CTA transforms one OFDM symbol;
+// only the 12*N_PRB used bins are written back, coalesced, already scaled.
+//
+// The kernel is issue-bound, so all index arithmetic is folded at compile time: every pass is a template
+// instance with constant N, L (length of the sub-transforms it combines) and radix, and both the skewed
+// shared-memory addresses and the twiddle addresses are "one base register + immediate offsets".
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,164 +42,139 @@ __device__ __forceinline__ void bfly_mj(float2& a, float2& b) {
   a = make_float2(__fadd_rn(a0.x, b0.y), __fsub_rn(a0.y, b0.x));
   b = make_float2(__fsub_rn(a0.x, b0.y), __fadd_rn(a0.y, b0.x));
 }
-// skew: one padding element per 16 float2 keeps strided exchanges off a single bank group
-__device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
 
-// One combining pass of radix R = 2^LOGR.  On entry v[r] = F_{n' + (N/L')r}[k] (sub-transforms of length
-// L); on exit v[u] = F'_{n'}[k + u L] (length L' = R L).  tw is the N/2-entry table of w_N^i.
-template <int LOGR>
-__device__ __forceinline__ void combine(float2 (&v)[8], int k, int L, int N, const float2* __restrict__ tw) {
-  constexpr int R = 1 << LOGR;
-  // stage A: pairs (r, r + R/2), twiddle w_{2L}^k
-  {
-    const float2 w = tw[k * (N / (2 * L))];
-#pragma unroll
-    for (int r = 0; r < R / 2; r++) bfly(v[r], v[r + R / 2], w);
-    // now v[r] = G_r[k], v[r + R/2] = G_r[k + L]
-  }
-  if (LOGR >= 2) {
-    // stage B: pairs (G_r, G_{r + R/4}) for k2 in {k, k + L}, twiddle w_{4L}^{k2}
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const float2 w = tw[(k + h * L) * (N / (4 * L))];
-#pragma unroll
-      for (int r = 0; r < R / 4; r++) bfly(v[h * (R / 2) + r], v[h * (R / 2) + r + R / 4], w);
-    }
-    // v[h*(R/2) + r] = H_r[k + hL], v[h*(R/2) + r + R/4] = H_r[k + hL + 2L]
-  }
-  if (LOGR >= 3) {
-    // stage C: pairs (H_0, H_1) for k4 in {k, k+L, k+2L, k+3L}, twiddle w_{8L}^{k4}
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const int k4 = k + h * L + q * 2 * L;
-        const float2 w = tw[k4 * (N / (8 * L))];
-        bfly(v[h * 4 + q * 2], v[h * 4 + q * 2 + 1], w);
-      }
-  }
-  // gather outputs in order u = 0..R-1 (output index k + uL)
-  float2 o[8];
-  if (LOGR == 3) {
-    // element h*4 + q*2 + e holds index k + hL + q 2L + e 4L  ->  u = h + 2q + 4e
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-#pragma unroll
-      for (int q = 0; q < 2; q++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) o[h + 2 * q + 4 * e] = v[h * 4 + q * 2 + e];
-  } else if (LOGR == 2) {
-    // element h*2 + e holds k + hL + e 2L -> u = h + 2e
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) o[h + 2 * e] = v[h * 2 + e];
-  } else {
-    o[0] = v[0]; o[1] = v[1];
-  }
-#pragma unroll
-  for (int u = 0; u < R; u++) v[u] = o[u];
-}
+// Shared-memory skew: element i lives at i + (i >> 4) (one padding float2 per 16), which keeps the strided
+// exchanges of the late passes off a single bank group.  The passes below never evaluate this per element;
+// they use the closed forms derived in fft_pass.
 
 // The first radix-8 pass (L = 1, k = 0): stage A uses w = 1, stage B w = 1 and -i, stage C w_8^0..3.
-__device__ __forceinline__ void combine_first8(float2 (&v)[8], int N, const float2* __restrict__ tw) {
+template <int N>
+__device__ __forceinline__ void combine_first8(float2 (&v)[8], const float2* __restrict__ tw) {
 #pragma unroll
   for (int r = 0; r < 4; r++) bfly_one(v[r], v[r + 4]);
   bfly_one(v[0], v[2]); bfly_one(v[1], v[3]);
   bfly_mj(v[4], v[6]); bfly_mj(v[5], v[7]);
   bfly_one(v[0], v[1]);
   bfly_mj(v[2], v[3]);
-  bfly(v[4], v[5], tw[N / 8]);
-  bfly(v[6], v[7], tw[3 * (N / 8)]);
-  float2 o[8];
-#pragma unroll
-  for (int h = 0; h < 2; h++)
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) o[h + 2 * q + 4 * e] = v[h * 4 + q * 2 + e];
-#pragma unroll
-  for (int u = 0; u < 8; u++) v[u] = o[u];
+  bfly(v[4], v[5], __ldg(tw + N / 8));
+  bfly(v[6], v[7], __ldg(tw + 3 * (N / 8)));
 }
 
-// First pass (global -> shared) or last pass (shared -> global, bin selection + scaling) for all
-// butterflies of this thread.  Data before a pass sits at index k*(N/L) + n, after it at k'*(N/L') + n'.
-template <int LOGR, bool FIRST, bool LAST>
-__device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, float2* sbuf, int N, int L,
-                                         const float2* __restrict__ tw, int tid, int nthreads, float2* __restrict__ gdst,
-                                         int nsc, float scale) {
+// One combining pass of radix R = 2^LOGR on sub-transforms of length L.  On entry v[r] = F_{n' + (N/L')r}[k];
+// on exit register reg_of_u(u) holds F'_{n'}[k + u L] (length L' = R L).  tw is the N/2-entry table of w_N^i.
+// Twiddle indices: stage A k N/(2L); stage B (k + hL) N/(4L); stage C (k + hL + q 2L) N/(8L) -- each is a
+// multiple of k plus a compile-time constant.
+template <int N, int L, int LOGR>
+__device__ __forceinline__ void combine(float2 (&v)[8], int k, const float2* __restrict__ tw) {
   constexpr int R = 1 << LOGR;
-  const int Lp = L * R, nsub = N / Lp;       // nsub = number of length-L' transforms
-  for (int b = tid; b < N / R; b += nthreads) {
-    const int k = b / nsub, np = b - k * nsub;
-    float2 v[8];
+  {
+    const float2 w = __ldg(tw + k * (N / (2 * L)));
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int idx = k * (N / L) + np + nsub * r;
-      v[r] = FIRST ? __ldg(gsrc + idx) : sbuf[skew(idx)];
+    for (int r = 0; r < R / 2; r++) bfly(v[r], v[r + R / 2], w);
+    // now v[r] = G_r[k], v[r + R/2] = G_r[k + L]
+  }
+  if (LOGR >= 2) {
+    const float2* t2 = tw + k * (N / (4 * L));
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float2 w = __ldg(t2 + h * (N / 4));
+#pragma unroll
+      for (int r = 0; r < R / 4; r++) bfly(v[h * (R / 2) + r], v[h * (R / 2) + r + R / 4], w);
     }
-    if (FIRST && LOGR == 3) combine_first8(v, N, tw); else combine<LOGR>(v, k, L, N, tw);
+    // v[h*(R/2) + r] = H_r[k + hL], v[h*(R/2) + r + R/4] = H_r[k + hL + 2L]
+  }
+  if (LOGR >= 3) {
+    const float2* t3 = tw + k * (N / (8 * L));
 #pragma unroll
-    for (int u = 0; u < R; u++) {
-      const int kp = k + u * L;
-      if (LAST) {
-        // kp is the DFT bin; keep the 12*N_PRB centred bins without DC, scaled by 1/sqrt(N)
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) bfly(v[h * 4 + q * 2], v[h * 4 + q * 2 + 1], __ldg(t3 + h * (N / 8) + q * (N / 4)));
+  }
+}
+
+// register that holds output u (index k + u L) after combine / combine_first8:
+// LOGR == 3: element h*4 + q*2 + e holds u = h + 2q + 4e;  LOGR == 2: element h*2 + e holds u = h + 2e
+template <int LOGR>
+__host__ __device__ constexpr int reg_of_u(int u) {
+  return LOGR == 3 ? ((u & 1) * 4 + ((u >> 1) & 1) * 2 + (u >> 2)) : LOGR == 2 ? ((u & 1) * 2 + (u >> 1)) : u;
+}
+
+// One pass for all butterflies of this thread.  Data before a pass sits at index k (N/L) + n (n < N/L), after
+// it at k' (N/L') + n'.  With nsub = N/L' and np < nsub:
+//   read  idx_r = k (N/L) + np + nsub r   (r < R)
+//   write idx_u = (k + u L) nsub + np = (k nsub + np) + u (N/R)
+// skew(i) = i + (i >> 4) splits into a base plus a per-r / per-u constant because no addend carries into bit 4:
+//   N/R >= 16 is a power of two                          -> skew(idx_u) = skew(k nsub + np) + u (N/R + N/(16R))
+//   N/L >= 16: k (N/L) is a multiple of 16, np < nsub    -> (idx_r >> 4) = k (N/L)/16 + (np >> 4) + ((nsub r) >> 4)
+//              (np >> 4 is 0 when nsub < 16; for nsub >= 16 nsub r is a multiple of 16)
+//   N/L <  16: np + nsub r < N/L, k (N/L) multiple of N/L -> (idx_r >> 4) = (k (N/L)) >> 4
+template <int N, int L, int LOGR, bool FIRST, bool LAST>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const float2* ssrc, float2* sdst,
+                                         float2* __restrict__ gdst, const float2* __restrict__ tw, int tid, int nthreads,
+                                         int nsc, float scale) {
+  constexpr int R = 1 << LOGR, nsub = N / (L * R), NL = N / L;
+  for (int b = tid; b < N / R; b += nthreads) {
+    const int k = b / nsub, np = b % nsub;          // powers of two: shift and mask
+    float2 v[8];
+    if (FIRST) {
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = __ldg(gsrc + np + nsub * r);       // L == 1, so k == 0
+    } else {
+      int base;
+      if (NL >= 16) base = k * (NL + NL / 16) + np + ((nsub >= 16) ? (np >> 4) : 0);
+      else base = k * NL + ((k * NL) >> 4) + np;
+      const float2* p = ssrc + base;
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = p[nsub * r + ((NL >= 16) ? ((nsub * r) >> 4) : 0)];
+    }
+    if (FIRST && LOGR == 3) combine_first8<N>(v, tw); else combine<N, L, LOGR>(v, k, tw);
+    if (LAST) {
+#pragma unroll
+      for (int u = 0; u < R; u++) {
+        // k + u L is the DFT bin; keep the 12*N_PRB centred bins without DC, scaled by 1/sqrt(N)
+        const int kp = k + u * L;
         int ko = -1;
         if (kp >= 1 && kp <= nsc / 2) ko = kp - 1 + nsc / 2;
         else if (kp >= N - nsc / 2) ko = kp - (N - nsc / 2);
-        if (ko >= 0) gdst[ko] = make_float2(__fmul_rn(v[u].x, scale), __fmul_rn(v[u].y, scale));
-      } else {
-        sbuf[skew(kp * nsub + np)] = v[u];
+        const float2 o = v[reg_of_u<LOGR>(u)];
+        if (ko >= 0) gdst[ko] = make_float2(__fmul_rn(o.x, scale), __fmul_rn(o.y, scale));
       }
+    } else {
+      const int w0 = k * nsub + np;
+      float2* p = sdst + w0 + (w0 >> 4);
+#pragma unroll
+      for (int u = 0; u < R; u++) p[u * (N / R + N / R / 16)] = v[reg_of_u<LOGR>(u)];
     }
   }
 }
 
-}  // namespace
-
-// Two shared buffers (ping-pong) avoid the read/write hazard of an in-place exchange, so each pass needs
-// a single barrier.  N <= 2048 -> 2 * 17 KB.
+// all passes of one N-point transform: radix 8 while it fits, then one radix-4 or radix-2 pass.  Two shared
+// buffers (ping-pong) avoid the read/write hazard of an in-place exchange, so each pass needs a single barrier.
 template <int LOG2N>
 __device__ __forceinline__ void fft_symbol(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s0,
                                            float2* s1, const float2* __restrict__ tw, int nsc, float scale) {
   constexpr int N = 1 << LOG2N;
+  static_assert(LOG2N >= 7 && LOG2N <= 11, "LTE transform sizes 128..2048");
   const int tid = threadIdx.x, nt = blockDim.x;
-  constexpr int NP3 = LOG2N / 3, REM = LOG2N % 3;       // NP3 radix-8 passes, then a radix-2^REM pass
-  int L = 1;
-  float2* cur = s0; float2* nxt = s1;
-  // first pass reads global memory (coalesced: consecutive threads read consecutive samples)
-  if (NP3 == 1 && REM == 0) { fft_pass<3, true, true>(gin, nullptr, N, L, tw, tid, nt, gout, nsc, scale); return; }
-  fft_pass<3, true, false>(gin, cur, N, L, tw, tid, nt, nullptr, nsc, scale);
-  L *= 8;
+  fft_pass<N, 1, 3, true, false>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale);
   __syncthreads();
-#pragma unroll
-  for (int p = 1; p < NP3; p++) {
-    const bool last = (p == NP3 - 1) && (REM == 0);
-    if (last) {
-      fft_pass<3, false, true>(nullptr, cur, N, L, tw, tid, nt, gout, nsc, scale);
-      return;
-    }
-    // read from cur, write to nxt
-    {
-      constexpr int R = 8;
-      const int Lp = L * R, nsub = N / Lp;
-      for (int b = tid; b < N / R; b += nt) {
-        const int k = b / nsub, np = b - k * nsub;
-        float2 v[8];
-#pragma unroll
-        for (int r = 0; r < R; r++) v[r] = cur[skew(k * (N / L) + np + nsub * r)];
-        combine<3>(v, k, L, N, tw);
-#pragma unroll
-        for (int u = 0; u < R; u++) nxt[skew((k + u * L) * nsub + np)] = v[u];
-      }
-    }
-    L *= 8;
+  fft_pass<N, 8, 3, false, false>(nullptr, s0, s1, nullptr, tw, tid, nt, nsc, scale);
+  __syncthreads();
+  if (LOG2N == 7) {             // 8 * 8 * 2
+    fft_pass<N, 64, 1, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
+  } else if (LOG2N == 8) {      // 8 * 8 * 4
+    fft_pass<N, 64, 2, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
+  } else if (LOG2N == 9) {      // 8 * 8 * 8
+    fft_pass<N, 64, 3, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
+  } else {                      // 8 * 8 * 8 * (2 | 4)
+    fft_pass<N, 64, 3, false, false>(nullptr, s1, s0, nullptr, tw, tid, nt, nsc, scale);
     __syncthreads();
-    float2* t = cur; cur = nxt; nxt = t;
+    if (LOG2N == 10) fft_pass<N, 512, 1, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+    else fft_pass<N, 512, 2, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
   }
-  if (REM == 2) fft_pass<2, false, true>(nullptr, cur, N, L, tw, tid, nt, gout, nsc, scale);
-  if (REM == 1) fft_pass<1, false, true>(nullptr, cur, N, L, tw, tid, nt, gout, nsc, scale);
 }
+
+}  // namespace
 
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
