@@ -134,6 +134,39 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t *plan, int n_sf, co
 /* number of kernels the most recent chain call launched (for the benchmark's gpu_launches) */
 int srsue_gpu_last_launch_count(srsue_gpu_ctx_t *ctx);
 
+/* ---- batching layer: heterogeneous streams of subframes ------------------------------------------
+ * Replaces, for batched/offline operation, the one-subframe-per-worker hand-off of the reference
+ * (ue/src/phy/phch_recv.cc:309-369, ue/src/common/thread_pool.cc:72-82) and the MAC's ownership of one soft
+ * buffer per HARQ process (ue/src/mac/dl_harq.cc:169-174,232).  A submission may mix any cells, bandwidths,
+ * grants, redundancy versions and UEs; descriptors with the same launch shape are packed into one launch of
+ * the chain each (plans are cached, least recently used evicted).  All pointers are HOST memory. */
+typedef struct srsue_gpu_batch srsue_gpu_batch_t;
+typedef struct {
+  srsue_gpu_cell_t cell;
+  srsue_gpu_pdsch_cfg_t cfg;       /* the grant as srslte_ue_dl_cfg_grant would configure it (incl. rv) */
+  const srsue_gpu_cf_t *iq;        /* in:  one subframe of time samples (sf_len = 15*nfft), caller-owned */
+  uint8_t *payload;                /* out: tbs/8 bytes, MSB first, caller-owned */
+  int64_t softbuffer_id;           /* < 0: no HARQ state (new transmission decoded from scratch);
+                                    * >= 0: device-resident soft buffer of this (UE, HARQ process) id */
+  int32_t new_data;                /* 1: reset the soft buffer first (dl_harq.cc:232); 0: combine into it */
+  int32_t crc_ok;                  /* out: 1 when the transport-block CRC passed (ack) */
+  int32_t n_iter;                  /* out: srslte_pdsch_last_noi() of this subframe */
+  float meas[5];                   /* out: noise, rsrp, rssi, rsrq, snr of this subframe */
+} srsue_gpu_sf_desc_t;
+
+/* max_subframes bounds one submission.  noise_est / noise_mode / max_iter as in srsue_gpu_pdsch_decode_batch. */
+int srsue_gpu_batch_create(srsue_gpu_ctx_t *ctx, int max_subframes, float noise_est, int noise_mode, int max_iter,
+                           srsue_gpu_batch_t **batch);
+void srsue_gpu_batch_destroy(srsue_gpu_batch_t *batch);
+/* enqueues uploads, launches and downloads for n descriptors and returns; `descs`, the IQ and the payload
+ * buffers must stay valid until srsue_gpu_batch_wait, which also fills the out fields of every descriptor */
+int srsue_gpu_batch_submit(srsue_gpu_batch_t *batch, srsue_gpu_sf_desc_t *descs, int n);
+int srsue_gpu_batch_wait(srsue_gpu_batch_t *batch);
+/* frees the device soft buffer of one id (a HARQ process that was acknowledged or flushed) */
+int srsue_gpu_batch_softbuffer_release(srsue_gpu_batch_t *batch, int64_t softbuffer_id);
+/* cached plans, resident soft buffers, kernels launched by the last submission */
+int srsue_gpu_batch_stats(const srsue_gpu_batch_t *batch, int *n_plans, int *n_softbuffers, int *launches);
+
 /* ---- host-side bookkeeping, usable without a GPU (what srslte_ue_dl_cfg_grant computes on the host,
  * phch_worker.cc:337; exported so that the tables can be checked on a CPU-only machine) ------------- */
 /* code-block segmentation of a transport block: out[8] = tbs, B, C, K+, K-, C+, C-, F */

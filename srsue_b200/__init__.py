@@ -26,6 +26,13 @@ class PlanInfo(C.Structure):
                                        "sb_cb_stride", "sb_sf_stride", "payload_stride", "max_batch")]
 
 
+class SfDesc(C.Structure):
+    """srsue_gpu_sf_desc_t (include/srsue_gpu/srsue_gpu.h)"""
+    _fields_ = [("cell", Cell), ("cfg", PdschCfg), ("iq", C.c_void_p), ("payload", C.c_void_p),
+                ("softbuffer_id", C.c_int64), ("new_data", C.c_int32), ("crc_ok", C.c_int32), ("n_iter", C.c_int32),
+                ("meas", C.c_float * 5)]
+
+
 class GpuError(RuntimeError):
     pass
 
@@ -165,6 +172,53 @@ class PdschPlan:
         _check(lib().srsue_gpu_pdsch_decode_batch_host(self.h, n_sf, _ptr(h_iq), C.c_float(noise_est), noise_mode, max_iter,
                                                        _ptr(h_payload), _ptr(h_tb_status), _ptr(h_meas)),
                "pdsch_decode_batch_host")
+
+
+class Batch:
+    """srsue_gpu_batch_*: heterogeneous subframe streams.  Keeps the numpy buffers alive until wait()."""
+
+    def __init__(self, ctx, max_subframes, noise_est=0.01, noise_mode=0, max_iter=4):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        lib().srsue_gpu_batch_softbuffer_release.argtypes = [C.c_void_p, C.c_int64]
+        _check(lib().srsue_gpu_batch_create(ctx.h, max_subframes, C.c_float(noise_est), noise_mode, max_iter, C.byref(self.h)),
+               "srsue_gpu_batch_create")
+        self._keep = None
+
+    def submit(self, items):
+        """items: list of dicts {cell, cfg, iq (complex64 array), softbuffer_id (default -1), new_data (default 1)}"""
+        import numpy as np
+        n = len(items)
+        descs = (SfDesc * n)()
+        payloads = []
+        for d, it in zip(descs, items):
+            d.cell, d.cfg = it["cell"], it["cfg"]
+            pl = np.zeros((it["cfg"].tbs + 7) // 8, np.uint8)
+            payloads.append(pl)
+            d.iq, d.payload = it["iq"].ctypes.data, pl.ctypes.data
+            d.softbuffer_id = it.get("softbuffer_id", -1)
+            d.new_data = it.get("new_data", 1)
+        self._keep = (descs, payloads, items)
+        _check(lib().srsue_gpu_batch_submit(self.h, descs, n), "srsue_gpu_batch_submit")
+
+    def wait(self):
+        _check(lib().srsue_gpu_batch_wait(self.h), "srsue_gpu_batch_wait")
+        descs, payloads, _ = self._keep
+        self._keep = None
+        return [dict(payload=pl, crc_ok=d.crc_ok, n_iter=d.n_iter, meas=list(d.meas)) for d, pl in zip(descs, payloads)]
+
+    def release_softbuffer(self, sid):
+        _check(lib().srsue_gpu_batch_softbuffer_release(self.h, sid), "srsue_gpu_batch_softbuffer_release")
+
+    def stats(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        lib().srsue_gpu_batch_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(plans=a.value, softbuffers=b.value, launches=c.value)
+
+    def close(self):
+        if self.h:
+            lib().srsue_gpu_batch_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 def make_cell(nof_prb, nof_ports=1, cell_id=1):

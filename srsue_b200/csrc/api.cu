@@ -65,6 +65,11 @@ struct Scratch {
 
 }  // namespace
 
+namespace srsue {
+// error reporting for the other translation units of the library (batch.cu)
+int internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+}  // namespace srsue
+
 struct srsue_gpu_ctx {
   int device = 0, num_sms = 0, smem_optin = 0, smem_sm = 0;
   std::mutex mu;

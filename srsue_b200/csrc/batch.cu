@@ -1,0 +1,316 @@
+// batch.cu -- the batching layer of libsrsue_gpu: takes an arbitrary stream of subframe descriptors (any mix of
+// bandwidths, grants, redundancy versions and UEs), packs the ones that share a (cell, grant) shape into one launch
+// each, and keeps per-(UE, HARQ process) soft buffers resident on the device.
+//
+// It replaces, for offline / batched operation, the hand-off of ONE subframe to ONE worker thread
+// (/root/reference/ue/src/phy/phch_recv.cc:309-369 acquiring a worker, ue/src/common/thread_pool.cc:72-82,206-254
+// running it) and the per-process soft-buffer ownership of the MAC (ue/src/mac/dl_harq.cc:169-174 init,
+// :232 reset on new data, :216-259 rv selection).  Everything here sits above the public C ABI of api.cu
+// (plans + srsue_gpu_pdsch_decode_batch); the only device code is the row gather/scatter of soft buffers.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "srsue_gpu/srsue_gpu.h"
+
+namespace srsue {
+int internal_fail(int code, const char* msg);   // api.cu: sets srsue_gpu_last_error()
+}
+
+namespace {
+
+#define B_FAIL(code, ...)                                   \
+  do {                                                      \
+    char buf_[384];                                         \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);              \
+    return srsue::internal_fail(code, buf_);                \
+  } while (0)
+
+#define B_CU(call)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) B_FAIL(SRSUE_GPU_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// copies rows between a packed [n][row_elems] array and per-row device buffers (rows[i] == nullptr: skip).
+// One CTA per row; 16-byte accesses (row buffers come from cudaMalloc, row_elems is a multiple of 8).
+__global__ void __launch_bounds__(256) softbuffer_rows_kernel(int16_t* packed, int16_t* const* rows, int row_elems, int to_rows) {
+  int16_t* r = rows[blockIdx.x];
+  if (r == nullptr) return;
+  uint4* a = reinterpret_cast<uint4*>(packed + (size_t)blockIdx.x * row_elems);
+  uint4* b = reinterpret_cast<uint4*>(r);
+  const int n = row_elems / 8;
+  if (to_rows) for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = a[i];
+  else for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = b[i];
+}
+
+struct PlanEntry {
+  srsue_gpu_pdsch_plan_t* plan = nullptr;
+  srsue_gpu_plan_info_t info{};
+  std::list<std::string>::iterator lru;
+};
+
+struct SoftBuffer { int16_t* d = nullptr; int elems = 0; };
+
+}  // namespace
+
+struct srsue_gpu_batch {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  int max_subframes = 0, chunk_cap = 0, max_iter = 4, noise_mode = 0, max_plans = 16;
+  float noise_est = 0.01f;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_up[2] = {}, ev_free[2] = {};
+  // plan cache keyed by the bytes of (cell, cfg)
+  std::map<std::string, PlanEntry> plans;
+  std::list<std::string> lru;
+  // device staging (grown on demand)
+  srsue_gpu_cf_t* d_iq[2] = {nullptr, nullptr}; size_t iq_elems[2] = {0, 0};
+  uint8_t* d_payload = nullptr; size_t payload_bytes = 0;
+  int32_t* d_status = nullptr; float* d_meas = nullptr;
+  int16_t* d_sb = nullptr; size_t sb_elems = 0;
+  int16_t** d_rows = nullptr;
+  // pinned result staging, in processing order
+  int32_t* h_status = nullptr; float* h_meas = nullptr; int16_t** h_rows = nullptr;
+  std::vector<int> order;                 // processing position -> descriptor index
+  srsue_gpu_sf_desc_t* pending = nullptr; int n_pending = 0;
+  std::map<int64_t, SoftBuffer> softbuffers;
+  int launches = 0, plan_launches = 0;
+  int half = 0;
+};
+
+namespace {
+
+std::string plan_key(const srsue_gpu_sf_desc_t& d) {
+  // explicit fields only (struct padding must not split buckets)
+  const int v[10] = {d.cell.nof_prb, d.cell.nof_ports, d.cell.cell_id, d.cfg.sf_idx, d.cfg.cfi, d.cfg.rnti, d.cfg.qm, d.cfg.tbs, d.cfg.rv, d.cfg.tm};
+  std::string k(reinterpret_cast<const char*>(v), sizeof(v));
+  for (int i = 0; i < 110; i++) k.push_back(d.cfg.prb_mask[i] ? 1 : 0);
+  return k;
+}
+
+int get_plan(srsue_gpu_batch* b, const std::string& key, const srsue_gpu_sf_desc_t& d, PlanEntry** out) {
+  auto it = b->plans.find(key);
+  if (it != b->plans.end()) {
+    b->lru.erase(it->second.lru);
+    b->lru.push_front(key);
+    it->second.lru = b->lru.begin();
+    *out = &it->second;
+    return 0;
+  }
+  if ((int)b->plans.size() >= b->max_plans) {
+    // evict the least recently used plan; its work may still be in flight on the compute stream
+    B_CU(cudaStreamSynchronize(b->s_compute));
+    const std::string victim = b->lru.back();
+    b->lru.pop_back();
+    srsue_gpu_pdsch_plan_destroy(b->plans[victim].plan);
+    b->plans.erase(victim);
+  }
+  PlanEntry e;
+  int rc = srsue_gpu_pdsch_plan_create(b->ctx, &d.cell, &d.cfg, b->chunk_cap, &e.plan);
+  if (rc) return rc;
+  srsue_gpu_pdsch_plan_info(e.plan, &e.info);
+  b->lru.push_front(key);
+  e.lru = b->lru.begin();
+  auto ins = b->plans.emplace(key, e);
+  *out = &ins.first->second;
+  return 0;
+}
+
+template <typename T>
+int grow(T** p, size_t* have, size_t want, cudaStream_t s) {
+  if (want <= *have) return 0;
+  if (*p) { B_CU(cudaStreamSynchronize(s)); B_CU(cudaFree(*p)); *p = nullptr; }
+  B_CU(cudaMalloc((void**)p, want * sizeof(T)));
+  *have = want;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srsue_gpu_batch_create(srsue_gpu_ctx_t* ctx, int max_subframes, float noise_est, int noise_mode, int max_iter,
+                           srsue_gpu_batch_t** out) {
+  if (!ctx || !out || max_subframes < 1 || max_iter < 1) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_create: bad arguments");
+  *out = nullptr;
+  auto* b = new srsue_gpu_batch();
+  b->ctx = ctx;
+  b->max_subframes = max_subframes;
+  b->chunk_cap = std::min(max_subframes, 1024);
+  b->noise_est = noise_est; b->noise_mode = noise_mode; b->max_iter = max_iter;
+  B_CU(cudaStreamCreateWithFlags(&b->s_compute, cudaStreamNonBlocking));
+  B_CU(cudaStreamCreateWithFlags(&b->s_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    B_CU(cudaEventCreateWithFlags(&b->ev_up[i], cudaEventDisableTiming));
+    B_CU(cudaEventCreateWithFlags(&b->ev_free[i], cudaEventDisableTiming));
+  }
+  B_CU(cudaMalloc((void**)&b->d_status, (size_t)b->chunk_cap * 4 * sizeof(int32_t)));
+  B_CU(cudaMalloc((void**)&b->d_meas, (size_t)b->chunk_cap * 5 * sizeof(float)));
+  B_CU(cudaMalloc((void**)&b->d_rows, (size_t)b->chunk_cap * sizeof(int16_t*)));
+  B_CU(cudaMallocHost((void**)&b->h_status, (size_t)max_subframes * 4 * sizeof(int32_t)));
+  B_CU(cudaMallocHost((void**)&b->h_meas, (size_t)max_subframes * 5 * sizeof(float)));
+  B_CU(cudaMallocHost((void**)&b->h_rows, (size_t)max_subframes * sizeof(int16_t*)));
+  *out = b;
+  return 0;
+}
+
+void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
+  if (!b) return;
+  cudaStreamSynchronize(b->s_compute);
+  cudaStreamSynchronize(b->s_copy);
+  for (auto& kv : b->plans) srsue_gpu_pdsch_plan_destroy(kv.second.plan);
+  for (auto& kv : b->softbuffers) cudaFree(kv.second.d);
+  cudaFree(b->d_iq[0]); cudaFree(b->d_iq[1]); cudaFree(b->d_payload); cudaFree(b->d_status); cudaFree(b->d_meas);
+  cudaFree(b->d_sb); cudaFree(b->d_rows);
+  cudaFreeHost(b->h_status); cudaFreeHost(b->h_meas); cudaFreeHost(b->h_rows);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(b->ev_up[i]); cudaEventDestroy(b->ev_free[i]); }
+  cudaStreamDestroy(b->s_compute); cudaStreamDestroy(b->s_copy);
+  delete b;
+}
+
+int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
+  if (!b || !descs || n < 0 || n > b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: bad arguments (n=%d)", n);
+  if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
+  b->launches = 0;
+  b->order.clear();
+  // ---- bucket the descriptors by launch shape, keeping arrival order inside a bucket -----------------------
+  std::map<std::string, std::vector<int>> groups;
+  std::vector<std::string> group_order;
+  std::map<int64_t, int> seen;
+  for (int i = 0; i < n; i++) {
+    const srsue_gpu_sf_desc_t& d = descs[i];
+    if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptor %d has a null buffer", i);
+    // buckets are launched one after the other, not in arrival order, so one HARQ process may appear only once
+    // per submission (its transmissions are 8 ms apart on the air anyway)
+    if (d.softbuffer_id >= 0 && !seen.emplace(d.softbuffer_id, i).second)
+      B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptors %d and %d use soft buffer %lld in one submission",
+             seen[d.softbuffer_id], i, (long long)d.softbuffer_id);
+    std::string k = plan_key(d);
+    // new transmissions and HARQ combines use different launches (reset vs accumulate), as do tracked and
+    // untracked soft buffers
+    k.push_back(d.softbuffer_id >= 0 ? (d.new_data ? 1 : 2) : 0);
+    auto it = groups.find(k);
+    if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }
+    it->second.push_back(i);
+  }
+  // ---- one chain launch per bucket chunk --------------------------------------------------------------------
+  for (const std::string& gk : group_order) {
+    const std::vector<int>& idx = groups[gk];
+    const srsue_gpu_sf_desc_t& d0 = descs[idx[0]];
+    const int mode = gk.back();                       // 0 untracked, 1 tracked new data, 2 tracked combine
+    if (mode == 0 && !d0.new_data) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: HARQ combining needs a softbuffer_id", idx[0]);
+    PlanEntry* pe = nullptr;
+    int rc = get_plan(b, gk.substr(0, gk.size() - 1), d0, &pe);
+    if (rc) return rc;
+    const srsue_gpu_plan_info_t& info = pe->info;
+    const size_t cap = (size_t)b->chunk_cap;
+    for (int i = 0; i < 2; i++) { rc = grow(&b->d_iq[i], &b->iq_elems[i], cap * info.sf_len, b->s_compute); if (rc) return rc; }
+    rc = grow(&b->d_payload, &b->payload_bytes, cap * info.payload_stride, b->s_compute);
+    if (rc) return rc;
+    if (mode) { rc = grow(&b->d_sb, &b->sb_elems, cap * info.sb_sf_stride, b->s_compute); if (rc) return rc; }
+    for (size_t off = 0; off < idx.size(); off += cap) {
+      const int m = (int)std::min(cap, idx.size() - off);
+      const int h = b->half;
+      b->half ^= 1;
+      // upload: merge subframes that are adjacent in host memory into one copy
+      B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
+      for (int r = 0; r < m;) {
+        int e = r + 1;
+        while (e < m && descs[idx[off + e]].iq == descs[idx[off + e - 1]].iq + info.sf_len) e++;
+        B_CU(cudaMemcpyAsync(b->d_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq,
+                             (size_t)(e - r) * info.sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, b->s_copy));
+        r = e;
+      }
+      B_CU(cudaEventRecord(b->ev_up[h], b->s_copy));
+      B_CU(cudaStreamWaitEvent(b->s_compute, b->ev_up[h], 0));
+      const size_t pos0 = b->order.size();
+      int16_t* d_sb = nullptr;
+      if (mode) {
+        // resident soft buffers of the (UE, HARQ process) ids of this chunk
+        for (int r = 0; r < m; r++) {
+          const srsue_gpu_sf_desc_t& d = descs[idx[off + r]];
+          SoftBuffer& sb = b->softbuffers[d.softbuffer_id];
+          if (sb.d && sb.elems != info.sb_sf_stride) {
+            if (mode == 2) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: soft buffer %lld holds a different transport block size", idx[off + r], (long long)d.softbuffer_id);
+            B_CU(cudaStreamSynchronize(b->s_compute));
+            B_CU(cudaFree(sb.d)); sb.d = nullptr;
+          }
+          if (!sb.d) {
+            if (mode == 2) {
+              b->softbuffers.erase(d.softbuffer_id);
+              B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: soft buffer %lld has no earlier transmission", idx[off + r], (long long)d.softbuffer_id);
+            }
+            B_CU(cudaMalloc((void**)&sb.d, (size_t)info.sb_sf_stride * sizeof(int16_t)));
+            sb.elems = info.sb_sf_stride;
+          }
+          b->h_rows[pos0 + r] = sb.d;
+        }
+        B_CU(cudaMemcpyAsync(b->d_rows, b->h_rows + pos0, (size_t)m * sizeof(int16_t*), cudaMemcpyHostToDevice, b->s_compute));
+        d_sb = b->d_sb;
+        if (mode == 2) { softbuffer_rows_kernel<<<m, 256, 0, b->s_compute>>>(d_sb, b->d_rows, info.sb_sf_stride, 0); b->launches++; }
+      }
+      rc = srsue_gpu_pdsch_decode_batch(pe->plan, m, b->d_iq[h], b->noise_est, b->noise_mode, b->max_iter, mode == 2, d_sb, b->d_payload,
+                                        b->d_status, b->d_meas, b->s_compute);
+      if (rc) return rc;
+      b->launches += srsue_gpu_last_launch_count(b->ctx);
+      B_CU(cudaEventRecord(b->ev_free[h], b->s_compute));
+      if (mode) { softbuffer_rows_kernel<<<m, 256, 0, b->s_compute>>>(d_sb, b->d_rows, info.sb_sf_stride, 1); b->launches++; }
+      // results: payload rows to the callers' buffers (adjacent buffers merged), status and measurements to staging
+      const size_t pbytes = (size_t)(info.payload_stride);
+      for (int r = 0; r < m;) {
+        int e = r + 1;
+        while (e < m && descs[idx[off + e]].payload == descs[idx[off + e - 1]].payload + pbytes) e++;
+        B_CU(cudaMemcpyAsync(descs[idx[off + r]].payload, b->d_payload + (size_t)r * pbytes, (size_t)(e - r) * pbytes,
+                             cudaMemcpyDeviceToHost, b->s_compute));
+        r = e;
+      }
+      B_CU(cudaMemcpyAsync(b->h_status + pos0 * 4, b->d_status, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->s_compute));
+      B_CU(cudaMemcpyAsync(b->h_meas + pos0 * 5, b->d_meas, (size_t)m * 5 * sizeof(float), cudaMemcpyDeviceToHost, b->s_compute));
+      for (int r = 0; r < m; r++) b->order.push_back(idx[off + r]);
+    }
+  }
+  b->pending = descs;
+  b->n_pending = n;
+  return 0;
+}
+
+int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
+  if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_wait: null batch");
+  if (!b->pending) return 0;
+  B_CU(cudaStreamSynchronize(b->s_compute));
+  for (size_t pos = 0; pos < b->order.size(); pos++) {
+    srsue_gpu_sf_desc_t& d = b->pending[b->order[pos]];
+    d.crc_ok = b->h_status[pos * 4 + 0];
+    d.n_iter = b->h_status[pos * 4 + 2];
+    std::memcpy(d.meas, b->h_meas + pos * 5, 5 * sizeof(float));
+  }
+  b->pending = nullptr;
+  b->n_pending = 0;
+  return 0;
+}
+
+int srsue_gpu_batch_softbuffer_release(srsue_gpu_batch_t* b, int64_t softbuffer_id) {
+  if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "softbuffer_release: null batch");
+  auto it = b->softbuffers.find(softbuffer_id);
+  if (it == b->softbuffers.end()) return 0;
+  B_CU(cudaStreamSynchronize(b->s_compute));
+  cudaFree(it->second.d);
+  b->softbuffers.erase(it);
+  return 0;
+}
+
+int srsue_gpu_batch_stats(const srsue_gpu_batch_t* b, int* n_plans, int* n_softbuffers, int* launches) {
+  if (!b) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  if (n_plans) *n_plans = (int)b->plans.size();
+  if (n_softbuffers) *n_softbuffers = (int)b->softbuffers.size();
+  if (launches) *launches = b->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -160,16 +160,16 @@ __device__ __forceinline__ void fft_symbol(const float2* __restrict__ gin, float
   __syncthreads();
   fft_pass<N, 8, 3, false, false>(nullptr, s0, s1, nullptr, tw, tid, nt, nsc, scale);
   __syncthreads();
-  if (LOG2N == 7) {             // 8 * 8 * 2
+  if constexpr (LOG2N == 7) {             // 8 * 8 * 2
     fft_pass<N, 64, 1, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
-  } else if (LOG2N == 8) {      // 8 * 8 * 4
+  } else if constexpr (LOG2N == 8) {      // 8 * 8 * 4
     fft_pass<N, 64, 2, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
-  } else if (LOG2N == 9) {      // 8 * 8 * 8
+  } else if constexpr (LOG2N == 9) {      // 8 * 8 * 8
     fft_pass<N, 64, 3, false, true>(nullptr, s1, nullptr, gout, tw, tid, nt, nsc, scale);
   } else {                      // 8 * 8 * 8 * (2 | 4)
     fft_pass<N, 64, 3, false, false>(nullptr, s1, s0, nullptr, tw, tid, nt, nsc, scale);
     __syncthreads();
-    if (LOG2N == 10) fft_pass<N, 512, 1, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+    if constexpr (LOG2N == 10) fft_pass<N, 512, 1, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
     else fft_pass<N, 512, 2, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
   }
 }

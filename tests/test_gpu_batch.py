@@ -1,0 +1,137 @@
+"""The batching layer (srsue_gpu_batch_*): a heterogeneous stream of subframes -- BASELINE config 5, mixed
+1.4-20 MHz bandwidths, modulations, transmission modes and subframe numbers in arrival order -- must come back
+exactly as the oracle decodes each subframe on its own; HARQ soft buffers stay resident between submissions
+(reference behaviour: one subframe per worker, phch_recv.cc:309-369; soft buffers per process, dl_harq.cc:169-259)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MIX = [  # prb, ports, qm, tbs, tm, sf_idx, cfi, snr
+    (6, 1, 2, 152, 1, 1, 1, 10.0),
+    (15, 1, 4, 2216, 1, 3, 2, 16.0),
+    (25, 1, 6, 11448, 1, 2, 2, 24.0),
+    (50, 2, 4, 6208, 2, 4, 1, 18.0),
+    (100, 1, 6, 75376, 1, 1, 1, 30.0),
+    (100, 2, 4, 30576, 2, 6, 1, 15.0),
+    (25, 1, 6, 11448, 1, 0, 2, 24.0),     # subframe 0: PSS/SSS/PBCH holes
+]
+
+
+def _pair(sg, o, row, rv=0):
+    prb, ports, qm, tbs, tm, sf, cfi, snr = row
+    ocell = o.make_cell(prb, ports, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=sf, cfi=cfi, qm=qm, tbs=tbs, tm=tm, rv=rv)
+    cell = sg.make_cell(prb, ports, 1)
+    cfg = sg.make_cfg(cell, sf_idx=sf, cfi=cfi, qm=qm, tbs=tbs, tm=tm, rv=rv)
+    return ocell, ocfg, cell, cfg
+
+
+def test_mixed_stream_matches_oracle(gpu, oracle):
+    sg, ctx = gpu
+    o = oracle
+    rng = np.random.default_rng(5)
+    order = [int(x) for x in rng.integers(0, len(MIX), 40)]
+    items, refs = [], []
+    for i, m in enumerate(order):
+        ocell, ocfg, cell, cfg = _pair(sg, o, MIX[m])
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 50000 + i, MIX[m][7])
+        items.append(dict(cell=cell, cfg=cfg, iq=iq))
+        refs.append((ocell, ocfg, iq, tb))
+    b = sg.Batch(ctx, 64)
+    b.submit(items)
+    res = b.wait()
+    st = b.stats()
+    assert st["plans"] == len(set(order)) and st["launches"] >= 5 * len(set(order))
+    for r, (ocell, ocfg, iq, tb) in zip(res, refs):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
+        assert (r["crc_ok"] == 1) == (rc == 0)
+        assert np.array_equal(r["payload"], pl)
+        assert r["n_iter"] == avg
+        assert np.allclose(r["meas"], meas, rtol=1e-4)
+        assert rc == 0 and np.array_equal(pl, tb)
+    # a second submission reuses the cached plans
+    b.submit(items[:7])
+    res2 = b.wait()
+    for r, r0 in zip(res2, res[:7]):
+        assert np.array_equal(r["payload"], r0["payload"]) and r["crc_ok"] == r0["crc_ok"]
+    assert b.stats()["plans"] == st["plans"]
+    b.close()
+
+
+def test_chunking_and_contiguous_merge(gpu, oracle):
+    """more subframes of one shape than the chunk capacity, IQ rows adjacent in memory (merged copies)"""
+    sg, ctx = gpu
+    o = oracle
+    ocell, ocfg, cell, cfg = _pair(sg, o, MIX[1])
+    pool = np.stack([o.gen_subframe(ocell, ocfg, 61000 + i, 16.0)[1] for i in range(6)])
+    n = 2500                                   # chunk capacity is 1024
+    big = np.ascontiguousarray(pool[np.arange(n) % 6])
+    items = [dict(cell=cell, cfg=cfg, iq=big[i]) for i in range(n)]
+    b = sg.Batch(ctx, n)
+    b.submit(items)
+    res = b.wait()
+    ref = [o.ue_dl_decode(ocell, ocfg, pool[i], 0.01, 0, 4) for i in range(6)]
+    for i, r in enumerate(res):
+        rc, pl, meas, avg = ref[i % 6]
+        assert (r["crc_ok"] == 1) == (rc == 0) and np.array_equal(r["payload"], pl) and r["n_iter"] == avg
+    b.close()
+
+
+def test_resident_harq_softbuffers(gpu, oracle):
+    """two HARQ processes interleaved with untracked traffic: rv 0 fails at low SNR, rv 2 combines into the
+    device-resident soft buffer in a later submission and matches the oracle carrying its own soft buffer"""
+    sg, ctx = gpu
+    o = oracle
+    row = (25, 1, 6, 11448, 1, 2, 2, 11.0)
+    other = MIX[0]
+    b = sg.Batch(ctx, 16)
+    sb_o = {7: None, 9: None}
+    verdicts = []
+    for rv in (0, 2):
+        items, refs = [], []
+        for sid, seed in ((7, 42), (9, 43)):
+            ocell, ocfg, cell, cfg = _pair(sg, o, row, rv)
+            tb, iq, _ = o.gen_subframe(ocell, ocfg, seed, row[7])
+            items.append(dict(cell=cell, cfg=cfg, iq=iq, softbuffer_id=sid, new_data=1 if rv == 0 else 0))
+            refs.append((sid, ocell, ocfg, iq, tb))
+            oc2, og2, c2, g2 = _pair(sg, o, other)
+            items.append(dict(cell=c2, cfg=g2, iq=o.gen_subframe(oc2, og2, 70 + sid, other[7])[1]))
+            refs.append(None)
+        b.submit(items)
+        res = b.wait()
+        for r, ref in zip(res, refs):
+            if ref is None:
+                assert r["crc_ok"] == 1
+                continue
+            sid, ocell, ocfg, iq, tb = ref
+            if sb_o[sid] is None:
+                sb_o[sid] = o.new_softbuf(o.cbsegm(ocfg.tbs).C)
+            sf_o = o.ofdm_rx(row[0], iq)
+            ce_o, _ = o.chest(ocell, row[5], sf_o)
+            rc, pl = o.pdsch_decode(ocell, ocfg, sf_o, ce_o, 0.01, 4, softbuf=sb_o[sid])
+            assert (r["crc_ok"] == 1) == (rc == 0)
+            assert np.array_equal(r["payload"], pl)
+            verdicts.append((rv, rc == 0))
+    assert b.stats()["softbuffers"] == 2
+    assert all(ok for rv, ok in verdicts if rv == 2) and not all(ok for rv, ok in verdicts if rv == 0)
+    b.release_softbuffer(7)
+    assert b.stats()["softbuffers"] == 1
+    b.close()
+
+
+def test_batch_argument_errors(gpu, oracle):
+    sg, ctx = gpu
+    o = oracle
+    ocell, ocfg, cell, cfg = _pair(sg, o, MIX[0])
+    iq = o.gen_subframe(ocell, ocfg, 1, 10.0)[1]
+    b = sg.Batch(ctx, 4)
+    with pytest.raises(sg.GpuError):      # same HARQ process twice in one submission
+        b.submit([dict(cell=cell, cfg=cfg, iq=iq, softbuffer_id=1), dict(cell=cell, cfg=cfg, iq=iq, softbuffer_id=1)])
+    with pytest.raises(sg.GpuError):      # combining needs an earlier transmission
+        b.submit([dict(cell=cell, cfg=cfg, iq=iq, softbuffer_id=2, new_data=0)])
+    with pytest.raises(sg.GpuError):      # more than max_subframes
+        b.submit([dict(cell=cell, cfg=cfg, iq=iq)] * 5)
+    b.submit([dict(cell=cell, cfg=cfg, iq=iq)])
+    assert b.wait()[0]["crc_ok"] == 1
+    b.close()
