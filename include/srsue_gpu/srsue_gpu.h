@@ -184,6 +184,11 @@ int srsue_gpu_host_gold(uint32_t c_init, int n, uint8_t *c);
 /* ---- pinned host memory helpers (so callers need not link the CUDA runtime) ------------------- */
 void *srsue_gpu_host_alloc(uint64_t bytes);
 void srsue_gpu_host_free(void *p);
+/* page-locks a caller-owned region (e.g. the capture buffer).  Subframes and payload buffers that lie inside
+ * regions from srsue_gpu_host_alloc / srsue_gpu_host_register are fetched and written by the GPU directly when
+ * they go through srsue_gpu_batch_submit; anything else is copied subframe by subframe. */
+int srsue_gpu_host_register(void *p, uint64_t bytes);
+int srsue_gpu_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

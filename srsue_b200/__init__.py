@@ -185,21 +185,31 @@ class Batch:
                "srsue_gpu_batch_create")
         self._keep = None
 
-    def submit(self, items):
-        """items: list of dicts {cell, cfg, iq (complex64 array), softbuffer_id (default -1), new_data (default 1)}"""
+    @staticmethod
+    def prepare(items):
+        """items: list of dicts {cell, cfg, iq (complex64 array), softbuffer_id (default -1), new_data (default 1),
+        payload (optional uint8 array)} -> (descriptor array, payload arrays, items), reusable across submissions"""
         import numpy as np
         n = len(items)
         descs = (SfDesc * n)()
         payloads = []
         for d, it in zip(descs, items):
             d.cell, d.cfg = it["cell"], it["cfg"]
-            pl = np.zeros((it["cfg"].tbs + 7) // 8, np.uint8)
+            pl = it.get("payload")
+            if pl is None:
+                pl = np.zeros((it["cfg"].tbs + 7) // 8, np.uint8)
             payloads.append(pl)
             d.iq, d.payload = it["iq"].ctypes.data, pl.ctypes.data
             d.softbuffer_id = it.get("softbuffer_id", -1)
             d.new_data = it.get("new_data", 1)
-        self._keep = (descs, payloads, items)
-        _check(lib().srsue_gpu_batch_submit(self.h, descs, n), "srsue_gpu_batch_submit")
+        return descs, payloads, items
+
+    def submit_prepared(self, prepared):
+        self._keep = prepared
+        _check(lib().srsue_gpu_batch_submit(self.h, prepared[0], len(prepared[0])), "srsue_gpu_batch_submit")
+
+    def submit(self, items):
+        self.submit_prepared(self.prepare(items))
 
     def wait(self):
         _check(lib().srsue_gpu_batch_wait(self.h), "srsue_gpu_batch_wait")

@@ -68,6 +68,21 @@ struct Scratch {
 namespace srsue {
 // error reporting for the other translation units of the library (batch.cu)
 int internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+
+// Pinned host regions the library knows about (srsue_gpu_host_alloc / srsue_gpu_host_register): the batching layer
+// lets the GPU fetch subframes that lie inside them directly (zero-copy) instead of issuing one copy per subframe.
+namespace {
+std::mutex g_regions_mu;
+std::map<uintptr_t, std::pair<size_t, bool>> g_regions;    // base -> (bytes, registered by us with cudaHostRegister)
+}
+bool host_region_contains(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_regions_mu);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  auto it = g_regions.upper_bound(a);
+  if (it == g_regions.begin()) return false;
+  --it;
+  return a >= it->first && a + bytes <= it->first + it->second.first;
+}
 }  // namespace srsue
 
 struct srsue_gpu_ctx {
@@ -785,8 +800,31 @@ int srsue_gpu_host_gold(uint32_t c_init, int n, uint8_t* c) {
 void* srsue_gpu_host_alloc(uint64_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(srsue::g_regions_mu);
+  srsue::g_regions[reinterpret_cast<uintptr_t>(p)] = {(size_t)bytes, false};
   return p;
 }
-void srsue_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+void srsue_gpu_host_free(void* p) {
+  if (!p) return;
+  { std::lock_guard<std::mutex> lk(srsue::g_regions_mu); srsue::g_regions.erase(reinterpret_cast<uintptr_t>(p)); }
+  cudaFreeHost(p);
+}
+int srsue_gpu_host_register(void* p, uint64_t bytes) {
+  if (!p || !bytes) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "host_register: null region");
+  CU_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  std::lock_guard<std::mutex> lk(srsue::g_regions_mu);
+  srsue::g_regions[reinterpret_cast<uintptr_t>(p)] = {(size_t)bytes, true};
+  return 0;
+}
+int srsue_gpu_host_unregister(void* p) {
+  {
+    std::lock_guard<std::mutex> lk(srsue::g_regions_mu);
+    auto it = srsue::g_regions.find(reinterpret_cast<uintptr_t>(p));
+    if (it == srsue::g_regions.end() || !it->second.second) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "host_unregister: unknown region");
+    srsue::g_regions.erase(it);
+  }
+  CU_CHECK(cudaHostUnregister(p));
+  return 0;
+}
 
 }  // extern "C"

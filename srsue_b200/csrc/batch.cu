@@ -21,6 +21,7 @@
 
 namespace srsue {
 int internal_fail(int code, const char* msg);   // api.cu: sets srsue_gpu_last_error()
+bool host_region_contains(const void* p, size_t bytes);   // api.cu: inside a known pinned region?
 }
 
 namespace {
@@ -50,6 +51,26 @@ __global__ void __launch_bounds__(256) softbuffer_rows_kernel(int16_t* packed, i
   else for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = b[i];
 }
 
+// Zero-copy gather of scattered subframes: rows[i] points into pinned host memory (UVA), the GPU pulls each row over
+// PCIe into the packed device array.  gridDim = (rows, slices); VEC = 16 or 8 bytes per access.
+template <typename V>
+__global__ void __launch_bounds__(256) gather_host_rows_kernel(V* __restrict__ packed, const V* const* __restrict__ rows, int row_vecs) {
+  const V* __restrict__ src = rows[blockIdx.x];
+  V* dst = packed + (size_t)blockIdx.x * row_vecs;
+  const int per = (row_vecs + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(row_vecs, lo + per);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+}
+
+// Zero-copy scatter of the payload rows into the callers' pinned buffers.  WORD = 4 when every row and pointer is
+// 4-byte aligned, else 1.
+template <typename W>
+__global__ void __launch_bounds__(128) scatter_host_rows_kernel(const W* __restrict__ packed, W* const* __restrict__ rows, int row_words) {
+  W* dst = rows[blockIdx.x];
+  const W* src = packed + (size_t)blockIdx.x * row_words;
+  for (int i = threadIdx.x; i < row_words; i += blockDim.x) dst[i] = src[i];
+}
+
 struct PlanEntry {
   srsue_gpu_pdsch_plan_t* plan = nullptr;
   srsue_gpu_plan_info_t info{};
@@ -77,6 +98,13 @@ struct srsue_gpu_batch {
   int16_t** d_rows = nullptr;
   // pinned result staging, in processing order
   int32_t* h_status = nullptr; float* h_meas = nullptr; int16_t** h_rows = nullptr;
+  const void** h_iq_rows = nullptr; void** h_pl_rows = nullptr;    // pinned pointer tables read by the zero-copy kernels
+  // pinned staging for scattered host buffers: small IQ rows are gathered by the CPU and uploaded with one copy per
+  // chunk, payload rows come back with one copy per chunk and are scattered in srsue_gpu_batch_wait
+  srsue_gpu_cf_t* h_iq[2] = {nullptr, nullptr}; size_t h_iq_elems[2] = {0, 0};
+  uint8_t* h_pl = nullptr; size_t h_pl_bytes = 0;
+  struct PlChunk { size_t pos0, stage_off, row_bytes; int rows; };
+  std::vector<PlChunk> pl_chunks;
   std::vector<int> order;                 // processing position -> descriptor index
   srsue_gpu_sf_desc_t* pending = nullptr; int n_pending = 0;
   std::map<int64_t, SoftBuffer> softbuffers;
@@ -123,6 +151,19 @@ int get_plan(srsue_gpu_batch* b, const std::string& key, const srsue_gpu_sf_desc
 }
 
 template <typename T>
+int grow_pinned(T** p, size_t* have, size_t want, cudaStream_t s) {
+  if (want <= *have) return 0;
+  if (*p) { B_CU(cudaStreamSynchronize(s)); B_CU(cudaFreeHost(*p)); *p = nullptr; }
+  B_CU(cudaMallocHost((void**)p, want * sizeof(T)));
+  *have = want;
+  return 0;
+}
+
+// IQ rows up to this size are gathered on the host when they are scattered in memory (one cudaMemcpyAsync call
+// costs a few microseconds, about the CPU time to copy 32-64 KB)
+constexpr size_t kGatherRowBytes = 32 * 1024;
+
+template <typename T>
 int grow(T** p, size_t* have, size_t want, cudaStream_t s) {
   if (want <= *have) return 0;
   if (*p) { B_CU(cudaStreamSynchronize(s)); B_CU(cudaFree(*p)); *p = nullptr; }
@@ -156,6 +197,8 @@ int srsue_gpu_batch_create(srsue_gpu_ctx_t* ctx, int max_subframes, float noise_
   B_CU(cudaMallocHost((void**)&b->h_status, (size_t)max_subframes * 4 * sizeof(int32_t)));
   B_CU(cudaMallocHost((void**)&b->h_meas, (size_t)max_subframes * 5 * sizeof(float)));
   B_CU(cudaMallocHost((void**)&b->h_rows, (size_t)max_subframes * sizeof(int16_t*)));
+  B_CU(cudaMallocHost((void**)&b->h_iq_rows, (size_t)max_subframes * sizeof(void*)));
+  B_CU(cudaMallocHost((void**)&b->h_pl_rows, (size_t)max_subframes * sizeof(void*)));
   *out = b;
   return 0;
 }
@@ -169,6 +212,8 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   cudaFree(b->d_iq[0]); cudaFree(b->d_iq[1]); cudaFree(b->d_payload); cudaFree(b->d_status); cudaFree(b->d_meas);
   cudaFree(b->d_sb); cudaFree(b->d_rows);
   cudaFreeHost(b->h_status); cudaFreeHost(b->h_meas); cudaFreeHost(b->h_rows);
+  cudaFreeHost(b->h_iq[0]); cudaFreeHost(b->h_iq[1]); cudaFreeHost(b->h_pl);
+  cudaFreeHost(b->h_iq_rows); cudaFreeHost(b->h_pl_rows);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(b->ev_up[i]); cudaEventDestroy(b->ev_free[i]); }
   cudaStreamDestroy(b->s_compute); cudaStreamDestroy(b->s_copy);
   delete b;
@@ -179,6 +224,10 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
   if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
   b->launches = 0;
   b->order.clear();
+  b->pl_chunks.clear();
+  size_t pl_total = 0, pl_off = 0;
+  for (int i = 0; i < n; i++) pl_total += (size_t)(descs[i].cfg.tbs + 7) / 8;
+  { int rc = grow_pinned(&b->h_pl, &b->h_pl_bytes, pl_total, b->s_compute); if (rc) return rc; }
   // ---- bucket the descriptors by launch shape, keeping arrival order inside a bucket -----------------------
   std::map<std::string, std::vector<int>> groups;
   std::vector<std::string> group_order;
@@ -218,14 +267,46 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
       const int m = (int)std::min(cap, idx.size() - off);
       const int h = b->half;
       b->half ^= 1;
-      // upload: merge subframes that are adjacent in host memory into one copy
-      B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
-      for (int r = 0; r < m;) {
-        int e = r + 1;
-        while (e < m && descs[idx[off + e]].iq == descs[idx[off + e - 1]].iq + info.sf_len) e++;
-        B_CU(cudaMemcpyAsync(b->d_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq,
-                             (size_t)(e - r) * info.sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, b->s_copy));
-        r = e;
+      // upload: subframes that are adjacent in host memory go up in one copy; scattered small ones are gathered
+      // into pinned staging first
+      int runs = 1;
+      for (int r = 1; r < m; r++) runs += descs[idx[off + r]].iq != descs[idx[off + r - 1]].iq + info.sf_len;
+      const size_t row_bytes = (size_t)info.sf_len * sizeof(srsue_gpu_cf_t);
+      const size_t pos_up = b->order.size();
+      bool zero_copy = runs > 4;
+      uintptr_t align_or = 0;
+      for (int r = 0; r < m && zero_copy; r++) {
+        zero_copy = srsue::host_region_contains(descs[idx[off + r]].iq, row_bytes);
+        align_or |= reinterpret_cast<uintptr_t>(descs[idx[off + r]].iq);
+      }
+      if (zero_copy) {
+        for (int r = 0; r < m; r++) b->h_iq_rows[pos_up + r] = descs[idx[off + r]].iq;
+        B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
+        const int slices = (int)std::max<size_t>(1, row_bytes / (32 * 1024));
+        if ((align_or & 15) == 0)
+          gather_host_rows_kernel<uint4><<<dim3(m, slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint4*>(b->d_iq[h]),
+              reinterpret_cast<const uint4* const*>(b->h_iq_rows + pos_up), (int)(row_bytes / 16));
+        else
+          gather_host_rows_kernel<uint2><<<dim3(m, slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint2*>(b->d_iq[h]),
+              reinterpret_cast<const uint2* const*>(b->h_iq_rows + pos_up), (int)(row_bytes / 8));
+        B_CU(cudaGetLastError());
+        b->launches++;
+      } else if (runs > 4 && row_bytes <= kGatherRowBytes) {
+        B_CU(cudaEventSynchronize(b->ev_up[h]));            // the previous upload from this staging half has finished
+        rc = grow_pinned(&b->h_iq[h], &b->h_iq_elems[h], cap * info.sf_len, b->s_copy);
+        if (rc) return rc;
+        for (int r = 0; r < m; r++) std::memcpy(b->h_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq, row_bytes);
+        B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
+        B_CU(cudaMemcpyAsync(b->d_iq[h], b->h_iq[h], (size_t)m * row_bytes, cudaMemcpyHostToDevice, b->s_copy));
+      } else {
+        B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
+        for (int r = 0; r < m;) {
+          int e = r + 1;
+          while (e < m && descs[idx[off + e]].iq == descs[idx[off + e - 1]].iq + info.sf_len) e++;
+          B_CU(cudaMemcpyAsync(b->d_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq, (size_t)(e - r) * row_bytes,
+                               cudaMemcpyHostToDevice, b->s_copy));
+          r = e;
+        }
       }
       B_CU(cudaEventRecord(b->ev_up[h], b->s_copy));
       B_CU(cudaStreamWaitEvent(b->s_compute, b->ev_up[h], 0));
@@ -263,12 +344,35 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
       if (mode) { softbuffer_rows_kernel<<<m, 256, 0, b->s_compute>>>(d_sb, b->d_rows, info.sb_sf_stride, 1); b->launches++; }
       // results: payload rows to the callers' buffers (adjacent buffers merged), status and measurements to staging
       const size_t pbytes = (size_t)(info.payload_stride);
-      for (int r = 0; r < m;) {
-        int e = r + 1;
-        while (e < m && descs[idx[off + e]].payload == descs[idx[off + e - 1]].payload + pbytes) e++;
-        B_CU(cudaMemcpyAsync(descs[idx[off + r]].payload, b->d_payload + (size_t)r * pbytes, (size_t)(e - r) * pbytes,
-                             cudaMemcpyDeviceToHost, b->s_compute));
-        r = e;
+      int pruns = 1;
+      for (int r = 1; r < m; r++) pruns += descs[idx[off + r]].payload != descs[idx[off + r - 1]].payload + pbytes;
+      bool pl_zero_copy = pruns > 4;
+      uintptr_t pl_align = pbytes;
+      for (int r = 0; r < m && pl_zero_copy; r++) {
+        pl_zero_copy = srsue::host_region_contains(descs[idx[off + r]].payload, pbytes);
+        pl_align |= reinterpret_cast<uintptr_t>(descs[idx[off + r]].payload);
+      }
+      if (pl_zero_copy) {
+        for (int r = 0; r < m; r++) b->h_pl_rows[pos0 + r] = descs[idx[off + r]].payload;
+        if ((pl_align & 3) == 0)
+          scatter_host_rows_kernel<uint32_t><<<m, 128, 0, b->s_compute>>>(reinterpret_cast<const uint32_t*>(b->d_payload),
+              reinterpret_cast<uint32_t* const*>(b->h_pl_rows + pos0), (int)(pbytes / 4));
+        else
+          scatter_host_rows_kernel<uint8_t><<<m, 128, 0, b->s_compute>>>(b->d_payload, reinterpret_cast<uint8_t* const*>(b->h_pl_rows + pos0), (int)pbytes);
+        B_CU(cudaGetLastError());
+        b->launches++;
+      } else if (pruns > 4) {
+        B_CU(cudaMemcpyAsync(b->h_pl + pl_off, b->d_payload, (size_t)m * pbytes, cudaMemcpyDeviceToHost, b->s_compute));
+        b->pl_chunks.push_back({pos0, pl_off, pbytes, m});
+        pl_off += (size_t)m * pbytes;
+      } else {
+        for (int r = 0; r < m;) {
+          int e = r + 1;
+          while (e < m && descs[idx[off + e]].payload == descs[idx[off + e - 1]].payload + pbytes) e++;
+          B_CU(cudaMemcpyAsync(descs[idx[off + r]].payload, b->d_payload + (size_t)r * pbytes, (size_t)(e - r) * pbytes,
+                               cudaMemcpyDeviceToHost, b->s_compute));
+          r = e;
+        }
       }
       B_CU(cudaMemcpyAsync(b->h_status + pos0 * 4, b->d_status, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->s_compute));
       B_CU(cudaMemcpyAsync(b->h_meas + pos0 * 5, b->d_meas, (size_t)m * 5 * sizeof(float), cudaMemcpyDeviceToHost, b->s_compute));
@@ -284,6 +388,9 @@ int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
   if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_wait: null batch");
   if (!b->pending) return 0;
   B_CU(cudaStreamSynchronize(b->s_compute));
+  for (const auto& c : b->pl_chunks)
+    for (int r = 0; r < c.rows; r++)
+      std::memcpy(b->pending[b->order[c.pos0 + r]].payload, b->h_pl + c.stage_off + (size_t)r * c.row_bytes, c.row_bytes);
   for (size_t pos = 0; pos < b->order.size(); pos++) {
     srsue_gpu_sf_desc_t& d = b->pending[b->order[pos]];
     d.crc_ok = b->h_status[pos * 4 + 0];

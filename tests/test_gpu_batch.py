@@ -135,3 +135,49 @@ def test_batch_argument_errors(gpu, oracle):
     b.submit([dict(cell=cell, cfg=cfg, iq=iq)])
     assert b.wait()[0]["crc_ok"] == 1
     b.close()
+
+
+@pytest.mark.parametrize("how", ["host_alloc", "host_register"])
+def test_zero_copy_pinned_rows(gpu, oracle, how):
+    """scattered subframes inside pinned regions known to the library are fetched / written by the GPU directly
+    (gather / scatter kernels over UVA); results must not depend on the transfer path"""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    L.srsue_gpu_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.srsue_gpu_host_unregister.argtypes = [C.c_void_p]
+    n = 12
+    for row in (MIX[0], MIX[2]):           # 19-byte payloads (byte path) and 1431-byte payloads
+        ocell, ocfg, cell, cfg = _pair(sg, o, row)
+        gen = [o.gen_subframe(ocell, ocfg, 81000 + i, row[7]) for i in range(n)]
+        sf_len, pb = len(gen[0][1]), (row[3] + 7) // 8
+        pbp = (pb + 3) // 4 * 4 if row is MIX[2] else pb
+        if how == "host_alloc":
+            p, q = L.srsue_gpu_host_alloc(n * sf_len * 8), L.srsue_gpu_host_alloc(n * pbp)
+            h_iq = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, sf_len * 2)).view(np.complex64)
+            h_pl = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint8)), shape=(n, pbp))
+        else:
+            h_iq = np.zeros((n, sf_len), np.complex64)
+            h_pl = np.zeros((n, pbp), np.uint8)
+            assert L.srsue_gpu_host_register(h_iq.ctypes.data, h_iq.nbytes) == 0
+            assert L.srsue_gpu_host_register(h_pl.ctypes.data, h_pl.nbytes) == 0
+        h_pl[:] = 0xEE
+        for i in range(n):
+            h_iq[i] = gen[i][1]
+        rev = list(range(n))[::-1]          # no two consecutive descriptors are adjacent in memory
+        items = [dict(cell=cell, cfg=cfg, iq=h_iq[i], payload=h_pl[i, :pb]) for i in rev]
+        b = sg.Batch(ctx, n)
+        b.submit(items)
+        res = b.wait()
+        assert b.stats()["launches"] >= 7    # chain + gather + scatter
+        for i, r in zip(rev, res):
+            assert r["crc_ok"] == 1 and np.array_equal(h_pl[i, :pb], gen[i][0])
+            assert (h_pl[i, pb:] == 0xEE).all()
+        b.close()
+        if how == "host_alloc":
+            L.srsue_gpu_host_free(p)
+            L.srsue_gpu_host_free(q)
+        else:
+            assert L.srsue_gpu_host_unregister(h_iq.ctypes.data) == 0
+            assert L.srsue_gpu_host_unregister(h_pl.ctypes.data) == 0
