@@ -15,17 +15,81 @@
 #include <string.h>
 #include "lte_oracle.h"
 
+/* Small process-wide caches of derived tables (scrambling sequences, rate-matching orders, QPP permutations): a
+ * receiver computes them once per configuration, not once per subframe (srsLTE precomputes its sequences in
+ * srslte_pdsch_set_rnti and its interleavers at init).  Entries are immutable once published and never freed. */
+#include <pthread.h>
+#define CACHE_N 32
+typedef struct { uint32_t a, b, c, d; int n; void *p; } cache_ent_t;
+static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+static void *cache_get(cache_ent_t *tab, int *cnt, uint32_t a, uint32_t b, uint32_t c, uint32_t d, int *n) {
+  void *p = 0;
+  pthread_mutex_lock(&g_cache_mu);
+  for (int i = 0; i < *cnt; i++)
+    if (tab[i].a == a && tab[i].b == b && tab[i].c == c && tab[i].d == d) { p = tab[i].p; if (n) *n = tab[i].n; break; }
+  pthread_mutex_unlock(&g_cache_mu);
+  return p;
+}
+/* returns the pointer to use: the published one (p is freed when another thread won the race or the table is full
+ * and keep_if_full is 0; when full the caller owns p and *owned is set) */
+static void *cache_put(cache_ent_t *tab, int *cnt, uint32_t a, uint32_t b, uint32_t c, uint32_t d, int n, void *p, int *owned) {
+  *owned = 0;
+  pthread_mutex_lock(&g_cache_mu);
+  for (int i = 0; i < *cnt; i++)
+    if (tab[i].a == a && tab[i].b == b && tab[i].c == c && tab[i].d == d) {
+      void *q = tab[i].p;
+      pthread_mutex_unlock(&g_cache_mu);
+      free(p);
+      return q;
+    }
+  if (*cnt < CACHE_N) {
+    cache_ent_t e = {a, b, c, d, n, p};
+    tab[(*cnt)++] = e;
+  } else {
+    *owned = 1;
+  }
+  pthread_mutex_unlock(&g_cache_mu);
+  return p;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * OFDM demodulation (SPEC.md 2)
  * ---------------------------------------------------------------------------------------------- */
-static void fft_pow2(const lteo_cf_t *in, lteo_cf_t *out, int n, int in_stride, const lteo_cf_t *tw, int ntw) {
-  int bits = 0;
-  while ((1 << bits) < n) bits++;
-  for (int i = 0; i < n; i++) {
-    int r = 0;
-    for (int b = 0; b < bits; b++) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
-    out[r] = in[(size_t)i * in_stride];
+static cache_ent_t g_tw_cache[CACHE_N], g_rev_cache[CACHE_N];
+static int g_tw_cnt = 0, g_rev_cnt = 0;
+
+/* twiddle table of lteo_fft_twiddles(n) and the bit-reversal permutation, computed once per size */
+static const lteo_cf_t *cached_twiddles(int n, int *owned) {
+  lteo_cf_t *tw = (lteo_cf_t *)cache_get(g_tw_cache, &g_tw_cnt, (uint32_t)n, 0, 0, 0, 0);
+  *owned = 0;
+  if (!tw) {
+    tw = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * (n / 2 + 1));
+    lteo_fft_twiddles(n, tw);
+    tw = (lteo_cf_t *)cache_put(g_tw_cache, &g_tw_cnt, (uint32_t)n, 0, 0, 0, n, tw, owned);
   }
+  return tw;
+}
+static const uint16_t *cached_bitrev(int n, int *owned) {
+  uint16_t *rv = (uint16_t *)cache_get(g_rev_cache, &g_rev_cnt, (uint32_t)n, 0, 0, 0, 0);
+  *owned = 0;
+  if (!rv) {
+    int bits = 0;
+    while ((1 << bits) < n) bits++;
+    rv = (uint16_t *)malloc(sizeof(uint16_t) * n);
+    for (int i = 0; i < n; i++) {
+      int r = 0;
+      for (int b = 0; b < bits; b++) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+      rv[i] = (uint16_t)r;
+    }
+    rv = (uint16_t *)cache_put(g_rev_cache, &g_rev_cnt, (uint32_t)n, 0, 0, 0, n, rv, owned);
+  }
+  return rv;
+}
+static void fft_pow2(const lteo_cf_t *in, lteo_cf_t *out, int n, int in_stride, const lteo_cf_t *tw, int ntw) {
+  int rv_owned = 0;
+  const uint16_t *rv = cached_bitrev(n, &rv_owned);
+  for (int i = 0; i < n; i++) out[rv[i]] = in[(size_t)i * in_stride];
+  if (rv_owned) free((void *)rv);
   for (int m = 2; m <= n; m <<= 1) {
     int half = m / 2, step = ntw / m;
     for (int g = 0; g < n; g += m)
@@ -41,17 +105,16 @@ static void fft_pow2(const lteo_cf_t *in, lteo_cf_t *out, int n, int in_stride, 
 
 /* forward DFT, n = 2^a or 3 * 2^a (1536): radix-2 DIT butterflies, one final radix-3 DIT stage */
 void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n) {
+  int tw_owned = 0;
   if (n % 3 != 0) {
-    lteo_cf_t *tw = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * (n / 2 + 1));
-    lteo_fft_twiddles(n, tw);
+    const lteo_cf_t *tw = cached_twiddles(n, &tw_owned);
     fft_pow2(in, out, n, 1, tw, n);
-    free(tw);
+    if (tw_owned) free((void *)tw);
     return;
   }
   int m = n / 3;
-  lteo_cf_t *tw = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * (m / 2 + 1));
+  const lteo_cf_t *tw = cached_twiddles(m, &tw_owned);
   lteo_cf_t *f = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * n);
-  lteo_fft_twiddles(m, tw);
   for (int r = 0; r < 3; r++) fft_pow2(in + r, f + r * m, m, 3, tw, m);
   const float c3 = (float)(sqrt(3.0) / 2.0);
   for (int k = 0; k < m; k++) {
@@ -68,7 +131,8 @@ void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n) {
     out[m + k].re = mm.re + c3 * d.im;     out[m + k].im = mm.im - c3 * d.re;
     out[2 * m + k].re = mm.re - c3 * d.im; out[2 * m + k].im = mm.im + c3 * d.re;
   }
-  free(tw); free(f);
+  if (tw_owned) free((void *)tw);
+  free(f);
 }
 
 void lteo_ofdm_rx(int nof_prb, const lteo_cf_t *iq, lteo_cf_t *sf_symbols) {
@@ -255,11 +319,20 @@ void lteo_demod(const lteo_cf_t *d, int nof_re, int qm, int16_t *llr) {
   }
 }
 
+static cache_ent_t g_gold_cache[CACHE_N];
+static int g_gold_cnt = 0;
+
 void lteo_descramble(int16_t *llr, int n, uint32_t c_init) {
-  uint8_t *c = (uint8_t *)malloc(n);
-  lteo_gold(c_init, n, c);
-  for (int i = 0; i < n; i++) if (c[i]) llr[i] = (int16_t)-llr[i];
-  free(c);
+  int owned = 0;
+  uint8_t *c = (uint8_t *)cache_get(g_gold_cache, &g_gold_cnt, c_init, (uint32_t)n, 0, 0, 0);
+  if (!c) {
+    c = (uint8_t *)malloc(n > 0 ? n : 1);
+    lteo_gold(c_init, n, c);
+    c = (uint8_t *)cache_put(g_gold_cache, &g_gold_cnt, c_init, (uint32_t)n, 0, 0, n, c, &owned);
+  }
+  /* branch-free two's-complement negation where c[i] == 1 (the sequence is random: a branch mispredicts half the time) */
+  for (int i = 0; i < n; i++) llr[i] = (int16_t)((llr[i] ^ -(int16_t)c[i]) + c[i]);
+  if (owned) free(c);
 }
 
 static inline int16_t sat_add(int a, int b) {
@@ -271,12 +344,23 @@ static inline int16_t sat_add(int a, int b) {
 
 /* accumulates E received LLRs into the soft buffer w (3K+12 triples), ascending e order; filler
  * positions of d0/d1 are forced to LTEO_FILLER_LLR */
+static cache_ent_t g_rm_cache[CACHE_N];
+static int g_rm_cnt = 0;
+
 void lteo_rm_rx(const int16_t *e, int E, int K, int F, int rv, int16_t *w) {
-  int32_t *seq = (int32_t *)malloc(sizeof(int32_t) * 3 * (K + 4));
-  int n = lteo_rm_sequence(K, F, rv, seq);
-  for (int i = 0; i < E; i++) w[seq[i % n]] = sat_add(w[seq[i % n]], e[i]);
+  int n = 0, owned = 0;
+  int32_t *seq = (int32_t *)cache_get(g_rm_cache, &g_rm_cnt, (uint32_t)K, (uint32_t)F, (uint32_t)rv, 0, &n);
+  if (!seq) {
+    seq = (int32_t *)malloc(sizeof(int32_t) * 3 * (K + 4));
+    n = lteo_rm_sequence(K, F, rv, seq);
+    seq = (int32_t *)cache_put(g_rm_cache, &g_rm_cnt, (uint32_t)K, (uint32_t)F, (uint32_t)rv, 0, n, seq, &owned);
+  }
+  for (int i = 0, j = 0; i < E; i++) {
+    w[seq[j]] = sat_add(w[seq[j]], e[i]);
+    if (++j == n) j = 0;
+  }
   for (int k = 0; k < F; k++) { w[3 * k] = LTEO_FILLER_LLR; w[3 * k + 1] = LTEO_FILLER_LLR; }
-  free(seq);
+  if (owned) free(seq);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -410,12 +494,25 @@ static void map_pass(map_state_t *m, int it, const int16_t *x, const int16_t *y,
   free(beta);
 }
 
+static cache_ent_t g_qpp_cache[CACHE_N];
+static int g_qpp_cnt = 0;
+static const uint16_t *cached_qpp(int K, int *owned) {
+  uint16_t *pi = (uint16_t *)cache_get(g_qpp_cache, &g_qpp_cnt, (uint32_t)K, 0, 0, 0, 0);
+  *owned = 0;
+  if (!pi) {
+    pi = (uint16_t *)malloc(sizeof(uint16_t) * K);
+    lteo_qpp_perm(K, pi);
+    pi = (uint16_t *)cache_put(g_qpp_cache, &g_qpp_cnt, (uint32_t)K, 0, 0, 0, K, pi, owned);
+  }
+  return pi;
+}
+
 int lteo_tdec_dbg(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok,
                   int16_t *la_out, int window_override) {
   trellis_init();
   int W = window_override > 0 ? window_override : lteo_window_len(K);
-  uint16_t *pi = (uint16_t *)malloc(sizeof(uint16_t) * K);
-  lteo_qpp_perm(K, pi);
+  int pi_owned = 0;
+  const uint16_t *pi = cached_qpp(K, &pi_owned);
   int16_t *sys = (int16_t *)malloc(sizeof(int16_t) * K * 8);
   int16_t *p1 = sys + K, *p2 = p1 + K, *la = p2 + K, *x = la + K, *ext = x + K, *A = ext + K;
   int16_t xt1[3], yt1[3], xt2[3], yt2[3];
@@ -451,11 +548,22 @@ int lteo_tdec_dbg(const int16_t *in, int K, int max_iter, int crc_type, uint8_t 
   if (crc_ok) *crc_ok = ok;
   if (la_out) memcpy(la_out, la, sizeof(int16_t) * K);
   map_state_free(&m1); map_state_free(&m2);
-  free(pi); free(sys);
+  if (pi_owned) free((void *)pi);
+  free(sys);
   return it;
 }
 
+#ifdef LTEO_SIMD
+#include "lteo_simd.inc"
+int lteo_simd_build(void) { return 1; }
+#else
+int lteo_simd_build(void) { return 0; }
+#endif
+
 int lteo_tdec(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok) {
+#ifdef LTEO_SIMD
+  return lteo_tdec_avx2(in, K, max_iter, crc_type, bits, crc_ok);
+#endif
   return lteo_tdec_dbg(in, K, max_iter, crc_type, bits, crc_ok, 0, 0);
 }
 

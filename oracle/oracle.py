@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblteoracle.so")
+_SO_AVX2 = os.path.join(_HERE, "_build", "liblteoracle_avx2.so")   # same sources, -O3 -mavx2 + window-parallel turbo
 
 MAX_K = 6144
 SB_STRIDE = 3 * MAX_K + 12
@@ -19,9 +20,9 @@ TD_C, TD_E, TD_INF = 511, 2047, 10000
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
-    if (not force and os.path.exists(_SO)
-            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".inc"))]
+    if (not force and os.path.exists(_SO) and os.path.exists(_SO_AVX2)
+            and all(min(os.path.getmtime(_SO), os.path.getmtime(_SO_AVX2)) >= os.path.getmtime(s) for s in srcs)):
         return _SO
     subprocess.check_call(["make", "-B", "-C", _HERE], stdout=subprocess.DEVNULL)
     return _SO
@@ -41,20 +42,41 @@ class CbSegm(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("tbs", "B", "C", "Kp", "Km", "Cp", "Cm", "F")]
 
 
-_lib = None
+_libs = {}
+_kind = "portable"
+
+
+def have_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " avx2 " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def select(kind):
+    """choose the build every function of this module calls: "portable" (-O2 scalar C, the checker) or "avx2"
+    (bit-identical, vectorised; the CPU baseline bench.py times).  Returns the previous choice."""
+    global _kind
+    assert kind in ("portable", "avx2")
+    if kind == "avx2" and not have_avx2():
+        raise RuntimeError("this host has no AVX2")
+    prev, _kind = _kind, kind
+    return prev
 
 
 def lib():
-    global _lib
-    if _lib is None:
+    if _kind not in _libs:
+        so = _SO if _kind == "portable" else _SO_AVX2
         build()
         try:
-            _lib = C.CDLL(_SO)
+            L = C.CDLL(so)
         except OSError:
             build(force=True)
-            _lib = C.CDLL(_SO)
-        _lib.lteo_crc_bits.restype = C.c_uint32
-    return _lib
+            L = C.CDLL(so)
+        L.lteo_crc_bits.restype = C.c_uint32
+        _libs[_kind] = L
+    return _libs[_kind]
 
 
 def _p(a, t=C.c_void_p):

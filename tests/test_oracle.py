@@ -164,3 +164,36 @@ def test_harq_combining_improves(oracle):
         rc, pl = oracle.pdsch_decode(cell, cfg, sf, ce, 0.01, 4, softbuf=sb)
         res.append((rc, np.array_equal(pl, tb)))
     assert res[0][0] != 0 and res[1] == (0, True)
+
+
+def test_avx2_build_is_bit_identical_to_portable():
+    """bench.py times oracle/_build/liblteoracle_avx2.so (window-parallel AVX2 turbo decoder, -O3) as the CPU baseline;
+    it must reproduce the portable checker bit for bit: turbo hard bits and iteration counts over code-block sizes
+    with 1..96 windows, and the whole chain on the three PDSCH configs."""
+    import numpy as np
+    from oracle import oracle as o
+    if not o.have_avx2():
+        pytest.skip("host without AVX2")
+    prev = o.select("portable")
+    try:
+        for K in (40, 104, 176, 512, 1056, 2048, 3136, 5824, 6144):
+            for seed, eb in ((1, 0.5), (2, 1.5), (3, None)):
+                llr = o.gen_turbo_llrs(K, seed, ebn0_db=eb)[1]
+                for crc in (0, 1):
+                    o.select("portable")
+                    a = o.tdec_mt(llr[None], K, 1, 5, crc)
+                    o.select("avx2")
+                    assert o.lib().lteo_simd_build() == 1
+                    b = o.tdec_mt(llr[None], K, 1, 5, crc)
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (K, seed, crc)
+        for prb, ports, qm, tbs, tm, snr in ((6, 1, 2, 152, 1, 10.0), (100, 1, 6, 75376, 1, 21.0), (100, 2, 4, 30576, 2, 15.0)):
+            o.select("portable")
+            cell = o.make_cell(prb, ports, 1)
+            cfg = o.make_cfg(cell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=tm)
+            iq = o.gen_subframe(cell, cfg, 7, snr)[1]
+            a = o.ue_dl_decode(cell, cfg, iq, 0.01, 1, 4)
+            o.select("avx2")
+            b = o.ue_dl_decode(cell, cfg, iq, 0.01, 1, 4)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    finally:
+        o.select(prev)
