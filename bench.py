@@ -27,6 +27,13 @@ WORKLOAD = dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, cfi=1, sf_idx=1, rnti=0
 METRIC = "pdsch_decoded_mbit_per_s_20mhz_mcs28_tm1"
 
 
+def channel_taps():
+    """fixed frequency-selective channel of BASELINE configs[2]: 6 sample-spaced taps per TX port, seed 77"""
+    rng = np.random.default_rng(77)
+    taps = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    return taps / np.sqrt((abs(taps) ** 2).sum(1, keepdims=True))
+
+
 def gen_pool(o, pool, snr_db, seed0):
     ocell = o.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"])
     ocfg = o.make_cfg(ocell, sf_idx=WORKLOAD["sf_idx"], cfi=WORKLOAD["cfi"], rnti=WORKLOAD["rnti"], qm=WORKLOAD["qm"],
@@ -34,7 +41,7 @@ def gen_pool(o, pool, snr_db, seed0):
     tbs, iqs = [], []
     for i in range(pool):
         # payload seed = 10000*cfg + unit index, noise seed = payload seed + 5e6 (inside gen_subframe)
-        tb, iq, _ = o.gen_subframe(ocell, ocfg, 20000 + seed0 + i, snr_db)
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 20000 + seed0 + i, snr_db, channel_taps() if WORKLOAD["tm"] == 2 else None)
         tbs.append(tb)
         iqs.append(iq)
     return ocell, ocfg, np.stack(tbs), np.stack(iqs)
@@ -90,11 +97,11 @@ def run_reference(args, rank, world):
     idx = np.arange(per_step) % len(iqs)
     iq = iqs[idx]
     for _ in range(args.warmup):
-        o.ue_dl_decode_mt(ocell, ocfg, iq[:cores], cores, 0.01, 0, args.max_iter)
+        o.ue_dl_decode_mt(ocell, ocfg, iq[:cores], cores, 0.01, args.noise_mode, args.max_iter)
     t0 = time.perf_counter()
     ok_bits = 0
     for _ in range(args.steps):
-        ok, payload, status = o.ue_dl_decode_mt(ocell, ocfg, iq, cores, 0.01, 0, args.max_iter)
+        ok, payload, status = o.ue_dl_decode_mt(ocell, ocfg, iq, cores, 0.01, args.noise_mode, args.max_iter)
         ok_bits += ok * WORKLOAD["tbs"]
     dt = time.perf_counter() - t0
     val = ok_bits / dt / 1e6
@@ -104,7 +111,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB" % args.snr, "subframes_per_step": per_step,
+        "config": {"workload": args.label, "subframes_per_step": per_step,
                    "max_iter": args.max_iter},
         "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -262,10 +269,21 @@ def main():
     ap.add_argument("--snr", type=float, default=30.0)
     ap.add_argument("--max-iter", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="mcs28", choices=["mcs28", "mixed"],
-                    help="mcs28: BASELINE configs[1] (the headline metric); mixed: configs[4], heterogeneous stream through the batching layer")
+    ap.add_argument("--workload", default="mcs28", choices=["mcs28", "tm2", "mixed"],
+                    help="mcs28: BASELINE configs[1] (the headline metric); tm2: configs[2] (2-port transmit diversity, MCS 16, "
+                         "frequency-selective channel, MMSE with the estimated noise); mixed: configs[4], heterogeneous stream "
+                         "through the batching layer")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global METRIC
+    if args.workload == "tm2":
+        WORKLOAD.update(ports=2, qm=4, tbs=30576, tm=2)
+        METRIC = "pdsch_decoded_mbit_per_s_20mhz_mcs16_tm2"
+        if args.snr == 30.0:
+            args.snr = 15.0
+    args.noise_mode = 1 if WORKLOAD["tm"] == 2 else 0
+    args.label = ("20MHz 100PRB TM2 2-port 16QAM MCS16 TBS30576, 6-tap channel + AWGN %gdB (BASELINE configs[2])" if WORKLOAD["tm"] == 2
+                  else "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB (BASELINE configs[1])") % args.snr
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -321,7 +339,7 @@ def main():
         plan.chest(B, d_sf, d_ce, d_meas)
         if ev:
             ev[2].record()
-        plan.pdsch_llr(B, d_sf, d_ce, d_meas, 0.01, 0, 0, d_sb)        # srsUE passes noise_estimate = 0.01
+        plan.pdsch_llr(B, d_sf, d_ce, d_meas, 0.01, args.noise_mode, 0, d_sb)        # srsUE passes noise_estimate = 0.01
         if ev:
             ev[3].record()
         plan.pdsch_turbo(B, d_sb, args.max_iter, d_pl, d_st)
@@ -370,12 +388,12 @@ def main():
     h_st = np.zeros((EB, 4), np.int32)
     eplan = sg.PdschPlan(ctx, cell, cfg, EB)
     for _ in range(2):
-        eplan.decode_batch_host(EB, h_iq, 0.01, 0, args.max_iter, h_pl, h_st)
+        eplan.decode_batch_host(EB, h_iq, 0.01, args.noise_mode, args.max_iter, h_pl, h_st)
     barrier()
     t0 = time.perf_counter()
     e2e_bits = 0
     for _ in range(args.steps):
-        eplan.decode_batch_host(EB, h_iq, 0.01, 0, args.max_iter, h_pl, h_st)
+        eplan.decode_batch_host(EB, h_iq, 0.01, args.noise_mode, args.max_iter, h_pl, h_st)
         e2e_bits += int((h_st[:, 0] == 1).sum()) * WORKLOAD["tbs"]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -412,7 +430,11 @@ def main():
         # algorithmic bytes per subframe: FFT 245 760 in + 134 400 out; channel estimate 134 400 in +
         # 134 400 out; K3+K4 fused: PDSCH REs 120 000 + estimates 120 000 in, soft buffer 454 584 out; turbo: soft
         # buffer in + transport block out
-        alg_bytes = {"ofdm_fft": 380160, "chest": 268800, "equalise_demap_dematch": 694584, "turbo_crc_tb": 464058}
+        np_ = WORKLOAD["ports"]
+        alg_bytes = {"ofdm_fft": I.sf_len * 8 + 14 * I.nsc * 8, "chest": 14 * I.nsc * 8 * (1 + np_),
+                     "equalise_demap_dematch": I.nof_re * 8 * (1 + np_) + I.C * (3 * I.Kp + 12) * 2,
+                     "turbo_crc_tb": I.C * (3 * I.Kp + 12) * 2 + I.payload_stride + 4 * I.C}
+        # cfg2: 380 160 / 268 800 / 694 584 / 464 058 bytes per subframe, the figures of SURVEY 8d
         stages = []
         for i, n in enumerate(names):
             gbs = alg_bytes[n] * B / (stage_ms[i] * 1e-3) / 1e9
@@ -422,7 +444,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB (BASELINE configs[1])" % args.snr,
+            "config": {"workload": args.label,
                        "subframes_per_step_per_gpu": B, "distinct_subframes": args.pool, "max_iter": args.max_iter,
                        "early_stop": "CRC24B per code block", "avg_turbo_iterations": avg_iter,
                        "l2_policy": "inputs larger than L2 (%.0f MB of IQ per step)" % (B * I.sf_len * 8 / 1e6),
@@ -444,9 +466,9 @@ def main():
             build_kind, restore = cpu_arm(o)
             n = max(cores * 64, 256)
             sub = iqs[np.arange(n) % args.pool]
-            o.ue_dl_decode_mt(ocell, ocfg, sub[:cores], cores, 0.01, 0, args.max_iter)      # warm the table caches
+            o.ue_dl_decode_mt(ocell, ocfg, sub[:cores], cores, 0.01, args.noise_mode, args.max_iter)      # warm the table caches
             t0 = time.perf_counter()
-            ok, cpl, _ = o.ue_dl_decode_mt(ocell, ocfg, sub, cores, 0.01, 0, args.max_iter)
+            ok, cpl, _ = o.ue_dl_decode_mt(ocell, ocfg, sub, cores, 0.01, args.noise_mode, args.max_iter)
             dt = time.perf_counter() - t0
             restore()
             same = bool(np.array_equal(cpl[:args.pool], tbs[:args.pool]))
