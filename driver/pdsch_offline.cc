@@ -62,7 +62,7 @@ int run_worker(const Header& h, cf_t* iq, FILE* out) {
   if (srslte_ue_dl_init(&ue_dl, cell)) { fprintf(stderr, "Initiating UE DL: %s\n", srsue_gpu_last_error()); return 1; }
   srslte_ue_dl_set_rnti(&ue_dl, (uint16_t)h.rnti);
   if (h.max_iter > 0) srslte_sch_set_max_noi(&ue_dl.pdsch.dl_sch, h.max_iter);     // phch_worker.cc:87-89
-  srsue_gpu_ue_dl_set_cfi(&ue_dl, h.cfi);                                          // until PCFICH runs on the device
+  srsue_gpu_ue_dl_set_cfi(&ue_dl, h.cfi);                                          // 0: decode the PCFICH; 1..3: capture without one
   mac_stub mac;
   if (!mac.init(h.nof_prb, h.tbs)) return 1;
   srslte_ra_dl_grant_t grant;

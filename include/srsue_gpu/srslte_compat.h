@@ -191,8 +191,11 @@ SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *ou
                                    uint32_t long_cb);
 
 /* ---- extensions (not in srsLTE) ------------------------------------------------------------------- */
-/* CFI / grant sources until PCFICH + PDCCH decode land on the device */
+/* srslte_ue_dl_decode_fft_estimate decodes the PCFICH on the device and returns its CFI; set_cfi(1..3) forces a
+ * value instead (captures without a control region), set_cfi(0) returns to decoding.  The grant still comes from
+ * the caller until PDCCH blind decoding lands on the device. */
 SRSLTE_API void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t *q, uint32_t cfi);
+/* cfi 0: use the CFI decoded from the PCFICH of each subframe */
 SRSLTE_API int srsue_gpu_ue_dl_set_grant(srslte_ue_dl_t *q, const srslte_ra_dl_grant_t *grant, uint32_t cfi, uint32_t rvidx);
 /* copy the device-resident soft buffer into buffer_f (srsLTE decoder-input order) for `tbs` bits */
 SRSLTE_API int srsue_gpu_softbuffer_rx_sync_host(srslte_softbuffer_rx_t *q, uint32_t tbs);

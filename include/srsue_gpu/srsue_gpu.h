@@ -101,6 +101,12 @@ int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
 int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
                     float *d_meas, void *stream);
+/* PCFICH: the control format indicator srslte_ue_dl_decode_fft_estimate returns through *cfi (phch_worker.cc:254).
+ * d_cfi [n_sf] = 1..3 (largest correlation, lowest CFI on ties); d_corr optional [n_sf][3] integer correlations of the
+ * 32 descrambled int16 LLRs with the three code words.  Uses the plan's cell and sf_idx only. */
+int srsue_gpu_pcfich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                            const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode,
+                            int32_t *d_cfi, int32_t *d_corr, void *stream);
 /* equalise + demap + descramble + rate-dematch into d_softbuf [n_sf][sb_sf_stride].  noise_mode 0: use
  * noise_est (srsUE passes 0.01), 1: use d_meas[.][0].  accumulate 0: new transmission, 1: HARQ combine.
  * d_dbg_d [n_sf][nof_re] / d_dbg_e [n_sf][G] optional taps of the equalised symbols / descrambled LLRs. */
@@ -173,6 +179,8 @@ int srsue_gpu_batch_stats(const srsue_gpu_batch_t *batch, int *n_plans, int *n_s
 int srsue_gpu_host_cbsegm(int tbs, int *out);
 /* number of PDSCH resource elements of a grant; re_idx (optional) receives l*nsc + k for each */
 int srsue_gpu_host_pdsch_re(const srsue_gpu_cell_t *cell, const srsue_gpu_pdsch_cfg_t *cfg, int32_t *re_idx);
+/* subcarriers (in OFDM symbol 0) of the 16 PCFICH symbols d(0..15) */
+int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t *cell, int32_t *k16);
 /* rate-matching read order for (K, F, rv): seq[n] = index 3k+stream of the n-th non-null circular-buffer
  * position (srsLTE decoder-input order); returns the number of entries (<= 3K+12) */
 int srsue_gpu_host_rm_sequence(int K, int F, int rv, int32_t *seq);

@@ -76,6 +76,8 @@ int      lteo_cb_E(const lteo_cbsegm_t *s, int G, int qm, int nl, int r);
 int      lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int32_t *re_idx);
 int      lteo_crs_positions(const lteo_cell_t *cell, int port, int l, int32_t *k_out);
 void     lteo_crs_values(const lteo_cell_t *cell, int sf_idx, int l, int8_t *re_sign, int8_t *im_sign);
+void     lteo_pcfich_re(const lteo_cell_t *cell, int32_t *k16);    /* subcarriers of d(0..15) in symbol 0 */
+void     lteo_pcfich_bits(const lteo_cell_t *cell, int sf_idx, int cfi, uint8_t *b32);
 void     lteo_fft_twiddles(int n, lteo_cf_t *tw);           /* tw[k] = exp(-2 pi i k / n), k < n/2 */
 
 /* ---- TX side (test-vector generator; double precision) ---------------------------------- */
@@ -87,6 +89,8 @@ int  lteo_pdsch_encode_bits(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg
 int  lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
                         const uint8_t *tb_bytes, lteo_cd_t *grid /* [ports][14][12*nof_prb] */);
 void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq /* 15*nfft samples */);
+/* adds the PCFICH of `cfi` (1..3) to a grid built by lteo_pdsch_tx_grid (symbol 0; TX diversity with 2 ports) */
+void lteo_pcfich_tx(const lteo_cell_t *cell, int sf_idx, int cfi, lteo_cd_t *grid);
 
 /* ---- RX side (the restated hot path) ---------------------------------------------------- */
 void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n);
@@ -100,6 +104,9 @@ void lteo_demod(const lteo_cf_t *d, int nof_re, int qm, int16_t *llr);
 void lteo_descramble(int16_t *llr, int n, uint32_t c_init);
 void lteo_rm_rx(const int16_t *e, int E, int K, int F, int rv, int16_t *w /* 3K+12 triples */);
 /* crc_type: 0 none, 1 CRC24A, 2 CRC24B.  returns iterations run.  bits: K hard bits.        */
+/* PCFICH (SPEC.md 9): returns the CFI 1..3 with the largest correlation; corr[3] = the three integer correlations */
+int  lteo_pcfich_decode(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce,
+                        float noise_est, int32_t *corr);
 int  lteo_tdec(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok);
 /* Debug variant: also returns ext/La after the last iteration and per-iteration bits        */
 int  lteo_tdec_dbg(const int16_t *in, int K, int max_iter, int crc_type, uint8_t *bits, int *crc_ok,

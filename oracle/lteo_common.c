@@ -320,6 +320,29 @@ int lteo_crs_positions(const lteo_cell_t *cell, int port, int l, int32_t *k_out)
   return 2 * cell->nof_prb;
 }
 
+/* PCFICH (36.211 6.7.4): subcarriers, in OFDM symbol 0, of the 16 symbols d(0..15).  Quadruplet i goes to the
+ * resource-element group that starts at k = kbar + floor(i N_RB / 2) * 6 (mod 12 N_RB), kbar = 6 * (N_ID mod 2 N_RB);
+ * inside the group the REs with k mod 3 == N_ID mod 3 are reserved for the CRS of ports 0 AND 1 (36.211 6.2.4: both
+ * are assumed present for the mapping even with one port), the four others carry the quadruplet in ascending k. */
+void lteo_pcfich_re(const lteo_cell_t *cell, int32_t *k16) {
+  int nrb = cell->nof_prb, nsc = 12 * nrb, n = 0;
+  int kbar = 6 * (cell->cell_id % (2 * nrb));
+  for (int i = 0; i < 4; i++) {
+    int k0 = (kbar + ((i * nrb) / 2) * 6) % nsc;
+    for (int j = 0; j < 6; j++)
+      if ((k0 + j) % 3 != cell->cell_id % 3) k16[n++] = k0 + j;
+  }
+}
+
+/* the 32 scrambled CFI code bits (36.212 5.3.4 code words, 36.211 6.7.1 scrambling) */
+void lteo_pcfich_bits(const lteo_cell_t *cell, int sf_idx, int cfi, uint8_t *b32) {
+  uint8_t c[32];
+  uint32_t c_init = ((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell->cell_id + 1) << 9) + (uint32_t)cell->cell_id;
+  lteo_gold(c_init, 32, c);
+  /* code words <0,1,1,...>, <1,0,1,...>, <1,1,0,...>: bit n is 0 where n mod 3 == cfi - 1 */
+  for (int n = 0; n < 32; n++) b32[n] = (uint8_t)(((n % 3) != (cfi - 1)) ^ c[n]);
+}
+
 /* CRS symbol values for symbol l of subframe sf_idx: r(m') = (re_sign + j im_sign)/sqrt(2),
  * m' = m + 110 - nof_prb, m = 0..2*nof_prb-1 (same sequence for both ports) */
 void lteo_crs_values(const lteo_cell_t *cell, int sf_idx, int l, int8_t *re_sign, int8_t *im_sign) {

@@ -344,6 +344,52 @@ static inline int16_t sat_add(int a, int b) {
 
 /* accumulates E received LLRs into the soft buffer w (3K+12 triples), ascending e order; filler
  * positions of d0/d1 are forced to LTEO_FILLER_LLR */
+/* ------------------------------------------------------------------------------------------------
+ * PCFICH (SPEC.md 9): the CFI that srslte_ue_dl_decode_fft_estimate returns (phch_worker.cc:254)
+ * ---------------------------------------------------------------------------------------------- */
+int lteo_pcfich_decode(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf, const lteo_cf_t *ce, float n0,
+                       int32_t *corr) {
+  int nsc = 12 * cell->nof_prb;
+  int32_t k[16];
+  lteo_cf_t d[16];
+  int16_t llr[32];
+  lteo_pcfich_re(cell, k);
+  if (cell->nof_ports == 2) {
+    const float sq2 = (float)sqrt(2.0);
+    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
+    for (int i = 0; i < 16; i += 2) {          /* the Alamouti combiner of lteo_equalize */
+      lteo_cf_t r0 = sf[k[i]], r1 = sf[k[i + 1]], h0 = ce0[k[i]], h1 = ce1[k[i]];
+      float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
+      float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
+      float b_re = h1.re * r1.re + h1.im * r1.im, b_im = h1.im * r1.re - h1.re * r1.im;
+      float c_re = h0.re * r1.re + h0.im * r1.im, c_im = h0.re * r1.im - h0.im * r1.re;
+      float e_re = h1.re * r0.re + h1.im * r0.im, e_im = h1.im * r0.re - h1.re * r0.im;
+      d[i].re = ((a_re + b_re) * sq2) / den;     d[i].im = ((a_im + b_im) * sq2) / den;
+      d[i + 1].re = ((c_re - e_re) * sq2) / den; d[i + 1].im = ((c_im - e_im) * sq2) / den;
+    }
+  } else {
+    for (int i = 0; i < 16; i++) {
+      lteo_cf_t y = sf[k[i]], h = ce[k[i]];
+      float den = (h.re * h.re + h.im * h.im) + n0;
+      d[i].re = (y.re * h.re + y.im * h.im) / den;
+      d[i].im = (y.im * h.re - y.re * h.im) / den;
+    }
+  }
+  lteo_demod(d, 16, 2, llr);
+  uint32_t c_init = ((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell->cell_id + 1) << 9) + (uint32_t)cell->cell_id;
+  lteo_descramble(llr, 32, c_init);
+  int best = 0;
+  int32_t c3[3];
+  for (int c = 0; c < 3; c++) {
+    int32_t acc = 0;
+    for (int n = 0; n < 32; n++) acc += ((n % 3) != c) ? (int32_t)llr[n] : -(int32_t)llr[n];   /* LLR > 0 <=> bit 1 */
+    c3[c] = acc;
+    if (acc > c3[best]) best = c;
+  }
+  if (corr) memcpy(corr, c3, sizeof(c3));
+  return best + 1;
+}
+
 static cache_ent_t g_rm_cache[CACHE_N];
 static int g_rm_cnt = 0;
 

@@ -175,6 +175,27 @@ int lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, con
   return 0;
 }
 
+void lteo_pcfich_tx(const lteo_cell_t *cell, int sf_idx, int cfi, lteo_cd_t *grid) {
+  int nsc = 12 * cell->nof_prb;
+  int32_t k[16];
+  uint8_t b[32];
+  lteo_pcfich_re(cell, k);
+  lteo_pcfich_bits(cell, sf_idx, cfi, b);
+  if (cell->nof_ports == 2) {
+    double a = 1.0 / sqrt(2.0);
+    lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
+    for (int i = 0; i < 16; i += 2) {
+      lteo_cd_t x0 = modulate(b + 2 * i, 2), x1 = modulate(b + 2 * i + 2, 2);
+      g0[k[i]].re = x0.re * a;      g0[k[i]].im = x0.im * a;
+      g1[k[i]].re = -x1.re * a;     g1[k[i]].im = x1.im * a;
+      g0[k[i + 1]].re = x1.re * a;  g0[k[i + 1]].im = x1.im * a;
+      g1[k[i + 1]].re = x0.re * a;  g1[k[i + 1]].im = -x0.im * a;
+    }
+  } else {
+    for (int i = 0; i < 16; i++) grid[k[i]] = modulate(b + 2 * i, 2);
+  }
+}
+
 static void fft_d(lteo_cd_t *x, int n, int inverse, const lteo_cd_t *tab, int ntab) {
   /* plain recursive double-precision FFT, any n = 2^a * 3^b (generator only); tab[i] = exp(-2 pi i/ntab) */
   if (n == 1) return;

@@ -313,7 +313,21 @@ def tdec_mt(llrs, K, nthreads, max_iter=4, crc_type=0):
 
 
 # ---- synthetic subframes (SURVEY.md 8d seeds) ----------------------------------------------
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None):
+def pcfich_re(cell):
+    k = np.zeros(16, np.int32)
+    lib().lteo_pcfich_re(C.byref(cell), _p(k))
+    return k
+
+
+def pcfich_decode(cell, sf_idx, sf, ce, noise_est=0.01):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    corr = np.zeros(3, np.int32)
+    cfi = lib().lteo_pcfich_decode(C.byref(cell), sf_idx, _p(sf), _p(ce), C.c_float(noise_est), _p(corr))
+    return cfi, corr
+
+
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -321,6 +335,8 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None):
     rng = np.random.default_rng(seed)
     tb = rng.integers(0, 256, (cfg.tbs + 7) // 8, dtype=np.uint8)
     grid = pdsch_tx_grid(cell, cfg, tb)
+    if pcfich:          # control format indicator of this subframe in symbol 0 (off by default: older fixtures)
+        lib().lteo_pcfich_tx(C.byref(cell), cfg.sf_idx, cfg.cfi, _p(grid))
     n = lib().lteo_symbol_sz(cell.nof_prb)
     nsc = 12 * cell.nof_prb
     rx = np.zeros((14, nsc), np.complex128)

@@ -147,6 +147,10 @@ class PdschPlan:
     def chest(self, n_sf, d_sf, d_ce, d_meas):
         _check(lib().srsue_gpu_chest(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), _stream()), "chest")
 
+    def pcfich_decode(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, d_cfi, d_corr=None):
+        _check(lib().srsue_gpu_pcfich_decode(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
+                                             _ptr(d_cfi), _ptr(d_corr), _stream()), "pcfich_decode")
+
     def pdsch_llr(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, accumulate, d_softbuf, d_dbg_d=None, d_dbg_e=None):
         _check(lib().srsue_gpu_pdsch_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                          accumulate, _ptr(d_softbuf), _ptr(d_dbg_d), _ptr(d_dbg_e), _stream()), "pdsch_llr")

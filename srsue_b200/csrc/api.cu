@@ -576,6 +576,30 @@ int srsue_gpu_chest(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d
   return chest_launch(p, n_sf, d_sf, d_ce, nullptr, d_meas, stream);
 }
 
+int srsue_gpu_pcfich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, const srsue_gpu_cf_t* d_ce,
+                            const float* d_meas, float noise_est, int noise_mode, int32_t* d_cfi, int32_t* d_corr, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce || !d_cfi || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pcfich_decode: null buffer");
+  PcfichArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
+  a.cfi = d_cfi; a.corr = d_corr;
+  pcfich_re(p->cell, a.re);
+  a.scramble = pcfich_scramble(p->cell, p->cfg.sf_idx);
+  a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.noise_mode = noise_mode; a.noise_est = noise_est;
+  a.k_sqpsk = (float)(100.0 * std::sqrt(2.0));
+  a.k_sq2 = (float)std::sqrt(2.0);
+  pcfich_kernel<<<(n_sf + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t* cell, int32_t* k16) {
+  if (!cell || !k16 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  pcfich_re(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, k16);
+  return 0;
+}
+
 int srsue_gpu_chest_pilots(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, srsue_gpu_cf_t* d_pilots, float* d_meas,
                            void* stream) {
   PLAN_CHECK(p, n_sf);

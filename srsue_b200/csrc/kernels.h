@@ -86,6 +86,19 @@ struct DemodArgs {
 };
 __global__ void pdsch_llr_dematch_kernel(const DemodArgs a);
 
+struct PcfichArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc]
+  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float* meas;         // [n_sf][5] (noise estimate when noise_mode == 1)
+  int32_t* cfi;              // [n_sf] decoded CFI 1..3
+  int32_t* corr;             // optional [n_sf][3] correlations with the three code words
+  int re[16];                // subcarriers of d(0..15) in symbol 0
+  uint32_t scramble;         // 32 scrambling bits, LSB first
+  int n_sf, nsc, nof_ports, noise_mode;
+  float noise_est, k_sqpsk, k_sq2;
+};
+__global__ void pcfich_kernel(const PcfichArgs a);
+
 struct TbArgs {
   const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
   const int32_t* cb_status;  // [n_sf * C]

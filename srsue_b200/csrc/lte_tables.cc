@@ -250,4 +250,26 @@ void fft_twiddles(int n, std::vector<float>& tw) {
   }
 }
 
+// Quadruplet i of the PCFICH sits in the resource-element group starting at kbar + floor(i N_RB / 2) * 6 with
+// kbar = 6 (N_ID mod 2 N_RB); the REs with k mod 3 == N_ID mod 3 belong to the CRS of ports 0/1 (both always assumed
+// for this mapping, 36.211 6.2.4).  Replaces the PCFICH part of srslte_ue_dl_decode_fft_estimate
+// (/root/reference/ue/src/phy/phch_worker.cc:254).
+void pcfich_re(const CellCfg& cell, int32_t* k16) {
+  const int nrb = cell.nof_prb, nsc = 12 * nrb;
+  const int kbar = 6 * (cell.cell_id % (2 * nrb));
+  int n = 0;
+  for (int i = 0; i < 4; i++) {
+    const int k0 = (kbar + ((i * nrb) / 2) * 6) % nsc;
+    for (int j = 0; j < 6; j++)
+      if ((k0 + j) % 3 != cell.cell_id % 3) k16[n++] = k0 + j;
+  }
+}
+
+uint32_t pcfich_scramble(const CellCfg& cell, int sf_idx) {
+  const uint32_t c_init = (((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell.cell_id + 1)) << 9) + (uint32_t)cell.cell_id;
+  std::vector<uint32_t> w;
+  gold_packed(c_init, 32, w);
+  return w[0];
+}
+
 }  // namespace srsue

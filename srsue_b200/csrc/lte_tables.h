@@ -51,6 +51,11 @@ void gold_bits(uint32_t c_init, int n, uint8_t* c);
 // packed LSB-first: bit i of the sequence is (w[i/32] >> (i%32)) & 1
 void gold_packed(uint32_t c_init, int n, std::vector<uint32_t>& w);
 
+// PCFICH (36.211 6.7): subcarriers of d(0..15) in OFDM symbol 0, and the 32 scrambling bits of subframe sf_idx packed
+// LSB first
+void pcfich_re(const CellCfg& cell, int32_t* k16);
+uint32_t pcfich_scramble(const CellCfg& cell, int sf_idx);
+
 bool cbsegm(int tbs, CbSegm* s);
 inline int cb_len(const CbSegm& s, int r) { return r < s.Cm ? s.Km : s.Kp; }
 int cb_E(const CbSegm& s, int G, int qm, int nl, int r);

@@ -243,6 +243,65 @@ __global__ void __launch_bounds__(512) pdsch_llr_dematch_kernel(const DemodArgs 
   }
 }
 
+// ---- PCFICH: the CFI srslte_ue_dl_decode_fft_estimate hands back (phch_worker.cc:254).  SPEC.md 9: the 16 symbols of
+// OFDM symbol 0 are equalised like PDSCH symbols (MMSE / Alamouti), demapped to int16 QPSK LLRs, descrambled and
+// correlated with the three 32-bit code words in integer arithmetic.  One warp per subframe, lane i < 16 owns d(i).
+__global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
+  const int sf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (sf >= a.n_sf) return;
+  const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
+  const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;
+  const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (lane < 16) {
+    float2 d;
+    if (a.nof_ports == 2) {
+      const float2* h1p = h0p + 14 * a.nsc;
+      const int g0 = a.re[lane & ~1], g1 = a.re[lane | 1];
+      const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
+      const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
+      if ((lane & 1) == 0) {
+        const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
+        const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
+        d = make_float2(__fdiv_rn(__fmul_rn(__fadd_rn(a_re, b_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fadd_rn(a_im, b_im), a.k_sq2), den));
+      } else {
+        const float c_re = dot_rn(h0.x, r1.x, h0.y, r1.y), c_im = det_rn(h0.x, r1.y, h0.y, r1.x);
+        const float e_re = dot_rn(h1.x, r0.x, h1.y, r0.y), e_im = det_rn(h1.y, r0.x, h1.x, r0.y);
+        d = make_float2(__fdiv_rn(__fmul_rn(__fsub_rn(c_re, e_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fsub_rn(c_im, e_im), a.k_sq2), den));
+      }
+    } else {
+      const int g = a.re[lane];
+      const float2 r = y[g], h = h0p[g];
+      const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
+      d = make_float2(__fdiv_rn(dot_rn(r.x, h.x, r.y, h.y), den), __fdiv_rn(det_rn(r.y, h.x, r.x, h.y), den));
+    }
+    int l[2] = {q16(-__fmul_rn(a.k_sqpsk, d.x)), q16(-__fmul_rn(a.k_sqpsk, d.y))};
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int n = 2 * lane + b;
+      if ((a.scramble >> n) & 1u) l[b] = -l[b];
+      // code word c has a 0 where n mod 3 == c, a 1 elsewhere; LLR > 0 <=> bit 1
+      const int m = n % 3;
+      c0 += (m != 0) ? l[b] : -l[b];
+      c1 += (m != 1) ? l[b] : -l[b];
+      c2 += (m != 2) ? l[b] : -l[b];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, off);
+    c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, off);
+    c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, off);
+  }
+  if (lane == 0) {
+    int best = 1, v = c0;
+    if (c1 > v) { best = 2; v = c1; }
+    if (c2 > v) { best = 3; }
+    a.cfi[sf] = best;
+    if (a.corr) { a.corr[sf * 3 + 0] = c0; a.corr[sf * 3 + 1] = c1; a.corr[sf * 3 + 2] = c2; }
+  }
+}
+
 // ---- K6b: transport-block assembly + CRC24A --------------------------------------------------------
 namespace {
 __device__ __forceinline__ uint32_t gf_mul24(uint32_t x, uint32_t yv, uint32_t poly) {

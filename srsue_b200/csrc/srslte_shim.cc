@@ -47,7 +47,8 @@ struct UeDlGpu {
   srsue_gpu_ctx_t* ctx = nullptr;
   srsue_gpu_cell_t cell{};
   int nsc = 0, sf_len = 0;
-  uint32_t cfi = 1;
+  uint32_t cfi = 0;       // 0: take the CFI from the PCFICH of every subframe; 1..3: forced by srsue_gpu_ue_dl_set_cfi
+  int32_t* d_cfi = nullptr;
   srsue_gpu_pdsch_plan_t* front[10] = {nullptr};
   std::map<std::string, srsue_gpu_pdsch_plan_t*> plans;
   srsue_gpu_cf_t *d_iq = nullptr, *d_sf = nullptr, *d_ce = nullptr;
@@ -151,7 +152,7 @@ void srslte_ue_dl_free(srslte_ue_dl_t* q) {
   if (u) {
     for (auto& f : u->front) srsue_gpu_pdsch_plan_destroy(f);
     for (auto& kv : u->plans) srsue_gpu_pdsch_plan_destroy(kv.second);
-    cudaFree(u->d_iq); cudaFree(u->d_sf); cudaFree(u->d_ce); cudaFree(u->d_meas); cudaFree(u->d_payload); cudaFree(u->d_tb_status);
+    cudaFree(u->d_iq); cudaFree(u->d_sf); cudaFree(u->d_ce); cudaFree(u->d_meas); cudaFree(u->d_cfi); cudaFree(u->d_payload); cudaFree(u->d_tb_status);
     if (u->stream) cudaStreamDestroy(u->stream);
     delete u;
   }
@@ -168,7 +169,7 @@ void srslte_ue_dl_set_rnti(srslte_ue_dl_t* q, uint16_t rnti) {
 }
 
 void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t* q, uint32_t cfi) {
-  if (q && q->gpu && cfi >= 1 && cfi <= 3) static_cast<UeDlGpu*>(q->gpu)->cfi = cfi;
+  if (q && q->gpu && cfi <= 3) static_cast<UeDlGpu*>(q->gpu)->cfi = cfi;     // 0: decode the PCFICH (default)
 }
 
 int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf_idx, uint32_t* cfi) {
@@ -187,6 +188,13 @@ int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf
   if (srsue_gpu_ofdm_rx(fp, 1, u->d_iq, u->d_sf, u->stream)) return SRSLTE_ERROR;
   if (srsue_gpu_chest(fp, 1, u->d_sf, u->d_ce, u->d_meas, u->stream)) return SRSLTE_ERROR;
   float meas[5];
+  int32_t cfi_dec = 0;
+  if (u->cfi == 0) {
+    // srsLTE decodes the PCFICH with the channel estimator's noise figure
+    if (!u->d_cfi && cudaMalloc((void**)&u->d_cfi, 4 * sizeof(int32_t)) != cudaSuccess) return SRSLTE_ERROR;
+    if (srsue_gpu_pcfich_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, u->d_cfi, u->d_cfi + 1, u->stream)) return SRSLTE_ERROR;
+    cudaMemcpyAsync(&cfi_dec, u->d_cfi, sizeof(cfi_dec), cudaMemcpyDeviceToHost, u->stream);
+  }
   cudaMemcpyAsync(q->sf_symbols, u->d_sf, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
   for (int p = 0; p < u->cell.nof_ports; p++)
     cudaMemcpyAsync(q->ce[p], u->d_ce + (size_t)p * grid, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
@@ -194,7 +202,7 @@ int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf
   if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
   q->chest.noise_estimate = meas[0]; q->chest.rsrp = meas[1]; q->chest.rssi = meas[2]; q->chest.rsrq = meas[3];
   u->dev_valid = true;
-  if (cfi) *cfi = u->cfi;
+  if (cfi) *cfi = u->cfi ? u->cfi : (uint32_t)cfi_dec;
   return SRSLTE_SUCCESS;
 }
 
@@ -281,7 +289,7 @@ int srslte_ue_dl_decode_rnti(srslte_ue_dl_t* q, cf_t* input, uint8_t* data, uint
   int rc = srslte_ue_dl_decode_fft_estimate(q, input, sf_idx, &cfi);
   if (rc < 0) return rc;
   if (!u->have_grant) return 0;                       // no DCI for this rnti
-  rc = srslte_ue_dl_cfg_grant(q, &u->grant, u->grant_cfi, sf_idx, u->grant_rv);
+  rc = srslte_ue_dl_cfg_grant(q, &u->grant, u->grant_cfi ? u->grant_cfi : cfi, sf_idx, u->grant_rv);   // cfi 0: from the PCFICH
   if (rc) return rc;
   if (u->grant_rv == 0) srslte_softbuffer_rx_reset(&q->softbuffer);
   q->pkts_total++;

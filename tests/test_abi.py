@@ -97,3 +97,21 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert lib.srslte_ue_dl_init(C.byref(q), Cell(nof_prb=6, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=0)) == -1
     t = Tdec()
     assert lib.srslte_tdec_init(C.byref(t), 6144) == -1
+
+
+def test_host_pcfich_mapping_matches_oracle():
+    """the PCFICH resource-element map (36.211 6.7.4) of the library equals the oracle's for every bandwidth and a
+    spread of cell ids, and avoids the CRS positions of ports 0 and 1"""
+    import ctypes as C
+    import numpy as np
+    import srsue_b200 as sg
+    from oracle import oracle as o
+    L = sg.lib()
+    for prb in (6, 15, 25, 50, 75, 100):
+        for cid in (0, 1, 2, 5, 77, 150, 301, 503):
+            cell = sg.make_cell(prb, 2, cid)
+            k = np.zeros(16, np.int32)
+            assert L.srsue_gpu_host_pcfich_re(C.byref(cell), k.ctypes.data_as(C.c_void_p)) == 0
+            ref = o.pcfich_re(o.make_cell(prb, 2, cid))
+            assert np.array_equal(k, ref)
+            assert len(set(k.tolist())) == 16 and all(x % 3 != cid % 3 for x in k)

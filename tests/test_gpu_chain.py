@@ -77,8 +77,8 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     from tests.srslte_ctypes import UeDl, Cell, Grant, SoftBuffer, make_grant
     prb, qm, tbs = 25, 4, 4968
     ocell = o.make_cell(prb, 1, 1)
-    ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=qm, tbs=tbs)
-    tb, iq, _ = o.gen_subframe(ocell, ocfg, 321, 20.0)
+    ocfg = o.make_cfg(ocell, sf_idx=1, cfi=2, qm=qm, tbs=tbs)
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 321, 20.0, pcfich=True)
     q = UeDl()
     cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=0)
     assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
@@ -89,9 +89,9 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     L.srslte_softbuffer_rx_reset(C.byref(sb))
     cfi = C.c_uint32(0)
     assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), iq.ctypes.data_as(C.c_void_p), 1, C.byref(cfi)) == 0
-    assert cfi.value == 1
+    assert cfi.value == 2                      # decoded from the PCFICH on the device
     grant = make_grant(prb, qm, tbs)
-    assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), 1, 1, 0) == 0
+    assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), cfi.value, 1, 0) == 0
     assert q.pdsch_cfg.nbits.nof_re == len(o.pdsch_re_list(ocell, ocfg))
     payload = np.zeros(tbs // 8, np.uint8)
     ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), q.sf_symbols, q.ce,
@@ -117,6 +117,36 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     assert np.array_equal(np.unpackbits(out), o.tdec(llr, K, 4, 0)[0])
     L.srslte_tdec_free(C.byref(h))
     L.srslte_softbuffer_rx_free(C.byref(sb))
+    L.srslte_ue_dl_free(C.byref(q))
+
+
+@pytest.mark.parametrize("cfi", [1, 2, 3])
+def test_srslte_ue_dl_decode_wrapper_cfg1(gpu, oracle, cfi):
+    """BASELINE configs[0]: a 1.4 MHz TM1 QPSK MCS 0 subframe through srslte_ue_dl_decode (the wrapper the north star
+    names): PCFICH -> CFI on the device, grant from the caller, chest noise figure in the equaliser."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, make_grant
+    prb, qm, tbs = 6, 2, 152
+    ocell = o.make_cell(prb, 1, 1)
+    q = UeDl()
+    cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=0)
+    assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+    L.srslte_ue_dl_set_rnti(C.byref(q), 0x1234)
+    L.srslte_sch_set_max_noi(C.byref(q.pdsch.dl_sch), 4)
+    grant = make_grant(prb, qm, tbs)
+    assert L.srsue_gpu_ue_dl_set_grant(C.byref(q), C.byref(grant), 0, 0) == 0        # cfi 0: from the PCFICH
+    for tti in (1, 12, 27):
+        ocfg = o.make_cfg(ocell, sf_idx=tti % 10, cfi=cfi, qm=qm, tbs=tbs)
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 900 + tti, 10.0, pcfich=True)
+        data = np.zeros(tbs // 8, np.uint8)
+        n = L.srslte_ue_dl_decode(C.byref(q), iq.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti)
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 1, 4)
+        assert rc == 0 and n == tbs
+        assert np.array_equal(data, pl) and np.array_equal(data, tb)
+    assert q.pkts_total == 3 and q.pkt_errors == 0
     L.srslte_ue_dl_free(C.byref(q))
 
 

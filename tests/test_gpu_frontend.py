@@ -181,3 +181,47 @@ def test_fused_channel_interpolation_is_bit_identical(gpu, oracle, name):
     assert torch.equal(d_meas, d_meas2)
     assert torch.equal(d_sb, d_sb2)
     plan.close()
+
+
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (15, 2, 77), (25, 1, 301), (50, 2, 5), (100, 1, 503), (100, 2, 0)])
+def test_pcfich_matches_oracle(gpu, oracle, prb, ports, cid):
+    """srsue_gpu_pcfich_decode: CFI and the three integer correlations equal the oracle's for every subframe of a batch
+    with mixed CFIs, at an SNR where decisions are reliable and at one where they are not."""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    ocell = o.make_cell(prb, ports, cid)
+    cell = sg.make_cell(prb, ports, cid)
+    sf_idx = cid % 10
+    tbs = 152 if prb == 6 else 1000
+    cfis = [1, 2, 3, 2, 1, 3] if prb > 10 else [1, 2, 3, 1, 2, 3]
+    for snr, noise_mode in ((8.0, 1), (-8.0, 0)):
+        iq = []
+        for i, cfi in enumerate(cfis):
+            ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, qm=2, tbs=tbs, tm=ports)
+            iq.append(o.gen_subframe(ocell, ocfg, 3000 + i, snr, None, pcfich=True)[1])
+        iq = np.stack(iq)
+        n = len(cfis)
+        cfg = sg.make_cfg(cell, sf_idx=sf_idx, cfi=1, qm=2, tbs=0, tm=ports)      # front-end-only plan
+        plan = sg.PdschPlan(ctx, cell, cfg, n)
+        I = plan.info
+        d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+        d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+        d_cfi = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_corr = torch.zeros((n, 3), dtype=torch.int32, device="cuda")
+        plan.ofdm_rx(n, d_iq, d_sf)
+        plan.chest(n, d_sf, d_ce, d_meas)
+        plan.pcfich_decode(n, d_sf, d_ce, d_meas, 0.01, noise_mode, d_cfi, d_corr)
+        torch.cuda.synchronize()
+        got, corr = d_cfi.cpu().numpy(), d_corr.cpu().numpy()
+        for i, cfi in enumerate(cfis):
+            sf_o = o.ofdm_rx(prb, iq[i])
+            ce_o, meas_o = o.chest(ocell, sf_idx, sf_o)
+            ref, rcorr = o.pcfich_decode(ocell, sf_idx, sf_o, ce_o, meas_o[0] if noise_mode else 0.01)
+            assert got[i] == ref and np.array_equal(corr[i], rcorr)
+            if snr > 0:
+                assert ref == cfi
+        plan.close()
