@@ -35,7 +35,7 @@ typedef struct srsue_gpu_pdsch_plan srsue_gpu_pdsch_plan_t; /* one per (cell, gr
 typedef struct { float re, im; } srsue_gpu_cf_t;        /* layout of srsLTE's cf_t (float _Complex) */
 
 typedef struct {
-  int nof_prb;      /* 6, 15, 25, 50, 100 (75 = 1536-point FFT: not supported yet) */
+  int nof_prb;      /* 6, 15, 25, 50, 75, 100 */
   int nof_ports;    /* 1 or 2 */
   int cell_id;      /* physical cell id, normal cyclic prefix */
 } srsue_gpu_cell_t;

@@ -382,7 +382,7 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
   if (!ctx || !cell || !cfg || !out || max_batch < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "plan_create: bad arguments");
   *out = nullptr;
   const int nfft = symbol_sz(cell->nof_prb);
-  if (nfft < 0 || nfft == 1536) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_prb=%d not supported (1536-point FFT not implemented)", cell->nof_prb);
+  if (nfft < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_prb=%d is not an LTE bandwidth", cell->nof_prb);
   if (cell->nof_ports < 1 || cell->nof_ports > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_ports must be 1 or 2");
   if (cfg->qm != 2 && cfg->qm != 4 && cfg->qm != 6) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "qm must be 2, 4 or 6");
   if (cfg->tm == 2 && cell->nof_ports != 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "transmit diversity needs 2 ports");
@@ -553,9 +553,11 @@ int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
   a.nfft = p->info.nfft; a.nsc = p->info.nsc; a.n_sf = n_sf;
   a.log2n = 0; while ((1 << a.log2n) < a.nfft) a.log2n++;
   a.scale = (float)(1.0 / std::sqrt((double)a.nfft));
+  a.c3 = (float)(std::sqrt(3.0) / 2.0);
   static const int fft_div = getenv("SRSUE_FFT_POINTS_PER_THREAD") ? atoi(getenv("SRSUE_FFT_POINTS_PER_THREAD")) : 8;   // tuning knob
   const int threads = std::max(32, a.nfft / std::max(8, fft_div));
-  const int smem = 2 * (a.nfft + a.nfft / 16 + 8) * (int)sizeof(float2);
+  // 1536 = 3 x 512: three sub-transforms side by side in each of the two buffers
+  const int smem = (a.nfft == 1536 ? 2 * 3 * (512 + 512 / 16 + 8) : 2 * (a.nfft + a.nfft / 16 + 8)) * (int)sizeof(float2);
   for (int done = 0; done < n_sf; done += 65535) {
     const int n = std::min(65535, n_sf - done);
     OfdmArgs b = a;

@@ -44,9 +44,10 @@ __global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, in
 struct OfdmArgs {
   const float2* iq;          // [n_sf][15 * nfft]
   float2* sf_symbols;        // [n_sf][14 * nsc]
-  const float2* tw;          // nfft/2 twiddles
+  const float2* tw;          // nfft/2 twiddles (1536: 256 of the 512-point transforms, then w_1536^k and w_1536^2k, k < 512)
   int n_sf, nfft, log2n, nsc;
   float scale;
+  float c3;                  // (float)(sqrt(3)/2), radix-3 stage of the 1536-point transform
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
 

@@ -241,6 +241,19 @@ int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& ta
 }
 
 void fft_twiddles(int n, std::vector<float>& tw) {
+  if (n % 3 == 0) {
+    // n = 3 m (1536): the table of the three m-point transforms, then the full-circle twiddles w1 = w_n^k and
+    // w2 = w_n^2k of the final radix-3 stage, evaluated in double and rounded once (SPEC.md 2)
+    const int m = n / 3;
+    fft_twiddles(m, tw);
+    tw.resize(m + 4 * m);
+    for (int k = 0; k < m; k++) {
+      const double a1 = -2.0 * M_PI * (double)k / (double)n, a2 = -2.0 * M_PI * (double)(2 * k) / (double)n;
+      tw[m + 2 * k] = (float)std::cos(a1); tw[m + 2 * k + 1] = (float)std::sin(a1);
+      tw[3 * m + 2 * k] = (float)std::cos(a2); tw[3 * m + 2 * k + 1] = (float)std::sin(a2);
+    }
+    return;
+  }
   tw.resize(n);
   for (int k = 0; k < n / 2; k++) {
     const double a = -2.0 * M_PI * (double)k / (double)n;

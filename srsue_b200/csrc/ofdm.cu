@@ -111,14 +111,14 @@ __host__ __device__ constexpr int reg_of_u(int u) {
 template <int N, int L, int LOGR, bool FIRST, bool LAST>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const float2* ssrc, float2* sdst,
                                          float2* __restrict__ gdst, const float2* __restrict__ tw, int tid, int nthreads,
-                                         int nsc, float scale) {
+                                         int nsc, float scale, int in_stride = 1) {
   constexpr int R = 1 << LOGR, nsub = N / (L * R), NL = N / L;
   for (int b = tid; b < N / R; b += nthreads) {
     const int k = b / nsub, np = b % nsub;          // powers of two: shift and mask
     float2 v[8];
     if (FIRST) {
 #pragma unroll
-      for (int r = 0; r < R; r++) v[r] = __ldg(gsrc + np + nsub * r);       // L == 1, so k == 0
+      for (int r = 0; r < R; r++) v[r] = __ldg(gsrc + (np + nsub * r) * in_stride);       // L == 1, so k == 0
     } else {
       int base;
       if (NL >= 16) base = k * (NL + NL / 16) + np + ((nsub >= 16) ? (np >> 4) : 0);
@@ -174,6 +174,52 @@ __device__ __forceinline__ void fft_symbol(const float2* __restrict__ gin, float
   }
 }
 
+// N = 1536 (75 PRB) = 3 x 512 (SPEC.md 2): sub-transform r takes the samples 3 i + r through the three radix-8
+// passes above (64 threads each, its own pair of shared buffers, result in natural order), then one radix-3 DIT
+// stage with the full-circle twiddles w1 = w_1536^k, w2 = w_1536^2k from the table:
+//   t1 = w1 f1, t2 = w2 f2, s = t1 + t2, d = t1 - t2, X[k] = f0 + s, m = f0 - s/2,
+//   X[k + 512] = m - i c3 d, X[k + 1024] = m + i c3 d, c3 = (float)(sqrt(3)/2), every operation rounded once.
+__device__ __forceinline__ void fft1536_symbol(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s_fft,
+                                               const float2* __restrict__ tw, int nsc, float scale, float c3) {
+  constexpr int M = 512, SUB = M + M / 16 + 8, N = 1536;
+  const int tid = threadIdx.x, r = tid / 64, lt = tid - r * 64;
+  if (r < 3) {
+    float2* s0 = s_fft + r * SUB;
+    float2* s1 = s_fft + (3 + r) * SUB;
+    fft_pass<M, 1, 3, true, false>(gin + r, nullptr, s0, nullptr, tw, lt, 64, nsc, scale, 3);
+    __syncthreads();
+    fft_pass<M, 8, 3, false, false>(nullptr, s0, s1, nullptr, tw, lt, 64, nsc, scale);
+    __syncthreads();
+    fft_pass<M, 64, 3, false, false>(nullptr, s1, s0, nullptr, tw, lt, 64, nsc, scale);
+  } else {
+    __syncthreads();
+    __syncthreads();
+  }
+  __syncthreads();
+  const float2* w1t = tw + M / 2;
+  const float2* w2t = tw + M / 2 + M;
+  for (int k = tid; k < M; k += blockDim.x) {
+    const int ks = k + (k >> 4);
+    const float2 f0 = s_fft[ks], f1 = s_fft[SUB + ks], f2 = s_fft[2 * SUB + ks];
+    const float2 t1 = cmul(__ldg(w1t + k), f1), t2 = cmul(__ldg(w2t + k), f2);
+    const float2 sm = make_float2(__fadd_rn(t1.x, t2.x), __fadd_rn(t1.y, t2.y));
+    const float2 df = make_float2(__fsub_rn(t1.x, t2.x), __fsub_rn(t1.y, t2.y));
+    const float2 mm = make_float2(__fsub_rn(f0.x, __fmul_rn(0.5f, sm.x)), __fsub_rn(f0.y, __fmul_rn(0.5f, sm.y)));
+    float2 o[3];
+    o[0] = make_float2(__fadd_rn(f0.x, sm.x), __fadd_rn(f0.y, sm.y));
+    o[1] = make_float2(__fadd_rn(mm.x, __fmul_rn(c3, df.y)), __fsub_rn(mm.y, __fmul_rn(c3, df.x)));
+    o[2] = make_float2(__fsub_rn(mm.x, __fmul_rn(c3, df.y)), __fadd_rn(mm.y, __fmul_rn(c3, df.x)));
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      const int kp = k + u * M;
+      int ko = -1;
+      if (kp >= 1 && kp <= nsc / 2) ko = kp - 1 + nsc / 2;
+      else if (kp >= N - nsc / 2) ko = kp - (N - nsc / 2);
+      if (ko >= 0) gout[ko] = make_float2(__fmul_rn(o[u].x, scale), __fmul_rn(o[u].y, scale));
+    }
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
@@ -188,6 +234,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   float2* s0 = s_fft;
   float2* s1 = s_fft + (N + N / 16 + 8);
+  if (N == 1536) { fft1536_symbol(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.c3); return; }
   switch (a.log2n) {
     case 7: fft_symbol<7>(gin, gout, s0, s1, a.tw, a.nsc, a.scale); break;
     case 8: fft_symbol<8>(gin, gout, s0, s1, a.tw, a.nsc, a.scale); break;

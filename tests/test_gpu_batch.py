@@ -14,6 +14,7 @@ MIX = [  # prb, ports, qm, tbs, tm, sf_idx, cfi, snr
     (50, 2, 4, 6208, 2, 4, 1, 18.0),
     (100, 1, 6, 75376, 1, 1, 1, 30.0),
     (100, 2, 4, 30576, 2, 6, 1, 15.0),
+    (75, 1, 6, 55056, 1, 7, 1, 30.0),
     (25, 1, 6, 11448, 1, 0, 2, 24.0),     # subframe 0: PSS/SSS/PBCH holes
 ]
 

@@ -18,6 +18,7 @@ CASES = {
     "cfg2_waterfall": dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, snr=19.0, taps=False, n=6, noise_mode=0),
     "cfg3_tm2_mcs16": dict(prb=100, ports=2, qm=4, tbs=30576, tm=2, snr=15.0, taps=True, n=4, noise_mode=1),
     "filler_and_two_K": dict(prb=50, ports=1, qm=4, tbs=6208, tm=1, snr=18.0, taps=False, n=3, noise_mode=0),
+    "bw75_15MHz": dict(prb=75, ports=1, qm=6, tbs=55056, tm=1, snr=30.0, taps=False, n=3, noise_mode=0),
     "low_snr_fail": dict(prb=25, ports=1, qm=6, tbs=11448, tm=1, snr=3.0, taps=False, n=3, noise_mode=0),
 }
 

@@ -22,6 +22,8 @@ def _cfgs(o):
         "bw25_sf5": dict(prb=25, ports=1, qm=4, tbs=4968, tm=1, snr=20.0, taps=None, sf=5),
         "bw50_2p": dict(prb=50, ports=2, qm=6, tbs=21384, tm=2, snr=28.0, taps=taps, sf=0),
         "bw15": dict(prb=15, ports=1, qm=2, tbs=1008, tm=1, snr=8.0, taps=None, sf=3),
+        "bw75": dict(prb=75, ports=1, qm=6, tbs=55056, tm=1, snr=30.0, taps=None, sf=2),          # 1536-point FFT
+        "bw75_2p": dict(prb=75, ports=2, qm=4, tbs=22920, tm=2, snr=16.0, taps=taps, sf=5),
     }
 
 
@@ -30,7 +32,7 @@ def _rel(a, b):
     return np.max(np.abs(a - b)) / rms
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "bw25_sf5", "bw50_2p", "bw15"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "bw25_sf5", "bw50_2p", "bw15", "bw75", "bw75_2p"])
 def test_frontend_stages_match_oracle(gpu, oracle, name):
     import torch
     sg, ctx = gpu
@@ -183,7 +185,7 @@ def test_fused_channel_interpolation_is_bit_identical(gpu, oracle, name):
     plan.close()
 
 
-@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (15, 2, 77), (25, 1, 301), (50, 2, 5), (100, 1, 503), (100, 2, 0)])
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (15, 2, 77), (25, 1, 301), (50, 2, 5), (75, 2, 8), (100, 1, 503), (100, 2, 0)])
 def test_pcfich_matches_oracle(gpu, oracle, prb, ports, cid):
     """srsue_gpu_pcfich_decode: CFI and the three integer correlations equal the oracle's for every subframe of a batch
     with mixed CFIs, at an SNR where decisions are reliable and at one where they are not."""
