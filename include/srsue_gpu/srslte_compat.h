@@ -115,7 +115,17 @@ typedef struct SRSLTE_API {
   void *gpu;
 } srslte_chest_dl_t;
 
-typedef struct SRSLTE_API { int unused; } srslte_pdcch_t;     /* PDCCH decode: next row */
+typedef struct SRSLTE_API { void *gpu; } srslte_pdcch_t;      /* back pointer to the owning ue_dl device state */
+
+/* DCI message as found on the PDCCH: payload bits (one per byte) without the CRC (phch_worker.cc:288,312) */
+#define SRSLTE_DCI_MAX_BITS 128
+typedef enum { SRSLTE_DCI_FORMAT0 = 0, SRSLTE_DCI_FORMAT1, SRSLTE_DCI_FORMAT1A, SRSLTE_DCI_FORMAT1C, SRSLTE_DCI_FORMAT_ERROR } srslte_dci_format_t;
+typedef struct SRSLTE_API {
+  uint8_t data[SRSLTE_DCI_MAX_BITS];
+  uint32_t nof_bits;
+  srslte_dci_format_t format;
+} srslte_dci_msg_t;
+
 typedef struct SRSLTE_API { uint32_t L; uint32_t ncce; } srslte_dci_location_t;
 
 typedef struct SRSLTE_API {
@@ -154,6 +164,16 @@ SRSLTE_API void srslte_ue_dl_set_rnti(srslte_ue_dl_t *q, uint16_t rnti);
 SRSLTE_API int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t *q, cf_t *input, uint32_t sf_idx, uint32_t *cfi);
 SRSLTE_API int srslte_ue_dl_cfg_grant(srslte_ue_dl_t *q, srslte_ra_dl_grant_t *grant, uint32_t cfi, uint32_t sf_idx,
                                       uint32_t rvidx);
+/* PDCCH (phch_worker.cc:260,293,320): soft bits of the whole control region on the device, then a blind search.
+ * find_dl_dci_type returns 1 when a DCI for rnti was found (UE-specific space: formats 1A and 1, then the common space:
+ * format 1A; SI/RA/P-RNTI: common space only), 0 when not, < 0 on error; it fills dci_msg, q->last_location and
+ * q->last_n_cce.  Turning the message into a grant (srslte_dci_msg_to_dl_grant, needs the 36.213 TBS tables) stays with
+ * the caller's libsrslte. */
+SRSLTE_API int srslte_pdcch_extract_llr(srslte_pdcch_t *q, cf_t *sf_symbols, cf_t *ce[SRSLTE_MAX_PORTS], float noise_estimate,
+                                        uint32_t nsubframe, uint32_t cfi);
+SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx,
+                                             uint16_t rnti, srslte_rnti_type_t rnti_type);
+SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);
 /* wrappers the north star names; the DCI search is a "next" row, so the grant to use is the one last
  * installed with srsue_gpu_ue_dl_set_grant().  Return decoded bits (tbs) / 0 (no grant) / < 0. */
 SRSLTE_API int srslte_ue_dl_decode(srslte_ue_dl_t *q, cf_t *input, uint8_t *data, uint32_t tti);

@@ -107,6 +107,18 @@ int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t
 int srsue_gpu_pcfich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
                             const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode,
                             int32_t *d_cfi, int32_t *d_corr, void *stream);
+/* PDCCH (srslte_pdcch_extract_llr + srslte_ue_dl_find_dl_dci_type, phch_worker.cc:260,293).  The control region is
+ * that of the plan's cell, cfi and sf_idx; ng_x6 = 6 x the PHICH Ng of the MIB (1, 3, 6, 12), normal PHICH duration.
+ * _info: REGs and CCEs available to PDCCH.  _extract_llr: d_llr [n_sf][8 * n_reg] int16, 72 per CCE in CCE order.
+ * _find_dci: blind search of the UE-specific (common = 0) or common search space for a payload of nof_bits bits whose
+ * CRC is masked with rnti; d_found [n_sf][4] = {found, L, first CCE, candidate index}, d_bits [n_sf][64] one bit per
+ * byte, d_rem optional [n_sf][candidates] = the RNTI each candidate decodes to.  Returns the number of candidates. */
+int srsue_gpu_pdcch_info(srsue_gpu_pdsch_plan_t *plan, int ng_x6, int *n_reg, int *nof_cce);
+int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                                const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int ng_x6,
+                                int16_t *d_llr, void *stream);
+int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_llr, int ng_x6, int rnti, int common,
+                             int nof_bits, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
 /* equalise + demap + descramble + rate-dematch into d_softbuf [n_sf][sb_sf_stride].  noise_mode 0: use
  * noise_est (srsUE passes 0.01), 1: use d_meas[.][0].  accumulate 0: new transmission, 1: HARQ combine.
  * d_dbg_d [n_sf][nof_re] / d_dbg_e [n_sf][G] optional taps of the equalised symbols / descrambled LLRs. */
@@ -179,6 +191,13 @@ int srsue_gpu_batch_stats(const srsue_gpu_batch_t *batch, int *n_plans, int *n_s
 int srsue_gpu_host_cbsegm(int tbs, int *out);
 /* number of PDSCH resource elements of a grant; re_idx (optional) receives l*nsc + k for each */
 int srsue_gpu_host_pdsch_re(const srsue_gpu_cell_t *cell, const srsue_gpu_pdsch_cfg_t *cfg, int32_t *re_idx);
+/* PDCCH bookkeeping: data REs (grid index l*nsc + k, 4 per REG) of the REGs that carry PDCCH, in mapping order (returns
+ * the number of REGs); quadruplet carried by each mapping position; search-space candidates (returns their number);
+ * payload size of DCI format 1A (fmt 0) / 1 (fmt 1) */
+int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t *cell, int cfi, int ng_x6, int32_t *re4);
+int srsue_gpu_host_pdcch_quad_perm(int n_quad, int cell_id, int32_t *src);
+int srsue_gpu_host_pdcch_search_space(int nof_cce, int sf_idx, int rnti, int common, int32_t *cand_L, int32_t *cand_ncce);
+int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb);
 /* subcarriers (in OFDM symbol 0) of the 16 PCFICH symbols d(0..15) */
 int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t *cell, int32_t *k16);
 /* rate-matching read order for (K, F, rv): seq[n] = index 3k+stream of the n-th non-null circular-buffer

@@ -104,6 +104,26 @@ void lteo_demod(const lteo_cf_t *d, int nof_re, int qm, int16_t *llr);
 void lteo_descramble(int16_t *llr, int n, uint32_t c_init);
 void lteo_rm_rx(const int16_t *e, int E, int K, int F, int rv, int16_t *w /* 3K+12 triples */);
 /* crc_type: 0 none, 1 CRC24A, 2 CRC24B.  returns iterations run.  bits: K hard bits.        */
+/* ---- PDCCH (SPEC.md 10; lteo_pdcch.c) ---- */
+typedef struct { const uint8_t *bits; int nof_bits; uint16_t rnti; int L, ncce; } lteo_dci_tx_t;
+int  lteo_ctrl_symbols(int nof_prb, int cfi);
+int  lteo_phich_groups(int nof_prb, int ng_x6);                         /* ng_x6 = 6 Ng: 1, 3, 6, 12 */
+int  lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k, int32_t *reg_l);
+void lteo_reg_res(const lteo_cell_t *cell, int k0, int l, int32_t *k4);
+int  lteo_cc_interleaver(int D, int32_t *out);
+void lteo_pdcch_quad_perm(int n_quad, int cell_id, int32_t *src);
+void lteo_conv_encode(const uint8_t *c, int D, uint8_t *d);
+int  lteo_cc_rm_sequence(int D, int32_t *seq);
+void lteo_dci_encode(const uint8_t *bits, int nof_bits, uint16_t rnti, int E, uint8_t *e);
+int  lteo_pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, int common, int32_t *cand_L, int32_t *cand_ncce);
+/* adds the PDCCHs of `list` to a grid built by lteo_pdsch_tx_grid; returns the number of CCEs or < 0 */
+int  lteo_pdcch_tx(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_x6, int n_dci, const lteo_dci_tx_t *list,
+                   lteo_cd_t *grid);
+int  lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_x6, const lteo_cf_t *sf_symbols,
+                            const lteo_cf_t *ce, float noise_est, int16_t *llr /* 8 * n_reg */);
+uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out);
+int  lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rnti, int common, int nof_bits,
+                         uint8_t *bits_out, int *found_L, int *found_ncce);
 /* PCFICH (SPEC.md 9): returns the CFI 1..3 with the largest correlation; corr[3] = the three integer correlations */
 int  lteo_pcfich_decode(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce,
                         float noise_est, int32_t *corr);

@@ -196,6 +196,47 @@ void lteo_pcfich_tx(const lteo_cell_t *cell, int sf_idx, int cfi, lteo_cd_t *gri
   }
 }
 
+/* PDCCH (36.211 6.8): multiplex the encoded DCIs at their CCE positions (<NIL> elsewhere), scramble, QPSK, quadruplet
+ * interleaver + cyclic shift, map to the control-region REGs (TX diversity with 2 ports) */
+int lteo_pdcch_tx(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_x6, int n_dci, const lteo_dci_tx_t *list,
+                  lteo_cd_t *grid) {
+  int nsc = 12 * cell->nof_prb, max_reg = 4 * 3 * cell->nof_prb;
+  int32_t *rk = (int32_t *)malloc(sizeof(int32_t) * max_reg), *rl = (int32_t *)malloc(sizeof(int32_t) * max_reg);
+  int n_reg = lteo_pdcch_regs(cell, cfi, ng_x6, rk, rl), n_cce = n_reg / 9, nb = 8 * n_reg;
+  uint8_t *b = (uint8_t *)malloc(nb), *c = (uint8_t *)malloc(nb);
+  memset(b, 2, nb);                                             /* 2 = <NIL>: nothing transmitted */
+  for (int i = 0; i < n_dci; i++) {
+    if (list[i].ncce < 0 || list[i].ncce + list[i].L > n_cce) { free(rk); free(rl); free(b); free(c); return -1; }
+    lteo_dci_encode(list[i].bits, list[i].nof_bits, list[i].rnti, 72 * list[i].L, b + 72 * list[i].ncce);
+  }
+  lteo_gold(((uint32_t)sf_idx << 9) + (uint32_t)cell->cell_id, nb, c);
+  for (int i = 0; i < nb; i++) if (b[i] < 2) b[i] ^= c[i];
+  int32_t *src = (int32_t *)malloc(sizeof(int32_t) * n_reg);
+  lteo_pdcch_quad_perm(n_reg, cell->cell_id, src);
+  double a = 1.0 / sqrt(2.0);
+  for (int m = 0; m < n_reg; m++) {
+    const uint8_t *q = b + 8 * src[m];
+    if (q[0] == 2) continue;                                    /* CCEs are whole: a quadruplet is all data or all NIL */
+    int32_t k4[4];
+    lteo_reg_res(cell, rk[m], rl[m], k4);
+    lteo_cd_t x[4];
+    for (int i = 0; i < 4; i++) x[i] = modulate(q + 2 * i, 2);
+    lteo_cd_t *g0 = grid + rl[m] * nsc, *g1 = grid + 14 * nsc + rl[m] * nsc;
+    if (cell->nof_ports == 2) {
+      for (int i = 0; i < 4; i += 2) {
+        g0[k4[i]].re = x[i].re * a;          g0[k4[i]].im = x[i].im * a;
+        g1[k4[i]].re = -x[i + 1].re * a;     g1[k4[i]].im = x[i + 1].im * a;
+        g0[k4[i + 1]].re = x[i + 1].re * a;  g0[k4[i + 1]].im = x[i + 1].im * a;
+        g1[k4[i + 1]].re = x[i].re * a;      g1[k4[i + 1]].im = -x[i].im * a;
+      }
+    } else {
+      for (int i = 0; i < 4; i++) g0[k4[i]] = x[i];
+    }
+  }
+  free(rk); free(rl); free(b); free(c); free(src);
+  return n_cce;
+}
+
 static void fft_d(lteo_cd_t *x, int n, int inverse, const lteo_cd_t *tab, int ntab) {
   /* plain recursive double-precision FFT, any n = 2^a * 3^b (generator only); tab[i] = exp(-2 pi i/ntab) */
   if (n == 1) return;

@@ -327,7 +327,73 @@ def pcfich_decode(cell, sf_idx, sf, ce, noise_est=0.01):
     return cfi, corr
 
 
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False):
+class DciTx(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("nof_bits", C.c_int), ("rnti", C.c_uint16), ("L", C.c_int), ("ncce", C.c_int)]
+
+
+def pdcch_regs(cell, cfi, ng_x6=6):
+    rk = np.zeros(12 * cell.nof_prb, np.int32)
+    rl = np.zeros(12 * cell.nof_prb, np.int32)
+    n = lib().lteo_pdcch_regs(C.byref(cell), cfi, ng_x6, _p(rk), _p(rl))
+    return rk[:n], rl[:n]
+
+
+def pdcch_quad_perm(n_quad, cell_id):
+    src = np.zeros(n_quad, np.int32)
+    lib().lteo_pdcch_quad_perm(n_quad, cell_id, _p(src))
+    return src
+
+
+def pdcch_search_space(nof_cce, sf_idx, rnti, common=False):
+    cl, cn = np.zeros(32, np.int32), np.zeros(32, np.int32)
+    n = lib().lteo_pdcch_search_space(nof_cce, sf_idx, C.c_uint16(rnti), int(common), _p(cl), _p(cn))
+    return list(zip(cl[:n].tolist(), cn[:n].tolist()))
+
+
+def dci_encode(bits, rnti, E):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    e = np.zeros(E, np.uint8)
+    lib().lteo_dci_encode(_p(bits), len(bits), C.c_uint16(rnti), E, _p(e))
+    return e
+
+
+def pdcch_tx(cell, sf_idx, cfi, dcis, grid, ng_x6=6):
+    """dcis: list of (bits uint8 array, rnti, L, ncce); adds them to grid [ports][14][nsc] complex128"""
+    keep = [np.ascontiguousarray(d[0], np.uint8) for d in dcis]
+    arr = (DciTx * max(len(dcis), 1))()
+    for a, k, d in zip(arr, keep, dcis):
+        a.bits, a.nof_bits, a.rnti, a.L, a.ncce = k.ctypes.data, len(k), d[1], d[2], d[3]
+    rc = lib().lteo_pdcch_tx(C.byref(cell), sf_idx, cfi, ng_x6, len(dcis), arr, _p(grid))
+    if rc < 0:
+        raise RuntimeError("pdcch_tx: DCI does not fit the control region")
+    return rc
+
+
+def pdcch_extract_llr(cell, sf_idx, cfi, sf, ce, noise_est=0.01, ng_x6=6):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    llr = np.zeros(8 * 12 * cell.nof_prb, np.int16)
+    ncce = lib().lteo_pdcch_extract_llr(C.byref(cell), sf_idx, cfi, ng_x6, _p(sf), _p(ce), C.c_float(noise_est), _p(llr))
+    return llr, ncce
+
+
+def pdcch_decode_candidate(llr, L, nof_bits):
+    llr = np.ascontiguousarray(llr, np.int16)
+    out = np.zeros(nof_bits, np.uint8)
+    lib().lteo_pdcch_decode_candidate.restype = C.c_uint16
+    r = lib().lteo_pdcch_decode_candidate(_p(llr), L, nof_bits, _p(out))
+    return out, r
+
+
+def pdcch_find_dci(llr, nof_cce, sf_idx, rnti, nof_bits, common=False):
+    llr = np.ascontiguousarray(llr, np.int16)
+    out = np.zeros(nof_bits, np.uint8)
+    L, n = C.c_int(), C.c_int()
+    found = lib().lteo_pdcch_find_dci(_p(llr), nof_cce, sf_idx, C.c_uint16(rnti), int(common), nof_bits, _p(out), C.byref(L), C.byref(n))
+    return found, out, L.value, n.value
+
+
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -337,6 +403,8 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False):
     grid = pdsch_tx_grid(cell, cfg, tb)
     if pcfich:          # control format indicator of this subframe in symbol 0 (off by default: older fixtures)
         lib().lteo_pcfich_tx(C.byref(cell), cfg.sf_idx, cfg.cfi, _p(grid))
+    if dcis:            # PDCCHs of this subframe: list of (bits, rnti, L, ncce)
+        pdcch_tx(cell, cfg.sf_idx, cfg.cfi, dcis, grid, ng_x6)
     n = lib().lteo_symbol_sz(cell.nof_prb)
     nsc = 12 * cell.nof_prb
     rx = np.zeros((14, nsc), np.complex128)

@@ -151,6 +151,22 @@ class PdschPlan:
         _check(lib().srsue_gpu_pcfich_decode(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                              _ptr(d_cfi), _ptr(d_corr), _stream()), "pcfich_decode")
 
+    def pdcch_info(self, ng_x6=6):
+        a, b = C.c_int(), C.c_int()
+        _check(lib().srsue_gpu_pdcch_info(self.h, ng_x6, C.byref(a), C.byref(b)), "pdcch_info")
+        return a.value, b.value
+
+    def pdcch_extract_llr(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, d_llr, ng_x6=6):
+        _check(lib().srsue_gpu_pdcch_extract_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
+                                                 ng_x6, _ptr(d_llr), _stream()), "pdcch_extract_llr")
+
+    def pdcch_find_dci(self, n_sf, d_llr, rnti, nof_bits, d_found, d_bits, d_rem=None, common=0, ng_x6=6):
+        n = lib().srsue_gpu_pdcch_find_dci(self.h, n_sf, _ptr(d_llr), ng_x6, rnti, common, nof_bits, _ptr(d_found), _ptr(d_bits),
+                                           _ptr(d_rem), _stream())
+        if n < 0:
+            _check(n, "pdcch_find_dci")
+        return n
+
     def pdsch_llr(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, accumulate, d_softbuf, d_dbg_d=None, d_dbg_e=None):
         _check(lib().srsue_gpu_pdsch_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                          accumulate, _ptr(d_softbuf), _ptr(d_dbg_d), _ptr(d_dbg_e), _stream()), "pdsch_llr")

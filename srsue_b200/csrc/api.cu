@@ -236,6 +236,10 @@ struct srsue_gpu_pdsch_plan {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
   Scratch scratch;             // decoder scratch of this plan (plans may run concurrently on different streams)
+  // PDCCH tables of (cell, cfi, sf_idx, ng): built on first use
+  int pd_ng = -1, pd_nreg = 0;
+  int32_t* d_pd_re4 = nullptr; int32_t* d_pd_src = nullptr; uint32_t* d_pd_scr = nullptr;
+  std::map<int, int32_t*> d_pd_rm;   // D -> rate-matching order
 };
 
 extern "C" {
@@ -521,6 +525,8 @@ void srsue_gpu_pdsch_plan_destroy(srsue_gpu_pdsch_plan_t* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaFree(p->d_re); cudaFree(p->d_scr); cudaFree(p->d_gather); cudaFree(p->d_e_start); cudaFree(p->d_cb_geom);
+  cudaFree(p->d_pd_re4); cudaFree(p->d_pd_src); cudaFree(p->d_pd_scr);
+  for (auto& kv : p->d_pd_rm) cudaFree(kv.second);
   cudaFree(p->d_crs); cudaFree(p->d_tw); cudaFree(p->d_list_m); cudaFree(p->d_list_p); cudaFree(p->d_tbmap); cudaFree(p->d_tbshift);
   cudaFree(p->d_sf); cudaFree(p->d_ce); cudaFree(p->d_pil); cudaFree(p->d_meas); cudaFree(p->d_sb); cudaFree(p->d_cb_bits);
   cudaFree(p->d_cb_status); cudaFree(p->d_iq); cudaFree(p->d_payload); cudaFree(p->d_tb_status);
@@ -595,6 +601,115 @@ int srsue_gpu_pcfich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu
   CU_CHECK(cudaGetLastError());
   return 0;
 }
+
+namespace {
+int pdcch_tables(srsue_gpu_pdsch_plan_t* p, int ng_x6) {
+  if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12 (6 x Ng)");
+  if (p->pd_ng == ng_x6) return 0;
+  cudaFree(p->d_pd_re4); cudaFree(p->d_pd_src); cudaFree(p->d_pd_scr);
+  p->d_pd_re4 = nullptr; p->d_pd_src = nullptr; p->d_pd_scr = nullptr; p->pd_ng = -1;
+  std::vector<int32_t> re4, src;
+  const int n_reg = pdcch_regs(p->cell, p->cfg.cfi, ng_x6, re4);
+  if (n_reg < 9) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "control region too small for a PDCCH");
+  pdcch_quad_perm(n_reg, p->cell.cell_id, src);
+  std::vector<uint32_t> scr;
+  gold_packed(((uint32_t)p->cfg.sf_idx << 9) + (uint32_t)p->cell.cell_id, 8 * n_reg, scr);
+  scr.push_back(0);
+  CU_CHECK(upload(&p->d_pd_re4, re4));
+  CU_CHECK(upload(&p->d_pd_src, src));
+  CU_CHECK(upload(&p->d_pd_scr, scr));
+  p->pd_ng = ng_x6; p->pd_nreg = n_reg;
+  return 0;
+}
+}  // namespace
+
+int srsue_gpu_pdcch_info(srsue_gpu_pdsch_plan_t* p, int ng_x6, int* n_reg, int* nof_cce) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  CU_CHECK(cudaSetDevice(p->ctx->device));
+  int rc = pdcch_tables(p, ng_x6);
+  if (rc) return rc;
+  if (n_reg) *n_reg = p->pd_nreg;
+  if (nof_cce) *nof_cce = p->pd_nreg / 9;
+  return 0;
+}
+
+int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, const srsue_gpu_cf_t* d_ce,
+                                const float* d_meas, float noise_est, int noise_mode, int ng_x6, int16_t* d_llr, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce || !d_llr || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_extract_llr: null buffer");
+  int rc = pdcch_tables(p, ng_x6);
+  if (rc) return rc;
+  PdcchLlrArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
+  a.re4 = p->d_pd_re4; a.src = p->d_pd_src; a.scramble = p->d_pd_scr; a.llr = d_llr;
+  a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.n_reg = p->pd_nreg; a.noise_mode = noise_mode;
+  a.noise_est = noise_est; a.k_sqpsk = (float)(100.0 * std::sqrt(2.0)); a.k_sq2 = (float)std::sqrt(2.0);
+  for (int done = 0; done < n_sf; done += 65535) {
+    const int n = std::min(65535, n_sf - done);
+    PdcchLlrArgs b = a;
+    b.sf_symbols += (size_t)done * 14 * a.nsc; b.ce += (size_t)done * a.nof_ports * 14 * a.nsc;
+    if (b.meas) b.meas += (size_t)done * 5;
+    b.llr += (size_t)done * 8 * a.n_reg; b.n_sf = n;
+    pdcch_llr_kernel<<<dim3((a.n_reg + 127) / 128, n), 128, 0, (cudaStream_t)stream>>>(b);
+    p->ctx->launch_count++;
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_llr, int ng_x6, int rnti, int common, int nof_bits,
+                             int32_t* d_found, uint8_t* d_bits, uint16_t* d_rem, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_llr || !d_found || !d_bits) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: null buffer");
+  if (nof_bits < 8 || nof_bits > 64 || rnti < 0 || rnti > 0xFFFF) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: nof_bits must be 8..64");
+  int rc = pdcch_tables(p, ng_x6);
+  if (rc) return rc;
+  const int D = nof_bits + 16;
+  auto it = p->d_pd_rm.find(D);
+  if (it == p->d_pd_rm.end()) {
+    std::vector<int32_t> seq;
+    cc_rm_sequence(D, seq);
+    int32_t* d = nullptr;
+    CU_CHECK(upload(&d, seq));
+    it = p->d_pd_rm.emplace(D, d).first;
+  }
+  PdcchSearchArgs a{};
+  a.llr = d_llr; a.llr_stride = 8LL * p->pd_nreg; a.rm_seq = it->second; a.found = d_found; a.bits = d_bits; a.rem = d_rem;
+  a.n_sf = n_sf; a.nof_bits = nof_bits; a.rnti = rnti;
+  a.n_cand = pdcch_search_space(p->pd_nreg / 9, p->cfg.sf_idx, (uint16_t)rnti, common != 0, a.cand_L, a.cand_ncce);
+  if (a.n_cand == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: empty search space");
+  const int per_words = 3 * D + 4 * D + (D + 3) / 4;
+  const int smem = a.n_cand * per_words * 4;
+  static bool attr = false;
+  if (!attr) { CU_CHECK(cudaFuncSetAttribute(pdcch_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  pdcch_search_kernel<<<n_sf, 32 * a.n_cand, smem, (cudaStream_t)stream>>>(a);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return a.n_cand;
+}
+
+int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t* cell, int cfi, int ng_x6, int32_t* re4) {
+  if (!cell || cfi < 1 || cfi > 3) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  std::vector<int32_t> v;
+  const int n = pdcch_regs(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, cfi, ng_x6, v);
+  if (re4) std::copy(v.begin(), v.end(), re4);
+  return n;
+}
+
+int srsue_gpu_host_pdcch_quad_perm(int n_quad, int cell_id, int32_t* src) {
+  if (n_quad < 1 || !src) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  std::vector<int32_t> v;
+  pdcch_quad_perm(n_quad, cell_id, v);
+  std::copy(v.begin(), v.end(), src);
+  return 0;
+}
+
+int srsue_gpu_host_pdcch_search_space(int nof_cce, int sf_idx, int rnti, int common, int32_t* cand_L, int32_t* cand_ncce) {
+  if (!cand_L || !cand_ncce || nof_cce < 1) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  return pdcch_search_space(nof_cce, sf_idx, (uint16_t)rnti, common != 0, cand_L, cand_ncce);
+}
+
+int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb) { return (fmt == 0 || fmt == 1) ? dci_format_sizeof(fmt, nof_prb) : SRSUE_GPU_ERROR_INVALID_INPUTS; }
 
 int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t* cell, int32_t* k16) {
   if (!cell || !k16 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;

@@ -100,6 +100,32 @@ struct PcfichArgs {
 };
 __global__ void pcfich_kernel(const PcfichArgs a);
 
+struct PdcchLlrArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc]
+  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float* meas;         // [n_sf][5]
+  const int32_t* re4;        // [n_reg][4] grid index of the data REs of every PDCCH REG, mapping order
+  const int32_t* src;        // [n_reg] quadruplet of the PDCCH bit stream carried by the REG
+  const uint32_t* scramble;  // 8 * n_reg scrambling bits, packed LSB first
+  int16_t* llr;              // [n_sf][8 * n_reg]: 72 LLRs per CCE in CCE order
+  int n_sf, nsc, nof_ports, n_reg, noise_mode;
+  float noise_est, k_sqpsk, k_sq2;
+};
+__global__ void pdcch_llr_kernel(const PdcchLlrArgs a);
+
+constexpr int kPdcchMaxCand = 24;
+struct PdcchSearchArgs {
+  const int16_t* llr;        // [n_sf][llr_stride]
+  long long llr_stride;
+  const int32_t* rm_seq;     // [3 D] rate-matching order for D = nof_bits + 16
+  int32_t* found;            // [n_sf][4]: found (0/1), L, first CCE, candidate index
+  uint8_t* bits;             // [n_sf][64]: payload of the match, one bit per byte
+  uint16_t* rem;             // optional [n_sf][n_cand]: RNTI every candidate decodes to
+  int n_sf, n_cand, nof_bits, rnti;
+  int cand_L[kPdcchMaxCand], cand_ncce[kPdcchMaxCand];
+};
+__global__ void pdcch_search_kernel(const PdcchSearchArgs a);
+
 struct TbArgs {
   const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
   const int32_t* cb_status;  // [n_sf * C]

@@ -2,6 +2,7 @@
 // 3GPP TS 36.211 6.3.5 / 6.10.1 / 7.2 and TS 36.212 5.1.1-5.1.4; window rule per oracle/SPEC.md 7.3.
 #include "lte_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -283,6 +284,97 @@ uint32_t pcfich_scramble(const CellCfg& cell, int sf_idx) {
   std::vector<uint32_t> w;
   gold_packed(c_init, 32, w);
   return w[0];
+}
+
+// ---- PDCCH tables.  Replace the bookkeeping inside srslte_pdcch_extract_llr / srslte_ue_dl_find_dl_dci_type
+// (/root/reference/ue/src/phy/phch_worker.cc:260,293): srsLTE's regs.c, pdcch.c and dci.c.
+int ctrl_symbols(int nof_prb, int cfi) { return cfi + (nof_prb <= 10 ? 1 : 0); }
+
+int pdcch_regs(const CellCfg& cell, int cfi, int ng_x6, std::vector<int32_t>& re4) {
+  const int nrb = cell.nof_prb, nsc = 12 * nrb, nsym = ctrl_symbols(nrb, cfi), n0 = 2 * nrb;
+  std::vector<uint8_t> taken(n0, 0);
+  int32_t pc[16];
+  pcfich_re(cell, pc);
+  for (int i = 0; i < 4; i++) taken[pc[4 * i] / 6] = 1;
+  // PHICH groups (normal duration: symbol 0 only, 36.211 6.9.3) over the REGs PCFICH left free
+  std::vector<int> free0;
+  for (int r = 0; r < n0; r++) if (!taken[r]) free0.push_back(r);
+  const int np0 = (int)free0.size(), groups = (ng_x6 * nrb + 47) / 48;
+  for (int g = 0; g < groups; g++)
+    for (int i = 0; i < 3; i++) taken[free0[(cell.cell_id + g + (i * np0) / 3) % np0]] = 1;
+  re4.clear();
+  for (int k = 0; k < nsc; k += 2)
+    for (int l = 0; l < nsym; l++) {
+      if (l == 0) {
+        if (k % 6 || taken[k / 6]) continue;
+        for (int j = 0; j < 6; j++) if ((k + j) % 3 != cell.cell_id % 3) re4.push_back(k + j);
+      } else {
+        if (k % 4) continue;
+        for (int j = 0; j < 4; j++) re4.push_back(l * nsc + k + j);
+      }
+    }
+  return (int)re4.size() / 4;
+}
+
+namespace {
+const uint8_t kCcCols[32] = {1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31, 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30};
+// 36.212 5.1.4.2.1: read order of D elements written row-wise (dummies first) into 32 permuted columns
+void cc_interleaver(int D, std::vector<int32_t>& out) {
+  const int R = (D + 31) / 32, nd = 32 * R - D;
+  out.clear();
+  for (int c = 0; c < 32; c++)
+    for (int r = 0; r < R; r++) {
+      const int y = r * 32 + kCcCols[c];
+      if (y >= nd) out.push_back(y - nd);
+    }
+}
+}  // namespace
+
+void pdcch_quad_perm(int n_quad, int cell_id, std::vector<int32_t>& src) {
+  std::vector<int32_t> w;
+  cc_interleaver(n_quad, w);
+  src.resize(n_quad);
+  for (int m = 0; m < n_quad; m++) src[m] = w[(m + cell_id) % n_quad];
+}
+
+void cc_rm_sequence(int D, std::vector<int32_t>& seq) {
+  std::vector<int32_t> p;
+  cc_interleaver(D, p);
+  seq.clear();
+  for (int s = 0; s < 3; s++)
+    for (int j = 0; j < D; j++) seq.push_back(s * D + p[j]);
+}
+
+int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int32_t* cand_L, int32_t* cand_ncce) {
+  int n = 0;
+  if (common) {
+    const int lim = std::min(nof_cce, 16);
+    for (int L = 4, M = 4; L <= 8; L *= 2, M /= 2)
+      for (int m = 0; m < M; m++)
+        if ((m + 1) * L <= lim) { cand_L[n] = L; cand_ncce[n] = m * L; n++; }
+    return n;
+  }
+  uint32_t Y = rnti;
+  for (int k = 0; k <= sf_idx; k++) Y = (39827u * Y) % 65537u;
+  const int Ms[4] = {6, 6, 2, 2};
+  for (int a = 0; a < 4; a++) {
+    const int L = 1 << a, nl = nof_cce / L;
+    for (int m = 0; m < Ms[a] && m < nl; m++) { cand_L[n] = L; cand_ncce[n] = L * (int)((Y + (uint32_t)m) % (uint32_t)nl); n++; }
+  }
+  return n;
+}
+
+int dci_format_sizeof(int fmt, int nof_prb) {
+  auto ambiguous = [](int n) { return n == 12 || n == 14 || n == 16 || n == 20 || n == 24 || n == 26 || n == 32 || n == 40 || n == 44 || n == 56; };
+  int riv = 0;
+  while ((1 << riv) < nof_prb * (nof_prb + 1) / 2) riv++;
+  int n1a = 15 + riv;                         // flag, local/distributed, RIV, MCS 5, HARQ 3, NDI, RV 2, TPC 2 (>= format 0)
+  if (ambiguous(n1a)) n1a++;
+  if (fmt == 0) return n1a;
+  const int P = nof_prb <= 10 ? 1 : nof_prb <= 26 ? 2 : nof_prb <= 63 ? 3 : 4;
+  int n1 = (nof_prb > 10 ? 1 : 0) + (nof_prb + P - 1) / P + 13;   // RA header, bitmap, MCS 5, HARQ 3, NDI, RV 2, TPC 2
+  while (n1 == n1a || ambiguous(n1)) n1++;
+  return n1;
 }
 
 }  // namespace srsue

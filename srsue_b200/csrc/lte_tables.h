@@ -56,6 +56,20 @@ void gold_packed(uint32_t c_init, int n, std::vector<uint32_t>& w);
 void pcfich_re(const CellCfg& cell, int32_t* k16);
 uint32_t pcfich_scramble(const CellCfg& cell, int sf_idx);
 
+// ---- PDCCH (36.211 6.8, 36.212 5.1.3.1 / 5.1.4.2, 36.213 9.1.1) ----
+int ctrl_symbols(int nof_prb, int cfi);
+// REGs of the control region that carry PDCCH in mapping order (k' ascending, then l'); re4[4*m + i] = grid index
+// (l * nsc + k) of the i-th data RE of REG m.  ng_x6 = 6 * Ng (1, 3, 6, 12), normal PHICH duration.
+int pdcch_regs(const CellCfg& cell, int cfi, int ng_x6, std::vector<int32_t>& re4);
+// src[m'] = quadruplet of the multiplexed PDCCH stream carried by REG m' (interleaver + cyclic shift by N_ID)
+void pdcch_quad_perm(int n_quad, int cell_id, std::vector<int32_t>& src);
+// circular-buffer order of the convolutional-code rate matcher for D = payload + 16 bits: seq[j] = stream * D + k
+void cc_rm_sequence(int D, std::vector<int32_t>& seq);
+// search-space candidates (L, first CCE) of subframe sf_idx for rnti (UE-specific) or the common space
+int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int32_t* cand_L, int32_t* cand_ncce);
+// payload size of DCI format 1A (fmt = 0) or 1 (fmt = 1) for FDD, including the padding rules of 36.212 5.3.3.1
+int dci_format_sizeof(int fmt, int nof_prb);
+
 bool cbsegm(int tbs, CbSegm* s);
 inline int cb_len(const CbSegm& s, int r) { return r < s.Cm ? s.Km : s.Kp; }
 int cb_E(const CbSegm& s, int G, int qm, int nl, int r);

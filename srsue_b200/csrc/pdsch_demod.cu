@@ -302,6 +302,52 @@ __global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
   }
 }
 
+// ---- PDCCH soft bits (srslte_pdcch_extract_llr, phch_worker.cc:260; SPEC.md 10): one thread per resource-element
+// group equalises its 4 symbols with the PDSCH formulas, demaps them to 8 int16 QPSK LLRs, descrambles and stores
+// them (one 16-byte store) at the quadruplet's place in the de-interleaved PDCCH bit stream.
+__global__ void __launch_bounds__(128) pdcch_llr_kernel(const PdcchLlrArgs a) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x, sf = blockIdx.y;
+  if (m >= a.n_reg) return;
+  const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
+  const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;
+  const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
+  const int4 g = *reinterpret_cast<const int4*>(a.re4 + 4 * m);
+  const int gi[4] = {g.x, g.y, g.z, g.w};
+  float2 d[4];
+  if (a.nof_ports == 2) {
+    const float2* h1p = h0p + 14 * a.nsc;
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      const float2 r0 = y[gi[i]], r1 = y[gi[i + 1]], h0 = h0p[gi[i]], h1 = h1p[gi[i]];
+      const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
+      const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
+      const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
+      const float c_re = dot_rn(h0.x, r1.x, h0.y, r1.y), c_im = det_rn(h0.x, r1.y, h0.y, r1.x);
+      const float e_re = dot_rn(h1.x, r0.x, h1.y, r0.y), e_im = det_rn(h1.y, r0.x, h1.x, r0.y);
+      d[i] = make_float2(__fdiv_rn(__fmul_rn(__fadd_rn(a_re, b_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fadd_rn(a_im, b_im), a.k_sq2), den));
+      d[i + 1] = make_float2(__fdiv_rn(__fmul_rn(__fsub_rn(c_re, e_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fsub_rn(c_im, e_im), a.k_sq2), den));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 r = y[gi[i]], h = h0p[gi[i]];
+      const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
+      d[i] = make_float2(__fdiv_rn(dot_rn(r.x, h.x, r.y, h.y), den), __fdiv_rn(det_rn(r.y, h.x, r.x, h.y), den));
+    }
+  }
+  const int q = a.src[m];
+  const uint32_t cb = (a.scramble[q >> 2] >> ((q & 3) * 8)) & 0xFFu;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int l0 = q16(-__fmul_rn(a.k_sqpsk, d[i].x)), l1 = q16(-__fmul_rn(a.k_sqpsk, d[i].y));
+    if ((cb >> (2 * i)) & 1u) l0 = -l0;
+    if ((cb >> (2 * i + 1)) & 1u) l1 = -l1;
+    w[i] = ((uint32_t)l0 & 0xFFFFu) | ((uint32_t)l1 << 16);
+  }
+  *reinterpret_cast<uint4*>(a.llr + (size_t)sf * 8 * a.n_reg + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- K6b: transport-block assembly + CRC24A --------------------------------------------------------
 namespace {
 __device__ __forceinline__ uint32_t gf_mul24(uint32_t x, uint32_t yv, uint32_t poly) {

@@ -49,7 +49,10 @@ struct UeDlGpu {
   int nsc = 0, sf_len = 0;
   uint32_t cfi = 0;       // 0: take the CFI from the PCFICH of every subframe; 1..3: forced by srsue_gpu_ue_dl_set_cfi
   int32_t* d_cfi = nullptr;
-  srsue_gpu_pdsch_plan_t* front[10] = {nullptr};
+  srsue_gpu_pdsch_plan_t* front[10][4] = {{nullptr}};      // front-end plans per (sf_idx, cfi): FFT, estimate, PCFICH, PDCCH
+  int16_t* d_pdcch_llr = nullptr; size_t pdcch_llr_elems = 0;
+  int32_t* d_dci_found = nullptr; uint8_t* d_dci_bits = nullptr;
+  int pdcch_sf = -1, pdcch_cfi = 0, ng_x6 = 6;
   std::map<std::string, srsue_gpu_pdsch_plan_t*> plans;
   srsue_gpu_cf_t *d_iq = nullptr, *d_sf = nullptr, *d_ce = nullptr;
   float* d_meas = nullptr;
@@ -63,6 +66,21 @@ struct UeDlGpu {
   srslte_ra_dl_grant_t grant{};
   cudaStream_t stream = nullptr;
 };
+
+int ng_x6_of(const srslte_cell_t& c) {
+  switch (c.phich_resources) { case SRSLTE_PHICH_R_1_6: return 1; case SRSLTE_PHICH_R_1_2: return 3; case SRSLTE_PHICH_R_1: return 6; default: return 12; }
+}
+
+// front-end-only plan (no grant) of (sf_idx, cfi)
+srsue_gpu_pdsch_plan_t* front_plan(UeDlGpu* u, uint32_t sf_idx, uint32_t cfi) {
+  if (sf_idx > 9 || cfi < 1 || cfi > 3) return nullptr;
+  if (!u->front[sf_idx][cfi]) {
+    srsue_gpu_pdsch_cfg_t c{};
+    c.sf_idx = (int)sf_idx; c.cfi = (int)cfi; c.qm = 2; c.tm = u->cell.nof_ports == 1 ? 1 : 2; c.tbs = 0;
+    if (srsue_gpu_pdsch_plan_create(u->ctx, &u->cell, &c, 1, &u->front[sf_idx][cfi]) != 0) return nullptr;
+  }
+  return u->front[sf_idx][cfi];
+}
 
 int to_gpu_cfg(const srslte_cell_t& cell, const srslte_pdsch_cfg_t* cfg, uint16_t rnti, srsue_gpu_pdsch_cfg_t* out) {
   std::memset(out, 0, sizeof(*out));
@@ -123,6 +141,7 @@ int srslte_ue_dl_init(srslte_ue_dl_t* q, srslte_cell_t cell) {
   auto* u = new UeDlGpu();
   u->ctx = ctx;
   u->cell = srsue_gpu_cell_t{(int)cell.nof_prb, (int)cell.nof_ports, (int)cell.id};
+  u->ng_x6 = ng_x6_of(cell);
   u->nsc = 12 * (int)cell.nof_prb;
   u->sf_len = 15 * symbol_sz((int)cell.nof_prb);
   const size_t grid = (size_t)14 * u->nsc;
@@ -137,6 +156,7 @@ int srslte_ue_dl_init(srslte_ue_dl_t* q, srslte_cell_t cell) {
   q->cell = cell;
   q->pdsch.cell = cell; q->pdsch.gpu = u; q->pdsch.dl_sch.max_iterations = 4;   /* ue.conf.example:83 */
   q->chest.cell = cell; q->chest.gpu = u;
+  q->pdcch.gpu = u;
   q->sf_symbols = (cf_t*)srslte_vec_malloc((uint32_t)(grid * sizeof(cf_t)));
   for (uint32_t p = 0; p < cell.nof_ports; p++) q->ce[p] = (cf_t*)srslte_vec_malloc((uint32_t)(grid * sizeof(cf_t)));
   u->h_sf = q->sf_symbols;
@@ -150,7 +170,8 @@ void srslte_ue_dl_free(srslte_ue_dl_t* q) {
   if (!q) return;
   auto* u = static_cast<UeDlGpu*>(q->gpu);
   if (u) {
-    for (auto& f : u->front) srsue_gpu_pdsch_plan_destroy(f);
+    for (auto& fs : u->front) for (auto& f : fs) srsue_gpu_pdsch_plan_destroy(f);
+    cudaFree(u->d_pdcch_llr); cudaFree(u->d_dci_found); cudaFree(u->d_dci_bits);
     for (auto& kv : u->plans) srsue_gpu_pdsch_plan_destroy(kv.second);
     cudaFree(u->d_iq); cudaFree(u->d_sf); cudaFree(u->d_ce); cudaFree(u->d_meas); cudaFree(u->d_cfi); cudaFree(u->d_payload); cudaFree(u->d_tb_status);
     if (u->stream) cudaStreamDestroy(u->stream);
@@ -175,12 +196,8 @@ void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t* q, uint32_t cfi) {
 int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf_idx, uint32_t* cfi) {
   if (!q || !q->gpu || !input || sf_idx > 9) return SRSLTE_ERROR_INVALID_INPUTS;
   auto* u = static_cast<UeDlGpu*>(q->gpu);
-  if (!u->front[sf_idx]) {
-    srsue_gpu_pdsch_cfg_t c{};
-    c.sf_idx = (int)sf_idx; c.cfi = 1; c.qm = 2; c.tm = u->cell.nof_ports == 1 ? 1 : 2; c.tbs = 0;
-    if (srsue_gpu_pdsch_plan_create(u->ctx, &u->cell, &c, 1, &u->front[sf_idx]) != 0) return SRSLTE_ERROR;
-  }
-  srsue_gpu_pdsch_plan_t* fp = u->front[sf_idx];
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, 1);
+  if (!fp) return SRSLTE_ERROR;
   const size_t grid = (size_t)14 * u->nsc;
   // the IQ buffer is reused by the caller right after we return (phch_worker.cc:254 vs :559,610,641):
   // it is fully consumed (H2D) before the synchronise below
@@ -277,6 +294,76 @@ int srslte_pdsch_decode_rnti(srslte_pdsch_t* q, srslte_pdsch_cfg_t* cfg, srslte_
   q->dl_sch.nof_iterations = (uint32_t)st[2];
   return st[0] ? SRSLTE_SUCCESS : SRSLTE_ERROR;
 }
+
+// ---- PDCCH ------------------------------------------------------------------------------------------------
+int srslte_pdcch_extract_llr(srslte_pdcch_t* q, cf_t* sf_symbols, cf_t* ce[SRSLTE_MAX_PORTS], float noise_estimate, uint32_t nsubframe,
+                             uint32_t cfi) {
+  if (!q || !q->gpu || !sf_symbols || !ce || nsubframe > 9 || cfi < 1 || cfi > 3) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, nsubframe, cfi);
+  if (!fp) return SRSLTE_ERROR;
+  const size_t grid = (size_t)14 * u->nsc;
+  bool own = u->dev_valid && sf_symbols == u->h_sf;
+  for (int pt = 0; pt < u->cell.nof_ports; pt++) own = own && (ce[pt] == u->h_ce[pt]);
+  if (!own) {
+    u->dev_valid = false;
+    cudaMemcpyAsync(u->d_sf, sf_symbols, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+    for (int pt = 0; pt < u->cell.nof_ports; pt++)
+      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+  }
+  int n_reg = 0, n_cce = 0;
+  if (srsue_gpu_pdcch_info(fp, u->ng_x6, &n_reg, &n_cce)) return SRSLTE_ERROR;
+  if ((size_t)8 * n_reg > u->pdcch_llr_elems) {
+    cudaFree(u->d_pdcch_llr);
+    if (cudaMalloc((void**)&u->d_pdcch_llr, (size_t)8 * n_reg * sizeof(int16_t)) != cudaSuccess) return SRSLTE_ERROR;
+    u->pdcch_llr_elems = (size_t)8 * n_reg;
+  }
+  u->pdcch_sf = -1;
+  if (srsue_gpu_pdcch_extract_llr(fp, 1, u->d_sf, u->d_ce, u->d_meas, noise_estimate, 0, u->ng_x6, u->d_pdcch_llr, u->stream)) return SRSLTE_ERROR;
+  u->pdcch_sf = (int)nsubframe; u->pdcch_cfi = (int)cfi;
+  return SRSLTE_SUCCESS;
+}
+
+int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t* q, srslte_dci_msg_t* dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti,
+                                  srslte_rnti_type_t rnti_type) {
+  if (!q || !q->gpu || !dci_msg || sf_idx > 9 || cfi < 1 || cfi > 3) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  if (u->pdcch_sf != (int)sf_idx || u->pdcch_cfi != (int)cfi) return SRSLTE_ERROR;      // srslte_pdcch_extract_llr comes first
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, cfi);
+  if (!fp) return SRSLTE_ERROR;
+  if (!u->d_dci_found && (cudaMalloc((void**)&u->d_dci_found, 4 * sizeof(int32_t)) != cudaSuccess ||
+                          cudaMalloc((void**)&u->d_dci_bits, 64) != cudaSuccess)) return SRSLTE_ERROR;
+  struct Try { int common; srslte_dci_format_t fmt; };
+  const Try user[3] = {{0, SRSLTE_DCI_FORMAT1A}, {0, SRSLTE_DCI_FORMAT1}, {1, SRSLTE_DCI_FORMAT1A}};
+  const Try bcast[1] = {{1, SRSLTE_DCI_FORMAT1A}};
+  const bool is_user = (rnti_type == SRSLTE_RNTI_USER || rnti_type == SRSLTE_RNTI_TEMP || rnti_type == SRSLTE_RNTI_SPS);
+  const Try* tries = is_user ? user : bcast;
+  const int n_tries = is_user ? 3 : 1;
+  for (int i = 0; i < n_tries; i++) {
+    const int nof_bits = dci_format_sizeof(tries[i].fmt == SRSLTE_DCI_FORMAT1A ? 0 : 1, u->cell.nof_prb);
+    const int rc = srsue_gpu_pdcch_find_dci(fp, 1, u->d_pdcch_llr, u->ng_x6, rnti, tries[i].common, nof_bits, u->d_dci_found, u->d_dci_bits,
+                                            nullptr, u->stream);
+    if (rc < 0) { if (tries[i].common) continue; return SRSLTE_ERROR; }
+    int32_t found[4];
+    uint8_t bits[64];
+    cudaMemcpyAsync(found, u->d_dci_found, sizeof(found), cudaMemcpyDeviceToHost, u->stream);
+    cudaMemcpyAsync(bits, u->d_dci_bits, sizeof(bits), cudaMemcpyDeviceToHost, u->stream);
+    if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
+    if (found[0]) {
+      std::memset(dci_msg, 0, sizeof(*dci_msg));
+      std::memcpy(dci_msg->data, bits, (size_t)nof_bits);
+      dci_msg->nof_bits = (uint32_t)nof_bits;
+      dci_msg->format = tries[i].fmt;
+      q->last_location.L = (uint32_t)found[1]; q->last_location.ncce = (uint32_t)found[2];
+      q->last_n_cce = (uint32_t)found[2];
+      q->nof_detected++;
+      return 1;
+    }
+  }
+  return 0;
+}
+
+uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t* q) { return q ? q->last_n_cce : 0; }
 
 void srslte_sch_set_max_noi(srslte_sch_t* q, uint32_t max_iterations) { if (q) q->max_iterations = max_iterations; }
 uint32_t srslte_pdsch_last_noi(srslte_pdsch_t* q) { return q ? q->dl_sch.nof_iterations : 0; }

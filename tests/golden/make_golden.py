@@ -66,6 +66,32 @@ def main():
     pv["digests"] = np.array(digests)
     np.savez_compressed(os.path.join(OUT, "pdsch.npz"), **pv)
     print("\n".join(digests))
+    control()
+
+
+def control():
+    """control region: PCFICH (CFI + correlations) and PDCCH (LLRs of every CCE, the RNTI every search-space candidate
+    decodes to, the blind-search result) of one 25-PRB, 2-port subframe carrying two DCIs at 6 dB"""
+    prb, ports, cid, cfi, sf_idx, rnti, nb = 25, 2, 77, 2, 3, 0x4601, 25
+    cell = o.make_cell(prb, ports, cid)
+    cfg = o.make_cfg(cell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=4, tbs=4968, tm=2)
+    rk, _ = o.pdcch_regs(cell, cfi, 6)
+    ncce = len(rk) // 9
+    ss = o.pdcch_search_space(ncce, sf_idx, rnti)
+    bits = np.random.default_rng(25).integers(0, 2, nb, dtype=np.uint8)
+    other = np.random.default_rng(26).integers(0, 2, nb, dtype=np.uint8)
+    L0, n0 = ss[-1]
+    dcis = [(bits, rnti, L0, n0), (other, 0x0999, 1, 0 if n0 >= 1 else ncce - 1)]
+    tb, iq, _ = o.gen_subframe(cell, cfg, 31337, 6.0, None, pcfich=True, dcis=dcis)
+    sf = o.ofdm_rx(prb, iq)
+    ce, meas = o.chest(cell, sf_idx, sf)
+    got_cfi, corr = o.pcfich_decode(cell, sf_idx, sf, ce, meas[0])
+    llr, nc = o.pdcch_extract_llr(cell, sf_idx, cfi, sf, ce, meas[0])
+    rem = np.array([o.pdcch_decode_candidate(llr[72 * n:], L, nb)[1] for L, n in ss], np.int32)
+    f, out, L1, n1 = o.pdcch_find_dci(llr, nc, sf_idx, rnti, nb)
+    np.savez_compressed(os.path.join(OUT, "control.npz"), iq=iq, cfi=np.array([got_cfi]), corr=corr, llr=llr[:8 * len(rk)],
+                        cand=np.array(ss, np.int32), rem=rem, found=np.array([f, L1, n1]), bits=out, sent=bits)
+    print("control: cfi", got_cfi, "corr", corr, "found", f, L1, n1, "sent at", L0, n0)
 
 
 if __name__ == "__main__":

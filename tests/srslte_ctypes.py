@@ -45,7 +45,11 @@ class Chest(C.Structure):
 
 
 class Pdcch(C.Structure):
-    _fields_ = [("unused", C.c_int)]
+    _fields_ = [("gpu", C.c_void_p)]
+
+
+class DciMsg(C.Structure):
+    _fields_ = [("data", C.c_uint8 * 128), ("nof_bits", C.c_uint32), ("format", C.c_int)]
 
 
 class DciLocation(C.Structure):

@@ -41,7 +41,8 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_chest_dl_get_noise_estimate", "srslte_softbuffer_rx_init", "srslte_softbuffer_rx_reset",
               "srslte_softbuffer_rx_reset_tbs", "srslte_softbuffer_rx_free", "srslte_ue_dl_decode", "srslte_ue_dl_decode_rnti",
               "srslte_tdec_init", "srslte_tdec_free", "srslte_tdec_reset", "srslte_tdec_iteration", "srslte_tdec_decision",
-              "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz"]:
+              "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz",
+              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_get_ncce"]:
         assert hasattr(lib, n), n
 
 
@@ -115,3 +116,40 @@ def test_host_pcfich_mapping_matches_oracle():
             ref = o.pcfich_re(o.make_cell(prb, 2, cid))
             assert np.array_equal(k, ref)
             assert len(set(k.tolist())) == 16 and all(x % 3 != cid % 3 for x in k)
+
+
+def test_host_pdcch_tables_match_oracle():
+    """control-region REG map (PCFICH / PHICH groups excluded), quadruplet interleaver + cyclic shift, search spaces and
+    DCI sizes of the library against the oracle / the published format sizes"""
+    import ctypes as C
+    import numpy as np
+    import srsue_b200 as sg
+    from oracle import oracle as o
+    L = sg.lib()
+    for prb in (6, 15, 25, 50, 75, 100):
+        for cid in (0, 1, 77, 301, 503):
+            ocell = o.make_cell(prb, 2, cid)
+            cell = sg.make_cell(prb, 2, cid)
+            for cfi in (1, 2, 3):
+                for ng in (1, 3, 6, 12):
+                    rk, rl = o.pdcch_regs(ocell, cfi, ng)
+                    re4 = np.zeros(4 * 12 * prb, np.int32)
+                    n = L.srsue_gpu_host_pdcch_regs(C.byref(cell), cfi, ng, re4.ctypes.data_as(C.c_void_p))
+                    assert n == len(rk)
+                    exp = []
+                    for k0, l in zip(rk.tolist(), rl.tolist()):
+                        ks = [k0 + j for j in range(6) if (k0 + j) % 3 != cid % 3] if l == 0 else [k0 + j for j in range(4)]
+                        exp += [l * 12 * prb + k for k in ks]
+                    assert re4[:4 * n].tolist() == exp
+                src = np.zeros(n, np.int32)
+                assert L.srsue_gpu_host_pdcch_quad_perm(n, cid, src.ctypes.data_as(C.c_void_p)) == 0
+                assert np.array_equal(src, o.pdcch_quad_perm(n, cid))
+                for common in (0, 1):
+                    for sf in (0, 4, 9):
+                        cl, cn = np.zeros(32, np.int32), np.zeros(32, np.int32)
+                        m = L.srsue_gpu_host_pdcch_search_space(n // 9, sf, 0x1234 + cid, common, cl.ctypes.data_as(C.c_void_p),
+                                                                cn.ctypes.data_as(C.c_void_p))
+                        assert list(zip(cl[:m].tolist(), cn[:m].tolist())) == o.pdcch_search_space(n // 9, sf, 0x1234 + cid, bool(common))
+    # 36.212 5.3.3.1 sizes (FDD): format 1A / format 1 at 1.4, 3, 5, 10, 15, 20 MHz
+    assert [L.srsue_gpu_host_dci_format_sizeof(0, p) for p in (6, 15, 25, 50, 75, 100)] == [21, 22, 25, 27, 27, 28]
+    assert [L.srsue_gpu_host_dci_format_sizeof(1, p) for p in (6, 15, 25, 50, 75, 100)] == [19, 23, 27, 31, 33, 39]

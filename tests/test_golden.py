@@ -62,6 +62,62 @@ def test_oracle_reproduces_digests(oracle, idx, name, prb, ports, qm, tbs, tm, s
     assert ",".join(map(str, dbg["iters"])) == want["iters"] and rc == int(want["rc"])
 
 
+CTRL = dict(prb=25, ports=2, cid=77, cfi=2, sf_idx=3, rnti=0x4601, nb=25)
+
+
+def test_oracle_reproduces_control_golden(oracle):
+    o = oracle
+    cv = np.load(os.path.join(G, "control.npz"))
+    c = CTRL
+    cell = o.make_cell(c["prb"], c["ports"], c["cid"])
+    sf = o.ofdm_rx(c["prb"], cv["iq"])
+    ce, meas = o.chest(cell, c["sf_idx"], sf)
+    cfi, corr = o.pcfich_decode(cell, c["sf_idx"], sf, ce, meas[0])
+    assert cfi == int(cv["cfi"][0]) == c["cfi"] and np.array_equal(corr, cv["corr"])
+    llr, nc = o.pdcch_extract_llr(cell, c["sf_idx"], cfi, sf, ce, meas[0])
+    assert np.array_equal(llr[:len(cv["llr"])], cv["llr"])
+    ss = o.pdcch_search_space(nc, c["sf_idx"], c["rnti"])
+    assert np.array_equal(np.array(ss, np.int32), cv["cand"])
+    assert [o.pdcch_decode_candidate(llr[72 * n:], L, c["nb"])[1] for L, n in ss] == cv["rem"].tolist()
+    f, out, L1, n1 = o.pdcch_find_dci(llr, nc, c["sf_idx"], c["rnti"], c["nb"])
+    assert [f, L1, n1] == cv["found"].tolist() and f == 1 and np.array_equal(out, cv["bits"]) and np.array_equal(out, cv["sent"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_control_golden(gpu):
+    import torch
+    sg, ctx = gpu
+    cv = np.load(os.path.join(G, "control.npz"))
+    c = CTRL
+    cell = sg.make_cell(c["prb"], c["ports"], c["cid"])
+    cfg = sg.make_cfg(cell, sf_idx=c["sf_idx"], cfi=c["cfi"], qm=2, tbs=0, tm=2)
+    plan = sg.PdschPlan(ctx, cell, cfg, 1)
+    I = plan.info
+    n_reg, ncce = plan.pdcch_info(6)
+    d_iq = torch.from_numpy(cv["iq"].view(np.float32).reshape(1, -1)).cuda()
+    d_sf = torch.zeros((1, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((1, 2 * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((1, 5), dtype=torch.float32, device="cuda")
+    d_cfi = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_corr = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    d_llr = torch.zeros((1, 8 * n_reg), dtype=torch.int16, device="cuda")
+    d_found = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    d_bits = torch.zeros((1, 64), dtype=torch.uint8, device="cuda")
+    d_rem = torch.zeros((1, 24), dtype=torch.uint16, device="cuda")
+    plan.ofdm_rx(1, d_iq, d_sf)
+    plan.chest(1, d_sf, d_ce, d_meas)
+    plan.pcfich_decode(1, d_sf, d_ce, d_meas, 0.0, 1, d_cfi, d_corr)
+    plan.pdcch_extract_llr(1, d_sf, d_ce, d_meas, 0.0, 1, d_llr)
+    ncand = plan.pdcch_find_dci(1, d_llr, c["rnti"], c["nb"], d_found, d_bits, d_rem)
+    torch.cuda.synchronize()
+    assert int(d_cfi.cpu()[0]) == int(cv["cfi"][0]) and np.array_equal(d_corr.cpu().numpy()[0], cv["corr"])
+    assert np.array_equal(d_llr.cpu().numpy()[0], cv["llr"])
+    assert ncand == len(cv["cand"]) and d_rem.cpu().numpy()[0, :ncand].astype(np.int32).tolist() == cv["rem"].tolist()
+    found = d_found.cpu().numpy()[0]
+    assert found[:3].tolist() == cv["found"].tolist() and np.array_equal(d_bits.cpu().numpy()[0, :c["nb"]], cv["bits"])
+    plan.close()
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_turbo_golden(gpu):
     import torch

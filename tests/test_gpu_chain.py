@@ -121,6 +121,63 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     L.srslte_ue_dl_free(C.byref(q))
 
 
+@pytest.mark.parametrize("prb,ports,fmt", [(25, 1, "1A"), (50, 2, "1"), (100, 1, "1A")])
+def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
+    """work_imp's downlink sequence (phch_worker.cc:254-348) with nothing supplied by the caller but the RNTI:
+    decode_fft_estimate -> CFI, pdcch_extract_llr, find_dl_dci_type -> DCI bits + CCE location, then cfg_grant +
+    pdsch_decode_rnti with the grant the test's stand-in for srslte_dci_msg_to_dl_grant derives."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, SoftBuffer, DciMsg, make_grant
+    qm, tbs, cfi, sf_idx, rnti = 4, 4968 if prb == 25 else 6208, 2, 3, 0x4601
+    nb = L.srsue_gpu_host_dci_format_sizeof(0 if fmt == "1A" else 1, prb)
+    ocell = o.make_cell(prb, ports, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs, tm=ports)
+    rk, _ = o.pdcch_regs(ocell, cfi, 6)
+    ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti)
+    L0, n0 = ss[-1]                                               # the last (largest) candidate of the UE-specific space
+    dci_bits = np.random.default_rng(prb).integers(0, 2, nb, dtype=np.uint8)
+    other = np.random.default_rng(1).integers(0, 2, nb, dtype=np.uint8)
+    dcis = [(dci_bits, rnti, L0, n0)]
+    if n0 >= 1:
+        dcis.append((other, 0x0999, 1, 0))                        # somebody else's DCI in the same control region
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 555, 20.0, None, pcfich=True, dcis=dcis)
+    q = UeDl()
+    cell = Cell(nof_prb=prb, nof_ports=ports, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)     # Ng = 1
+    assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+    L.srslte_ue_dl_set_rnti(C.byref(q), rnti)
+    sb = SoftBuffer()
+    assert L.srslte_softbuffer_rx_init(C.byref(sb), prb) == 0
+    L.srslte_softbuffer_rx_reset(C.byref(sb))
+    got_cfi = C.c_uint32(0)
+    assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), iq.ctypes.data_as(C.c_void_p), sf_idx, C.byref(got_cfi)) == 0
+    assert got_cfi.value == cfi
+    assert L.srslte_pdcch_extract_llr(C.byref(q.pdcch), q.sf_symbols, q.ce, C.c_float(0.0), sf_idx, got_cfi.value) == 0
+    msg = DciMsg()
+    assert L.srslte_ue_dl_find_dl_dci_type(C.byref(q), C.byref(msg), got_cfi.value, sf_idx, rnti, 0) == 1
+    assert msg.nof_bits == nb and np.array_equal(np.frombuffer(msg.data, np.uint8)[:nb], dci_bits)
+    assert n0 <= L.srslte_ue_dl_get_ncce(C.byref(q)) < n0 + L0
+    # the same search in the oracle (ZF equaliser: noise 0, as phch_worker.cc:260 passes)
+    sf_o = o.ofdm_rx(prb, iq)
+    ce_o, _ = o.chest(ocell, sf_idx, sf_o)
+    llr_o, ncce = o.pdcch_extract_llr(ocell, sf_idx, cfi, sf_o, ce_o, 0.0)
+    f, out, L1, n1 = o.pdcch_find_dci(llr_o, ncce, sf_idx, rnti, nb)
+    assert f == 1 and np.array_equal(out, dci_bits) and (q.last_location.L, q.last_location.ncce) == (L1, n1)
+    # a different RNTI finds nothing
+    assert L.srslte_ue_dl_find_dl_dci_type(C.byref(q), C.byref(msg), got_cfi.value, sf_idx, 0x0777, 0) == 0
+    # grant -> PDSCH
+    grant = make_grant(prb, qm, tbs)
+    assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), got_cfi.value, sf_idx, 0) == 0
+    payload = np.zeros(tbs // 8, np.uint8)
+    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), q.sf_symbols, q.ce,
+                                     C.c_float(0.01), C.c_uint16(rnti), payload.ctypes.data_as(C.c_void_p))
+    assert ret == 0 and np.array_equal(payload, tb)
+    L.srslte_softbuffer_rx_free(C.byref(sb))
+    L.srslte_ue_dl_free(C.byref(q))
+
+
 @pytest.mark.parametrize("cfi", [1, 2, 3])
 def test_srslte_ue_dl_decode_wrapper_cfg1(gpu, oracle, cfi):
     """BASELINE configs[0]: a 1.4 MHz TM1 QPSK MCS 0 subframe through srslte_ue_dl_decode (the wrapper the north star

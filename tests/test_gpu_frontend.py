@@ -227,3 +227,70 @@ def test_pcfich_matches_oracle(gpu, oracle, prb, ports, cid):
             if snr > 0:
                 assert ref == cfi
         plan.close()
+
+
+@pytest.mark.parametrize("prb,ports,cid,cfi", [(6, 1, 1, 3), (15, 2, 77, 2), (25, 1, 301, 2), (50, 2, 5, 1), (75, 1, 8, 3), (100, 1, 503, 1),
+                                               (100, 2, 0, 3)])
+def test_pdcch_matches_oracle(gpu, oracle, prb, ports, cid, cfi):
+    """PDCCH on the device: the LLRs of every control-channel element, the RNTI every search-space candidate decodes to
+    (rate de-matching + tail-biting Viterbi + CRC16) and the blind-search verdict equal the oracle's, with DCIs present
+    at a reliable SNR and in a subframe that is mostly noise."""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    ocell = o.make_cell(prb, ports, cid)
+    cell = sg.make_cell(prb, ports, cid)
+    sf_idx, rnti = (cid + cfi) % 10, 0x1234 + cid
+    nb = sg.lib().srsue_gpu_host_dci_format_sizeof(0, prb)
+    rk, _ = o.pdcch_regs(ocell, cfi, 6)
+    ncce = len(rk) // 9
+    ss = o.pdcch_search_space(ncce, sf_idx, rnti)
+    rng = np.random.default_rng(cid)
+    n = 4
+    for snr in (8.0, -3.0):
+        iq, sent = [], []
+        for i in range(n):
+            L0, n0 = ss[(3 * i + 1) % len(ss)]
+            bits = rng.integers(0, 2, nb, dtype=np.uint8)
+            dcis = [(bits, rnti, L0, n0)] if i != 2 else []         # subframe 2 carries no DCI for this UE
+            ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, qm=2, tbs=152 if prb == 6 else 1000, tm=ports)
+            iq.append(o.gen_subframe(ocell, ocfg, 4000 + i, snr, None, pcfich=True, dcis=dcis)[1])
+            sent.append(dcis)
+        iq = np.stack(iq)
+        cfg = sg.make_cfg(cell, sf_idx=sf_idx, cfi=cfi, qm=2, tbs=0, tm=ports)
+        plan = sg.PdschPlan(ctx, cell, cfg, n)
+        I = plan.info
+        n_reg, nc = plan.pdcch_info(6)
+        assert n_reg == len(rk) and nc == ncce
+        d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+        d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+        d_llr = torch.zeros((n, 8 * n_reg), dtype=torch.int16, device="cuda")
+        d_found = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+        d_bits = torch.zeros((n, 64), dtype=torch.uint8, device="cuda")
+        d_rem = torch.zeros((n, 24), dtype=torch.uint16, device="cuda")
+        plan.ofdm_rx(n, d_iq, d_sf)
+        plan.chest(n, d_sf, d_ce, d_meas)
+        plan.pdcch_extract_llr(n, d_sf, d_ce, d_meas, 0.0, 1, d_llr)
+        ncand = plan.pdcch_find_dci(n, d_llr, rnti, nb, d_found, d_bits, d_rem)
+        torch.cuda.synchronize()
+        assert ncand == len(ss)
+        llr_g, found, bits_g = d_llr.cpu().numpy(), d_found.cpu().numpy(), d_bits.cpu().numpy()
+        rem = d_rem.cpu().numpy().reshape(-1)[:n * ncand].reshape(n, ncand)
+        for i in range(n):
+            sf_o = o.ofdm_rx(prb, iq[i])
+            ce_o, meas_o = o.chest(ocell, sf_idx, sf_o)
+            llr_o, _ = o.pdcch_extract_llr(ocell, sf_idx, cfi, sf_o, ce_o, meas_o[0])
+            assert np.array_equal(llr_g[i], llr_o[:8 * n_reg])
+            for c, (L0, n0) in enumerate(ss):
+                assert rem[i, c] == o.pdcch_decode_candidate(llr_o[72 * n0:], L0, nb)[1]
+            f, out, L1, n1 = o.pdcch_find_dci(llr_o, ncce, sf_idx, rnti, nb)
+            assert found[i, 0] == f
+            if f:
+                assert (found[i, 1], found[i, 2]) == (L1, n1) and np.array_equal(bits_g[i, :nb], out)
+            if snr > 0:
+                assert f == (1 if sent[i] else 0)
+                if f:
+                    assert np.array_equal(out, sent[i][0][0])
+        plan.close()
