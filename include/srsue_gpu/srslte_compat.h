@@ -173,6 +173,8 @@ SRSLTE_API int srslte_pdcch_extract_llr(srslte_pdcch_t *q, cf_t *sf_symbols, cf_
                                         uint32_t nsubframe, uint32_t cfi);
 SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx,
                                              uint16_t rnti, srslte_rnti_type_t rnti_type);
+/* uplink grant search (phch_worker.cc:426): DCI format 0 in the UE-specific space; 1 found / 0 / < 0 */
+SRSLTE_API int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti);
 SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);
 /* wrappers the north star names; the DCI search is a "next" row, so the grant to use is the one last
  * installed with srsue_gpu_ue_dl_set_grant().  Return decoded bits (tbs) / 0 (no grant) / < 0. */

@@ -112,13 +112,15 @@ int srsue_gpu_pcfich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_
  * _info: REGs and CCEs available to PDCCH.  _extract_llr: d_llr [n_sf][8 * n_reg] int16, 72 per CCE in CCE order.
  * _find_dci: blind search of the UE-specific (common = 0) or common search space for a payload of nof_bits bits whose
  * CRC is masked with rnti; d_found [n_sf][4] = {found, L, first CCE, candidate index}, d_bits [n_sf][64] one bit per
- * byte, d_rem optional [n_sf][candidates] = the RNTI each candidate decodes to.  Returns the number of candidates. */
+ * byte, d_rem optional [n_sf][candidates] = the RNTI each candidate decodes to.  first_bit: -1, or the value payload
+ * bit 0 must have (formats 0 and 1A share size and search space; the flag tells them apart).  Returns the number of
+ * candidates. */
 int srsue_gpu_pdcch_info(srsue_gpu_pdsch_plan_t *plan, int ng_x6, int *n_reg, int *nof_cce);
 int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
                                 const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int ng_x6,
                                 int16_t *d_llr, void *stream);
 int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_llr, int ng_x6, int rnti, int common,
-                             int nof_bits, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
+                             int nof_bits, int first_bit, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
 /* equalise + demap + descramble + rate-dematch into d_softbuf [n_sf][sb_sf_stride].  noise_mode 0: use
  * noise_est (srsUE passes 0.01), 1: use d_meas[.][0].  accumulate 0: new transmission, 1: HARQ combine.
  * d_dbg_d [n_sf][nof_re] / d_dbg_e [n_sf][G] optional taps of the equalised symbols / descrambled LLRs. */

@@ -160,8 +160,8 @@ class PdschPlan:
         _check(lib().srsue_gpu_pdcch_extract_llr(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                                  ng_x6, _ptr(d_llr), _stream()), "pdcch_extract_llr")
 
-    def pdcch_find_dci(self, n_sf, d_llr, rnti, nof_bits, d_found, d_bits, d_rem=None, common=0, ng_x6=6):
-        n = lib().srsue_gpu_pdcch_find_dci(self.h, n_sf, _ptr(d_llr), ng_x6, rnti, common, nof_bits, _ptr(d_found), _ptr(d_bits),
+    def pdcch_find_dci(self, n_sf, d_llr, rnti, nof_bits, d_found, d_bits, d_rem=None, common=0, ng_x6=6, first_bit=-1):
+        n = lib().srsue_gpu_pdcch_find_dci(self.h, n_sf, _ptr(d_llr), ng_x6, rnti, common, nof_bits, first_bit, _ptr(d_found), _ptr(d_bits),
                                            _ptr(d_rem), _stream())
         if n < 0:
             _check(n, "pdcch_find_dci")

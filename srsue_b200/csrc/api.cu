@@ -658,7 +658,7 @@ int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue
 }
 
 int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_llr, int ng_x6, int rnti, int common, int nof_bits,
-                             int32_t* d_found, uint8_t* d_bits, uint16_t* d_rem, void* stream) {
+                             int first_bit, int32_t* d_found, uint8_t* d_bits, uint16_t* d_rem, void* stream) {
   PLAN_CHECK(p, n_sf);
   if (!d_llr || !d_found || !d_bits) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: null buffer");
   if (nof_bits < 8 || nof_bits > 64 || rnti < 0 || rnti > 0xFFFF) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: nof_bits must be 8..64");
@@ -675,7 +675,7 @@ int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t*
   }
   PdcchSearchArgs a{};
   a.llr = d_llr; a.llr_stride = 8LL * p->pd_nreg; a.rm_seq = it->second; a.found = d_found; a.bits = d_bits; a.rem = d_rem;
-  a.n_sf = n_sf; a.nof_bits = nof_bits; a.rnti = rnti;
+  a.n_sf = n_sf; a.nof_bits = nof_bits; a.rnti = rnti; a.first_bit = first_bit < 0 ? -1 : (first_bit ? 1 : 0);
   a.n_cand = pdcch_search_space(p->pd_nreg / 9, p->cfg.sf_idx, (uint16_t)rnti, common != 0, a.cand_L, a.cand_ncce);
   if (a.n_cand == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: empty search space");
   const int per_words = 3 * D + 4 * D + (D + 3) / 4;

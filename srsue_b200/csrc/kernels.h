@@ -122,6 +122,7 @@ struct PdcchSearchArgs {
   uint8_t* bits;             // [n_sf][64]: payload of the match, one bit per byte
   uint16_t* rem;             // optional [n_sf][n_cand]: RNTI every candidate decodes to
   int n_sf, n_cand, nof_bits, rnti;
+  int first_bit;             // -1: any; 0 / 1: a match also needs this value in payload bit 0 (format 0 / 1A flag)
   int cand_L[kPdcchMaxCand], cand_ncce[kPdcchMaxCand];
 };
 __global__ void pdcch_search_kernel(const PdcchSearchArgs a);

@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(32 * kPdcchMaxCand) pdcch_search_kernel(const 
       for (int i = 0; i < 16; i++) { reg <<= 1; if (reg & 0x10000u) reg ^= 0x11021u; }
       uint32_t rx = 0;
       for (int i = 0; i < 16; i++) rx = (rx << 1) | dec[a.nof_bits + i];
-      s_rem[w] = (int)((reg ^ rx) & 0xFFFFu);
-      if (a.rem) a.rem[(size_t)sf * a.n_cand + w] = (uint16_t)s_rem[w];
+      const int rem = (int)((reg ^ rx) & 0xFFFFu);
+      if (a.rem) a.rem[(size_t)sf * a.n_cand + w] = (uint16_t)rem;
+      // formats 0 and 1A share size and search space and differ in payload bit 0: a wrong flag is not a match
+      s_rem[w] = (a.first_bit >= 0 && dec[0] != a.first_bit) ? -1 : rem;
     }
   }
   __syncthreads();

@@ -324,6 +324,43 @@ int srslte_pdcch_extract_llr(srslte_pdcch_t* q, cf_t* sf_symbols, cf_t* ce[SRSLT
   return SRSLTE_SUCCESS;
 }
 
+namespace {
+// one blind search; returns 1 found / 0 not found / < 0 error and fills dci_msg + the location fields of q
+int dci_search(srslte_ue_dl_t* q, UeDlGpu* u, srsue_gpu_pdsch_plan_t* fp, srslte_dci_msg_t* dci_msg, uint16_t rnti, int common,
+               srslte_dci_format_t fmt, int first_bit) {
+  const int nof_bits = dci_format_sizeof(fmt == SRSLTE_DCI_FORMAT1 ? 1 : 0, u->cell.nof_prb);     // format 0 is padded to 1A's size
+  const int rc = srsue_gpu_pdcch_find_dci(fp, 1, u->d_pdcch_llr, u->ng_x6, rnti, common, nof_bits, first_bit, u->d_dci_found,
+                                          u->d_dci_bits, nullptr, u->stream);
+  if (rc < 0) return common ? 0 : SRSLTE_ERROR;          // a control region smaller than 4 CCEs has no common space
+  int32_t found[4];
+  uint8_t bits[64];
+  cudaMemcpyAsync(found, u->d_dci_found, sizeof(found), cudaMemcpyDeviceToHost, u->stream);
+  cudaMemcpyAsync(bits, u->d_dci_bits, sizeof(bits), cudaMemcpyDeviceToHost, u->stream);
+  if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  if (!found[0]) return 0;
+  std::memset(dci_msg, 0, sizeof(*dci_msg));
+  std::memcpy(dci_msg->data, bits, (size_t)nof_bits);
+  dci_msg->nof_bits = (uint32_t)nof_bits;
+  dci_msg->format = fmt;
+  q->last_location.L = (uint32_t)found[1]; q->last_location.ncce = (uint32_t)found[2];
+  q->last_n_cce = (uint32_t)found[2];
+  q->nof_detected++;
+  return 1;
+}
+}  // namespace
+
+// uplink grants (phch_worker.cc:426): DCI format 0 in the UE-specific space, same size as 1A, flag bit 0
+int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t* q, srslte_dci_msg_t* dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti) {
+  if (!q || !q->gpu || !dci_msg || sf_idx > 9 || cfi < 1 || cfi > 3) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  if (u->pdcch_sf != (int)sf_idx || u->pdcch_cfi != (int)cfi) return SRSLTE_ERROR;
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, cfi);
+  if (!fp) return SRSLTE_ERROR;
+  if (!u->d_dci_found && (cudaMalloc((void**)&u->d_dci_found, 4 * sizeof(int32_t)) != cudaSuccess ||
+                          cudaMalloc((void**)&u->d_dci_bits, 64) != cudaSuccess)) return SRSLTE_ERROR;
+  return dci_search(q, u, fp, dci_msg, rnti, 0, SRSLTE_DCI_FORMAT0, 0);
+}
+
 int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t* q, srslte_dci_msg_t* dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti,
                                   srslte_rnti_type_t rnti_type) {
   if (!q || !q->gpu || !dci_msg || sf_idx > 9 || cfi < 1 || cfi > 3) return SRSLTE_ERROR_INVALID_INPUTS;
@@ -340,25 +377,8 @@ int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t* q, srslte_dci_msg_t* dci_msg, 
   const Try* tries = is_user ? user : bcast;
   const int n_tries = is_user ? 3 : 1;
   for (int i = 0; i < n_tries; i++) {
-    const int nof_bits = dci_format_sizeof(tries[i].fmt == SRSLTE_DCI_FORMAT1A ? 0 : 1, u->cell.nof_prb);
-    const int rc = srsue_gpu_pdcch_find_dci(fp, 1, u->d_pdcch_llr, u->ng_x6, rnti, tries[i].common, nof_bits, u->d_dci_found, u->d_dci_bits,
-                                            nullptr, u->stream);
-    if (rc < 0) { if (tries[i].common) continue; return SRSLTE_ERROR; }
-    int32_t found[4];
-    uint8_t bits[64];
-    cudaMemcpyAsync(found, u->d_dci_found, sizeof(found), cudaMemcpyDeviceToHost, u->stream);
-    cudaMemcpyAsync(bits, u->d_dci_bits, sizeof(bits), cudaMemcpyDeviceToHost, u->stream);
-    if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
-    if (found[0]) {
-      std::memset(dci_msg, 0, sizeof(*dci_msg));
-      std::memcpy(dci_msg->data, bits, (size_t)nof_bits);
-      dci_msg->nof_bits = (uint32_t)nof_bits;
-      dci_msg->format = tries[i].fmt;
-      q->last_location.L = (uint32_t)found[1]; q->last_location.ncce = (uint32_t)found[2];
-      q->last_n_cce = (uint32_t)found[2];
-      q->nof_detected++;
-      return 1;
-    }
+    const int rc = dci_search(q, u, fp, dci_msg, rnti, tries[i].common, tries[i].fmt, tries[i].fmt == SRSLTE_DCI_FORMAT1A ? 1 : -1);
+    if (rc) return rc;
   }
   return 0;
 }

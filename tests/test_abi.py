@@ -42,7 +42,7 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_softbuffer_rx_reset_tbs", "srslte_softbuffer_rx_free", "srslte_ue_dl_decode", "srslte_ue_dl_decode_rnti",
               "srslte_tdec_init", "srslte_tdec_free", "srslte_tdec_reset", "srslte_tdec_iteration", "srslte_tdec_decision",
               "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz",
-              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_get_ncce"]:
+              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce"]:
         assert hasattr(lib, n), n
 
 

@@ -139,10 +139,19 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti)
     L0, n0 = ss[-1]                                               # the last (largest) candidate of the UE-specific space
     dci_bits = np.random.default_rng(prb).integers(0, 2, nb, dtype=np.uint8)
+    dci_bits[0] = 1                                               # format 0 / 1A flag: 1 = format 1A
     other = np.random.default_rng(1).integers(0, 2, nb, dtype=np.uint8)
     dcis = [(dci_bits, rnti, L0, n0)]
     if n0 >= 1:
         dcis.append((other, 0x0999, 1, 0))                        # somebody else's DCI in the same control region
+    # an uplink grant (format 0: the size of 1A, flag 0) for the same RNTI on an earlier candidate of the search space
+    nb0 = L.srsue_gpu_host_dci_format_sizeof(0, prb)
+    ul_bits = np.random.default_rng(7).integers(0, 2, nb0, dtype=np.uint8)
+    ul_bits[0] = 0
+    taken = set(range(n0, n0 + L0)) | ({0} if n0 >= 1 else set())
+    ul_at = next(((Lc, nc) for Lc, nc in ss if Lc == 2 and taken.isdisjoint(range(nc, nc + Lc))), None)
+    if ul_at:
+        dcis.append((ul_bits, rnti, ul_at[0], ul_at[1]))
     tb, iq, _ = o.gen_subframe(ocell, ocfg, 555, 20.0, None, pcfich=True, dcis=dcis)
     q = UeDl()
     cell = Cell(nof_prb=prb, nof_ports=ports, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)     # Ng = 1
@@ -163,10 +172,20 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     sf_o = o.ofdm_rx(prb, iq)
     ce_o, _ = o.chest(ocell, sf_idx, sf_o)
     llr_o, ncce = o.pdcch_extract_llr(ocell, sf_idx, cfi, sf_o, ce_o, 0.0)
-    f, out, L1, n1 = o.pdcch_find_dci(llr_o, ncce, sf_idx, rnti, nb)
-    assert f == 1 and np.array_equal(out, dci_bits) and (q.last_location.L, q.last_location.ncce) == (L1, n1)
+    cands = []                     # the oracle's matches in search-space order, with the shim's format-flag rule
+    for Lc, nc in o.pdcch_search_space(ncce, sf_idx, rnti):
+        b, r = o.pdcch_decode_candidate(llr_o[72 * nc:], Lc, nb)
+        if r == rnti and (fmt != "1A" or b[0] == 1):
+            cands.append((Lc, nc, b))
+    assert cands and (q.last_location.L, q.last_location.ncce) == cands[0][:2] and np.array_equal(cands[0][2], dci_bits)
     # a different RNTI finds nothing
     assert L.srslte_ue_dl_find_dl_dci_type(C.byref(q), C.byref(msg), got_cfi.value, sf_idx, 0x0777, 0) == 0
+    # the uplink grant of the same subframe (phch_worker.cc:426)
+    if ul_at:
+        ul = DciMsg()
+        assert L.srslte_ue_dl_find_ul_dci(C.byref(q), C.byref(ul), got_cfi.value, sf_idx, rnti) == 1
+        assert ul.nof_bits == nb0 and np.array_equal(np.frombuffer(ul.data, np.uint8)[:nb0], ul_bits)
+        assert ul_at[1] <= q.last_location.ncce < ul_at[1] + ul_at[0]
     # grant -> PDSCH
     grant = make_grant(prb, qm, tbs)
     assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), got_cfi.value, sf_idx, 0) == 0
