@@ -261,3 +261,67 @@ def test_cpp_offline_driver_worker_and_batch(gpu, oracle, tmp_path):
             assert np.array_equal(payload, pl), (mode, i)
             assert abs(snr - meas[4]) <= 1e-4 * meas[4]
     assert ref[2][0] != 0 and ref[0][0] == 0      # the noisy subframe fails, the others decode
+
+
+def _random_cases(n, seed):
+    """random cells / grants: every bandwidth, 1-2 ports, all modulations, partial and scattered PRB allocations, every
+    subframe number (0 and 5 lose PSS/SSS/PBCH REs), every CFI, random cell ids and RNTIs, code rates 0.1 .. 0.9"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        prb = int(rng.choice([6, 15, 25, 50, 75, 100]))
+        ports = int(rng.integers(1, 3))
+        qm = int(rng.choice([2, 4, 6]))
+        cid = int(rng.integers(0, 504))
+        sf = int(rng.integers(0, 10))
+        cfi = int(rng.integers(1, 4))
+        nalloc = int(rng.integers(max(1, prb // 8), prb + 1))
+        prbs = sorted(rng.choice(prb, nalloc, replace=False).tolist()) if rng.random() < 0.5 else list(range(int(rng.integers(0, prb - nalloc + 1)), 0))
+        if not prbs:
+            start = int(rng.integers(0, prb - nalloc + 1))
+            prbs = list(range(start, start + nalloc))
+        out.append(dict(prb=prb, ports=ports, qm=qm, cid=cid, sf=sf, cfi=cfi, prbs=prbs, rnti=int(rng.integers(1, 65520)),
+                        rate=float(rng.uniform(0.1, 0.9)), seed=int(rng.integers(1, 1 << 30))))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases(24, 20261018), ids=lambda c: "%dprb_%dp_qm%d_sf%d_cfi%d_n%d" % (
+    c["prb"], c["ports"], c["qm"], c["sf"], c["cfi"], len(c["prbs"])))
+def test_random_grants_match_oracle(gpu, oracle, case):
+    """whole chain on randomly drawn cells and grants, noise around the decoding threshold of each so that both CRC
+    verdicts occur: payload, verdict, iteration count and measurements equal the oracle's for every subframe"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    c = case
+    tm = 1 if c["ports"] == 1 else 2
+    ocell = o.make_cell(c["prb"], c["ports"], c["cid"])
+    probe = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=40, tm=tm, prbs=c["prbs"])
+    nre = len(o.pdsch_re_list(ocell, probe))
+    if tm == 2:
+        nre -= nre % 2
+    tbs = max(40, int(c["rate"] * nre * c["qm"]) // 8 * 8 - 24)
+    tbs = min(tbs, 75376)
+    ocfg = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=tm, prbs=c["prbs"])
+    cell = sg.make_cell(c["prb"], c["ports"], c["cid"])
+    cfg = sg.make_cfg(cell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=tm, prbs=c["prbs"])
+    # Es/N0 near the Shannon limit of the spectral efficiency + margin, one subframe above and one below
+    eff = tbs / max(nre, 1)
+    base = 10 * np.log10(2 ** eff - 1) + 2.5
+    n = 3
+    iq = np.stack([o.gen_subframe(ocell, ocfg, c["seed"] + i, base + d, _taps() if (tm == 2 and i == 1) else None)[1]
+                   for i, d in enumerate((6.0, 1.0, -4.0))])
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    assert I.nof_re == len(o.pdsch_re_list(ocell, ocfg))
+    h_pl = np.zeros((n, I.payload_stride), np.uint8)
+    h_st = np.zeros((n, 4), np.int32)
+    h_meas = np.zeros((n, 5), np.float32)
+    plan.decode_batch_host(n, iq, 0.01, 1, 5, h_pl, h_st, h_meas)
+    for i in range(n):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 1, 5)
+        assert (h_st[i, 0] == 1) == (rc == 0), "CRC verdict differs (sf %d)" % i
+        assert np.array_equal(h_pl[i], pl), "transport block differs (sf %d)" % i
+        assert h_st[i, 2] == avg
+        assert np.allclose(h_meas[i], meas, rtol=1e-4)
+    plan.close()
