@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "srsue_gpu/srslte_compat.h"
@@ -71,9 +73,11 @@ int run_worker(const Header& h, cf_t* iq, FILE* out) {
   grant.nof_prb = h.nof_prb; grant.Qm = h.qm; grant.mcs.tbs = h.tbs;
   grant.mcs.mod = h.qm == 2 ? SRSLTE_MOD_QPSK : h.qm == 4 ? SRSLTE_MOD_16QAM : SRSLTE_MOD_64QAM;
   const int sf_len = SRSLTE_SF_LEN_PRB(h.nof_prb);
+  std::vector<double> lat_us;
   for (int n = 0; n < h.n_sf; n++) {
     cf_t* signal_buffer = iq + (size_t)n * sf_len;
     uint32_t cfi = 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (srslte_ue_dl_decode_fft_estimate(&ue_dl, signal_buffer, h.sf_idx, &cfi) < 0) { fprintf(stderr, "Getting PDCCH FFT estimate\n"); return 1; }
     tb_action_dl_t dl_action;
     mac.new_grant_dl(grant, h.rv, (uint16_t)h.rnti, &dl_action);
@@ -85,10 +89,20 @@ int run_worker(const Header& h, cf_t* iq, FILE* out) {
                                           noise_estimate, dl_action.rnti, dl_action.payload_ptr) == 0;
       }
     }
+    lat_us.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
     const int32_t ack = dl_ack, n_iter = (int32_t)srslte_pdsch_last_noi(&ue_dl.pdsch);
     const float snr = srslte_chest_dl_get_snr(&ue_dl.chest);
     fwrite(&ack, 4, 1, out); fwrite(&n_iter, 4, 1, out); fwrite(&snr, 4, 1, out);
     fwrite(dl_action.payload_ptr, 1, h.tbs / 8, out);
+  }
+  // per-subframe latency of the worker sequence (the real-time budget of a phch_worker is a few ms, phy.h:118-119)
+  if (lat_us.size() > 2) {
+    std::vector<double> v(lat_us.begin() + 2, lat_us.end());        // the first calls build plans and tables
+    std::sort(v.begin(), v.end());
+    double sum = 0;
+    for (double x : v) sum += x;
+    fprintf(stderr, "worker latency per subframe over %zu subframes: mean %.0f us, median %.0f us, max %.0f us\n", v.size(),
+            sum / v.size(), v[v.size() / 2], v.back());
   }
   srslte_ue_dl_free(&ue_dl);
   return 0;
