@@ -136,6 +136,9 @@ def run_mixed(args, rank, local_rank, world):
     import srsue_b200 as sg
     from srsue_b200.shard import balance_by_work
     from oracle import oracle as o
+    from srsue_b200.shard import bind_rank_to_gpu_numa
+    if world > 1:
+        bind_rank_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -304,6 +307,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsrsue_gpu has no CPU path")
+    from srsue_b200.shard import bind_rank_to_gpu_numa
+    numa_cpus = bind_rank_to_gpu_numa(local_rank) if world > 1 else None      # pinned staging on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -448,7 +453,8 @@ def main():
                        "subframes_per_step_per_gpu": B, "distinct_subframes": args.pool, "max_iter": args.max_iter,
                        "early_stop": "CRC24B per code block", "avg_turbo_iterations": avg_iter,
                        "l2_policy": "inputs larger than L2 (%.0f MB of IQ per step)" % (B * I.sf_len * 8 / 1e6),
-                       "parallelism": "independent subframe batches per GPU, no collective"},
+                       "parallelism": "independent subframe batches per GPU, no collective",
+                       "host_affinity": ("rank pinned to %d CPUs of its GPU's NUMA node" % len(numa_cpus)) if numa_cpus else "default"},
             "subframes_per_s": value * 1e6 / WORKLOAD["tbs"],
             "verified_bit_exact_payload": verified and e2e_ok,
             "e2e": {"value": e2e_bits_all / e2e_s_max / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": nbytes_iq,

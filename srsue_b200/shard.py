@@ -37,3 +37,35 @@ def reduce_metrics(elapsed_s, units, dist=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def bind_rank_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs local_cpulist of the GPU's PCI function),
+    before any pinned host buffer is allocated: pages are then first-touched on that node and the H2D / D2H copies of
+    the rank do not cross the socket interconnect.  Host-side dispatch detail of SURVEY 8e (one process per GPU with its
+    own pinned staging); returns the CPU set or None when the topology cannot be read."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001
+        return None
