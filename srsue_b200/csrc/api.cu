@@ -93,6 +93,7 @@ struct srsue_gpu_ctx {
   int last_grid = 0, last_block = 0, last_smem = 0, last_ncb = 0;
   int launch_count = 0;
   bool attr_set = false;
+  bool pdcch_attr_set = false;
 };
 
 namespace {
@@ -680,8 +681,10 @@ int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t*
   if (a.n_cand == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: empty search space");
   const int per_words = 3 * D + 4 * D + (D + 3) / 4;
   const int smem = a.n_cand * per_words * 4;
-  static bool attr = false;
-  if (!attr) { CU_CHECK(cudaFuncSetAttribute(pdcch_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  if (!p->ctx->pdcch_attr_set) {        // per device: a process may hold contexts on several GPUs
+    CU_CHECK(cudaFuncSetAttribute(pdcch_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    p->ctx->pdcch_attr_set = true;
+  }
   pdcch_search_kernel<<<n_sf, 32 * a.n_cand, smem, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());

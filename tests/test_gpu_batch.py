@@ -182,3 +182,28 @@ def test_zero_copy_pinned_rows(gpu, oracle, how):
         else:
             assert L.srsue_gpu_host_unregister(h_iq.ctypes.data) == 0
             assert L.srsue_gpu_host_unregister(h_pl.ctypes.data) == 0
+
+
+def test_plan_cache_eviction(gpu, oracle):
+    """more distinct launch shapes in one submission than the plan cache holds (16): least recently used plans are
+    destroyed and rebuilt without affecting results"""
+    sg, ctx = gpu
+    o = oracle
+    items, refs = [], []
+    for sf in range(10):
+        for cfi in (1, 2):
+            ocell = o.make_cell(6, 1, 3)
+            ocfg = o.make_cfg(ocell, sf_idx=sf, cfi=cfi, qm=2, tbs=104)
+            cell = sg.make_cell(6, 1, 3)
+            cfg = sg.make_cfg(cell, sf_idx=sf, cfi=cfi, qm=2, tbs=104)
+            tb, iq, _ = o.gen_subframe(ocell, ocfg, 9000 + 10 * sf + cfi, 12.0)
+            items.append(dict(cell=cell, cfg=cfg, iq=iq))
+            refs.append(tb)
+    b = sg.Batch(ctx, 64)
+    for _ in range(2):                       # the second pass re-creates the evicted plans
+        b.submit(items)
+        res = b.wait()
+        assert b.stats()["plans"] == 16
+        for r, tb in zip(res, refs):
+            assert r["crc_ok"] == 1 and np.array_equal(r["payload"], tb)
+    b.close()
