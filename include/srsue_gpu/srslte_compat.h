@@ -176,6 +176,8 @@ SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t
 /* uplink grant search (phch_worker.cc:426): DCI format 0 in the UE-specific space; 1 found / 0 / < 0 */
 SRSLTE_API int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti);
 SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);
+/* HARQ indicator of the uplink transmission (phch_worker.cc:381); needs srslte_ue_dl_decode_fft_estimate of this subframe */
+SRSLTE_API bool srslte_ue_dl_decode_phich(srslte_ue_dl_t *q, uint32_t sf_idx, uint32_t n_prb_lowest, uint32_t n_dmrs);
 /* wrappers the north star names; the DCI search is a "next" row, so the grant to use is the one last
  * installed with srsue_gpu_ue_dl_set_grant().  Return decoded bits (tbs) / 0 (no grant) / < 0. */
 SRSLTE_API int srslte_ue_dl_decode(srslte_ue_dl_t *q, cf_t *input, uint8_t *data, uint32_t tti);

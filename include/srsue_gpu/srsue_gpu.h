@@ -121,6 +121,11 @@ int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const sr
                                 int16_t *d_llr, void *stream);
 int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_llr, int ng_x6, int rnti, int common,
                              int nof_bits, int first_bit, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
+/* PHICH (srslte_ue_dl_decode_phich, phch_worker.cc:381): HARQ indicator of (n_group, n_seq) in every subframe of the
+ * batch; d_ack [n_sf] = 1 for ACK, d_metric optional [n_sf] (ACK iff < 0).  Normal CP, normal PHICH duration. */
+int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                           const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int ng_x6,
+                           int n_group, int n_seq, int32_t *d_ack, float *d_metric, void *stream);
 /* equalise + demap + descramble + rate-dematch into d_softbuf [n_sf][sb_sf_stride].  noise_mode 0: use
  * noise_est (srsUE passes 0.01), 1: use d_meas[.][0].  accumulate 0: new transmission, 1: HARQ combine.
  * d_dbg_d [n_sf][nof_re] / d_dbg_e [n_sf][G] optional taps of the equalised symbols / descrambled LLRs. */
@@ -200,6 +205,10 @@ int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t *cell, int cfi, int ng_x6, 
 int srsue_gpu_host_pdcch_quad_perm(int n_quad, int cell_id, int32_t *src);
 int srsue_gpu_host_pdcch_search_space(int nof_cce, int sf_idx, int rnti, int common, int32_t *cand_L, int32_t *cand_ncce);
 int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb);
+/* PHICH bookkeeping: (group, sequence) answering an uplink transmission with lowest PRB I_lowest and DMRS cyclic shift
+ * n_dmrs (36.213 9.1.2); the 12 subcarriers of a group in OFDM symbol 0 */
+int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
+int srsue_gpu_host_phich_res(const srsue_gpu_cell_t *cell, int n_group, int32_t *k12);
 /* subcarriers (in OFDM symbol 0) of the 16 PCFICH symbols d(0..15) */
 int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t *cell, int32_t *k16);
 /* rate-matching read order for (K, F, rv): seq[n] = index 3k+stream of the n-th non-null circular-buffer

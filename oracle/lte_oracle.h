@@ -124,6 +124,12 @@ int  lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng
 uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out);
 int  lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rnti, int common, int nof_bits,
                          uint8_t *bits_out, int *found_L, int *found_ncce);
+/* ---- PHICH (SPEC.md 11) ---- */
+void lteo_phich_res(const lteo_cell_t *cell, int ng_x6, int n_group, int32_t *k12);
+void lteo_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
+void lteo_phich_tx(const lteo_cell_t *cell, int sf_idx, int ng_x6, int n_group, int n_seq, int ack, lteo_cd_t *grid);
+int  lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce,
+                       float noise_est, int n_group, int n_seq, float *metric);
 /* PCFICH (SPEC.md 9): returns the CFI 1..3 with the largest correlation; corr[3] = the three integer correlations */
 int  lteo_pcfich_decode(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce,
                         float noise_est, int32_t *corr);

@@ -258,3 +258,114 @@ int lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rn
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * PHICH (36.211 6.9; srslte_ue_dl_decode_phich, phch_worker.cc:381).  SPEC.md 11.
+ * ---------------------------------------------------------------------------------------------- */
+/* the 12 subcarriers (OFDM symbol 0) of PHICH group n_group: 3 REGs x 4 data REs, normal PHICH duration */
+void lteo_phich_res(const lteo_cell_t *cell, int ng_x6, int n_group, int32_t *k12) {
+  int nrb = cell->nof_prb, n0 = 2 * nrb;
+  uint8_t *used = (uint8_t *)calloc(n0, 1);
+  int32_t k16[16];
+  lteo_pcfich_re(cell, k16);
+  for (int i = 0; i < 4; i++) used[k16[4 * i] / 6] = 1;
+  int32_t *free_idx = (int32_t *)malloc(sizeof(int32_t) * n0);
+  int np0 = 0;
+  for (int r = 0; r < n0; r++) if (!used[r]) free_idx[np0++] = r;
+  (void)ng_x6;
+  for (int i = 0; i < 3; i++) {
+    int reg = free_idx[(cell->cell_id + n_group + (i * np0) / 3) % np0];
+    lteo_reg_res(cell, 6 * reg, 0, k12 + 4 * i);
+  }
+  free(used); free(free_idx);
+}
+
+/* (n_group, n_seq) of the PHICH that answers an uplink transmission (36.213 9.1.2, FDD, normal CP) */
+void lteo_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq) {
+  int ngroups = lteo_phich_groups(nof_prb, ng_x6);
+  *n_group = (I_lowest + n_dmrs) % ngroups;
+  *n_seq = (I_lowest / ngroups + n_dmrs) % 8;
+}
+
+/* orthogonal sequence element w(i), i < 4, of sequence n_seq < 8 as (re, im) in {0, +-1} */
+static void phich_w(int n_seq, int i, int *re, int *im) {
+  static const int8_t w4[4][4] = {{1, 1, 1, 1}, {1, -1, 1, -1}, {1, 1, -1, -1}, {1, -1, -1, 1}};
+  int v = w4[n_seq & 3][i];
+  if (n_seq < 4) { *re = v; *im = 0; } else { *re = 0; *im = v; }
+}
+
+/* adds one PHICH (ack = 1: HI 1) to a grid; several PHICHs of a group superpose */
+void lteo_phich_tx(const lteo_cell_t *cell, int sf_idx, int ng_x6, int n_group, int n_seq, int ack, lteo_cd_t *grid) {
+  int nsc = 12 * cell->nof_prb;
+  int32_t k[12];
+  uint8_t c[12];
+  lteo_phich_res(cell, ng_x6, n_group, k);
+  lteo_gold(((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell->cell_id + 1) << 9) + (uint32_t)cell->cell_id, 12, c);
+  double a = 1.0 / sqrt(2.0);
+  lteo_cd_t d[12];
+  for (int i = 0; i < 12; i++) {
+    int wr, wi;
+    phich_w(n_seq, i % 4, &wr, &wi);
+    double z = (ack ? -1.0 : 1.0) * a * (c[i] ? -1.0 : 1.0);     /* BPSK: z (1 + j), real factor z */
+    /* w * z(1+j): (wr + j wi)(1 + j) = (wr - wi) + j (wr + wi) */
+    d[i].re = z * (wr - wi); d[i].im = z * (wr + wi);
+  }
+  lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
+  if (cell->nof_ports == 2) {
+    for (int i = 0; i < 12; i += 2) {
+      g0[k[i]].re += d[i].re * a;          g0[k[i]].im += d[i].im * a;
+      g1[k[i]].re += -d[i + 1].re * a;     g1[k[i]].im += d[i + 1].im * a;
+      g0[k[i + 1]].re += d[i + 1].re * a;  g0[k[i + 1]].im += d[i + 1].im * a;
+      g1[k[i + 1]].re += d[i].re * a;      g1[k[i + 1]].im += -d[i].im * a;
+    }
+  } else {
+    for (int i = 0; i < 12; i++) { g0[k[i]].re += d[i].re; g0[k[i]].im += d[i].im; }
+  }
+}
+
+/* returns the HI (1 = ACK).  The 12 REs are equalised with the SPEC.md 4 formulas, multiplied by conj(w) (exact sign
+ * swaps) and the scrambling sign, m_i = re + im, metric = ((m_0 + m_1) + m_2) + ... in float; ACK iff metric < 0 */
+int lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo_cf_t *sf, const lteo_cf_t *ce, float n0,
+                      int n_group, int n_seq, float *metric_out) {
+  int nsc = 12 * cell->nof_prb;
+  int32_t k[12];
+  uint8_t c[12];
+  lteo_cf_t d[12];
+  lteo_phich_res(cell, ng_x6, n_group, k);
+  lteo_gold(((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell->cell_id + 1) << 9) + (uint32_t)cell->cell_id, 12, c);
+  if (cell->nof_ports == 2) {
+    const float sq2 = (float)sqrt(2.0);
+    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
+    for (int i = 0; i < 12; i += 2) {
+      lteo_cf_t r0 = sf[k[i]], r1 = sf[k[i + 1]], h0 = ce0[k[i]], h1 = ce1[k[i]];
+      float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
+      float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
+      float b_re = h1.re * r1.re + h1.im * r1.im, b_im = h1.im * r1.re - h1.re * r1.im;
+      float c_re = h0.re * r1.re + h0.im * r1.im, c_im = h0.re * r1.im - h0.im * r1.re;
+      float e_re = h1.re * r0.re + h1.im * r0.im, e_im = h1.im * r0.re - h1.re * r0.im;
+      d[i].re = ((a_re + b_re) * sq2) / den;     d[i].im = ((a_im + b_im) * sq2) / den;
+      d[i + 1].re = ((c_re - e_re) * sq2) / den; d[i + 1].im = ((c_im - e_im) * sq2) / den;
+    }
+  } else {
+    for (int i = 0; i < 12; i++) {
+      lteo_cf_t y = sf[k[i]], h = ce[k[i]];
+      float den = (h.re * h.re + h.im * h.im) + n0;
+      d[i].re = (y.re * h.re + y.im * h.im) / den;
+      d[i].im = (y.im * h.re - y.re * h.im) / den;
+    }
+  }
+  float metric = 0.0f;
+  for (int i = 0; i < 12; i++) {
+    int wr, wi;
+    phich_w(n_seq, i % 4, &wr, &wi);
+    /* d * conj(w): w = +-1 -> +-d;  w = +-j -> d * (-+j) = (+-d.im, -+d.re) */
+    float tr, ti;
+    if (wi == 0) { tr = wr > 0 ? d[i].re : -d[i].re; ti = wr > 0 ? d[i].im : -d[i].im; }
+    else { tr = wi > 0 ? d[i].im : -d[i].im; ti = wi > 0 ? -d[i].re : d[i].re; }
+    if (c[i]) { tr = -tr; ti = -ti; }
+    float m = tr + ti;
+    metric = (i == 0) ? m : metric + m;
+  }
+  if (metric_out) *metric_out = metric;
+  return metric < 0.0f;
+}

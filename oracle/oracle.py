@@ -393,7 +393,27 @@ def pdcch_find_dci(llr, nof_cce, sf_idx, rnti, nof_bits, common=False):
     return found, out, L.value, n.value
 
 
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6):
+def phich_index(nof_prb, I_lowest, n_dmrs, ng_x6=6):
+    g, q = C.c_int(), C.c_int()
+    lib().lteo_phich_index(nof_prb, ng_x6, I_lowest, n_dmrs, C.byref(g), C.byref(q))
+    return g.value, q.value
+
+
+def phich_res(cell, n_group, ng_x6=6):
+    k = np.zeros(12, np.int32)
+    lib().lteo_phich_res(C.byref(cell), ng_x6, n_group, _p(k))
+    return k
+
+
+def phich_decode(cell, sf_idx, sf, ce, n_group, n_seq, noise_est=0.0, ng_x6=6):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    m = C.c_float()
+    ack = lib().lteo_phich_decode(C.byref(cell), sf_idx, ng_x6, _p(sf), _p(ce), C.c_float(noise_est), n_group, n_seq, C.byref(m))
+    return ack, np.float32(m.value)
+
+
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -405,6 +425,8 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=Non
         lib().lteo_pcfich_tx(C.byref(cell), cfg.sf_idx, cfg.cfi, _p(grid))
     if dcis:            # PDCCHs of this subframe: list of (bits, rnti, L, ncce)
         pdcch_tx(cell, cfg.sf_idx, cfg.cfi, dcis, grid, ng_x6)
+    for (g_, q_, ack_) in (phichs or []):     # HARQ indicators: (n_group, n_seq, ack)
+        lib().lteo_phich_tx(C.byref(cell), cfg.sf_idx, ng_x6, g_, q_, ack_, _p(grid))
     n = lib().lteo_symbol_sz(cell.nof_prb)
     nsc = 12 * cell.nof_prb
     rx = np.zeros((14, nsc), np.complex128)

@@ -691,6 +691,39 @@ int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t*
   return a.n_cand;
 }
 
+int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, const srsue_gpu_cf_t* d_ce,
+                           const float* d_meas, float noise_est, int noise_mode, int ng_x6, int n_group, int n_seq, int32_t* d_ack,
+                           float* d_metric, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce || !d_ack || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: null buffer");
+  if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12");
+  if (n_group < 0 || n_group >= phich_groups(p->cell.nof_prb, ng_x6) || n_seq < 0 || n_seq > 7)
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: group %d / sequence %d out of range", n_group, n_seq);
+  PhichArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
+  a.ack = d_ack; a.metric = d_metric;
+  phich_res(p->cell, n_group, a.re);
+  a.scramble = pcfich_scramble(p->cell, p->cfg.sf_idx) & 0xFFFu;     // the same c_init as the PCFICH (36.211 6.9.1)
+  a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.n_seq = n_seq; a.noise_mode = noise_mode;
+  a.noise_est = noise_est; a.k_sq2 = (float)std::sqrt(2.0);
+  phich_kernel<<<(n_sf + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq) {
+  if (!n_group || !n_seq || nof_prb < 6 || I_lowest < 0 || n_dmrs < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  phich_index(nof_prb, ng_x6, I_lowest, n_dmrs, n_group, n_seq);
+  return 0;
+}
+
+int srsue_gpu_host_phich_res(const srsue_gpu_cell_t* cell, int n_group, int32_t* k12) {
+  if (!cell || !k12 || n_group < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  phich_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, n_group, k12);
+  return 0;
+}
+
 int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t* cell, int cfi, int ng_x6, int32_t* re4) {
   if (!cell || cfi < 1 || cfi > 3) return SRSUE_GPU_ERROR_INVALID_INPUTS;
   std::vector<int32_t> v;

@@ -127,6 +127,19 @@ struct PdcchSearchArgs {
 };
 __global__ void pdcch_search_kernel(const PdcchSearchArgs a);
 
+struct PhichArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc]
+  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float* meas;         // [n_sf][5]
+  int32_t* ack;              // [n_sf] HARQ indicator: 1 = ACK
+  float* metric;             // optional [n_sf]: the decision metric (ACK iff < 0)
+  int re[12];                // subcarriers (symbol 0) of the group's 3 REGs
+  uint32_t scramble;         // 12 scrambling bits, LSB first
+  int n_sf, nsc, nof_ports, n_seq, noise_mode;
+  float noise_est, k_sq2;
+};
+__global__ void phich_kernel(const PhichArgs a);
+
 struct TbArgs {
   const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
   const int32_t* cb_status;  // [n_sf * C]

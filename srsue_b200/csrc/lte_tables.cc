@@ -377,4 +377,27 @@ int dci_format_sizeof(int fmt, int nof_prb) {
   return n1;
 }
 
+int phich_groups(int nof_prb, int ng_x6) { return (ng_x6 * nof_prb + 47) / 48; }
+
+void phich_res(const CellCfg& cell, int n_group, int32_t* k12) {
+  const int n0 = 2 * cell.nof_prb;
+  std::vector<uint8_t> taken(n0, 0);
+  int32_t pc[16];
+  pcfich_re(cell, pc);
+  for (int i = 0; i < 4; i++) taken[pc[4 * i] / 6] = 1;
+  std::vector<int> free0;
+  for (int r = 0; r < n0; r++) if (!taken[r]) free0.push_back(r);
+  const int np0 = (int)free0.size();
+  for (int i = 0, n = 0; i < 3; i++) {
+    const int k0 = 6 * free0[(cell.cell_id + n_group + (i * np0) / 3) % np0];
+    for (int j = 0; j < 6; j++) if ((k0 + j) % 3 != cell.cell_id % 3) k12[n++] = k0 + j;
+  }
+}
+
+void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq) {
+  const int g = phich_groups(nof_prb, ng_x6);
+  *n_group = (I_lowest + n_dmrs) % g;
+  *n_seq = (I_lowest / g + n_dmrs) % 8;
+}
+
 }  // namespace srsue

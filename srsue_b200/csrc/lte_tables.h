@@ -67,6 +67,11 @@ void pdcch_quad_perm(int n_quad, int cell_id, std::vector<int32_t>& src);
 void cc_rm_sequence(int D, std::vector<int32_t>& seq);
 // search-space candidates (L, first CCE) of subframe sf_idx for rnti (UE-specific) or the common space
 int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int32_t* cand_L, int32_t* cand_ncce);
+// PHICH (36.211 6.9, 36.213 9.1.2; normal CP and duration): number of groups, the 12 subcarriers of a group in symbol 0,
+// and (group, sequence) of the indicator that answers an uplink transmission
+int phich_groups(int nof_prb, int ng_x6);
+void phich_res(const CellCfg& cell, int n_group, int32_t* k12);
+void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq);
 // payload size of DCI format 1A (fmt = 0) or 1 (fmt = 1) for FDD, including the padding rules of 36.212 5.3.3.1
 int dci_format_sizeof(int fmt, int nof_prb);
 

@@ -302,6 +302,55 @@ __global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
   }
 }
 
+// ---- PHICH (srslte_ue_dl_decode_phich, phch_worker.cc:381; SPEC.md 11): one thread per subframe equalises the 12 REs
+// of the group, removes the orthogonal sequence (conj(w) is a sign swap) and the scrambling sign, and adds re + im of
+// the 12 results in index order; ACK iff the sum is negative.
+__global__ void __launch_bounds__(128) phich_kernel(const PhichArgs a) {
+  const int sf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sf >= a.n_sf) return;
+  const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
+  const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;
+  const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
+  float metric = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    float2 d[2];
+    if (a.nof_ports == 2) {
+      const float2* h1p = h0p + 14 * a.nsc;
+      const float2 r0 = y[a.re[i]], r1 = y[a.re[i + 1]], h0 = h0p[a.re[i]], h1 = h1p[a.re[i]];
+      const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
+      const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
+      const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
+      const float c_re = dot_rn(h0.x, r1.x, h0.y, r1.y), c_im = det_rn(h0.x, r1.y, h0.y, r1.x);
+      const float e_re = dot_rn(h1.x, r0.x, h1.y, r0.y), e_im = det_rn(h1.y, r0.x, h1.x, r0.y);
+      d[0] = make_float2(__fdiv_rn(__fmul_rn(__fadd_rn(a_re, b_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fadd_rn(a_im, b_im), a.k_sq2), den));
+      d[1] = make_float2(__fdiv_rn(__fmul_rn(__fsub_rn(c_re, e_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fsub_rn(c_im, e_im), a.k_sq2), den));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const float2 r = y[a.re[i + j]], h = h0p[a.re[i + j]];
+        const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
+        d[j] = make_float2(__fdiv_rn(dot_rn(r.x, h.x, r.y, h.y), den), __fdiv_rn(det_rn(r.y, h.x, r.x, h.y), den));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int q = (i + j) & 3;
+      // w(q) of sequence n_seq & 3: {1,1,1,1}, {1,-1,1,-1}, {1,1,-1,-1}, {1,-1,-1,1}; sequences 4..7 are j times these
+      const int s = a.n_seq & 3;
+      const bool neg_w = (s == 1 && (q & 1)) || (s == 2 && (q & 2)) || (s == 3 && (q == 1 || q == 2));
+      float tr, ti;
+      if (a.n_seq < 4) { tr = d[j].x; ti = d[j].y; } else { tr = d[j].y; ti = -d[j].x; }      // d * conj(j) = (im, -re)
+      const bool neg = neg_w != (((a.scramble >> (i + j)) & 1u) != 0);
+      if (neg) { tr = -tr; ti = -ti; }
+      const float m = __fadd_rn(tr, ti);
+      metric = (i + j == 0) ? m : __fadd_rn(metric, m);
+    }
+  }
+  a.ack[sf] = metric < 0.0f;
+  if (a.metric) a.metric[sf] = metric;
+}
+
 // ---- PDCCH soft bits (srslte_pdcch_extract_llr, phch_worker.cc:260; SPEC.md 10): one thread per resource-element
 // group equalises its 4 symbols with the PDSCH formulas, demaps them to 8 int16 QPSK LLRs, descrambles and stores
 // them (one 16-byte store) at the quadruplet's place in the de-interleaved PDCCH bit stream.

@@ -385,6 +385,23 @@ int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t* q, srslte_dci_msg_t* dci_msg, 
 
 uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t* q) { return q ? q->last_n_cce : 0; }
 
+bool srslte_ue_dl_decode_phich(srslte_ue_dl_t* q, uint32_t sf_idx, uint32_t n_prb_lowest, uint32_t n_dmrs) {
+  if (!q || !q->gpu || sf_idx > 9) return false;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  if (!u->dev_valid) return false;                   // the grid of this subframe must be on the device (decode_fft_estimate)
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, 1);
+  if (!fp) return false;
+  int n_group = 0, n_seq = 0;
+  phich_index(u->cell.nof_prb, u->ng_x6, (int)n_prb_lowest, (int)n_dmrs, &n_group, &n_seq);
+  if (!u->d_cfi && cudaMalloc((void**)&u->d_cfi, 4 * sizeof(int32_t)) != cudaSuccess) return false;
+  // srsLTE decodes the PHICH with the channel estimator's noise figure
+  if (srsue_gpu_phich_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, u->ng_x6, n_group, n_seq, u->d_cfi + 2, nullptr, u->stream)) return false;
+  int32_t ack = 0;
+  cudaMemcpyAsync(&ack, u->d_cfi + 2, sizeof(ack), cudaMemcpyDeviceToHost, u->stream);
+  if (cudaStreamSynchronize(u->stream) != cudaSuccess) return false;
+  return ack != 0;
+}
+
 void srslte_sch_set_max_noi(srslte_sch_t* q, uint32_t max_iterations) { if (q) q->max_iterations = max_iterations; }
 uint32_t srslte_pdsch_last_noi(srslte_pdsch_t* q) { return q ? q->dl_sch.nof_iterations : 0; }
 

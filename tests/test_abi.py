@@ -42,7 +42,7 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_softbuffer_rx_reset_tbs", "srslte_softbuffer_rx_free", "srslte_ue_dl_decode", "srslte_ue_dl_decode_rnti",
               "srslte_tdec_init", "srslte_tdec_free", "srslte_tdec_reset", "srslte_tdec_iteration", "srslte_tdec_decision",
               "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz",
-              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce"]:
+              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce", "srslte_ue_dl_decode_phich"]:
         assert hasattr(lib, n), n
 
 
@@ -153,3 +153,25 @@ def test_host_pdcch_tables_match_oracle():
     # 36.212 5.3.3.1 sizes (FDD): format 1A / format 1 at 1.4, 3, 5, 10, 15, 20 MHz
     assert [L.srsue_gpu_host_dci_format_sizeof(0, p) for p in (6, 15, 25, 50, 75, 100)] == [21, 22, 25, 27, 27, 28]
     assert [L.srsue_gpu_host_dci_format_sizeof(1, p) for p in (6, 15, 25, 50, 75, 100)] == [19, 23, 27, 31, 33, 39]
+
+
+def test_host_phich_tables_match_oracle():
+    import ctypes as C
+    import numpy as np
+    import srsue_b200 as sg
+    from oracle import oracle as o
+    L = sg.lib()
+    for prb in (6, 15, 25, 50, 75, 100):
+        for cid in (0, 1, 77, 301, 503):
+            cell = sg.make_cell(prb, 1, cid)
+            ocell = o.make_cell(prb, 1, cid)
+            for ng in (1, 3, 6, 12):
+                groups = (ng * prb + 47) // 48
+                for g in range(groups):
+                    k = np.zeros(12, np.int32)
+                    assert L.srsue_gpu_host_phich_res(C.byref(cell), g, k.ctypes.data_as(C.c_void_p)) == 0
+                    assert np.array_equal(k, o.phich_res(ocell, g, ng))
+                for I_lowest, n_dmrs in ((0, 0), (3, 1), (prb - 1, 7), (prb // 2, 4)):
+                    a, b = C.c_int(), C.c_int()
+                    assert L.srsue_gpu_host_phich_index(prb, ng, I_lowest, n_dmrs, C.byref(a), C.byref(b)) == 0
+                    assert (a.value, b.value) == o.phich_index(prb, I_lowest, n_dmrs, ng)

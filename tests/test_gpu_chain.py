@@ -152,7 +152,10 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     ul_at = next(((Lc, nc) for Lc, nc in ss if Lc == 2 and taken.isdisjoint(range(nc, nc + Lc))), None)
     if ul_at:
         dcis.append((ul_bits, rnti, ul_at[0], ul_at[1]))
-    tb, iq, _ = o.gen_subframe(ocell, ocfg, 555, 20.0, None, pcfich=True, dcis=dcis)
+    # HARQ indicators for two earlier uplink transmissions of this UE (phch_worker.cc:381)
+    ul_tx = [(3, 1, 1), (prb // 2, 0, 0)]                          # (I_lowest, n_dmrs, ack)
+    phichs = [o.phich_index(prb, Il, nd, 6) + (a,) for Il, nd, a in ul_tx]
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 555, 20.0, None, pcfich=True, dcis=dcis, phichs=phichs)
     q = UeDl()
     cell = Cell(nof_prb=prb, nof_ports=ports, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)     # Ng = 1
     assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
@@ -163,6 +166,9 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     got_cfi = C.c_uint32(0)
     assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), iq.ctypes.data_as(C.c_void_p), sf_idx, C.byref(got_cfi)) == 0
     assert got_cfi.value == cfi
+    L.srslte_ue_dl_decode_phich.restype = C.c_bool
+    for Il, nd, a in ul_tx:
+        assert bool(L.srslte_ue_dl_decode_phich(C.byref(q), sf_idx, Il, nd)) == bool(a)
     assert L.srslte_pdcch_extract_llr(C.byref(q.pdcch), q.sf_symbols, q.ce, C.c_float(0.0), sf_idx, got_cfi.value) == 0
     msg = DciMsg()
     assert L.srslte_ue_dl_find_dl_dci_type(C.byref(q), C.byref(msg), got_cfi.value, sf_idx, rnti, 0) == 1

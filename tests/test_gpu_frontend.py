@@ -294,3 +294,50 @@ def test_pdcch_matches_oracle(gpu, oracle, prb, ports, cid, cfi):
                 if f:
                     assert np.array_equal(out, sent[i][0][0])
         plan.close()
+
+
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (25, 2, 77), (50, 1, 301), (75, 2, 8), (100, 1, 503), (100, 2, 0)])
+def test_phich_matches_oracle(gpu, oracle, prb, ports, cid):
+    """HARQ indicators: decision and float metric (bit-identical) for several indicators of one subframe batch, including
+    two sequences sharing a group, at a reliable SNR and in noise"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    ocell = o.make_cell(prb, ports, cid)
+    cell = sg.make_cell(prb, ports, cid)
+    sf_idx = cid % 10
+    groups = (6 * prb + 47) // 48
+    rng = np.random.default_rng(cid + prb)
+    for snr in (10.0, -10.0):
+        n = 5
+        ph = [(0, 0, 1), (0, 5, 0), (groups - 1, 3, 1)]
+        acks = [[int(rng.integers(0, 2)) for _ in ph] for _ in range(n)]
+        iq = []
+        for i in range(n):
+            ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=2, qm=2, tbs=152 if prb == 6 else 1000, tm=ports)
+            iq.append(o.gen_subframe(ocell, ocfg, 6000 + i, snr, None, pcfich=True,
+                                     phichs=[(g, q, a) for (g, q, _), a in zip(ph, acks[i])])[1])
+        iq = np.stack(iq)
+        cfg = sg.make_cfg(cell, sf_idx=sf_idx, cfi=2, qm=2, tbs=0, tm=ports)
+        plan = sg.PdschPlan(ctx, cell, cfg, n)
+        I = plan.info
+        d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+        d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+        d_ack = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_met = torch.zeros(n, dtype=torch.float32, device="cuda")
+        plan.ofdm_rx(n, d_iq, d_sf)
+        plan.chest(n, d_sf, d_ce, d_meas)
+        for j, (g, q, _) in enumerate(ph):
+            plan.phich_decode(n, d_sf, d_ce, d_meas, 0.0, 1, g, q, d_ack, d_met)
+            torch.cuda.synchronize()
+            ack_g, met_g = d_ack.cpu().numpy(), d_met.cpu().numpy()
+            for i in range(n):
+                sf_o = o.ofdm_rx(prb, iq[i])
+                ce_o, meas_o = o.chest(ocell, sf_idx, sf_o)
+                a, m = o.phich_decode(ocell, sf_idx, sf_o, ce_o, g, q, meas_o[0])
+                assert ack_g[i] == a and met_g[i] == m
+                if snr > 0:
+                    assert a == acks[i][j]
+        plan.close()
