@@ -20,27 +20,52 @@ namespace srsue {
 
 namespace {
 
+// Packed FP32 (sm_100a FADD2 / FMUL2, PTX add/sub/mul.rn.f32x2): one instruction rounds both halves of a register pair
+// exactly like two scalar round-to-nearest operations, so a complex value costs one issue slot instead of two.  The
+// kernel is issue-bound, and the operand modifiers of these instructions (scalar broadcast, lane swap, per-lane negate)
+// make the shuffles of a complex multiply free.  ptxas contracts mul.f32x2 feeding add.f32x2 into FFMA2 even with
+// explicit .rn and -fmad=false (one rounding instead of two -- not the arithmetic of SPEC.md 2), so the two products of
+// a complex multiply are packed, their sum/difference stays scalar, and only sums of sums are packed again.
+typedef unsigned long long u64_t;
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<u64_t*>(&r)) : "l"(*reinterpret_cast<u64_t*>(&a)), "l"(*reinterpret_cast<u64_t*>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<u64_t*>(&r)) : "l"(*reinterpret_cast<u64_t*>(&a)), "l"(*reinterpret_cast<u64_t*>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<u64_t*>(&r)) : "l"(*reinterpret_cast<u64_t*>(&a)), "l"(*reinterpret_cast<u64_t*>(&b)));
+  return r;
+}
+
+// t = w * b with t.re = w.re b.re - w.im b.im, t.im = w.re b.im + w.im b.re, four products and two sums each rounded once
 __device__ __forceinline__ float2 cmul(float2 w, float2 b) {
-  return make_float2(__fsub_rn(__fmul_rn(w.x, b.x), __fmul_rn(w.y, b.y)),
-                     __fadd_rn(__fmul_rn(w.x, b.y), __fmul_rn(w.y, b.x)));
+  const float2 p1 = mul2(make_float2(w.x, w.x), b);                       // (w.re b.re, w.re b.im)
+  const float2 p2 = mul2(make_float2(w.y, w.y), make_float2(b.y, b.x));   // (w.im b.im, w.im b.re)
+  return make_float2(__fsub_rn(p1.x, p2.x), __fadd_rn(p1.y, p2.y));
 }
 __device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
   const float2 t = cmul(w, b);
   const float2 a0 = a;
-  a = make_float2(__fadd_rn(a0.x, t.x), __fadd_rn(a0.y, t.y));
-  b = make_float2(__fsub_rn(a0.x, t.x), __fsub_rn(a0.y, t.y));
+  a = add2(a0, t);
+  b = sub2(a0, t);
 }
 // butterflies with the exact twiddles 1 and -i (the table holds exactly (1,0) and (0,-1) there, SPEC.md 2):
 // w*b is then b resp. (b.im, -b.re) without any rounding, so the products can be skipped
 __device__ __forceinline__ void bfly_one(float2& a, float2& b) {
   const float2 a0 = a, b0 = b;
-  a = make_float2(__fadd_rn(a0.x, b0.x), __fadd_rn(a0.y, b0.y));
-  b = make_float2(__fsub_rn(a0.x, b0.x), __fsub_rn(a0.y, b0.y));
+  a = add2(a0, b0);
+  b = sub2(a0, b0);
 }
 __device__ __forceinline__ void bfly_mj(float2& a, float2& b) {
-  const float2 a0 = a, b0 = b;
-  a = make_float2(__fadd_rn(a0.x, b0.y), __fsub_rn(a0.y, b0.x));
-  b = make_float2(__fsub_rn(a0.x, b0.y), __fadd_rn(a0.y, b0.x));
+  const float2 a0 = a, t = make_float2(b.y, -b.x);
+  a = add2(a0, t);
+  b = sub2(a0, t);
 }
 
 // Shared-memory skew: element i lives at i + (i >> 4) (one padding float2 per 16), which keeps the strided
@@ -137,7 +162,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const 
         if (kp >= 1 && kp <= nsc / 2) ko = kp - 1 + nsc / 2;
         else if (kp >= N - nsc / 2) ko = kp - (N - nsc / 2);
         const float2 o = v[reg_of_u<LOGR>(u)];
-        if (ko >= 0) gdst[ko] = make_float2(__fmul_rn(o.x, scale), __fmul_rn(o.y, scale));
+        if (ko >= 0) gdst[ko] = mul2(o, make_float2(scale, scale));
       }
     } else {
       const int w0 = k * nsub + np;
