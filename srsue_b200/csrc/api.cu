@@ -561,15 +561,18 @@ int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
   a.log2n = 0; while ((1 << a.log2n) < a.nfft) a.log2n++;
   a.scale = (float)(1.0 / std::sqrt((double)a.nfft));
   a.c3 = (float)(std::sqrt(3.0) / 2.0);
-  static const int fft_div = getenv("SRSUE_FFT_POINTS_PER_THREAD") ? atoi(getenv("SRSUE_FFT_POINTS_PER_THREAD")) : 8;   // tuning knob
-  const int threads = std::max(32, a.nfft / std::max(8, fft_div));
+  const int threads = std::max(32, a.nfft / 8);       // 8 points per thread (16 and 32 measured slower)
   // 1536 = 3 x 512: three sub-transforms side by side in each of the two buffers
   const int smem = (a.nfft == 1536 ? 2 * 3 * (512 + 512 / 16 + 8) : 2 * (a.nfft + a.nfft / 16 + 8)) * (int)sizeof(float2);
   for (int done = 0; done < n_sf; done += 65535) {
     const int n = std::min(65535, n_sf - done);
     OfdmArgs b = a;
     b.iq += (size_t)done * 15 * a.nfft; b.sf_symbols += (size_t)done * 14 * a.nsc; b.n_sf = n;
-    ofdm_rx_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+    // single exchange buffer (8 CTAs per SM) wherever the CTA has exactly N/8 threads; SRSUE_FFT_INPLACE=0 selects the
+    // two-buffer kernel for comparison
+    static const int inplace = getenv("SRSUE_FFT_INPLACE") ? atoi(getenv("SRSUE_FFT_INPLACE")) : 1;
+    if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
+    else ofdm_rx_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
     p->ctx->launch_count++;
   }
   CU_CHECK(cudaGetLastError());
@@ -770,7 +773,7 @@ static int chest_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_
   const int smem = 2 * p->cell.nof_ports * 4 * 2 * p->cell.nof_prb * (int)sizeof(float2);
   // 128 threads measured best on B200 (0.19 ms vs 0.26 ms per 4096 subframes with 512): the kernel is bound by its
   // three ordered reduction warps, smaller CTAs pack more of them per SM.  Needs >= 3 warps.
-  static const int chest_threads = std::max(96, getenv("SRSUE_CHEST_THREADS") ? atoi(getenv("SRSUE_CHEST_THREADS")) : 128);
+  static const int chest_threads = std::min(128, std::max(96, getenv("SRSUE_CHEST_THREADS") ? atoi(getenv("SRSUE_CHEST_THREADS")) : 128));
   chest_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
@@ -832,7 +835,7 @@ static int llr_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
     if (b.dbg_e) b.dbg_e += (size_t)done * p->info.G;
     b.n_sf = n;
     // 128 threads measured best on B200 (0.68 ms vs 0.85 ms per 4096 subframes with 512): finer occupancy granularity
-    static const int demod_threads = std::max(32, getenv("SRSUE_DEMOD_THREADS") ? atoi(getenv("SRSUE_DEMOD_THREADS")) : 128);
+    static const int demod_threads = std::min(256, std::max(32, getenv("SRSUE_DEMOD_THREADS") ? atoi(getenv("SRSUE_DEMOD_THREADS")) : 128));
     pdsch_llr_dematch_kernel<<<dim3(a.C, n), demod_threads, smem, (cudaStream_t)stream>>>(b);
     p->ctx->launch_count++;
   }

@@ -50,6 +50,7 @@ struct OfdmArgs {
   float c3;                  // (float)(sqrt(3)/2), radix-3 stage of the 1536-point transform
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_inplace_kernel(const OfdmArgs a);
 
 struct ChestArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc]

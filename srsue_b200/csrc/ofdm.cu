@@ -133,7 +133,7 @@ __host__ __device__ constexpr int reg_of_u(int u) {
 //   N/L >= 16: k (N/L) is a multiple of 16, np < nsub    -> (idx_r >> 4) = k (N/L)/16 + (np >> 4) + ((nsub r) >> 4)
 //              (np >> 4 is 0 when nsub < 16; for nsub >= 16 nsub r is a multiple of 16)
 //   N/L <  16: np + nsub r < N/L, k (N/L) multiple of N/L -> (idx_r >> 4) = (k (N/L)) >> 4
-template <int N, int L, int LOGR, bool FIRST, bool LAST>
+template <int N, int L, int LOGR, bool FIRST, bool LAST, bool SYNC_RW = false>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const float2* ssrc, float2* sdst,
                                          float2* __restrict__ gdst, const float2* __restrict__ tw, int tid, int nthreads,
                                          int nsc, float scale, int in_stride = 1) {
@@ -152,6 +152,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const 
 #pragma unroll
       for (int r = 0; r < R; r++) v[r] = p[nsub * r + ((NL >= 16) ? ((nsub * r) >> 4) : 0)];
     }
+    if (SYNC_RW) __syncthreads();     // in-place exchange: every thread has read its inputs before anyone overwrites them
     if (FIRST && LOGR == 3) combine_first8<N>(v, tw); else combine<N, L, LOGR>(v, k, tw);
     if (LAST) {
 #pragma unroll
@@ -246,6 +247,49 @@ __device__ __forceinline__ void fft1536_symbol(const float2* __restrict__ gin, f
 }
 
 }  // namespace
+
+// Single-buffer variant (N >= 256, exactly N/8 threads, the default): the exchange is done in place with a barrier
+// between the reads and the writes of a pass.  Half the shared memory per CTA and 32 registers per thread give 8 CTAs =
+// 64 warps per SM instead of 48; the kernel is latency-bound (the first butterflies wait for DRAM, the twiddle loads for
+// L1), so the extra warps buy more than the two extra barriers cost: 0.414 -> 0.385 ms per 4096 subframes at N = 2048.
+template <int LOG2N>
+__device__ __forceinline__ void fft_symbol_inplace(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s0,
+                                                   const float2* __restrict__ tw, int nsc, float scale) {
+  constexpr int N = 1 << LOG2N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  fft_pass<N, 1, 3, true, false>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale);
+  __syncthreads();
+  fft_pass<N, 8, 3, false, false, true>(nullptr, s0, s0, nullptr, tw, tid, nt, nsc, scale);
+  __syncthreads();
+  if constexpr (LOG2N == 8) {
+    fft_pass<N, 64, 2, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+  } else if constexpr (LOG2N == 9) {
+    fft_pass<N, 64, 3, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+  } else {
+    fft_pass<N, 64, 3, false, false, true>(nullptr, s0, s0, nullptr, tw, tid, nt, nsc, scale);
+    __syncthreads();
+    if constexpr (LOG2N == 10) fft_pass<N, 512, 1, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+    else fft_pass<N, 512, 2, false, true>(nullptr, s0, nullptr, gout, tw, tid, nt, nsc, scale);
+  }
+}
+
+__global__ void __launch_bounds__(256, 7) ofdm_rx_inplace_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  const int N = a.nfft;
+  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const float2* gin = a.iq + (size_t)sf * 15 * N + start;
+  float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
+  switch (a.log2n) {
+    case 8: fft_symbol_inplace<8>(gin, gout, s_fft, a.tw, a.nsc, a.scale); break;
+    case 9: fft_symbol_inplace<9>(gin, gout, s_fft, a.tw, a.nsc, a.scale); break;
+    case 10: fft_symbol_inplace<10>(gin, gout, s_fft, a.tw, a.nsc, a.scale); break;
+    case 11: fft_symbol_inplace<11>(gin, gout, s_fft, a.tw, a.nsc, a.scale); break;
+    default: break;
+  }
+}
 
 __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];

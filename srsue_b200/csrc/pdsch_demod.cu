@@ -145,7 +145,7 @@ __device__ __forceinline__ uint32_t clamp_pair(uint32_t v) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(512) pdsch_llr_dematch_kernel(const DemodArgs a) {
+__global__ void __launch_bounds__(256, 8) pdsch_llr_dematch_kernel(const DemodArgs a) {
   extern __shared__ __align__(16) int16_t s_e[];
   const int r = blockIdx.x, sf = blockIdx.y;
   const int e0 = a.cb_e_start[r], e1 = a.cb_e_start[r + 1], E = e1 - e0;
