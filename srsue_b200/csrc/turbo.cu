@@ -193,38 +193,33 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   }
 
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
+  // Register prefetch TWO groups ahead: all warps of the CTA run this short, load-dominated sweep at the
+  // same time (the passes are barrier-separated), so there is no other phase to hide the L2 latency behind.
+  // The last group of this sweep (steps 0..7) is the first group of the forward sweep: its channel LLRs (ny, ns)
+  // and the beta vector it starts from (nbeta) stay in registers across the pass boundary instead of being
+  // re-loaded from L2 with nothing to overlap.
+  uint32_t ny[kSW], ns[kSW], nbeta[8];
   {
-    // Register prefetch TWO groups ahead: all warps of the CTA run this short, load-dominated sweep at the
-    // same time (the passes are barrier-separated), so there is no other phase to hide the L2 latency behind.
-    uint32_t ny[kSW], ns[kSW], my[kSW], ms[kSW];
+    uint32_t my[kSW], ms[kSW];
     ld8(yq + (nsw - 1) * gstride, ny);
     if (DEC == 0) ld8(sysq + (nsw - 1) * gstride, ns);
     if (nsw > 1) {
       ld8(yq + (nsw - 2) * gstride, my);
       if (DEC == 0) ld8(sysq + (nsw - 2) * gstride, ms);
     }
-#pragma unroll 1
-    for (int sw = nsw - 1; sw >= 0; sw--) {
-      uint32_t x[kSW], y[kSW];
-#pragma unroll
-      for (int i = 0; i < kSW; i++) y[i] = ny[i];
+    auto group = [&](int sw, const uint32_t (&y)[kSW], const uint32_t (&sv)[kSW]) {
+      uint32_t x[kSW];
       if (DEC == 0) {
         const uint32_t* ap = c.Aw + sw * kSW * T + t;
 #pragma unroll
-        for (int i = 0; i < kSW; i++) x[i] = vadd(ns[i], ap[i * T]);
+        for (int i = 0; i < kSW; i++) x[i] = vadd(sv[i], ap[i * T]);
       } else {
         // position table read as LDS.U16 (immediate offsets, LSU pipe), not unpacked on the ALU pipe
         const uint16_t* pq = perm16 + sw * (2 * kSW) * T;
 #pragma unroll
         for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
       }
-#pragma unroll
-      for (int i = 0; i < kSW; i++) { ny[i] = my[i]; if (DEC == 0) ns[i] = ms[i]; }
-      if (sw > 1) {
-        ld8(yq + (sw - 2) * gstride, my);
-        if (DEC == 0) ld8(sysq + (sw - 2) * gstride, ms);
-      }
-      st8(ckpt4 + sw * gstride, b);                 // thread-private scratch, read back in pass 2
+      if (sw) st8(ckpt4 + sw * gstride, b);         // thread-private scratch, read back in pass 2 (group 0 stays in registers)
 #pragma unroll
       for (int i = kSW - 1; i >= 0; i--) {
         uint32_t nb[8];
@@ -233,7 +228,21 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
         for (int s = 0; s < 8; s++) b[s] = nb[s];
         if ((i & 3) == 0) normalise(b);
       }
+    };
+#pragma unroll 1
+    for (int sw = nsw - 1; sw >= 1; sw--) {
+      uint32_t y[kSW], sv[kSW];
+#pragma unroll
+      for (int i = 0; i < kSW; i++) { y[i] = ny[i]; ny[i] = my[i]; if (DEC == 0) { sv[i] = ns[i]; ns[i] = ms[i]; } }
+      if (sw > 1) {
+        ld8(yq + (sw - 2) * gstride, my);
+        if (DEC == 0) ld8(sysq + (sw - 2) * gstride, ms);
+      }
+      group(sw, y, sv);
     }
+#pragma unroll
+    for (int s = 0; s < 8; s++) nbeta[s] = b[s];
+    group(0, ny, ns);
   }
   // beta at the window start feeds the previous window in the next iteration
 #pragma unroll
@@ -242,10 +251,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   // ---- pass 2: forward sweep ----------------------------------------------------------------------
   uint32_t crc = 0;
   {
-    uint32_t ny[kSW], ns[kSW], nbeta[8];            // register prefetch: channel LLRs, next checkpoint
-    ld8(yq, ny);
-    if (DEC == 0) ld8(sysq, ns);
-    ldp8(ckpt4, nbeta);
+    // ny / ns / nbeta of sub-window 0 come from the backward sweep; later ones are prefetched one group ahead
 #pragma unroll 1
     for (int sw = 0; sw < nsw; sw++) {
       uint32_t x[kSW], y[kSW], aux[kSW];            // aux: DEC1 systematic LLRs
