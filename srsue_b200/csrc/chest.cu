@@ -29,7 +29,7 @@ __device__ __forceinline__ float warp_sum_ordered(int n, int lane, F elem) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(128, 8) chest_kernel(const ChestArgs a) {
+__global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
   extern __shared__ __align__(16) float2 s_ch[];
   __shared__ float s_ftab[17];
   __shared__ float s_ttab[14];
