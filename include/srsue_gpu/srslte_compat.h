@@ -214,6 +214,26 @@ SRSLTE_API void srslte_tdec_decision_byte(srslte_tdec_t *h, uint8_t *output, uin
 SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *output, uint32_t nof_iterations,
                                    uint32_t long_cb);
 
+/* ---- MIB decode (ue/src/phy/phch_recv.cc:98,246-253) ------------------------------------------------- */
+#define SRSLTE_BCH_PAYLOAD_LEN 24
+#define SRSLTE_UE_MIB_FOUND 1
+#define SRSLTE_UE_MIB_NOTFOUND 0
+typedef struct SRSLTE_API { void *gpu; } srslte_pbch_t;
+typedef struct SRSLTE_API {
+  srslte_pbch_t pbch;
+  srslte_cell_t cell;
+  void *gpu;
+} srslte_ue_mib_t;
+SRSLTE_API int srslte_ue_mib_init(srslte_ue_mib_t *q, srslte_cell_t cell);            /* 0 = ok (phch_recv.cc:98) */
+SRSLTE_API void srslte_ue_mib_free(srslte_ue_mib_t *q);
+SRSLTE_API void srslte_pbch_decode_reset(srslte_pbch_t *q);                            /* phch_recv.cc:246 */
+/* input: the samples of a subframe 0.  Returns SRSLTE_UE_MIB_FOUND and the 24 MIB bits (one per byte), the number of
+ * transmit ports and the frame's position in the 40 ms BCH period; every call decodes from this subframe alone */
+SRSLTE_API int srslte_ue_mib_decode(srslte_ue_mib_t *q, cf_t *input, uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN],
+                                    uint32_t *nof_tx_ports, uint32_t *sfn_offset);
+SRSLTE_API void srslte_pbch_mib_unpack(uint8_t *msg, srslte_cell_t *cell, uint32_t *sfn);   /* phch_recv.cc:216,253 */
+SRSLTE_API void srslte_pbch_mib_pack(srslte_cell_t *cell, uint32_t sfn, uint8_t *msg);
+
 /* ---- extensions (not in srsLTE) ------------------------------------------------------------------- */
 /* srslte_ue_dl_decode_fft_estimate decodes the PCFICH on the device and returns its CFI; set_cfi(1..3) forces a
  * value instead (captures without a control region), set_cfi(0) returns to decoding.  The grant still comes from

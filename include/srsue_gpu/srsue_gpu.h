@@ -121,6 +121,13 @@ int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const sr
                                 int16_t *d_llr, void *stream);
 int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_llr, int ng_x6, int rnti, int common,
                              int nof_bits, int first_bit, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
+/* PBCH / MIB (srslte_ue_mib_decode, phch_recv.cc:247): blind decode of the master information block from subframes 0
+ * (plan with sf_idx 0): transmit-port hypotheses 1 and 2 (2 only when the plan's cell has two ports, i.e. both were
+ * estimated) x the four positions in the 40 ms BCH period.  d_result [n_sf][4] = {found, ports, frame number mod 4, 0},
+ * d_mib [n_sf][24] one bit per byte (dl-Bandwidth 3, phich-Duration 1, phich-Resource 2, SFN/4 8, spare 10). */
+int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
+                          const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode,
+                          int32_t *d_result, uint8_t *d_mib, void *stream);
 /* PHICH (srslte_ue_dl_decode_phich, phch_worker.cc:381): HARQ indicator of (n_group, n_seq) in every subframe of the
  * batch; d_ack [n_sf] = 1 for ACK, d_metric optional [n_sf] (ACK iff < 0).  Normal CP, normal PHICH duration. */
 int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
@@ -205,6 +212,8 @@ int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t *cell, int cfi, int ng_x6, 
 int srsue_gpu_host_pdcch_quad_perm(int n_quad, int cell_id, int32_t *src);
 int srsue_gpu_host_pdcch_search_space(int nof_cce, int sf_idx, int rnti, int common, int32_t *cand_L, int32_t *cand_ncce);
 int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb);
+/* grid indices (l * nsc + k) of the 240 PBCH resource elements of a subframe 0 */
+int srsue_gpu_host_pbch_res(const srsue_gpu_cell_t *cell, int32_t *g240);
 /* PHICH bookkeeping: (group, sequence) answering an uplink transmission with lowest PRB I_lowest and DMRS cyclic shift
  * n_dmrs (36.213 9.1.2); the 12 subcarriers of a group in OFDM symbol 0 */
 int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);

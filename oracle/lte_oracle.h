@@ -124,6 +124,14 @@ int  lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng
 uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out);
 int  lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rnti, int common, int nof_bits,
                          uint8_t *bits_out, int *found_L, int *found_ncce);
+/* ---- PBCH / MIB (SPEC.md 12) ---- */
+uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out);
+void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240);
+void lteo_pbch_tx(const lteo_cell_t *cell, const uint8_t *mib24, int frame_idx, lteo_cd_t *grid);
+void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce, float noise_est,
+                   int16_t *llr480);
+int  lteo_pbch_decode(const lteo_cell_t *cell, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce, float noise_est,
+                      uint8_t *mib24, int *nof_ports, int *sfn_offset);
 /* ---- PHICH (SPEC.md 11) ---- */
 void lteo_phich_res(const lteo_cell_t *cell, int ng_x6, int n_group, int32_t *k12);
 void lteo_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);

@@ -198,12 +198,10 @@ int lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_
  * metrics, branch metric = sum_j (code bit ? +LLR : -LLR), ties keep the predecessor with input-history bit 0;
  * trace back from the best final state (lowest index on ties); the middle D decisions are the output.
  */
-uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out) {
-  int D = nof_bits + 16, E = 72 * L, T = 3 * D;
-  int32_t *seq = (int32_t *)malloc(sizeof(int32_t) * 3 * D);
-  int32_t *soft = (int32_t *)calloc(3 * D, sizeof(int32_t));
-  int n = lteo_cc_rm_sequence(D, seq);
-  for (int k = 0; k < E; k++) soft[seq[k % n]] += llr[k];
+/* tail-biting Viterbi over soft[3 D] (D = nof_bits + 16) + CRC16: writes the D decided bits to bits_out (payload first)
+ * and returns CRC16(payload) xor received CRC */
+uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out) {
+  int D = nof_bits + 16, T = 3 * D;
   /* state = the 6 previous inputs, bit 5 = most recent.  Next state after input u: (u << 5) | (state >> 1). */
   int32_t pm[64], nm[64];
   uint8_t *surv = (uint8_t *)malloc((size_t)T * 64);      /* surv[t][ns] = dropped oldest bit of the chosen predecessor */
@@ -235,11 +233,24 @@ uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, ui
     st = ((st & 31) << 1) | surv[(size_t)t * 64 + st];
   }
   uint8_t *c = dec + D;                                     /* middle repetition */
-  memcpy(bits_out, c, nof_bits);
+  memcpy(bits_out, c, D);
   uint32_t crc = lteo_crc_bits(c, nof_bits, LTEO_CRC16, 16), rx = 0;
   for (int i = 0; i < 16; i++) rx = (rx << 1) | c[nof_bits + i];
-  free(seq); free(soft); free(surv); free(dec);
+  free(surv); free(dec);
   return (uint16_t)(crc ^ rx);
+}
+
+uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out) {
+  int D = nof_bits + 16, E = 72 * L;
+  int32_t *seq = (int32_t *)malloc(sizeof(int32_t) * 3 * D);
+  int32_t *soft = (int32_t *)calloc(3 * D, sizeof(int32_t));
+  uint8_t *bits = (uint8_t *)malloc(D);
+  int n = lteo_cc_rm_sequence(D, seq);
+  for (int k = 0; k < E; k++) soft[seq[k % n]] += llr[k];
+  uint16_t rem = lteo_viterbi_crc16(soft, nof_bits, bits);
+  memcpy(bits_out, bits, nof_bits);
+  free(seq); free(soft); free(bits);
+  return rem;
 }
 
 /* blind search over the UE-specific (common = 0) or common search space for a DCI of nof_bits addressed to rnti.
@@ -368,4 +379,117 @@ int lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo
   }
   if (metric_out) *metric_out = metric;
   return metric < 0.0f;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * PBCH / MIB (36.211 6.6, 36.212 5.3.1; srslte_ue_mib_decode, phch_recv.cc:247).  SPEC.md 12.
+ * ---------------------------------------------------------------------------------------------- */
+/* grid indices (l * nsc + k) of the 240 PBCH resource elements of subframe 0: slot 1, symbols 0..3, the 72 central
+ * subcarriers, k first then l; the CRS positions of antenna ports 0..3 are always left out (symbols 0 and 1) */
+void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240) {
+  int nsc = 12 * cell->nof_prb, k0 = nsc / 2 - 36, n = 0;
+  for (int l = 0; l < 4; l++)
+    for (int k = 0; k < 72; k++) {
+      if (l < 2 && (k0 + k) % 3 == cell->cell_id % 3) continue;
+      g240[n++] = (7 + l) * nsc + k0 + k;
+    }
+}
+
+/* the 16-bit CRC mask that signals the number of transmit antenna ports */
+static uint32_t pbch_crc_mask(int nof_ports) { return nof_ports == 1 ? 0x0000u : nof_ports == 2 ? 0xFFFFu : 0x5555u; }
+
+/* adds the PBCH of radio frame (sfn mod 4) = frame_idx to the grid of a subframe 0 */
+void lteo_pbch_tx(const lteo_cell_t *cell, const uint8_t *mib24, int frame_idx, lteo_cd_t *grid) {
+  int nsc = 12 * cell->nof_prb;
+  uint8_t c[40], d[120], e[1920], scr[1920];
+  int32_t seq[120], g[240];
+  memcpy(c, mib24, 24);
+  uint32_t crc = lteo_crc_bits(mib24, 24, LTEO_CRC16, 16) ^ pbch_crc_mask(cell->nof_ports);
+  for (int i = 0; i < 16; i++) c[24 + i] = (uint8_t)((crc >> (15 - i)) & 1);
+  lteo_conv_encode(c, 40, d);
+  lteo_cc_rm_sequence(40, seq);
+  for (int k = 0; k < 1920; k++) e[k] = d[seq[k % 120]];
+  lteo_gold((uint32_t)cell->cell_id, 1920, scr);
+  lteo_pbch_res(cell, g);
+  double a = 1.0 / sqrt(2.0);
+  lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
+  for (int i = 0; i < 240; i += 2) {
+    lteo_cd_t x[2];
+    for (int j = 0; j < 2; j++) {
+      int b0 = e[480 * frame_idx + 2 * (i + j)] ^ scr[480 * frame_idx + 2 * (i + j)];
+      int b1 = e[480 * frame_idx + 2 * (i + j) + 1] ^ scr[480 * frame_idx + 2 * (i + j) + 1];
+      x[j].re = (b0 ? -a : a); x[j].im = (b1 ? -a : a);
+    }
+    if (cell->nof_ports == 2) {
+      g0[g[i]].re = x[0].re * a;      g0[g[i]].im = x[0].im * a;
+      g1[g[i]].re = -x[1].re * a;     g1[g[i]].im = x[1].im * a;
+      g0[g[i + 1]].re = x[1].re * a;  g0[g[i + 1]].im = x[1].im * a;
+      g1[g[i + 1]].re = x[0].re * a;  g1[g[i + 1]].im = -x[0].im * a;
+    } else {
+      g0[g[i]] = x[0]; g0[g[i + 1]] = x[1];
+    }
+  }
+}
+
+/* LLRs of the 480 PBCH bits of one subframe 0 under the hypothesis of `hyp_ports` transmit ports (1: single-port
+ * equaliser with port 0's estimate; 2: Alamouti combiner), SPEC.md 4-5 arithmetic, not yet descrambled */
+void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf, const lteo_cf_t *ce, float n0, int16_t *llr480) {
+  int nsc = 12 * cell->nof_prb;
+  int32_t g[240];
+  lteo_cf_t d[240];
+  lteo_pbch_res(cell, g);
+  if (hyp_ports == 2) {
+    const float sq2 = (float)sqrt(2.0);
+    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
+    for (int i = 0; i < 240; i += 2) {
+      lteo_cf_t r0 = sf[g[i]], r1 = sf[g[i + 1]], h0 = ce0[g[i]], h1 = ce1[g[i]];
+      float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
+      float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
+      float b_re = h1.re * r1.re + h1.im * r1.im, b_im = h1.im * r1.re - h1.re * r1.im;
+      float c_re = h0.re * r1.re + h0.im * r1.im, c_im = h0.re * r1.im - h0.im * r1.re;
+      float e_re = h1.re * r0.re + h1.im * r0.im, e_im = h1.im * r0.re - h1.re * r0.im;
+      d[i].re = ((a_re + b_re) * sq2) / den;     d[i].im = ((a_im + b_im) * sq2) / den;
+      d[i + 1].re = ((c_re - e_re) * sq2) / den; d[i + 1].im = ((c_im - e_im) * sq2) / den;
+    }
+  } else {
+    for (int i = 0; i < 240; i++) {
+      lteo_cf_t y = sf[g[i]], h = ce[g[i]];
+      float den = (h.re * h.re + h.im * h.im) + n0;
+      d[i].re = (y.re * h.re + y.im * h.im) / den;
+      d[i].im = (y.im * h.re - y.re * h.im) / den;
+    }
+  }
+  lteo_demod(d, 240, 2, llr480);
+}
+
+/* Blind MIB decode from one subframe 0: port hypotheses 1 then 2 (2 only when the estimator ran with two ports), for
+ * each the four positions of the frame inside the 40 ms BCH period: descramble with that quarter of the sequence,
+ * exact int32 soft combining of the 480 LLRs onto the 120 coded bits, the tail-biting Viterbi decoder of the PDCCH
+ * (D = 40), CRC16 xor received CRC == antenna mask.  Returns 1 and fills mib24 / nof_ports / sfn_offset for the first
+ * match, else 0. */
+int lteo_pbch_decode(const lteo_cell_t *cell, const lteo_cf_t *sf, const lteo_cf_t *ce, float n0, uint8_t *mib24,
+                     int *nof_ports, int *sfn_offset) {
+  uint8_t scr[1920];
+  lteo_gold((uint32_t)cell->cell_id, 1920, scr);
+  for (int hyp = 1; hyp <= (cell->nof_ports >= 2 ? 2 : 1); hyp++) {
+    int16_t llr[480], des[480];
+    lteo_pbch_llr(cell, hyp, sf, ce, n0, llr);
+    for (int q = 0; q < 4; q++) {
+      for (int k = 0; k < 480; k++) des[k] = scr[480 * q + k] ? (int16_t)-llr[k] : llr[k];
+      /* the PDCCH candidate decoder with E = 480 = 4 x 120: L such that 72 L = 480 does not exist, so call the pieces */
+      int32_t seq[120], soft[120];
+      lteo_cc_rm_sequence(40, seq);
+      memset(soft, 0, sizeof(soft));
+      for (int k = 0; k < 480; k++) soft[seq[k % 120]] += des[k];
+      uint8_t bits[40];
+      uint16_t rem = lteo_viterbi_crc16(soft, 24, bits);
+      if (rem == pbch_crc_mask(hyp)) {
+        memcpy(mib24, bits, 24);
+        if (nof_ports) *nof_ports = hyp;
+        if (sfn_offset) *sfn_offset = q;
+        return 1;
+      }
+    }
+  }
+  return 0;
 }

@@ -413,7 +413,32 @@ def phich_decode(cell, sf_idx, sf, ce, n_group, n_seq, noise_est=0.0, ng_x6=6):
     return ack, np.float32(m.value)
 
 
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None):
+def mib_pack(nof_prb, phich_ext, ng_x6, sfn):
+    """the 24 MIB bits (36.331): dl-Bandwidth, phich-Duration, phich-Resource, the 8 MSBs of the SFN, 10 spare zeros"""
+    bw = [6, 15, 25, 50, 75, 100].index(nof_prb)
+    ng = [1, 3, 6, 12].index(ng_x6)
+    v = (bw << 21) | (int(phich_ext) << 20) | (ng << 18) | (((sfn >> 2) & 0xFF) << 10)
+    return np.array([(v >> (23 - i)) & 1 for i in range(24)], np.uint8)
+
+
+def pbch_decode(cell, sf, ce, noise_est=0.0):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    bits = np.zeros(24, np.uint8)
+    p, q = C.c_int(), C.c_int()
+    f = lib().lteo_pbch_decode(C.byref(cell), _p(sf), _p(ce), C.c_float(noise_est), _p(bits), C.byref(p), C.byref(q))
+    return f, bits, p.value, q.value
+
+
+def pbch_llr(cell, hyp_ports, sf, ce, noise_est=0.0):
+    sf = np.ascontiguousarray(sf, np.complex64)
+    ce = np.ascontiguousarray(ce, np.complex64)
+    llr = np.zeros(480, np.int16)
+    lib().lteo_pbch_llr(C.byref(cell), hyp_ports, _p(sf), _p(ce), C.c_float(noise_est), _p(llr))
+    return llr
+
+
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None, mib=None):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -425,6 +450,10 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=Non
         lib().lteo_pcfich_tx(C.byref(cell), cfg.sf_idx, cfg.cfi, _p(grid))
     if dcis:            # PDCCHs of this subframe: list of (bits, rnti, L, ncce)
         pdcch_tx(cell, cfg.sf_idx, cfg.cfi, dcis, grid, ng_x6)
+    if mib is not None:     # (24 MIB bits, radio frame number mod 4): PBCH of a subframe 0
+        assert cfg.sf_idx == 0
+        mb = np.ascontiguousarray(mib[0], np.uint8)
+        lib().lteo_pbch_tx(C.byref(cell), _p(mb), int(mib[1]), _p(grid))
     for (g_, q_, ack_) in (phichs or []):     # HARQ indicators: (n_group, n_seq, ack)
         lib().lteo_phich_tx(C.byref(cell), cfg.sf_idx, ng_x6, g_, q_, ack_, _p(grid))
     n = lib().lteo_symbol_sz(cell.nof_prb)

@@ -151,6 +151,10 @@ class PdschPlan:
         _check(lib().srsue_gpu_pcfich_decode(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                              _ptr(d_cfi), _ptr(d_corr), _stream()), "pcfich_decode")
 
+    def pbch_decode(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, d_result, d_mib):
+        _check(lib().srsue_gpu_pbch_decode(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
+                                           _ptr(d_result), _ptr(d_mib), _stream()), "pbch_decode")
+
     def phich_decode(self, n_sf, d_sf, d_ce, d_meas, noise_est, noise_mode, n_group, n_seq, d_ack, d_metric=None, ng_x6=6):
         _check(lib().srsue_gpu_phich_decode(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), C.c_float(noise_est), noise_mode,
                                             ng_x6, n_group, n_seq, _ptr(d_ack), _ptr(d_metric), _stream()), "phich_decode")

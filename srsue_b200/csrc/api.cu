@@ -241,6 +241,7 @@ struct srsue_gpu_pdsch_plan {
   int pd_ng = -1, pd_nreg = 0;
   int32_t* d_pd_re4 = nullptr; int32_t* d_pd_src = nullptr; uint32_t* d_pd_scr = nullptr;
   std::map<int, int32_t*> d_pd_rm;   // D -> rate-matching order
+  int32_t* d_pbch_re = nullptr; uint32_t* d_pbch_scr = nullptr; int32_t* d_pbch_rm = nullptr;   // PBCH tables, built on first use
 };
 
 extern "C" {
@@ -527,6 +528,7 @@ void srsue_gpu_pdsch_plan_destroy(srsue_gpu_pdsch_plan_t* p) {
   cudaSetDevice(p->ctx->device);
   cudaFree(p->d_re); cudaFree(p->d_scr); cudaFree(p->d_gather); cudaFree(p->d_e_start); cudaFree(p->d_cb_geom);
   cudaFree(p->d_pd_re4); cudaFree(p->d_pd_src); cudaFree(p->d_pd_scr);
+  cudaFree(p->d_pbch_re); cudaFree(p->d_pbch_scr); cudaFree(p->d_pbch_rm);
   for (auto& kv : p->d_pd_rm) cudaFree(kv.second);
   cudaFree(p->d_crs); cudaFree(p->d_tw); cudaFree(p->d_list_m); cudaFree(p->d_list_p); cudaFree(p->d_tbmap); cudaFree(p->d_tbshift);
   cudaFree(p->d_sf); cudaFree(p->d_ce); cudaFree(p->d_pil); cudaFree(p->d_meas); cudaFree(p->d_sb); cudaFree(p->d_cb_bits);
@@ -611,6 +613,7 @@ int pdcch_tables(srsue_gpu_pdsch_plan_t* p, int ng_x6) {
   if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12 (6 x Ng)");
   if (p->pd_ng == ng_x6) return 0;
   cudaFree(p->d_pd_re4); cudaFree(p->d_pd_src); cudaFree(p->d_pd_scr);
+  cudaFree(p->d_pbch_re); cudaFree(p->d_pbch_scr); cudaFree(p->d_pbch_rm);
   p->d_pd_re4 = nullptr; p->d_pd_src = nullptr; p->d_pd_scr = nullptr; p->pd_ng = -1;
   std::vector<int32_t> re4, src;
   const int n_reg = pdcch_regs(p->cell, p->cfg.cfi, ng_x6, re4);
@@ -712,6 +715,38 @@ int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_
   phich_kernel<<<(n_sf + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_sf, const srsue_gpu_cf_t* d_ce,
+                          const float* d_meas, float noise_est, int noise_mode, int32_t* d_result, uint8_t* d_mib, void* stream) {
+  PLAN_CHECK(p, n_sf);
+  if (!d_sf || !d_ce || !d_result || !d_mib || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: null buffer");
+  if (p->cfg.sf_idx != 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: the PBCH is in subframe 0 (plan has sf_idx %d)", p->cfg.sf_idx);
+  if (!p->d_pbch_re) {
+    std::vector<int32_t> re(240), seq;
+    pbch_res(p->cell, re.data());
+    std::vector<uint32_t> scr;
+    gold_packed((uint32_t)p->cell.cell_id, 1920, scr);
+    cc_rm_sequence(40, seq);
+    CU_CHECK(upload(&p->d_pbch_re, re));
+    CU_CHECK(upload(&p->d_pbch_scr, scr));
+    CU_CHECK(upload(&p->d_pbch_rm, seq));
+  }
+  PbchArgs a{};
+  a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
+  a.re = p->d_pbch_re; a.scramble = p->d_pbch_scr; a.rm_seq = p->d_pbch_rm; a.result = d_result; a.mib = d_mib;
+  a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.noise_mode = noise_mode; a.noise_est = noise_est;
+  a.k_sqpsk = (float)(100.0 * std::sqrt(2.0)); a.k_sq2 = (float)std::sqrt(2.0);
+  pbch_kernel<<<n_sf, 256, 0, (cudaStream_t)stream>>>(a);
+  p->ctx->launch_count++;
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_host_pbch_res(const srsue_gpu_cell_t* cell, int32_t* g240) {
+  if (!cell || !g240 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  pbch_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, g240);
   return 0;
 }
 

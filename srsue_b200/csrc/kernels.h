@@ -141,6 +141,20 @@ struct PhichArgs {
 };
 __global__ void phich_kernel(const PhichArgs a);
 
+struct PbchArgs {
+  const float2* sf_symbols;  // [n_sf][14 * nsc] grids of subframes 0
+  const float2* ce;          // [n_sf][ports][14 * nsc]
+  const float* meas;         // [n_sf][5]
+  const int32_t* re;         // [240] grid index of the PBCH resource elements
+  const uint32_t* scramble;  // 1920 scrambling bits, packed LSB first
+  const int32_t* rm_seq;     // [120] rate-matching order for D = 40
+  int32_t* result;           // [n_sf][4]: found, transmit ports, frame number mod 4, 0
+  uint8_t* mib;              // [n_sf][24] MIB bits, one per byte
+  int n_sf, nsc, nof_ports, noise_mode;
+  float noise_est, k_sqpsk, k_sq2;
+};
+__global__ void pbch_kernel(const PbchArgs a);
+
 struct TbArgs {
   const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
   const int32_t* cb_status;  // [n_sf * C]

@@ -400,4 +400,15 @@ void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group,
   *n_seq = (I_lowest / g + n_dmrs) % 8;
 }
 
+// slot 1, symbols 0..3, the 72 central subcarriers, k first then l; CRS positions of ports 0..3 left out (symbols 0, 1)
+void pbch_res(const CellCfg& cell, int32_t* g240) {
+  const int nsc = 12 * cell.nof_prb, k0 = nsc / 2 - 36;
+  int n = 0;
+  for (int l = 0; l < 4; l++)
+    for (int k = 0; k < 72; k++) {
+      if (l < 2 && (k0 + k) % 3 == cell.cell_id % 3) continue;
+      g240[n++] = (7 + l) * nsc + k0 + k;
+    }
+}
+
 }  // namespace srsue

@@ -67,6 +67,8 @@ void pdcch_quad_perm(int n_quad, int cell_id, std::vector<int32_t>& src);
 void cc_rm_sequence(int D, std::vector<int32_t>& seq);
 // search-space candidates (L, first CCE) of subframe sf_idx for rnti (UE-specific) or the common space
 int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int32_t* cand_L, int32_t* cand_ncce);
+// PBCH (36.211 6.6.4): grid indices of the 240 resource elements in a subframe 0
+void pbch_res(const CellCfg& cell, int32_t* g240);
 // PHICH (36.211 6.9, 36.213 9.1.2; normal CP and duration): number of groups, the 12 subcarriers of a group in symbol 0,
 // and (group, sequence) of the indicator that answers an uplink transmission
 int phich_groups(int nof_prb, int ng_x6);

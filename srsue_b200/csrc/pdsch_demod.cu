@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#include "viterbi.cuh"
 
 namespace srsue {
 
@@ -299,6 +300,73 @@ __global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
     if (c2 > v) { best = 3; }
     a.cfi[sf] = best;
     if (a.corr) { a.corr[sf * 3 + 0] = c0; a.corr[sf * 3 + 1] = c1; a.corr[sf * 3 + 2] = c2; }
+  }
+}
+
+// ---- PBCH / MIB (srslte_ue_mib_decode, phch_recv.cc:247; SPEC.md 12): one CTA of 8 warps per subframe 0.  All threads
+// turn the 240 resource elements into 480 LLRs under both transmit-port hypotheses; warp w then decodes hypothesis
+// w / 4 (1 or 2 ports) at frame position w % 4 of the 40 ms BCH period: descrambling with that quarter of the sequence,
+// exact integer soft combining onto the 120 coded bits, tail-biting Viterbi, CRC16 against the antenna mask.
+__global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
+  __shared__ int16_t s_llr[2][480];
+  __shared__ int32_t s_soft[8][120];
+  __shared__ uint32_t s_surv[8][80][2];
+  __shared__ uint8_t s_dec[8][40];
+  __shared__ int s_rem[8];
+  const int sf = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
+  const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;
+  const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
+  const int n_hyp = a.nof_ports >= 2 ? 2 : 1;
+  // hypothesis 1: every thread below 240 equalises one RE; hypothesis 2: every thread below 120 one Alamouti pair
+  if (tid < 240) {
+    const int g = a.re[tid];
+    const float2 r = y[g], h = h0p[g];
+    const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
+    const float2 d = make_float2(__fdiv_rn(dot_rn(r.x, h.x, r.y, h.y), den), __fdiv_rn(det_rn(r.y, h.x, r.x, h.y), den));
+    s_llr[0][2 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.x));
+    s_llr[0][2 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.y));
+  }
+  if (n_hyp == 2 && tid < 120) {
+    const float2* h1p = h0p + 14 * a.nsc;
+    const int g0 = a.re[2 * tid], g1 = a.re[2 * tid + 1];
+    const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
+    const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
+    const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
+    const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
+    const float c_re = dot_rn(h0.x, r1.x, h0.y, r1.y), c_im = det_rn(h0.x, r1.y, h0.y, r1.x);
+    const float e_re = dot_rn(h1.x, r0.x, h1.y, r0.y), e_im = det_rn(h1.y, r0.x, h1.x, r0.y);
+    const float2 d0 = make_float2(__fdiv_rn(__fmul_rn(__fadd_rn(a_re, b_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fadd_rn(a_im, b_im), a.k_sq2), den));
+    const float2 d1 = make_float2(__fdiv_rn(__fmul_rn(__fsub_rn(c_re, e_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fsub_rn(c_im, e_im), a.k_sq2), den));
+    s_llr[1][4 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.x));
+    s_llr[1][4 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.y));
+    s_llr[1][4 * tid + 2] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.x));
+    s_llr[1][4 * tid + 3] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.y));
+  }
+  __syncthreads();
+  const int hyp = w >> 2, q = w & 3;
+  if (hyp < n_hyp) {
+    int32_t* soft = s_soft[w];
+    for (int i = lane; i < 120; i += 32) soft[i] = 0;
+    __syncwarp();
+    for (int k = lane; k < 480; k += 32) {
+      const int bit = 480 * q + k;
+      const int v = s_llr[hyp][k];
+      atomicAdd(&soft[a.rm_seq[k % 120]], ((a.scramble[bit >> 5] >> (bit & 31)) & 1u) ? -v : v);
+    }
+    __syncwarp();
+    const int rem = viterbi_crc16_warp(soft, 24, &s_surv[w][0][0], s_dec[w], lane);
+    if (lane == 0) s_rem[w] = (rem == (hyp == 0 ? 0x0000 : 0xFFFF)) ? 1 : 0;
+  } else if (lane == 0) {
+    s_rem[w] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int hit = -1;
+    for (int c = 0; c < 8 && hit < 0; c++) if (s_rem[c]) hit = c;
+    int32_t* o = a.result + (size_t)sf * 4;
+    o[0] = hit >= 0; o[1] = hit >= 0 ? (hit >> 2) + 1 : 0; o[2] = hit >= 0 ? (hit & 3) : 0; o[3] = 0;
+    if (hit >= 0) for (int i = 0; i < 24; i++) a.mib[(size_t)sf * 24 + i] = s_dec[hit][i];
   }
 }
 

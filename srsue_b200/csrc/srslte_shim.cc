@@ -402,6 +402,90 @@ bool srslte_ue_dl_decode_phich(srslte_ue_dl_t* q, uint32_t sf_idx, uint32_t n_pr
   return ack != 0;
 }
 
+// ---- MIB ---------------------------------------------------------------------------------------------------
+namespace {
+struct MibGpu {
+  srslte_ue_dl_t ue_dl;          // front end (FFT + estimator) for two ports, so that both port hypotheses can be tried
+  int32_t* d_result = nullptr;
+  uint8_t* d_mib = nullptr;
+};
+}  // namespace
+
+int srslte_ue_mib_init(srslte_ue_mib_t* q, srslte_cell_t cell) {
+  if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  auto* m = new MibGpu();
+  srslte_cell_t c2 = cell;
+  c2.nof_ports = 2;
+  if (srslte_ue_dl_init(&m->ue_dl, c2) != SRSLTE_SUCCESS ||
+      cudaMalloc((void**)&m->d_result, 4 * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void**)&m->d_mib, 24) != cudaSuccess) {
+    srslte_ue_dl_free(&m->ue_dl);
+    cudaFree(m->d_result); cudaFree(m->d_mib);
+    delete m;
+    return SRSLTE_ERROR;
+  }
+  q->cell = cell;
+  q->gpu = m; q->pbch.gpu = m;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_ue_mib_free(srslte_ue_mib_t* q) {
+  if (!q || !q->gpu) return;
+  auto* m = static_cast<MibGpu*>(q->gpu);
+  srslte_ue_dl_free(&m->ue_dl);
+  cudaFree(m->d_result); cudaFree(m->d_mib);
+  delete m;
+  q->gpu = nullptr; q->pbch.gpu = nullptr;
+}
+
+void srslte_pbch_decode_reset(srslte_pbch_t*) {}      // nothing is accumulated between frames
+
+int srslte_ue_mib_decode(srslte_ue_mib_t* q, cf_t* input, uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN], uint32_t* nof_tx_ports,
+                         uint32_t* sfn_offset) {
+  if (!q || !q->gpu || !input || !bch_payload) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* m = static_cast<MibGpu*>(q->gpu);
+  auto* u = static_cast<UeDlGpu*>(m->ue_dl.gpu);
+  srsue_gpu_pdsch_plan_t* fp = front_plan(u, 0, 1);
+  if (!fp) return SRSLTE_ERROR;
+  if (cudaMemcpyAsync(u->d_iq, input, u->sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  if (srsue_gpu_ofdm_rx(fp, 1, u->d_iq, u->d_sf, u->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_chest(fp, 1, u->d_sf, u->d_ce, u->d_meas, u->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_pbch_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, m->d_result, m->d_mib, u->stream)) return SRSLTE_ERROR;
+  int32_t res[4];
+  uint8_t mib[24];
+  cudaMemcpyAsync(res, m->d_result, sizeof(res), cudaMemcpyDeviceToHost, u->stream);
+  cudaMemcpyAsync(mib, m->d_mib, sizeof(mib), cudaMemcpyDeviceToHost, u->stream);
+  if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
+  u->dev_valid = false;
+  if (!res[0]) return SRSLTE_UE_MIB_NOTFOUND;
+  std::memcpy(bch_payload, mib, 24);
+  if (nof_tx_ports) *nof_tx_ports = (uint32_t)res[1];
+  if (sfn_offset) *sfn_offset = (uint32_t)res[2];
+  return SRSLTE_UE_MIB_FOUND;
+}
+
+// 36.331 MasterInformationBlock: dl-Bandwidth (3), phich-Duration (1), phich-Resource (2), systemFrameNumber (8), spare (10)
+void srslte_pbch_mib_unpack(uint8_t* msg, srslte_cell_t* cell, uint32_t* sfn) {
+  if (!msg) return;
+  auto field = [&](int pos, int n) { uint32_t v = 0; for (int i = 0; i < n; i++) v = (v << 1) | (msg[pos + i] & 1); return v; };
+  static const uint32_t bw[8] = {6, 15, 25, 50, 75, 100, 0, 0};
+  if (cell) {
+    cell->nof_prb = bw[field(0, 3)];
+    cell->phich_length = field(3, 1) ? SRSLTE_PHICH_EXT : SRSLTE_PHICH_NORM;
+    cell->phich_resources = (srslte_phich_resources_t)field(4, 2);
+  }
+  if (sfn) *sfn = field(6, 8) << 2;
+}
+
+void srslte_pbch_mib_pack(srslte_cell_t* cell, uint32_t sfn, uint8_t* msg) {
+  if (!cell || !msg) return;
+  uint32_t b = 0;
+  for (; b < 6; b++) { static const uint32_t bw[6] = {6, 15, 25, 50, 75, 100}; if (bw[b] == cell->nof_prb) break; }
+  const uint32_t v = (b << 21) | ((cell->phich_length == SRSLTE_PHICH_EXT ? 1u : 0u) << 20) | ((uint32_t)cell->phich_resources << 18) |
+                     (((sfn >> 2) & 0xFFu) << 10);
+  for (int i = 0; i < 24; i++) msg[i] = (uint8_t)((v >> (23 - i)) & 1u);
+}
+
 void srslte_sch_set_max_noi(srslte_sch_t* q, uint32_t max_iterations) { if (q) q->max_iterations = max_iterations; }
 uint32_t srslte_pdsch_last_noi(srslte_pdsch_t* q) { return q ? q->dl_sch.nof_iterations : 0; }
 

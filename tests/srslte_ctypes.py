@@ -78,3 +78,7 @@ def make_grant(nof_prb, qm, tbs, prbs=None):
     g.mcs.tbs = tbs
     g.mcs.idx = 0
     return g
+
+
+class UeMib(C.Structure):
+    _fields_ = [("pbch", C.c_void_p), ("cell", Cell), ("gpu", C.c_void_p)]

@@ -42,7 +42,9 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_softbuffer_rx_reset_tbs", "srslte_softbuffer_rx_free", "srslte_ue_dl_decode", "srslte_ue_dl_decode_rnti",
               "srslte_tdec_init", "srslte_tdec_free", "srslte_tdec_reset", "srslte_tdec_iteration", "srslte_tdec_decision",
               "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz",
-              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce", "srslte_ue_dl_decode_phich"]:
+              "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce", "srslte_ue_dl_decode_phich",
+              "srslte_ue_mib_init", "srslte_ue_mib_free", "srslte_ue_mib_decode", "srslte_pbch_decode_reset", "srslte_pbch_mib_unpack",
+              "srslte_pbch_mib_pack"]:
         assert hasattr(lib, n), n
 
 

@@ -341,3 +341,82 @@ def test_phich_matches_oracle(gpu, oracle, prb, ports, cid):
                 if snr > 0:
                     assert a == acks[i][j]
         plan.close()
+
+
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (6, 2, 2), (25, 2, 77), (50, 1, 301), (75, 2, 8), (100, 1, 503), (100, 2, 0)])
+def test_pbch_mib_matches_oracle(gpu, oracle, prb, ports, cid):
+    """blind MIB decode from subframes 0 (port hypotheses x frame positions): verdict, MIB bits, detected number of ports
+    and frame offset equal the oracle's; at a reliable SNR they equal what was sent"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    ocell = o.make_cell(prb, ports, cid)
+    cell = sg.make_cell(prb, ports, cid)
+    for snr in (6.0, -9.0):
+        sfns = [0, 5, 1022, 1023, 640]
+        n = len(sfns)
+        mibs = [o.mib_pack(prb, 0, 6, s) for s in sfns]
+        iq = []
+        for i, s in enumerate(sfns):
+            ocfg = o.make_cfg(ocell, sf_idx=0, cfi=2, qm=2, tbs=104, tm=ports, prbs=[0] if prb > 6 else None)
+            iq.append(o.gen_subframe(ocell, ocfg, 7000 + i, snr, None, pcfich=True, mib=(mibs[i], s % 4))[1])
+        iq = np.stack(iq)
+        cfg = sg.make_cfg(cell, sf_idx=0, cfi=2, qm=2, tbs=0, tm=ports)
+        plan = sg.PdschPlan(ctx, cell, cfg, n)
+        I = plan.info
+        d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+        d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+        d_res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+        d_mib = torch.zeros((n, 24), dtype=torch.uint8, device="cuda")
+        plan.ofdm_rx(n, d_iq, d_sf)
+        plan.chest(n, d_sf, d_ce, d_meas)
+        plan.pbch_decode(n, d_sf, d_ce, d_meas, 0.0, 1, d_res, d_mib)
+        torch.cuda.synchronize()
+        res, mib_g = d_res.cpu().numpy(), d_mib.cpu().numpy()
+        for i, s in enumerate(sfns):
+            sf_o = o.ofdm_rx(prb, iq[i])
+            ce_o, meas_o = o.chest(ocell, 0, sf_o)
+            f, bits, p, q = o.pbch_decode(ocell, sf_o, ce_o, meas_o[0])
+            assert res[i, 0] == f
+            if f:
+                assert (res[i, 1], res[i, 2]) == (p, q) and np.array_equal(mib_g[i], bits)
+            if snr > 0:
+                assert f == 1 and p == ports and q == s % 4 and np.array_equal(bits, mibs[i])
+        plan.close()
+
+
+def test_srslte_ue_mib_decode_shim(gpu, oracle):
+    """phch_recv's MIB step (phch_recv.cc:246-253): srslte_ue_mib_decode on the samples of a subframe 0, then
+    srslte_pbch_mib_unpack -> bandwidth, PHICH configuration, SFN"""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeMib, Cell
+    prb, ports, cid, sfn = 50, 2, 123, 777
+    ocell = o.make_cell(prb, ports, cid)
+    ocfg = o.make_cfg(ocell, sf_idx=0, cfi=1, qm=2, tbs=104, tm=2, prbs=[3])
+    mib = o.mib_pack(prb, 0, 3, sfn)                     # Ng = 1/2
+    iq = o.gen_subframe(ocell, ocfg, 99, 8.0, None, pcfich=True, mib=(mib, sfn % 4))[1]
+    q = UeMib()
+    cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=cid, cp=0, phich_length=0, phich_resources=0)   # ports unknown yet
+    assert L.srslte_ue_mib_init(C.byref(q), cell) == 0
+    L.srslte_pbch_decode_reset(C.byref(q))
+    payload = (C.c_uint8 * 24)()
+    nports, off = C.c_uint32(0), C.c_uint32(0)
+    assert L.srslte_ue_mib_decode(C.byref(q), iq.ctypes.data_as(C.c_void_p), payload, C.byref(nports), C.byref(off)) == 1
+    assert nports.value == 2 and off.value == sfn % 4 and np.array_equal(np.frombuffer(payload, np.uint8), mib)
+    out_cell, out_sfn = Cell(), C.c_uint32(0)
+    L.srslte_pbch_mib_unpack(payload, C.byref(out_cell), C.byref(out_sfn))
+    assert out_cell.nof_prb == prb and out_cell.phich_resources == 1 and out_cell.phich_length == 0
+    assert out_sfn.value + off.value == sfn              # the MIB carries SFN / 4, the offset the two LSBs
+    packed = (C.c_uint8 * 24)()
+    out_cell.phich_resources = 1
+    L.srslte_pbch_mib_pack(C.byref(out_cell), sfn, packed)
+    assert np.array_equal(np.frombuffer(packed, np.uint8), mib)
+    # noise only: nothing found
+    noise = (np.random.default_rng(1).standard_normal((len(iq), 2)) @ np.array([1, 1j])).astype(np.complex64)
+    assert L.srslte_ue_mib_decode(C.byref(q), noise.ctypes.data_as(C.c_void_p), payload, C.byref(nports), C.byref(off)) == 0
+    L.srslte_ue_mib_free(C.byref(q))
