@@ -460,8 +460,12 @@ def main():
             "e2e": {"value": e2e_bits_all / e2e_s_max / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": nbytes_iq,
                     "d2h_bytes_per_step": EB * (I.payload_stride + 16), "subframes_per_step": EB},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "alu", "kernel": "turbo_decode_kernel", "achieved": turbo_tops, "peak": alu_peak_tops,
+            "roofline": {"bound": "alu", "kernel": "turbo_decode_crc_kernel", "achieved": turbo_tops, "peak": alu_peak_tops,
                          "unit": "Tint16op/s", "frac": turbo_tops / alu_peak_tops, "traffic": None,
+                         "algorithmic_ops_per_launch": turbo_ops, "launch_ms": stage_ms[3],
+                         "ncu_evidence": {"source": "profiles/chain_kernels_r01_v3.ncu.txt (batch 1024 = 13312 code blocks per launch)",
+                                          "alu_pipe_pct": 55.4, "issue_active_pct": 52.9, "dram_bytes_per_launch": 883.9e6,
+                                          "algorithmic_bytes_per_launch": 475.2e6},
                          "peak_source": "measured VIADD.16x2 + VIADDMNMX.S16x2 issue rates at %.0f MHz (profiles/alu_peak_r01.json)" % sm_max,
                          "note": "integer-ALU bound (north star); HBM-bound front-end kernels are listed in `stages`"},
             "stages": stages,
