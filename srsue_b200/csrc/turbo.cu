@@ -143,7 +143,11 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   const int gstride = 2 * T;                       // uint4 per 8-step group
   const uint4* sysq = c.in4 + 2 * t;
   const uint4* yq = sysq + (DEC ? 2 : 1) * (plane / 8);
-  uint4* ckpt4 = g.ckpt + (size_t)c.gslot * (size_t)(nsw * gstride) + 2 * t;
+  // checkpoints of one CTA are laid out [sub-window][slot][thread]: for small code blocks (few threads per slot) the
+  // slots a warp spans are then contiguous, one 16-byte access per thread = whole 128-byte lines
+  const int slot_in_cta = (int)(c.gslot - blockIdx.x * g.ncb_cta);
+  const int cstride = g.ncb_cta * gstride;         // uint4 per sub-window of the whole CTA
+  uint4* ckpt4 = g.ckpt + (size_t)blockIdx.x * (size_t)(nsw * cstride) + slot_in_cta * gstride + 2 * t;
   uint16_t* bits = reinterpret_cast<uint16_t*>(g.bits_scratch) + (size_t)c.gslot * (size_t)plane;
   int16_t* A16 = reinterpret_cast<int16_t*>(c.Aw);
 
@@ -219,7 +223,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 #pragma unroll
         for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
       }
-      if (sw) st8(ckpt4 + sw * gstride, b);         // thread-private scratch, read back in pass 2 (group 0 stays in registers)
+      if (sw) st8(ckpt4 + sw * cstride, b);         // thread-private scratch, read back in pass 2 (group 0 stays in registers)
 #pragma unroll
       for (int i = kSW - 1; i >= 0; i--) {
         uint32_t nb[8];
@@ -272,7 +276,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
       if (sw + 1 < nsw) {
         ld8(yq + (sw + 1) * gstride, ny);
         if (DEC == 0) ld8(sysq + (sw + 1) * gstride, ns);
-        ldp8(ckpt4 + (sw + 1) * gstride, nbeta);
+        ldp8(ckpt4 + (sw + 1) * cstride, nbeta);
       }
 #pragma unroll
       for (int i = kSW - 1; i >= 1; i--) {
