@@ -214,6 +214,37 @@ SRSLTE_API void srslte_tdec_decision_byte(srslte_tdec_t *h, uint8_t *output, uin
 SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *output, uint32_t nof_iterations,
                                    uint32_t long_cb);
 
+/* ---- cell search (ue/src/phy/phch_recv.cc:140-188) --------------------------------------------------- */
+typedef struct SRSLTE_API { uint32_t full_secs; double frac_secs; } srslte_timestamp_t;
+typedef struct SRSLTE_API { double gain; } srslte_agc_t;
+typedef struct SRSLTE_API { srslte_agc_t agc; } srslte_ue_sync_t;      /* only what init_cell dereferences: cs.ue_sync.agc */
+typedef struct SRSLTE_API {
+  uint32_t cell_id;
+  srslte_cp_t cp;
+  float peak;          /* mean peak-to-side ratio of the frames that agreed on this cell */
+  float mode;          /* fraction of the scanned frames that agreed */
+  float psr;
+  float cfo;           /* Hz */
+} srslte_ue_cellsearch_result_t;
+typedef struct SRSLTE_API {
+  srslte_ue_sync_t ue_sync;
+  uint32_t nof_frames_to_scan;
+  float detect_threshold;
+  void *gpu;
+} srslte_ue_cellsearch_t;
+/* recv_callback(handler, buffer, nsamples, rx_time) delivers nsamples cf_t at 1.92 Msps (radio_recv_wrapper_cs,
+ * phch_recv.cc:73): the scan pulls nof_frames_to_scan x 5 ms through it, searches them in one batch on the device and
+ * returns the cell most frames agree on.  scan: > 0 found (found_cells[*max_N_id_2] filled), 0 nothing, < 0 error. */
+SRSLTE_API int srslte_ue_cellsearch_init(srslte_ue_cellsearch_t *q,
+                                         int (*recv_callback)(void *, void *, uint32_t, srslte_timestamp_t *), void *stream_handler);
+SRSLTE_API void srslte_ue_cellsearch_free(srslte_ue_cellsearch_t *q);
+SRSLTE_API int srslte_ue_cellsearch_set_nof_frames_to_scan(srslte_ue_cellsearch_t *q, uint32_t nof_frames);
+SRSLTE_API void srslte_ue_cellsearch_set_threshold(srslte_ue_cellsearch_t *q, float threshold);
+SRSLTE_API int srslte_ue_cellsearch_scan(srslte_ue_cellsearch_t *q, srslte_ue_cellsearch_result_t found_cells[3], uint32_t *max_N_id_2);
+SRSLTE_API int srslte_ue_cellsearch_scan_N_id_2(srslte_ue_cellsearch_t *q, uint32_t N_id_2, srslte_ue_cellsearch_result_t *found_cell);
+SRSLTE_API int srslte_ue_sync_start_agc(srslte_ue_sync_t *q, double (*set_gain_callback)(void *, double), float init_gain_value);
+SRSLTE_API float srslte_agc_get_gain(srslte_agc_t *q);
+
 /* ---- MIB decode (ue/src/phy/phch_recv.cc:98,246-253) ------------------------------------------------- */
 #define SRSLTE_BCH_PAYLOAD_LEN 24
 #define SRSLTE_UE_MIB_FOUND 1

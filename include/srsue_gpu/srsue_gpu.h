@@ -68,6 +68,23 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t *ctx);
 const char *srsue_gpu_last_error(void);
 int srsue_gpu_version(void);
 
+/* ---- cell search (srslte_ue_cellsearch_scan, ue/src/phy/phch_recv.cc:146-177) -------------------- */
+typedef struct {
+  int32_t peak_pos;     /* first sample of the PSS symbol body (after its cyclic prefix) inside the buffer */
+  int32_t n_id_2;       /* 0..2 */
+  int32_t n_id_1;       /* 0..167, -1 when the SSS symbol does not lie inside the buffer (peak_pos < 137) */
+  int32_t sf5;          /* 0: the PSS belongs to subframe 0, 1: to subframe 5 */
+  int32_t valid;
+  float peak;           /* |correlation|^2 at the peak */
+  float mean_power;     /* mean of |correlation|^2 over all roots and positions (peak / mean_power = peak-to-side ratio) */
+  float cfo;            /* carrier frequency offset in units of the 15 kHz subcarrier spacing */
+  float sss_corr;
+} srsue_gpu_sync_result_t;
+/* d_iq: n_bufs buffers of n_samples (>= 265; typically a 5 ms half frame = 9600) at 1.92 Msps, `stride` samples apart.
+ * force_n_id_2: -1 searches the three PSS roots, 0..2 only that one.  Cell id = 3 * n_id_1 + n_id_2. */
+int srsue_gpu_cell_search(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride,
+                          int force_n_id_2, srsue_gpu_sync_result_t *d_result, void *stream);
+
 /* ---- turbo decoder (device pointers; `stream` is a cudaStream_t passed as void*) ------------ */
 /* geometry of the windowed decoder for code-block size K: window length, windows, tcb elements */
 int srsue_gpu_tdec_geometry(int K, int *W, int *P, int *cb_elems);

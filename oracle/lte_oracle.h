@@ -124,6 +124,13 @@ int  lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng
 uint16_t lteo_pdcch_decode_candidate(const int16_t *llr, int L, int nof_bits, uint8_t *bits_out);
 int  lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rnti, int common, int nof_bits,
                          uint8_t *bits_out, int *found_L, int *found_ncce);
+/* ---- cell search: PSS / SSS (SPEC.md 13; lteo_sync.c) ---- */
+void  lteo_pss_seq(int n_id_2, lteo_cd_t *d62);
+void  lteo_sss_seq(int n_id_1, int n_id_2, int sf5, int8_t *d62);
+void  lteo_sync_tx(const lteo_cell_t *cell, int sf_idx, lteo_cd_t *grid);
+void  lteo_pss_time(int n_id_2, lteo_cf_t *t128);
+float lteo_pss_search(const lteo_cf_t *x, int n_samples, int *peak_pos, int *n_id_2, float *cfo, float *mean_power);
+int   lteo_sss_detect(const lteo_cf_t *x, int peak_pos, int n_id_2, int *sf5, float *corr);
 /* ---- PBCH / MIB (SPEC.md 12) ---- */
 uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out);
 void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240);

@@ -413,6 +413,23 @@ def phich_decode(cell, sf_idx, sf, ce, n_group, n_seq, noise_est=0.0, ng_x6=6):
     return ack, np.float32(m.value)
 
 
+def pss_search(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    pos, nid2 = C.c_int(), C.c_int()
+    cfo, mp = C.c_float(), C.c_float()
+    lib().lteo_pss_search.restype = C.c_float
+    peak = lib().lteo_pss_search(_p(x), len(x), C.byref(pos), C.byref(nid2), C.byref(cfo), C.byref(mp))
+    return dict(peak=np.float32(peak), pos=pos.value, n_id_2=nid2.value, cfo=np.float32(cfo.value), mean_power=np.float32(mp.value))
+
+
+def sss_detect(x, peak_pos, n_id_2):
+    x = np.ascontiguousarray(x, np.complex64)
+    sf5 = C.c_int()
+    corr = C.c_float()
+    n1 = lib().lteo_sss_detect(_p(x), peak_pos, n_id_2, C.byref(sf5), C.byref(corr))
+    return n1, sf5.value, np.float32(corr.value)
+
+
 def mib_pack(nof_prb, phich_ext, ng_x6, sfn):
     """the 24 MIB bits (36.331): dl-Bandwidth, phich-Duration, phich-Resource, the 8 MSBs of the SFN, 10 spare zeros"""
     bw = [6, 15, 25, 50, 75, 100].index(nof_prb)
@@ -438,7 +455,7 @@ def pbch_llr(cell, hyp_ports, sf, ce, noise_est=0.0):
     return llr
 
 
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None, mib=None):
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None, mib=None, sync=False):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -450,6 +467,8 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=Non
         lib().lteo_pcfich_tx(C.byref(cell), cfg.sf_idx, cfg.cfi, _p(grid))
     if dcis:            # PDCCHs of this subframe: list of (bits, rnti, L, ncce)
         pdcch_tx(cell, cfg.sf_idx, cfg.cfi, dcis, grid, ng_x6)
+    if sync and cfg.sf_idx in (0, 5):     # PSS + SSS of the cell
+        lib().lteo_sync_tx(C.byref(cell), cfg.sf_idx, _p(grid))
     if mib is not None:     # (24 MIB bits, radio frame number mod 4): PBCH of a subframe 0
         assert cfg.sf_idx == 0
         mb = np.ascontiguousarray(mib[0], np.uint8)

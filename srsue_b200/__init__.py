@@ -33,6 +33,12 @@ class SfDesc(C.Structure):
                 ("meas", C.c_float * 5)]
 
 
+class SyncResult(C.Structure):
+    """srsue_gpu_sync_result_t"""
+    _fields_ = [("peak_pos", C.c_int32), ("n_id_2", C.c_int32), ("n_id_1", C.c_int32), ("sf5", C.c_int32), ("valid", C.c_int32),
+                ("peak", C.c_float), ("mean_power", C.c_float), ("cfo", C.c_float), ("sss_corr", C.c_float)]
+
+
 class GpuError(RuntimeError):
     pass
 
@@ -117,6 +123,11 @@ class Context:
     def tdec_run_all_host(self, h_triples, n_cb, K, max_iter, crc_type, h_bits, h_status):
         _check(lib().srsue_gpu_tdec_run_all_host(self.h, _ptr(h_triples), n_cb, K, max_iter, crc_type, _ptr(h_bits),
                                                  _ptr(h_status)), "tdec_run_all_host")
+
+    def cell_search(self, d_iq, n_bufs, n_samples, stride, d_result, force_n_id_2=-1):
+        lib().srsue_gpu_cell_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+        _check(lib().srsue_gpu_cell_search(self.h, _ptr(d_iq), n_bufs, n_samples, stride, force_n_id_2, _ptr(d_result), _stream()),
+               "cell_search")
 
     def tdec_last_launch(self):
         g, b, s, n = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -155,6 +155,24 @@ struct PbchArgs {
 };
 __global__ void pbch_kernel(const PbchArgs a);
 
+// result of the cell search on one buffer (mirrors srsue_gpu_sync_result_t of the C ABI)
+struct srsue_sync_result { int32_t peak_pos, n_id_2, n_id_1, sf5, valid; float peak, mean_power, cfo, sss_corr; };
+struct SyncArgs {
+  const float2* iq;          // [n_bufs][stride] samples at 1.92 Msps
+  long long stride;
+  int n_samples, n_bufs;
+  int force_n_id_2;          // -1: search the three roots, else only this one
+  const float2* pss_time;    // [3][128]
+  const float2* pss_freq;    // [3][62]
+  const int8_t* sss;         // [3][2][168][62]
+  const float2* tw128;       // 64 twiddles of the 128-point transform
+  unsigned long long* peak_key;   // [n_bufs] scratch, zeroed before the launch
+  double* power_sum;              // [n_bufs] scratch, zeroed before the launch
+  srsue_sync_result* result;      // [n_bufs]
+};
+__global__ void pss_corr_kernel(const SyncArgs a);
+__global__ void sss_detect_kernel(const SyncArgs a);
+
 struct TbArgs {
   const uint8_t* cb_bits;    // [n_sf * C][cb_bits_stride] packed hard bits per code block
   const int32_t* cb_status;  // [n_sf * C]

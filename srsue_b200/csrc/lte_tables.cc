@@ -411,4 +411,62 @@ void pbch_res(const CellCfg& cell, int32_t* g240) {
     }
 }
 
+// ---- synchronisation signals.  Replace the sequence generators behind srslte_ue_cellsearch_scan
+// (/root/reference/ue/src/phy/phch_recv.cc:146-177): srsLTE's pss.c / sss.c.
+namespace {
+void pss_freq_d(int n_id_2, double* re, double* im) {
+  static const int roots[3] = {25, 29, 34};
+  const int u = roots[n_id_2];
+  for (int n = 0; n < 62; n++) {
+    const int m = (n < 31) ? n * (n + 1) : (n + 1) * (n + 2);
+    const double a = -M_PI * (double)u * (double)(m % 126) / 63.0;
+    re[n] = std::cos(a); im[n] = std::sin(a);
+  }
+}
+void mseq31(int taps, int8_t* s31) {
+  int x[31] = {0, 0, 0, 0, 1};
+  for (int i = 0; i < 26; i++) {
+    int v = 0;
+    for (int j = 0; j < 5; j++) if (taps & (1 << j)) v ^= x[i + j];
+    x[i + 5] = v;
+  }
+  for (int i = 0; i < 31; i++) s31[i] = (int8_t)(1 - 2 * x[i]);
+}
+}  // namespace
+
+void pss_freq(int n_id_2, float* d62x2) {
+  double re[62], im[62];
+  pss_freq_d(n_id_2, re, im);
+  for (int n = 0; n < 62; n++) { d62x2[2 * n] = (float)re[n]; d62x2[2 * n + 1] = (float)im[n]; }
+}
+
+void pss_time(int n_id_2, float* t128x2) {
+  double dr[62], di[62];
+  pss_freq_d(n_id_2, dr, di);
+  for (int n = 0; n < 128; n++) {
+    double re = 0, im = 0;
+    for (int i = 0; i < 62; i++) {
+      const int bin = (i < 31) ? i - 31 : i - 30;
+      const double a = 2.0 * M_PI * (double)(bin * n) / 128.0;
+      re += dr[i] * std::cos(a) - di[i] * std::sin(a);
+      im += dr[i] * std::sin(a) + di[i] * std::cos(a);
+    }
+    t128x2[2 * n] = (float)(re / std::sqrt(128.0)); t128x2[2 * n + 1] = (float)(im / std::sqrt(128.0));
+  }
+}
+
+void sss_seq(int n_id_1, int n_id_2, int sf5, int8_t* d62) {
+  int8_t s[31], c[31], z[31];
+  mseq31(0x05, s); mseq31(0x09, c); mseq31(0x17, z);
+  const int qp = n_id_1 / 30, q = (n_id_1 + qp * (qp + 1) / 2) / 30, mp = n_id_1 + q * (q + 1) / 2;
+  const int m0 = mp % 31, m1 = (m0 + mp / 31 + 1) % 31;
+  for (int n = 0; n < 31; n++) {
+    const int s0 = s[(n + m0) % 31], s1 = s[(n + m1) % 31];
+    const int c0 = c[(n + n_id_2) % 31], c1 = c[(n + n_id_2 + 3) % 31];
+    const int z0 = z[(n + (m0 % 8)) % 31], z1 = z[(n + (m1 % 8)) % 31];
+    if (!sf5) { d62[2 * n] = (int8_t)(s0 * c0); d62[2 * n + 1] = (int8_t)(s1 * c1 * z0); }
+    else { d62[2 * n] = (int8_t)(s1 * c0); d62[2 * n + 1] = (int8_t)(s0 * c1 * z1); }
+  }
+}
+
 }  // namespace srsue

@@ -67,6 +67,11 @@ void pdcch_quad_perm(int n_quad, int cell_id, std::vector<int32_t>& src);
 void cc_rm_sequence(int D, std::vector<int32_t>& seq);
 // search-space candidates (L, first CCE) of subframe sf_idx for rnti (UE-specific) or the common space
 int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int32_t* cand_L, int32_t* cand_ncce);
+// Cell search (36.211 6.11): PSS in frequency (62 values) and as a 128-sample time replica at 1.92 Msps (both evaluated in
+// double and rounded once, interleaved re/im), SSS as +-1 for (N_id_1, N_id_2, subframe 0 or 5)
+void pss_freq(int n_id_2, float* d62x2);
+void pss_time(int n_id_2, float* t128x2);
+void sss_seq(int n_id_1, int n_id_2, int sf5, int8_t* d62);
 // PBCH (36.211 6.6.4): grid indices of the 240 resource elements in a subframe 0
 void pbch_res(const CellCfg& cell, int32_t* g240);
 // PHICH (36.211 6.9, 36.213 9.1.2; normal CP and duration): number of groups, the 12 subcarriers of a group in symbol 0,

@@ -402,6 +402,115 @@ bool srslte_ue_dl_decode_phich(srslte_ue_dl_t* q, uint32_t sf_idx, uint32_t n_pr
   return ack != 0;
 }
 
+// ---- cell search ---------------------------------------------------------------------------------------------
+namespace {
+struct CellSearchGpu {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  int (*recv)(void*, void*, uint32_t, srslte_timestamp_t*) = nullptr;
+  void* handler = nullptr;
+  srsue_gpu_cf_t* h_iq = nullptr;     // pinned staging for the scanned frames
+  srsue_gpu_cf_t* d_iq = nullptr;
+  srsue_gpu_sync_result_t* d_res = nullptr;
+  uint32_t cap_frames = 0;
+  cudaStream_t stream = nullptr;
+};
+constexpr int kHalfFrame = 9600;       // 5 ms at 1.92 Msps
+
+int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_result_t* out, uint32_t* n_id_2_out) {
+  auto* g = static_cast<CellSearchGpu*>(q->gpu);
+  const uint32_t nf = q->nof_frames_to_scan ? q->nof_frames_to_scan : 8;
+  if (nf > g->cap_frames) {
+    if (g->h_iq) cudaFreeHost(g->h_iq);
+    cudaFree(g->d_iq); cudaFree(g->d_res);
+    g->h_iq = nullptr; g->d_iq = nullptr; g->d_res = nullptr; g->cap_frames = 0;
+    if (cudaMallocHost((void**)&g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t)) != cudaSuccess ||
+        cudaMalloc((void**)&g->d_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t)) != cudaSuccess ||
+        cudaMalloc((void**)&g->d_res, (size_t)nf * sizeof(srsue_gpu_sync_result_t)) != cudaSuccess) return SRSLTE_ERROR;
+    g->cap_frames = nf;
+  }
+  srslte_timestamp_t ts;
+  for (uint32_t f = 0; f < nf; f++)
+    if (g->recv(g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+  if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
+  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, force, g->d_res, g->stream)) return SRSLTE_ERROR;
+  std::vector<srsue_gpu_sync_result_t> res(nf);
+  cudaMemcpyAsync(res.data(), g->d_res, nf * sizeof(srsue_gpu_sync_result_t), cudaMemcpyDeviceToHost, g->stream);
+  if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
+  // detections: frames whose peak-to-side ratio reaches the threshold and whose SSS lies inside the frame; the cell
+  // most of them agree on wins (srsLTE takes the mode of the per-frame candidates as well)
+  std::map<int, int> votes;
+  for (const auto& r : res)
+    if (r.valid && r.mean_power > 0.f && r.peak / r.mean_power >= q->detect_threshold) votes[3 * r.n_id_1 + r.n_id_2]++;
+  int best_id = -1, best_votes = 0;
+  for (const auto& kv : votes) if (kv.second > best_votes) { best_votes = kv.second; best_id = kv.first; }
+  if (best_id < 0) return 0;
+  double psr = 0, cfo = 0;
+  for (const auto& r : res)
+    if (r.valid && 3 * r.n_id_1 + r.n_id_2 == best_id && r.peak / r.mean_power >= q->detect_threshold) { psr += r.peak / r.mean_power; cfo += r.cfo; }
+  std::memset(out, 0, sizeof(*out));
+  out->cell_id = (uint32_t)best_id;
+  out->cp = SRSLTE_CP_NORM;
+  out->peak = out->psr = (float)(psr / best_votes);
+  out->mode = (float)best_votes / (float)nf;
+  out->cfo = (float)(cfo / best_votes * 15000.0);
+  if (n_id_2_out) *n_id_2_out = (uint32_t)(best_id % 3);
+  return best_votes;
+}
+}  // namespace
+
+int srslte_ue_cellsearch_init(srslte_ue_cellsearch_t* q, int (*recv_callback)(void*, void*, uint32_t, srslte_timestamp_t*), void* stream_handler) {
+  if (!q || !recv_callback) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  srsue_gpu_ctx_t* ctx = shared_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  auto* g = new CellSearchGpu();
+  g->ctx = ctx; g->recv = recv_callback; g->handler = stream_handler;
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return SRSLTE_ERROR; }
+  q->gpu = g;
+  q->nof_frames_to_scan = 8;
+  q->detect_threshold = 10.0f;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_ue_cellsearch_free(srslte_ue_cellsearch_t* q) {
+  if (!q || !q->gpu) return;
+  auto* g = static_cast<CellSearchGpu*>(q->gpu);
+  if (g->h_iq) cudaFreeHost(g->h_iq);
+  cudaFree(g->d_iq); cudaFree(g->d_res);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  q->gpu = nullptr;
+}
+
+int srslte_ue_cellsearch_set_nof_frames_to_scan(srslte_ue_cellsearch_t* q, uint32_t nof_frames) {
+  if (!q || nof_frames == 0 || nof_frames > 1024) return SRSLTE_ERROR_INVALID_INPUTS;
+  q->nof_frames_to_scan = nof_frames;
+  return SRSLTE_SUCCESS;
+}
+void srslte_ue_cellsearch_set_threshold(srslte_ue_cellsearch_t* q, float threshold) { if (q) q->detect_threshold = threshold; }
+
+int srslte_ue_cellsearch_scan(srslte_ue_cellsearch_t* q, srslte_ue_cellsearch_result_t found_cells[3], uint32_t* max_N_id_2) {
+  if (!q || !q->gpu || !found_cells) return SRSLTE_ERROR_INVALID_INPUTS;
+  srslte_ue_cellsearch_result_t r;
+  uint32_t n2 = 0;
+  const int rc = cellsearch_run(q, -1, &r, &n2);
+  if (rc > 0) { found_cells[n2] = r; if (max_N_id_2) *max_N_id_2 = n2; }
+  return rc;
+}
+
+int srslte_ue_cellsearch_scan_N_id_2(srslte_ue_cellsearch_t* q, uint32_t N_id_2, srslte_ue_cellsearch_result_t* found_cell) {
+  if (!q || !q->gpu || !found_cell || N_id_2 > 2) return SRSLTE_ERROR_INVALID_INPUTS;
+  return cellsearch_run(q, (int)N_id_2, found_cell, nullptr);
+}
+
+// automatic gain control is the radio's business here: the callback is remembered by nobody and the gain stays as set
+int srslte_ue_sync_start_agc(srslte_ue_sync_t* q, double (*)(void*, double), float init_gain_value) {
+  if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
+  q->agc.gain = init_gain_value;
+  return SRSLTE_SUCCESS;
+}
+float srslte_agc_get_gain(srslte_agc_t* q) { return q ? (float)q->gain : 0.f; }
+
 // ---- MIB ---------------------------------------------------------------------------------------------------
 namespace {
 struct MibGpu {

@@ -44,7 +44,9 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_tdec_decision_byte", "srslte_tdec_run_all", "srslte_vec_malloc", "srslte_symbol_sz",
               "srslte_pdcch_extract_llr", "srslte_ue_dl_find_dl_dci_type", "srslte_ue_dl_find_ul_dci", "srslte_ue_dl_get_ncce", "srslte_ue_dl_decode_phich",
               "srslte_ue_mib_init", "srslte_ue_mib_free", "srslte_ue_mib_decode", "srslte_pbch_decode_reset", "srslte_pbch_mib_unpack",
-              "srslte_pbch_mib_pack"]:
+              "srslte_pbch_mib_pack", "srslte_ue_cellsearch_init", "srslte_ue_cellsearch_free", "srslte_ue_cellsearch_scan",
+              "srslte_ue_cellsearch_scan_N_id_2", "srslte_ue_cellsearch_set_nof_frames_to_scan", "srslte_ue_cellsearch_set_threshold",
+              "srslte_ue_sync_start_agc", "srslte_agc_get_gain"]:
         assert hasattr(lib, n), n
 
 

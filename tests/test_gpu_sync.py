@@ -1,0 +1,115 @@
+"""Cell search (srsue_gpu_cell_search): PSS position / N_id_2 / peak power, SSS cell group and subframe 0-or-5, CFO, against
+the oracle on synthetic 1.92 Msps half frames (a 6-PRB cell is exactly that rate) with random timing offsets, carrier
+offsets and noise (reference: srslte_ue_cellsearch_scan, phch_recv.cc:146-177)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _half_frame(o, cell, first_sf, seed, snr, cfo, shift):
+    out = []
+    for i in range(5):
+        cfg = o.make_cfg(cell, sf_idx=first_sf + i, cfi=2, qm=2, tbs=104, tm=cell.nof_ports)
+        out.append(o.gen_subframe(cell, cfg, seed + i, snr, None, pcfich=True, sync=True)[1])
+    x = np.concatenate(out)
+    x = x * np.exp(2j * np.pi * cfo * np.arange(len(x)) / 128)
+    return np.roll(x, shift).astype(np.complex64)
+
+
+def test_cell_search_matches_oracle(gpu, oracle):
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    rng = np.random.default_rng(11)
+    cases = []
+    for cid in (0, 1, 2, 77, 150, 301, 503, 250):
+        for first in (0, 5):
+            cases.append((cid, first, float(rng.choice([12.0, 3.0, -2.0])), float(rng.uniform(-0.3, 0.3)), int(rng.integers(0, 8000))))
+    cases.append((33, 0, -25.0, 0.0, 100))          # noise only: whatever is found must still equal the oracle
+    bufs = np.stack([_half_frame(o, o.make_cell(6, 1 + (cid % 2), cid), first, 100 * cid + first, snr, cfo, shift)
+                     for cid, first, snr, cfo, shift in cases])
+    n, ns = bufs.shape
+    d_iq = torch.from_numpy(bufs.view(np.float32).reshape(n, -1)).cuda()
+    d_res = torch.zeros(n * C.sizeof(sg.SyncResult), dtype=torch.uint8, device="cuda")
+    ctx.cell_search(d_iq, n, ns, ns, d_res)
+    torch.cuda.synchronize()
+    res = (sg.SyncResult * n).from_buffer_copy(d_res.cpu().numpy().tobytes())
+    for i, (cid, first, snr, cfo, shift) in enumerate(cases):
+        r, ref = res[i], o.pss_search(bufs[i])
+        assert (r.peak_pos, r.n_id_2) == (ref["pos"], ref["n_id_2"])
+        assert np.float32(r.peak) == ref["peak"]                                     # bit-identical correlation power
+        assert abs(r.mean_power - ref["mean_power"]) <= 1e-5 * ref["mean_power"]
+        assert abs(r.cfo - ref["cfo"]) <= 1e-5
+        if ref["pos"] >= 137:
+            n1, sf5, corr = o.sss_detect(bufs[i], ref["pos"], ref["n_id_2"])
+            assert r.valid == 1 and (r.n_id_1, r.sf5) == (n1, sf5) and np.float32(r.sss_corr) == corr
+        else:
+            assert r.valid == 0 and r.n_id_1 == -1
+        if snr > 0:
+            assert r.peak_pos == (832 + shift) % 9600 and 3 * r.n_id_1 + r.n_id_2 == cid and r.sf5 == (first == 5)
+            assert abs(r.cfo - cfo) < 0.05
+            assert r.peak / r.mean_power > 20
+
+
+def test_forced_root_and_cellsearch_shim(gpu, oracle):
+    """srslte_ue_cellsearch_scan / _scan_N_id_2 as phch_recv::init_cell uses them (phch_recv.cc:146-177): the scan pulls
+    5 ms frames through the radio callback, searches them in one batch and reports the cell most frames agree on"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    cid, cfo = 302, 0.11
+    cell = o.make_cell(6, 1, cid)
+    frames = [_half_frame(o, cell, 5 * (i % 2), 500 + 10 * i, 8.0, cfo, 2000) for i in range(6)]
+    # forced root through the batch API: same peak as the free search when the forced root is the right one
+    bufs = np.stack(frames)
+    n, ns = bufs.shape
+    d_iq = torch.from_numpy(bufs.view(np.float32).reshape(n, -1)).cuda()
+    d_res = torch.zeros(n * C.sizeof(sg.SyncResult), dtype=torch.uint8, device="cuda")
+    ctx.cell_search(d_iq, n, ns, ns, d_res, force_n_id_2=cid % 3)
+    torch.cuda.synchronize()
+    res = (sg.SyncResult * n).from_buffer_copy(d_res.cpu().numpy().tobytes())
+    for i in range(n):
+        assert res[i].n_id_2 == cid % 3 and 3 * res[i].n_id_1 + res[i].n_id_2 == cid and res[i].sf5 == i % 2
+    ctx.cell_search(d_iq, n, ns, ns, d_res, force_n_id_2=(cid + 1) % 3)
+    torch.cuda.synchronize()
+    wrong = (sg.SyncResult * n).from_buffer_copy(d_res.cpu().numpy().tobytes())
+    assert all(w.peak < 0.2 * r.peak for w, r in zip(wrong, res))
+
+    class Result(C.Structure):
+        _fields_ = [("cell_id", C.c_uint32), ("cp", C.c_int), ("peak", C.c_float), ("mode", C.c_float), ("psr", C.c_float), ("cfo", C.c_float)]
+
+    class CellSearch(C.Structure):
+        _fields_ = [("agc_gain", C.c_double), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
+
+    state = {"i": 0}
+    RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
+
+    def recv(handler, data, nsamples, ts):
+        f = frames[state["i"] % len(frames)]
+        state["i"] += 1
+        assert nsamples == len(f)
+        C.memmove(data, f.ctypes.data, f.nbytes)
+        return nsamples
+
+    cb = RECV(recv)
+    cs = CellSearch()
+    assert L.srslte_ue_cellsearch_init(C.byref(cs), cb, None) == 0
+    assert L.srslte_ue_cellsearch_set_nof_frames_to_scan(C.byref(cs), 6) == 0
+    L.srslte_ue_cellsearch_set_threshold.argtypes = [C.c_void_p, C.c_float]
+    L.srslte_ue_cellsearch_set_threshold(C.byref(cs), 5.0)
+    found = (Result * 3)()
+    best = C.c_uint32(9)
+    assert L.srslte_ue_cellsearch_scan(C.byref(cs), found, C.byref(best)) == 6
+    assert best.value == cid % 3 and found[best.value].cell_id == cid and found[best.value].cp == 0
+    assert found[best.value].mode == 1.0 and abs(found[best.value].cfo - cfo * 15000) < 600 and found[best.value].psr > 20
+    one = Result()
+    assert L.srslte_ue_cellsearch_scan_N_id_2(C.byref(cs), cid % 3, C.byref(one)) == 6 and one.cell_id == cid
+    # a wrong root only produces noise peaks: max / mean of ~9500 exponential variates is about ln(9500) = 9
+    L.srslte_ue_cellsearch_set_threshold(C.byref(cs), 15.0)
+    assert L.srslte_ue_cellsearch_scan_N_id_2(C.byref(cs), (cid + 1) % 3, C.byref(one)) == 0
+    assert L.srslte_ue_cellsearch_scan_N_id_2(C.byref(cs), cid % 3, C.byref(one)) == 6
+    L.srslte_ue_cellsearch_free(C.byref(cs))
