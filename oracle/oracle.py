@@ -455,7 +455,8 @@ def pbch_llr(cell, hyp_ports, sf, ce, noise_est=0.0):
     return llr
 
 
-def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None, mib=None, sync=False):
+def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=None, ng_x6=6, phichs=None, mib=None, sync=False,
+                 noise_seed=None):
     """One synthetic DL subframe: returns (tb_bytes, iq complex64 of 15*N_FFT samples, sigma2).
 
     Payload RNG: numpy default_rng(seed); noise RNG: default_rng(seed + 5_000_000).  `taps` is an
@@ -491,7 +492,7 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=Non
     # unitary (I)FFT on both sides: a unit-power RE stays unit power and the per-RE noise variance
     # equals the per-sample one, so snr_db is Es/N0 per resource element
     sigma2 = 10.0 ** (-snr_db / 10.0)
-    nrng = np.random.default_rng(seed + 5_000_000)
+    nrng = np.random.default_rng(seed + 5_000_000 if noise_seed is None else noise_seed)   # retransmissions: same payload, new noise
     noise = (nrng.standard_normal(len(iq)) + 1j * nrng.standard_normal(len(iq))) * np.sqrt(sigma2 / 2)
     return tb, (iq + noise).astype(np.complex64), sigma2
 
@@ -504,7 +505,7 @@ def gen_turbo_llrs(K, seed, ebn0_db=None, scale=64.0):
     s = 2.0 * d - 1.0                                 # bit 1 -> +1 (positive LLR <=> bit 1)
     if ebn0_db is not None:
         sigma2 = 1.0 / (2.0 * (1.0 / 3.0) * 10.0 ** (ebn0_db / 10.0))
-        nrng = np.random.default_rng(seed + 5_000_000)
+        nrng = np.random.default_rng(seed + 5_000_000 if noise_seed is None else noise_seed)   # retransmissions: same payload, new noise
         s = s + nrng.standard_normal(len(s)) * np.sqrt(sigma2)
     llr = np.clip(np.trunc(scale * s), -2048, 2047).astype(np.int16)
     return c, llr
