@@ -331,3 +331,40 @@ def test_random_grants_match_oracle(gpu, oracle, case):
         assert h_st[i, 2] == avg
         assert np.allclose(h_meas[i], meas, rtol=1e-4)
     plan.close()
+
+
+@pytest.mark.parametrize("kind", ["zeros", "noise_zf", "huge", "tiny"])
+def test_degenerate_inputs_match_oracle(gpu, oracle, kind):
+    """inputs a receiver sees in practice but a generator never makes: silence (0/0 in the zero-forcing equaliser -> NaN ->
+    LLR 0), pure noise with noise_estimate 0, samples large enough to saturate every LLR, samples near the denormal
+    range.  Verdicts, payload bytes, iteration counts and (NaN-aware) measurements must still equal the oracle's."""
+    sg, ctx = gpu
+    o = oracle
+    prb, qm, tbs = 25, 4, 4968
+    ocell = o.make_cell(prb, 2, 9)
+    ocfg = o.make_cfg(ocell, sf_idx=4, cfi=2, qm=qm, tbs=tbs, tm=2)
+    cell = sg.make_cell(prb, 2, 9)
+    cfg = sg.make_cfg(cell, sf_idx=4, cfi=2, qm=qm, tbs=tbs, tm=2)
+    n_samp = 15 * 512
+    rng = np.random.default_rng(3)
+    good = o.gen_subframe(ocell, ocfg, 77, 25.0, _taps())[1]
+    if kind == "zeros":
+        iq, n0 = np.zeros(n_samp, np.complex64), 0.0
+    elif kind == "noise_zf":
+        iq, n0 = (rng.standard_normal(n_samp) + 1j * rng.standard_normal(n_samp)).astype(np.complex64), 0.0
+    elif kind == "huge":
+        iq, n0 = (good * np.float32(3e18)).astype(np.complex64), 0.01
+    else:
+        iq, n0 = (good * np.float32(1e-30)).astype(np.complex64), 0.0
+    iq2 = np.stack([iq, good])
+    plan = sg.PdschPlan(ctx, cell, cfg, 2)
+    I = plan.info
+    h_pl = np.zeros((2, I.payload_stride), np.uint8)
+    h_st = np.zeros((2, 4), np.int32)
+    h_meas = np.zeros((2, 5), np.float32)
+    plan.decode_batch_host(2, iq2, n0, 0, 4, h_pl, h_st, h_meas)
+    for i in range(2):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq2[i], n0, 0, 4)
+        assert (h_st[i, 0] == 1) == (rc == 0) and np.array_equal(h_pl[i], pl) and h_st[i, 2] == avg
+        assert np.allclose(h_meas[i], meas, rtol=1e-4, equal_nan=True)
+    plan.close()
