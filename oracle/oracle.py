@@ -505,7 +505,7 @@ def gen_turbo_llrs(K, seed, ebn0_db=None, scale=64.0):
     s = 2.0 * d - 1.0                                 # bit 1 -> +1 (positive LLR <=> bit 1)
     if ebn0_db is not None:
         sigma2 = 1.0 / (2.0 * (1.0 / 3.0) * 10.0 ** (ebn0_db / 10.0))
-        nrng = np.random.default_rng(seed + 5_000_000 if noise_seed is None else noise_seed)   # retransmissions: same payload, new noise
+        nrng = np.random.default_rng(seed + 5_000_000)
         s = s + nrng.standard_normal(len(s)) * np.sqrt(sigma2)
     llr = np.clip(np.trunc(scale * s), -2048, 2047).astype(np.int16)
     return c, llr

@@ -95,7 +95,7 @@ def test_srslte_shaped_entry_points(gpu, oracle):
     assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), cfi.value, 1, 0) == 0
     assert q.pdsch_cfg.nbits.nof_re == len(o.pdsch_re_list(ocell, ocfg))
     payload = np.zeros(tbs // 8, np.uint8)
-    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), q.sf_symbols, q.ce,
+    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), C.c_void_p(q.sf_symbols), q.ce,
                                      C.c_float(0.01), C.c_uint16(0x1234), payload.ctypes.data_as(C.c_void_p))
     rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
     assert ret == 0 and rc == 0
@@ -169,7 +169,7 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     L.srslte_ue_dl_decode_phich.restype = C.c_bool
     for Il, nd, a in ul_tx:
         assert bool(L.srslte_ue_dl_decode_phich(C.byref(q), sf_idx, Il, nd)) == bool(a)
-    assert L.srslte_pdcch_extract_llr(C.byref(q.pdcch), q.sf_symbols, q.ce, C.c_float(0.0), sf_idx, got_cfi.value) == 0
+    assert L.srslte_pdcch_extract_llr(C.byref(q.pdcch), C.c_void_p(q.sf_symbols), q.ce, C.c_float(0.0), sf_idx, got_cfi.value) == 0
     msg = DciMsg()
     assert L.srslte_ue_dl_find_dl_dci_type(C.byref(q), C.byref(msg), got_cfi.value, sf_idx, rnti, 0) == 1
     assert msg.nof_bits == nb and np.array_equal(np.frombuffer(msg.data, np.uint8)[:nb], dci_bits)
@@ -196,7 +196,7 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     grant = make_grant(prb, qm, tbs)
     assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), got_cfi.value, sf_idx, 0) == 0
     payload = np.zeros(tbs // 8, np.uint8)
-    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), q.sf_symbols, q.ce,
+    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), C.c_void_p(q.sf_symbols), q.ce,
                                      C.c_float(0.01), C.c_uint16(rnti), payload.ctypes.data_as(C.c_void_p))
     assert ret == 0 and np.array_equal(payload, tb)
     L.srslte_softbuffer_rx_free(C.byref(sb))
@@ -368,3 +368,62 @@ def test_degenerate_inputs_match_oracle(gpu, oracle, kind):
         assert (h_st[i, 0] == 1) == (rc == 0) and np.array_equal(h_pl[i], pl) and h_st[i, 2] == avg
         assert np.allclose(h_meas[i], meas, rtol=1e-4, equal_nan=True)
     plan.close()
+
+
+def test_four_concurrent_workers(gpu, oracle):
+    """srsUE runs up to four phch_workers at once (ue/hdr/phy/phy.h:118), each with its own srslte_ue_dl_t; the shim gives
+    every ue_dl its own stream, plans and decoder scratch.  Four threads decode different bandwidth-25 subframes through
+    the srsLTE-shaped calls at the same time, several rounds; every result must equal the oracle's."""
+    import ctypes as C
+    import threading
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, SoftBuffer, make_grant
+    prb = 25
+    shapes = [(2, 1384), (4, 4968), (6, 11448), (4, 2216)]          # (Qm, TBS) per worker
+    rounds = 6
+    work, errors = [], []
+    for w, (qm, tbs) in enumerate(shapes):
+        ocell = o.make_cell(prb, 1, 10 + w)
+        items = []
+        for r in range(rounds):
+            ocfg = o.make_cfg(ocell, sf_idx=(w + r) % 10, cfi=1 + (r % 3), rnti=0x100 + w, qm=qm, tbs=tbs)
+            tb, iq, _ = o.gen_subframe(ocell, ocfg, 8000 + 10 * w + r, 22.0, None, pcfich=True)
+            rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
+            items.append((ocfg, iq, rc, pl, avg))
+        work.append((ocell, qm, tbs, items))
+
+    def worker(w):
+        try:
+            ocell, qm, tbs, items = work[w]
+            q = UeDl()
+            cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=10 + w, cp=0, phich_length=0, phich_resources=2)
+            assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+            L.srslte_ue_dl_set_rnti(C.byref(q), 0x100 + w)
+            sb = SoftBuffer()
+            assert L.srslte_softbuffer_rx_init(C.byref(sb), prb) == 0
+            grant = make_grant(prb, qm, tbs)
+            for _ in range(3):                                    # three passes over the items keeps all four busy
+                for ocfg, iq, rc, pl, avg in items:
+                    cfi = C.c_uint32(0)
+                    assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), iq.ctypes.data_as(C.c_void_p), ocfg.sf_idx, C.byref(cfi)) == 0
+                    assert cfi.value == ocfg.cfi
+                    L.srslte_softbuffer_rx_reset(C.byref(sb))
+                    assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), cfi.value, ocfg.sf_idx, 0) == 0
+                    payload = np.zeros(tbs // 8, np.uint8)
+                    ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), C.c_void_p(q.sf_symbols), q.ce,
+                                                     C.c_float(0.01), C.c_uint16(0x100 + w), payload.ctypes.data_as(C.c_void_p))
+                    assert (ret == 0) == (rc == 0) and np.array_equal(payload, pl)
+                    assert L.srslte_pdsch_last_noi(C.byref(q.pdsch)) == avg
+            L.srslte_softbuffer_rx_free(C.byref(sb))
+            L.srslte_ue_dl_free(C.byref(q))
+        except Exception as e:  # noqa: BLE001
+            errors.append((w, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
