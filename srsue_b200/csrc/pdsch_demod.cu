@@ -498,16 +498,25 @@ __global__ void __launch_bounds__(1024) tb_assemble_kernel(const TbArgs a) {
   __syncthreads();
   if (r < a.C) {
     const int src_off = a.tbmap[4 * r], nb = a.tbmap[4 * r + 1], tb_pos = a.tbmap[4 * r + 2], chunk = a.tbmap[4 * r + 3];
-    const uint8_t* src = a.cb_bits + ((size_t)sf * a.C + r) * a.cb_bits_stride + src_off;
-    uint8_t* dst = a.payload + (size_t)sf * a.payload_stride;
+    const uint8_t* __restrict__ src = a.cb_bits + ((size_t)sf * a.C + r) * a.cb_bits_stride + src_off;
+    uint8_t* __restrict__ dst = a.payload + (size_t)sf * a.payload_stride;
     const int nb_payload = a.tbs / 8;
-    // coalesced copy of the payload bytes (the last 3 bytes of the stream are the TB CRC, not payload)
+    // This lane's contiguous chunk first: all its loads are issued before anything depends on them (a loop that
+    // loads and uses one byte per iteration pays one L2 round trip per byte -- 23 in a row at K = 5824).
+    constexpr int kMaxChunk = 24;                                  // ceil(6144 / 8 / 32)
+    const int b0 = lane * chunk;
+    uint8_t v[kMaxChunk];
+#pragma unroll
+    for (int i = 0; i < kMaxChunk; i++) v[i] = (i < chunk && b0 + i < nb) ? src[b0 + i] : (uint8_t)0;
+    // coalesced copy of the payload bytes (the last 3 bytes of the stream are the TB CRC, not payload), 8 loads in flight
+#pragma unroll 8
     for (int b = lane; b < nb; b += 32)
       if (tb_pos + b < nb_payload) dst[tb_pos + b] = src[b];
-    // CRC of this lane's contiguous chunk
-    const int b0 = lane * chunk, b1 = min(nb, b0 + chunk);
     uint32_t crc = 0;
-    for (int b = b0; b < b1; b++) crc = ((crc << 8) & 0xFFFFFFu) ^ s_tab[((crc >> 16) ^ src[b]) & 0xFFu];
+    const int b1 = min(nb, b0 + chunk);
+#pragma unroll
+    for (int i = 0; i < kMaxChunk; i++)
+      if (i < chunk && b0 + i < nb) crc = ((crc << 8) & 0xFFFFFFu) ^ s_tab[((crc >> 16) ^ v[i]) & 0xFFu];
     uint32_t part = (b1 > b0) ? gf_mul24(crc, a.tbshift[r * 32 + lane], kCrc24A) : 0u;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, off);
