@@ -14,6 +14,7 @@
 #define SRSUE_GPU_SRSLTE_COMPAT_H
 #include <stdbool.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "srsue_gpu/srsue_gpu.h"
@@ -262,8 +263,33 @@ SRSLTE_API void srslte_pbch_decode_reset(srslte_pbch_t *q);                     
  * transmit ports and the frame's position in the 40 ms BCH period; every call decodes from this subframe alone */
 SRSLTE_API int srslte_ue_mib_decode(srslte_ue_mib_t *q, cf_t *input, uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN],
                                     uint32_t *nof_tx_ports, uint32_t *sfn_offset);
+/* MIB search on the air interface at 1.92 Msps (phch_recv.cc:194-213): pulls 5 ms frames through the radio callback, finds
+ * the PSS/SSS of cell_id, and decodes the PBCH of the subframes 0 it sees; returns 1 (found), 0 (not within
+ * max_frames_timeout frames) or < 0 */
+typedef struct SRSLTE_API {
+  srslte_ue_sync_t ue_sync;
+  uint32_t cell_id;
+  void *gpu;
+} srslte_ue_mib_sync_t;
+SRSLTE_API int srslte_ue_mib_sync_init(srslte_ue_mib_sync_t *q, uint32_t cell_id, srslte_cp_t cp,
+                                       int (*recv_callback)(void *, void *, uint32_t, srslte_timestamp_t *), void *stream_handler);
+SRSLTE_API void srslte_ue_mib_sync_free(srslte_ue_mib_sync_t *q);
+SRSLTE_API int srslte_ue_mib_sync_decode(srslte_ue_mib_sync_t *q, uint32_t max_frames_timeout,
+                                         uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN], uint32_t *nof_tx_ports, uint32_t *sfn_offset);
 SRSLTE_API void srslte_pbch_mib_unpack(uint8_t *msg, srslte_cell_t *cell, uint32_t *sfn);   /* phch_recv.cc:216,253 */
 SRSLTE_API void srslte_pbch_mib_pack(srslte_cell_t *cell, uint32_t sfn, uint8_t *msg);
+
+/* ---- small utilities the DL callers use (phch_recv.cc:192,218,220,275,335-338; phch_worker.cc:305) ---- */
+SRSLTE_API void srslte_bit_pack_vector(uint8_t *unpacked, uint8_t *packed, int nof_bits);      /* bits (one per byte) -> bytes, MSB first */
+SRSLTE_API void srslte_bit_unpack_vector(uint8_t *packed, uint8_t *unpacked, int nof_bits);
+SRSLTE_API uint32_t srslte_bit_pack(uint8_t **bits, int nof_bits);                           /* reads nof_bits, advances *bits */
+SRSLTE_API void srslte_bit_unpack(uint32_t value, uint8_t **bits, int nof_bits);
+SRSLTE_API const char *srslte_cp_string(srslte_cp_t cp);
+SRSLTE_API void srslte_cell_fprint(FILE *stream, srslte_cell_t *cell, uint32_t sfn);
+SRSLTE_API int srslte_sampling_freq_hz(uint32_t nof_prb);
+SRSLTE_API void srslte_timestamp_copy(srslte_timestamp_t *dest, srslte_timestamp_t *src);
+SRSLTE_API int srslte_timestamp_add(srslte_timestamp_t *t, uint32_t full_secs, double frac_secs);
+SRSLTE_API uint32_t srslte_tti_interval(uint32_t tti1, uint32_t tti2);                       /* (tti1 - tti2) mod 10240 */
 
 /* ---- extensions (not in srsLTE) ------------------------------------------------------------------- */
 /* srslte_ue_dl_decode_fft_estimate decodes the PCFICH on the device and returns its CFI; set_cfi(1..3) forces a

@@ -81,9 +81,10 @@ typedef struct {
   float sss_corr;
 } srsue_gpu_sync_result_t;
 /* d_iq: n_bufs buffers of n_samples (>= 265; typically a 5 ms half frame = 9600) at 1.92 Msps, `stride` samples apart.
- * force_n_id_2: -1 searches the three PSS roots, 0..2 only that one.  Cell id = 3 * n_id_1 + n_id_2. */
+ * force_n_id_2: -1 searches the three PSS roots, 0..2 only that one.  first_pos: first sample offset searched (0, or 137
+ * so that the SSS symbol in front of every candidate lies inside the buffer).  Cell id = 3 * n_id_1 + n_id_2. */
 int srsue_gpu_cell_search(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride,
-                          int force_n_id_2, srsue_gpu_sync_result_t *d_result, void *stream);
+                          int force_n_id_2, int first_pos, srsue_gpu_sync_result_t *d_result, void *stream);
 
 /* ---- turbo decoder (device pointers; `stream` is a cudaStream_t passed as void*) ------------ */
 /* geometry of the windowed decoder for code-block size K: window length, windows, tcb elements */

@@ -288,8 +288,9 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
 }
 
 int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int n_bufs, int n_samples, long long stride,
-                          int force_n_id_2, srsue_gpu_sync_result_t* d_result, void* stream) {
-  if (!ctx || !d_iq || !d_result || n_bufs < 1 || n_samples < 137 + 128 || stride < n_samples || force_n_id_2 > 2)
+                          int force_n_id_2, int first_pos, srsue_gpu_sync_result_t* d_result, void* stream) {
+  if (!ctx || !d_iq || !d_result || n_bufs < 1 || n_samples < 137 + 128 || stride < n_samples || force_n_id_2 > 2 || first_pos < 0 ||
+      first_pos >= n_samples - 127)
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "cell_search: bad arguments");
   static_assert(sizeof(srsue_gpu_sync_result_t) == sizeof(srsue_sync_result), "result layouts must match");
   CU_CHECK(cudaSetDevice(ctx->device));
@@ -321,6 +322,7 @@ int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int 
   SyncArgs a{};
   a.iq = reinterpret_cast<const float2*>(d_iq); a.stride = stride; a.n_samples = n_samples; a.n_bufs = n_bufs;
   a.force_n_id_2 = force_n_id_2 < 0 ? -1 : force_n_id_2;
+  a.first_pos = first_pos;
   a.pss_time = ctx->d_pss_time; a.pss_freq = ctx->d_pss_freq; a.sss = ctx->d_sss; a.tw128 = ctx->d_tw128;
   a.peak_key = ctx->d_peak_key; a.power_sum = ctx->d_power_sum; a.result = reinterpret_cast<srsue_sync_result*>(d_result);
   const int n_pos = n_samples - 127;

@@ -162,6 +162,7 @@ struct SyncArgs {
   long long stride;
   int n_samples, n_bufs;
   int force_n_id_2;          // -1: search the three roots, else only this one
+  int first_pos;             // first sample offset searched (137 guarantees that the SSS symbol lies inside the buffer)
   const float2* pss_time;    // [3][128]
   const float2* pss_freq;    // [3][62]
   const int8_t* sss;         // [3][2][168][62]

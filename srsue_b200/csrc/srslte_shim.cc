@@ -432,7 +432,7 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
   for (uint32_t f = 0; f < nf; f++)
     if (g->recv(g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
   if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, force, g->d_res, g->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, force, 0, g->d_res, g->stream)) return SRSLTE_ERROR;
   std::vector<srsue_gpu_sync_result_t> res(nf);
   cudaMemcpyAsync(res.data(), g->d_res, nf * sizeof(srsue_gpu_sync_result_t), cudaMemcpyDeviceToHost, g->stream);
   if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
@@ -510,6 +510,122 @@ int srslte_ue_sync_start_agc(srslte_ue_sync_t* q, double (*)(void*, double), flo
   return SRSLTE_SUCCESS;
 }
 float srslte_agc_get_gain(srslte_agc_t* q) { return q ? (float)q->gain : 0.f; }
+
+// ---- MIB search over the air interface ----------------------------------------------------------------------
+namespace {
+struct MibSyncGpu {
+  srslte_ue_cellsearch_t cs;       // the frame puller + batched cell search
+  srslte_ue_mib_t mib;             // 6-PRB front end + PBCH decoder
+  int (*recv)(void*, void*, uint32_t, srslte_timestamp_t*) = nullptr;
+  void* handler = nullptr;
+  std::vector<srsue_gpu_cf_t> win; // two consecutive 5 ms frames
+};
+}  // namespace
+
+int srslte_ue_mib_sync_init(srslte_ue_mib_sync_t* q, uint32_t cell_id, srslte_cp_t cp,
+                            int (*recv_callback)(void*, void*, uint32_t, srslte_timestamp_t*), void* stream_handler) {
+  if (!q || !recv_callback || cell_id > 503 || cp != SRSLTE_CP_NORM) return SRSLTE_ERROR_INVALID_INPUTS;
+  std::memset(q, 0, sizeof(*q));
+  auto* m = new MibSyncGpu();
+  srslte_cell_t c{};
+  c.nof_prb = 6; c.nof_ports = 1; c.id = cell_id; c.cp = cp;        // the PBCH sits in the six central PRBs: 1.92 Msps suffice
+  if (srslte_ue_cellsearch_init(&m->cs, recv_callback, stream_handler) != SRSLTE_SUCCESS || srslte_ue_mib_init(&m->mib, c) != SRSLTE_SUCCESS) {
+    srslte_ue_cellsearch_free(&m->cs);
+    srslte_ue_mib_free(&m->mib);
+    delete m;
+    return SRSLTE_ERROR;
+  }
+  m->recv = recv_callback; m->handler = stream_handler;
+  m->win.resize(2 * kHalfFrame);
+  q->cell_id = cell_id;
+  q->gpu = m;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_ue_mib_sync_free(srslte_ue_mib_sync_t* q) {
+  if (!q || !q->gpu) return;
+  auto* m = static_cast<MibSyncGpu*>(q->gpu);
+  srslte_ue_cellsearch_free(&m->cs);
+  srslte_ue_mib_free(&m->mib);
+  delete m;
+  q->gpu = nullptr;
+}
+
+int srslte_ue_mib_sync_decode(srslte_ue_mib_sync_t* q, uint32_t max_frames_timeout, uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN],
+                              uint32_t* nof_tx_ports, uint32_t* sfn_offset) {
+  if (!q || !q->gpu || !bch_payload) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* m = static_cast<MibSyncGpu*>(q->gpu);
+  auto* g = static_cast<CellSearchGpu*>(m->cs.gpu);
+  if (!g->d_res) {          // scratch for one-frame searches
+    if (cudaMalloc((void**)&g->d_iq, (size_t)2 * kHalfFrame * sizeof(srsue_gpu_cf_t)) != cudaSuccess ||
+        cudaMalloc((void**)&g->d_res, sizeof(srsue_gpu_sync_result_t)) != cudaSuccess) return SRSLTE_ERROR;
+    g->cap_frames = 0;      // not usable by the scan path: it reallocates when it needs more
+  }
+  srslte_timestamp_t ts;
+  // sliding window of two 5 ms frames: the PSS of the older one is searched, and a subframe 0 that starts in it lies
+  // completely inside the window
+  if (m->recv(m->handler, m->win.data() + kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+  for (uint32_t f = 0; f < max_frames_timeout; f++) {
+    std::memcpy(m->win.data(), m->win.data() + kHalfFrame, kHalfFrame * sizeof(srsue_gpu_cf_t));
+    if (m->recv(m->handler, m->win.data() + kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+    if (cudaMemcpyAsync(g->d_iq, m->win.data(), (size_t)2 * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
+    // exactly one PSS period, starting at offset 832: the subframe that contains a candidate then begins inside the window
+    if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, (int)(q->cell_id % 3), 832, g->d_res, g->stream)) return SRSLTE_ERROR;
+    srsue_gpu_sync_result_t r;
+    cudaMemcpyAsync(&r, g->d_res, sizeof(r), cudaMemcpyDeviceToHost, g->stream);
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
+    if (!r.valid || 3 * r.n_id_1 + r.n_id_2 != (int)q->cell_id || r.sf5) continue;      // not our cell, or the PSS of subframe 5
+    if (r.mean_power <= 0.f || r.peak / r.mean_power < 10.0f) continue;
+    // subframe 0 starts 832 samples before the PSS symbol body: CP 10 + 128, five more symbols of 9 + 128, CP 9
+    const int start = r.peak_pos - 832;
+    if (start < 0 || start + 1920 > 2 * kHalfFrame) continue;
+    const int rc = srslte_ue_mib_decode(&m->mib, reinterpret_cast<cf_t*>(m->win.data() + start), bch_payload, nof_tx_ports, sfn_offset);
+    if (rc == SRSLTE_UE_MIB_FOUND) return 1;
+    if (rc < 0) return rc;
+  }
+  return 0;
+}
+
+// ---- small utilities ----------------------------------------------------------------------------------------
+void srslte_bit_pack_vector(uint8_t* unpacked, uint8_t* packed, int nof_bits) {
+  for (int i = 0; i < (nof_bits + 7) / 8; i++) packed[i] = 0;
+  for (int i = 0; i < nof_bits; i++) packed[i >> 3] |= (uint8_t)((unpacked[i] & 1) << (7 - (i & 7)));
+}
+void srslte_bit_unpack_vector(uint8_t* packed, uint8_t* unpacked, int nof_bits) {
+  for (int i = 0; i < nof_bits; i++) unpacked[i] = (packed[i >> 3] >> (7 - (i & 7))) & 1;
+}
+uint32_t srslte_bit_pack(uint8_t** bits, int nof_bits) {
+  uint32_t v = 0;
+  for (int i = 0; i < nof_bits; i++) v = (v << 1) | ((*bits)[i] & 1);
+  *bits += nof_bits;
+  return v;
+}
+void srslte_bit_unpack(uint32_t value, uint8_t** bits, int nof_bits) {
+  for (int i = 0; i < nof_bits; i++) (*bits)[i] = (uint8_t)((value >> (nof_bits - 1 - i)) & 1);
+  *bits += nof_bits;
+}
+const char* srslte_cp_string(srslte_cp_t cp) { return cp == SRSLTE_CP_NORM ? "Normal  " : "Extended"; }
+void srslte_cell_fprint(FILE* stream, srslte_cell_t* cell, uint32_t sfn) {
+  if (!stream || !cell) return;
+  static const char* ng[4] = {"1/6", "1/2", "1", "2"};
+  fprintf(stream, " - Cell ID:         %d\n - Nof ports:       %d\n - CP:              %s\n - PRB:             %d\n"
+                  " - PHICH Length:    %s\n - PHICH Resources: %s\n - SFN:             %d\n",
+          cell->id, cell->nof_ports, srslte_cp_string(cell->cp), cell->nof_prb, cell->phich_length == SRSLTE_PHICH_EXT ? "Extended" : "Normal",
+          ng[cell->phich_resources & 3], sfn);
+}
+int srslte_sampling_freq_hz(uint32_t nof_prb) {
+  const int n = symbol_sz((int)nof_prb);
+  return n > 0 ? 15000 * n : SRSLTE_ERROR;
+}
+void srslte_timestamp_copy(srslte_timestamp_t* dest, srslte_timestamp_t* src) { if (dest && src) *dest = *src; }
+int srslte_timestamp_add(srslte_timestamp_t* t, uint32_t full_secs, double frac_secs) {
+  if (!t || frac_secs < 0.0 || frac_secs >= 1.0) return SRSLTE_ERROR;
+  t->full_secs += full_secs;
+  t->frac_secs += frac_secs;
+  if (t->frac_secs >= 1.0) { t->frac_secs -= 1.0; t->full_secs++; }
+  return SRSLTE_SUCCESS;
+}
+uint32_t srslte_tti_interval(uint32_t tti1, uint32_t tti2) { return tti1 >= tti2 ? tti1 - tti2 : 10240 - tti2 + tti1; }
 
 // ---- MIB ---------------------------------------------------------------------------------------------------
 namespace {

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) pss_corr_kernel(const SyncArgs a) {
   if (tid < 128) s_t[tid] = a.pss_time[u * 128 + tid];
   __syncthreads();
   const int p = p0 + tid;
-  if (p >= n_pos) return;
+  if (p >= n_pos || p < a.first_pos) return;
   float c1r = 0.f, c1i = 0.f, c2r = 0.f, c2i = 0.f;
 #pragma unroll 8
   for (int n = 0; n < 64; n++) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
     const float re = __fadd_rn(__fmul_rn(c[0], c[2]), __fmul_rn(c[1], c[3])), im = __fsub_rn(__fmul_rn(c[0], c[3]), __fmul_rn(c[1], c[2]));
     r->peak_pos = pos; r->n_id_2 = u;
     r->peak = __uint_as_float((uint32_t)(key >> 32));
-    r->mean_power = (float)(a.power_sum[buf] / ((a.force_n_id_2 >= 0 ? 1.0 : 3.0) * (double)n_pos));
+    r->mean_power = (float)(a.power_sum[buf] / ((a.force_n_id_2 >= 0 ? 1.0 : 3.0) * (double)(n_pos - a.first_pos)));
     r->cfo = (float)(atan2((double)im, (double)re) / 3.14159265358979323846);
     r->valid = pos >= 137;
     if (pos < 137) { r->n_id_1 = -1; r->sf5 = 0; r->sss_corr = 0.f; }

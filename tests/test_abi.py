@@ -46,7 +46,10 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_ue_mib_init", "srslte_ue_mib_free", "srslte_ue_mib_decode", "srslte_pbch_decode_reset", "srslte_pbch_mib_unpack",
               "srslte_pbch_mib_pack", "srslte_ue_cellsearch_init", "srslte_ue_cellsearch_free", "srslte_ue_cellsearch_scan",
               "srslte_ue_cellsearch_scan_N_id_2", "srslte_ue_cellsearch_set_nof_frames_to_scan", "srslte_ue_cellsearch_set_threshold",
-              "srslte_ue_sync_start_agc", "srslte_agc_get_gain"]:
+              "srslte_ue_sync_start_agc", "srslte_agc_get_gain", "srslte_ue_mib_sync_init", "srslte_ue_mib_sync_decode",
+              "srslte_ue_mib_sync_free", "srslte_bit_pack_vector", "srslte_bit_unpack_vector", "srslte_bit_pack", "srslte_bit_unpack",
+              "srslte_cp_string", "srslte_cell_fprint", "srslte_sampling_freq_hz", "srslte_timestamp_copy", "srslte_timestamp_add",
+              "srslte_tti_interval"]:
         assert hasattr(lib, n), n
 
 

@@ -113,3 +113,70 @@ def test_forced_root_and_cellsearch_shim(gpu, oracle):
     assert L.srslte_ue_cellsearch_scan_N_id_2(C.byref(cs), (cid + 1) % 3, C.byref(one)) == 0
     assert L.srslte_ue_cellsearch_scan_N_id_2(C.byref(cs), cid % 3, C.byref(one)) == 6
     L.srslte_ue_cellsearch_free(C.byref(cs))
+
+
+def test_init_cell_sequence_cellsearch_then_mib(gpu, oracle):
+    """phch_recv::init_cell (phch_recv.cc:136-226) end to end on a synthetic air interface: cell search at 1.92 Msps,
+    then srslte_ue_mib_sync_decode finds a subframe 0 and decodes the MIB -> cell id, ports, bandwidth, PHICH, SFN"""
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import Cell
+    cid, ports, sfn0, cfo, shift = 217, 2, 406, 0.05, 6100
+    # the central 1.92 MHz of a cell look the same whatever its bandwidth: generate a 6-PRB view whose MIB announces 50 PRB
+    cell = o.make_cell(6, ports, cid)
+    stream = []
+    for half in range(8):                                   # 40 ms of air interface
+        sfn = sfn0 + half // 2
+        for i in range(5):
+            sf = 5 * (half % 2) + i
+            cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=104, tm=ports)
+            mib = (o.mib_pack(50, 0, 6, sfn), sfn % 4) if sf == 0 else None
+            stream.append(o.gen_subframe(cell, cfg, 1000 * half + i, 9.0, None, pcfich=True, sync=True, mib=mib)[1])
+    x = np.concatenate(stream)
+    x = np.roll(x * np.exp(2j * np.pi * cfo * np.arange(len(x)) / 128), shift).astype(np.complex64)
+    state = {"pos": 0}
+    RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
+
+    def recv(handler, data, nsamples, ts):
+        idx = (state["pos"] + np.arange(nsamples)) % len(x)
+        buf = np.ascontiguousarray(x[idx])
+        state["pos"] += nsamples
+        C.memmove(data, buf.ctypes.data, buf.nbytes)
+        return nsamples
+
+    cb = RECV(recv)
+
+    class Result(C.Structure):
+        _fields_ = [("cell_id", C.c_uint32), ("cp", C.c_int), ("peak", C.c_float), ("mode", C.c_float), ("psr", C.c_float), ("cfo", C.c_float)]
+
+    class CellSearch(C.Structure):
+        _fields_ = [("agc_gain", C.c_double), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
+
+    class MibSync(C.Structure):
+        _fields_ = [("agc_gain", C.c_double), ("cell_id", C.c_uint32), ("gpu", C.c_void_p)]
+
+    cs = CellSearch()
+    assert L.srslte_ue_cellsearch_init(C.byref(cs), cb, None) == 0
+    L.srslte_ue_cellsearch_set_nof_frames_to_scan(C.byref(cs), 6)
+    L.srslte_ue_cellsearch_set_threshold.argtypes = [C.c_void_p, C.c_float]
+    L.srslte_ue_cellsearch_set_threshold(C.byref(cs), 15.0)
+    found = (Result * 3)()
+    best = C.c_uint32(0)
+    assert L.srslte_ue_cellsearch_scan(C.byref(cs), found, C.byref(best)) > 0
+    assert found[best.value].cell_id == cid
+    L.srslte_ue_cellsearch_free(C.byref(cs))
+    ms = MibSync()
+    assert L.srslte_ue_mib_sync_init(C.byref(ms), found[best.value].cell_id, found[best.value].cp, cb, None) == 0
+    payload = (C.c_uint8 * 24)()
+    nports, off = C.c_uint32(0), C.c_uint32(0)
+    assert L.srslte_ue_mib_sync_decode(C.byref(ms), 12, payload, C.byref(nports), C.byref(off)) == 1
+    L.srslte_ue_mib_sync_free(C.byref(ms))
+    out_cell, sfn = Cell(), C.c_uint32(0)
+    L.srslte_pbch_mib_unpack(payload, C.byref(out_cell), C.byref(sfn))
+    assert nports.value == ports and out_cell.nof_prb == 50 and out_cell.phich_resources == 2
+    assert sfn0 <= sfn.value + off.value <= sfn0 + 3          # one of the four frames of the synthetic stream
+    packed = (C.c_uint8 * 3)()
+    L.srslte_bit_pack_vector(payload, packed, 24)
+    assert bytes(packed) == np.packbits(np.frombuffer(payload, np.uint8)).tobytes()
+    assert L.srslte_sampling_freq_hz(50) == 15360000 and L.srslte_tti_interval(3, 10238) == 5
