@@ -72,7 +72,7 @@ int srsue_gpu_version(void);
 typedef struct {
   int32_t peak_pos;     /* first sample of the PSS symbol body (after its cyclic prefix) inside the buffer */
   int32_t n_id_2;       /* 0..2 */
-  int32_t n_id_1;       /* 0..167, -1 when the SSS symbol does not lie inside the buffer (peak_pos < 137) */
+  int32_t n_id_1;       /* 0..167, -1 when the SSS symbol does not lie inside the buffer (peak_pos < 137 nfft / 128) */
   int32_t sf5;          /* 0: the PSS belongs to subframe 0, 1: to subframe 5 */
   int32_t valid;
   float peak;           /* |correlation|^2 at the peak */
@@ -80,10 +80,12 @@ typedef struct {
   float cfo;            /* carrier frequency offset in units of the 15 kHz subcarrier spacing */
   float sss_corr;
 } srsue_gpu_sync_result_t;
-/* d_iq: n_bufs buffers of n_samples (>= 265; typically a 5 ms half frame = 9600) at 1.92 Msps, `stride` samples apart.
- * force_n_id_2: -1 searches the three PSS roots, 0..2 only that one.  first_pos: first sample offset searched (0, or 137
- * so that the SSS symbol in front of every candidate lies inside the buffer).  Cell id = 3 * n_id_1 + n_id_2. */
-int srsue_gpu_cell_search(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride,
+/* d_iq: n_bufs buffers of n_samples (typically a 5 ms half frame = 75 * nfft), `stride` samples apart, at the sampling
+ * rate whose OFDM symbol has nfft samples (128 = 1.92 Msps, the cell-search rate; up to 2048 = 30.72 Msps for tracking at
+ * the cell's own rate).  force_n_id_2: -1 searches the three PSS roots, 0..2 only that one.  first_pos: first sample offset searched (0, or 137
+ * scaled by nfft / 128 so that the SSS symbol in front of every candidate lies inside the buffer).  peak_pos is relative
+ * to the buffer start.  Cell id = 3 * n_id_1 + n_id_2. */
+int srsue_gpu_cell_search(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride, int nfft,
                           int force_n_id_2, int first_pos, srsue_gpu_sync_result_t *d_result, void *stream);
 
 /* ---- turbo decoder (device pointers; `stream` is a cudaStream_t passed as void*) ------------ */

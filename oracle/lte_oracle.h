@@ -131,6 +131,10 @@ void  lteo_sync_tx(const lteo_cell_t *cell, int sf_idx, lteo_cd_t *grid);
 void  lteo_pss_time(int n_id_2, lteo_cf_t *t128);
 float lteo_pss_search(const lteo_cf_t *x, int n_samples, int *peak_pos, int *n_id_2, float *cfo, float *mean_power);
 int   lteo_sss_detect(const lteo_cf_t *x, int peak_pos, int n_id_2, int *sf5, float *corr);
+void  lteo_pss_time_n(int n_id_2, int nfft, lteo_cf_t *t);
+float lteo_pss_search_n(const lteo_cf_t *x, int n_samples, int nfft, int force_n_id_2, int first_pos, int *peak_pos, int *n_id_2,
+                        float *cfo, float *mean_power);
+int   lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr);
 /* ---- PBCH / MIB (SPEC.md 12) ---- */
 uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out);
 void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240);

@@ -65,27 +65,28 @@ void lteo_sync_tx(const lteo_cell_t *cell, int sf_idx, lteo_cd_t *grid) {
 
 /* time-domain PSS replica at 1.92 Msps: 128-point IDFT of the sequence on bins -31..-1, 1..31, scaled 1/sqrt(128)
  * (the OFDM modulator's convention), evaluated in double and rounded once */
-void lteo_pss_time(int n_id_2, lteo_cf_t *t128) {
+void lteo_pss_time_n(int n_id_2, int nfft, lteo_cf_t *t) {
   lteo_cd_t d[62];
   lteo_pss_seq(n_id_2, d);
-  for (int n = 0; n < 128; n++) {
+  for (int n = 0; n < nfft; n++) {
     double re = 0, im = 0;
     for (int i = 0; i < 62; i++) {
       int bin = (i < 31) ? i - 31 : i - 30;                       /* -31..-1, 1..31 */
-      double a = 2.0 * M_PI * (double)(bin * n) / 128.0;
+      double a = 2.0 * M_PI * (double)(bin * n) / (double)nfft;
       re += d[i].re * cos(a) - d[i].im * sin(a);
       im += d[i].re * sin(a) + d[i].im * cos(a);
     }
-    t128[n].re = (float)(re / sqrt(128.0)); t128[n].im = (float)(im / sqrt(128.0));
+    t[n].re = (float)(re / sqrt((double)nfft)); t[n].im = (float)(im / sqrt((double)nfft));
   }
 }
+void lteo_pss_time(int n_id_2, lteo_cf_t *t128) { lteo_pss_time_n(n_id_2, 128, t128); }
 
 /* c(p) = sum_{n<128} x[p+n] conj(t[n]), n ascending, every product and sum rounded once; first and second half kept
  * apart for the CFO estimate */
-static void pss_corr_at(const lteo_cf_t *x, const lteo_cf_t *t, lteo_cf_t *c1, lteo_cf_t *c2) {
+static void pss_corr_at(const lteo_cf_t *x, const lteo_cf_t *t, int nfft, lteo_cf_t *c1, lteo_cf_t *c2) {
   for (int h = 0; h < 2; h++) {
     float re = 0.0f, im = 0.0f;
-    for (int n = 64 * h; n < 64 * h + 64; n++) {
+    for (int n = nfft / 2 * h; n < nfft / 2 * h + nfft / 2; n++) {
       float pr = x[n].re * t[n].re + x[n].im * t[n].im;
       float pi = x[n].im * t[n].re - x[n].re * t[n].im;
       re = re + pr; im = im + pi;
@@ -101,28 +102,37 @@ static void pss_corr_at(const lteo_cf_t *x, const lteo_cf_t *t, lteo_cf_t *c1, l
  * N_id_2 and the CFO in units of the subcarrier spacing: angle(conj(c1) c2) / pi.
  */
 float lteo_pss_search(const lteo_cf_t *x, int n_samples, int *peak_pos, int *n_id_2, float *cfo, float *mean_power) {
-  lteo_cf_t t[3][128];
-  for (int u = 0; u < 3; u++) lteo_pss_time(u, t[u]);
-  int n_pos = n_samples - 127;
+  return lteo_pss_search_n(x, n_samples, 128, -1, 0, peak_pos, n_id_2, cfo, mean_power);
+}
+
+/* the same at any LTE sampling rate (replica of nfft samples), optionally for one root only and from first_pos on */
+float lteo_pss_search_n(const lteo_cf_t *x, int n_samples, int nfft, int force_n_id_2, int first_pos, int *peak_pos, int *n_id_2,
+                        float *cfo, float *mean_power) {
+  lteo_cf_t *t[3];
+  for (int u = 0; u < 3; u++) { t[u] = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * nfft); lteo_pss_time_n(u, nfft, t[u]); }
+  int n_pos = n_samples - (nfft - 1);
   float best = -1.0f; int bu = 0, bp = 0;
   lteo_cf_t b1 = {0, 0}, b2 = {0, 0};
   double acc = 0.0;
-  for (int u = 0; u < 3; u++)
-    for (int p = 0; p < n_pos; p++) {
+  for (int u = 0; u < 3; u++) {
+    if (force_n_id_2 >= 0 && u != force_n_id_2) continue;
+    for (int p = first_pos; p < n_pos; p++) {
       lteo_cf_t c1, c2;
-      pss_corr_at(x + p, t[u], &c1, &c2);
+      pss_corr_at(x + p, t[u], nfft, &c1, &c2);
       float cr = c1.re + c2.re, ci = c1.im + c2.im;
       float pw = cr * cr + ci * ci;
       acc += pw;
       if (pw > best) { best = pw; bu = u; bp = p; b1 = c1; b2 = c2; }
     }
+  }
+  for (int u = 0; u < 3; u++) free(t[u]);
   if (peak_pos) *peak_pos = bp;
   if (n_id_2) *n_id_2 = bu;
   if (cfo) {
     float re = b1.re * b2.re + b1.im * b2.im, im = b1.re * b2.im - b1.im * b2.re;      /* conj(c1) c2 */
     *cfo = (float)(atan2((double)im, (double)re) / M_PI);
   }
-  if (mean_power) *mean_power = (float)(acc / (3.0 * n_pos));
+  if (mean_power) *mean_power = (float)(acc / ((force_n_id_2 >= 0 ? 1.0 : 3.0) * (n_pos - first_pos)));
   return best;
 }
 
@@ -134,14 +144,19 @@ float lteo_pss_search(const lteo_cf_t *x, int n_samples, int *peak_pos, int *n_i
  * the best N_id_1; outputs whether the half-frame starts with subframe 5 and the metric.
  */
 int lteo_sss_detect(const lteo_cf_t *x, int peak_pos, int n_id_2, int *sf5, float *corr_out) {
-  lteo_cf_t yp[128], ys[128];
+  return lteo_sss_detect_n(x, peak_pos, n_id_2, 128, sf5, corr_out);
+}
+
+/* the same at any LTE sampling rate: nfft-point transforms, the SSS symbol nfft + 9 nfft / 128 samples before the PSS */
+int lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr_out) {
+  lteo_cf_t *yp = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * 2 * nfft), *ys = yp + nfft;
   lteo_cd_t d[62];
-  lteo_fft(x + peak_pos, yp, 128);
-  lteo_fft(x + peak_pos - 137, ys, 128);
+  lteo_fft(x + peak_pos, yp, nfft);
+  lteo_fft(x + peak_pos - (nfft + 9 * nfft / 128), ys, nfft);
   lteo_pss_seq(n_id_2, d);
   float zr[62], zi[62];
   for (int i = 0; i < 62; i++) {
-    int bin = (i < 31) ? 128 + (i - 31) : i - 30;
+    int bin = (i < 31) ? nfft + (i - 31) : i - 30;
     float dr = (float)d[i].re, di = (float)d[i].im;
     float hr = yp[bin].re * dr + yp[bin].im * di, hi = yp[bin].im * dr - yp[bin].re * di;   /* Y conj(d) */
     zr[i] = ys[bin].re * hr + ys[bin].im * hi;                                              /* Ys conj(H) */
@@ -157,6 +172,7 @@ int lteo_sss_detect(const lteo_cf_t *x, int peak_pos, int n_id_2, int *sf5, floa
       float acc = ar * ar + ai * ai;
       if (first || acc > best) { best = acc; bn = n1; b5 = s5; first = 0; }
     }
+  free(yp);
   if (sf5) *sf5 = b5;
   if (corr_out) *corr_out = best;
   return bn;

@@ -413,20 +413,20 @@ def phich_decode(cell, sf_idx, sf, ce, n_group, n_seq, noise_est=0.0, ng_x6=6):
     return ack, np.float32(m.value)
 
 
-def pss_search(x):
+def pss_search(x, nfft=128, force_n_id_2=-1, first_pos=0):
     x = np.ascontiguousarray(x, np.complex64)
     pos, nid2 = C.c_int(), C.c_int()
     cfo, mp = C.c_float(), C.c_float()
-    lib().lteo_pss_search.restype = C.c_float
-    peak = lib().lteo_pss_search(_p(x), len(x), C.byref(pos), C.byref(nid2), C.byref(cfo), C.byref(mp))
+    lib().lteo_pss_search_n.restype = C.c_float
+    peak = lib().lteo_pss_search_n(_p(x), len(x), nfft, force_n_id_2, first_pos, C.byref(pos), C.byref(nid2), C.byref(cfo), C.byref(mp))
     return dict(peak=np.float32(peak), pos=pos.value, n_id_2=nid2.value, cfo=np.float32(cfo.value), mean_power=np.float32(mp.value))
 
 
-def sss_detect(x, peak_pos, n_id_2):
+def sss_detect(x, peak_pos, n_id_2, nfft=128):
     x = np.ascontiguousarray(x, np.complex64)
     sf5 = C.c_int()
     corr = C.c_float()
-    n1 = lib().lteo_sss_detect(_p(x), peak_pos, n_id_2, C.byref(sf5), C.byref(corr))
+    n1 = lib().lteo_sss_detect_n(_p(x), peak_pos, n_id_2, nfft, C.byref(sf5), C.byref(corr))
     return n1, sf5.value, np.float32(corr.value)
 
 

@@ -124,9 +124,11 @@ class Context:
         _check(lib().srsue_gpu_tdec_run_all_host(self.h, _ptr(h_triples), n_cb, K, max_iter, crc_type, _ptr(h_bits),
                                                  _ptr(h_status)), "tdec_run_all_host")
 
-    def cell_search(self, d_iq, n_bufs, n_samples, stride, d_result, force_n_id_2=-1, first_pos=0):
-        lib().srsue_gpu_cell_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-        _check(lib().srsue_gpu_cell_search(self.h, _ptr(d_iq), n_bufs, n_samples, stride, force_n_id_2, first_pos, _ptr(d_result), _stream()),
+    def cell_search(self, d_iq, n_bufs, n_samples, stride, d_result, force_n_id_2=-1, first_pos=0, nfft=128):
+        lib().srsue_gpu_cell_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p]
+        _check(lib().srsue_gpu_cell_search(self.h, _ptr(d_iq), n_bufs, n_samples, stride, nfft, force_n_id_2, first_pos, _ptr(d_result),
+                                           _stream()),
                "cell_search")
 
     def tdec_last_launch(self):

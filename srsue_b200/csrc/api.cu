@@ -95,7 +95,8 @@ struct srsue_gpu_ctx {
   bool attr_set = false;
   bool pdcch_attr_set = false;
   // cell-search tables and scratch (built on first use)
-  float2* d_pss_time = nullptr; float2* d_pss_freq = nullptr; int8_t* d_sss = nullptr; float2* d_tw128 = nullptr;
+  float2* d_pss_freq = nullptr; int8_t* d_sss = nullptr;
+  std::map<int, std::pair<float2*, float2*>> sync_tabs;      // nfft -> (PSS time replicas [3][nfft], nfft/2 twiddles)
   unsigned long long* d_peak_key = nullptr; double* d_power_sum = nullptr; int sync_cap = 0;
 };
 
@@ -282,33 +283,41 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
     for (int i = 0; i < 2; i++) cudaFree(kv.second.d_tpos[i]);
   }
   ctx->scratch.release();
-  cudaFree(ctx->d_pss_time); cudaFree(ctx->d_pss_freq); cudaFree(ctx->d_sss); cudaFree(ctx->d_tw128);
+  cudaFree(ctx->d_pss_freq); cudaFree(ctx->d_sss);
+  for (auto& kv : ctx->sync_tabs) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
   cudaFree(ctx->d_peak_key); cudaFree(ctx->d_power_sum);
   delete ctx;
 }
 
-int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int n_bufs, int n_samples, long long stride,
+int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int n_bufs, int n_samples, long long stride, int nfft,
                           int force_n_id_2, int first_pos, srsue_gpu_sync_result_t* d_result, void* stream) {
-  if (!ctx || !d_iq || !d_result || n_bufs < 1 || n_samples < 137 + 128 || stride < n_samples || force_n_id_2 > 2 || first_pos < 0 ||
-      first_pos >= n_samples - 127)
-    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "cell_search: bad arguments");
+  const bool pow2 = nfft >= 128 && nfft <= 2048 && (nfft & (nfft - 1)) == 0;
+  if (!ctx || !d_iq || !d_result || n_bufs < 1 || !pow2 || n_samples < 2 * nfft + 9 * nfft / 128 || stride < n_samples ||
+      force_n_id_2 > 2 || first_pos < 0 || first_pos >= n_samples - (nfft - 1))
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "cell_search: bad arguments (nfft must be 128, 256, 512, 1024 or 2048)");
   static_assert(sizeof(srsue_gpu_sync_result_t) == sizeof(srsue_sync_result), "result layouts must match");
   CU_CHECK(cudaSetDevice(ctx->device));
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->d_sss) {
-    std::vector<float> pt(3 * 128 * 2), pf(3 * 62 * 2), tw;
+    std::vector<float> pf(3 * 62 * 2);
     std::vector<int8_t> ss((size_t)3 * 336 * 62);
     for (int u = 0; u < 3; u++) {
-      pss_time(u, pt.data() + (size_t)u * 256);
       pss_freq(u, pf.data() + (size_t)u * 124);
       for (int s5 = 0; s5 < 2; s5++)
         for (int n1 = 0; n1 < 168; n1++) sss_seq(n1, u, s5, ss.data() + ((size_t)u * 336 + s5 * 168 + n1) * 62);
     }
-    fft_twiddles(128, tw);
-    CU_CHECK(upload(reinterpret_cast<float**>(&ctx->d_pss_time), pt));
     CU_CHECK(upload(reinterpret_cast<float**>(&ctx->d_pss_freq), pf));
-    CU_CHECK(upload(reinterpret_cast<float**>(&ctx->d_tw128), tw));
     CU_CHECK(upload(&ctx->d_sss, ss));
+  }
+  auto it = ctx->sync_tabs.find(nfft);
+  if (it == ctx->sync_tabs.end()) {
+    std::vector<float> pt((size_t)3 * nfft * 2), tw;
+    for (int u = 0; u < 3; u++) pss_time_n(u, nfft, pt.data() + (size_t)u * nfft * 2);
+    fft_twiddles(nfft, tw);
+    std::pair<float2*, float2*> tabs{nullptr, nullptr};
+    CU_CHECK(upload(reinterpret_cast<float**>(&tabs.first), pt));
+    CU_CHECK(upload(reinterpret_cast<float**>(&tabs.second), tw));
+    it = ctx->sync_tabs.emplace(nfft, tabs).first;
   }
   if (n_bufs > ctx->sync_cap) {
     cudaFree(ctx->d_peak_key); cudaFree(ctx->d_power_sum);
@@ -321,17 +330,19 @@ int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int 
   CU_CHECK(cudaMemsetAsync(ctx->d_power_sum, 0, (size_t)n_bufs * sizeof(double), st));
   SyncArgs a{};
   a.iq = reinterpret_cast<const float2*>(d_iq); a.stride = stride; a.n_samples = n_samples; a.n_bufs = n_bufs;
+  a.nfft = nfft; a.log2n = 0; while ((1 << a.log2n) < nfft) a.log2n++;
   a.force_n_id_2 = force_n_id_2 < 0 ? -1 : force_n_id_2;
   a.first_pos = first_pos;
-  a.pss_time = ctx->d_pss_time; a.pss_freq = ctx->d_pss_freq; a.sss = ctx->d_sss; a.tw128 = ctx->d_tw128;
+  a.pss_time = it->second.first; a.pss_freq = ctx->d_pss_freq; a.sss = ctx->d_sss; a.tw = it->second.second;
   a.peak_key = ctx->d_peak_key; a.power_sum = ctx->d_power_sum; a.result = reinterpret_cast<srsue_sync_result*>(d_result);
-  const int n_pos = n_samples - 127;
+  const int n_pos = n_samples - (nfft - 1);
+  const int smem_pss = (256 + 2 * nfft) * (int)sizeof(float2), smem_sss = 2 * nfft * (int)sizeof(float2);
   for (int done = 0; done < n_bufs; done += 65535) {
     const int n = std::min(65535, n_bufs - done);
     SyncArgs b = a;
     b.iq += (size_t)done * stride; b.peak_key += done; b.power_sum += done; b.result += done; b.n_bufs = n;
-    pss_corr_kernel<<<dim3((n_pos + 255) / 256, force_n_id_2 < 0 ? 3 : 1, n), 256, 0, st>>>(b);
-    sss_detect_kernel<<<n, 128, 0, st>>>(b);
+    pss_corr_kernel<<<dim3((n_pos - first_pos + 255) / 256, force_n_id_2 < 0 ? 3 : 1, n), 256, smem_pss, st>>>(b);
+    sss_detect_kernel<<<n, 128, smem_sss, st>>>(b);
     ctx->launch_count += 2;
   }
   CU_CHECK(cudaGetLastError());

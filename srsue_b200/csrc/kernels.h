@@ -161,12 +161,13 @@ struct SyncArgs {
   const float2* iq;          // [n_bufs][stride] samples at 1.92 Msps
   long long stride;
   int n_samples, n_bufs;
+  int nfft, log2n;           // samples per OFDM symbol at the buffer's sampling rate (128 at 1.92 Msps ... 2048)
   int force_n_id_2;          // -1: search the three roots, else only this one
   int first_pos;             // first sample offset searched (137 guarantees that the SSS symbol lies inside the buffer)
-  const float2* pss_time;    // [3][128]
+  const float2* pss_time;    // [3][nfft]
   const float2* pss_freq;    // [3][62]
   const int8_t* sss;         // [3][2][168][62]
-  const float2* tw128;       // 64 twiddles of the 128-point transform
+  const float2* tw;          // nfft / 2 twiddles of the nfft-point transform
   unsigned long long* peak_key;   // [n_bufs] scratch, zeroed before the launch
   double* power_sum;              // [n_bufs] scratch, zeroed before the launch
   srsue_sync_result* result;      // [n_bufs]

@@ -440,20 +440,21 @@ void pss_freq(int n_id_2, float* d62x2) {
   for (int n = 0; n < 62; n++) { d62x2[2 * n] = (float)re[n]; d62x2[2 * n + 1] = (float)im[n]; }
 }
 
-void pss_time(int n_id_2, float* t128x2) {
+void pss_time_n(int n_id_2, int nfft, float* tx2) {
   double dr[62], di[62];
   pss_freq_d(n_id_2, dr, di);
-  for (int n = 0; n < 128; n++) {
+  for (int n = 0; n < nfft; n++) {
     double re = 0, im = 0;
     for (int i = 0; i < 62; i++) {
       const int bin = (i < 31) ? i - 31 : i - 30;
-      const double a = 2.0 * M_PI * (double)(bin * n) / 128.0;
+      const double a = 2.0 * M_PI * (double)(bin * n) / (double)nfft;
       re += dr[i] * std::cos(a) - di[i] * std::sin(a);
       im += dr[i] * std::sin(a) + di[i] * std::cos(a);
     }
-    t128x2[2 * n] = (float)(re / std::sqrt(128.0)); t128x2[2 * n + 1] = (float)(im / std::sqrt(128.0));
+    tx2[2 * n] = (float)(re / std::sqrt((double)nfft)); tx2[2 * n + 1] = (float)(im / std::sqrt((double)nfft));
   }
 }
+void pss_time(int n_id_2, float* t128x2) { pss_time_n(n_id_2, 128, t128x2); }
 
 void sss_seq(int n_id_1, int n_id_2, int sf5, int8_t* d62) {
   int8_t s[31], c[31], z[31];

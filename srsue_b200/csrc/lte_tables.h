@@ -71,6 +71,7 @@ int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int3
 // double and rounded once, interleaved re/im), SSS as +-1 for (N_id_1, N_id_2, subframe 0 or 5)
 void pss_freq(int n_id_2, float* d62x2);
 void pss_time(int n_id_2, float* t128x2);
+void pss_time_n(int n_id_2, int nfft, float* tx2);   // the same replica at any LTE sampling rate
 void sss_seq(int n_id_1, int n_id_2, int sf5, int8_t* d62);
 // PBCH (36.211 6.6.4): grid indices of the 240 resource elements in a subframe 0
 void pbch_res(const CellCfg& cell, int32_t* g240);

@@ -432,7 +432,7 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
   for (uint32_t f = 0; f < nf; f++)
     if (g->recv(g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
   if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, force, 0, g->d_res, g->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, 128, force, 0, g->d_res, g->stream)) return SRSLTE_ERROR;
   std::vector<srsue_gpu_sync_result_t> res(nf);
   cudaMemcpyAsync(res.data(), g->d_res, nf * sizeof(srsue_gpu_sync_result_t), cudaMemcpyDeviceToHost, g->stream);
   if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
@@ -570,7 +570,7 @@ int srslte_ue_mib_sync_decode(srslte_ue_mib_sync_t* q, uint32_t max_frames_timeo
     if (m->recv(m->handler, m->win.data() + kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
     if (cudaMemcpyAsync(g->d_iq, m->win.data(), (size_t)2 * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
     // exactly one PSS period, starting at offset 832: the subframe that contains a candidate then begins inside the window
-    if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, (int)(q->cell_id % 3), 832, g->d_res, g->stream)) return SRSLTE_ERROR;
+    if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, 128, (int)(q->cell_id % 3), 832, g->d_res, g->stream)) return SRSLTE_ERROR;
     srsue_gpu_sync_result_t r;
     cudaMemcpyAsync(&r, g->d_res, sizeof(r), cudaMemcpyDeviceToHost, g->stream);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;

@@ -15,25 +15,27 @@ namespace srsue {
 
 // c(p) for 256 consecutive positions of one buffer and one root.  grid (ceil(n_pos / 256), 3, n_bufs)
 __global__ void __launch_bounds__(256) pss_corr_kernel(const SyncArgs a) {
-  __shared__ float2 s_x[256 + 128];
-  __shared__ float2 s_t[128];
-  const int u = a.force_n_id_2 >= 0 ? a.force_n_id_2 : blockIdx.y, buf = blockIdx.z, p0 = blockIdx.x * 256, tid = threadIdx.x;
-  const int n_pos = a.n_samples - 127;
+  extern __shared__ __align__(16) float2 s_sync[];              // samples [256 + nfft - 1], then the replica [nfft]
+  const int N = a.nfft;
+  float2* s_x = s_sync;
+  float2* s_t = s_sync + 256 + N;
+  const int u = a.force_n_id_2 >= 0 ? a.force_n_id_2 : blockIdx.y, buf = blockIdx.z, p0 = a.first_pos + blockIdx.x * 256, tid = threadIdx.x;
+  const int n_pos = a.n_samples - (N - 1);
   const float2* x = a.iq + (size_t)buf * a.stride;
-  for (int i = tid; i < 256 + 127; i += 256) s_x[i] = (p0 + i < a.n_samples) ? x[p0 + i] : make_float2(0.f, 0.f);
-  if (tid < 128) s_t[tid] = a.pss_time[u * 128 + tid];
+  for (int i = tid; i < 256 + N - 1; i += 256) s_x[i] = (p0 + i < a.n_samples) ? x[p0 + i] : make_float2(0.f, 0.f);
+  for (int i = tid; i < N; i += 256) s_t[i] = a.pss_time[u * N + i];
   __syncthreads();
   const int p = p0 + tid;
-  if (p >= n_pos || p < a.first_pos) return;
+  if (p >= n_pos) return;
   float c1r = 0.f, c1i = 0.f, c2r = 0.f, c2i = 0.f;
 #pragma unroll 8
-  for (int n = 0; n < 64; n++) {
+  for (int n = 0; n < N / 2; n++) {
     const float2 xv = s_x[tid + n], t = s_t[n];
     c1r = __fadd_rn(c1r, __fadd_rn(__fmul_rn(xv.x, t.x), __fmul_rn(xv.y, t.y)));
     c1i = __fadd_rn(c1i, __fsub_rn(__fmul_rn(xv.y, t.x), __fmul_rn(xv.x, t.y)));
   }
 #pragma unroll 8
-  for (int n = 64; n < 128; n++) {
+  for (int n = N / 2; n < N; n++) {
     const float2 xv = s_x[tid + n], t = s_t[n];
     c2r = __fadd_rn(c2r, __fadd_rn(__fmul_rn(xv.x, t.x), __fmul_rn(xv.y, t.y)));
     c2i = __fadd_rn(c2i, __fsub_rn(__fmul_rn(xv.y, t.x), __fmul_rn(xv.x, t.y)));
@@ -50,14 +52,17 @@ __global__ void __launch_bounds__(256) pss_corr_kernel(const SyncArgs a) {
   if ((tid & 31) == 0) atomicAdd(a.power_sum + buf, v);
 }
 
-// one CTA of 128 threads per buffer: CFO at the peak, two 128-point FFTs, SSS correlations
+// one CTA of 128 threads per buffer: CFO at the peak, two nfft-point FFTs, SSS correlations
 __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
-  __shared__ float2 s_f[2][128];
+  extern __shared__ __align__(16) float2 s_sync[];              // two transforms of nfft points
   __shared__ float2 s_z[62];
   __shared__ float s_best[128];
   __shared__ int s_idx[128];
+  const int N = a.nfft, gap = N + 9 * N / 128;                  // the SSS symbol starts one symbol + one cyclic prefix earlier
+  float2* s_f0 = s_sync;
+  float2* s_f1 = s_sync + N;
   const int buf = blockIdx.x, tid = threadIdx.x;
-  const int n_pos = a.n_samples - 127;
+  const int n_pos = a.n_samples - (N - 1);
   const unsigned long long key = a.peak_key[buf];
   const uint32_t flat = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
   const int u = (int)(flat / (uint32_t)n_pos), pos = (int)(flat % (uint32_t)n_pos);
@@ -67,8 +72,8 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
     // the two half correlations again, for the CFO: angle(conj(c1) c2) / pi in units of the subcarrier spacing
     float c[4] = {0.f, 0.f, 0.f, 0.f};
     for (int h = 0; h < 2; h++)
-      for (int n = 64 * h; n < 64 * h + 64; n++) {
-        const float2 xv = x[pos + n], t = a.pss_time[u * 128 + n];
+      for (int n = N / 2 * h; n < N / 2 * h + N / 2; n++) {
+        const float2 xv = x[pos + n], t = a.pss_time[u * N + n];
         c[2 * h] = __fadd_rn(c[2 * h], __fadd_rn(__fmul_rn(xv.x, t.x), __fmul_rn(xv.y, t.y)));
         c[2 * h + 1] = __fadd_rn(c[2 * h + 1], __fsub_rn(__fmul_rn(xv.y, t.x), __fmul_rn(xv.x, t.y)));
       }
@@ -77,29 +82,37 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
     r->peak = __uint_as_float((uint32_t)(key >> 32));
     r->mean_power = (float)(a.power_sum[buf] / ((a.force_n_id_2 >= 0 ? 1.0 : 3.0) * (double)(n_pos - a.first_pos)));
     r->cfo = (float)(atan2((double)im, (double)re) / 3.14159265358979323846);
-    r->valid = pos >= 137;
-    if (pos < 137) { r->n_id_1 = -1; r->sf5 = 0; r->sss_corr = 0.f; }
+    r->valid = pos >= gap;
+    if (pos < gap) { r->n_id_1 = -1; r->sf5 = 0; r->sss_corr = 0.f; }
   }
-  if (pos < 137) return;
-  // radix-2 decimation-in-time FFTs (SPEC.md 2): threads 0..63 the PSS symbol, 64..127 the SSS symbol
-  const int f = tid >> 6, j = tid & 63;
-  const float2* src = x + (f == 0 ? pos : pos - 137);
-  for (int i = j; i < 128; i += 64) s_f[f][__brev((unsigned)i) >> 25] = src[i];
+  if (pos < gap) return;
+  // radix-2 decimation-in-time FFTs (SPEC.md 2) of the PSS symbol (s_f0) and the SSS symbol (s_f1), both by all threads
+  const int shift = 32 - a.log2n;
+  for (int i = tid; i < N; i += 128) {
+    const int rv = (int)(__brev((unsigned)i) >> shift);
+    s_f0[rv] = x[pos + i];
+    s_f1[rv] = x[pos - gap + i];
+  }
   __syncthreads();
-  for (int m = 2; m <= 128; m <<= 1) {
-    const int half = m >> 1, g = j / half, jj = j - g * half;
-    const float2 w = a.tw128[jj * (128 / m)];
-    float2* pa = &s_f[f][g * m + jj];
-    float2* pb = pa + half;
-    const float2 av = *pa, bv = *pb;
-    const float tr = __fsub_rn(__fmul_rn(w.x, bv.x), __fmul_rn(w.y, bv.y)), ti = __fadd_rn(__fmul_rn(w.x, bv.y), __fmul_rn(w.y, bv.x));
-    *pa = make_float2(__fadd_rn(av.x, tr), __fadd_rn(av.y, ti));
-    *pb = make_float2(__fsub_rn(av.x, tr), __fsub_rn(av.y, ti));
+  for (int m = 2; m <= N; m <<= 1) {
+    const int half = m >> 1;
+    for (int j = tid; j < N; j += 128) {                        // butterflies 0 .. N/2-1 of each transform
+      float2* base = (j < N / 2) ? s_f0 : s_f1;
+      const int b = (j < N / 2) ? j : j - N / 2;
+      const int g = b / half, jj = b - g * half;
+      const float2 w = a.tw[jj * (N / m)];
+      float2* pa = base + g * m + jj;
+      float2* pb = pa + half;
+      const float2 av = *pa, bv = *pb;
+      const float tr = __fsub_rn(__fmul_rn(w.x, bv.x), __fmul_rn(w.y, bv.y)), ti = __fadd_rn(__fmul_rn(w.x, bv.y), __fmul_rn(w.y, bv.x));
+      *pa = make_float2(__fadd_rn(av.x, tr), __fadd_rn(av.y, ti));
+      *pb = make_float2(__fsub_rn(av.x, tr), __fsub_rn(av.y, ti));
+    }
     __syncthreads();
   }
   if (tid < 62) {
-    const int bin = (tid < 31) ? 128 + (tid - 31) : tid - 30;
-    const float2 d = a.pss_freq[u * 62 + tid], yp = s_f[0][bin], ys = s_f[1][bin];
+    const int bin = (tid < 31) ? N + (tid - 31) : tid - 30;
+    const float2 d = a.pss_freq[u * 62 + tid], yp = s_f0[bin], ys = s_f1[bin];
     const float hr = __fadd_rn(__fmul_rn(yp.x, d.x), __fmul_rn(yp.y, d.y)), hi = __fsub_rn(__fmul_rn(yp.y, d.x), __fmul_rn(yp.x, d.y));
     s_z[tid] = make_float2(__fadd_rn(__fmul_rn(ys.x, hr), __fmul_rn(ys.y, hi)), __fsub_rn(__fmul_rn(ys.y, hr), __fmul_rn(ys.x, hi)));
   }

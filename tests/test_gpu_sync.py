@@ -180,3 +180,38 @@ def test_init_cell_sequence_cellsearch_then_mib(gpu, oracle):
     L.srslte_bit_pack_vector(payload, packed, 24)
     assert bytes(packed) == np.packbits(np.frombuffer(payload, np.uint8)).tobytes()
     assert L.srslte_sampling_freq_hz(50) == 15360000 and L.srslte_tti_interval(3, 10238) == 5
+
+
+@pytest.mark.parametrize("prb,nfft", [(15, 256), (25, 512), (50, 1024), (100, 2048)])
+def test_pss_sss_at_the_cells_own_rate(gpu, oracle, prb, nfft):
+    """tracking-style search at the cell's sampling rate: one root, a window around the expected position, nfft-sample
+    replica and nfft-point transforms; position, power, cell group and subframe equal the oracle's"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    cid = 100 + prb
+    cell = o.make_cell(prb, 1, cid)
+    bufs = []
+    for first in (0, 5):
+        sfs = []
+        for sf in (first, first + 1):
+            cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=1000, tm=1)
+            sfs.append(o.gen_subframe(cell, cfg, 40 + sf, 7.0, None, pcfich=True, sync=True)[1])
+        x = np.concatenate(sfs)
+        bufs.append((x * np.exp(2j * np.pi * 0.07 * np.arange(len(x)) / nfft)).astype(np.complex64))
+    exp = 832 * nfft // 128
+    ns = exp + 3 * nfft
+    win = np.stack([b[:ns] for b in bufs])
+    d_iq = torch.from_numpy(win.view(np.float32).reshape(2, -1)).cuda()
+    d_res = torch.zeros(2 * C.sizeof(sg.SyncResult), dtype=torch.uint8, device="cuda")
+    ctx.cell_search(d_iq, 2, ns, ns, d_res, force_n_id_2=cid % 3, first_pos=exp - 40, nfft=nfft)
+    torch.cuda.synchronize()
+    res = (sg.SyncResult * 2).from_buffer_copy(d_res.cpu().numpy().tobytes())
+    for i in range(2):
+        ref = o.pss_search(win[i], nfft, cid % 3, exp - 40)
+        n1, sf5, corr = o.sss_detect(win[i], ref["pos"], ref["n_id_2"], nfft)
+        r = res[i]
+        assert (r.peak_pos, r.n_id_2, r.n_id_1, r.sf5) == (ref["pos"], ref["n_id_2"], n1, sf5)
+        assert np.float32(r.peak) == ref["peak"] and np.float32(r.sss_corr) == corr and abs(r.cfo - ref["cfo"]) <= 1e-5
+        # at an oversampled rate the correlation peak is several samples wide: noise may move it by a sample
+        assert abs(r.peak_pos - exp) <= 2 and 3 * r.n_id_1 + r.n_id_2 == cid and r.sf5 == i and abs(r.cfo - 0.07) < 0.06
