@@ -218,7 +218,13 @@ SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *ou
 /* ---- cell search (ue/src/phy/phch_recv.cc:140-188) --------------------------------------------------- */
 typedef struct SRSLTE_API { uint32_t full_secs; double frac_secs; } srslte_timestamp_t;
 typedef struct SRSLTE_API { double gain; } srslte_agc_t;
-typedef struct SRSLTE_API { srslte_agc_t agc; } srslte_ue_sync_t;      /* only what init_cell dereferences: cs.ue_sync.agc */
+typedef struct SRSLTE_API { float threshold; float em_alpha; } srslte_sync_t;
+/* subframe synchroniser (phch_recv.cc:100-113,236-258,302-334): what the callers dereference are .agc and .strack */
+typedef struct SRSLTE_API {
+  srslte_agc_t agc;
+  srslte_sync_t strack;
+  void *gpu;
+} srslte_ue_sync_t;
 typedef struct SRSLTE_API {
   uint32_t cell_id;
   srslte_cp_t cp;
@@ -244,6 +250,25 @@ SRSLTE_API void srslte_ue_cellsearch_set_threshold(srslte_ue_cellsearch_t *q, fl
 SRSLTE_API int srslte_ue_cellsearch_scan(srslte_ue_cellsearch_t *q, srslte_ue_cellsearch_result_t found_cells[3], uint32_t *max_N_id_2);
 SRSLTE_API int srslte_ue_cellsearch_scan_N_id_2(srslte_ue_cellsearch_t *q, uint32_t N_id_2, srslte_ue_cellsearch_result_t *found_cell);
 SRSLTE_API int srslte_ue_sync_start_agc(srslte_ue_sync_t *q, double (*set_gain_callback)(void *, double), float init_gain_value);
+/* Subframe synchronisation at the cell's own sampling rate.  Every call pulls samples through the radio callback.  While
+ * searching (a 5 ms PSS/SSS search for the cell's id) the calls return 0; once aligned every call returns 1 with exactly
+ * one subframe in the buffer, checks the PSS of subframes 0 and 5 in a window around its expected place, follows timing
+ * drift by reading a few samples more or less, averages the carrier offset, and falls back to searching after ten
+ * consecutive missed peaks.  < 0 on error.  The samples are handed out as received (no CFO correction). */
+SRSLTE_API int srslte_ue_sync_init(srslte_ue_sync_t *q, srslte_cell_t cell,
+                                   int (*recv_callback)(void *, void *, uint32_t, srslte_timestamp_t *), void *stream_handler);
+SRSLTE_API void srslte_ue_sync_free(srslte_ue_sync_t *q);
+SRSLTE_API int srslte_ue_sync_zerocopy(srslte_ue_sync_t *q, cf_t *input_buffer);            /* phch_recv.cc:322 */
+SRSLTE_API int srslte_ue_sync_get_buffer(srslte_ue_sync_t *q, cf_t **sf_symbols);           /* phch_recv.cc:237 */
+SRSLTE_API uint32_t srslte_ue_sync_get_sfidx(srslte_ue_sync_t *q);
+SRSLTE_API float srslte_ue_sync_get_cfo(srslte_ue_sync_t *q);                               /* Hz */
+SRSLTE_API float srslte_ue_sync_get_sfo(srslte_ue_sync_t *q);                               /* Hz, from the timing corrections */
+SRSLTE_API void srslte_ue_sync_set_cfo(srslte_ue_sync_t *q, float cfo);
+SRSLTE_API void srslte_ue_sync_set_agc_period(srslte_ue_sync_t *q, uint32_t period);
+SRSLTE_API void srslte_ue_sync_decode_sss_on_track(srslte_ue_sync_t *q, bool enabled);
+SRSLTE_API void srslte_ue_sync_get_last_timestamp(srslte_ue_sync_t *q, srslte_timestamp_t *timestamp);
+SRSLTE_API void srslte_sync_set_threshold(srslte_sync_t *q, float threshold);
+SRSLTE_API void srslte_sync_set_em_alpha(srslte_sync_t *q, float alpha);
 SRSLTE_API float srslte_agc_get_gain(srslte_agc_t *q);
 
 /* ---- MIB decode (ue/src/phy/phch_recv.cc:98,246-253) ------------------------------------------------- */

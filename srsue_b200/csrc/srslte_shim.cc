@@ -511,6 +511,166 @@ int srslte_ue_sync_start_agc(srslte_ue_sync_t* q, double (*)(void*, double), flo
 }
 float srslte_agc_get_gain(srslte_agc_t* q) { return q ? (float)q->gain : 0.f; }
 
+// ---- subframe synchroniser -------------------------------------------------------------------------------------
+namespace {
+struct UeSyncGpu {
+  srsue_gpu_ctx_t* ctx = nullptr;
+  int (*recv)(void*, void*, uint32_t, srslte_timestamp_t*) = nullptr;
+  void* handler = nullptr;
+  uint32_t cell_id = 0;
+  int nfft = 0, sf_len = 0, off_pss = 0, win = 0;
+  bool tracking = false, sss_on_track = true;
+  uint32_t sf_idx = 0;
+  int pending_shift = 0;               // samples to skip (> 0) or to re-use (< 0) before the next subframe
+  int lost = 0;
+  float cfo_mean = 0.f;                // subcarrier spacings
+  double drift_samples = 0.0, tracked_sf = 0.0;
+  std::vector<srsue_gpu_cf_t> window;  // two half frames while searching
+  std::vector<srsue_gpu_cf_t> tail;    // the end of the previous subframe (for negative timing corrections)
+  std::vector<srsue_gpu_cf_t> own;     // buffer of srslte_ue_sync_get_buffer
+  srsue_gpu_cf_t* d_iq = nullptr;
+  srsue_gpu_sync_result_t* d_res = nullptr;
+  cudaStream_t stream = nullptr;
+  srslte_timestamp_t last_ts{};
+};
+
+// one cell search on host samples: upload, search root n_id_2 from first_pos on, read the result back
+int sync_search(UeSyncGpu* g, const srsue_gpu_cf_t* x, int n_samples, int first_pos, srsue_gpu_sync_result_t* r) {
+  if (cudaMemcpyAsync(g->d_iq, x, (size_t)n_samples * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
+  if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, n_samples, n_samples, g->nfft, (int)(g->cell_id % 3), first_pos, g->d_res, g->stream)) return SRSLTE_ERROR;
+  cudaMemcpyAsync(r, g->d_res, sizeof(*r), cudaMemcpyDeviceToHost, g->stream);
+  return cudaStreamSynchronize(g->stream) == cudaSuccess ? SRSLTE_SUCCESS : SRSLTE_ERROR;
+}
+
+int sync_find(srslte_ue_sync_t* q, UeSyncGpu* g) {
+  const int H = 5 * g->sf_len;
+  // slide the two-half-frame window by one half frame
+  std::memmove(g->window.data(), g->window.data() + H, (size_t)H * sizeof(srsue_gpu_cf_t));
+  if (g->recv(g->handler, g->window.data() + H, (uint32_t)H, &g->last_ts) < 0) return SRSLTE_ERROR;
+  srsue_gpu_sync_result_t r;
+  if (sync_search(g, g->window.data(), g->off_pss + H + g->nfft - 1, g->off_pss, &r)) return SRSLTE_ERROR;
+  const float thr = q->strack.threshold > 0.f ? q->strack.threshold : 10.f;
+  if (!r.valid || r.mean_power <= 0.f || r.peak / r.mean_power < thr || 3 * r.n_id_1 + r.n_id_2 != (int)g->cell_id) return 0;
+  // the subframe that holds this PSS starts at s; align the stream to the next subframe boundary after the window
+  const int s = r.peak_pos - g->off_pss;
+  const int have = 2 * H - s;                                   // samples of the stream from s to the end of the window
+  const int k = (have + g->sf_len - 1) / g->sf_len;             // subframes begun by then
+  const int skip = k * g->sf_len - have;
+  if (skip > 0) {
+    std::vector<srsue_gpu_cf_t> junk((size_t)skip);
+    if (g->recv(g->handler, junk.data(), (uint32_t)skip, &g->last_ts) < 0) return SRSLTE_ERROR;
+  }
+  g->sf_idx = (uint32_t)(((r.sf5 ? 5 : 0) + k - 1) % 10);        // index of the last subframe already past
+  g->tracking = true;
+  g->lost = 0;
+  g->pending_shift = 0;
+  g->cfo_mean = r.cfo;
+  std::fill(g->tail.begin(), g->tail.end(), srsue_gpu_cf_t{0.f, 0.f});
+  return 0;
+}
+
+int sync_track(srslte_ue_sync_t* q, UeSyncGpu* g, srsue_gpu_cf_t* buf) {
+  const int L = g->sf_len, T = (int)g->tail.size();
+  int shift = g->pending_shift;
+  g->pending_shift = 0;
+  if (shift > 0) {                                              // we are early: drop samples
+    std::vector<srsue_gpu_cf_t> junk((size_t)shift);
+    if (g->recv(g->handler, junk.data(), (uint32_t)shift, &g->last_ts) < 0) return SRSLTE_ERROR;
+    shift = 0;
+  }
+  const int reuse = std::min(-shift, T);                         // we are late: the subframe began in the previous read
+  if (reuse > 0) std::memcpy(buf, g->tail.data() + (T - reuse), (size_t)reuse * sizeof(srsue_gpu_cf_t));
+  if (g->recv(g->handler, buf + reuse, (uint32_t)(L - reuse), &g->last_ts) < 0) return SRSLTE_ERROR;
+  std::memcpy(g->tail.data(), buf + (L - T), (size_t)T * sizeof(srsue_gpu_cf_t));
+  g->sf_idx = (g->sf_idx + 1) % 10;
+  g->tracked_sf += 1.0;
+  if (g->sf_idx == 0 || g->sf_idx == 5) {
+    srsue_gpu_sync_result_t r;
+    if (sync_search(g, buf, g->off_pss + g->win + g->nfft, g->off_pss - g->win, &r)) return SRSLTE_ERROR;
+    const float thr = q->strack.threshold > 0.f ? q->strack.threshold : 10.f;
+    const bool good = r.valid && r.mean_power > 0.f && r.peak / r.mean_power >= thr &&
+                      (!g->sss_on_track || (3 * r.n_id_1 + r.n_id_2 == (int)g->cell_id && (r.sf5 != 0) == (g->sf_idx == 5)));
+    if (good) {
+      g->lost = 0;
+      g->pending_shift = r.peak_pos - g->off_pss;
+      g->drift_samples += g->pending_shift;
+      const float alpha = q->strack.em_alpha > 0.f ? q->strack.em_alpha : 0.1f;
+      g->cfo_mean = (1.f - alpha) * g->cfo_mean + alpha * r.cfo;
+    } else if (++g->lost >= 10) {
+      g->tracking = false;                                        // back to searching; the window restarts empty
+      std::fill(g->window.begin(), g->window.end(), srsue_gpu_cf_t{0.f, 0.f});
+    }
+  }
+  return 1;
+}
+}  // namespace
+
+int srslte_ue_sync_init(srslte_ue_sync_t* q, srslte_cell_t cell, int (*recv_callback)(void*, void*, uint32_t, srslte_timestamp_t*),
+                        void* stream_handler) {
+  if (!q || !recv_callback || cell.id > 503 || cell.cp != SRSLTE_CP_NORM) return SRSLTE_ERROR_INVALID_INPUTS;
+  const int n = symbol_sz((int)cell.nof_prb);
+  if (n < 0 || n == 1536) return SRSLTE_ERROR_INVALID_INPUTS;      // the synchroniser needs a power-of-two symbol size
+  std::memset(q, 0, sizeof(*q));
+  srsue_gpu_ctx_t* ctx = shared_ctx();
+  if (!ctx) return SRSLTE_ERROR;
+  auto* g = new UeSyncGpu();
+  g->ctx = ctx; g->recv = recv_callback; g->handler = stream_handler; g->cell_id = cell.id;
+  g->nfft = n; g->sf_len = 15 * n; g->off_pss = 832 * n / 128; g->win = n / 8;
+  g->window.assign((size_t)10 * g->sf_len, srsue_gpu_cf_t{0.f, 0.f});
+  g->tail.assign((size_t)g->win, srsue_gpu_cf_t{0.f, 0.f});
+  g->own.resize((size_t)g->sf_len);
+  const size_t max_search = (size_t)g->off_pss + 5 * g->sf_len + n;
+  if (cudaMalloc((void**)&g->d_iq, max_search * sizeof(srsue_gpu_cf_t)) != cudaSuccess ||
+      cudaMalloc((void**)&g->d_res, sizeof(srsue_gpu_sync_result_t)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaFree(g->d_iq); cudaFree(g->d_res);
+    delete g;
+    return SRSLTE_ERROR;
+  }
+  q->strack.threshold = 10.f; q->strack.em_alpha = 0.1f;
+  q->gpu = g;
+  return SRSLTE_SUCCESS;
+}
+
+void srslte_ue_sync_free(srslte_ue_sync_t* q) {
+  if (!q || !q->gpu) return;
+  auto* g = static_cast<UeSyncGpu*>(q->gpu);
+  cudaFree(g->d_iq); cudaFree(g->d_res);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  q->gpu = nullptr;
+}
+
+int srslte_ue_sync_zerocopy(srslte_ue_sync_t* q, cf_t* input_buffer) {
+  if (!q || !q->gpu || !input_buffer) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* g = static_cast<UeSyncGpu*>(q->gpu);
+  return g->tracking ? sync_track(q, g, reinterpret_cast<srsue_gpu_cf_t*>(input_buffer)) : sync_find(q, g);
+}
+
+int srslte_ue_sync_get_buffer(srslte_ue_sync_t* q, cf_t** sf_symbols) {
+  if (!q || !q->gpu || !sf_symbols) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* g = static_cast<UeSyncGpu*>(q->gpu);
+  *sf_symbols = reinterpret_cast<cf_t*>(g->own.data());
+  return srslte_ue_sync_zerocopy(q, *sf_symbols);
+}
+
+uint32_t srslte_ue_sync_get_sfidx(srslte_ue_sync_t* q) { return (q && q->gpu) ? static_cast<UeSyncGpu*>(q->gpu)->sf_idx : 0; }
+float srslte_ue_sync_get_cfo(srslte_ue_sync_t* q) { return (q && q->gpu) ? 15000.f * static_cast<UeSyncGpu*>(q->gpu)->cfo_mean : 0.f; }
+float srslte_ue_sync_get_sfo(srslte_ue_sync_t* q) {
+  if (!q || !q->gpu) return 0.f;
+  auto* g = static_cast<UeSyncGpu*>(q->gpu);
+  // accumulated timing corrections per elapsed time: samples per second of sampling-clock offset
+  return g->tracked_sf > 0.0 ? (float)(g->drift_samples / (g->tracked_sf * 1e-3)) : 0.f;
+}
+void srslte_ue_sync_set_cfo(srslte_ue_sync_t* q, float cfo) { if (q && q->gpu) static_cast<UeSyncGpu*>(q->gpu)->cfo_mean = cfo / 15000.f; }
+void srslte_ue_sync_set_agc_period(srslte_ue_sync_t*, uint32_t) {}
+void srslte_ue_sync_decode_sss_on_track(srslte_ue_sync_t* q, bool enabled) { if (q && q->gpu) static_cast<UeSyncGpu*>(q->gpu)->sss_on_track = enabled; }
+void srslte_ue_sync_get_last_timestamp(srslte_ue_sync_t* q, srslte_timestamp_t* timestamp) {
+  if (q && q->gpu && timestamp) *timestamp = static_cast<UeSyncGpu*>(q->gpu)->last_ts;
+}
+void srslte_sync_set_threshold(srslte_sync_t* q, float threshold) { if (q) q->threshold = threshold; }
+void srslte_sync_set_em_alpha(srslte_sync_t* q, float alpha) { if (q) q->em_alpha = alpha; }
+
 // ---- MIB search over the air interface ----------------------------------------------------------------------
 namespace {
 struct MibSyncGpu {

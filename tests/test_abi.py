@@ -49,7 +49,10 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_ue_sync_start_agc", "srslte_agc_get_gain", "srslte_ue_mib_sync_init", "srslte_ue_mib_sync_decode",
               "srslte_ue_mib_sync_free", "srslte_bit_pack_vector", "srslte_bit_unpack_vector", "srslte_bit_pack", "srslte_bit_unpack",
               "srslte_cp_string", "srslte_cell_fprint", "srslte_sampling_freq_hz", "srslte_timestamp_copy", "srslte_timestamp_add",
-              "srslte_tti_interval"]:
+              "srslte_tti_interval", "srslte_ue_sync_init", "srslte_ue_sync_free", "srslte_ue_sync_zerocopy", "srslte_ue_sync_get_buffer",
+              "srslte_ue_sync_get_sfidx", "srslte_ue_sync_get_cfo", "srslte_ue_sync_get_sfo", "srslte_ue_sync_set_cfo",
+              "srslte_ue_sync_set_agc_period", "srslte_ue_sync_decode_sss_on_track", "srslte_ue_sync_get_last_timestamp",
+              "srslte_sync_set_threshold", "srslte_sync_set_em_alpha"]:
         assert hasattr(lib, n), n
 
 

@@ -9,6 +9,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+class UeSync(C.Structure):
+    """srslte_ue_sync_t of include/srsue_gpu/srslte_compat.h"""
+    _fields_ = [("agc_gain", C.c_double), ("threshold", C.c_float), ("em_alpha", C.c_float), ("gpu", C.c_void_p)]
+
+
 def _half_frame(o, cell, first_sf, seed, snr, cfo, shift):
     out = []
     for i in range(5):
@@ -83,7 +88,7 @@ def test_forced_root_and_cellsearch_shim(gpu, oracle):
         _fields_ = [("cell_id", C.c_uint32), ("cp", C.c_int), ("peak", C.c_float), ("mode", C.c_float), ("psr", C.c_float), ("cfo", C.c_float)]
 
     class CellSearch(C.Structure):
-        _fields_ = [("agc_gain", C.c_double), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
+        _fields_ = [("ue_sync", UeSync), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
 
     state = {"i": 0}
     RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
@@ -151,10 +156,10 @@ def test_init_cell_sequence_cellsearch_then_mib(gpu, oracle):
         _fields_ = [("cell_id", C.c_uint32), ("cp", C.c_int), ("peak", C.c_float), ("mode", C.c_float), ("psr", C.c_float), ("cfo", C.c_float)]
 
     class CellSearch(C.Structure):
-        _fields_ = [("agc_gain", C.c_double), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
+        _fields_ = [("ue_sync", UeSync), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
 
     class MibSync(C.Structure):
-        _fields_ = [("agc_gain", C.c_double), ("cell_id", C.c_uint32), ("gpu", C.c_void_p)]
+        _fields_ = [("ue_sync", UeSync), ("cell_id", C.c_uint32), ("gpu", C.c_void_p)]
 
     cs = CellSearch()
     assert L.srslte_ue_cellsearch_init(C.byref(cs), cb, None) == 0
@@ -215,3 +220,68 @@ def test_pss_sss_at_the_cells_own_rate(gpu, oracle, prb, nfft):
         assert np.float32(r.peak) == ref["peak"] and np.float32(r.sss_corr) == corr and abs(r.cfo - ref["cfo"]) <= 1e-5
         # at an oversampled rate the correlation peak is several samples wide: noise may move it by a sample
         assert abs(r.peak_pos - exp) <= 2 and 3 * r.n_id_1 + r.n_id_2 == cid and r.sf5 == i and abs(r.cfo - 0.07) < 0.06
+
+
+def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle):
+    """srslte_ue_sync_zerocopy (phch_recv.cc:322) on a continuous 5 MHz stream that starts at an arbitrary sample, loses
+    two samples at one point and repeats one at another (sampling-clock drift): 0 while searching, then exactly one aligned
+    subframe per call with the right subframe index, re-aligned within a few subframes after each slip"""
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import Cell
+    prb, nfft, cid = 25, 512, 183
+    sf_len = 15 * nfft
+    cell = o.make_cell(prb, 1, cid)
+    sfs = []
+    for sf in range(10):
+        cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=1000, tm=1)
+        sfs.append(o.gen_subframe(cell, cfg, 300 + sf, 10.0, None, pcfich=True, sync=True)[1])
+    frame = np.concatenate(sfs)
+    S = np.tile(frame, 9)                                    # 90 subframes
+    starts = np.arange(90) * sf_len                          # true start of every subframe in S
+    # two samples vanish inside subframe 42, one sample is repeated inside subframe 65
+    p1, p2 = 42 * sf_len + 1000, 65 * sf_len + 2000
+    M = np.concatenate([S[:p1], S[p1 + 2:p2], S[p2 - 1:]])
+    mstart = starts.copy()
+    mstart[43:] -= 2
+    mstart[66:] += 1
+    state = {"pos": 3333}                                    # the radio starts somewhere inside subframe 0
+    RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
+
+    def recv(handler, data, nsamples, ts):
+        a = state["pos"]
+        assert a + nsamples <= len(M)
+        C.memmove(data, M[a:a + nsamples].ctypes.data, nsamples * 8)
+        state["pos"] = a + nsamples
+        return nsamples
+
+    cb = RECV(recv)
+    q = UeSync()
+    c = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=cid, cp=0, phich_length=0, phich_resources=2)
+    assert L.srslte_ue_sync_init(C.byref(q), c, cb, None) == 0
+    buf = np.zeros(sf_len, np.complex64)
+    delivered, zeros = [], 0
+    while state["pos"] + 6 * sf_len < len(M):
+        rc = L.srslte_ue_sync_zerocopy(C.byref(q), buf.ctypes.data_as(C.c_void_p))
+        assert rc >= 0
+        if rc == 0:
+            zeros += 1
+            assert not delivered, "lost synchronisation"
+            continue
+        end = state["pos"]                                    # the buffer ends where the stream position is now
+        delivered.append((end - sf_len, L.srslte_ue_sync_get_sfidx(C.byref(q)), buf.copy()))
+    assert 1 <= zeros <= 3 and len(delivered) > 60
+    aligned = 0
+    for a, sfidx, data in delivered:
+        j = int(np.argmin(np.abs(mstart - a)))
+        assert sfidx == j % 10
+        if 43 <= j <= 46 or 66 <= j <= 71:                    # re-aligning after a slip (next PSS check + one subframe)
+            continue
+        assert a == mstart[j], (j, a - mstart[j])
+        aligned += 1
+    assert aligned > 50
+    L.srslte_ue_sync_get_cfo.restype = C.c_float
+    L.srslte_ue_sync_get_sfo.restype = C.c_float
+    assert abs(L.srslte_ue_sync_get_cfo(C.byref(q))) < 600.0
+    L.srslte_ue_sync_free(C.byref(q))
