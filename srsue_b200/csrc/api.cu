@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -91,9 +92,9 @@ struct srsue_gpu_ctx {
   std::map<int, TurboTables> turbo;
   Scratch scratch;
   int last_grid = 0, last_block = 0, last_smem = 0, last_ncb = 0;
-  int launch_count = 0;
-  bool attr_set = false;
-  bool pdcch_attr_set = false;
+  std::atomic<int> launch_count{0};       // workers on different streams share the context
+  std::atomic<bool> attr_set{false};
+  std::atomic<bool> pdcch_attr_set{false};
   // cell-search tables and scratch (built on first use)
   float2* d_pss_freq = nullptr; int8_t* d_sss = nullptr;
   std::map<int, std::pair<float2*, float2*>> sync_tabs;      // nfft -> (PSS time replicas [3][nfft], nfft/2 twiddles)
@@ -135,11 +136,10 @@ int turbo_slot_words(const TurboGeom& g) {
 // CTAs per SM of the persistent decoder.  Two independent CTAs per SM drift out of phase, which spreads the
 // L2 demand of the load-dominated backward sweeps and halves the width of every barrier.
 int turbo_ctas_per_sm() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("SRSUE_TURBO_CTAS_PER_SM");
-    v = e ? std::max(1, std::min(4, atoi(e))) : 2;
-  }
+    return e ? std::max(1, std::min(4, atoi(e))) : 2;
+  }();
   return v;
 }
 
@@ -447,7 +447,7 @@ int srsue_gpu_tdec_last_launch(srsue_gpu_ctx_t* ctx, int* grid, int* block, int*
   return 0;
 }
 
-int srsue_gpu_last_launch_count(srsue_gpu_ctx_t* ctx) { return ctx ? ctx->launch_count : 0; }
+int srsue_gpu_last_launch_count(srsue_gpu_ctx_t* ctx) { return ctx ? ctx->launch_count.load() : 0; }
 
 // ---- PDSCH plan -------------------------------------------------------------------------------------
 int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* cell, const srsue_gpu_pdsch_cfg_t* cfg,
