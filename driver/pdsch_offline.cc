@@ -9,6 +9,7 @@
 // thread hand-off of thread_pool::start_worker (ue/src/common/thread_pool.cc:246-254).
 //
 //   pdsch_offline worker|batch <in.bin> <out.bin>
+//   pdsch_offline acquire <capture.bin> <out.txt>     cell search -> MIB -> subframe synchronisation on a 1.92 Msps capture
 // in.bin : 12 int32 {magic 0x53525355, nof_prb, nof_ports, cell_id, sf_idx, cfi, rnti, qm, tbs, rv, n_sf, max_iter}
 //          followed by n_sf * SRSLTE_SF_LEN_PRB(nof_prb) cf_t samples
 // out.bin: per subframe {int32 ack, int32 n_iter, float snr} followed by tbs/8 payload bytes
@@ -140,10 +141,97 @@ int run_batch(const Header& h, cf_t* iq, FILE* out) {
   return 0;
 }
 
+// ---- mode "acquire": what phch_recv does before any subframe reaches a worker (phch_recv.cc:136-264): cell search,
+// MIB search, then subframe synchronisation with the system frame number taken from the MIB of subframes 0.  The
+// "radio" is a capture file at 1.92 Msps that wraps around (in.bin: int32 magic 0x53525355, int32 n_samples, cf_t...).
+struct FileRadio { const cf_t* x; size_t n, pos; };
+int file_recv(void* h, void* data, uint32_t nsamples, srslte_timestamp_t* ts) {
+  auto* r = static_cast<FileRadio*>(h);
+  cf_t* out = static_cast<cf_t*>(data);
+  for (uint32_t i = 0; i < nsamples; i++) { out[i] = r->x[r->pos]; r->pos = (r->pos + 1) % r->n; }
+  if (ts) { ts->full_secs = 0; ts->frac_secs = 0.0; }
+  return (int)nsamples;
+}
+
+int run_acquire(const cf_t* iq, size_t n, FILE* out) {
+  FileRadio radio{iq, n, 0};
+  srslte_ue_cellsearch_t cs;
+  srslte_ue_cellsearch_result_t found_cells[3];
+  std::memset(found_cells, 0, sizeof(found_cells));
+  if (srslte_ue_cellsearch_init(&cs, file_recv, &radio)) { fprintf(stderr, "Initiating UE cell search\n"); return 1; }
+  srslte_ue_cellsearch_set_nof_frames_to_scan(&cs, 8);
+  srslte_ue_cellsearch_set_threshold(&cs, 15.0f);
+  uint32_t max_peak_cell = 0;
+  const int ret = srslte_ue_cellsearch_scan(&cs, found_cells, &max_peak_cell);
+  srslte_ue_cellsearch_free(&cs);
+  if (ret <= 0) { fprintf(stderr, "Could not find any PSS in this capture\n"); return 1; }
+  srslte_cell_t cell;
+  std::memset(&cell, 0, sizeof(cell));
+  cell.id = found_cells[max_peak_cell].cell_id;
+  cell.cp = found_cells[max_peak_cell].cp;
+  const float cellsearch_cfo = found_cells[max_peak_cell].cfo;
+  srslte_ue_mib_sync_t ue_mib_sync;
+  if (srslte_ue_mib_sync_init(&ue_mib_sync, cell.id, cell.cp, file_recv, &radio)) { fprintf(stderr, "Initiating UE MIB synchronization\n"); return 1; }
+  uint8_t bch_payload[SRSLTE_BCH_PAYLOAD_LEN];
+  uint32_t sfn = 0, sfn_offset = 0;
+  const int mret = srslte_ue_mib_sync_decode(&ue_mib_sync, 40, bch_payload, &cell.nof_ports, &sfn_offset);
+  srslte_ue_mib_sync_free(&ue_mib_sync);
+  if (mret != 1) { fprintf(stderr, "Error decoding MIB\n"); return 1; }
+  srslte_pbch_mib_unpack(bch_payload, &cell, &sfn);
+  fprintf(out, "cell_id %u ports %u prb %u phich_ng %d cfo_hz %.0f\n", cell.id, cell.nof_ports, cell.nof_prb, (int)cell.phich_resources,
+          cellsearch_cfo);
+  // the capture is at 1.92 Msps: synchronise on its six central PRBs and follow the frame number (sync_sfn, phch_recv.cc:230-264)
+  srslte_cell_t view = cell;
+  view.nof_prb = 6;
+  srslte_ue_sync_t ue_sync;
+  srslte_ue_mib_t ue_mib;
+  if (srslte_ue_sync_init(&ue_sync, view, file_recv, &radio) || srslte_ue_mib_init(&ue_mib, view)) { fprintf(stderr, "Initiating ue_sync\n"); return 1; }
+  srslte_ue_sync_set_cfo(&ue_sync, cellsearch_cfo);
+  cf_t* sf_buffer = nullptr;
+  int delivered = 0, mib_ok = 0, sf_errors = 0;
+  int expect = -1;
+  for (int i = 0; i < 80 && delivered < 40; i++) {
+    const int r = srslte_ue_sync_get_buffer(&ue_sync, &sf_buffer);
+    if (r < 0) { fprintf(stderr, "ue_sync failed\n"); return 1; }
+    if (r == 0) continue;
+    const int sf = (int)srslte_ue_sync_get_sfidx(&ue_sync);
+    if (expect >= 0 && sf != expect) sf_errors++;
+    expect = (sf + 1) % 10;
+    delivered++;
+    if (sf == 0) {
+      uint32_t off = 0, s2 = 0;
+      srslte_pbch_decode_reset(&ue_mib.pbch);
+      if (srslte_ue_mib_decode(&ue_mib, sf_buffer, bch_payload, nullptr, &off) == SRSLTE_UE_MIB_FOUND) {
+        srslte_pbch_mib_unpack(bch_payload, nullptr, &s2);
+        fprintf(out, "tti %u\n", (s2 + off) * 10);
+        mib_ok++;
+      }
+    }
+  }
+  fprintf(out, "delivered %d sf_errors %d mib_decoded %d\n", delivered, sf_errors, mib_ok);
+  srslte_ue_mib_free(&ue_mib);
+  srslte_ue_sync_free(&ue_sync);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
-  if (argc != 4) { fprintf(stderr, "usage: %s worker|batch <in.bin> <out.bin>\n", argv[0]); return 2; }
+  if (argc != 4) { fprintf(stderr, "usage: %s worker|batch|acquire <in.bin> <out>\n", argv[0]); return 2; }
+  if (std::strcmp(argv[1], "acquire") == 0) {
+    FILE* in = fopen(argv[2], "rb");
+    if (!in) { perror(argv[2]); return 1; }
+    int32_t hdr[2];
+    if (fread(hdr, sizeof(hdr), 1, in) != 1 || hdr[0] != 0x53525355 || hdr[1] < 19200) { fprintf(stderr, "bad capture header\n"); return 1; }
+    std::vector<cf_t> x((size_t)hdr[1]);
+    if (fread(x.data(), sizeof(cf_t), x.size(), in) != x.size()) { fprintf(stderr, "short read\n"); return 1; }
+    fclose(in);
+    FILE* out = fopen(argv[3], "w");
+    if (!out) { perror(argv[3]); return 1; }
+    const int rc = run_acquire(x.data(), x.size(), out);
+    fclose(out);
+    return rc;
+  }
   FILE* in = fopen(argv[2], "rb");
   if (!in) { perror(argv[2]); return 1; }
   Header h;

@@ -285,3 +285,36 @@ def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle):
     L.srslte_ue_sync_get_sfo.restype = C.c_float
     assert abs(L.srslte_ue_sync_get_cfo(C.byref(q))) < 600.0
     L.srslte_ue_sync_free(C.byref(q))
+
+
+def test_cpp_driver_acquire_mode(gpu, oracle, tmp_path):
+    """driver/pdsch_offline.cc acquire: phch_recv's start-up (cell search, MIB search, subframe synchronisation with the
+    frame number from the MIB) in C++ over a capture file that wraps around"""
+    import os, struct, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "pdsch_offline")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built (run __graft_entry__.build())")
+    o = oracle
+    cid, ports, sfn0 = 344, 1, 100
+    cell = o.make_cell(6, ports, cid)
+    stream = []
+    for fr in range(4):                                   # 40 ms: one BCH period, so the wrap-around is seamless
+        for sf in range(10):
+            cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=104, tm=ports)
+            mib = (o.mib_pack(6, 0, 6, sfn0 + fr), (sfn0 + fr) % 4) if sf == 0 else None
+            stream.append(o.gen_subframe(cell, cfg, 100 * fr + sf, 10.0, None, pcfich=True, sync=True, mib=mib)[1])
+    x = np.roll(np.concatenate(stream), 4567).astype(np.complex64)
+    fin, fout = str(tmp_path / "cap.bin"), str(tmp_path / "out.txt")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("2i", 0x53525355, len(x)))
+        f.write(x.tobytes())
+    r = subprocess.run([exe, "acquire", fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(fout).read().splitlines()
+    first = dict(zip(lines[0].split()[::2], lines[0].split()[1::2]))
+    assert (int(first["cell_id"]), int(first["ports"]), int(first["prb"]), int(first["phich_ng"])) == (cid, ports, 6, 2)
+    ttis = [int(l.split()[1]) for l in lines if l.startswith("tti")]
+    assert len(ttis) >= 3 and all(10 * sfn0 <= t <= 10 * (sfn0 + 3) and t % 10 == 0 for t in ttis)
+    last = dict(zip(lines[-1].split()[::2], lines[-1].split()[1::2]))
+    assert int(last["delivered"]) == 40 and int(last["sf_errors"]) == 0 and int(last["mib_decoded"]) == len(ttis)
