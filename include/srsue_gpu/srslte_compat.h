@@ -37,6 +37,11 @@ extern "C" {
 #define SRSLTE_TCOD_MAX_LEN_CB 6144
 #define SRSLTE_TCOD_TOTALTAIL 12
 #define SRSLTE_SIRNTI 0xFFFF
+#define SRSLTE_PRNTI 0xFFFE
+#define SRSLTE_RARNTI_START 0x0001
+#define SRSLTE_RARNTI_END 0x003C
+#define SRSLTE_CRNTI_START 0x003D
+#define SRSLTE_CRNTI_END 0xFFF3
 
 /* cf_t: srsLTE uses C99 `_Complex float`; {re, im} pairs have the same layout */
 #ifdef SRSUE_GPU_PLAIN_CF
@@ -70,6 +75,33 @@ typedef struct SRSLTE_API {
   uint32_t Qm;
   srslte_ra_mcs_t mcs;
 } srslte_ra_dl_grant_t;
+
+/* Unpacked downlink DCI (phch_worker.cc:288 `srslte_ra_dl_dci_t dci_unpacked`; its ndi, harq_process and rv_idx feed
+ * the MAC grant at :303-307).  Allocation types follow 36.213 7.1.6.1-7.1.6.3. */
+typedef enum { SRSLTE_RA_ALLOC_TYPE0 = 0, SRSLTE_RA_ALLOC_TYPE1, SRSLTE_RA_ALLOC_TYPE2 } srslte_ra_type_t;
+typedef struct SRSLTE_API { uint32_t rbg_bitmask; } srslte_ra_type0_t;
+typedef struct SRSLTE_API { uint32_t vrb_bitmask; uint32_t rbg_subset; bool shift; } srslte_ra_type1_t;
+typedef enum { SRSLTE_RA_TYPE2_NPRB1A_2 = 0, SRSLTE_RA_TYPE2_NPRB1A_3 } srslte_ra_type2_nprb1a_t;
+typedef enum { SRSLTE_RA_TYPE2_NG1 = 0, SRSLTE_RA_TYPE2_NG2 } srslte_ra_type2_ngap_t;
+typedef enum { SRSLTE_RA_TYPE2_LOC = 0, SRSLTE_RA_TYPE2_DIST } srslte_ra_type2_mode_t;
+typedef struct SRSLTE_API {
+  uint32_t riv, L_crb, RB_start;
+  srslte_ra_type2_nprb1a_t n_prb1a;
+  srslte_ra_type2_ngap_t n_gap;
+  srslte_ra_type2_mode_t mode;
+} srslte_ra_type2_t;
+typedef struct SRSLTE_API {
+  srslte_ra_type_t alloc_type;
+  srslte_ra_type0_t type0_alloc;
+  srslte_ra_type1_t type1_alloc;
+  srslte_ra_type2_t type2_alloc;
+  uint32_t mcs_idx;
+  uint32_t harq_process;
+  int rv_idx;
+  bool ndi;
+  bool dci_is_1a;
+  uint32_t tpc;
+} srslte_ra_dl_dci_t;
 
 /* uplink grant: only present so that srslte_phy_grant_t keeps its shape (mac_interface.h:59) */
 typedef struct SRSLTE_API {
@@ -168,13 +200,33 @@ SRSLTE_API int srslte_ue_dl_cfg_grant(srslte_ue_dl_t *q, srslte_ra_dl_grant_t *g
 /* PDCCH (phch_worker.cc:260,293,320): soft bits of the whole control region on the device, then a blind search.
  * find_dl_dci_type returns 1 when a DCI for rnti was found (UE-specific space: formats 1A and 1, then the common space:
  * format 1A; SI/RA/P-RNTI: common space only), 0 when not, < 0 on error; it fills dci_msg, q->last_location and
- * q->last_n_cce.  Turning the message into a grant (srslte_dci_msg_to_dl_grant, needs the 36.213 TBS tables) stays with
- * the caller's libsrslte. */
+ * q->last_n_cce.  srslte_dci_msg_to_dl_grant (below) turns the message into a grant. */
 SRSLTE_API int srslte_pdcch_extract_llr(srslte_pdcch_t *q, cf_t *sf_symbols, cf_t *ce[SRSLTE_MAX_PORTS], float noise_estimate,
                                         uint32_t nsubframe, uint32_t cfi);
 SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx,
                                              uint16_t rnti, srslte_rnti_type_t rnti_type);
 /* uplink grant search (phch_worker.cc:426): DCI format 0 in the UE-specific space; 1 found / 0 / < 0 */
+/* DCI payload -> unpacked fields -> grant (phch_worker.cc:297).  Formats 1A and 1, FDD; localized allocations only
+ * (distributed virtual resource blocks return an error).  Transport-block sizes come from the 27 x 110 table of 36.213
+ * 7.1.7.2.1, which the caller installs once per process with srsue_gpu_ra_set_tbs_table(); until then every call that
+ * needs a size returns SRSLTE_ERROR with a message.  Returns 0 on success (as srsLTE does). */
+SRSLTE_API int srsue_gpu_ra_set_tbs_table(const int32_t *table, uint32_t nof_rows /* 27 */, uint32_t nof_cols /* 110 */);
+SRSLTE_API int srsue_gpu_ra_have_tbs_table(void);
+SRSLTE_API int srslte_dci_msg_to_dl_grant(srslte_dci_msg_t *msg, uint16_t msg_rnti, uint32_t nof_prb, srslte_ra_dl_dci_t *dl_dci,
+                                          srslte_ra_dl_grant_t *grant);
+SRSLTE_API int srslte_dci_msg_unpack_pdsch(srslte_dci_msg_t *msg, srslte_ra_dl_dci_t *data, uint32_t nof_prb, bool crc_is_crnti);
+SRSLTE_API int srslte_dci_msg_pack_pdsch(srslte_ra_dl_dci_t *data, srslte_dci_format_t format, srslte_dci_msg_t *msg, uint32_t nof_prb,
+                                        bool crc_is_crnti);
+SRSLTE_API int srslte_ra_dl_dci_to_grant(srslte_ra_dl_dci_t *dci, uint32_t nof_prb, bool crc_is_crnti, srslte_ra_dl_grant_t *grant);
+SRSLTE_API int srslte_ra_dl_dci_to_grant_prb_allocation(srslte_ra_dl_dci_t *dci, srslte_ra_dl_grant_t *grant, uint32_t nof_prb);
+SRSLTE_API int srslte_ra_tbs_idx_from_mcs(uint32_t mcs_idx);
+SRSLTE_API srslte_mod_t srslte_ra_mod_from_mcs(uint32_t mcs_idx);
+SRSLTE_API int srslte_ra_tbs_from_idx(uint32_t tbs_idx, uint32_t n_prb);
+SRSLTE_API uint32_t srslte_ra_type0_P(uint32_t nof_prb);
+SRSLTE_API uint32_t srslte_ra_type2_n_rb(uint32_t nof_prb);
+SRSLTE_API uint32_t srslte_ra_type2_to_riv(uint32_t L_crb, uint32_t RB_start, uint32_t nof_prb);
+SRSLTE_API void srslte_ra_type2_from_riv(uint32_t riv, uint32_t *L_crb, uint32_t *RB_start, uint32_t nof_prb, uint32_t nof_vrb);
+SRSLTE_API char *srslte_ra_dl_dci_string(srslte_ra_dl_dci_t *dci);                       /* phch_worker.cc:317 */
 SRSLTE_API int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti);
 SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);
 /* HARQ indicator of the uplink transmission (phch_worker.cc:381); needs srslte_ue_dl_decode_fft_estimate of this subframe */

@@ -881,10 +881,28 @@ int srslte_ue_dl_decode_rnti(srslte_ue_dl_t* q, cf_t* input, uint8_t* data, uint
   const uint32_t sf_idx = tti % 10;
   int rc = srslte_ue_dl_decode_fft_estimate(q, input, sf_idx, &cfi);
   if (rc < 0) return rc;
-  if (!u->have_grant) return 0;                       // no DCI for this rnti
-  rc = srslte_ue_dl_cfg_grant(q, &u->grant, u->grant_cfi ? u->grant_cfi : cfi, sf_idx, u->grant_rv);   // cfi 0: from the PCFICH
+  uint32_t rv = u->grant_rv;
+  if (u->have_grant) {
+    rc = srslte_ue_dl_cfg_grant(q, &u->grant, u->grant_cfi ? u->grant_cfi : cfi, sf_idx, rv);   // cfi 0: from the PCFICH
+  } else {
+    // srsLTE's own sequence: PDCCH soft bits, blind search for this rnti, DCI -> grant (needs the installed TBS table)
+    if (!srsue_gpu_ra_have_tbs_table()) return 0;      // no grant source at all
+    rc = srslte_pdcch_extract_llr(&q->pdcch, q->sf_symbols, q->ce, srslte_chest_dl_get_noise_estimate(&q->chest), sf_idx, cfi);
+    if (rc) return rc;
+    srslte_dci_msg_t dci_msg;
+    const srslte_rnti_type_t type = rnti == SRSLTE_SIRNTI ? SRSLTE_RNTI_SI : rnti == SRSLTE_PRNTI ? SRSLTE_RNTI_PCH
+                                    : (rnti >= SRSLTE_RARNTI_START && rnti <= SRSLTE_RARNTI_END) ? SRSLTE_RNTI_RAR : SRSLTE_RNTI_USER;
+    rc = srslte_ue_dl_find_dl_dci_type(q, &dci_msg, cfi, sf_idx, rnti, type);
+    if (rc != 1) return rc < 0 ? rc : 0;               // no DCI for this rnti
+    srslte_ra_dl_dci_t dci_unpacked;
+    srslte_ra_dl_grant_t grant;
+    if (srslte_dci_msg_to_dl_grant(&dci_msg, rnti, q->cell.nof_prb, &dci_unpacked, &grant)) return SRSLTE_ERROR;
+    if (grant.mcs.tbs <= 0) return 0;                  // MCS 29..31: the size belongs to MAC's HARQ entity, not to this wrapper
+    rv = (uint32_t)dci_unpacked.rv_idx;
+    rc = srslte_ue_dl_cfg_grant(q, &grant, cfi, sf_idx, rv);
+  }
   if (rc) return rc;
-  if (u->grant_rv == 0) srslte_softbuffer_rx_reset(&q->softbuffer);
+  if (rv == 0) srslte_softbuffer_rx_reset(&q->softbuffer);
   q->pkts_total++;
   // srslte_ue_dl_decode uses the channel estimator's noise figure (srsUE's worker passes 0.01 instead)
   rc = srslte_pdsch_decode_rnti(&q->pdsch, &q->pdsch_cfg, &q->softbuffer, q->sf_symbols, q->ce,

@@ -80,5 +80,38 @@ def make_grant(nof_prb, qm, tbs, prbs=None):
     return g
 
 
+class RaType0(C.Structure):
+    _fields_ = [("rbg_bitmask", C.c_uint32)]
+
+
+class RaType1(C.Structure):
+    _fields_ = [("vrb_bitmask", C.c_uint32), ("rbg_subset", C.c_uint32), ("shift", C.c_bool)]
+
+
+class RaType2(C.Structure):
+    _fields_ = [("riv", C.c_uint32), ("L_crb", C.c_uint32), ("RB_start", C.c_uint32), ("n_prb1a", C.c_int),
+                ("n_gap", C.c_int), ("mode", C.c_int)]
+
+
+class RaDlDci(C.Structure):
+    _fields_ = [("alloc_type", C.c_int), ("type0_alloc", RaType0), ("type1_alloc", RaType1), ("type2_alloc", RaType2),
+                ("mcs_idx", C.c_uint32), ("harq_process", C.c_uint32), ("rv_idx", C.c_int), ("ndi", C.c_bool),
+                ("dci_is_1a", C.c_bool), ("tpc", C.c_uint32)]
+
+
+def install_tbs_table(L, entries):
+    """Install a SYNTHETIC 27 x 110 transport-block-size table (a smooth byte-aligned stand-in for 36.213 Table
+    7.1.7.2.1-1, which this tree does not carry) with the given {(I_TBS, N_PRB): size} cells overlaid."""
+    import numpy as np
+    t = np.zeros((27, 110), np.int32)
+    for i in range(27):
+        for n in range(1, 111):
+            t[i, n - 1] = 8 * ((n * (16 + 28 * i)) // 8)
+    for (i, n), v in entries.items():
+        t[i, n - 1] = v
+    assert L.srsue_gpu_ra_set_tbs_table(t.ctypes.data_as(C.c_void_p), 27, 110) == 0
+    return t
+
+
 class UeMib(C.Structure):
     _fields_ = [("pbch", C.c_void_p), ("cell", Cell), ("gpu", C.c_void_p)]

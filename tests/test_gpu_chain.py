@@ -124,22 +124,37 @@ def test_srslte_shaped_entry_points(gpu, oracle):
 @pytest.mark.parametrize("prb,ports,fmt", [(25, 1, "1A"), (50, 2, "1"), (100, 1, "1A")])
 def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
     """work_imp's downlink sequence (phch_worker.cc:254-348) with nothing supplied by the caller but the RNTI:
-    decode_fft_estimate -> CFI, pdcch_extract_llr, find_dl_dci_type -> DCI bits + CCE location, then cfg_grant +
-    pdsch_decode_rnti with the grant the test's stand-in for srslte_dci_msg_to_dl_grant derives."""
+    decode_fft_estimate -> CFI, pdcch_extract_llr, find_dl_dci_type -> DCI bits + CCE location, dci_msg_to_dl_grant,
+    then cfg_grant + pdsch_decode_rnti on that grant."""
     import ctypes as C
     sg, ctx = gpu
     o = oracle
     L = sg.lib()
-    from tests.srslte_ctypes import UeDl, Cell, SoftBuffer, DciMsg, make_grant
+    from tests.srslte_ctypes import UeDl, Cell, SoftBuffer, DciMsg, Grant, RaDlDci, install_tbs_table
     qm, tbs, cfi, sf_idx, rnti = 4, 4968 if prb == 25 else 6208, 2, 3, 0x4601
     nb = L.srsue_gpu_host_dci_format_sizeof(0 if fmt == "1A" else 1, prb)
     ocell = o.make_cell(prb, ports, 1)
-    ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs, tm=ports)
+    # the eNodeB side: a real DCI for a partial allocation (1A: localized type 2; 1: a type 0 RBG bitmap), MCS 12
+    sent = RaDlDci()
+    sent.mcs_idx, sent.harq_process, sent.rv_idx, sent.ndi = 12, 5, 0, True
+    if fmt == "1A":
+        sent.alloc_type = 2
+        sent.type2_alloc.RB_start, sent.type2_alloc.L_crb = 2, prb - 5
+        prbs = list(range(2, prb - 3))
+    else:
+        P = L.srslte_ra_type0_P(prb)
+        nbm = -(-prb // P)
+        sent.alloc_type = 0
+        sent.type0_alloc.rbg_bitmask = int("".join("0" if i % 4 == 1 else "1" for i in range(nbm)), 2)
+        prbs = [i for i in range(prb) if (i // P) % 4 != 1]
+    install_tbs_table(L, {(11, len(prbs)): tbs})
+    sent_msg = DciMsg()
+    assert L.srslte_dci_msg_pack_pdsch(C.byref(sent), 2 if fmt == "1A" else 1, C.byref(sent_msg), prb, True) == nb
+    ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs, tm=ports, prbs=prbs)
     rk, _ = o.pdcch_regs(ocell, cfi, 6)
     ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti)
     L0, n0 = ss[-1]                                               # the last (largest) candidate of the UE-specific space
-    dci_bits = np.random.default_rng(prb).integers(0, 2, nb, dtype=np.uint8)
-    dci_bits[0] = 1                                               # format 0 / 1A flag: 1 = format 1A
+    dci_bits = np.frombuffer(sent_msg.data, np.uint8)[:nb].copy()
     other = np.random.default_rng(1).integers(0, 2, nb, dtype=np.uint8)
     dcis = [(dci_bits, rnti, L0, n0)]
     if n0 >= 1:
@@ -192,8 +207,14 @@ def test_phch_worker_sequence_with_pdcch_search(gpu, oracle, prb, ports, fmt):
         assert L.srslte_ue_dl_find_ul_dci(C.byref(q), C.byref(ul), got_cfi.value, sf_idx, rnti) == 1
         assert ul.nof_bits == nb0 and np.array_equal(np.frombuffer(ul.data, np.uint8)[:nb0], ul_bits)
         assert ul_at[1] <= q.last_location.ncce < ul_at[1] + ul_at[0]
-    # grant -> PDSCH
-    grant = make_grant(prb, qm, tbs)
+    # DCI -> grant (phch_worker.cc:297) -> PDSCH
+    grant, unpacked = Grant(), RaDlDci()
+    assert L.srslte_dci_msg_to_dl_grant(C.byref(msg), rnti, prb, C.byref(unpacked), C.byref(grant)) == 0
+    assert (grant.nof_prb, grant.Qm, grant.mcs.tbs) == (len(prbs), qm, tbs)
+    assert [i for i in range(prb) if grant.prb_idx[0][i]] == prbs
+    assert (unpacked.ndi, unpacked.harq_process, unpacked.rv_idx) == (True, 5, 0)
+    L.srslte_ra_dl_dci_string.restype = C.c_char_p
+    assert b"mcs=12 harq_pid=5" in L.srslte_ra_dl_dci_string(C.byref(unpacked))
     assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), got_cfi.value, sf_idx, 0) == 0
     payload = np.zeros(tbs // 8, np.uint8)
     ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), C.c_void_p(q.sf_symbols), q.ce,
@@ -229,6 +250,49 @@ def test_srslte_ue_dl_decode_wrapper_cfg1(gpu, oracle, cfi):
         rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 1, 4)
         assert rc == 0 and n == tbs
         assert np.array_equal(data, pl) and np.array_equal(data, tb)
+    assert q.pkts_total == 3 and q.pkt_errors == 0
+    L.srslte_ue_dl_free(C.byref(q))
+
+
+@pytest.mark.parametrize("prb,rnti", [(25, 0x4601), (6, 0xFFFF)])
+def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
+    """srslte_ue_dl_decode with no grant from the caller: CFI from the PCFICH, blind PDCCH search for the RNTI, DCI ->
+    grant through the installed size table, PDSCH decode.  The SI-RNTI case takes the format 1A N_PRB^1A column."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, DciMsg, RaDlDci, install_tbs_table
+    si = rnti == 0xFFFF
+    cfi, tbs, mcs = (3, 296, 5) if si else (2, 2216, 9)
+    ocell = o.make_cell(prb, 1, 1)
+    q = UeDl()
+    cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)
+    assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+    L.srslte_ue_dl_set_rnti(C.byref(q), rnti)
+    L.srslte_sch_set_max_noi(C.byref(q.pdsch.dl_sch), 4)
+    for tti in (4, 13, 26):
+        sf_idx = tti % 10
+        sent = RaDlDci()
+        sent.alloc_type, sent.mcs_idx, sent.rv_idx = 2, mcs, 0
+        start, ln = (1, 4) if si else (tti % 5, prb - 6)
+        sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
+        install_tbs_table(L, {(mcs, 3 if si else ln): tbs})
+        m = DciMsg()
+        nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), 2, C.byref(m), prb, not si)
+        assert nb > 0
+        rk, _ = o.pdcch_regs(ocell, cfi, 6)
+        ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti) if not si else [(4, 0)]
+        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=2, tbs=tbs, prbs=range(start, start + ln))
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 4000 + tti, 12.0, None, pcfich=True,
+                                   dcis=[(np.frombuffer(m.data, np.uint8)[:nb].copy(), rnti, ss[0][0], ss[0][1])])
+        data = np.zeros(tbs // 8, np.uint8)
+        n = L.srslte_ue_dl_decode(C.byref(q), iq.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti)
+        assert n == tbs and np.array_equal(data, tb)
+        assert q.pdsch_cfg.grant.nof_prb == ln and q.pdsch_cfg.grant.mcs.idx == mcs
+        # a subframe without a DCI for this RNTI decodes nothing
+        _, iq0, _ = o.gen_subframe(ocell, ocfg, 4100 + tti, 12.0, None, pcfich=True)
+        assert L.srslte_ue_dl_decode(C.byref(q), iq0.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti) == 0
     assert q.pkts_total == 3 and q.pkt_errors == 0
     L.srslte_ue_dl_free(C.byref(q))
 
