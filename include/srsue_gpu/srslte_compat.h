@@ -374,6 +374,9 @@ SRSLTE_API uint32_t srslte_tti_interval(uint32_t tti1, uint32_t tti2);          
  * the caller until PDCCH blind decoding lands on the device. */
 SRSLTE_API void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t *q, uint32_t cfi);
 /* cfi 0: use the CFI decoded from the PCFICH of each subframe */
+/* carrier-offset correction of the downlink samples, in subcarrier spacings (the value phch_worker::set_cfo gets at
+ * phch_recv.cc:329); applied inside srslte_ue_dl_decode_fft_estimate from the next subframe on.  0: off. */
+SRSLTE_API int srsue_gpu_ue_dl_set_cfo(srslte_ue_dl_t *q, float cfo);
 SRSLTE_API int srsue_gpu_ue_dl_set_grant(srslte_ue_dl_t *q, const srslte_ra_dl_grant_t *grant, uint32_t cfi, uint32_t rvidx);
 /* copy the device-resident soft buffer into buffer_f (srsLTE decoder-input order) for `tbs` bits */
 SRSLTE_API int srsue_gpu_softbuffer_rx_sync_host(srslte_softbuffer_rx_t *q, uint32_t tbs);

@@ -118,6 +118,13 @@ int srsue_gpu_pdsch_plan_info(const srsue_gpu_pdsch_plan_t *plan, srsue_gpu_plan
 /* d_iq [n_sf][sf_len] -> d_sf_symbols [n_sf][14*nsc] */
 int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_iq, srsue_gpu_cf_t *d_sf_symbols,
                       void *stream);
+/* The same with the carrier-frequency-offset correction srsLTE's synchroniser applies to the samples before the worker
+ * sees them (srslte_cfo_correct inside srslte_ue_sync_zerocopy, ue/src/phy/phch_recv.cc:322), fused into the sample
+ * loads of the transform.  Phase steps come from srsue_gpu_host_cfo_step(cfo in subcarrier spacings, nfft): one per
+ * subframe in d_cfo_steps, or cfo_step for all of them when d_cfo_steps is NULL (0: no rotation). */
+int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_iq, srsue_gpu_cf_t *d_sf_symbols,
+                          const int32_t *d_cfo_steps, int32_t cfo_step, void *stream);
+int srsue_gpu_host_cfo_step(float cfo, int nfft);
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
 int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
                     float *d_meas, void *stream);

@@ -135,6 +135,12 @@ void  lteo_pss_time_n(int n_id_2, int nfft, lteo_cf_t *t);
 float lteo_pss_search_n(const lteo_cf_t *x, int n_samples, int nfft, int force_n_id_2, int first_pos, int *peak_pos, int *n_id_2,
                         float *cfo, float *mean_power);
 int   lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr);
+/* CFO correction (SPEC.md 14): y[n] = x[n] * T[(n * step mod 2^32) >> 20], T = 4096-entry unit circle */
+#define LTEO_CFO_TABLE_LOG2 12
+#define LTEO_CFO_TABLE (1 << LTEO_CFO_TABLE_LOG2)
+void  lteo_cfo_table(lteo_cf_t *tab);
+int32_t lteo_cfo_step(float cfo, int nfft);
+void  lteo_cfo_correct(const lteo_cf_t *in, lteo_cf_t *out, int n_samples, int32_t step);
 /* ---- PBCH / MIB (SPEC.md 12) ---- */
 uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out);
 void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240);

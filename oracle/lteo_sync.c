@@ -177,3 +177,42 @@ int lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, in
   if (corr_out) *corr_out = best;
   return bn;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Carrier-frequency-offset correction (SPEC.md 14).  Follows what srsLTE's subframe synchroniser does to the
+ * samples before handing them to the worker (srslte_cfo_correct inside srslte_ue_sync_zerocopy, called at
+ * /root/reference/ue/src/phy/phch_recv.cc:322; the estimate it uses is reported at :328).  srsLTE is an
+ * un-vendored dependency: parity unpinned, arithmetic frozen here.
+ * ---------------------------------------------------------------------------------------------- */
+#include <pthread.h>
+static lteo_cf_t g_cexp[LTEO_CFO_TABLE];
+static pthread_once_t g_cexp_once = PTHREAD_ONCE_INIT;
+static void cexp_init(void) {
+  for (int j = 0; j < LTEO_CFO_TABLE; j++) {
+    double a = 2.0 * M_PI * (double)j / (double)LTEO_CFO_TABLE;
+    g_cexp[j].re = (float)cos(a);
+    g_cexp[j].im = (float)sin(a);
+  }
+}
+
+void lteo_cfo_table(lteo_cf_t *tab) {
+  pthread_once(&g_cexp_once, cexp_init);
+  memcpy(tab, g_cexp, sizeof(g_cexp));
+}
+
+/* phase step per sample in units of 2^-32 turns: removes an offset of `cfo` subcarrier spacings at nfft samples per symbol */
+int32_t lteo_cfo_step(float cfo, int nfft) {
+  double s = -(double)cfo / (double)nfft * 4294967296.0;
+  return (int32_t)(uint32_t)(uint64_t)llrint(s);
+}
+
+void lteo_cfo_correct(const lteo_cf_t *in, lteo_cf_t *out, int n_samples, int32_t step) {
+  pthread_once(&g_cexp_once, cexp_init);
+  for (int n = 0; n < n_samples; n++) {
+    uint32_t ph = (uint32_t)n * (uint32_t)step;
+    lteo_cf_t w = g_cexp[ph >> (32 - LTEO_CFO_TABLE_LOG2)], x = in[n];
+    float a = x.re * w.re, b = x.im * w.im, c = x.re * w.im, d = x.im * w.re;
+    out[n].re = a - b;
+    out[n].im = c + d;
+  }
+}

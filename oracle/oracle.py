@@ -422,6 +422,24 @@ def pss_search(x, nfft=128, force_n_id_2=-1, first_pos=0):
     return dict(peak=np.float32(peak), pos=pos.value, n_id_2=nid2.value, cfo=np.float32(cfo.value), mean_power=np.float32(mp.value))
 
 
+def cfo_step(cfo, nfft):
+    lib().lteo_cfo_step.restype = C.c_int32
+    return int(lib().lteo_cfo_step(C.c_float(cfo), nfft))
+
+
+def cfo_correct(x, step):
+    x = np.ascontiguousarray(x, np.complex64)
+    y = np.zeros_like(x)
+    lib().lteo_cfo_correct(_p(x), _p(y), len(x), C.c_int32(step))
+    return y
+
+
+def cfo_table():
+    t = np.zeros(4096, np.complex64)
+    lib().lteo_cfo_table(_p(t))
+    return t
+
+
 def sss_detect(x, peak_pos, n_id_2, nfft=128):
     x = np.ascontiguousarray(x, np.complex64)
     sf5 = C.c_int()

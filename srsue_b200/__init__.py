@@ -26,6 +26,11 @@ class PlanInfo(C.Structure):
                                        "sb_cb_stride", "sb_sf_stride", "payload_stride", "max_batch")]
 
 
+def host_cfo_step(cfo, nfft):
+    """Phase step per sample (2^-32 turns) that removes `cfo` subcarrier spacings at nfft samples per symbol."""
+    return int(lib().srsue_gpu_host_cfo_step(C.c_float(cfo), int(nfft)))
+
+
 class SfDesc(C.Structure):
     """srsue_gpu_sf_desc_t (include/srsue_gpu/srsue_gpu.h)"""
     _fields_ = [("cell", Cell), ("cfg", PdschCfg), ("iq", C.c_void_p), ("payload", C.c_void_p),
@@ -154,8 +159,14 @@ class PdschPlan:
             lib().srsue_gpu_pdsch_plan_destroy(self.h)
             self.h = C.c_void_p()
 
-    def ofdm_rx(self, n_sf, d_iq, d_sf):
-        _check(lib().srsue_gpu_ofdm_rx(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _stream()), "ofdm_rx")
+    def ofdm_rx(self, n_sf, d_iq, d_sf, d_cfo_steps=None, cfo_step=0):
+        """OFDM demodulation; with d_cfo_steps (int32 per subframe) or cfo_step (all subframes) the carrier-offset
+        rotation of SPEC.md 14 is applied as the samples are loaded (steps from host_cfo_step)."""
+        if d_cfo_steps is None and cfo_step == 0:
+            _check(lib().srsue_gpu_ofdm_rx(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _stream()), "ofdm_rx")
+        else:
+            _check(lib().srsue_gpu_ofdm_rx_cfo(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _ptr(d_cfo_steps), C.c_int32(cfo_step),
+                                               _stream()), "ofdm_rx_cfo")
 
     def chest(self, n_sf, d_sf, d_ce, d_meas):
         _check(lib().srsue_gpu_chest(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), _stream()), "chest")

@@ -99,6 +99,7 @@ struct srsue_gpu_ctx {
   float2* d_pss_freq = nullptr; int8_t* d_sss = nullptr;
   std::map<int, std::pair<float2*, float2*>> sync_tabs;      // nfft -> (PSS time replicas [3][nfft], nfft/2 twiddles)
   unsigned long long* d_peak_key = nullptr; double* d_power_sum = nullptr; int sync_cap = 0;
+  float2* d_cexp = nullptr;                                  // CFO correction: 4096-entry unit circle (built on first use)
 };
 
 namespace {
@@ -285,7 +286,7 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
   ctx->scratch.release();
   cudaFree(ctx->d_pss_freq); cudaFree(ctx->d_sss);
   for (auto& kv : ctx->sync_tabs) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
-  cudaFree(ctx->d_peak_key); cudaFree(ctx->d_power_sum);
+  cudaFree(ctx->d_peak_key); cudaFree(ctx->d_power_sum); cudaFree(ctx->d_cexp);
   delete ctx;
 }
 
@@ -620,10 +621,27 @@ int srsue_gpu_pdsch_plan_info(const srsue_gpu_pdsch_plan_t* p, srsue_gpu_plan_in
     CU_CHECK(cudaSetDevice((p)->ctx->device));                                                         \
   } while (0)
 
+int srsue_gpu_host_cfo_step(float cfo, int nfft) { return nfft > 0 ? cfo_step(cfo, nfft) : 0; }
+
 int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, srsue_gpu_cf_t* d_sf, void* stream) {
+  return srsue_gpu_ofdm_rx_cfo(p, n_sf, d_iq, d_sf, nullptr, 0, stream);
+}
+
+int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, srsue_gpu_cf_t* d_sf,
+                          const int32_t* d_cfo_steps, int32_t cfo_step_all, void* stream) {
   PLAN_CHECK(p, n_sf);
   if (!d_iq || !d_sf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx: null buffer");
+  const bool rotate = d_cfo_steps != nullptr || cfo_step_all != 0;
   OfdmArgs a{};
+  if (rotate) {
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    if (!p->ctx->d_cexp) {
+      std::vector<float> tab;
+      cfo_table(tab);
+      CU_CHECK(upload(reinterpret_cast<float**>(&p->ctx->d_cexp), tab));
+    }
+    a.cexp = p->ctx->d_cexp; a.cfo_steps = d_cfo_steps; a.cfo_step = cfo_step_all;
+  }
   a.iq = reinterpret_cast<const float2*>(d_iq); a.sf_symbols = reinterpret_cast<float2*>(d_sf);
   a.tw = reinterpret_cast<const float2*>(p->d_tw);
   a.nfft = p->info.nfft; a.nsc = p->info.nsc; a.n_sf = n_sf;
@@ -640,7 +658,10 @@ int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
     // single exchange buffer (8 CTAs per SM) wherever the CTA has exactly N/8 threads; SRSUE_FFT_INPLACE=0 selects the
     // two-buffer kernel for comparison
     static const int inplace = getenv("SRSUE_FFT_INPLACE") ? atoi(getenv("SRSUE_FFT_INPLACE")) : 1;
-    if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
+    if (rotate) {
+      if (b.cfo_steps) b.cfo_steps += done;
+      ofdm_rx_cfo_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+    } else if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
     else ofdm_rx_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
     p->ctx->launch_count++;
   }

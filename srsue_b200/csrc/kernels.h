@@ -48,8 +48,13 @@ struct OfdmArgs {
   int n_sf, nfft, log2n, nsc;
   float scale;
   float c3;                  // (float)(sqrt(3)/2), radix-3 stage of the 1536-point transform
+  // CFO correction fused into the first pass (ofdm_rx_cfo_kernel only; SPEC.md 14)
+  const float2* cexp;        // 4096-entry unit circle
+  const int32_t* cfo_steps;  // [n_sf] phase step per sample, or nullptr: cfo_step for every subframe
+  int32_t cfo_step;
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_cfo_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_inplace_kernel(const OfdmArgs a);
 
 struct ChestArgs {

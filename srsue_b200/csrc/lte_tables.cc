@@ -364,6 +364,21 @@ int pdcch_search_space(int nof_cce, int sf_idx, uint16_t rnti, bool common, int3
   return n;
 }
 
+void cfo_table(std::vector<float>& tab) {
+  const int n = 1 << kCfoTableLog2;
+  tab.resize(2 * (size_t)n);
+  for (int j = 0; j < n; j++) {
+    const double a = 2.0 * 3.14159265358979323846 * (double)j / (double)n;
+    tab[2 * j] = (float)std::cos(a);
+    tab[2 * j + 1] = (float)std::sin(a);
+  }
+}
+
+int32_t cfo_step(float cfo, int nfft) {
+  const double s = -(double)cfo / (double)nfft * 4294967296.0;
+  return (int32_t)(uint32_t)(uint64_t)std::llrint(s);
+}
+
 int dci_format_sizeof(int fmt, int nof_prb) {
   auto ambiguous = [](int n) { return n == 12 || n == 14 || n == 16 || n == 20 || n == 24 || n == 26 || n == 32 || n == 40 || n == 44 || n == 56; };
   int riv = 0;

@@ -109,5 +109,9 @@ int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& ta
 int tcb_offset(const TurboGeom& g, int triple_index);
 
 void fft_twiddles(int n, std::vector<float>& tw /* re,im pairs, n/2 entries */);
+// CFO correction (SPEC.md 14): 4096-entry unit circle and the 2^-32-turn phase step per sample
+constexpr int kCfoTableLog2 = 12;
+void cfo_table(std::vector<float>& tab /* re,im pairs, 4096 entries */);
+int32_t cfo_step(float cfo, int nfft);
 
 }  // namespace srsue

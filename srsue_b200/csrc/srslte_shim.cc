@@ -62,6 +62,7 @@ struct UeDlGpu {
   const void* h_sf = nullptr;       // addresses of those host mirrors
   const void* h_ce[SRSLTE_MAX_PORTS] = {nullptr};
   bool have_grant = false;
+  int32_t cfo_step = 0;             // carrier-offset correction applied while the samples are transformed (0: none)
   uint32_t grant_cfi = 1, grant_rv = 0;
   srslte_ra_dl_grant_t grant{};
   cudaStream_t stream = nullptr;
@@ -193,6 +194,16 @@ void srsue_gpu_ue_dl_set_cfi(srslte_ue_dl_t* q, uint32_t cfi) {
   if (q && q->gpu && cfi <= 3) static_cast<UeDlGpu*>(q->gpu)->cfi = cfi;     // 0: decode the PCFICH (default)
 }
 
+// The downlink half of phch_worker::set_cfo (phch_worker.cc:120, fed from srslte_ue_sync_get_cfo at phch_recv.cc:328-329):
+// srsLTE's synchroniser rotates the samples on the CPU before the worker sees them; here the rotation rides on the
+// sample loads of the FFT.  cfo in subcarrier spacings (what set_cfo receives); 0 switches the correction off.
+int srsue_gpu_ue_dl_set_cfo(srslte_ue_dl_t* q, float cfo) {
+  if (!q || !q->gpu || !(cfo > -1.0f && cfo < 1.0f)) return SRSLTE_ERROR_INVALID_INPUTS;
+  auto* u = static_cast<UeDlGpu*>(q->gpu);
+  u->cfo_step = srsue_gpu_host_cfo_step(cfo, srslte_symbol_sz(q->cell.nof_prb));
+  return SRSLTE_SUCCESS;
+}
+
 int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf_idx, uint32_t* cfi) {
   if (!q || !q->gpu || !input || sf_idx > 9) return SRSLTE_ERROR_INVALID_INPUTS;
   auto* u = static_cast<UeDlGpu*>(q->gpu);
@@ -202,7 +213,7 @@ int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf
   // the IQ buffer is reused by the caller right after we return (phch_worker.cc:254 vs :559,610,641):
   // it is fully consumed (H2D) before the synchronise below
   if (cudaMemcpyAsync(u->d_iq, input, u->sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_ofdm_rx(fp, 1, u->d_iq, u->d_sf, u->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_ofdm_rx_cfo(fp, 1, u->d_iq, u->d_sf, nullptr, u->cfo_step, u->stream)) return SRSLTE_ERROR;
   if (srsue_gpu_chest(fp, 1, u->d_sf, u->d_ce, u->d_meas, u->stream)) return SRSLTE_ERROR;
   float meas[5];
   int32_t cfi_dec = 0;
@@ -833,7 +844,7 @@ int srslte_ue_mib_decode(srslte_ue_mib_t* q, cf_t* input, uint8_t bch_payload[SR
   srsue_gpu_pdsch_plan_t* fp = front_plan(u, 0, 1);
   if (!fp) return SRSLTE_ERROR;
   if (cudaMemcpyAsync(u->d_iq, input, u->sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_ofdm_rx(fp, 1, u->d_iq, u->d_sf, u->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_ofdm_rx_cfo(fp, 1, u->d_iq, u->d_sf, nullptr, u->cfo_step, u->stream)) return SRSLTE_ERROR;
   if (srsue_gpu_chest(fp, 1, u->d_sf, u->d_ce, u->d_meas, u->stream)) return SRSLTE_ERROR;
   if (srsue_gpu_pbch_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, m->d_result, m->d_mib, u->stream)) return SRSLTE_ERROR;
   int32_t res[4];

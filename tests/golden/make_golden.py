@@ -94,5 +94,20 @@ def control():
     print("control: cfi", got_cfi, "corr", corr, "found", f, L1, n1, "sent at", L0, n0)
 
 
+def cfo():
+    """carrier-offset correction (SPEC.md 14): 1.4 MHz subframe of noise, +0.37 and -0.081 subcarrier spacings"""
+    rng = np.random.default_rng(14)
+    x = (rng.standard_normal(1920) + 1j * rng.standard_normal(1920)).astype(np.complex64)
+    steps = np.array([o.cfo_step(0.37, 128), o.cfo_step(-0.081, 128)], np.int32)
+    y = np.stack([o.cfo_correct(x, int(s)) for s in steps])
+    sf = np.stack([o.ofdm_rx(6, v) for v in y])
+    np.savez_compressed(os.path.join(OUT, "cfo.npz"), x=x, steps=steps, y=y, sf=sf, tab=o.cfo_table()[::64])
+    print("cfo: steps", steps)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cfo":
+        cfo()
+    else:
+        main()
+        cfo()

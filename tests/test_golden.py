@@ -83,6 +83,36 @@ def test_oracle_reproduces_control_golden(oracle):
     assert [f, L1, n1] == cv["found"].tolist() and f == 1 and np.array_equal(out, cv["bits"]) and np.array_equal(out, cv["sent"])
 
 
+def test_oracle_reproduces_cfo_golden(oracle):
+    o = oracle
+    v = np.load(os.path.join(G, "cfo.npz"))
+    assert [o.cfo_step(0.37, 128), o.cfo_step(-0.081, 128)] == v["steps"].tolist()
+    assert np.array_equal(o.cfo_table()[::64], v["tab"])
+    for i, st in enumerate(v["steps"]):
+        y = o.cfo_correct(v["x"], int(st))
+        assert np.array_equal(y, v["y"][i]) and np.array_equal(o.ofdm_rx(6, y), v["sf"][i])
+    # independent anchor: the rotation against a double-precision complex exponential (table resolution 2 pi / 4096)
+    n = np.arange(1920)
+    ref = v["x"].astype(np.complex128) * np.exp(-2j * np.pi * 0.37 * n / 128)
+    assert np.max(np.abs(v["y"][0] - ref) / np.abs(v["x"])) < 2 * np.pi / 4096 + 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_cfo_golden(gpu):
+    import torch
+    sg, ctx = gpu
+    v = np.load(os.path.join(G, "cfo.npz"))
+    cell = sg.make_cell(6, 1, 1)
+    plan = sg.PdschPlan(ctx, cell, sg.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152), 2)
+    d_iq = torch.from_numpy(np.stack([v["x"], v["x"]]).view(np.float32)).cuda()
+    d_sf = torch.zeros((2, 14 * 72 * 2), dtype=torch.float32, device="cuda")
+    assert [sg.host_cfo_step(0.37, 128), sg.host_cfo_step(-0.081, 128)] == v["steps"].tolist()
+    plan.ofdm_rx(2, d_iq, d_sf, d_cfo_steps=torch.from_numpy(v["steps"]).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sf.cpu().numpy().view(np.complex64), v["sf"].reshape(2, -1))
+    plan.close()
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_control_golden(gpu):
     import torch

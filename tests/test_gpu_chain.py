@@ -297,6 +297,60 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     L.srslte_ue_dl_free(C.byref(q))
 
 
+@pytest.mark.parametrize("prb,cfo", [(25, 0.12), (75, -0.31)])
+def test_worker_sequence_with_carrier_offset(gpu, oracle, prb, cfo):
+    """phch_worker::set_cfo (phch_worker.cc:120) -> srsue_gpu_ue_dl_set_cfo: a 64QAM subframe received with a carrier
+    offset decodes once the offset is handed to the worker, equals the oracle's rotate-then-transform bit for bit, and
+    is lost without the correction."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import UeDl, Cell, SoftBuffer, make_grant
+    qm, tbs, cfi, sf_idx, rnti = 6, 12960 if prb == 25 else 39232, 2, 4, 0x1234
+    n = o.lib().lteo_symbol_sz(prb)
+    ocell = o.make_cell(prb, 1, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs)
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 77, 30.0)
+    rx = (iq.astype(np.complex128) * np.exp(2j * np.pi * cfo * np.arange(len(iq)) / n)).astype(np.complex64)
+    q = UeDl()
+    cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)
+    assert L.srslte_ue_dl_init(C.byref(q), cell) == 0
+    L.srslte_ue_dl_set_rnti(C.byref(q), rnti)
+    L.srsue_gpu_ue_dl_set_cfi(C.byref(q), cfi)
+    sb = SoftBuffer()
+    assert L.srslte_softbuffer_rx_init(C.byref(sb), prb) == 0
+    grant = make_grant(prb, qm, tbs)
+    nsc = 12 * prb
+
+    def run():
+        got_cfi = C.c_uint32(0)
+        L.srslte_softbuffer_rx_reset(C.byref(sb))
+        assert L.srslte_ue_dl_decode_fft_estimate(C.byref(q), rx.ctypes.data_as(C.c_void_p), sf_idx, C.byref(got_cfi)) == 0
+        sf = np.ctypeslib.as_array(C.cast(q.sf_symbols, C.POINTER(C.c_float)), (14 * nsc * 2,)).view(np.complex64).copy()
+        assert L.srslte_ue_dl_cfg_grant(C.byref(q), C.byref(grant), cfi, sf_idx, 0) == 0
+        payload = np.zeros(tbs // 8, np.uint8)
+        ret = L.srslte_pdsch_decode_rnti(C.byref(q.pdsch), C.byref(q.pdsch_cfg), C.byref(sb), C.c_void_p(q.sf_symbols), q.ce,
+                                         C.c_float(0.01), C.c_uint16(rnti), payload.ctypes.data_as(C.c_void_p))
+        return ret, payload, sf
+
+    ret, payload, sf = run()
+    assert ret != 0 and np.array_equal(sf, o.ofdm_rx(prb, rx))                 # uncorrected: inter-carrier interference
+    assert L.srsue_gpu_ue_dl_set_cfo(C.byref(q), C.c_float(cfo)) == 0
+    ret, payload, sf = run()
+    sf_o = o.ofdm_rx(prb, o.cfo_correct(rx, o.cfo_step(cfo, n)))
+    assert np.array_equal(sf, sf_o)
+    ce_o, _ = o.chest(ocell, sf_idx, sf_o)
+    res_o = o.pdsch_decode(ocell, ocfg, sf_o, ce_o, 0.01, 4)
+    rc_o, pl_o = res_o[0], res_o[1]
+    assert ret == 0 and rc_o == 0 and np.array_equal(payload, tb) and np.array_equal(payload, pl_o)
+    assert L.srsue_gpu_ue_dl_set_cfo(C.byref(q), C.c_float(0.0)) == 0
+    assert run()[0] != 0
+    assert L.srsue_gpu_ue_dl_set_cfo(C.byref(q), C.c_float(1.5)) != 0
+    L.srslte_softbuffer_rx_free(C.byref(sb))
+    L.srslte_ue_dl_free(C.byref(q))
+
+
 def test_cpp_offline_driver_worker_and_batch(gpu, oracle, tmp_path):
     """driver/pdsch_offline.cc: the C++ host side replaying phch_worker's call sequence (mode worker) and the
     batched call (mode batch) must both reproduce the oracle's transport blocks, CRC verdicts and iterations."""

@@ -93,6 +93,39 @@ def test_frontend_stages_match_oracle(gpu, oracle, name):
     plan.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("prb", [6, 15, 25, 50, 75, 100])
+def test_ofdm_rx_with_cfo_correction_matches_oracle(gpu, oracle, prb):
+    """SPEC.md 14: the rotation srsLTE's synchroniser applies to the samples (phch_recv.cc:322), fused into the first
+    FFT pass; per-subframe steps (one of them 0 = identity) and one step for all subframes."""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    n = o.lib().lteo_symbol_sz(prb)
+    rng = np.random.default_rng(prb)
+    n_sf = 4
+    iq = (rng.standard_normal((n_sf, 15 * n)) + 1j * rng.standard_normal((n_sf, 15 * n))).astype(np.complex64)
+    cfos = [0.43, -0.27, 0.0, 0.0031]
+    steps = np.array([sg.host_cfo_step(c, n) for c in cfos], np.int32)
+    assert steps.tolist() == [o.cfo_step(c, n) for c in cfos] and steps[2] == 0
+    cell = sg.make_cell(prb, 1, 1)
+    plan = sg.PdschPlan(ctx, cell, sg.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152), n_sf)
+    d_iq = torch.from_numpy(iq.view(np.float32)).cuda()
+    d_sf = torch.zeros((n_sf, 14 * 12 * prb * 2), dtype=torch.float32, device="cuda")
+    plan.ofdm_rx(n_sf, d_iq, d_sf, d_cfo_steps=torch.from_numpy(steps).cuda())
+    torch.cuda.synchronize()
+    got = d_sf.cpu().numpy().view(np.complex64)
+    for i in range(n_sf):
+        assert np.array_equal(got[i], o.ofdm_rx(prb, o.cfo_correct(iq[i], int(steps[i])))), "subframe %d" % i
+    assert np.array_equal(got[2], o.ofdm_rx(prb, iq[2]))
+    plan.ofdm_rx(n_sf, d_iq, d_sf, cfo_step=int(steps[1]))
+    torch.cuda.synchronize()
+    got = d_sf.cpu().numpy().view(np.complex64)
+    for i in range(n_sf):
+        assert np.array_equal(got[i], o.ofdm_rx(prb, o.cfo_correct(iq[i], int(steps[1]))))
+    plan.close()
+
+
 def test_ofdm_oracle_vs_numpy_fft(oracle):
     """anchor: the oracle's OFDM demodulator against numpy's FFT (runs without a GPU too)"""
     o = oracle
