@@ -125,6 +125,15 @@ int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf
 int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_iq, srsue_gpu_cf_t *d_sf_symbols,
                           const int32_t *d_cfo_steps, int32_t cfo_step, void *stream);
 int srsue_gpu_host_cfo_step(float cfo, int nfft);
+/* int16 {re, im} samples (the radio's wire format, the usual capture-file format; srsLTE converts them to float on the
+ * CPU before its receiver sees them): sample = (float)v * scale, converted as the transform loads them.  Half the bytes
+ * over PCIe and out of HBM.  d_iq16 [n_sf][sf_len][2]. */
+int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_iq16, float scale, srsue_gpu_cf_t *d_sf_symbols,
+                           void *stream);
+/* What the d_iq / h_iq arguments of srsue_gpu_pdsch_decode_batch[_host] point at for this plan: SRSUE_GPU_IQ_CF32 (default)
+ * or SRSUE_GPU_IQ_SC16 with its scale (e.g. 1/32768). */
+enum { SRSUE_GPU_IQ_CF32 = 0, SRSUE_GPU_IQ_SC16 = 1 };
+int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t *plan, int format, float scale);
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
 int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
                     float *d_meas, void *stream);

@@ -168,6 +168,14 @@ class PdschPlan:
             _check(lib().srsue_gpu_ofdm_rx_cfo(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _ptr(d_cfo_steps), C.c_int32(cfo_step),
                                                _stream()), "ofdm_rx_cfo")
 
+    def ofdm_rx_sc16(self, n_sf, d_iq16, scale, d_sf):
+        """OFDM demodulation of int16 {re, im} samples; sample = float(v) * scale."""
+        _check(lib().srsue_gpu_ofdm_rx_sc16(self.h, n_sf, _ptr(d_iq16), C.c_float(scale), _ptr(d_sf), _stream()), "ofdm_rx_sc16")
+
+    def set_iq_format(self, sc16, scale=1.0 / 32768.0):
+        """decode_batch / decode_batch_host take int16 {re, im} samples (sc16=True) or complex64 (False, the default)."""
+        _check(lib().srsue_gpu_pdsch_plan_set_iq_format(self.h, 1 if sc16 else 0, C.c_float(scale)), "set_iq_format")
+
     def chest(self, n_sf, d_sf, d_ce, d_meas):
         _check(lib().srsue_gpu_chest(self.h, n_sf, _ptr(d_sf), _ptr(d_ce), _ptr(d_meas), _stream()), "chest")
 

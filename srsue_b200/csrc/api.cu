@@ -239,6 +239,7 @@ struct srsue_gpu_pdsch_plan {
   uint8_t* d_cb_bits = nullptr; int32_t* d_cb_status = nullptr;
   // staging for the host-pointer call
   float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
+  int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what the d_iq / h_iq arguments of the batch calls point at
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
   Scratch scratch;             // decoder scratch of this plan (plans may run concurrently on different streams)
@@ -623,16 +624,40 @@ int srsue_gpu_pdsch_plan_info(const srsue_gpu_pdsch_plan_t* p, srsue_gpu_plan_in
 
 int srsue_gpu_host_cfo_step(float cfo, int nfft) { return nfft > 0 ? cfo_step(cfo, nfft) : 0; }
 
+static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, const int16_t* d_iq16, float iq16_scale,
+                       srsue_gpu_cf_t* d_sf, const int32_t* d_cfo_steps, int32_t cfo_step_all, void* stream);
+
 int srsue_gpu_ofdm_rx(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, srsue_gpu_cf_t* d_sf, void* stream) {
-  return srsue_gpu_ofdm_rx_cfo(p, n_sf, d_iq, d_sf, nullptr, 0, stream);
+  return ofdm_launch(p, n_sf, d_iq, nullptr, 0.f, d_sf, nullptr, 0, stream);
 }
 
 int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, srsue_gpu_cf_t* d_sf,
                           const int32_t* d_cfo_steps, int32_t cfo_step_all, void* stream) {
+  return ofdm_launch(p, n_sf, d_iq, nullptr, 0.f, d_sf, d_cfo_steps, cfo_step_all, stream);
+}
+
+int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_iq16, float scale, srsue_gpu_cf_t* d_sf, void* stream) {
+  if (!(scale > 0.f)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx_sc16: scale must be positive");
+  return ofdm_launch(p, n_sf, nullptr, d_iq16, scale, d_sf, nullptr, 0, stream);
+}
+
+int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t* p, int format, float scale) {
+  if (!p || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
+  if (p->d_iq && format != p->iq_format) { cudaFree(p->d_iq); p->d_iq = nullptr; cudaFree(p->d_payload); p->d_payload = nullptr;
+                                           cudaFree(p->d_tb_status); p->d_tb_status = nullptr; }
+  p->iq_format = format;
+  if (format == SRSUE_GPU_IQ_SC16) p->iq16_scale = scale;
+  return 0;
+}
+
+static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t* d_iq, const int16_t* d_iq16, float iq16_scale,
+                       srsue_gpu_cf_t* d_sf, const int32_t* d_cfo_steps, int32_t cfo_step_all, void* stream) {
   PLAN_CHECK(p, n_sf);
-  if (!d_iq || !d_sf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx: null buffer");
+  if ((!d_iq && !d_iq16) || !d_sf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx: null buffer");
   const bool rotate = d_cfo_steps != nullptr || cfo_step_all != 0;
   OfdmArgs a{};
+  a.iq16 = reinterpret_cast<const short2*>(d_iq16); a.iq16_scale = iq16_scale;
   if (rotate) {
     std::lock_guard<std::mutex> lk(p->ctx->mu);
     if (!p->ctx->d_cexp) {
@@ -654,11 +679,16 @@ int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
   for (int done = 0; done < n_sf; done += 65535) {
     const int n = std::min(65535, n_sf - done);
     OfdmArgs b = a;
-    b.iq += (size_t)done * 15 * a.nfft; b.sf_symbols += (size_t)done * 14 * a.nsc; b.n_sf = n;
+    if (b.iq) b.iq += (size_t)done * 15 * a.nfft;
+    if (b.iq16) b.iq16 += (size_t)done * 15 * a.nfft;
+    b.sf_symbols += (size_t)done * 14 * a.nsc; b.n_sf = n;
     // single exchange buffer (8 CTAs per SM) wherever the CTA has exactly N/8 threads; SRSUE_FFT_INPLACE=0 selects the
     // two-buffer kernel for comparison
     static const int inplace = getenv("SRSUE_FFT_INPLACE") ? atoi(getenv("SRSUE_FFT_INPLACE")) : 1;
-    if (rotate) {
+    if (b.iq16) {
+      if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_iq16_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
+      else ofdm_rx_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+    } else if (rotate) {
       if (b.cfo_steps) b.cfo_steps += done;
       ofdm_rx_cfo_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
     } else if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
@@ -1000,7 +1030,9 @@ int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsu
   p->ctx->launch_count = 0;
   float* meas = d_meas ? d_meas : p->d_meas;
   int16_t* sb = d_softbuf ? d_softbuf : p->d_sb;
-  int rc = srsue_gpu_ofdm_rx(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream);
+  int rc = p->iq_format == SRSUE_GPU_IQ_SC16
+               ? srsue_gpu_ofdm_rx_sc16(p, n_sf, reinterpret_cast<const int16_t*>(d_iq), p->iq16_scale, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream)
+               : srsue_gpu_ofdm_rx(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream);
   // (the fused variant srsue_gpu_chest_pilots + srsue_gpu_pdsch_llr_fused moves 250 KB less per subframe but was
   // measured SLOWER on B200, 1.25 ms vs 1.08 ms per 4096 subframes: the demapper is issue-bound, not HBM-bound)
   if (!rc) rc = srsue_gpu_chest(p, n_sf, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), reinterpret_cast<srsue_gpu_cf_t*>(p->d_ce), meas, stream);
@@ -1015,8 +1047,9 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t* p, int n_sf, const
   PLAN_CHECK(p, n_sf);
   if (!h_iq || !h_payload || !h_tb_status) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "decode_batch_host: null buffer");
   const size_t B = (size_t)p->info.max_batch;
+  const size_t esz = p->iq_format == SRSUE_GPU_IQ_SC16 ? sizeof(short2) : sizeof(float2);     // bytes per sample of h_iq
   if (!p->d_iq) {
-    CU_CHECK(cudaMalloc((void**)&p->d_iq, B * p->info.sf_len * sizeof(float2)));
+    CU_CHECK(cudaMalloc((void**)&p->d_iq, B * p->info.sf_len * esz));
     CU_CHECK(cudaMalloc((void**)&p->d_payload, B * p->info.payload_stride));
     CU_CHECK(cudaMalloc((void**)&p->d_tb_status, B * 4 * sizeof(int32_t)));
   }
@@ -1032,15 +1065,16 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t* p, int n_sf, const
   int n_ch = 0;
   for (int off = 0; off < n_sf; off += chunk, n_ch++) {
     const int n = std::min(chunk, n_sf - off);
-    CU_CHECK(cudaMemcpyAsync(p->d_iq + (size_t)off * p->info.sf_len, reinterpret_cast<const float2*>(h_iq) + (size_t)off * p->info.sf_len,
-                             (size_t)n * p->info.sf_len * sizeof(float2), cudaMemcpyHostToDevice, sx));
+    CU_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(p->d_iq) + (size_t)off * p->info.sf_len * esz,
+                             reinterpret_cast<const char*>(h_iq) + (size_t)off * p->info.sf_len * esz,
+                             (size_t)n * p->info.sf_len * esz, cudaMemcpyHostToDevice, sx));
     CU_CHECK(cudaEventRecord(p->ev[n_ch], sx));
   }
   n_ch = 0;
   for (int off = 0; off < n_sf; off += chunk, n_ch++) {
     const int n = std::min(chunk, n_sf - off);
     CU_CHECK(cudaStreamWaitEvent(sc, p->ev[n_ch], 0));
-    int rc = srsue_gpu_pdsch_decode_batch(p, n, reinterpret_cast<srsue_gpu_cf_t*>(p->d_iq + (size_t)off * p->info.sf_len), noise_est,
+    int rc = srsue_gpu_pdsch_decode_batch(p, n, reinterpret_cast<srsue_gpu_cf_t*>(reinterpret_cast<char*>(p->d_iq) + (size_t)off * p->info.sf_len * esz), noise_est,
                                           noise_mode, max_iter, 0, nullptr, p->d_payload + (size_t)off * p->info.payload_stride,
                                           p->d_tb_status + (size_t)off * 4, p->d_meas + (size_t)off * 5, sc);
     if (rc) return rc;

@@ -52,9 +52,14 @@ struct OfdmArgs {
   const float2* cexp;        // 4096-entry unit circle
   const int32_t* cfo_steps;  // [n_sf] phase step per sample, or nullptr: cfo_step for every subframe
   int32_t cfo_step;
+  // int16 {re, im} input (ofdm_rx_*iq16_kernel only): sample = (float)v * iq16_scale
+  const short2* iq16;
+  float iq16_scale;
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_cfo_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_inplace_iq16_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_iq16_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_inplace_kernel(const OfdmArgs a);
 
 struct ChestArgs {

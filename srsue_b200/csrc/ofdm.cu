@@ -134,18 +134,26 @@ __host__ __device__ constexpr int reg_of_u(int u) {
 //              (np >> 4 is 0 when nsub < 16; for nsub >= 16 nsub r is a multiple of 16)
 //   N/L <  16: np + nsub r < N/L, k (N/L) multiple of N/L -> (idx_r >> 4) = (k (N/L)) >> 4
 // CFO: the first pass rotates sample i of the symbol by T[((rot_n0 + i) * rot_step) >> 20] as it loads it (SPEC.md 14)
-template <int N, int L, int LOGR, bool FIRST, bool LAST, bool SYNC_RW = false, bool CFO = false>
+// IQ16: gsrc points at int16 {re, im} pairs (the radio's wire format); a sample is (float)v * iq16_scale, rounded once
+template <int N, int L, int LOGR, bool FIRST, bool LAST, bool SYNC_RW = false, bool CFO = false, bool IQ16 = false>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const float2* ssrc, float2* sdst,
                                          float2* __restrict__ gdst, const float2* __restrict__ tw, int tid, int nthreads,
                                          int nsc, float scale, int in_stride = 1, uint32_t rot_n0 = 0, uint32_t rot_step = 0,
-                                         const float2* __restrict__ rot_tab = nullptr) {
+                                         const float2* __restrict__ rot_tab = nullptr, float iq16_scale = 0.f) {
   constexpr int R = 1 << LOGR, nsub = N / (L * R), NL = N / L;
   for (int b = tid; b < N / R; b += nthreads) {
     const int k = b / nsub, np = b % nsub;          // powers of two: shift and mask
     float2 v[8];
     if (FIRST) {
 #pragma unroll
-      for (int r = 0; r < R; r++) v[r] = __ldg(gsrc + (np + nsub * r) * in_stride);       // L == 1, so k == 0
+      for (int r = 0; r < R; r++) {                                                        // L == 1, so k == 0
+        if (IQ16) {
+          const short2 q = __ldg(reinterpret_cast<const short2*>(gsrc) + (np + nsub * r) * in_stride);
+          v[r] = make_float2(__fmul_rn((float)q.x, iq16_scale), __fmul_rn((float)q.y, iq16_scale));
+        } else {
+          v[r] = __ldg(gsrc + (np + nsub * r) * in_stride);
+        }
+      }
       if (CFO) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -185,14 +193,15 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ gsrc, const 
 
 // all passes of one N-point transform: radix 8 while it fits, then one radix-4 or radix-2 pass.  Two shared
 // buffers (ping-pong) avoid the read/write hazard of an in-place exchange, so each pass needs a single barrier.
-template <int LOG2N, bool CFO = false>
+template <int LOG2N, bool CFO = false, bool IQ16 = false>
 __device__ __forceinline__ void fft_symbol(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s0,
                                            float2* s1, const float2* __restrict__ tw, int nsc, float scale,
-                                           uint32_t rot_n0 = 0, uint32_t rot_step = 0, const float2* __restrict__ rot_tab = nullptr) {
+                                           uint32_t rot_n0 = 0, uint32_t rot_step = 0, const float2* __restrict__ rot_tab = nullptr,
+                                           float iq16_scale = 0.f) {
   constexpr int N = 1 << LOG2N;
   static_assert(LOG2N >= 7 && LOG2N <= 11, "LTE transform sizes 128..2048");
   const int tid = threadIdx.x, nt = blockDim.x;
-  fft_pass<N, 1, 3, true, false, false, CFO>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale, 1, rot_n0, rot_step, rot_tab);
+  fft_pass<N, 1, 3, true, false, false, CFO, IQ16>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale, 1, rot_n0, rot_step, rot_tab, iq16_scale);
   __syncthreads();
   fft_pass<N, 8, 3, false, false>(nullptr, s0, s1, nullptr, tw, tid, nt, nsc, scale);
   __syncthreads();
@@ -215,16 +224,20 @@ __device__ __forceinline__ void fft_symbol(const float2* __restrict__ gin, float
 // stage with the full-circle twiddles w1 = w_1536^k, w2 = w_1536^2k from the table:
 //   t1 = w1 f1, t2 = w2 f2, s = t1 + t2, d = t1 - t2, X[k] = f0 + s, m = f0 - s/2,
 //   X[k + 512] = m - i c3 d, X[k + 1024] = m + i c3 d, c3 = (float)(sqrt(3)/2), every operation rounded once.
-template <bool CFO = false>
+template <bool CFO = false, bool IQ16 = false>
 __device__ __forceinline__ void fft1536_symbol(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s_fft,
                                                const float2* __restrict__ tw, int nsc, float scale, float c3,
-                                               uint32_t rot_n0 = 0, uint32_t rot_step = 0, const float2* __restrict__ rot_tab = nullptr) {
+                                               uint32_t rot_n0 = 0, uint32_t rot_step = 0, const float2* __restrict__ rot_tab = nullptr,
+                                               float iq16_scale = 0.f) {
   constexpr int M = 512, SUB = M + M / 16 + 8, N = 1536;
   const int tid = threadIdx.x, r = tid / 64, lt = tid - r * 64;
   if (r < 3) {
     float2* s0 = s_fft + r * SUB;
     float2* s1 = s_fft + (3 + r) * SUB;
-    fft_pass<M, 1, 3, true, false, false, CFO>(gin + r, nullptr, s0, nullptr, tw, lt, 64, nsc, scale, 3, rot_n0 + r, rot_step, rot_tab);
+    // (IQ16: gin is already the int16-pair address of sample 0, so + r is applied in the element type of the source)
+    fft_pass<M, 1, 3, true, false, false, CFO, IQ16>(
+        IQ16 ? reinterpret_cast<const float2*>(reinterpret_cast<const short2*>(gin) + r) : gin + r, nullptr, s0, nullptr, tw, lt, 64, nsc,
+        scale, 3, rot_n0 + r, rot_step, rot_tab, iq16_scale);
     __syncthreads();
     fft_pass<M, 8, 3, false, false>(nullptr, s0, s1, nullptr, tw, lt, 64, nsc, scale);
     __syncthreads();
@@ -264,12 +277,12 @@ __device__ __forceinline__ void fft1536_symbol(const float2* __restrict__ gin, f
 // between the reads and the writes of a pass.  Half the shared memory per CTA and 32 registers per thread give 8 CTAs =
 // 64 warps per SM instead of 48; the kernel is latency-bound (the first butterflies wait for DRAM, the twiddle loads for
 // L1), so the extra warps buy more than the two extra barriers cost: 0.414 -> 0.385 ms per 4096 subframes at N = 2048.
-template <int LOG2N>
+template <int LOG2N, bool IQ16 = false>
 __device__ __forceinline__ void fft_symbol_inplace(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s0,
-                                                   const float2* __restrict__ tw, int nsc, float scale) {
+                                                   const float2* __restrict__ tw, int nsc, float scale, float iq16_scale = 0.f) {
   constexpr int N = 1 << LOG2N;
   const int tid = threadIdx.x, nt = blockDim.x;
-  fft_pass<N, 1, 3, true, false>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale);
+  fft_pass<N, 1, 3, true, false, false, false, IQ16>(gin, nullptr, s0, nullptr, tw, tid, nt, nsc, scale, 1, 0, 0, nullptr, iq16_scale);
   __syncthreads();
   fft_pass<N, 8, 3, false, false, true>(nullptr, s0, s0, nullptr, tw, tid, nt, nsc, scale);
   __syncthreads();
@@ -322,6 +335,48 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
     case 9: fft_symbol<9>(gin, gout, s0, s1, a.tw, a.nsc, a.scale); break;
     case 10: fft_symbol<10>(gin, gout, s0, s1, a.tw, a.nsc, a.scale); break;
     case 11: fft_symbol<11>(gin, gout, s0, s1, a.tw, a.nsc, a.scale); break;
+    default: break;
+  }
+}
+
+// int16 {re, im} input (what the radio puts on the wire and what capture files usually hold): half the bytes over PCIe
+// and out of HBM; the conversion (float)v * scale rides on the loads of the first pass.
+__global__ void __launch_bounds__(256, 7) ofdm_rx_inplace_iq16_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  const int N = a.nfft;
+  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
+  float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
+  switch (a.log2n) {
+    case 8: fft_symbol_inplace<8, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.iq16_scale); break;
+    case 9: fft_symbol_inplace<9, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.iq16_scale); break;
+    case 10: fft_symbol_inplace<10, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.iq16_scale); break;
+    case 11: fft_symbol_inplace<11, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.iq16_scale); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(256) ofdm_rx_iq16_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  const int N = a.nfft;
+  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
+  float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
+  float2* s0 = s_fft;
+  float2* s1 = s_fft + (N + N / 16 + 8);
+  if (N == 1536) { fft1536_symbol<false, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.c3, 0, 0, nullptr, a.iq16_scale); return; }
+  switch (a.log2n) {
+    case 7: fft_symbol<7, false, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, 0, 0, nullptr, a.iq16_scale); break;
+    case 8: fft_symbol<8, false, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, 0, 0, nullptr, a.iq16_scale); break;
+    case 9: fft_symbol<9, false, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, 0, 0, nullptr, a.iq16_scale); break;
+    case 10: fft_symbol<10, false, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, 0, 0, nullptr, a.iq16_scale); break;
+    case 11: fft_symbol<11, false, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, 0, 0, nullptr, a.iq16_scale); break;
     default: break;
   }
 }

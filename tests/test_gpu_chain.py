@@ -351,6 +351,44 @@ def test_worker_sequence_with_carrier_offset(gpu, oracle, prb, cfo):
     L.srslte_ue_dl_free(C.byref(q))
 
 
+@pytest.mark.parametrize("prb,ports,qm,tbs", [(100, 1, 6, 75376), (25, 2, 4, 6200)])
+def test_batch_host_sc16_input(gpu, oracle, prb, ports, qm, tbs):
+    """srsue_gpu_pdsch_plan_set_iq_format(SC16): the batched host call fed with int16 captures gives exactly what the
+    oracle gives on the same samples converted to float first (srsLTE's order), and switching back to cf32 works."""
+    sg, ctx = gpu
+    o = oracle
+    n = 6
+    ocell = o.make_cell(prb, ports, 1)
+    ocfg = o.make_cfg(ocell, sf_idx=2, cfi=1, qm=qm, tbs=tbs, tm=ports)
+    cell = sg.make_cell(prb, ports, 1)
+    cfg = sg.make_cfg(cell, sf_idx=2, cfi=1, qm=qm, tbs=tbs, tm=ports)
+    sent, iqs = [], []
+    for i in range(n):
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 9100 + i, 30.0)
+        sent.append(tb); iqs.append(iq)
+    iq = np.stack(iqs)
+    peak = float(np.abs(iq.view(np.float32)).max())
+    scale = np.float32(peak / 32000.0)
+    q16 = np.rint(iq.view(np.float32) / scale).astype(np.int16)                      # the capture: (n, sf_len * 2) int16
+    xf = (q16.astype(np.float32) * scale).view(np.complex64)
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    plan.set_iq_format(True, float(scale))
+    h_pl = np.zeros((n, plan.info.payload_stride), np.uint8)
+    h_st = np.zeros((n, 4), np.int32)
+    h_meas = np.zeros((n, 5), np.float32)
+    plan.decode_batch_host(n, q16, 0.01, 1, 4, h_pl, h_st, h_meas)
+    for i in range(n):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, xf[i], 0.01, 1, 4)
+        assert rc == 0 and h_st[i, 0] == 1
+        assert np.array_equal(h_pl[i, :tbs // 8], pl) and np.array_equal(pl, sent[i])
+        assert np.allclose(h_meas[i], meas, rtol=1e-4)
+    plan.set_iq_format(False)
+    h_pl[:] = 0
+    plan.decode_batch_host(n, iq, 0.01, 1, 4, h_pl, h_st, h_meas)
+    assert all(np.array_equal(h_pl[i, :tbs // 8], sent[i]) for i in range(n))
+    plan.close()
+
+
 def test_cpp_offline_driver_worker_and_batch(gpu, oracle, tmp_path):
     """driver/pdsch_offline.cc: the C++ host side replaying phch_worker's call sequence (mode worker) and the
     batched call (mode batch) must both reproduce the oracle's transport blocks, CRC verdicts and iterations."""

@@ -126,6 +126,30 @@ def test_ofdm_rx_with_cfo_correction_matches_oracle(gpu, oracle, prb):
     plan.close()
 
 
+@pytest.mark.parametrize("prb", [6, 15, 25, 50, 75, 100])
+def test_ofdm_rx_sc16_matches_oracle(gpu, oracle, prb):
+    """int16 samples (the radio's wire format): the conversion float(v) * scale on the FFT's loads equals converting first"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    n = o.lib().lteo_symbol_sz(prb)
+    rng = np.random.default_rng(200 + prb)
+    n_sf = 3
+    q = rng.integers(-32768, 32768, (n_sf, 15 * n, 2), dtype=np.int16)
+    q[0, :4] = [[-32768, 32767], [0, 0], [1, -1], [32767, -32768]]
+    cell = sg.make_cell(prb, 1, 1)
+    plan = sg.PdschPlan(ctx, cell, sg.make_cfg(cell, sf_idx=1, cfi=1, qm=2, tbs=152), n_sf)
+    d_sf = torch.zeros((n_sf, 14 * 12 * prb * 2), dtype=torch.float32, device="cuda")
+    for scale in (1.0 / 32768.0, 3.1e-4):
+        x = (q.astype(np.float32) * np.float32(scale)).view(np.complex64).reshape(n_sf, -1)
+        plan.ofdm_rx_sc16(n_sf, torch.from_numpy(q).cuda(), scale, d_sf)
+        torch.cuda.synchronize()
+        got = d_sf.cpu().numpy().view(np.complex64)
+        for i in range(n_sf):
+            assert np.array_equal(got[i], o.ofdm_rx(prb, x[i])), "subframe %d scale %g" % (i, scale)
+    plan.close()
+
+
 def test_ofdm_oracle_vs_numpy_fft(oracle):
     """anchor: the oracle's OFDM demodulator against numpy's FFT (runs without a GPU too)"""
     o = oracle
