@@ -226,6 +226,20 @@ SRSLTE_API uint32_t srslte_ra_type0_P(uint32_t nof_prb);
 SRSLTE_API uint32_t srslte_ra_type2_n_rb(uint32_t nof_prb);
 SRSLTE_API uint32_t srslte_ra_type2_to_riv(uint32_t L_crb, uint32_t RB_start, uint32_t nof_prb);
 SRSLTE_API void srslte_ra_type2_from_riv(uint32_t riv, uint32_t *L_crb, uint32_t *RB_start, uint32_t nof_prb, uint32_t nof_vrb);
+/* CQI reporting (phch_worker.cc:504-527): chest SNR -> CQI index, report timing, UCI bit packing */
+typedef enum { SRSLTE_CQI_TYPE_WIDEBAND = 0, SRSLTE_CQI_TYPE_SUBBAND } srslte_cqi_type_t;
+typedef struct SRSLTE_API { uint8_t wideband_cqi; } srslte_cqi_wideband_t;
+typedef struct SRSLTE_API { uint8_t subband_cqi; uint8_t subband_label; } srslte_cqi_subband_t;
+typedef struct SRSLTE_API {
+  srslte_cqi_type_t type;
+  srslte_cqi_wideband_t wideband;
+  srslte_cqi_subband_t subband;
+} srslte_cqi_value_t;
+#define SRSLTE_CQI_MAX_BITS 64
+SRSLTE_API uint8_t srslte_cqi_from_snr(float snr_db);
+SRSLTE_API bool srslte_cqi_send(uint32_t I_cqi_pmi, uint32_t tti);
+SRSLTE_API int srslte_cqi_value_pack(srslte_cqi_value_t *value, uint8_t *buff);
+#define SRSLTE_VEC_EMA(data, average, alpha) ((alpha) * (data) + (1 - (alpha)) * (average))     /* phch_worker.cc:512 */
 SRSLTE_API char *srslte_ra_dl_dci_string(srslte_ra_dl_dci_t *dci);                       /* phch_worker.cc:317 */
 SRSLTE_API int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti);
 SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);

@@ -239,6 +239,41 @@ int srslte_dci_msg_pack_pdsch(srslte_ra_dl_dci_t* d, srslte_dci_format_t format,
   return nbits;
 }
 
+// ---- CQI reporting helpers (phch_worker.cc:504-527) ------------------------------------------------------------------
+// Wideband CQI from the channel estimator's SNR in dB: a ladder of about 2 dB per CQI step from -6.5 dB (CQI 1, QPSK
+// rate 0.08) to 21 dB (CQI 15, 64QAM rate 0.93), the usual AWGN spacing of the 36.213 Table 7.2.3-1 efficiencies.  Not
+// calibrated against this receiver's BLER curves; srsLTE's own table lives in its un-vendored lib/phch/cqi.c and may
+// differ by a fraction of a dB per step.
+uint8_t srslte_cqi_from_snr(float snr_db) {
+  static const float thr[15] = {-6.5f, -4.5f, -2.5f, -0.5f, 1.5f, 3.5f, 5.5f, 7.5f, 9.5f, 11.5f, 13.5f, 15.0f, 17.0f, 19.0f, 21.0f};
+  uint8_t cqi = 0;
+  for (int i = 0; i < 15; i++) if (snr_db >= thr[i]) cqi = (uint8_t)(i + 1);
+  return cqi;
+}
+
+// 36.213 Table 7.2.2-1A (FDD): does a periodic CQI/PMI report with configuration index I_cqi_pmi fall on this tti?
+bool srslte_cqi_send(uint32_t I_cqi_pmi, uint32_t tti) {
+  static const struct { uint32_t first, last, period; } row[] = {
+      {0, 1, 2}, {2, 6, 5}, {7, 16, 10}, {17, 36, 20}, {37, 76, 40}, {77, 156, 80}, {157, 316, 160},
+      {318, 349, 32}, {350, 413, 64}, {414, 541, 128}};
+  for (const auto& r : row)
+    if (I_cqi_pmi >= r.first && I_cqi_pmi <= r.last) return (tti + r.period - (I_cqi_pmi - r.first) % r.period) % r.period == 0;
+  return false;                                                            // 317 and 542..1023 are reserved
+}
+
+// wideband: 4 bits; UE-selected subband (PUCCH format 2, one bandwidth part): 4 bits + 1 label bit.  MSB first.
+int srslte_cqi_value_pack(srslte_cqi_value_t* value, uint8_t* buff) {
+  if (!value || !buff) return SRSLTE_ERROR_INVALID_INPUTS;
+  uint8_t* y = buff;
+  auto put = [&](uint32_t v, int n) { for (int i = n - 1; i >= 0; i--) *y++ = (uint8_t)((v >> i) & 1u); };
+  switch (value->type) {
+    case SRSLTE_CQI_TYPE_WIDEBAND: put(value->wideband.wideband_cqi, 4); break;
+    case SRSLTE_CQI_TYPE_SUBBAND: put(value->subband.subband_cqi, 4); put(value->subband.subband_label, 1); break;
+    default: return SRSLTE_ERROR;
+  }
+  return (int)(y - buff);
+}
+
 char* srslte_ra_dl_dci_string(srslte_ra_dl_dci_t* d) {
   static thread_local char s[160];
   if (!d) { s[0] = 0; return s; }

@@ -150,3 +150,25 @@ def test_no_table_fails_loudly():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "no transport-block-size table installed" in r.stderr
+
+
+def test_cqi_helpers(L):
+    """phch_worker.cc:504-527: CQI index from the estimator's SNR, report timing (36.213 Table 7.2.2-1A), UCI bits"""
+    L.srslte_cqi_from_snr.restype = C.c_uint8
+    L.srslte_cqi_send.restype = C.c_bool
+    cq = [L.srslte_cqi_from_snr(C.c_float(s)) for s in np.arange(-10, 30, 0.25)]
+    assert cq[0] == 0 and cq[-1] == 15 and all(b - a in (0, 1) for a, b in zip(cq, cq[1:])) and set(cq) == set(range(16))
+    for idx, period, off in ((0, 2, 0), (1, 2, 1), (2, 5, 0), (6, 5, 4), (7, 10, 0), (16, 10, 9), (17, 20, 0), (36, 20, 19),
+                             (37, 40, 0), (76, 40, 39), (77, 80, 0), (157, 160, 0), (316, 160, 159), (318, 32, 0), (349, 32, 31),
+                             (350, 64, 0), (414, 128, 0), (541, 128, 127)):
+        hits = [t for t in range(10240) if L.srslte_cqi_send(idx, t)]
+        assert hits == list(range(off, 10240, period)), idx
+    assert not any(L.srslte_cqi_send(i, t) for i in (317, 542, 1023) for t in range(200))
+
+    class Cqi(C.Structure):
+        _fields_ = [("type", C.c_int), ("wideband_cqi", C.c_uint8), ("subband_cqi", C.c_uint8), ("subband_label", C.c_uint8)]
+    buf = (C.c_uint8 * 64)()
+    v = Cqi(0, 11, 0, 0)
+    assert L.srslte_cqi_value_pack(C.byref(v), buf) == 4 and list(buf[:4]) == [1, 0, 1, 1]
+    v = Cqi(1, 0, 6, 1)
+    assert L.srslte_cqi_value_pack(C.byref(v), buf) == 5 and list(buf[:5]) == [0, 1, 1, 0, 1]
