@@ -132,6 +132,9 @@ int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t
                            void *stream);
 /* What the d_iq / h_iq arguments of srsue_gpu_pdsch_decode_batch[_host] point at for this plan: SRSUE_GPU_IQ_CF32 (default)
  * or SRSUE_GPU_IQ_SC16 with its scale (e.g. 1/32768). */
+/* carrier-offset correction for the batch calls of this plan (cf32 input): per-subframe steps on the device (row i of the
+ * next srsue_gpu_pdsch_decode_batch call), or one step for all subframes when d_cfo_steps is NULL; (NULL, 0) switches it off */
+int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t *plan, const int32_t *d_cfo_steps, int32_t cfo_step);
 enum { SRSUE_GPU_IQ_CF32 = 0, SRSUE_GPU_IQ_SC16 = 1 };
 int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t *plan, int format, float scale);
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
@@ -220,6 +223,8 @@ typedef struct {
   int32_t crc_ok;                  /* out: 1 when the transport-block CRC passed (ack) */
   int32_t n_iter;                  /* out: srslte_pdsch_last_noi() of this subframe */
   float meas[5];                   /* out: noise, rsrp, rssi, rsrq, snr of this subframe */
+  float cfo;                       /* in:  carrier offset of this capture in subcarrier spacings (|cfo| < 1), removed while the
+                                    * samples are transformed (oracle/SPEC.md 14); 0: none */
 } srsue_gpu_sf_desc_t;
 
 /* max_subframes bounds one submission.  noise_est / noise_mode / max_iter as in srsue_gpu_pdsch_decode_batch. */

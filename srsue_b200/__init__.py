@@ -35,7 +35,7 @@ class SfDesc(C.Structure):
     """srsue_gpu_sf_desc_t (include/srsue_gpu/srsue_gpu.h)"""
     _fields_ = [("cell", Cell), ("cfg", PdschCfg), ("iq", C.c_void_p), ("payload", C.c_void_p),
                 ("softbuffer_id", C.c_int64), ("new_data", C.c_int32), ("crc_ok", C.c_int32), ("n_iter", C.c_int32),
-                ("meas", C.c_float * 5)]
+                ("meas", C.c_float * 5), ("cfo", C.c_float)]
 
 
 class SyncResult(C.Structure):
@@ -248,7 +248,7 @@ class Batch:
     @staticmethod
     def prepare(items):
         """items: list of dicts {cell, cfg, iq (complex64 array), softbuffer_id (default -1), new_data (default 1),
-        payload (optional uint8 array)} -> (descriptor array, payload arrays, items), reusable across submissions"""
+        payload (optional uint8 array), cfo (subcarrier spacings, default 0)} -> (descriptor array, payload arrays, items), reusable across submissions"""
         import numpy as np
         n = len(items)
         descs = (SfDesc * n)()
@@ -262,6 +262,7 @@ class Batch:
             d.iq, d.payload = it["iq"].ctypes.data, pl.ctypes.data
             d.softbuffer_id = it.get("softbuffer_id", -1)
             d.new_data = it.get("new_data", 1)
+            d.cfo = it.get("cfo", 0.0)
         return descs, payloads, items
 
     def submit_prepared(self, prepared):

@@ -239,6 +239,7 @@ struct srsue_gpu_pdsch_plan {
   uint8_t* d_cb_bits = nullptr; int32_t* d_cb_status = nullptr;
   // staging for the host-pointer call
   float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
+  const int32_t* cfo_steps = nullptr; int32_t cfo_step_all = 0;            // carrier-offset correction of the batch calls (cf32 input)
   int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what the d_iq / h_iq arguments of the batch calls point at
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
@@ -641,6 +642,12 @@ int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d
   return ofdm_launch(p, n_sf, nullptr, d_iq16, scale, d_sf, nullptr, 0, stream);
 }
 
+int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t* p, const int32_t* d_cfo_steps, int32_t cfo_step) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  p->cfo_steps = d_cfo_steps; p->cfo_step_all = cfo_step;
+  return 0;
+}
+
 int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t* p, int format, float scale) {
   if (!p || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
@@ -1032,7 +1039,7 @@ int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsu
   int16_t* sb = d_softbuf ? d_softbuf : p->d_sb;
   int rc = p->iq_format == SRSUE_GPU_IQ_SC16
                ? srsue_gpu_ofdm_rx_sc16(p, n_sf, reinterpret_cast<const int16_t*>(d_iq), p->iq16_scale, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream)
-               : srsue_gpu_ofdm_rx(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream);
+               : srsue_gpu_ofdm_rx_cfo(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), p->cfo_steps, p->cfo_step_all, stream);
   // (the fused variant srsue_gpu_chest_pilots + srsue_gpu_pdsch_llr_fused moves 250 KB less per subframe but was
   // measured SLOWER on B200, 1.25 ms vs 1.08 ms per 4096 subframes: the demapper is issue-bound, not HBM-bound)
   if (!rc) rc = srsue_gpu_chest(p, n_sf, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), reinterpret_cast<srsue_gpu_cf_t*>(p->d_ce), meas, stream);

@@ -96,6 +96,7 @@ struct srsue_gpu_batch {
   int32_t* d_status = nullptr; float* d_meas = nullptr;
   int16_t* d_sb = nullptr; size_t sb_elems = 0;
   int16_t** d_rows = nullptr;
+  int32_t *h_cfo = nullptr, *d_cfo = nullptr;      // per-row carrier-offset phase steps of the chunk being launched
   // pinned result staging, in processing order
   int32_t* h_status = nullptr; float* h_meas = nullptr; int16_t** h_rows = nullptr;
   const void** h_iq_rows = nullptr; void** h_pl_rows = nullptr;    // pinned pointer tables read by the zero-copy kernels
@@ -194,6 +195,8 @@ int srsue_gpu_batch_create(srsue_gpu_ctx_t* ctx, int max_subframes, float noise_
   B_CU(cudaMalloc((void**)&b->d_status, (size_t)b->chunk_cap * 4 * sizeof(int32_t)));
   B_CU(cudaMalloc((void**)&b->d_meas, (size_t)b->chunk_cap * 5 * sizeof(float)));
   B_CU(cudaMalloc((void**)&b->d_rows, (size_t)b->chunk_cap * sizeof(int16_t*)));
+  B_CU(cudaMalloc((void**)&b->d_cfo, (size_t)b->chunk_cap * sizeof(int32_t)));
+  B_CU(cudaMallocHost((void**)&b->h_cfo, (size_t)max_subframes * sizeof(int32_t)));
   B_CU(cudaMallocHost((void**)&b->h_status, (size_t)max_subframes * 4 * sizeof(int32_t)));
   B_CU(cudaMallocHost((void**)&b->h_meas, (size_t)max_subframes * 5 * sizeof(float)));
   B_CU(cudaMallocHost((void**)&b->h_rows, (size_t)max_subframes * sizeof(int16_t*)));
@@ -210,7 +213,7 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   for (auto& kv : b->plans) srsue_gpu_pdsch_plan_destroy(kv.second.plan);
   for (auto& kv : b->softbuffers) cudaFree(kv.second.d);
   cudaFree(b->d_iq[0]); cudaFree(b->d_iq[1]); cudaFree(b->d_payload); cudaFree(b->d_status); cudaFree(b->d_meas);
-  cudaFree(b->d_sb); cudaFree(b->d_rows);
+  cudaFree(b->d_sb); cudaFree(b->d_rows); cudaFree(b->d_cfo); cudaFreeHost(b->h_cfo);
   cudaFreeHost(b->h_status); cudaFreeHost(b->h_meas); cudaFreeHost(b->h_rows);
   cudaFreeHost(b->h_iq[0]); cudaFreeHost(b->h_iq[1]); cudaFreeHost(b->h_pl);
   cudaFreeHost(b->h_iq_rows); cudaFreeHost(b->h_pl_rows);
@@ -336,8 +339,18 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
         d_sb = b->d_sb;
         if (mode == 2) { softbuffer_rows_kernel<<<m, 256, 0, b->s_compute>>>(d_sb, b->d_rows, info.sb_sf_stride, 0); b->launches++; }
       }
+      bool any_cfo = false;
+      for (int r = 0; r < m; r++) {
+        const float cfo = descs[idx[off + r]].cfo;
+        if (!(cfo > -1.0f && cfo < 1.0f)) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: cfo %g outside (-1, 1) subcarrier spacings", idx[off + r], (double)cfo);
+        b->h_cfo[pos0 + r] = cfo != 0.0f ? srsue_gpu_host_cfo_step(cfo, info.nfft) : 0;
+        any_cfo |= b->h_cfo[pos0 + r] != 0;
+      }
+      if (any_cfo) B_CU(cudaMemcpyAsync(b->d_cfo, b->h_cfo + pos0, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, b->s_compute));
+      srsue_gpu_pdsch_plan_set_cfo(pe->plan, any_cfo ? b->d_cfo : nullptr, 0);
       rc = srsue_gpu_pdsch_decode_batch(pe->plan, m, b->d_iq[h], b->noise_est, b->noise_mode, b->max_iter, mode == 2, d_sb, b->d_payload,
                                         b->d_status, b->d_meas, b->s_compute);
+      srsue_gpu_pdsch_plan_set_cfo(pe->plan, nullptr, 0);
       if (rc) return rc;
       b->launches += srsue_gpu_last_launch_count(b->ctx);
       B_CU(cudaEventRecord(b->ev_free[h], b->s_compute));

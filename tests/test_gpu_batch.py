@@ -207,3 +207,35 @@ def test_plan_cache_eviction(gpu, oracle):
         for r, tb in zip(res, refs):
             assert r["crc_ok"] == 1 and np.array_equal(r["payload"], tb)
     b.close()
+
+
+def test_mixed_stream_with_carrier_offsets(gpu, oracle):
+    """Captures of different UEs carry different carrier offsets: the per-descriptor cfo is removed while each row is
+    transformed (SPEC.md 14) and the result equals the oracle's rotate-then-decode, row by row; rows with cfo 0 in the
+    same launch stay untouched."""
+    sg, ctx = gpu
+    o = oracle
+    rng = np.random.default_rng(77)
+    order = [int(x) for x in rng.integers(0, len(MIX), 24)]
+    items, refs = [], []
+    for i, m in enumerate(order):
+        ocell, ocfg, cell, cfg = _pair(sg, o, MIX[m])
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 61000 + i, MIX[m][7] + 6.0)
+        n = o.lib().lteo_symbol_sz(MIX[m][0])
+        cfo = 0.0 if i % 3 == 0 else float(np.float32(rng.uniform(-0.4, 0.4)))
+        rx = (iq.astype(np.complex128) * np.exp(2j * np.pi * cfo * np.arange(len(iq)) / n)).astype(np.complex64)
+        items.append(dict(cell=cell, cfg=cfg, iq=rx, cfo=cfo))
+        refs.append((ocell, ocfg, rx, tb, o.cfo_step(cfo, n)))
+    b = sg.Batch(ctx, 32)
+    b.submit(items)
+    res = b.wait()
+    for r, (ocell, ocfg, rx, tb, step) in zip(res, refs):
+        x = o.cfo_correct(rx, step) if step else rx
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, x, 0.01, 0, 4)
+        assert (r["crc_ok"] == 1) == (rc == 0) and np.array_equal(r["payload"], pl) and r["n_iter"] == avg
+        assert np.allclose(r["meas"], meas, rtol=1e-4)
+        assert rc == 0 and np.array_equal(pl, tb)
+    items[3]["cfo"] = 1.5
+    with pytest.raises(sg.GpuError):
+        b.submit(items[:5])
+    b.close()
