@@ -254,7 +254,7 @@ def test_srslte_ue_dl_decode_wrapper_cfg1(gpu, oracle, cfi):
     L.srslte_ue_dl_free(C.byref(q))
 
 
-@pytest.mark.parametrize("prb,rnti", [(25, 0x4601), (6, 0xFFFF)])
+@pytest.mark.parametrize("prb,rnti", [(25, 0x4601), (6, 0xFFFF), (50, 0x0102)])
 def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     """srslte_ue_dl_decode with no grant from the caller: CFI from the PCFICH, blind PDCCH search for the RNTI, DCI ->
     grant through the installed size table, PDSCH decode.  The SI-RNTI case takes the format 1A N_PRB^1A column."""
@@ -264,7 +264,7 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     L = sg.lib()
     from tests.srslte_ctypes import UeDl, Cell, DciMsg, RaDlDci, install_tbs_table
     si = rnti == 0xFFFF
-    cfi, tbs, mcs = (3, 296, 5) if si else (2, 2216, 9)
+    cfi, tbs, mcs = (3, 296, 5) if si else (2, 2216, 9) if prb == 25 else (1, 776, 6)
     ocell = o.make_cell(prb, 1, 1)
     q = UeDl()
     cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)
@@ -274,22 +274,34 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     for tti in (4, 13, 26):
         sf_idx = tti % 10
         sent = RaDlDci()
-        sent.alloc_type, sent.mcs_idx, sent.rv_idx = 2, mcs, 0
-        start, ln = (1, 4) if si else (tti % 5, prb - 6)
-        sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
+        sent.mcs_idx, sent.rv_idx = mcs, 0
+        if prb == 50:
+            # format 1, allocation type 1 (36.213 7.1.6.2): RBG subset 1 of P = 3, shifted, every other VRB of it
+            P, p, n1 = 3, 1, 17 - 2 - 1
+            sent.alloc_type, sent.type1_alloc.rbg_subset, sent.type1_alloc.shift = 1, p, True
+            sent.type1_alloc.vrb_bitmask = int("10" * (n1 // 2), 2)
+            subset = [i for i in range(prb) if (i // P) % P == p]
+            prbs = [subset[i + len(subset) - n1] for i in range(n1) if i % 2 == 0]
+            ln, fmt = len(prbs), 1
+        else:
+            start, ln = (1, 4) if si else (tti % 5, prb - 6)
+            sent.alloc_type = 2
+            sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
+            prbs, fmt = list(range(start, start + ln)), 2
         install_tbs_table(L, {(mcs, 3 if si else ln): tbs})
         m = DciMsg()
-        nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), 2, C.byref(m), prb, not si)
+        nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), fmt, C.byref(m), prb, not si)
         assert nb > 0
         rk, _ = o.pdcch_regs(ocell, cfi, 6)
         ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti) if not si else [(4, 0)]
-        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=2, tbs=tbs, prbs=range(start, start + ln))
+        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=2, tbs=tbs, prbs=prbs)
         tb, iq, _ = o.gen_subframe(ocell, ocfg, 4000 + tti, 12.0, None, pcfich=True,
                                    dcis=[(np.frombuffer(m.data, np.uint8)[:nb].copy(), rnti, ss[0][0], ss[0][1])])
         data = np.zeros(tbs // 8, np.uint8)
         n = L.srslte_ue_dl_decode(C.byref(q), iq.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti)
         assert n == tbs and np.array_equal(data, tb)
         assert q.pdsch_cfg.grant.nof_prb == ln and q.pdsch_cfg.grant.mcs.idx == mcs
+        assert [i for i in range(prb) if q.pdsch_cfg.grant.prb_idx[0][i]] == prbs
         # a subframe without a DCI for this RNTI decodes nothing
         _, iq0, _ = o.gen_subframe(ocell, ocfg, 4100 + tti, 12.0, None, pcfich=True)
         assert L.srslte_ue_dl_decode(C.byref(q), iq0.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti) == 0
