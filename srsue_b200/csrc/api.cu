@@ -651,8 +651,14 @@ int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t* p, const int32_t* d_cfo
 int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t* p, int format, float scale) {
   if (!p || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
-  if (p->d_iq && format != p->iq_format) { cudaFree(p->d_iq); p->d_iq = nullptr; cudaFree(p->d_payload); p->d_payload = nullptr;
-                                           cudaFree(p->d_tb_status); p->d_tb_status = nullptr; }
+  if (p->d_iq && format != p->iq_format) {
+    // the staging buffers of srsue_gpu_pdsch_decode_batch_host are sized for the old sample format
+    CU_CHECK(cudaSetDevice(p->ctx->device));
+    CU_CHECK(cudaDeviceSynchronize());
+    cudaFree(p->d_iq); p->d_iq = nullptr;
+    cudaFree(p->d_payload); p->d_payload = nullptr;
+    cudaFree(p->d_tb_status); p->d_tb_status = nullptr;
+  }
   p->iq_format = format;
   if (format == SRSUE_GPU_IQ_SC16) p->iq16_scale = scale;
   return 0;
