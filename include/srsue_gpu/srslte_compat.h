@@ -320,7 +320,9 @@ SRSLTE_API int srslte_ue_sync_start_agc(srslte_ue_sync_t *q, double (*set_gain_c
  * searching (a 5 ms PSS/SSS search for the cell's id) the calls return 0; once aligned every call returns 1 with exactly
  * one subframe in the buffer, checks the PSS of subframes 0 and 5 in a window around its expected place, follows timing
  * drift by reading a few samples more or less, averages the carrier offset, and falls back to searching after ten
- * consecutive missed peaks.  < 0 on error.  The samples are handed out as received (no CFO correction). */
+ * consecutive missed peaks.  < 0 on error.  The samples are handed out as received: where srsLTE rotates them on the
+ * CPU by the tracked offset, here the worker's transform does it on its loads -- pass srslte_ue_sync_get_cfo()/15000
+ * to srsue_gpu_ue_dl_set_cfo(), which is what phch_recv.cc:328-329 already hands to phch_worker::set_cfo. */
 SRSLTE_API int srslte_ue_sync_init(srslte_ue_sync_t *q, srslte_cell_t cell,
                                    int (*recv_callback)(void *, void *, uint32_t, srslte_timestamp_t *), void *stream_handler);
 SRSLTE_API void srslte_ue_sync_free(srslte_ue_sync_t *q);
