@@ -1043,6 +1043,8 @@ int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsu
   p->ctx->launch_count = 0;
   float* meas = d_meas ? d_meas : p->d_meas;
   int16_t* sb = d_softbuf ? d_softbuf : p->d_sb;
+  if (p->iq_format == SRSUE_GPU_IQ_SC16 && (p->cfo_steps || p->cfo_step_all))
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "carrier-offset correction is only implemented for cf32 input");
   int rc = p->iq_format == SRSUE_GPU_IQ_SC16
                ? srsue_gpu_ofdm_rx_sc16(p, n_sf, reinterpret_cast<const int16_t*>(d_iq), p->iq16_scale, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream)
                : srsue_gpu_ofdm_rx_cfo(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), p->cfo_steps, p->cfo_step_all, stream);
