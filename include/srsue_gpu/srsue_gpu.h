@@ -130,9 +130,12 @@ int srsue_gpu_host_cfo_step(float cfo, int nfft);
  * over PCIe and out of HBM.  d_iq16 [n_sf][sf_len][2]. */
 int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_iq16, float scale, srsue_gpu_cf_t *d_sf_symbols,
                            void *stream);
+/* both: convert, then rotate by the carrier offset (steps as in srsue_gpu_ofdm_rx_cfo) */
+int srsue_gpu_ofdm_rx_sc16_cfo(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_iq16, float scale, srsue_gpu_cf_t *d_sf_symbols,
+                               const int32_t *d_cfo_steps, int32_t cfo_step, void *stream);
 /* What the d_iq / h_iq arguments of srsue_gpu_pdsch_decode_batch[_host] point at for this plan: SRSUE_GPU_IQ_CF32 (default)
  * or SRSUE_GPU_IQ_SC16 with its scale (e.g. 1/32768). */
-/* carrier-offset correction for the batch calls of this plan (cf32 input): per-subframe steps on the device (row i of the
+/* carrier-offset correction for the batch calls of this plan: per-subframe steps on the device (row i of the
  * next srsue_gpu_pdsch_decode_batch call), or one step for all subframes when d_cfo_steps is NULL; (NULL, 0) switches it off */
 int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t *plan, const int32_t *d_cfo_steps, int32_t cfo_step);
 enum { SRSUE_GPU_IQ_CF32 = 0, SRSUE_GPU_IQ_SC16 = 1 };

@@ -168,9 +168,14 @@ class PdschPlan:
             _check(lib().srsue_gpu_ofdm_rx_cfo(self.h, n_sf, _ptr(d_iq), _ptr(d_sf), _ptr(d_cfo_steps), C.c_int32(cfo_step),
                                                _stream()), "ofdm_rx_cfo")
 
-    def ofdm_rx_sc16(self, n_sf, d_iq16, scale, d_sf):
-        """OFDM demodulation of int16 {re, im} samples; sample = float(v) * scale."""
-        _check(lib().srsue_gpu_ofdm_rx_sc16(self.h, n_sf, _ptr(d_iq16), C.c_float(scale), _ptr(d_sf), _stream()), "ofdm_rx_sc16")
+    def ofdm_rx_sc16(self, n_sf, d_iq16, scale, d_sf, d_cfo_steps=None, cfo_step=0):
+        """OFDM demodulation of int16 {re, im} samples; sample = float(v) * scale, then the optional carrier-offset rotation."""
+        _check(lib().srsue_gpu_ofdm_rx_sc16_cfo(self.h, n_sf, _ptr(d_iq16), C.c_float(scale), _ptr(d_sf), _ptr(d_cfo_steps),
+                                                C.c_int32(cfo_step), _stream()), "ofdm_rx_sc16")
+
+    def set_cfo(self, d_cfo_steps=None, cfo_step=0):
+        """carrier-offset correction for decode_batch / decode_batch_host of this plan; (None, 0) switches it off"""
+        _check(lib().srsue_gpu_pdsch_plan_set_cfo(self.h, _ptr(d_cfo_steps), C.c_int32(cfo_step)), "set_cfo")
 
     def set_iq_format(self, sc16, scale=1.0 / 32768.0):
         """decode_batch / decode_batch_host take int16 {re, im} samples (sc16=True) or complex64 (False, the default)."""

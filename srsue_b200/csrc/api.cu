@@ -239,7 +239,7 @@ struct srsue_gpu_pdsch_plan {
   uint8_t* d_cb_bits = nullptr; int32_t* d_cb_status = nullptr;
   // staging for the host-pointer call
   float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
-  const int32_t* cfo_steps = nullptr; int32_t cfo_step_all = 0;            // carrier-offset correction of the batch calls (cf32 input)
+  const int32_t* cfo_steps = nullptr; int32_t cfo_step_all = 0;            // carrier-offset correction of the batch calls
   int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what the d_iq / h_iq arguments of the batch calls point at
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
@@ -638,8 +638,13 @@ int srsue_gpu_ofdm_rx_cfo(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
 }
 
 int srsue_gpu_ofdm_rx_sc16(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_iq16, float scale, srsue_gpu_cf_t* d_sf, void* stream) {
+  return srsue_gpu_ofdm_rx_sc16_cfo(p, n_sf, d_iq16, scale, d_sf, nullptr, 0, stream);
+}
+
+int srsue_gpu_ofdm_rx_sc16_cfo(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_iq16, float scale, srsue_gpu_cf_t* d_sf,
+                               const int32_t* d_cfo_steps, int32_t cfo_step_all, void* stream) {
   if (!(scale > 0.f)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ofdm_rx_sc16: scale must be positive");
-  return ofdm_launch(p, n_sf, nullptr, d_iq16, scale, d_sf, nullptr, 0, stream);
+  return ofdm_launch(p, n_sf, nullptr, d_iq16, scale, d_sf, d_cfo_steps, cfo_step_all, stream);
 }
 
 int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t* p, const int32_t* d_cfo_steps, int32_t cfo_step) {
@@ -698,7 +703,10 @@ static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t
     // single exchange buffer (8 CTAs per SM) wherever the CTA has exactly N/8 threads; SRSUE_FFT_INPLACE=0 selects the
     // two-buffer kernel for comparison
     static const int inplace = getenv("SRSUE_FFT_INPLACE") ? atoi(getenv("SRSUE_FFT_INPLACE")) : 1;
-    if (b.iq16) {
+    if (b.iq16 && rotate) {
+      if (b.cfo_steps) b.cfo_steps += done;
+      ofdm_rx_cfo_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+    } else if (b.iq16) {
       if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_iq16_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
       else ofdm_rx_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
     } else if (rotate) {
@@ -1043,10 +1051,9 @@ int srsue_gpu_pdsch_decode_batch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsu
   p->ctx->launch_count = 0;
   float* meas = d_meas ? d_meas : p->d_meas;
   int16_t* sb = d_softbuf ? d_softbuf : p->d_sb;
-  if (p->iq_format == SRSUE_GPU_IQ_SC16 && (p->cfo_steps || p->cfo_step_all))
-    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "carrier-offset correction is only implemented for cf32 input");
   int rc = p->iq_format == SRSUE_GPU_IQ_SC16
-               ? srsue_gpu_ofdm_rx_sc16(p, n_sf, reinterpret_cast<const int16_t*>(d_iq), p->iq16_scale, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), stream)
+               ? srsue_gpu_ofdm_rx_sc16_cfo(p, n_sf, reinterpret_cast<const int16_t*>(d_iq), p->iq16_scale, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf),
+                                            p->cfo_steps, p->cfo_step_all, stream)
                : srsue_gpu_ofdm_rx_cfo(p, n_sf, d_iq, reinterpret_cast<srsue_gpu_cf_t*>(p->d_sf), p->cfo_steps, p->cfo_step_all, stream);
   // (the fused variant srsue_gpu_chest_pilots + srsue_gpu_pdsch_llr_fused moves 250 KB less per subframe but was
   // measured SLOWER on B200, 1.25 ms vs 1.08 ms per 4096 subframes: the demapper is issue-bound, not HBM-bound)
@@ -1089,9 +1096,12 @@ int srsue_gpu_pdsch_decode_batch_host(srsue_gpu_pdsch_plan_t* p, int n_sf, const
   for (int off = 0; off < n_sf; off += chunk, n_ch++) {
     const int n = std::min(chunk, n_sf - off);
     CU_CHECK(cudaStreamWaitEvent(sc, p->ev[n_ch], 0));
+    const int32_t* steps_all = p->cfo_steps;              // per-subframe carrier-offset steps follow the chunk
+    if (steps_all) p->cfo_steps = steps_all + off;
     int rc = srsue_gpu_pdsch_decode_batch(p, n, reinterpret_cast<srsue_gpu_cf_t*>(reinterpret_cast<char*>(p->d_iq) + (size_t)off * p->info.sf_len * esz), noise_est,
                                           noise_mode, max_iter, 0, nullptr, p->d_payload + (size_t)off * p->info.payload_stride,
                                           p->d_tb_status + (size_t)off * 4, p->d_meas + (size_t)off * 5, sc);
+    p->cfo_steps = steps_all;
     if (rc) return rc;
     CU_CHECK(cudaMemcpyAsync(h_payload + (size_t)off * p->info.payload_stride, p->d_payload + (size_t)off * p->info.payload_stride,
                              (size_t)n * p->info.payload_stride, cudaMemcpyDeviceToHost, sc));

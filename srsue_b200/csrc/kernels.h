@@ -60,6 +60,7 @@ __global__ void ofdm_rx_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_cfo_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_inplace_iq16_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_iq16_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_cfo_iq16_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_inplace_kernel(const OfdmArgs a);
 
 struct ChestArgs {

@@ -381,6 +381,30 @@ __global__ void __launch_bounds__(256) ofdm_rx_iq16_kernel(const OfdmArgs a) {
   }
 }
 
+// int16 input and the carrier-offset rotation together (a live radio's case): convert, then rotate, both on the loads.
+__global__ void __launch_bounds__(256) ofdm_rx_cfo_iq16_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  const int N = a.nfft;
+  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
+  float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
+  float2* s0 = s_fft;
+  float2* s1 = s_fft + (N + N / 16 + 8);
+  const uint32_t step = (uint32_t)(a.cfo_steps ? __ldg(a.cfo_steps + sf) : a.cfo_step);
+  if (N == 1536) { fft1536_symbol<true, true>(gin, gout, s_fft, a.tw, a.nsc, a.scale, a.c3, (uint32_t)start, step, a.cexp, a.iq16_scale); return; }
+  switch (a.log2n) {
+    case 7: fft_symbol<7, true, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, (uint32_t)start, step, a.cexp, a.iq16_scale); break;
+    case 8: fft_symbol<8, true, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, (uint32_t)start, step, a.cexp, a.iq16_scale); break;
+    case 9: fft_symbol<9, true, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, (uint32_t)start, step, a.cexp, a.iq16_scale); break;
+    case 10: fft_symbol<10, true, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, (uint32_t)start, step, a.cexp, a.iq16_scale); break;
+    case 11: fft_symbol<11, true, true>(gin, gout, s0, s1, a.tw, a.nsc, a.scale, (uint32_t)start, step, a.cexp, a.iq16_scale); break;
+    default: break;
+  }
+}
+
 // The two-buffer kernel with the carrier-offset rotation fused into the sample loads (all transform sizes).
 __global__ void __launch_bounds__(256) ofdm_rx_cfo_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];

@@ -394,6 +394,23 @@ def test_batch_host_sc16_input(gpu, oracle, prb, ports, qm, tbs):
         assert rc == 0 and h_st[i, 0] == 1
         assert np.array_equal(h_pl[i, :tbs // 8], pl) and np.array_equal(pl, sent[i])
         assert np.allclose(h_meas[i], meas, rtol=1e-4)
+    # the same captures with a carrier offset each, removed through the plan's per-subframe steps
+    import torch
+    nfft = o.lib().lteo_symbol_sz(prb)
+    cfos = [0.0, 0.2, -0.33, 0.05, 0.41, -0.12]
+    rot = np.stack([(iq[i].astype(np.complex128) * np.exp(2j * np.pi * cfos[i] * np.arange(iq.shape[1]) / nfft)).astype(np.complex64)
+                    for i in range(n)])
+    r16 = np.rint(rot.view(np.float32) / scale).astype(np.int16)
+    steps = np.array([sg.host_cfo_step(c, nfft) for c in cfos], np.int32)
+    d_steps = torch.from_numpy(steps).cuda()
+    plan.set_cfo(d_steps)
+    h_pl[:] = 0
+    plan.decode_batch_host(n, r16, 0.01, 1, 4, h_pl, h_st, h_meas)
+    for i in range(n):
+        xr = o.cfo_correct((r16[i].astype(np.float32) * scale).view(np.complex64), int(steps[i]))
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, xr, 0.01, 1, 4)
+        assert rc == 0 and h_st[i, 0] == 1 and np.array_equal(h_pl[i, :tbs // 8], pl) and np.array_equal(pl, sent[i])
+    plan.set_cfo(None, 0)
     plan.set_iq_format(False)
     h_pl[:] = 0
     plan.decode_batch_host(n, iq, 0.01, 1, 4, h_pl, h_st, h_meas)

@@ -147,6 +147,13 @@ def test_ofdm_rx_sc16_matches_oracle(gpu, oracle, prb):
         got = d_sf.cpu().numpy().view(np.complex64)
         for i in range(n_sf):
             assert np.array_equal(got[i], o.ofdm_rx(prb, x[i])), "subframe %d scale %g" % (i, scale)
+        # a live radio's case: int16 samples with a carrier offset -- convert, then rotate (SPEC.md 14), both on the loads
+        steps = np.array([sg.host_cfo_step(c, n) for c in (0.31, 0.0, -0.08)], np.int32)
+        plan.ofdm_rx_sc16(n_sf, torch.from_numpy(q).cuda(), scale, d_sf, d_cfo_steps=torch.from_numpy(steps).cuda())
+        torch.cuda.synchronize()
+        got = d_sf.cpu().numpy().view(np.complex64)
+        for i in range(n_sf):
+            assert np.array_equal(got[i], o.ofdm_rx(prb, o.cfo_correct(x[i], int(steps[i])))), "cfo subframe %d" % i
     plan.close()
 
 
