@@ -52,8 +52,23 @@ def test_reference_call_sites_are_covered(lib):
               "srslte_tti_interval", "srslte_ue_sync_init", "srslte_ue_sync_free", "srslte_ue_sync_zerocopy", "srslte_ue_sync_get_buffer",
               "srslte_ue_sync_get_sfidx", "srslte_ue_sync_get_cfo", "srslte_ue_sync_get_sfo", "srslte_ue_sync_set_cfo",
               "srslte_ue_sync_set_agc_period", "srslte_ue_sync_decode_sss_on_track", "srslte_ue_sync_get_last_timestamp",
-              "srslte_sync_set_threshold", "srslte_sync_set_em_alpha"]:
+              "srslte_sync_set_threshold", "srslte_sync_set_em_alpha",
+              "srslte_dci_msg_to_dl_grant", "srslte_ra_dl_dci_string", "srslte_cqi_from_snr", "srslte_cqi_send",
+              "srslte_cqi_value_pack", "srsue_gpu_ue_dl_set_cfo", "srsue_gpu_ra_set_tbs_table"]:
         assert hasattr(lib, n), n
+
+
+def test_headers_are_plain_c_and_cxx(tmp_path):
+    """the boundary is a C ABI: both headers must parse as C99 (srsLTE is C) and as C++11 (srsUE is C++)"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "srsue_gpu/srslte_compat.h"\n'
+                   'int main(void) { srslte_ra_dl_dci_t d; srslte_cqi_value_t v; srsue_gpu_sf_desc_t s; (void)d; (void)v; (void)s; return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I" + inc, str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
 
 
 def test_host_tables_agree_with_oracle(lib, oracle):
