@@ -206,8 +206,8 @@ SRSLTE_API int srslte_pdcch_extract_llr(srslte_pdcch_t *q, cf_t *sf_symbols, cf_
 SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx,
                                              uint16_t rnti, srslte_rnti_type_t rnti_type);
 /* uplink grant search (phch_worker.cc:426): DCI format 0 in the UE-specific space; 1 found / 0 / < 0 */
-/* DCI payload -> unpacked fields -> grant (phch_worker.cc:297).  Formats 1A and 1, FDD; localized allocations only
- * (distributed virtual resource blocks return an error).  Transport-block sizes come from the 27 x 110 table of 36.213
+/* DCI payload -> unpacked fields -> grant (phch_worker.cc:297).  Formats 1A and 1, FDD; allocation types 0, 1 and 2,
+ * localized and distributed (36.211 6.2.3.2: the grant's two slot masks then differ).  Transport-block sizes come from the 27 x 110 table of 36.213
  * 7.1.7.2.1, which the caller installs once per process with srsue_gpu_ra_set_tbs_table(); until then every call that
  * needs a size returns SRSLTE_ERROR with a message.  Returns 0 on success (as srsLTE does). */
 SRSLTE_API int srsue_gpu_ra_set_tbs_table(const int32_t *table, uint32_t nof_rows /* 27 */, uint32_t nof_cols /* 110 */);
@@ -240,6 +240,9 @@ SRSLTE_API uint8_t srslte_cqi_from_snr(float snr_db);
 SRSLTE_API bool srslte_cqi_send(uint32_t I_cqi_pmi, uint32_t tti);
 SRSLTE_API int srslte_cqi_value_pack(srslte_cqi_value_t *value, uint8_t *buff);
 #define SRSLTE_VEC_EMA(data, average, alpha) ((alpha) * (data) + (1 - (alpha)) * (average))     /* phch_worker.cc:512 */
+/* distributed virtual -> physical resource block of one slot (0xFFFFFFFF when out of range) and the number of VRBs */
+SRSLTE_API uint32_t srsue_gpu_host_dvrb_to_prb(uint32_t nof_prb, int gap2, uint32_t n_vrb, int slot);
+SRSLTE_API uint32_t srsue_gpu_host_n_vrb_dl(uint32_t nof_prb, int gap2);
 SRSLTE_API char *srslte_ra_dl_dci_string(srslte_ra_dl_dci_t *dci);                       /* phch_worker.cc:317 */
 SRSLTE_API int srslte_ue_dl_find_ul_dci(srslte_ue_dl_t *q, srslte_dci_msg_t *dci_msg, uint32_t cfi, uint32_t sf_idx, uint16_t rnti);
 SRSLTE_API uint32_t srslte_ue_dl_get_ncce(srslte_ue_dl_t *q);

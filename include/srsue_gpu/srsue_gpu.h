@@ -49,7 +49,8 @@ typedef struct {
   int rv;           /* redundancy version 0..3 */
   int tm;           /* 1: single antenna port, 2: transmit diversity */
   int nof_prb_alloc;
-  uint8_t prb_mask[110];  /* 1 = PRB allocated (same PRBs in both slots) */
+  uint8_t prb_mask[110];  /* 1 = PRB allocated in both slots; 2 = in slot 0 only, 4 = in slot 1 only (distributed
+                           * virtual resource blocks, 36.211 6.2.3.2; 6 = 1) */
 } srsue_gpu_pdsch_cfg_t;
 
 typedef struct {

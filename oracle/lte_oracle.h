@@ -55,7 +55,7 @@ typedef struct {
   int rv;           /* 0..3 */
   int tm;           /* 1 = single port, 2 = transmit diversity (needs nof_ports == 2) */
   int nof_prb_alloc;
-  uint8_t prb_mask[110]; /* 1 = PRB allocated (same PRBs in both slots) */
+  uint8_t prb_mask[110]; /* 1 = PRB allocated in both slots; 2 = slot 0 only; 4 = slot 1 only */
 } lteo_pdsch_cfg_t;
 
 typedef struct { int tbs, B, C, Kp, Km, Cp, Cm, F; } lteo_cbsegm_t;

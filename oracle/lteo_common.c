@@ -358,7 +358,7 @@ void lteo_crs_values(const lteo_cell_t *cell, int sf_idx, int l, int8_t *re_sign
 }
 
 /* Ordered list of PDSCH resource elements (grid index l*nsc + k): symbols after the control region,
- * allocated PRBs ascending, subcarriers ascending, skipping the CRS of every configured port and, in
+ * allocated PRBs of the symbol's slot ascending, subcarriers ascending, skipping the CRS of every configured port and, in
  * subframes 0/5, the PSS/SSS (and PBCH in subframe 0) REs of the six central PRBs (36.211 6.3.5). */
 int lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int32_t *re_idx) {
   int nsc = 12 * cell->nof_prb, n = 0;
@@ -376,7 +376,8 @@ int lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int
     if ((cfg->sf_idx == 0 || cfg->sf_idx == 5) && (l == 5 || l == 6)) sync = 1;   /* SSS, PSS */
     if (cfg->sf_idx == 0 && l >= 7 && l <= 10) sync = 1;                           /* PBCH    */
     for (int prb = 0; prb < cell->nof_prb; prb++) {
-      if (!cfg->prb_mask[prb]) continue;
+      uint8_t pm = cfg->prb_mask[prb];                 /* bit 0: both slots, bit 1: slot 0 only, bit 2: slot 1 only */
+      if (!((pm & 1) || (pm & (l >= 7 ? 4 : 2)))) continue;
       for (int k = 12 * prb; k < 12 * prb + 12; k++) {
         if (crs && (k % 6 == o0 || k % 6 == o1)) continue;
         /* with a single configured port only port-0 CRS REs are reserved */

@@ -301,12 +301,14 @@ def make_cell(nof_prb, nof_ports=1, cell_id=1):
     return Cell(nof_prb, nof_ports, cell_id)
 
 
-def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None):
+def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None, prbs_slot1=None):
+    """prbs: allocated PRBs (all when None); prbs_slot1: the PRBs of the second slot when they differ from the first
+    (distributed virtual resource blocks) -- prb_mask then holds 1 (both slots), 2 (slot 0 only) or 4 (slot 1 only)"""
     cfg = PdschCfg()
     cfg.sf_idx, cfg.cfi, cfg.rnti, cfg.qm, cfg.tbs, cfg.rv, cfg.tm = sf_idx, cfi, rnti, qm, tbs, rv, tm
-    n = 0
-    for p in (range(cell.nof_prb) if prbs is None else prbs):
-        cfg.prb_mask[p] = 1
-        n += 1
-    cfg.nof_prb_alloc = n
+    s0 = set(range(cell.nof_prb) if prbs is None else prbs)
+    s1 = s0 if prbs_slot1 is None else set(prbs_slot1)
+    for p in s0 | s1:
+        cfg.prb_mask[p] = 1 if (p in s0 and p in s1) else 2 if p in s0 else 4
+    cfg.nof_prb_alloc = len(s0)
     return cfg

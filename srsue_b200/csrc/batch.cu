@@ -119,7 +119,7 @@ std::string plan_key(const srsue_gpu_sf_desc_t& d) {
   // explicit fields only (struct padding must not split buckets)
   const int v[10] = {d.cell.nof_prb, d.cell.nof_ports, d.cell.cell_id, d.cfg.sf_idx, d.cfg.cfi, d.cfg.rnti, d.cfg.qm, d.cfg.tbs, d.cfg.rv, d.cfg.tm};
   std::string k(reinterpret_cast<const char*>(v), sizeof(v));
-  for (int i = 0; i < 110; i++) k.push_back(d.cfg.prb_mask[i] ? 1 : 0);
+  for (int i = 0; i < 110; i++) k.push_back((char)(d.cfg.prb_mask[i] & 7));
   return k;
 }
 

@@ -175,7 +175,7 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
     bool central_reserved = ((cfg.sf_idx == 0 || cfg.sf_idx == 5) && (l == 5 || l == 6)) ||
                             (cfg.sf_idx == 0 && l >= 7 && l <= 10);
     for (int prb = 0; prb < cell.nof_prb; prb++) {
-      if (!cfg.prb_mask[prb]) continue;
+      if (!prb_in_slot(cfg.prb_mask[prb], l / 7)) continue;
       for (int k = 12 * prb; k < 12 * prb + 12; k++) {
         if (o0 >= 0 && (k % 6 == o0 || k % 6 == o1)) continue;
         if (central_reserved && k >= mid_lo && k < mid_hi) continue;

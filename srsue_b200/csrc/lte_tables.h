@@ -19,8 +19,10 @@ struct CellCfg { int nof_prb, nof_ports, cell_id; };
 
 struct PdschCfg {
   int sf_idx, cfi, rnti, qm, tbs, rv, tm, nof_prb_alloc;
-  uint8_t prb_mask[110];
+  uint8_t prb_mask[110];     // bit 0: PRB allocated in both slots; bit 1: in slot 0 only; bit 2: in slot 1 only
 };
+inline bool prb_in_slot(uint8_t m, int slot) { return (m & 1) || (m & (slot ? 4 : 2)); }
+
 
 struct CbSegm { int tbs, B, C, Kp, Km, Cp, Cm, F; };
 

@@ -8,6 +8,7 @@
 // The 27 x 110 transport-block-size table (36.213 Table 7.1.7.2.1-1) is published data this tree does not carry; the
 // caller installs it once with srsue_gpu_ra_set_tbs_table() (srsLTE keeps it as tbs_table[27][110] in
 // lib/phch/tbs_tables.h).  Without it every conversion that needs a size fails loudly.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -27,9 +28,51 @@ int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) b++; return b; }
 uint32_t rbg_size(uint32_t nof_prb) { return nof_prb <= 10 ? 1 : nof_prb <= 26 ? 2 : nof_prb <= 63 ? 3 : 4; }
 bool is_crnti(uint16_t r) { return r >= SRSLTE_CRNTI_START && r <= SRSLTE_CRNTI_END; }
 
+// ---- distributed virtual resource blocks (36.211 6.2.3.2) -------------------------------------------------------------
+uint32_t n_gap(uint32_t nof_prb, bool gap2) {            // Table 6.2.3.2-1
+  if (nof_prb <= 10) return (nof_prb + 1) / 2;
+  if (nof_prb == 11) return 4;
+  if (nof_prb <= 19) return 8;
+  if (nof_prb <= 26) return 12;
+  if (nof_prb <= 44) return 18;
+  if (nof_prb <= 49) return 27;
+  if (nof_prb <= 63) return gap2 ? 9 : 27;
+  if (nof_prb <= 79) return gap2 ? 16 : 32;
+  return gap2 ? 16 : 48;
+}
+uint32_t n_vrb_dl(uint32_t nof_prb, bool gap2) {
+  const uint32_t g = n_gap(nof_prb, gap2);
+  return gap2 ? (nof_prb / (2 * g)) * 2 * g : 2 * std::min(g, nof_prb - g);
+}
+// physical resource block of distributed virtual resource block n_vrb in slot 0 / 1
+uint32_t dvrb_to_prb(uint32_t nof_prb, bool gap2, uint32_t n_vrb, int slot) {
+  const uint32_t g = n_gap(nof_prb, gap2), P = rbg_size(nof_prb);
+  const uint32_t nt = gap2 ? 2 * g : n_vrb_dl(nof_prb, false);            // size of one interleaving unit
+  const uint32_t n_row = (nt + 4 * P - 1) / (4 * P) * P, n_null = 4 * n_row - nt;
+  const uint32_t unit = n_vrb / nt, v = n_vrb % nt;
+  const uint32_t p1 = 2 * n_row * (v % 2) + v / 2, p2 = n_row * (v % 4) + v / 4;
+  uint32_t t;
+  if (n_null && v >= nt - n_null && v % 2 == 1) t = p1 - n_row;
+  else if (n_null && v >= nt - n_null && v % 2 == 0) t = p1 - n_row + n_null / 2;
+  else if (n_null && v < nt - n_null && v % 4 >= 2) t = p2 - n_null / 2;
+  else t = p2;
+  if (slot) t = (t + nt / 2) % nt;
+  t += nt * unit;
+  return t < nt / 2 ? t : t + g - nt / 2;
+}
+
 }  // namespace
 
 extern "C" {
+
+uint32_t srsue_gpu_host_dvrb_to_prb(uint32_t nof_prb, int gap2, uint32_t n_vrb, int slot) {
+  if (nof_prb < 6 || nof_prb > SRSLTE_MAX_PRB || (gap2 && nof_prb < 50) || n_vrb >= n_vrb_dl(nof_prb, gap2 != 0)) return 0xFFFFFFFFu;
+  return dvrb_to_prb(nof_prb, gap2 != 0, n_vrb, slot ? 1 : 0);
+}
+uint32_t srsue_gpu_host_n_vrb_dl(uint32_t nof_prb, int gap2) {
+  return (nof_prb < 6 || nof_prb > SRSLTE_MAX_PRB || (gap2 && nof_prb < 50)) ? 0 : n_vrb_dl(nof_prb, gap2 != 0);
+}
+
 
 int srsue_gpu_ra_set_tbs_table(const int32_t* table, uint32_t nof_rows, uint32_t nof_cols) {
   if (!table || nof_rows != 27 || nof_cols != 110) return SRSLTE_ERROR_INVALID_INPUTS;
@@ -51,7 +94,7 @@ uint32_t srslte_ra_type2_to_riv(uint32_t L_crb, uint32_t RB_start, uint32_t nof_
 
 void srslte_ra_type2_from_riv(uint32_t riv, uint32_t* L_crb, uint32_t* RB_start, uint32_t nof_prb, uint32_t nof_vrb) {
   uint32_t L = riv / nof_prb + 1, s = riv % nof_prb;
-  if (L > nof_vrb - s) { L = nof_vrb - L + 2; s = nof_vrb - 1 - s; }
+  if (s >= nof_vrb || L > nof_vrb - s) { L = nof_prb - L + 2; s = nof_prb - 1 - s; }   // the folded half of 36.213 7.1.6.3
   if (L_crb) *L_crb = L;
   if (RB_start) *RB_start = s;
 }
@@ -85,7 +128,12 @@ int srslte_dci_msg_unpack_pdsch(srslte_dci_msg_t* msg, srslte_ra_dl_dci_t* d, ui
     d->dci_is_1a = true;
     d->alloc_type = SRSLTE_RA_ALLOC_TYPE2;
     d->type2_alloc.mode = take(&y, 1) ? SRSLTE_RA_TYPE2_DIST : SRSLTE_RA_TYPE2_LOC;
-    d->type2_alloc.riv = take(&y, (int)srslte_ra_type2_n_rb(nof_prb));
+    int riv_bits = (int)srslte_ra_type2_n_rb(nof_prb);
+    if (d->type2_alloc.mode == SRSLTE_RA_TYPE2_DIST && crc_is_crnti && nof_prb >= 50) {     // MSB of the field: the gap
+      d->type2_alloc.n_gap = take(&y, 1) ? SRSLTE_RA_TYPE2_NG2 : SRSLTE_RA_TYPE2_NG1;
+      riv_bits--;
+    }
+    d->type2_alloc.riv = take(&y, riv_bits);
     d->mcs_idx = take(&y, 5);
     d->harq_process = take(&y, 3);
     const uint32_t ndi = take(&y, 1);
@@ -95,10 +143,9 @@ int srslte_dci_msg_unpack_pdsch(srslte_dci_msg_t* msg, srslte_ra_dl_dci_t* d, ui
     const uint32_t tpc = take(&y, 2);
     d->tpc = tpc;
     if (!crc_is_crnti) d->type2_alloc.n_prb1a = (tpc & 1) ? SRSLTE_RA_TYPE2_NPRB1A_3 : SRSLTE_RA_TYPE2_NPRB1A_2;
-    if (d->type2_alloc.mode == SRSLTE_RA_TYPE2_LOC) {
-      srslte_ra_type2_from_riv(d->type2_alloc.riv, &d->type2_alloc.L_crb, &d->type2_alloc.RB_start, nof_prb, nof_prb);
-      if (d->type2_alloc.L_crb < 1 || d->type2_alloc.RB_start + d->type2_alloc.L_crb > nof_prb) return SRSLTE_ERROR;
-    }
+    const uint32_t nof_vrb = d->type2_alloc.mode == SRSLTE_RA_TYPE2_LOC ? nof_prb : n_vrb_dl(nof_prb, d->type2_alloc.n_gap == SRSLTE_RA_TYPE2_NG2);
+    srslte_ra_type2_from_riv(d->type2_alloc.riv, &d->type2_alloc.L_crb, &d->type2_alloc.RB_start, nof_prb, nof_vrb);
+    if (d->type2_alloc.L_crb < 1 || d->type2_alloc.RB_start + d->type2_alloc.L_crb > nof_vrb) return SRSLTE_ERROR;
     return SRSLTE_SUCCESS;
   }
   if (msg->format == SRSLTE_DCI_FORMAT1) {
@@ -156,9 +203,17 @@ int srslte_ra_dl_dci_to_grant_prb_allocation(srslte_ra_dl_dci_t* d, srslte_ra_dl
       break;
     }
     case SRSLTE_RA_ALLOC_TYPE2: {
-      if (d->type2_alloc.mode != SRSLTE_RA_TYPE2_LOC) {
-        fprintf(stderr, "[srsue_gpu] distributed virtual resource blocks (36.211 6.2.3.2) are not supported\n");
-        return SRSLTE_ERROR;
+      if (d->type2_alloc.mode == SRSLTE_RA_TYPE2_DIST) {
+        const bool gap2 = d->type2_alloc.n_gap == SRSLTE_RA_TYPE2_NG2;
+        if ((gap2 && nof_prb < 50) || d->type2_alloc.RB_start + d->type2_alloc.L_crb > n_vrb_dl(nof_prb, gap2)) return SRSLTE_ERROR;
+        for (uint32_t i = 0; i < d->type2_alloc.L_crb; i++)
+          for (int slot = 0; slot < 2; slot++) {
+            const uint32_t n = dvrb_to_prb(nof_prb, gap2, d->type2_alloc.RB_start + i, slot);
+            if (n >= nof_prb) return SRSLTE_ERROR;
+            grant->prb_idx[slot][n] = true;
+          }
+        grant->nof_prb = d->type2_alloc.L_crb;
+        return SRSLTE_SUCCESS;                            // the two slots differ: no copy below
       }
       if (d->type2_alloc.RB_start + d->type2_alloc.L_crb > nof_prb) return SRSLTE_ERROR;
       for (uint32_t i = 0; i < d->type2_alloc.L_crb; i++) grant->prb_idx[0][d->type2_alloc.RB_start + i] = true;
@@ -206,10 +261,13 @@ int srslte_dci_msg_pack_pdsch(srslte_ra_dl_dci_t* d, srslte_dci_format_t format,
   if (format == SRSLTE_DCI_FORMAT1A) {
     if (d->alloc_type != SRSLTE_RA_ALLOC_TYPE2) return SRSLTE_ERROR;
     put(1, 1);
-    put(d->type2_alloc.mode == SRSLTE_RA_TYPE2_DIST, 1);
-    const uint32_t riv = d->type2_alloc.mode == SRSLTE_RA_TYPE2_LOC ? srslte_ra_type2_to_riv(d->type2_alloc.L_crb, d->type2_alloc.RB_start, nof_prb)
-                                                                     : d->type2_alloc.riv;
-    put(riv, (int)srslte_ra_type2_n_rb(nof_prb));
+    const bool dist = d->type2_alloc.mode == SRSLTE_RA_TYPE2_DIST;
+    put(dist, 1);
+    int riv_bits = (int)srslte_ra_type2_n_rb(nof_prb);
+    if (dist && crc_is_crnti && nof_prb >= 50) { put(d->type2_alloc.n_gap == SRSLTE_RA_TYPE2_NG2, 1); riv_bits--; }
+    const uint32_t riv = srslte_ra_type2_to_riv(d->type2_alloc.L_crb, d->type2_alloc.RB_start, nof_prb);
+    if (riv >> riv_bits) return SRSLTE_ERROR;
+    put(riv, riv_bits);
     put(d->mcs_idx, 5);
     put(d->harq_process, 3);
     put(crc_is_crnti ? d->ndi : (d->type2_alloc.n_gap == SRSLTE_RA_TYPE2_NG2), 1);

@@ -68,6 +68,9 @@ struct UeDlGpu {
   cudaStream_t stream = nullptr;
 };
 
+// srsue_gpu_pdsch_cfg_t::prb_mask value of one PRB from the grant's two slot masks
+uint8_t slot_mask(bool s0, bool s1) { return (s0 && s1) ? 1 : (uint8_t)((s0 ? 2 : 0) | (s1 ? 4 : 0)); }
+
 int ng_x6_of(const srslte_cell_t& c) {
   switch (c.phich_resources) { case SRSLTE_PHICH_R_1_6: return 1; case SRSLTE_PHICH_R_1_2: return 3; case SRSLTE_PHICH_R_1: return 6; default: return 12; }
 }
@@ -94,9 +97,8 @@ int to_gpu_cfg(const srslte_cell_t& cell, const srslte_pdsch_cfg_t* cfg, uint16_
   out->tm = cell.nof_ports == 1 ? 1 : 2;      // srsLTE: single antenna port or transmit diversity
   int n = 0;
   for (uint32_t i = 0; i < cell.nof_prb; i++) {
-    if (cfg->grant.prb_idx[0][i] != cfg->grant.prb_idx[1][i]) return -1;   // slot hopping not supported
-    out->prb_mask[i] = cfg->grant.prb_idx[0][i] ? 1 : 0;
-    n += out->prb_mask[i];
+    out->prb_mask[i] = slot_mask(cfg->grant.prb_idx[0][i], cfg->grant.prb_idx[1][i]);
+    n += cfg->grant.prb_idx[0][i] ? 1 : 0;
   }
   out->nof_prb_alloc = n;
   return 0;
@@ -246,7 +248,7 @@ int srslte_ue_dl_cfg_grant(srslte_ue_dl_t* q, srslte_ra_dl_grant_t* grant, uint3
   CellCfg cell{(int)q->cell.nof_prb, (int)q->cell.nof_ports, (int)q->cell.id};
   PdschCfg pc{};
   pc.sf_idx = (int)sf_idx; pc.cfi = (int)cfi;
-  for (uint32_t i = 0; i < q->cell.nof_prb; i++) pc.prb_mask[i] = grant->prb_idx[0][i] ? 1 : 0;
+  for (uint32_t i = 0; i < q->cell.nof_prb; i++) pc.prb_mask[i] = slot_mask(grant->prb_idx[0][i], grant->prb_idx[1][i]);
   std::vector<int32_t> re;
   pdsch_re_list(cell, pc, re);
   c->nbits.nof_re = (uint32_t)re.size();

@@ -254,7 +254,7 @@ def test_srslte_ue_dl_decode_wrapper_cfg1(gpu, oracle, cfi):
     L.srslte_ue_dl_free(C.byref(q))
 
 
-@pytest.mark.parametrize("prb,rnti", [(25, 0x4601), (6, 0xFFFF), (50, 0x0102)])
+@pytest.mark.parametrize("prb,rnti", [(25, 0x4601), (6, 0xFFFF), (50, 0x0102), (15, 0x0203)])
 def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     """srslte_ue_dl_decode with no grant from the caller: CFI from the PCFICH, blind PDCCH search for the RNTI, DCI ->
     grant through the installed size table, PDSCH decode.  The SI-RNTI case takes the format 1A N_PRB^1A column."""
@@ -264,7 +264,8 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
     L = sg.lib()
     from tests.srslte_ctypes import UeDl, Cell, DciMsg, RaDlDci, install_tbs_table
     si = rnti == 0xFFFF
-    cfi, tbs, mcs = (3, 296, 5) if si else (2, 2216, 9) if prb == 25 else (1, 776, 6)
+    cfi, tbs, mcs = (3, 296, 5) if si else (2, 2216, 9) if prb == 25 else (1, 776, 6) if prb == 50 else (2, 680, 7)
+    L.srsue_gpu_host_dvrb_to_prb.restype = C.c_uint32
     ocell = o.make_cell(prb, 1, 1)
     q = UeDl()
     cell = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=1, cp=0, phich_length=0, phich_resources=2)
@@ -283,18 +284,29 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
             subset = [i for i in range(prb) if (i // P) % P == p]
             prbs = [subset[i + len(subset) - n1] for i in range(n1) if i % 2 == 0]
             ln, fmt = len(prbs), 1
+        elif prb == 15:
+            # format 1A, distributed virtual resource blocks (36.211 6.2.3.2): the two slots use different PRBs
+            start, ln = tti % 4, 6
+            sent.alloc_type, sent.type2_alloc.mode = 2, 1
+            sent.type2_alloc.RB_start, sent.type2_alloc.L_crb = start, ln
+            prbs = sorted(L.srsue_gpu_host_dvrb_to_prb(prb, 0, v, 0) for v in range(start, start + ln))
+            prbs1 = sorted(L.srsue_gpu_host_dvrb_to_prb(prb, 0, v, 1) for v in range(start, start + ln))
+            assert prbs != prbs1
+            fmt = 2
         else:
             start, ln = (1, 4) if si else (tti % 5, prb - 6)
             sent.alloc_type = 2
             sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
             prbs, fmt = list(range(start, start + ln)), 2
+        if prb != 15:
+            prbs1 = prbs
         install_tbs_table(L, {(mcs, 3 if si else ln): tbs})
         m = DciMsg()
         nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), fmt, C.byref(m), prb, not si)
         assert nb > 0
         rk, _ = o.pdcch_regs(ocell, cfi, 6)
         ss = o.pdcch_search_space(len(rk) // 9, sf_idx, rnti) if not si else [(4, 0)]
-        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=2, tbs=tbs, prbs=prbs)
+        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=cfi, rnti=rnti, qm=2, tbs=tbs, prbs=prbs, prbs_slot1=prbs1)
         tb, iq, _ = o.gen_subframe(ocell, ocfg, 4000 + tti, 12.0, None, pcfich=True,
                                    dcis=[(np.frombuffer(m.data, np.uint8)[:nb].copy(), rnti, ss[0][0], ss[0][1])])
         data = np.zeros(tbs // 8, np.uint8)
@@ -302,6 +314,9 @@ def test_srslte_ue_dl_decode_finds_its_own_grant(gpu, oracle, prb, rnti):
         assert n == tbs and np.array_equal(data, tb)
         assert q.pdsch_cfg.grant.nof_prb == ln and q.pdsch_cfg.grant.mcs.idx == mcs
         assert [i for i in range(prb) if q.pdsch_cfg.grant.prb_idx[0][i]] == prbs
+        assert [i for i in range(prb) if q.pdsch_cfg.grant.prb_idx[1][i]] == prbs1
+        rc_o, pl_o, _, _ = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 1, 4)
+        assert rc_o == 0 and np.array_equal(data, pl_o)
         # a subframe without a DCI for this RNTI decodes nothing
         _, iq0, _ = o.gen_subframe(ocell, ocfg, 4100 + tti, 12.0, None, pcfich=True)
         assert L.srslte_ue_dl_decode(C.byref(q), iq0.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), tti) == 0

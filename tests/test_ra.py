@@ -128,7 +128,7 @@ def test_format1_type0_and_type1(L, n):
         assert g.mcs.tbs == t[itbs, len(exp) - 1]
 
 
-def test_retransmission_mcs_and_distributed(L):
+def test_retransmission_mcs(L):
     install_tbs_table(L, {})
     d = RaDlDci()
     d.alloc_type, d.mcs_idx = 2, 30
@@ -137,8 +137,6 @@ def test_retransmission_mcs_and_distributed(L):
     assert L.srslte_dci_msg_pack_pdsch(C.byref(d), FMT1A, C.byref(msg), 25, True) > 0
     assert L.srslte_dci_msg_to_dl_grant(C.byref(msg), 0x4601, 25, C.byref(u), C.byref(g)) == 0
     assert g.mcs.tbs == 0 and g.Qm == 4                                   # size of the first transmission: MAC's to fill
-    msg.data[1] = 1                                                       # distributed virtual resource blocks
-    assert L.srslte_dci_msg_to_dl_grant(C.byref(msg), 0x4601, 25, C.byref(u), C.byref(g)) != 0
     assert L.srsue_gpu_ra_set_tbs_table(None, 27, 110) != 0 and L.srslte_ra_tbs_from_idx(27, 1) < 0
 
 
@@ -172,3 +170,84 @@ def test_cqi_helpers(L):
     assert L.srslte_cqi_value_pack(C.byref(v), buf) == 4 and list(buf[:4]) == [1, 0, 1, 1]
     v = Cqi(1, 0, 6, 1)
     assert L.srslte_cqi_value_pack(C.byref(v), buf) == 5 and list(buf[:5]) == [0, 1, 1, 0, 1]
+
+
+def _dvrb(L, n, gap2):
+    L.srsue_gpu_host_dvrb_to_prb.restype = C.c_uint32
+    L.srsue_gpu_host_n_vrb_dl.restype = C.c_uint32
+    nv = L.srsue_gpu_host_n_vrb_dl(n, gap2)
+    return nv, [[L.srsue_gpu_host_dvrb_to_prb(n, gap2, v, s) for v in range(nv)] for s in (0, 1)]
+
+
+def test_distributed_vrb_mapping_properties(L):
+    """36.211 6.2.3.2: every distributed VRB lands on a distinct PRB inside the carrier in each slot, the two slots of a
+    VRB are one gap apart (gap 1) / half an interleaving unit apart (gap 2), consecutive VRBs are spread out, and the
+    1.4 MHz case equals the mapping worked out by hand from the interleaver (2 rows x 4 columns, 2 nulls)."""
+    gaps1 = {6: 3, 7: 4, 10: 5, 11: 4, 12: 8, 19: 8, 20: 12, 25: 12, 26: 12, 27: 18, 44: 18, 45: 27, 49: 27, 50: 27, 63: 27,
+             64: 32, 75: 32, 79: 32, 80: 48, 100: 48, 110: 48}
+    for n in range(6, 111):
+        for gap2 in ((0, 1) if n >= 50 else (0,)):
+            nv, (s0, s1) = _dvrb(L, n, gap2)
+            assert nv > 0 and nv % 2 == 0 and nv <= n
+            assert len(set(s0)) == nv and len(set(s1)) == nv and max(s0 + s1) < n
+            if not gap2:
+                g = gaps1.get(n)
+                assert nv == 2 * min(g, n - g) if g else True
+                assert all(abs(a - b) == (g if g else abs(s0[0] - s1[0])) for a, b in zip(s0, s1))
+            else:
+                g = 9 if n <= 63 else 16
+                assert nv == (n // (2 * g)) * 2 * g and all(abs(a - b) == g for a, b in zip(s0, s1))
+            assert L.srsue_gpu_host_dvrb_to_prb(n, gap2, nv, 0) == 0xFFFFFFFF
+    assert _dvrb(L, 6, 0)[1][0] == [0, 2, 3, 5, 1, 4] and _dvrb(L, 6, 0)[1][1] == [3, 5, 0, 2, 4, 1]
+    assert _dvrb(L, 25, 0)[1][0][:8] == [0, 6, 12, 18, 1, 7, 13, 19]
+    assert L.srsue_gpu_host_n_vrb_dl(25, 1) == 0                              # no second gap below 50 PRB
+
+
+@pytest.mark.parametrize("n", BWS)
+def test_format1a_distributed_round_trip(L, n):
+    install_tbs_table(L, {})
+    rng = np.random.default_rng(300 + n)
+    for k in range(60):
+        gap2 = int(n >= 50 and k % 2)
+        nv, (s0, s1) = _dvrb(L, n, gap2)
+        d = RaDlDci()
+        d.alloc_type, d.mcs_idx, d.harq_process, d.rv_idx, d.ndi = 2, int(rng.integers(0, 29)), int(rng.integers(0, 8)), 1, True
+        d.type2_alloc.mode, d.type2_alloc.n_gap = 1, gap2
+        d.type2_alloc.RB_start = int(rng.integers(0, nv))
+        lmax = nv - d.type2_alloc.RB_start
+        d.type2_alloc.L_crb = int(rng.integers(1, lmax + 1))
+        msg, u, g = DciMsg(), RaDlDci(), Grant()
+        nb = L.srslte_dci_msg_pack_pdsch(C.byref(d), FMT1A, C.byref(msg), n, True)
+        if nb < 0:
+            # with the gap flag taking the field's MSB (>= 50 PRB) not every (start, length) is expressible
+            assert n >= 50
+            continue
+        assert L.srslte_dci_msg_to_dl_grant(C.byref(msg), 0x4601, n, C.byref(u), C.byref(g)) == 0
+        assert (u.type2_alloc.mode, u.type2_alloc.n_gap, u.type2_alloc.RB_start, u.type2_alloc.L_crb) == \
+               (1, gap2, d.type2_alloc.RB_start, d.type2_alloc.L_crb)
+        vr = range(d.type2_alloc.RB_start, d.type2_alloc.RB_start + d.type2_alloc.L_crb)
+        assert [i for i in range(110) if g.prb_idx[0][i]] == sorted(s0[v] for v in vr)
+        assert [i for i in range(110) if g.prb_idx[1][i]] == sorted(s1[v] for v in vr)
+        assert g.nof_prb == d.type2_alloc.L_crb
+
+
+def test_per_slot_allocation_tables_match_oracle(L):
+    """the PDSCH resource-element list for a grant whose slots use different PRBs: library table == oracle's"""
+    import srsue_b200 as sg
+    from oracle import oracle as o
+    for prb, ports, sf, cfi in ((25, 1, 3, 2), (50, 2, 0, 1), (100, 1, 5, 3), (6, 1, 1, 3)):
+        nv, (s0, s1) = _dvrb(L, prb, 0)
+        vr = range(1, min(nv, 9))
+        a, b = [s0[v] for v in vr], [s1[v] for v in vr]
+        cell, ocell = sg.make_cell(prb, ports, 9), o.make_cell(prb, ports, 9)
+        cfg = sg.make_cfg(cell, sf_idx=sf, cfi=cfi, prbs=a, prbs_slot1=b)
+        ocfg = o.make_cfg(ocell, sf_idx=sf, cfi=cfi, prbs=a, prbs_slot1=b)
+        assert bytes(cfg.prb_mask) == bytes(ocfg.prb_mask) and set(bytes(cfg.prb_mask)) <= {0, 1, 2, 4}
+        re = np.zeros(14 * 12 * prb, np.int32)
+        n = L.srsue_gpu_host_pdsch_re(C.byref(cell), C.byref(cfg), re.ctypes.data_as(C.c_void_p))
+        ref = o.pdsch_re_list(ocell, ocfg)
+        assert n == len(ref) and np.array_equal(re[:n], ref)
+        nsc = 12 * prb
+        for idx in re[:n]:
+            l, k = divmod(int(idx), nsc)
+            assert (k // 12) in (a if l < 7 else b)
