@@ -219,7 +219,8 @@ typedef struct srsue_gpu_batch srsue_gpu_batch_t;
 typedef struct {
   srsue_gpu_cell_t cell;
   srsue_gpu_pdsch_cfg_t cfg;       /* the grant as srslte_ue_dl_cfg_grant would configure it (incl. rv) */
-  const srsue_gpu_cf_t *iq;        /* in:  one subframe of time samples (sf_len = 15*nfft), caller-owned */
+  const srsue_gpu_cf_t *iq;        /* in:  one subframe of time samples (sf_len = 15*nfft), caller-owned; int16 {re, im}
+                                    * pairs behind the same pointer after srsue_gpu_batch_set_iq_format(SC16) */
   uint8_t *payload;                /* out: tbs/8 bytes, MSB first, caller-owned */
   int64_t softbuffer_id;           /* < 0: no HARQ state (new transmission decoded from scratch);
                                     * >= 0: device-resident soft buffer of this (UE, HARQ process) id */
@@ -235,6 +236,9 @@ typedef struct {
 int srsue_gpu_batch_create(srsue_gpu_ctx_t *ctx, int max_subframes, float noise_est, int noise_mode, int max_iter,
                            srsue_gpu_batch_t **batch);
 void srsue_gpu_batch_destroy(srsue_gpu_batch_t *batch);
+/* what the `iq` pointer of every descriptor points at from the next submission on: SRSUE_GPU_IQ_CF32 (default) or
+ * SRSUE_GPU_IQ_SC16 (int16 {re, im} pairs, sample = (float)v * scale) */
+int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t *batch, int format, float scale);
 /* enqueues uploads, launches and downloads for n descriptors and returns; `descs`, the IQ and the payload
  * buffers must stay valid until srsue_gpu_batch_wait, which also fills the out fields of every descriptor */
 int srsue_gpu_batch_submit(srsue_gpu_batch_t *batch, srsue_gpu_sf_desc_t *descs, int n);

@@ -252,7 +252,7 @@ class Batch:
 
     @staticmethod
     def prepare(items):
-        """items: list of dicts {cell, cfg, iq (complex64 array), softbuffer_id (default -1), new_data (default 1),
+        """items: list of dicts {cell, cfg, iq (complex64 array; int16 pairs after set_iq_format(True)), softbuffer_id (default -1), new_data (default 1),
         payload (optional uint8 array), cfo (subcarrier spacings, default 0)} -> (descriptor array, payload arrays, items), reusable across submissions"""
         import numpy as np
         n = len(items)
@@ -269,6 +269,10 @@ class Batch:
             d.new_data = it.get("new_data", 1)
             d.cfo = it.get("cfo", 0.0)
         return descs, payloads, items
+
+    def set_iq_format(self, sc16, scale=1.0 / 32768.0):
+        """every item's iq is an int16 {re, im} array (sc16=True; sample = float(v) * scale) or complex64 (False, default)"""
+        _check(lib().srsue_gpu_batch_set_iq_format(self.h, 1 if sc16 else 0, C.c_float(scale)), "srsue_gpu_batch_set_iq_format")
 
     def submit_prepared(self, prepared):
         self._keep = prepared

@@ -96,6 +96,7 @@ struct srsue_gpu_batch {
   int32_t* d_status = nullptr; float* d_meas = nullptr;
   int16_t* d_sb = nullptr; size_t sb_elems = 0;
   int16_t** d_rows = nullptr;
+  int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what every descriptor's iq points at
   int32_t *h_cfo = nullptr, *d_cfo = nullptr;      // per-row carrier-offset phase steps of the chunk being launched
   // pinned result staging, in processing order
   int32_t* h_status = nullptr; float* h_meas = nullptr; int16_t** h_rows = nullptr;
@@ -222,6 +223,14 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   delete b;
 }
 
+int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t* b, int format, float scale) {
+  if (!b || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
+    return srsue::internal_fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
+  b->iq_format = format;
+  if (format == SRSUE_GPU_IQ_SC16) b->iq16_scale = scale;
+  return 0;
+}
+
 int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
   if (!b || !descs || n < 0 || n > b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: bad arguments (n=%d)", n);
   if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
@@ -273,8 +282,10 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
       // upload: subframes that are adjacent in host memory go up in one copy; scattered small ones are gathered
       // into pinned staging first
       int runs = 1;
-      for (int r = 1; r < m; r++) runs += descs[idx[off + r]].iq != descs[idx[off + r - 1]].iq + info.sf_len;
-      const size_t row_bytes = (size_t)info.sf_len * sizeof(srsue_gpu_cf_t);
+      // (all addresses in bytes: a sample is 8 bytes as cf32, 4 as int16 pairs)
+      const size_t row_bytes = (size_t)info.sf_len * (b->iq_format == SRSUE_GPU_IQ_SC16 ? 4 : sizeof(srsue_gpu_cf_t));
+      auto row_ptr = [&](int r) { return reinterpret_cast<const char*>(descs[idx[off + r]].iq); };
+      for (int r = 1; r < m; r++) runs += row_ptr(r) != row_ptr(r - 1) + row_bytes;
       const size_t pos_up = b->order.size();
       bool zero_copy = runs > 4;
       uintptr_t align_or = 0;
@@ -298,15 +309,15 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
         B_CU(cudaEventSynchronize(b->ev_up[h]));            // the previous upload from this staging half has finished
         rc = grow_pinned(&b->h_iq[h], &b->h_iq_elems[h], cap * info.sf_len, b->s_copy);
         if (rc) return rc;
-        for (int r = 0; r < m; r++) std::memcpy(b->h_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq, row_bytes);
+        for (int r = 0; r < m; r++) std::memcpy(reinterpret_cast<char*>(b->h_iq[h]) + (size_t)r * row_bytes, descs[idx[off + r]].iq, row_bytes);
         B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
         B_CU(cudaMemcpyAsync(b->d_iq[h], b->h_iq[h], (size_t)m * row_bytes, cudaMemcpyHostToDevice, b->s_copy));
       } else {
         B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
         for (int r = 0; r < m;) {
           int e = r + 1;
-          while (e < m && descs[idx[off + e]].iq == descs[idx[off + e - 1]].iq + info.sf_len) e++;
-          B_CU(cudaMemcpyAsync(b->d_iq[h] + (size_t)r * info.sf_len, descs[idx[off + r]].iq, (size_t)(e - r) * row_bytes,
+          while (e < m && row_ptr(e) == row_ptr(e - 1) + row_bytes) e++;
+          B_CU(cudaMemcpyAsync(reinterpret_cast<char*>(b->d_iq[h]) + (size_t)r * row_bytes, descs[idx[off + r]].iq, (size_t)(e - r) * row_bytes,
                                cudaMemcpyHostToDevice, b->s_copy));
           r = e;
         }
@@ -348,6 +359,7 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
       }
       if (any_cfo) B_CU(cudaMemcpyAsync(b->d_cfo, b->h_cfo + pos0, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, b->s_compute));
       srsue_gpu_pdsch_plan_set_cfo(pe->plan, any_cfo ? b->d_cfo : nullptr, 0);
+      srsue_gpu_pdsch_plan_set_iq_format(pe->plan, b->iq_format, b->iq16_scale);
       rc = srsue_gpu_pdsch_decode_batch(pe->plan, m, b->d_iq[h], b->noise_est, b->noise_mode, b->max_iter, mode == 2, d_sb, b->d_payload,
                                         b->d_status, b->d_meas, b->s_compute);
       srsue_gpu_pdsch_plan_set_cfo(pe->plan, nullptr, 0);

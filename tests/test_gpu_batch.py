@@ -239,3 +239,42 @@ def test_mixed_stream_with_carrier_offsets(gpu, oracle):
     with pytest.raises(sg.GpuError):
         b.submit(items[:5])
     b.close()
+
+
+def test_mixed_stream_of_int16_captures(gpu, oracle):
+    """srsue_gpu_batch_set_iq_format(SC16): every descriptor points at int16 pairs (one common scale); results equal the
+    oracle on the samples converted to float first, with and without a carrier offset, scattered and adjacent rows."""
+    sg, ctx = gpu
+    o = oracle
+    rng = np.random.default_rng(99)
+    order = [int(x) for x in rng.integers(0, len(MIX), 20)] + [4, 4, 4]
+    scale = np.float32(4.0 / 32000.0)
+    items, refs = [], []
+    for i, m in enumerate(order):
+        ocell, ocfg, cell, cfg = _pair(sg, o, MIX[m])
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 71000 + i, MIX[m][7] + 6.0)
+        n = o.lib().lteo_symbol_sz(MIX[m][0])
+        cfo = 0.0 if i % 2 == 0 else float(np.float32(rng.uniform(-0.3, 0.3)))
+        rx = iq.astype(np.complex128) * np.exp(2j * np.pi * cfo * np.arange(len(iq)) / n)
+        q16 = np.rint(rx.astype(np.complex64).view(np.float32) / scale).clip(-32768, 32767).astype(np.int16)
+        items.append(dict(cell=cell, cfg=cfg, iq=q16, cfo=cfo))
+        refs.append((ocell, ocfg, (q16.astype(np.float32) * scale).view(np.complex64), tb, o.cfo_step(cfo, n)))
+    # the last three rows adjacent in host memory (one upload)
+    blk = np.concatenate([it["iq"] for it in items[-3:]])
+    for j, it in enumerate(items[-3:]):
+        it["iq"] = blk[j * len(blk) // 3:(j + 1) * len(blk) // 3]
+    b = sg.Batch(ctx, 32)
+    b.set_iq_format(True, float(scale))
+    b.submit(items)
+    res = b.wait()
+    for r, (ocell, ocfg, x, tb, step) in zip(res, refs):
+        xr = o.cfo_correct(x, step) if step else x
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, xr, 0.01, 0, 4)
+        assert (r["crc_ok"] == 1) == (rc == 0) and np.array_equal(r["payload"], pl) and r["n_iter"] == avg
+        assert rc == 0 and np.array_equal(pl, tb)
+    b.set_iq_format(False)
+    ocell, ocfg, cell, cfg = _pair(sg, o, MIX[2])
+    tb, iq, _ = o.gen_subframe(ocell, ocfg, 72000, 30.0)
+    b.submit([dict(cell=cell, cfg=cfg, iq=iq)])
+    assert np.array_equal(b.wait()[0]["payload"], tb)
+    b.close()
