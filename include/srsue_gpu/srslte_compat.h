@@ -286,7 +286,17 @@ SRSLTE_API int srslte_tdec_run_all(srslte_tdec_t *h, int16_t *input, uint8_t *ou
 
 /* ---- cell search (ue/src/phy/phch_recv.cc:140-188) --------------------------------------------------- */
 typedef struct SRSLTE_API { uint32_t full_secs; double frac_secs; } srslte_timestamp_t;
-typedef struct SRSLTE_API { double gain; } srslte_agc_t;
+/* Automatic gain control of the synchroniser objects (phch_recv.cc:111,152,202 start it; :174,212 read the gain back).
+ * gain is what the radio callback was last given / answered, in dB as phch_recv.cc:87-90 passes it to
+ * radio::set_rx_gain_th.  Every `period` received blocks (0: every block) the mean sample power of the block is
+ * compared with `target` and the gain moved by `bandwidth` of the error in dB, inside [0, max_gain]. */
+typedef struct SRSLTE_API {
+  double gain;
+  double (*set_gain_callback)(void *, double);
+  void *handler;
+  float target, bandwidth, max_gain, last_power;
+  uint32_t period, count, nof_updates;
+} srslte_agc_t;
 typedef struct SRSLTE_API { float threshold; float em_alpha; } srslte_sync_t;
 /* subframe synchroniser (phch_recv.cc:100-113,236-258,302-334): what the callers dereference are .agc and .strack */
 typedef struct SRSLTE_API {

@@ -9,6 +9,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -70,6 +72,24 @@ struct UeDlGpu {
 
 // srsue_gpu_pdsch_cfg_t::prb_mask value of one PRB from the grant's two slot masks
 uint8_t slot_mask(bool s0, bool s1) { return (s0 && s1) ? 1 : (uint8_t)((s0 ? 2 : 0) | (s1 ? 4 : 0)); }
+
+// one received block: measure, and every `period` blocks move the radio's gain towards the target power
+void agc_process(srslte_agc_t* a, void* handler, const srsue_gpu_cf_t* x, size_t n) {
+  if (!a || !a->set_gain_callback || !x || n == 0) return;
+  if (!a->handler) a->handler = handler;
+  if (a->count++ < a->period) return;
+  a->count = 0;
+  double acc = 0.0;
+  size_t m = 0;
+  for (size_t i = 0; i < n; i += 4, m++) acc += (double)x[i].re * x[i].re + (double)x[i].im * x[i].im;    // every 4th sample
+  const double p = acc / (double)m;
+  a->last_power = (float)p;
+  if (!(p > 0.0)) return;
+  double g = a->gain + a->bandwidth * 10.0 * std::log10((double)a->target / p);
+  g = std::min((double)a->max_gain, std::max(0.0, g));
+  a->gain = a->set_gain_callback(a->handler, g);
+  a->nof_updates++;
+}
 
 int ng_x6_of(const srslte_cell_t& c) {
   switch (c.phich_resources) { case SRSLTE_PHICH_R_1_6: return 1; case SRSLTE_PHICH_R_1_2: return 3; case SRSLTE_PHICH_R_1: return 6; default: return 12; }
@@ -443,7 +463,10 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
   }
   srslte_timestamp_t ts;
   for (uint32_t f = 0; f < nf; f++)
+  {
     if (g->recv(g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+    agc_process(&q->ue_sync.agc, g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame);
+  }
   if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
   if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, 128, force, 0, g->d_res, g->stream)) return SRSLTE_ERROR;
   std::vector<srsue_gpu_sync_result_t> res(nf);
@@ -516,10 +539,16 @@ int srslte_ue_cellsearch_scan_N_id_2(srslte_ue_cellsearch_t* q, uint32_t N_id_2,
   return cellsearch_run(q, (int)N_id_2, found_cell, nullptr);
 }
 
-// automatic gain control is the radio's business here: the callback is remembered by nobody and the gain stays as set
-int srslte_ue_sync_start_agc(srslte_ue_sync_t* q, double (*)(void*, double), float init_gain_value) {
+// ---- automatic gain control (host logic; srsLTE runs srslte_agc_process on every block its synchroniser receives) --------
+int srslte_ue_sync_start_agc(srslte_ue_sync_t* q, double (*set_gain_callback)(void*, double), float init_gain_value) {
   if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
-  q->agc.gain = init_gain_value;
+  srslte_agc_t* a = &q->agc;
+  a->gain = init_gain_value;
+  a->set_gain_callback = set_gain_callback;
+  a->target = 0.1f;            // mean |x|^2: 10 dB of headroom below full scale for the OFDM peaks
+  a->bandwidth = 0.5f;
+  a->max_gain = 90.f;
+  a->count = 0; a->nof_updates = 0; a->last_power = 0.f;
   return SRSLTE_SUCCESS;
 }
 float srslte_agc_get_gain(srslte_agc_t* q) { return q ? (float)q->gain : 0.f; }
@@ -560,6 +589,7 @@ int sync_find(srslte_ue_sync_t* q, UeSyncGpu* g) {
   // slide the two-half-frame window by one half frame
   std::memmove(g->window.data(), g->window.data() + H, (size_t)H * sizeof(srsue_gpu_cf_t));
   if (g->recv(g->handler, g->window.data() + H, (uint32_t)H, &g->last_ts) < 0) return SRSLTE_ERROR;
+  agc_process(&q->agc, g->handler, g->window.data() + H, (size_t)H);
   srsue_gpu_sync_result_t r;
   if (sync_search(g, g->window.data(), g->off_pss + H + g->nfft - 1, g->off_pss, &r)) return SRSLTE_ERROR;
   const float thr = q->strack.threshold > 0.f ? q->strack.threshold : 10.f;
@@ -594,6 +624,7 @@ int sync_track(srslte_ue_sync_t* q, UeSyncGpu* g, srsue_gpu_cf_t* buf) {
   const int reuse = std::min(-shift, T);                         // we are late: the subframe began in the previous read
   if (reuse > 0) std::memcpy(buf, g->tail.data() + (T - reuse), (size_t)reuse * sizeof(srsue_gpu_cf_t));
   if (g->recv(g->handler, buf + reuse, (uint32_t)(L - reuse), &g->last_ts) < 0) return SRSLTE_ERROR;
+  agc_process(&q->agc, g->handler, buf, (size_t)L);
   std::memcpy(g->tail.data(), buf + (L - T), (size_t)T * sizeof(srsue_gpu_cf_t));
   g->sf_idx = (g->sf_idx + 1) % 10;
   g->tracked_sf += 1.0;
@@ -676,7 +707,7 @@ float srslte_ue_sync_get_sfo(srslte_ue_sync_t* q) {
   return g->tracked_sf > 0.0 ? (float)(g->drift_samples / (g->tracked_sf * 1e-3)) : 0.f;
 }
 void srslte_ue_sync_set_cfo(srslte_ue_sync_t* q, float cfo) { if (q && q->gpu) static_cast<UeSyncGpu*>(q->gpu)->cfo_mean = cfo / 15000.f; }
-void srslte_ue_sync_set_agc_period(srslte_ue_sync_t*, uint32_t) {}
+void srslte_ue_sync_set_agc_period(srslte_ue_sync_t* q, uint32_t period) { if (q) q->agc.period = period; }
 void srslte_ue_sync_decode_sss_on_track(srslte_ue_sync_t* q, bool enabled) { if (q && q->gpu) static_cast<UeSyncGpu*>(q->gpu)->sss_on_track = enabled; }
 void srslte_ue_sync_get_last_timestamp(srslte_ue_sync_t* q, srslte_timestamp_t* timestamp) {
   if (q && q->gpu && timestamp) *timestamp = static_cast<UeSyncGpu*>(q->gpu)->last_ts;
@@ -738,9 +769,11 @@ int srslte_ue_mib_sync_decode(srslte_ue_mib_sync_t* q, uint32_t max_frames_timeo
   // sliding window of two 5 ms frames: the PSS of the older one is searched, and a subframe 0 that starts in it lies
   // completely inside the window
   if (m->recv(m->handler, m->win.data() + kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+  agc_process(&q->ue_sync.agc, m->handler, m->win.data() + kHalfFrame, kHalfFrame);
   for (uint32_t f = 0; f < max_frames_timeout; f++) {
     std::memcpy(m->win.data(), m->win.data() + kHalfFrame, kHalfFrame * sizeof(srsue_gpu_cf_t));
     if (m->recv(m->handler, m->win.data() + kHalfFrame, kHalfFrame, &ts) < 0) return SRSLTE_ERROR;
+    agc_process(&q->ue_sync.agc, m->handler, m->win.data() + kHalfFrame, kHalfFrame);
     if (cudaMemcpyAsync(g->d_iq, m->win.data(), (size_t)2 * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
     // exactly one PSS period, starting at offset 832: the subframe that contains a candidate then begins inside the window
     if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, 128, (int)(q->cell_id % 3), 832, g->d_res, g->stream)) return SRSLTE_ERROR;

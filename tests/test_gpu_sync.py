@@ -9,9 +9,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+class Agc(C.Structure):
+    """srslte_agc_t of include/srsue_gpu/srslte_compat.h"""
+    _fields_ = [("gain", C.c_double), ("set_gain_callback", C.c_void_p), ("handler", C.c_void_p), ("target", C.c_float),
+                ("bandwidth", C.c_float), ("max_gain", C.c_float), ("last_power", C.c_float), ("period", C.c_uint32),
+                ("count", C.c_uint32), ("nof_updates", C.c_uint32)]
+
+
 class UeSync(C.Structure):
     """srslte_ue_sync_t of include/srsue_gpu/srslte_compat.h"""
-    _fields_ = [("agc_gain", C.c_double), ("threshold", C.c_float), ("em_alpha", C.c_float), ("gpu", C.c_void_p)]
+    _fields_ = [("agc", Agc), ("threshold", C.c_float), ("em_alpha", C.c_float), ("gpu", C.c_void_p)]
 
 
 def _half_frame(o, cell, first_sf, seed, snr, cfo, shift):
@@ -318,3 +325,62 @@ def test_cpp_driver_acquire_mode(gpu, oracle, tmp_path):
     assert len(ttis) >= 3 and all(10 * sfn0 <= t <= 10 * (sfn0 + 3) and t % 10 == 0 for t in ttis)
     last = dict(zip(lines[-1].split()[::2], lines[-1].split()[1::2]))
     assert int(last["delivered"]) == 40 and int(last["sf_errors"]) == 0 and int(last["mib_decoded"]) == len(ttis)
+
+
+def test_ue_sync_agc_closes_the_loop(gpu, oracle):
+    """srslte_ue_sync_start_agc (phch_recv.cc:111): a radio whose samples scale with the gain it was last told; the loop
+    settles the mean sample power at the target within a few blocks, keeps the synchroniser locked, honours the period
+    set at phch_recv.cc:302, and srslte_agc_get_gain reports the radio's answer."""
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import Cell
+    prb, nfft, cid = 6, 128, 77
+    sf_len = 15 * nfft
+    cell = o.make_cell(prb, 1, cid)
+    sfs = []
+    for sf in range(10):
+        cfg = o.make_cfg(cell, sf_idx=sf, cfi=3, qm=2, tbs=104, tm=1)
+        sfs.append(o.gen_subframe(cell, cfg, 800 + sf, 15.0, None, pcfich=True, sync=True)[1])
+    S = np.tile(np.concatenate(sfs), 8)
+    p_nat = float(np.mean(np.abs(S) ** 2))
+    radio = {"pos": 777, "gain": 0.0, "calls": []}
+    g_ref = 30.0                                              # the stream has its natural power at 30 dB of gain
+    RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
+    GAIN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double)
+
+    def recv(handler, data, nsamples, ts):
+        a = radio["pos"]
+        x = (S[a:a + nsamples] * np.float32(10.0 ** ((radio["gain"] - g_ref) / 20.0))).astype(np.complex64)
+        C.memmove(data, x.ctypes.data, nsamples * 8)
+        radio["pos"] = a + nsamples
+        return nsamples
+
+    def set_gain(handler, gain):
+        radio["gain"] = round(gain * 2.0) / 2.0               # the radio has 0.5 dB steps
+        radio["calls"].append(radio["gain"])
+        return radio["gain"]
+
+    cb, gcb = RECV(recv), GAIN(set_gain)
+    q = UeSync()
+    c = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=cid, cp=0, phich_length=0, phich_resources=2)
+    assert L.srslte_ue_sync_init(C.byref(q), c, cb, None) == 0
+    assert L.srslte_ue_sync_start_agc(C.byref(q), gcb, C.c_float(55.0)) == 0          # far too hot: 25 dB above natural
+    L.srslte_agc_get_gain.restype = C.c_float
+    buf = np.zeros(sf_len, np.complex64)
+    got, powers = 0, []
+    while radio["pos"] + 12 * sf_len < len(S):
+        rc = L.srslte_ue_sync_zerocopy(C.byref(q), buf.ctypes.data_as(C.c_void_p))
+        assert rc >= 0
+        if rc == 1:
+            got += 1
+            powers.append(float(np.mean(np.abs(buf) ** 2)))
+            if got == 20:
+                n_before = len(radio["calls"])
+                L.srslte_ue_sync_set_agc_period(C.byref(q), 20)
+    want = g_ref + 10.0 * np.log10(0.1 / p_nat)
+    assert got > 40 and abs(radio["gain"] - want) <= 1.0 and abs(L.srslte_agc_get_gain(C.byref(q.agc)) - radio["gain"]) < 1e-6
+    # subframes differ in content (sync signals, empty control symbols), so single subframes sit a few dB around the target
+    assert abs(10 * np.log10(np.mean(powers[10:]) / 0.1)) < 2.0 and all(abs(10 * np.log10(p / 0.1)) < 6.0 for p in powers[10:])
+    assert len(radio["calls"]) - n_before <= (got - 20) // 20 + 1 and q.agc.nof_updates == len(radio["calls"])
+    L.srslte_ue_sync_free(C.byref(q))
