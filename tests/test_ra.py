@@ -251,3 +251,28 @@ def test_per_slot_allocation_tables_match_oracle(L):
         for idx in re[:n]:
             l, k = divmod(int(idx), nsc)
             assert (k // 12) in (a if l < 7 else b)
+
+
+@pytest.mark.parametrize("n", BWS)
+def test_random_dci_bits_never_escape_the_carrier(L, n):
+    """blind decoding does produce false positives: any bit pattern must either be refused or give a grant whose PRBs lie
+    inside the carrier, with the same number of PRBs in both slots and a size from the table"""
+    t = install_tbs_table(L, {})
+    rng = np.random.default_rng(4000 + n)
+    accepted = 0
+    for fmt, size_fmt in ((FMT1A, 0), (FMT1, 1)):
+        nb = L.srsue_gpu_host_dci_format_sizeof(size_fmt, n)
+        for k in range(1500):
+            msg, u, g = DciMsg(), RaDlDci(), Grant()
+            bits = rng.integers(0, 2, nb, dtype=np.uint8)
+            C.memmove(msg.data, bits.ctypes.data, nb)
+            msg.nof_bits, msg.format = nb, fmt
+            rnti = 0x4601 if k % 3 else 0xFFFF
+            if L.srslte_dci_msg_to_dl_grant(C.byref(msg), rnti, n, C.byref(u), C.byref(g)) != 0:
+                continue
+            accepted += 1
+            s0 = [i for i in range(110) if g.prb_idx[0][i]]
+            s1 = [i for i in range(110) if g.prb_idx[1][i]]
+            assert 1 <= len(s0) == len(s1) == g.nof_prb and max(s0 + s1) < n
+            assert g.Qm in (2, 4, 6) and (g.mcs.tbs == 0 or g.mcs.tbs in t)
+    assert accepted > 500
