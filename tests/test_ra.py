@@ -276,3 +276,37 @@ def test_random_dci_bits_never_escape_the_carrier(L, n):
             assert 1 <= len(s0) == len(s1) == g.nof_prb and max(s0 + s1) < n
             assert g.Qm in (2, 4, 6) and (g.mcs.tbs == 0 or g.mcs.tbs in t)
     assert accepted > 500
+
+
+def test_distributed_vrb_closed_form_equals_block_interleaver(L):
+    """36.211 6.2.3.2 describes the mapping twice: as closed-form equations (what ra.cc implements) and as a block
+    interleaver -- VRB numbers written row by row into N_row x 4, N_null nulls in the last N_null/2 rows of the 2nd and
+    4th column, read column by column ignoring nulls; the j-th number read lands on position j of its interleaving unit,
+    the second slot is shifted by half a unit, and the upper half of a unit is lifted by N_gap - unit/2."""
+    def P_of(n):
+        return 1 if n <= 10 else 2 if n <= 26 else 3 if n <= 63 else 4
+    for n in range(6, 111):
+        for gap2 in ((0, 1) if n >= 50 else (0,)):
+            nv, (s0, s1) = _dvrb(L, n, gap2)
+            gap = abs(s0[0] - s1[0])                                  # checked against Table 6.2.3.2-1 in the test above
+            unit = 2 * gap if gap2 else nv
+            P = P_of(n)
+            n_row = -(-unit // (4 * P)) * P
+            n_null = 4 * n_row - unit
+            cells, v = {}, 0
+            for r in range(n_row):
+                for c in range(4):
+                    if c in (1, 3) and r >= n_row - n_null // 2:
+                        continue                                      # a null
+                    cells[(r, c)] = v
+                    v += 1
+            assert v == unit
+            order = [cells[(r, c)] for c in range(4) for r in range(n_row) if (r, c) in cells]
+            pos = {vrb: j for j, vrb in enumerate(order)}
+            for vrb in range(nv):
+                u, w = divmod(vrb, unit)
+                for slot, got in ((0, s0[vrb]), (1, s1[vrb])):
+                    t = pos[w] if slot == 0 else (pos[w] + unit // 2) % unit
+                    t += unit * u
+                    want = t if t < unit // 2 else t + gap - unit // 2
+                    assert got == want, (n, gap2, vrb, slot)
