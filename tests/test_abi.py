@@ -200,3 +200,25 @@ def test_host_phich_tables_match_oracle():
                     a, b = C.c_int(), C.c_int()
                     assert L.srsue_gpu_host_phich_index(prb, ng, I_lowest, n_dmrs, C.byref(a), C.byref(b)) == 0
                     assert (a.value, b.value) == o.phich_index(prb, I_lowest, n_dmrs, ng)
+
+
+def test_pdcch_quadruplet_interleaver_equals_block_description():
+    """36.211 6.8.5 / 36.212 5.1.4.2.1 as a matrix: <NULL>s in front up to a multiple of 32, written row by row, the columns
+    permuted with the pattern of Table 5.1.4-2, read column by column without the NULLs, then a cyclic shift by the cell
+    id -- an independent construction of what srsue_gpu_host_pdcch_quad_perm (and the oracle) compute in closed form."""
+    import ctypes as C
+    import numpy as np
+    import srsue_b200 as sg
+    L = sg.lib()
+    P = [1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31, 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30]
+    for m in (18, 41, 59, 87, 144, 207, 360, 789):
+        for cid in (0, 1, 77, 503):
+            rows = -(-m // 32)
+            y = [None] * (rows * 32 - m) + list(range(m))
+            mat = [y[r * 32:(r + 1) * 32] for r in range(rows)]
+            perm = [mat[r][P[c]] for c in range(32) for r in range(rows)]
+            w = [v for v in perm if v is not None]
+            want = [w[(i + cid) % m] for i in range(m)]
+            src = np.zeros(m, np.int32)
+            assert L.srsue_gpu_host_pdcch_quad_perm(m, cid, src.ctypes.data_as(C.c_void_p)) == 0
+            assert src.tolist() == want, (m, cid)

@@ -197,3 +197,98 @@ def test_avx2_build_is_bit_identical_to_portable():
             assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
     finally:
         o.select(prev)
+
+
+def test_turbo_rate_matching_order_equals_matrix_description(oracle):
+    """36.212 5.1.4.1 built literally: <NULL>-padded R x 32 matrices written row by row, columns permuted with the pattern
+    of Table 5.1.4-1 and read column by column (streams 0 and 1), the shifted permutation for stream 2, the circular
+    buffer v0 | v1/v2 interlaced, the start k0 of each redundancy version, NULLs (padding and filler bits of d0, d1)
+    skipped -- an independent construction of the closed-form read order the oracle and the GPU tables use."""
+    P = [0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30, 1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31]
+    for K, F in ((40, 0), (176, 16), (1056, 24), (3136, 56), (6144, 0)):
+        D = K + 4
+        R = -(-D // 32)
+        Kpi = 32 * R
+        nd = Kpi - D
+        streams = []
+        for i in range(3):
+            y = [None] * nd + [None if (i < 2 and k < F) else 3 * k + i for k in range(D)]
+            if i < 2:
+                mat = [y[r * 32:(r + 1) * 32] for r in range(R)]
+                streams.append([mat[r][P[c]] for c in range(32) for r in range(R)])
+            else:
+                streams.append([y[(P[k // R] + 32 * (k % R) + 1) % Kpi] for k in range(Kpi)])
+        w = list(streams[0])
+        for k in range(Kpi):
+            w += [streams[1][k], streams[2][k]]
+        Kw = 3 * Kpi
+        for rv in range(4):
+            k0 = R * (2 * -(-Kw // (8 * R)) * rv + 2)
+            want = [w[(k0 + j) % Kw] for j in range(Kw) if w[(k0 + j) % Kw] is not None]
+            assert oracle.rm_sequence(K, F, rv).tolist() == want, (K, F, rv)
+
+
+def test_turbo_encoder_equals_transfer_function(oracle):
+    """36.212 5.1.3.2 from its definition: G(D) = [1, (1 + D + D^3) / (1 + D^2 + D^3)] for both constituent encoders, the
+    second fed through the QPP interleaver, trellis termination by feeding back the register taps, and the tail multiplexing
+    of 5.1.3.2.2 -- written here as shift-register recurrences, independently of the oracle's state-machine step."""
+    o = oracle
+    rng = np.random.default_rng(8)
+
+    def rsc(bits):
+        a = [0, 0, 0]                                    # a[k-1], a[k-2], a[k-3]
+        z = []
+        for x in bits:
+            ak = x ^ a[1] ^ a[2]
+            z.append(ak ^ a[0] ^ a[2])
+            a = [ak, a[0], a[1]]
+        xt, zt = [], []
+        for _ in range(3):                               # termination: the input that makes the feedback sum zero
+            x = a[1] ^ a[2]
+            xt.append(x)
+            zt.append(0 ^ a[0] ^ a[2])
+            a = [0, a[0], a[1]]
+        assert a == [0, 0, 0]
+        return z, xt, zt
+
+    for K in (40, 512, 6144):
+        c = rng.integers(0, 2, K, dtype=np.uint8)
+        pi = o.qpp_perm(K)
+        z, x, zt = rsc(c.tolist())
+        zp, xp, zpt = rsc(c[pi].tolist())
+        d = np.zeros((K + 4, 3), np.uint8)
+        d[:K, 0], d[:K, 1], d[:K, 2] = c, z, zp
+        d[K] = [x[0], zt[0], x[1]]
+        d[K + 1] = [zt[1], x[2], zt[2]]
+        d[K + 2] = [xp[0], zpt[0], xp[1]]
+        d[K + 3] = [zpt[1], xp[2], zpt[2]]
+        assert np.array_equal(o.turbo_encode(c), d.reshape(-1)), K
+
+
+def test_dci_encoding_equals_standard_description(oracle):
+    """36.212 5.3.3.2-5.3.3.4 built literally: CRC16 with the RNTI XORed onto it (MSB first), the rate-1/3 tail-biting
+    convolutional code with generators 133, 171, 165 (octal) written as circular convolutions, the sub-block interleaver of
+    5.1.4.2.1 per stream (<NULL>s in front, column pattern of Table 5.1.4-2), the circular buffer v0 | v1 | v2 read from 0
+    without the NULLs -- an independent construction of what the oracle's PDCCH transmitter produces."""
+    o = oracle
+    rng = np.random.default_rng(21)
+    P = [1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31, 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30]
+    taps = ([0, 2, 3, 5, 6], [0, 1, 2, 3, 6], [0, 1, 2, 4, 6])          # 133, 171, 165 octal, MSB = current bit
+    for nb, rnti, E in ((21, 0x4601, 72), (27, 0xFFFF, 144), (39, 0x0003, 288), (31, 0x1234, 576)):
+        a = rng.integers(0, 2, nb, dtype=np.uint8)
+        crc = o.crc_bits(a, o.CRC16, 16) ^ rnti
+        c = a.tolist() + [(crc >> (15 - i)) & 1 for i in range(16)]
+        K = len(c)
+        streams = [[0] * K for _ in range(3)]
+        for i, t in enumerate(taps):
+            for k in range(K):
+                streams[i][k] = sum(c[(k - j) % K] for j in t) & 1
+        R = -(-K // 32)
+        v = []
+        for i in range(3):
+            y = [None] * (32 * R - K) + streams[i]
+            mat = [y[r * 32:(r + 1) * 32] for r in range(R)]
+            v += [mat[r][P[col]] for col in range(32) for r in range(R)]
+        w = [x for x in v if x is not None]                             # reading skips the NULLs, so drop them up front
+        want = [w[k % len(w)] for k in range(E)]
+        assert o.dci_encode(a, rnti, E).tolist() == want, (nb, rnti, E)
