@@ -222,3 +222,53 @@ def test_pdcch_quadruplet_interleaver_equals_block_description():
             src = np.zeros(m, np.int32)
             assert L.srsue_gpu_host_pdcch_quad_perm(m, cid, src.ctypes.data_as(C.c_void_p)) == 0
             assert src.tolist() == want, (m, cid)
+
+
+def test_control_mappings_equal_standard_formulas():
+    """36.211 literally: PCFICH quadruplet i sits in the REG that starts at k = k_bar + floor(i N_RB / 2) * 6 with
+    k_bar = 6 (N_ID mod 2 N_RB) (6.7.4); PHICH group m', quadruplet i sits in the free REG number
+    (N_ID + m' + floor(i n_0 / 3)) mod n_0 of symbol 0, n_0 = REGs not taken by the PCFICH (6.9.3, normal duration);
+    the PDCCH search space is L {(Y_k + m) mod floor(N_CCE / L)} + i with Y_k = 39827 Y_{k-1} mod 65537, Y_{-1} = RNTI (36.213 9.1.1)."""
+    import ctypes as C
+    import numpy as np
+    import srsue_b200 as sg
+    L = sg.lib()
+    for prb in (6, 15, 25, 50, 75, 100):
+        nsc = 12 * prb
+        for cid in (0, 3, 77, 150, 503):
+            cell = sg.make_cell(prb, 2, cid)
+            k = np.zeros(16, np.int32)
+            assert L.srsue_gpu_host_pcfich_re(C.byref(cell), k.ctypes.data_as(C.c_void_p)) == 0
+            kbar = 6 * (cid % (2 * prb))
+            want, pc_regs = [], []
+            for i in range(4):
+                k0 = (kbar + (i * prb // 2) * 6) % nsc
+                pc_regs.append(k0 // 6)
+                want += [k0 + j for j in range(6) if (k0 + j) % 3 != cid % 3]
+            assert k.tolist() == want
+            free = [r for r in range(2 * prb) if r not in pc_regs]
+            for g in range(-(-(12 * prb) // 48)):                         # ceil(Ng (N_RB / 8)) groups at the largest Ng = 2
+                k12 = np.zeros(12, np.int32)
+                assert L.srsue_gpu_host_phich_res(C.byref(cell), g, k12.ctypes.data_as(C.c_void_p)) == 0
+                exp = []
+                for i in range(3):
+                    k0 = 6 * free[(cid + g + (i * len(free)) // 3) % len(free)]
+                    exp += [k0 + j for j in range(6) if (k0 + j) % 3 != cid % 3]
+                assert k12.tolist() == exp, (prb, cid, g)
+    for ncce in (6, 12, 21, 41, 87):
+        for rnti in (0x0001, 0x4601, 0xFFF3):
+            for sf in range(10):
+                y = rnti
+                for _ in range(sf + 1):
+                    y = (39827 * y) % 65537
+                for common in (0, 1):
+                    exp = []
+                    for Lc, M in (((4, 4), (8, 2)) if common else ((1, 6), (2, 6), (4, 2), (8, 2))):
+                        if ncce // Lc == 0:
+                            continue
+                        for m in range(M):
+                            exp.append((Lc, Lc * (((0 if common else y) + m) % (ncce // Lc))))
+                    cl, cn = np.zeros(32, np.int32), np.zeros(32, np.int32)
+                    n = L.srsue_gpu_host_pdcch_search_space(ncce, sf, rnti, common, cl.ctypes.data_as(C.c_void_p), cn.ctypes.data_as(C.c_void_p))
+                    got = list(zip(cl[:n].tolist(), cn[:n].tolist()))
+                    assert sorted(set(got)) == sorted(set(exp)), (ncce, rnti, sf, common)
