@@ -292,3 +292,44 @@ def test_dci_encoding_equals_standard_description(oracle):
         w = [x for x in v if x is not None]                             # reading skips the NULLs, so drop them up front
         want = [w[k % len(w)] for k in range(E)]
         assert o.dci_encode(a, rnti, E).tolist() == want, (nb, rnti, E)
+
+
+def test_sync_sequences_equal_standard_definition(oracle):
+    """36.211 6.11 literally: PSS Zadoff-Chu roots 25/29/34; SSS from the three m-sequences, (m0, m1) taken from the block
+    structure of Table 6.11.2.1-1 (differences 1..7 with 30, 29, ... entries; last row 167 -> (2, 9)) rather than from the
+    closed form the oracle uses."""
+    import ctypes as C
+    lib = oracle.lib()
+
+    def mseq(taps):
+        x = [0, 0, 0, 0, 1]
+        for i in range(26):
+            x.append(sum(x[i + t] for t in taps) % 2)
+        return [1 - 2 * v for v in x]
+
+    s_t, c_t, z_t = mseq((2, 0)), mseq((3, 0)), mseq((4, 2, 1, 0))
+    pairs = [(m0, m0 + d) for d in range(1, 8) for m0 in range(31 - d)][:168]
+    assert pairs[0] == (0, 1) and pairs[29] == (29, 30) and pairs[30] == (0, 2) and pairs[167] == (2, 9)
+    got = np.zeros(62, np.int8)
+    for n1 in range(168):
+        m0, m1 = pairs[n1]
+        for n2 in range(3):
+            for sf5 in (0, 1):
+                a, b = (m0, m1) if sf5 == 0 else (m1, m0)
+                want = []
+                for n in range(31):
+                    c0, c1 = c_t[(n + n2) % 31], c_t[(n + n2 + 3) % 31]
+                    want.append(s_t[(n + a) % 31] * c0)
+                    want.append(s_t[(n + b) % 31] * c1 * z_t[(n + (a % 8)) % 31])
+                lib.lteo_sss_seq(n1, n2, sf5, got.ctypes.data_as(C.c_void_p))
+                assert got.tolist() == want, (n1, n2, sf5)
+    t = np.zeros(128, np.complex64)
+    for n2, u in enumerate((25, 29, 34)):
+        lib.lteo_pss_time(n2, t.ctypes.data_as(C.c_void_p))
+        n = np.arange(62)
+        d = np.where(n < 31, np.exp(-1j * np.pi * u * n * (n + 1) / 63), np.exp(-1j * np.pi * u * (n + 1) * (n + 2) / 63))
+        X = np.zeros(128, np.complex128)
+        X[128 - 31:] = d[:31]                                  # subcarriers -31 .. -1
+        X[1:32] = d[31:]                                       # subcarriers +1 .. +31, DC empty
+        ref = np.fft.ifft(X) * 128 / np.sqrt(128)
+        assert np.max(np.abs(t - ref)) < 1e-6
