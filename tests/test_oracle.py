@@ -333,3 +333,92 @@ def test_sync_sequences_equal_standard_definition(oracle):
         X[1:32] = d[31:]                                       # subcarriers +1 .. +31, DC empty
         ref = np.fft.ifft(X) * 128 / np.sqrt(128)
         assert np.max(np.abs(t - ref)) < 1e-6
+
+
+def test_cell_reference_signal_equals_standard_definition(oracle):
+    """36.211 6.10.1 literally: r(m) from the Gold sequence with c_init = 2^10 (7 (n_s + 1) + l + 1)(2 N_ID + 1) + 2 N_ID + 1
+    (normal CP), the centred window m' = m + 110 - N_RB, and k = 6 m + (v + N_ID mod 6) mod 6 with v = 0 / 3 for port 0 at
+    l = 0 / 4 and the opposite for port 1."""
+    import ctypes as C
+    lib = oracle.lib()
+    for prb, cid in ((6, 0), (25, 77), (100, 503)):
+        for ports in (1, 2):
+            cell = oracle.make_cell(prb, ports, cid)
+            for sf in (0, 3, 9):
+                for l in (0, 4, 7, 11):
+                    ns, ls = 2 * sf + l // 7, l % 7
+                    c_init = (1 << 10) * (7 * (ns + 1) + ls + 1) * (2 * cid + 1) + 2 * cid + 1
+                    c = oracle.gold(c_init, 440)
+                    re, im = np.zeros(2 * prb, np.int8), np.zeros(2 * prb, np.int8)
+                    lib.lteo_crs_values(C.byref(cell), sf, l, re.ctypes.data_as(C.c_void_p), im.ctypes.data_as(C.c_void_p))
+                    mp = np.arange(2 * prb) + 110 - prb
+                    assert np.array_equal(re, 1 - 2 * c[2 * mp].astype(np.int8)) and np.array_equal(im, 1 - 2 * c[2 * mp + 1].astype(np.int8))
+                    for port in range(ports):
+                        k = np.zeros(2 * prb, np.int32)
+                        n = lib.lteo_crs_positions(C.byref(cell), port, l, k.ctypes.data_as(C.c_void_p))
+                        v = (0 if ls == 0 else 3) if port == 0 else (3 if ls == 0 else 0)
+                        assert n == 2 * prb and k.tolist() == [6 * m + (v + cid % 6) % 6 for m in range(2 * prb)]
+
+
+def test_pdsch_bit_chain_equals_standard_description(oracle):
+    """36.212 5.1.1-5.1.5 + 36.211 6.3.1 for a whole transport block, written out in numpy: CRC24A, segmentation (B', K+, K-,
+    C+, C-, F filler bits in front of the first block), CRC24B per block when C > 1, turbo coding, rate matching with the
+    E_r split of 5.1.4.1.2 (G' = G / (N_L Q_m), gamma = G' mod C), concatenation, scrambling with
+    c_init = n_RNTI 2^14 + floor(n_s / 2) 2^9 + N_ID.  The turbo encoder and the rate-matching order have their own
+    independent constructions above; here they are used as given."""
+    import ctypes as C
+    o = oracle
+    lib = o.lib()
+    Ks = o.qpp_Ks()
+    rng = np.random.default_rng(33)
+    for prb, ports, qm, tbs, tm, rv, sf in ((6, 1, 2, 152, 1, 0, 1), (50, 2, 4, 6208, 2, 0, 4), (100, 1, 6, 75376, 1, 0, 1),
+                                             (25, 1, 6, 11448, 1, 2, 0), (75, 1, 6, 55056, 1, 3, 7)):
+        cell = o.make_cell(prb, ports, 21)
+        cfg = o.make_cfg(cell, sf_idx=sf, cfi=1, rnti=0x3A7B, qm=qm, tbs=tbs, rv=rv, tm=tm)
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        G = len(o.pdsch_re_list(cell, cfg)) * qm
+        e = np.zeros(G, np.uint8)
+        g_out = C.c_int()
+        assert lib.lteo_pdsch_encode_bits(C.byref(cell), C.byref(cfg), tb.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                          C.byref(g_out)) == 0 and g_out.value == G
+        # --- the standard, step by step
+        a = np.unpackbits(tb)
+        crc = o.crc_bits(a, o.CRC24A)
+        b = np.concatenate([a, [(crc >> (23 - i)) & 1 for i in range(24)]]).astype(np.uint8)
+        B, Z = len(b), 6144
+        if B <= Z:
+            L, Cn, Bp = 0, 1, B
+        else:
+            L, Cn = 24, -(-B // (Z - 24))
+            Bp = B + Cn * 24
+        Kp = min(k for k in Ks if Cn * k >= Bp)
+        if Cn == 1:
+            Cp, Km, Cm = 1, 0, 0
+        else:
+            Km = max(k for k in Ks if k < Kp)
+            Cm = (Cn * Kp - Bp) // (Kp - Km)
+            Cp = Cn - Cm
+        F = Cp * Kp + Cm * Km - Bp
+        nl = 2 if tm == 2 else 1
+        Gp = G // (nl * qm)
+        gamma = Gp % Cn
+        out, rp = [], 0
+        for r in range(Cn):
+            K = Km if r < Cm else Kp
+            cb = np.zeros(K, np.uint8)
+            nfill = F if r == 0 else 0
+            take = K - L - nfill
+            cb[nfill:nfill + take] = b[rp:rp + take]
+            rp += take
+            if L:
+                c24 = o.crc_bits(cb[:K - L], o.CRC24B)
+                cb[K - L:] = [(c24 >> (23 - i)) & 1 for i in range(24)]
+            d = o.turbo_encode(cb)
+            seq = o.rm_sequence(K, nfill, rv)
+            E = nl * qm * (Gp // Cn) if r <= Cn - gamma - 1 else nl * qm * -(-Gp // Cn)
+            out.append(d[seq[np.arange(E) % len(seq)]])
+        assert rp == B
+        bits = np.concatenate(out)
+        c_init = (0x3A7B << 14) + (sf << 9) + 21
+        want = bits ^ o.gold(c_init, len(bits))
+        assert len(want) == G and np.array_equal(e, want), (prb, tbs)
