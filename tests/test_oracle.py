@@ -422,3 +422,52 @@ def test_pdsch_bit_chain_equals_standard_description(oracle):
         c_init = (0x3A7B << 14) + (sf << 9) + 21
         want = bits ^ o.gold(c_init, len(bits))
         assert len(want) == G and np.array_equal(e, want), (prb, tbs)
+
+
+def test_modulation_and_transmit_diversity_equal_standard_description(oracle):
+    """36.211 7.1 (QPSK / 16QAM / 64QAM tables as their closed forms), 6.3.3.3 + 6.3.4.3 (two-port transmit diversity:
+    y0(2i) = x0(i), y0(2i+1) = x1(i), y1(2i) = -conj(x1(i)), y1(2i+1) = conj(x0(i)), all over sqrt 2) and 6.3.5 (mapping in
+    the RE order) against the grid the oracle's transmitter builds, and the CRS it puts around the data."""
+    import ctypes as C
+    o = oracle
+    lib = o.lib()
+    rng = np.random.default_rng(35)
+    for prb, ports, qm, tbs, tm, sf in ((6, 1, 2, 152, 1, 1), (25, 1, 4, 4968, 1, 3), (50, 1, 6, 30576, 1, 5), (25, 2, 4, 4968, 2, 2),
+                                        (100, 2, 6, 46888, 2, 0)):
+        cell = o.make_cell(prb, ports, 31)
+        cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, rnti=0x0ABC, qm=qm, tbs=tbs, tm=tm)
+        tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        re = o.pdsch_re_list(cell, cfg)
+        G = len(re) * qm
+        e = np.zeros(G, np.uint8)
+        g_out = C.c_int()
+        assert lib.lteo_pdsch_encode_bits(C.byref(cell), C.byref(cfg), tb.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                          C.byref(g_out)) == 0
+        b = (1 - 2 * e.astype(np.float64)).reshape(-1, qm)           # 1 - 2 b_i
+        if qm == 2:
+            d = (b[:, 0] + 1j * b[:, 1]) / np.sqrt(2)
+        elif qm == 4:
+            d = (b[:, 0] * (2 - b[:, 2]) + 1j * b[:, 1] * (2 - b[:, 3])) / np.sqrt(10)
+        else:
+            d = (b[:, 0] * (4 - b[:, 2] * (2 - b[:, 4])) + 1j * b[:, 1] * (4 - b[:, 3] * (2 - b[:, 5]))) / np.sqrt(42)
+        grid = o.pdsch_tx_grid(cell, cfg, tb).reshape(ports, -1)
+        if tm == 1:
+            assert np.allclose(grid[0][re], d, atol=1e-12)
+        else:
+            x0, x1 = d[0::2], d[1::2]
+            y0 = np.empty(len(d), np.complex128)
+            y1 = np.empty(len(d), np.complex128)
+            y0[0::2], y0[1::2] = x0, x1
+            y1[0::2], y1[1::2] = -np.conj(x1), np.conj(x0)
+            assert np.allclose(grid[0][re], y0 / np.sqrt(2), atol=1e-12) and np.allclose(grid[1][re], y1 / np.sqrt(2), atol=1e-12)
+        # reference signals: unit-power QPSK on the CRS positions of each port, nothing on the other port's positions
+        nsc = 12 * prb
+        for port in range(ports):
+            for l in (0, 4, 7, 11):
+                k = np.zeros(2 * prb, np.int32)
+                lib.lteo_crs_positions(C.byref(cell), port, l, k.ctypes.data_as(C.c_void_p))
+                sr, si = np.zeros(2 * prb, np.int8), np.zeros(2 * prb, np.int8)
+                lib.lteo_crs_values(C.byref(cell), sf, l, sr.ctypes.data_as(C.c_void_p), si.ctypes.data_as(C.c_void_p))
+                assert np.allclose(grid[port][l * nsc + k], (sr + 1j * si) / np.sqrt(2), atol=1e-12)
+                if ports == 2:
+                    assert np.all(grid[1 - port][l * nsc + k] == 0)
