@@ -471,3 +471,70 @@ def test_modulation_and_transmit_diversity_equal_standard_description(oracle):
                 assert np.allclose(grid[port][l * nsc + k], (sr + 1j * si) / np.sqrt(2), atol=1e-12)
                 if ports == 2:
                     assert np.all(grid[1 - port][l * nsc + k] == 0)
+
+
+def test_pcfich_transmission_equals_standard_description(oracle):
+    """36.212 5.3.4 (CFI code words '011', '101', '110' repeated to 32 bits), 36.211 6.7.1 scrambling with
+    c_init = (floor(n_s/2) + 1)(2 N_ID + 1) 2^9 + N_ID, QPSK, and the 16 resource elements of 6.7.4 (single port)."""
+    import ctypes as C
+    o = oracle
+    lib = o.lib()
+    words = {1: [0, 1, 1], 2: [1, 0, 1], 3: [1, 1, 0]}
+    for prb, cid, sf in ((6, 0, 0), (25, 77, 3), (100, 503, 9)):
+        cell = o.make_cell(prb, 1, cid)
+        k16 = o.pcfich_re(cell)
+        for cfi in (1, 2, 3):
+            grid = np.zeros((1, 14, 12 * prb), np.complex128)
+            lib.lteo_pcfich_tx(C.byref(cell), sf, cfi, grid.ctypes.data_as(C.c_void_p))
+            b = np.array([words[cfi][i % 3] for i in range(32)], np.uint8) ^ o.gold((sf + 1) * (2 * cid + 1) * 512 + cid, 32)
+            d = ((1 - 2.0 * b[0::2]) + 1j * (1 - 2.0 * b[1::2])) / np.sqrt(2)
+            assert np.allclose(grid[0, 0, k16], d, atol=1e-12)
+            assert np.count_nonzero(grid) == 16
+
+
+def test_phich_and_pbch_transmission_equal_standard_description(oracle):
+    """PHICH (36.212 5.3.5, 36.211 6.9.1-6.9.3, single port): HI repeated three times, BPSK, spread with the orthogonal
+    sequence of Table 6.9.1-2, cell-specific scrambling, three quadruplets on the group's REGs.  PBCH (36.212 5.3.1,
+    36.211 6.6): 24 MIB bits + CRC16 XOR the antenna mask, tail-biting code, rate matching to 1920 bits, scrambling with
+    c_init = N_ID, QPSK, the quarter of the frame on the 240 resource elements of slot 1."""
+    import ctypes as C
+    o = oracle
+    lib = o.lib()
+    W = [[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1], [1j, 1j, 1j, 1j], [1j, -1j, 1j, -1j], [1j, 1j, -1j, -1j],
+         [1j, -1j, -1j, 1j]]
+    for prb, cid, sf in ((6, 5, 0), (25, 77, 3), (100, 503, 8)):
+        cell = o.make_cell(prb, 1, cid)
+        for ng_x6 in (1, 6, 12):
+            g = lib.lteo_phich_groups(prb, ng_x6) - 1
+            k12 = o.phich_res(cell, g, ng_x6)
+            c = o.gold((sf + 1) * (2 * cid + 1) * 512 + cid, 12)
+            for seq in (0, 3, 5, 7):
+                for ack in (0, 1):
+                    grid = np.zeros((1, 14, 12 * prb), np.complex128)
+                    lib.lteo_phich_tx(C.byref(cell), sf, ng_x6, g, seq, ack, grid.ctypes.data_as(C.c_void_p))
+                    z = (1 - 2 * ack) * (1 + 1j) / np.sqrt(2)                # BPSK of the repeated indicator
+                    d = np.array([W[seq][i % 4] * (1 - 2 * int(c[i])) * z for i in range(12)])
+                    assert np.allclose(grid[0, 0, k12], d, atol=1e-12) and np.count_nonzero(grid) == 12
+    P = [1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31, 0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30]
+    taps = ([0, 2, 3, 5, 6], [0, 1, 2, 3, 6], [0, 1, 2, 4, 6])
+    for prb, cid in ((6, 9), (50, 301)):
+        cell = o.make_cell(prb, 1, cid)
+        g240 = np.zeros(240, np.int32)
+        lib.lteo_pbch_res(C.byref(cell), g240.ctypes.data_as(C.c_void_p))
+        mib = o.mib_pack(prb, 0, 6, 516)
+        crc = o.crc_bits(mib, o.CRC16, 16) ^ 0x0000                          # one antenna port: mask 0
+        cbits = mib.tolist() + [(crc >> (15 - i)) & 1 for i in range(16)]
+        K = 40
+        v = []
+        for t in taps:
+            y = [None] * (64 - K) + [sum(cbits[(k - j) % K] for j in t) & 1 for k in range(K)]
+            mat = [y[r * 32:(r + 1) * 32] for r in range(2)]
+            v += [mat[r][P[col]] for col in range(32) for r in range(2)]
+        w = [x for x in v if x is not None]
+        e = np.array([w[k % 120] for k in range(1920)], np.uint8) ^ o.gold(cid, 1920)
+        for q in range(4):
+            grid = np.zeros((1, 14, 12 * prb), np.complex128)
+            lib.lteo_pbch_tx(C.byref(cell), mib.ctypes.data_as(C.c_void_p), q, grid.ctypes.data_as(C.c_void_p))
+            b = e[480 * q:480 * (q + 1)]
+            d = ((1 - 2.0 * b[0::2]) + 1j * (1 - 2.0 * b[1::2])) / np.sqrt(2)
+            assert np.allclose(grid.reshape(-1)[g240], d, atol=1e-12) and np.count_nonzero(grid) == 240
