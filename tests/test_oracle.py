@@ -538,3 +538,29 @@ def test_phich_and_pbch_transmission_equal_standard_description(oracle):
             b = e[480 * q:480 * (q + 1)]
             d = ((1 - 2.0 * b[0::2]) + 1j * (1 - 2.0 * b[1::2])) / np.sqrt(2)
             assert np.allclose(grid.reshape(-1)[g240], d, atol=1e-12) and np.count_nonzero(grid) == 240
+
+
+def test_pdcch_reg_order_equals_standard_description(oracle):
+    """36.211 6.8.5 step 10 literally: walk k' upwards and, for each k', l' = 0 .. L-1; wherever (k', l') starts a
+    resource-element group (6 subcarriers in symbols with cell-specific reference signals, 4 elsewhere) that is not taken
+    by the PCFICH or a PHICH group, it receives the next quadruplet."""
+    import ctypes as C
+    o = oracle
+    lib = o.lib()
+    for prb, ports, cid in ((6, 1, 3), (25, 2, 77), (100, 1, 301)):
+        cell = o.make_cell(prb, ports, cid)
+        pc = {int(k) // 6 * 6 for k in o.pcfich_re(cell)[::4]}
+        for cfi in (1, 2, 3):
+            nsym = cfi + (1 if prb <= 10 else 0)
+            for ng_x6 in (1, 6, 12):
+                taken = {(k, 0) for k in pc}
+                for g in range(lib.lteo_phich_groups(prb, ng_x6)):
+                    taken |= {(int(k) // 6 * 6, 0) for k in o.phich_res(cell, g, ng_x6)[::4]}
+                want = []
+                for k in range(12 * prb):
+                    for l in range(nsym):
+                        size = 6 if l == 0 else 4                      # up to two antenna ports: only symbol 0 carries CRS
+                        if k % size == 0 and (k, l) not in taken:
+                            want.append((k, l))
+                rk, rl = o.pdcch_regs(cell, cfi, ng_x6)
+                assert list(zip(rk.tolist(), rl.tolist())) == want, (prb, cfi, ng_x6)
