@@ -564,3 +564,35 @@ def test_pdcch_reg_order_equals_standard_description(oracle):
                             want.append((k, l))
                 rk, rl = o.pdcch_regs(cell, cfi, ng_x6)
                 assert list(zip(rk.tolist(), rl.tolist())) == want, (prb, cfi, ng_x6)
+
+
+def test_pdcch_transmission_equals_standard_description(oracle):
+    """36.211 6.8.2-6.8.5 for a whole control region (one port): the coded DCIs at bit 72 n_CCE of the multiplexed block,
+    <NIL> elsewhere, scrambling with c_init = floor(n_s/2) 2^9 + N_ID over the whole block, QPSK, quadruplets permuted
+    (interleaver + cyclic shift by N_ID) and written to the REGs in mapping order, four data REs per REG."""
+    o = oracle
+    rng = np.random.default_rng(41)
+    for prb, cid, sf, cfi in ((6, 3, 2, 3), (25, 77, 0, 2), (50, 301, 9, 1)):
+        cell = o.make_cell(prb, 1, cid)
+        rk, rl = o.pdcch_regs(cell, cfi, 6)
+        n_reg = len(rk)
+        n_cce = n_reg // 9
+        dcis = []
+        for L, ncce, nb, rnti in ((1, 0, 25, 0x0101), (2, 2, 27, 0x4601), (4, 4, 21, 0xFFFF)):
+            if ncce + L <= n_cce:
+                dcis.append((rng.integers(0, 2, nb, dtype=np.uint8), rnti, L, ncce))
+        grid = np.zeros((1, 14, 12 * prb), np.complex128)
+        assert o.pdcch_tx(cell, sf, cfi, dcis, grid, 6) == n_cce
+        c = o.gold(sf * 512 + cid, 8 * n_reg)
+        sym = np.zeros(4 * n_reg, np.complex128)                           # <NIL> elements transmit nothing
+        for bits, rnti, L, ncce in dcis:
+            e = o.dci_encode(bits, rnti, 72 * L) ^ c[72 * ncce:72 * (ncce + L)]
+            sym[36 * ncce:36 * (ncce + L)] = ((1 - 2.0 * e[0::2]) + 1j * (1 - 2.0 * e[1::2])) / np.sqrt(2)
+        src = o.pdcch_quad_perm(n_reg, cid)
+        want = np.zeros_like(grid)
+        for j in range(n_reg):
+            size = 6 if rl[j] == 0 else 4
+            ks = [k for k in range(rk[j], rk[j] + size) if not (rl[j] == 0 and k % 3 == cid % 3)]
+            assert len(ks) == 4
+            want[0, rl[j], ks] = sym[4 * src[j]:4 * src[j] + 4]
+        assert np.allclose(grid, want, atol=1e-12)
