@@ -112,7 +112,7 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   TurboTables t;
   t.g = turbo_geom(K);
   std::vector<uint16_t> pos;
-  turbo_perm_pos(t.g, pos);
+  turbo_perm_table(t.g, pos);
   CU_CHECK(upload(&t.d_perm, pos));
   const uint32_t polys[2] = {kCrc24A, kCrc24B};
   for (int i = 0; i < 2; i++) {
@@ -134,24 +134,40 @@ int turbo_slot_words(const TurboGeom& g) {
   return base + ((g.T - base) % 32 + 32) % 32;
 }
 
+// stride of the position-table rows in shared memory (template parameter of the kernels)
+int turbo_perm_stride(const TurboGeom& g) { return g.T <= 32 ? 32 : 64; }
+
 // CTAs per SM of the persistent decoder.  Two independent CTAs per SM drift out of phase, which spreads the
 // L2 demand of the load-dominated backward sweeps and halves the width of every barrier.
 int turbo_ctas_per_sm() {
   static const int v = [] {
     const char* e = getenv("SRSUE_TURBO_CTAS_PER_SM");
-    return e ? std::max(1, std::min(4, atoi(e))) : 2;
+    return e ? std::max(1, std::min(4, atoi(e))) : 0;        // 0: choose per code-block size (turbo_launch_cfg)
   }();
   return v;
 }
 
+// Shared memory of one decoder CTA with ncb slots: position table, flags, per slot the exchange array and the decision
+// bits of the current iteration (one per trellis step), per thread six 16-byte staging chunks and a scratch word
+int turbo_smem_bytes(const TurboGeom& g, int ncb) {
+  const int threads = ((ncb * g.T + 31) / 32) * 32;
+  const int slot_bytes = turbo_slot_words(g) * 4 + (g.W / 8) * g.T * 2;
+  return g.W * turbo_perm_stride(g) * 4 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes + 16 + threads * 100;
+}
+
 TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb, bool crc) {
-  const int per_sm = turbo_ctas_per_sm();
-  const int slot_bytes = turbo_slot_words(g) * 4;
   (void)crc;
-  const int fixed = g.plane * 2 + 96;                               // position table + flags
-  const int smem_budget = (ctx->smem_sm - per_sm * 1024) / per_sm;  // 1 KB per CTA is reserved by the driver
-  int ncb = (std::min(smem_budget, ctx->smem_optin) - fixed) / (slot_bytes + 8);
-  ncb = std::min(ncb, (kTurboMaxThreads / per_sm) / g.T);
+  // CTAs per SM: whichever of 1 and 2 keeps more code-block slots resident (1 KB per CTA is reserved by the driver);
+  // SRSUE_TURBO_CTAS_PER_SM overrides
+  auto slots_for = [&](int per_sm) {
+    const int budget = std::min((ctx->smem_sm - per_sm * 1024) / per_sm, ctx->smem_optin);
+    int ncb = std::min(kTurboMaxThreads / per_sm, 1024) / g.T;
+    while (ncb > 0 && turbo_smem_bytes(g, ncb) > budget) ncb--;
+    return ncb;
+  };
+  int per_sm = turbo_ctas_per_sm();
+  if (per_sm == 0) per_sm = (2 * slots_for(2) >= slots_for(1)) ? 2 : 1;
+  int ncb = slots_for(per_sm);
   if (const char* e = getenv("SRSUE_TURBO_MAX_SLOTS")) ncb = std::min(ncb, std::max(1, atoi(e)));   // tuning knob
   // spread small batches over all SMs rather than filling a few CTAs
   ncb = std::min(ncb, std::max(1, (n_cb + ctx->num_sms * per_sm - 1) / (ctx->num_sms * per_sm)));
@@ -160,7 +176,7 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   c.ncb = ncb;
   c.threads = ((ncb * g.T + 31) / 32) * 32;
   c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms * per_sm);
-  c.smem = g.plane * 2 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes;
+  c.smem = turbo_smem_bytes(g, ncb);
   return c;
 }
 
@@ -182,35 +198,36 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   const TurboGeom& g = tt->g;
   const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb, crc_type != 0);
   const size_t slots = (size_t)lc.grid * lc.ncb;
-  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), slots * (size_t)g.plane * 2, 0);
+  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), 0, 0);
   if (rc) return rc;
   const size_t ckpt_bytes = slots * (size_t)(g.W / 8) * g.T * 32;
   if (ckpt_bytes > scr.ckpt_bytes) { cudaFree(scr.ckpt); CU_CHECK(cudaMalloc((void**)&scr.ckpt, ckpt_bytes)); scr.ckpt_bytes = ckpt_bytes; }
   if (!ctx->attr_set) {
     CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     CU_CHECK(cudaFuncSetAttribute(turbo_decode_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    CU_CHECK(cudaFuncSetAttribute(turbo_decode_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    CU_CHECK(cudaFuncSetAttribute(turbo_decode_crc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     ctx->attr_set = true;
   }
   TurboArgs a{};
   a.in = d_in; a.in_stride = in_stride; a.cb_list = d_cb_list; a.n_cb = n_cb;
   a.out_bits = d_bits; a.out_stride = out_stride; a.out_status = d_status;
   a.max_iter = max_iter; a.crc_type = crc_type;
-  a.crc_poly = (crc_type == 2) ? kCrc24B : kCrc24A;
   a.K = g.K; a.W = g.W; a.P = g.P; a.Ppad = g.Ppad; a.T = g.T; a.plane = g.plane;
-  a.perm_pos = tt->d_perm;
-  a.crc_tpos = tt->d_tpos[crc_type == 2 ? 1 : 0];
+  a.perm_tab = tt->d_perm;
+  a.crc_lin = tt->d_tpos[crc_type == 2 ? 1 : 0];
   a.ncb_cta = lc.ncb;
   a.slot_words = turbo_slot_words(g);
-  a.nii = scr.nii;
-  a.bits_scratch = scr.bits;
+  a.nii = reinterpret_cast<uint4*>(scr.nii);
   a.ckpt = scr.ckpt;
   if (!scr.counter) CU_CHECK(cudaMalloc((void**)&scr.counter, 256));
   // work counter of the persistent slots: the first grid * ncb code blocks are assigned statically
   CU_CHECK(cudaMemsetAsync(scr.counter, 0, sizeof(int), st));
   a.work_counter = scr.counter;
   a.work_base = lc.grid * lc.ncb;
-  if (crc_type) turbo_decode_crc_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
-  else turbo_decode_kernel<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  const bool wide = turbo_perm_stride(g) == 64;
+  if (crc_type) (wide ? turbo_decode_crc_wide_kernel : turbo_decode_crc_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  else (wide ? turbo_decode_wide_kernel : turbo_decode_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   CU_CHECK(cudaGetLastError());
   ctx->last_grid = lc.grid; ctx->last_block = lc.threads; ctx->last_smem = lc.smem; ctx->last_ncb = lc.ncb;
   ctx->launch_count++;

@@ -20,21 +20,21 @@ struct TurboArgs {
   int out_stride;
   int32_t* out_status;       // [cb] iterations | crc_ok << 8
   int max_iter, crc_type;    // crc_type: 0 none, 1 CRC24A, 2 CRC24B
-  uint32_t crc_poly;
   int K, W, P, Ppad, T, plane;
-  const uint16_t* perm_pos;  // [plane]
-  const uint32_t* crc_tpos;  // [plane] x^(K-1-n+24) mod g at the A position of bit n (0 in padding columns)
+  const uint16_t* perm_tab;  // [W][2][T]: byte offset in the exchange array A of pi((2t + h) * W + i)  (turbo_perm_table)
+  const uint32_t* crc_lin;   // [W/2][T][2][2]: x^(K-1-n+24) mod g for n = pi((2t + h) * W + 2 q + i), 0 in padding columns
   int ncb_cta;               // code-block slots per CTA
   int slot_words;            // 32-bit words between the exchange arrays of consecutive slots (plane/2 + skew)
-  int16_t* nii;              // [grid * ncb_cta][2][2][2][8][Ppad + 2]
-  uint8_t* bits_scratch;     // [grid * ncb_cta][plane] x 16 bit
-  uint4* ckpt;               // [grid * ncb_cta][W/8][T][2]  beta checkpoints
+  uint4* nii;                // [grid * ncb_cta][2 dec][2 parity][2 kinds][Ppad + 2] records of 8 x int16 (turbo.cu)
+  uint4* ckpt;               // [grid][W/8][2][ncb_cta][T]  beta checkpoints (two 16-byte halves per thread)
   int* work_counter;         // dynamic work items handed out so far (zeroed before the launch)
   int work_base;             // first dynamically assigned code block = grid * ncb_cta
 };
 
 __global__ void turbo_decode_kernel(const TurboArgs g);        // fixed iteration count
 __global__ void turbo_decode_crc_kernel(const TurboArgs g);    // CRC accumulated on the fly, early stop
+__global__ void turbo_decode_wide_kernel(const TurboArgs g);       // the same for code blocks with more than 32 threads (T > 32)
+__global__ void turbo_decode_crc_wide_kernel(const TurboArgs g);
 __global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
                                       int n_cb, TurboGeomDev g);
 __global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,

@@ -185,37 +185,44 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
   }
 }
 
-void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos) {
+void turbo_perm_table(const TurboGeom& g, std::vector<uint16_t>& tab) {
   int f1 = 0, f2 = 0;
   qpp_params(g.K, &f1, &f2);
-  pos.assign(g.plane, 0);
+  tab.assign((size_t)g.W * 2 * g.T, 0);
   for (int j = 0; j < g.Ppad; j++)
     for (int i = 0; i < g.W; i++) {
-      // entry order follows the thread-private [group][thread][8 steps] x {window 2t, 2t+1} layout;
-      // the value is a position in the shared exchange array A, which is [W][Ppad]
-      const int e = ((((i / 8) * g.T + j / 2) * 8 + i % 8) * 2) + (j & 1);
-      if (j >= g.P) { pos[e] = (uint16_t)(i * g.Ppad + j); continue; }     // padding column maps onto itself
+      const size_t e = ((size_t)i * 2 + (j & 1)) * g.T + j / 2;
+      if (j >= g.P) { tab[e] = (uint16_t)(2 * (i * g.Ppad + j)); continue; }     // padding column maps onto itself
       const int64_t k = (int64_t)j * g.W + i;
       const int n = (int)((f1 * k + (int64_t)f2 * k * k) % g.K);
-      pos[e] = (uint16_t)((n % g.W) * g.Ppad + n / g.W);
+      tab[e] = (uint16_t)(2 * ((n % g.W) * g.Ppad + n / g.W));
     }
 }
 
-void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tpos) {
-  tpos.assign(g.plane, 0u);
-  uint32_t v = crc_xpow(poly, 24);                 // contribution of the last bit, n = K-1
+void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tlin) {
+  int f1 = 0, f2 = 0;
+  qpp_params(g.K, &f1, &f2);
+  std::vector<uint32_t> nat(g.K);                    // contribution of natural position n
+  uint32_t v = crc_xpow(poly, 24);                   // last bit, n = K-1
   for (int n = g.K - 1; n >= 0; n--) {
-    tpos[(n % g.W) * g.Ppad + n / g.W] = v;
+    nat[n] = v;
     v <<= 1;                                         // times x, reduced
     if (v & 0x1000000u) v ^= poly;
   }
+  tlin.assign((size_t)g.plane, 0u);
+  for (int j = 0; j < g.P; j++)
+    for (int i = 0; i < g.W; i++) {
+      const int64_t k = (int64_t)j * g.W + i;
+      const int n = (int)((f1 * k + (int64_t)f2 * k * k) % g.K);
+      tlin[((((size_t)(i / 2) * g.T + j / 2) * 2 + i % 2) * 2) + (j & 1)] = nat[n];
+    }
 }
 
 int tcb_offset(const TurboGeom& g, int triple_index) {
   const int k = triple_index / 3, stream = triple_index % 3;
   if (k < g.K) {
     const int j = k / g.W, i = k % g.W;       // window, step
-    return stream * g.plane + ((((i / 8) * g.T + j / 2) * 8 + i % 8) * 2) + (j & 1);
+    return stream * g.plane + ((((i / 4) * g.T + j / 2) * 4 + i % 4) * 2) + (j & 1);
   }
   return 3 * g.plane + (triple_index - 3 * g.K);      // 12 tail values in srsLTE order
 }

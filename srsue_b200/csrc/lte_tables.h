@@ -29,8 +29,8 @@ struct CbSegm { int tbs, B, C, Kp, Km, Cp, Cm, F; };
 // Geometry of the windowed decoder for one code-block size (oracle/SPEC.md 7.3) and of the
 // device-native decoder-input layout ("tcb"): three planes sys/par1/par2 of W x Ppad int16 followed by
 // 16 int16 holding the 12 tail values.  Inside a plane the element of (window j, step i) sits at
-// (((i/8)*T + j/2)*8 + i%8)*2 + j%2: the 8 steps x 2 windows that one decoder thread consumes per
-// sub-window are 32 contiguous bytes, and consecutive threads are contiguous (two coalesced LDG.128).
+// (((i/4)*T + j/2)*4 + i%4)*2 + j%2: the 4 steps x 2 windows of one decoder thread are one 16-byte chunk and the
+// chunks of consecutive threads are contiguous, so the 16-byte asynchronous copy a warp issues covers whole sectors.
 struct TurboGeom {
   int K, W, P, Ppad, T;   // T = Ppad / 2 threads per code block
   int plane;              // W * Ppad
@@ -95,12 +95,13 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
 int crs_offset(const CellCfg& cell, int port, int l);
 void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_sign, std::vector<int8_t>& im_sign);
 
-// DEC2 access table: for trellis step i of window j (entry in tcb plane order) the position of
-// pi(j*W+i) in the shared exchange array A, which is laid out [W][Ppad]
-void turbo_perm_pos(const TurboGeom& g, std::vector<uint16_t>& pos);
-// CRC contribution of a hard bit at every position of the exchange array A ([W][Ppad]): the CRC of the K
-// decoded bits is the XOR over the set bits n of x^(K-1-n+24) mod g (zero initial state, no final xor)
-void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tpos);
+// DEC2 access table, [W][2][T] entries: for trellis step i of window 2t + h the BYTE offset of pi((2t + h) * W + i) in the
+// shared exchange array A, which is laid out [W][Ppad] int16 (consecutive threads read consecutive 16-bit entries)
+void turbo_perm_table(const TurboGeom& g, std::vector<uint16_t>& tab);
+// CRC contribution of the hard bit decided at every DEC2 trellis step, [W/2][T][2][2] entries (one 16-byte chunk per
+// thread and pair of steps, chunks of consecutive threads contiguous): the CRC of the K decoded bits is the XOR over the set bits n of x^(K-1-n+24) mod g (zero
+// initial state, no final xor); entry (q, t, i, h) belongs to n = pi((2t + h) * W + 2 q + i), 0 in padding columns
+void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tlin);
 
 // Rate de-matching gather table for one (K, F, rv): for every element m of the tcb buffer
 // (cb_elems entries) the first circular-buffer read index n in [0, N) that lands on it, 0xFFFF if

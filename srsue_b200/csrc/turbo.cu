@@ -12,14 +12,21 @@
 // spent) takes the next one from a global counter, so early stopping saves time per block.
 //   shared memory : the extrinsic exchange array A of every slot (window-transposed: natural-order
 //                   accesses are one conflict-free LDS.32 per thread, QPP-interleaved accesses conflict-free
-//                   LDS.U16 by the contention-free property), the DEC2 position table and the per-position
-//                   CRC contribution table of this K;
+//                   LDS.U16 by the contention-free property); the DEC2 position table of this K laid out
+//                   [step][window parity][thread] so that a warp reads consecutive 16-bit entries; the hard
+//                   decisions of the current iteration, one bit per trellis step in DEC2 order;
 //   L2 / HBM      : the channel LLRs (read-only, thread-contiguous "tcb" layout -> coalesced LDG.128,
-//                   register-prefetched), the thread-private beta checkpoints of the current pass, the
-//                   window-boundary metrics (NII) and the hard decisions.
+//                   register-prefetched half a sub-window ahead), the thread-private beta checkpoints of the
+//                   current pass, the window-boundary metrics (NII), the per-step CRC contributions.
 // Each MAP pass is: backward sweep storing beta every 8 steps, then forward sweep that re-creates beta
 // for 8 steps in registers and produces alpha, the extrinsic and (DEC2) the hard decision, whose CRC
-// contribution x^(position) mod g is accumulated on the fly (the CRC is linear over GF(2)).
+// contribution x^(position) mod g is accumulated on the fly (the CRC is linear over GF(2)).  Hard decisions
+// leave the SM once per code block: the slot that finishes scatters its decision bits into its (now free)
+// exchange array at the natural positions and packs them from there.
+//
+// Issue budget (per thread and trellis step, both passes of a half iteration; see DESIGN.md "K5 in detail"):
+// ALU pipe 8 (beta) + 7 (beta again) + 8 (alpha) + 14 (extrinsic) + 1 (clamp) + DEC2 only: 2 masks, 2 CRC, 1 half
+// extraction; FMA pipe: the gamma additions, normalisations and address arithmetic.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,23 +38,18 @@ namespace {
 
 constexpr int kSW = 8;                 // sub-window: beta values re-created in registers
 constexpr uint32_t kNegInfPair = ((uint32_t)(uint16_t)(-kTdInf) << 16) | (uint16_t)(-kTdInf);
-constexpr uint32_t kEPair = ((uint32_t)kTdE << 16) | (uint32_t)kTdE;
-constexpr uint32_t kNegEPair = ((uint32_t)(uint16_t)(-kTdE) << 16) | (uint16_t)(-kTdE);
+constexpr uint32_t pair16(int v) { return ((uint32_t)(uint16_t)v << 16) | (uint32_t)(uint16_t)v; }
+constexpr uint32_t k2EPair = pair16(2 * kTdE), kNegEPair = pair16(-kTdE), kEp1Pair = pair16(kTdE + 1);
 
 __device__ __forceinline__ uint32_t vadd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
-__device__ __forceinline__ uint32_t vsub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
 // max(a + b, c) per int16 half, the add wrapping (VIADDMNMX.S16x2)
 __device__ __forceinline__ uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
-__device__ __forceinline__ uint32_t vclampE(uint32_t v) { return __vmins2(__vmaxs2(v, kNegEPair), kEPair); }
+// max(min(a + b, 2E), 0) per int16 half: with a + b = v + E this is clamp(v, -E, E) + E in ONE instruction
+// (VIADDMNMX.S16x2.RELU) instead of a min and a max
+__device__ __forceinline__ uint32_t vclamp2E(uint32_t a, uint32_t b) { return __viaddmin_s16x2_relu(a, b, k2EPair); }
 // lo + hi * 65536 with lo, hi zero-extended 16-bit loads: one IMAD on the FMA pipe (a PRMT would take an
 // ALU-pipe slot, and the ALU pipe is the one this kernel saturates)
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
-// store a 16-bit value at base[idx] with the address formed by one IMAD.WIDE (FMA pipe)
-__device__ __forceinline__ void st16_wide(uint16_t* base, uint32_t idx, uint32_t v) {
-  uint64_t addr;
-  asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(addr) : "r"(idx), "l"(base));
-  asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"((uint16_t)v) : "memory");
-}
 __device__ __forceinline__ uint32_t pack16s(int lo, int hi) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu); }
 
 // beta_k from beta_{k+1} (SPEC 7.4); branch labels follow the RSC trellis of 36.212 5.1.3.2.1
@@ -76,15 +78,22 @@ __device__ __forceinline__ void alpha_step(uint32_t (&a)[8], uint32_t x, uint32_
   for (int s = 0; s < 8; s++) a[s] = n[s];
 }
 
-__device__ __forceinline__ void normalise(uint32_t (&m)[8]) {
-  const uint32_t m0 = m[0];
+// Normalisation (SPEC 7.4 subtracts m(0)).  A packed subtraction costs sm_100a a NOT on the ALU pipe plus two adds, so
+// the kernel adds ~m(0) = -m(0) - 1 instead: every metric of the vector ends up ONE LOWER than the oracle's, m(0) = -1.
+// The extrinsic max(...) - max(...) and the decision only see differences inside one alpha and one beta vector, so the
+// outputs are unchanged; the no-wrap bound of SPEC 7.6 has a margin of 1284, the offset costs 2 of it.
+// `m1` is the constant (-1, -1) held in a register the compiler cannot see through (it would otherwise re-materialise it
+// with an ALU-pipe PRMT at every use).
+__device__ __forceinline__ void normalise(uint32_t (&m)[8], uint32_t m1) {
+  const uint32_t n0 = ~m[0];
 #pragma unroll
-  for (int s = 1; s < 8; s++) m[s] = vsub(m[s], m0);
-  m[0] = 0;
+  for (int s = 1; s < 8; s++) m[s] = vadd(m[s], n0);
+  m[0] = m1;
 }
 
-// extrinsic of one trellis step from alpha_k and beta_{k+1}: max(A10, A11 + y) - max(A00, A01 + y)
-__device__ __forceinline__ uint32_t ext_step(const uint32_t (&a)[8], const uint32_t (&bn)[8], uint32_t y) {
+// The four branch-label maxima of one trellis step from alpha_k and beta_{k+1} (SPEC 7.4), combined to
+//   l1 = max(A10, A11 + y),  l0 = max(A00, A01 + y);   extrinsic = l1 - l0
+__device__ __forceinline__ void ext_parts(const uint32_t (&a)[8], const uint32_t (&bn)[8], uint32_t y, uint32_t& l1, uint32_t& l0) {
   uint32_t a00 = vadd(a[0], bn[0]);
   a00 = vaddmax(a[1], bn[4], a00); a00 = vaddmax(a[6], bn[7], a00); a00 = vaddmax(a[7], bn[3], a00);
   uint32_t a11 = vadd(a[0], bn[4]);
@@ -93,9 +102,8 @@ __device__ __forceinline__ uint32_t ext_step(const uint32_t (&a)[8], const uint3
   a01 = vaddmax(a[3], bn[1], a01); a01 = vaddmax(a[4], bn[2], a01); a01 = vaddmax(a[5], bn[6], a01);
   uint32_t a10 = vadd(a[2], bn[1]);
   a10 = vaddmax(a[3], bn[5], a10); a10 = vaddmax(a[4], bn[6], a10); a10 = vaddmax(a[5], bn[2], a10);
-  const uint32_t l1 = vaddmax(a11, y, a10);
-  const uint32_t l0 = vaddmax(a01, y, a00);
-  return vsub(l1, l0);
+  l1 = vaddmax(a11, y, a10);
+  l0 = vaddmax(a01, y, a00);
 }
 
 // PRMT with the sign-replicate bit of every selector nibble set (__byte_perm masks that bit off)
@@ -118,42 +126,123 @@ __device__ __forceinline__ void st8(uint4* p, const uint32_t (&v)[8]) {
   p[0] = make_uint4(v[0], v[1], v[2], v[3]);
   p[1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
+// Asynchronous 16-byte copy global -> shared (LDGSTS, L2 only).  The channel LLRs and checkpoints of the NEXT group
+// travel this way: a register-destination load would be sunk by ptxas to its first use (observed: zero prefetch
+// distance, a third of all stall samples), a copy with no destination register needs no register to be kept live.
+// Staging chunks are addressed by their 32-bit shared-window address so that every access is an LDS/LDGSTS, never a
+// generic load.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void lds8(uint32_t saddr, uint32_t stride, uint32_t (&v)[8]) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(saddr + stride) : "memory");
+}
+// One word through shared memory with volatile accesses.  ptxas keeps memory operations in order around the copies but
+// hoists every arithmetic instruction it can above them, which leaves the copies at the very end of the loop body, right
+// before the wait.  Reading one input of the following trellis step back from shared memory AFTER the copies ties the
+// arithmetic of the second half of a group to that point, so the copies really are issued half a group ahead.
+__device__ __forceinline__ void pin_store(uint32_t saddr, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t pin_load(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(const unsigned char* base, uint32_t off) {
+  return *reinterpret_cast<const uint16_t*>(base + off);
+}
+__device__ __forceinline__ void sts16(unsigned char* base, uint32_t off, uint32_t v) {
+  *reinterpret_cast<uint16_t*>(base + off) = (uint16_t)v;
+}
 
 // What one slot thread needs to find its code block and its scratch; everything else is derived in place
 // (keeps the live state across the long unrolled sweeps small).
 struct SlotCtx {
   const uint4* in4;       // code block in tcb layout (global)
   uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
-  uint32_t gslot;         // global slot number: selects the NII / checkpoint / decision scratch
+  uint16_t* bits;         // shared: hard decisions of the slot, [W/8][T] x (byte of window 2t | byte of window 2t+1 << 8)
+  uint32_t pin;           // shared-window address of this thread's scratch word (pin_store / pin_load)
+  uint32_t stage;         // shared-window address of this thread's staging chunks: chunk k (16 bytes) at stage + k * 16 * blockDim.x
+                          // (y: 0,1  sys: 2,3  checkpoint: 4,5)
+  uint32_t gslot;         // global slot number: selects the NII / checkpoint scratch
 };
 
+// Window-boundary metrics (NII, SPEC 7.3) live in global memory as one 16-byte record per window and kind: the eight
+// int16 state metrics alpha reached at the END of window j (record j + 1 of kind 0) or beta reached at its START (record j
+// of kind 1).  A thread reads / writes the records of its two windows with 128-bit accesses and transposes them to / from
+// the packed (window 2t | window 2t+1 << 16) registers with byte permutes -- no 16-bit gathers, no branches.
+__device__ __forceinline__ void nii_unpack(const uint4& lo, const uint4& hi, uint32_t (&m)[8]) {
+  m[0] = __byte_perm(lo.x, hi.x, 0x5410); m[1] = __byte_perm(lo.x, hi.x, 0x7632);
+  m[2] = __byte_perm(lo.y, hi.y, 0x5410); m[3] = __byte_perm(lo.y, hi.y, 0x7632);
+  m[4] = __byte_perm(lo.z, hi.z, 0x5410); m[5] = __byte_perm(lo.z, hi.z, 0x7632);
+  m[6] = __byte_perm(lo.w, hi.w, 0x5410); m[7] = __byte_perm(lo.w, hi.w, 0x7632);
+}
+__device__ __forceinline__ void nii_pack(const uint32_t (&m)[8], uint4& lo, uint4& hi) {
+  lo.x = __byte_perm(m[0], m[1], 0x5410); hi.x = __byte_perm(m[0], m[1], 0x7632);
+  lo.y = __byte_perm(m[2], m[3], 0x5410); hi.y = __byte_perm(m[2], m[3], 0x7632);
+  lo.z = __byte_perm(m[4], m[5], 0x5410); hi.z = __byte_perm(m[4], m[5], 0x7632);
+  lo.w = __byte_perm(m[6], m[7], 0x5410); hi.w = __byte_perm(m[6], m[7], 0x7632);
+}
+
 // One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.  Returns the
-// thread's CRC contribution of the hard decisions (DEC2 with crc_on), else 0.
-template <int DEC, bool CRC>
-__device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm16,
-                                             const uint32_t* s_tpos, int t, int it) {
+// thread's CRC contribution of the hard decisions (DEC2 with CRC), else 0.  perm_t = position table + t.
+template <int DEC, bool CRC, int TS>
+__device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm_t, int t, int it) {
   const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
   const int j0 = 2 * t, j1 = 2 * t + 1;
   const int rd = it & 1, wr = rd ^ 1;
-  int16_t* nii = g.nii + (size_t)c.gslot * (size_t)(2 * 2 * 2 * 8 * NP);
-  const int16_t* nii_a_rd = nii + ((DEC * 2 + rd) * 2 + 0) * 8 * NP;
-  const int16_t* nii_b_rd = nii + ((DEC * 2 + rd) * 2 + 1) * 8 * NP;
-  uint32_t* nii_a_wr = reinterpret_cast<uint32_t*>(nii + ((DEC * 2 + wr) * 2 + 0) * 8 * NP);
-  uint32_t* nii_b_wr = reinterpret_cast<uint32_t*>(nii + ((DEC * 2 + wr) * 2 + 1) * 8 * NP);
+  // records: [slot][dec][parity][kind][NP] uint4
+  uint4* nii = g.nii + (size_t)c.gslot * (size_t)(2 * 2 * 2 * NP);
+  const uint4* nii_a_rd = nii + ((DEC * 2 + rd) * 2 + 0) * NP;
+  const uint4* nii_b_rd = nii + ((DEC * 2 + rd) * 2 + 1) * NP;
+  uint4* nii_a_wr = nii + ((DEC * 2 + wr) * 2 + 0) * NP;
+  uint4* nii_b_wr = nii + ((DEC * 2 + wr) * 2 + 1) * NP;
+  // tcb planes and checkpoints are laid out [group][half][thread] x 16 bytes: the chunk a warp copies with one LDGSTS
+  // is contiguous (whole 32-byte sectors, half as many L2 requests as a thread-contiguous 32-byte layout)
   const int gstride = 2 * T;                       // uint4 per 8-step group
-  const uint4* sysq = c.in4 + 2 * t;
+  const uint4* sysq = c.in4 + t;
   const uint4* yq = sysq + (DEC ? 2 : 1) * (plane / 8);
-  // checkpoints of one CTA are laid out [sub-window][slot][thread]: for small code blocks (few threads per slot) the
-  // slots a warp spans are then contiguous, one 16-byte access per thread = whole 128-byte lines
   const int slot_in_cta = (int)(c.gslot - blockIdx.x * g.ncb_cta);
-  const int cstride = g.ncb_cta * gstride;         // uint4 per sub-window of the whole CTA
-  uint4* ckpt4 = g.ckpt + (size_t)blockIdx.x * (size_t)(nsw * cstride) + slot_in_cta * gstride + 2 * t;
-  uint16_t* bits = reinterpret_cast<uint16_t*>(g.bits_scratch) + (size_t)c.gslot * (size_t)plane;
-  int16_t* A16 = reinterpret_cast<int16_t*>(c.Aw);
+  const int cstride = g.ncb_cta * gstride;         // uint4 per sub-window of the whole CTA: [half][slot][thread]
+  const int chalf = g.ncb_cta * T;
+  uint4* ckpt4 = g.ckpt + (size_t)blockIdx.x * (size_t)(nsw * cstride) + slot_in_cta * T + t;
+  unsigned char* Ab = reinterpret_cast<unsigned char*>(c.Aw);
+  uint32_t m1;                                     // (-1, -1), see normalise()
+  asm volatile("mov.b32 %0, 0xFFFFFFFF;" : "=r"(m1));
 
-  uint32_t b[8];
-  // ---- beta at the end of the two windows -------------------------------------------------------
+  // The channel LLRs (and, forward, the checkpoint) of a group reach the thread through its private staging chunks in
+  // shared memory: requested with cp.async at the top of the previous group (a whole group of issue slots ahead), read
+  // into registers with LDS.128 at the top of the group.  Nobody else touches the chunks, so no barrier is involved.
+  const uint32_t cstr = 16u * blockDim.x;          // bytes between the chunks of one thread
+  const uint32_t stg = c.stage, pin = c.pin;
+  auto fetch = [&](int sw, bool with_ckpt) {
+    cp_async16(stg, yq + sw * gstride);
+    cp_async16(stg + cstr, yq + sw * gstride + T);
+    if (DEC == 0) {
+      cp_async16(stg + 2 * cstr, sysq + sw * gstride);
+      cp_async16(stg + 3 * cstr, sysq + sw * gstride + T);
+    }
+    if (with_ckpt) {
+      cp_async16(stg + 4 * cstr, ckpt4 + sw * cstride);
+      cp_async16(stg + 5 * cstr, ckpt4 + sw * cstride + chalf);
+    }
+    cp_async_commit();
+  };
+  fetch(nsw - 1, false);
+
+  // ---- boundary metrics: all four records are requested at once; the first iteration reads the zeros init_slot wrote
+  uint32_t b[8], a[8];
   {
+    const uint4 ra0 = nii_a_rd[j0], ra1 = nii_a_rd[j0 + 1], rb0 = nii_b_rd[j0 + 1], rb1 = nii_b_rd[j0 + 2];
+    nii_unpack(ra0, ra1, a);
+    nii_unpack(rb0, rb1, b);
+    if (j0 == 0) {                                  // trellis start: alpha_0 = (0, -INF, ...)
+      a[0] &= 0xFFFF0000u;
+#pragma unroll
+      for (int s = 1; s < 8; s++) a[s] = (a[s] & 0xFFFF0000u) | (uint32_t)(uint16_t)(-kTdInf);
+    }
     const bool last0 = (j0 == P - 1), last1 = (j1 == P - 1);
     if (last0 || last1) {
       // trellis termination: beta_{K+3} = (0, -INF, ...) and three ordinary steps over the tail
@@ -170,171 +259,172 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 #pragma unroll
         for (int s = 0; s < 8; s++) bt[s] = bq[s];
       }
-      normalise(bt);                                  // metric index K is a multiple of 4
+      normalise(bt, m1);                              // metric index K is a multiple of 4
 #pragma unroll
-      for (int s = 0; s < 8; s++) {
-        int lo = 0, hi = 0;
-        if (last0) lo = (int)(int16_t)(bt[s] & 0xFFFFu); else if (it) lo = nii_b_rd[s * NP + j0 + 1];
-        if (last1) hi = (int)(int16_t)(bt[s] >> 16); else if (it) hi = nii_b_rd[s * NP + j1 + 1];
-        b[s] = pack16s(lo, hi);
-      }
-    } else if (it) {
-#pragma unroll
-      for (int s = 0; s < 8; s++) b[s] = pack16s(nii_b_rd[s * NP + j0 + 1], nii_b_rd[s * NP + j1 + 1]);
-    } else {
-#pragma unroll
-      for (int s = 0; s < 8; s++) b[s] = 0;
+      for (int s = 0; s < 8; s++) b[s] = last0 ? ((b[s] & 0xFFFF0000u) | (bt[s] & 0xFFFFu)) : ((b[s] & 0xFFFFu) | (bt[s] & 0xFFFF0000u));
     }
-  }
-  // ---- alpha at the start of the two windows ------------------------------------------------------
-  uint32_t a[8];
-#pragma unroll
-  for (int s = 0; s < 8; s++) {
-    int lo, hi;
-    if (j0 == 0) lo = s ? -kTdInf : 0; else lo = it ? nii_a_rd[s * NP + j0 - 1] : 0;
-    hi = it ? nii_a_rd[s * NP + j0] : 0;
-    a[s] = pack16s(lo, hi);
   }
 
+  uint32_t Cy[kSW], Cs[kSW], Cb[8];
+
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
-  // Register prefetch TWO groups ahead: all warps of the CTA run this short, load-dominated sweep at the
-  // same time (the passes are barrier-separated), so there is no other phase to hide the L2 latency behind.
-  // The last group of this sweep (steps 0..7) is the first group of the forward sweep: its channel LLRs (ny, ns)
-  // and the beta vector it starts from (nbeta) stay in registers across the pass boundary instead of being
-  // re-loaded from L2 with nothing to overlap.
-  uint32_t ny[kSW], ns[kSW], nbeta[8];
-  {
-    uint32_t my[kSW], ms[kSW];
-    ld8(yq + (nsw - 1) * gstride, ny);
-    if (DEC == 0) ld8(sysq + (nsw - 1) * gstride, ns);
-    if (nsw > 1) {
-      ld8(yq + (nsw - 2) * gstride, my);
-      if (DEC == 0) ld8(sysq + (nsw - 2) * gstride, ms);
-    }
-    auto group = [&](int sw, const uint32_t (&y)[kSW], const uint32_t (&sv)[kSW]) {
-      uint32_t x[kSW];
-      if (DEC == 0) {
-        const uint32_t* ap = c.Aw + sw * kSW * T + t;
-#pragma unroll
-        for (int i = 0; i < kSW; i++) x[i] = vadd(sv[i], ap[i * T]);
-      } else {
-        // position table read as LDS.U16 (immediate offsets, LSU pipe), not unpacked on the ALU pipe
-        const uint16_t* pq = perm16 + sw * (2 * kSW) * T;
-#pragma unroll
-        for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
-      }
-      if (sw) st8(ckpt4 + sw * cstride, b);         // thread-private scratch, read back in pass 2 (group 0 stays in registers)
-#pragma unroll
-      for (int i = kSW - 1; i >= 0; i--) {
-        uint32_t nb[8];
-        beta_step(b, nb, x[i], y[i], vadd(x[i], y[i]));
-#pragma unroll
-        for (int s = 0; s < 8; s++) b[s] = nb[s];
-        if ((i & 3) == 0) normalise(b);
-      }
-    };
 #pragma unroll 1
-    for (int sw = nsw - 1; sw >= 1; sw--) {
-      uint32_t y[kSW], sv[kSW];
+  for (int sw = nsw - 1; sw >= 0; sw--) {
+    cp_async_wait_all();
+    lds8(stg, cstr, Cy);
+    if (DEC == 0) lds8(stg + 2 * cstr, cstr, Cs);
+    pin_store(pin, Cy[kSW - 1]);
+    {                                               // checkpoint: thread-private scratch, read back in pass 2
+      uint4* cp = ckpt4 + sw * cstride;
+      cp[0] = make_uint4(b[0], b[1], b[2], b[3]);
+      cp[chalf] = make_uint4(b[4], b[5], b[6], b[7]);
+    }
+    fetch(sw > 0 ? sw - 1 : 0, sw == 0);            // after group 0: its data and checkpoint again, for the forward sweep
+    Cy[kSW - 1] = pin_load(pin);                    // ties the arithmetic below to this point (see pin_store)
+    // x of a group: DEC1 systematic + a-priori (natural order, one LDS.32 for both windows); DEC2 the two
+    // interleaved positions of the exchange array
+    uint32_t x[kSW];
+    if (DEC == 0) {
+      const uint32_t* ap = c.Aw + sw * kSW * T + t;
 #pragma unroll
-      for (int i = 0; i < kSW; i++) { y[i] = ny[i]; ny[i] = my[i]; if (DEC == 0) { sv[i] = ns[i]; ns[i] = ms[i]; } }
-      if (sw > 1) {
-        ld8(yq + (sw - 2) * gstride, my);
-        if (DEC == 0) ld8(sysq + (sw - 2) * gstride, ms);
-      }
-      group(sw, y, sv);
+      for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+    } else {
+      const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
+#pragma unroll
+      for (int i = 0; i < kSW; i++) x[i] = pack16(lds16(Ab, pq[(2 * i) * TS]), lds16(Ab, pq[(2 * i + 1) * TS]));
     }
 #pragma unroll
-    for (int s = 0; s < 8; s++) nbeta[s] = b[s];
-    group(0, ny, ns);
+    for (int i = kSW - 1; i >= 0; i--) {
+      uint32_t nb[8];
+      beta_step(b, nb, x[i], Cy[i], vadd(x[i], Cy[i]));
+#pragma unroll
+      for (int s = 0; s < 8; s++) b[s] = nb[s];
+      if ((i & 3) == 0) normalise(b, m1);
+    }
   }
   // beta at the window start feeds the previous window in the next iteration
-#pragma unroll
-  for (int s = 0; s < 8; s++) nii_b_wr[(s * NP + j0) >> 1] = b[s];
+  {
+    uint4 lo, hi;
+    nii_pack(b, lo, hi);
+    nii_b_wr[j0] = lo;
+    nii_b_wr[j0 + 1] = hi;
+  }
 
   // ---- pass 2: forward sweep ----------------------------------------------------------------------
   uint32_t crc = 0;
-  {
-    // ny / ns / nbeta of sub-window 0 come from the backward sweep; later ones are prefetched one group ahead
+  const uint4* crcq = reinterpret_cast<const uint4*>(g.crc_lin) + t;      // [sw][4][T] uint4
 #pragma unroll 1
-    for (int sw = 0; sw < nsw; sw++) {
-      uint32_t x[kSW], y[kSW], aux[kSW];            // aux: DEC1 systematic LLRs
-      uint32_t* ap = c.Aw + sw * kSW * T + t;
-      const uint16_t* pq = perm16 + sw * (2 * kSW) * T;
+  for (int sw = 0; sw < nsw; sw++) {
+    cp_async_wait_all();
+    lds8(stg, cstr, Cy);
+    if (DEC == 0) lds8(stg + 2 * cstr, cstr, Cs);
+    lds8(stg + 4 * cstr, cstr, Cb);
+    pin_store(pin, Cy[kSW - 1]);
+    if (sw + 1 < nsw) fetch(sw + 1, true);
+    Cy[kSW - 1] = pin_load(pin);
+    uint32_t x[kSW];
+    uint32_t pa[2 * kSW];                           // DEC2: byte offsets of the two interleaved positions per step
+    uint32_t* ap = c.Aw + sw * kSW * T + t;
+    if (DEC == 0) {
 #pragma unroll
-      for (int i = 0; i < kSW; i++) y[i] = ny[i];
-      if (DEC == 0) {
+      for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+    } else {
+      const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
 #pragma unroll
-        for (int i = 0; i < kSW; i++) { aux[i] = ns[i]; x[i] = vadd(ns[i], ap[i * T]); }
-      } else {
+      for (int i = 0; i < 2 * kSW; i++) pa[i] = pq[i * TS];
 #pragma unroll
-        for (int i = 0; i < kSW; i++) x[i] = pack16((uint16_t)A16[pq[2 * i]], (uint16_t)A16[pq[2 * i + 1]]);
-      }
-      uint32_t B[kSW][8];                           // B[i] = beta_{i+1} of this sub-window
-#pragma unroll
-      for (int s = 0; s < 8; s++) B[kSW - 1][s] = nbeta[s];
-      if (sw + 1 < nsw) {
-        ld8(yq + (sw + 1) * gstride, ny);
-        if (DEC == 0) ld8(sysq + (sw + 1) * gstride, ns);
-        ldp8(ckpt4 + (sw + 1) * cstride, nbeta);
-      }
-#pragma unroll
-      for (int i = kSW - 1; i >= 1; i--) {
-        beta_step(B[i], B[i - 1], x[i], y[i], vadd(x[i], y[i]));
-        if ((i & 3) == 0) normalise(B[i - 1]);
-      }
-#pragma unroll
-      for (int i = 0; i < kSW; i++) {
-        const uint32_t ext = ext_step(a, B[i], y[i]);
-        const uint32_t la = vclampE(ext);
-        if (DEC == 0) {
-          ap[i * T] = vadd(aux[i], la);
-        } else {
-          const uint32_t p0 = pq[2 * i], p1 = pq[2 * i + 1];
-          A16[p0] = (int16_t)(la & 0xFFFFu);
-          A16[p1] = (int16_t)(la >> 16);
-          // decision = (x + ext) > 0  <=>  sign bit of -(x + ext), kept as the sign of a 16-bit word
-          const uint32_t nd = vsub(0u, vadd(x[i], ext));
-          st16_wide(bits, p0, nd);
-          st16_wide(bits, p1, nd >> 16);
-          if (CRC) crc ^= (sign_fill<0x9999>(nd) & __ldg(s_tpos + p0)) ^ (sign_fill<0xBBBB>(nd) & __ldg(s_tpos + p1));
-        }
-        alpha_step(a, x[i], y[i], vadd(x[i], y[i]));
-        if ((i & 3) == 3) normalise(a);
-      }
+      for (int i = 0; i < kSW; i++) x[i] = pack16(lds16(Ab, pa[2 * i]), lds16(Ab, pa[2 * i + 1]));
     }
-  }
+    uint32_t B[kSW][8];                             // B[i] = beta_{i+1} of this sub-window
 #pragma unroll
-  for (int s = 0; s < 8; s++) nii_a_wr[(s * NP + j0) >> 1] = a[s];
+    for (int s = 0; s < 8; s++) B[kSW - 1][s] = Cb[s];
+#pragma unroll
+    for (int i = kSW - 1; i >= 1; i--) {
+      beta_step(B[i], B[i - 1], x[i], Cy[i], vadd(x[i], Cy[i]));
+      if ((i & 3) == 0) normalise(B[i - 1], m1);
+    }
+    uint4 tq[4];                                    // CRC contributions of the 16 decisions of this group (L1-resident table)
+    uint32_t acc0 = 0xFFu, acc1 = 0xFFu;            // decision bits of the two windows, step i at bit 7-i: start from all
+                                                    // ones, every zero decision subtracts its bit
+#pragma unroll
+    for (int i = 0; i < kSW; i++) {
+      if (DEC == 1 && CRC && (i & 3) == 0) {
+        tq[i >> 1] = __ldg(crcq + ((size_t)sw * 4 + (i >> 1)) * T);
+        tq[(i >> 1) + 1] = __ldg(crcq + ((size_t)sw * 4 + (i >> 1) + 1) * T);
+      }
+      // extrinsic = l1 - l0 without a packed subtraction (-l0 = ~l0 + 1): q = l1 + ~l0 = ext - 1, exact in 16 bits
+      uint32_t l1, l0;
+      ext_parts(a, B[i], Cy[i], l1, l0);
+      const uint32_t q = vadd(l1, ~l0);
+      const uint32_t r = vclamp2E(q, kEp1Pair);                // clamp(ext, -E, E) + E
+      if (DEC == 0) {
+        ap[i * T] = vadd(vadd(Cs[i], kNegEPair), r);
+      } else {
+        const uint32_t la = vadd(r, kNegEPair);
+        sts16(Ab, pa[2 * i], la);
+        sts16(Ab, pa[2 * i + 1], la >> 16);
+        // decision = (x + ext) > 0  <=>  x + ext - 1 >= 0: the masks below are set where the bit is ZERO
+        const uint32_t s1 = vadd(q, x[i]);
+        const uint32_t z0 = sign_fill<0x9999>(s1), z1 = sign_fill<0xBBBB>(s1);
+        acc0 = z0 * (0x80u >> i) + acc0;
+        acc1 = z1 * (0x80u >> i) + acc1;
+        if (CRC) {
+          const uint32_t t0 = (i & 1) ? tq[i >> 1].z : tq[i >> 1].x, t1 = (i & 1) ? tq[i >> 1].w : tq[i >> 1].y;
+          crc ^= (~z0 & t0) ^ (~z1 & t1);
+        }
+      }
+      alpha_step(a, x[i], Cy[i], vadd(x[i], Cy[i]));
+      if ((i & 3) == 3) normalise(a, m1);
+    }
+    if (DEC == 1) c.bits[sw * T + t] = (uint16_t)(acc0 | (acc1 << 8));
+  }
+  {
+    uint4 lo, hi;
+    nii_pack(a, lo, hi);
+    nii_a_wr[j0 + 1] = lo;
+    nii_a_wr[j0 + 2] = hi;
+  }
   return crc;
 }
 
-template <bool CRC>
+template <bool CRC, int TS>
 __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int T = g.T, W = g.W, P = g.P, plane = g.plane;
+  const int T = g.T, W = g.W, P = g.P, plane = g.plane, nsw = W / kSW;
   const int tid = threadIdx.x;
   const int slot = tid / T, t = tid - slot * T;
   const bool valid = slot < g.ncb_cta;
   constexpr bool crc_on = CRC;
   const int nflag = (g.ncb_cta + 3) & ~3;
 
-  uint32_t* s_permw = smem;                                  // plane/2 words: DEC2 positions [W/8][T][8][2] x u16
-  const uint32_t* s_tpos = g.crc_tpos;                       // x^(pos) mod g per A position: 23 KB, read through L1
-  uint32_t* s_crc = s_permw + plane / 2;                     // per slot: CRC accumulator
+  uint32_t* s_permw = smem;                                  // W * TS words: DEC2 positions [W][2][TS] x u16 (byte offsets into A)
+  uint32_t* s_crc = s_permw + W * TS;                        // per slot: CRC accumulator
   int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
-  uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words
+  uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words (+ skew)
   int* s_active = s_next + nflag;
+  uint16_t* s_bits = reinterpret_cast<uint16_t*>(s_slots + (size_t)g.ncb_cta * g.slot_words);   // per slot: nsw * T x u16
+  // staging chunks of all threads, 16-byte aligned: [6][blockDim.x] uint4, then [blockDim.x] scratch words
+  uint4* s_stage = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_bits + (size_t)g.ncb_cta * nsw * T) + 15) & ~(uintptr_t)15);
 
-  for (int i = tid; i < plane / 2; i += blockDim.x) s_permw[i] = reinterpret_cast<const uint32_t*>(g.perm_pos)[i];
+  {
+    // position table: global [W][2][T] -> shared [W][2][TS] (rows padded to the warp-friendly stride)
+    uint16_t* d = reinterpret_cast<uint16_t*>(s_permw);
+    for (int e = tid; e < 2 * W * T; e += blockDim.x) {
+      const int row = e / T, col = e - row * T;
+      d[row * TS + col] = g.perm_tab[e];
+    }
+  }
 
   SlotCtx c;
   // slot stride = plane/2 words plus a skew that makes consecutive slots continue the bank sequence
   // (base(s+1) = base(s) + T mod 32): a warp that straddles two slots then stays conflict-free
   c.Aw = s_slots + (size_t)(valid ? slot : 0) * g.slot_words;
+  c.bits = s_bits + (size_t)(valid ? slot : 0) * (nsw * T);
+  c.stage = (uint32_t)__cvta_generic_to_shared(s_stage + tid);
+  c.pin = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(s_stage + 6 * blockDim.x) + tid);
   c.gslot = blockIdx.x * g.ncb_cta + (valid ? slot : 0);
   c.in4 = nullptr;
-  const uint16_t* perm16 = reinterpret_cast<const uint16_t*>(s_permw) + 2 * kSW * t;
+  const uint16_t* perm_t = reinterpret_cast<const uint16_t*>(s_permw) + t;
 
   // ---- persistent slots ------------------------------------------------------------------------------
   int cur = blockIdx.x * g.ncb_cta + slot;                    // the first assignment is static
@@ -346,14 +436,27 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
     // a-priori LLRs start at zero: each thread clears its own column of A
     for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
+    // boundary metrics of the first iteration are all zero: every thread clears exactly the records it will read
+    // (read parity 0 of both decoders), so no barrier is needed between a refill and the first pass
+    {
+      const int NP = g.Ppad + 2;
+      uint4* nii = g.nii + (size_t)c.gslot * (size_t)(2 * 2 * 2 * NP);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int dec = 0; dec < 2; dec++) {
+        uint4* ra = nii + (dec * 4 + 0) * NP;
+        uint4* rb = nii + (dec * 4 + 1) * NP;
+        ra[2 * t] = z; ra[2 * t + 1] = z; rb[2 * t + 1] = z; rb[2 * t + 2] = z;
+      }
+    }
     // the block comes straight from HBM: request all three planes now (the groups the backward sweep needs
     // first go first) so that only the first sub-window waits for DRAM
-    const uint4* p0 = c.in4 + 2 * t;
-    for (int sw = W / kSW - 1; sw >= 0; sw--) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + sw * 2 * T));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (plane / 8) + sw * 2 * T));
+    const uint4* p0 = c.in4 + t;
+    for (int sw = 2 * nsw - 1; sw >= 0; sw--) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + sw * T));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (plane / 8) + sw * T));
     }
-    for (int sw = W / kSW - 1; sw >= 0; sw--) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 2 * (plane / 8) + sw * 2 * T));
+    for (int sw = 2 * nsw - 1; sw >= 0; sw--) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 2 * (plane / 8) + sw * T));
   };
   if (have) init_slot();
   if (tid == 0) *s_active = 0;
@@ -363,31 +466,28 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
   while (*s_active > 0) {
     if (valid && t == 0) s_crc[slot] = 0;
-    if (have) map_pass<0, CRC>(g, c, perm16, s_tpos, t, it);
+    if (have) map_pass<0, CRC, TS>(g, c, perm_t, t, it);
     __syncthreads();
     if (have) {
-      const uint32_t part = map_pass<1, CRC>(g, c, perm16, s_tpos, t, it);
+      const uint32_t part = map_pass<1, CRC, TS>(g, c, perm_t, t, it);
       if (crc_on) atomicXor(&s_crc[slot], part);
     }
     __syncthreads();
     const bool crc_ok = crc_on && valid && s_crc[slot] == 0;
     const bool fin = have && (crc_ok || it + 1 >= g.max_iter);
     if (fin) {
-      // ---- pack the hard decisions of this iteration, MSB first, natural order --------------------
-      uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
-      const int wbytes = W / 8;
-      const uint32_t* bp = reinterpret_cast<const uint32_t*>(g.bits_scratch) + ((size_t)c.gslot * plane) / 2 + t;
-#pragma unroll 4
-      for (int bb = 0; bb < wbytes; bb++) {
-        uint32_t v0 = 0, v1 = 0;
+      // ---- de-interleave the hard decisions of this iteration: every thread scatters the 2 x W bits of its
+      // windows (DEC2 order) as 0/1 halfwords to their natural positions in the exchange array, which nobody needs
+      // any more ----
+      unsigned char* Ab = reinterpret_cast<unsigned char*>(c.Aw);
+      for (int sw = 0; sw < nsw; sw++) {
+        const uint32_t w = c.bits[sw * T + t];
+        const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const uint32_t w = bp[(bb * 8 + q) * T];
-          v0 = (v0 << 1) | ((w >> 15) & 1u);
-          v1 = (v1 << 1) | (w >> 31);
+        for (int i = 0; i < kSW; i++) {
+          sts16(Ab, pq[(2 * i) * TS], (w >> (7 - i)) & 1u);
+          sts16(Ab, pq[(2 * i + 1) * TS], (w >> (15 - i)) & 1u);
         }
-        out[(2 * t) * wbytes + bb] = (uint8_t)v0;
-        if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)v1;
       }
       if (t == 0) {
         g.out_status[cbi] = (it + 1) | ((crc_ok ? 1 : 0) << 8);
@@ -400,6 +500,16 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     }
     __syncthreads();
     if (fin) {
+      // ---- pack, MSB first, natural order: word i*T + t holds the bits of step i of windows 2t and 2t+1 ----
+      uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
+      const int wbytes = W / 8;
+      for (int bb = 0; bb < wbytes; bb++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) v = v * 2u + c.Aw[(bb * 8 + q) * T + t];
+        out[(2 * t) * wbytes + bb] = (uint8_t)v;
+        if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)(v >> 16);
+      }
       cur = s_next[slot];
       have = cur < g.n_cb;
       it = 0;
@@ -410,8 +520,10 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false, 32>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64>(g); }
 
 // ---- layout conversion at the API edge -----------------------------------------------------------
 // srsLTE decoder-input order (3K+12 interleaved triples) -> tcb layout, clamping to +-C (SPEC 7.2)
@@ -424,11 +536,11 @@ __global__ void triples_to_tcb_kernel(const int16_t* __restrict__ in, long long 
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.cb_elems; e += gridDim.x * blockDim.x) {
     int v = 0;
     if (e < 3 * g.plane) {
-      // tcb element -> (stream, window j, step i): element ((sw*T + t)*8 + ii)*2 + h, j = 2t + h, i = 8sw + ii
+      // tcb element -> (stream, window j, step i): element ((hs*T + t)*4 + ii)*2 + h, j = 2t + h, i = 4hs + ii
       const int stream = e / g.plane, r = e - stream * g.plane;
-      const int h = r & 1, ii = (r >> 1) & 7, q = r >> 4;
-      const int sw = q / g.T, t = q - sw * g.T;
-      const int i = sw * 8 + ii, j = 2 * t + h;
+      const int h = r & 1, ii = (r >> 1) & 3, q = r >> 3;
+      const int hs = q / g.T, t = q - hs * g.T;
+      const int i = hs * 4 + ii, j = 2 * t + h;
       if (j < g.P) v = src[3 * (j * g.W + i) + stream];
     } else if (e - 3 * g.plane < 12) {
       v = src[3 * g.K + (e - 3 * g.plane)];
@@ -449,7 +561,7 @@ __global__ void tcb_to_triples_kernel(const int16_t* __restrict__ in, long long 
     if (e < 3 * g.K) {
       const int k = e / 3, stream = e - 3 * k;
       const int j = k / g.W, i = k - j * g.W;
-      off = stream * g.plane + ((((i >> 3) * g.T + (j >> 1)) * 8 + (i & 7)) << 1) + (j & 1);
+      off = stream * g.plane + ((((i >> 2) * g.T + (j >> 1)) * 4 + (i & 3)) << 1) + (j & 1);
     } else {
       off = 3 * g.plane + (e - 3 * g.K);
     }
