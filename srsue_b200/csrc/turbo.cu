@@ -37,6 +37,7 @@ namespace srsue {
 namespace {
 
 constexpr int kSW = 8;                 // sub-window: beta values re-created in registers
+constexpr int kL2Ahead = 3;            // backward sweep: groups between an L2 prefetch and the copy that needs the lines
 constexpr uint32_t kNegInfPair = ((uint32_t)(uint16_t)(-kTdInf) << 16) | (uint16_t)(-kTdInf);
 constexpr uint32_t pair16(int v) { return ((uint32_t)(uint16_t)v << 16) | (uint32_t)(uint16_t)v; }
 constexpr uint32_t k2EPair = pair16(2 * kTdE), kNegEPair = pair16(-kTdE), kEp1Pair = pair16(kTdE + 1);
@@ -94,6 +95,14 @@ __device__ __forceinline__ void normalise(uint32_t (&m)[8], uint32_t m1) {
 // The four branch-label maxima of one trellis step from alpha_k and beta_{k+1} (SPEC 7.4), combined to
 //   l1 = max(A10, A11 + y),  l0 = max(A00, A01 + y);   extrinsic = l1 - l0
 __device__ __forceinline__ void ext_parts(const uint32_t (&a)[8], const uint32_t (&bn)[8], uint32_t y, uint32_t& l1, uint32_t& l0) {
+#ifdef SRSUE_TURBO_EXT_MAX3
+  // Variant: three of the four sums of every label by plain adds (FMA pipe) and one three-input maximum
+  // (VIMNMX3.S16x2), the fourth by add-max: 10 ALU-pipe + 13 FMA-pipe instructions instead of 14 + 5.
+  const uint32_t a00 = vaddmax(a[7], bn[3], __vimax3_s16x2(vadd(a[0], bn[0]), vadd(a[1], bn[4]), vadd(a[6], bn[7])));
+  const uint32_t a11 = vaddmax(a[7], bn[7], __vimax3_s16x2(vadd(a[0], bn[4]), vadd(a[1], bn[0]), vadd(a[6], bn[3])));
+  const uint32_t a01 = vaddmax(a[5], bn[6], __vimax3_s16x2(vadd(a[2], bn[5]), vadd(a[3], bn[1]), vadd(a[4], bn[2])));
+  const uint32_t a10 = vaddmax(a[5], bn[2], __vimax3_s16x2(vadd(a[2], bn[1]), vadd(a[3], bn[5]), vadd(a[4], bn[6])));
+#else
   uint32_t a00 = vadd(a[0], bn[0]);
   a00 = vaddmax(a[1], bn[4], a00); a00 = vaddmax(a[6], bn[7], a00); a00 = vaddmax(a[7], bn[3], a00);
   uint32_t a11 = vadd(a[0], bn[4]);
@@ -102,6 +111,7 @@ __device__ __forceinline__ void ext_parts(const uint32_t (&a)[8], const uint32_t
   a01 = vaddmax(a[3], bn[1], a01); a01 = vaddmax(a[4], bn[2], a01); a01 = vaddmax(a[5], bn[6], a01);
   uint32_t a10 = vadd(a[2], bn[1]);
   a10 = vaddmax(a[3], bn[5], a10); a10 = vaddmax(a[4], bn[6], a10); a10 = vaddmax(a[5], bn[2], a10);
+#endif
   l1 = vaddmax(a11, y, a10);
   l0 = vaddmax(a01, y, a00);
 }
@@ -133,6 +143,13 @@ __device__ __forceinline__ void st8(uint4* p, const uint32_t (&v)[8]) {
 // generic load.
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
+// base + idx * 16 bytes as ONE IMAD.WIDE on the FMA pipe (the compiler's own 64-bit address arithmetic is three or four
+// LEA / IADD3.X on the ALU pipe, which is the pipe this kernel saturates)
+__device__ __forceinline__ const uint4* at16(const uint4* base, uint32_t idx) {
+  uint64_t a;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(idx), "l"(base));
+  return reinterpret_cast<const uint4*>(a);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -218,18 +235,25 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   const uint32_t cstr = 16u * blockDim.x;          // bytes between the chunks of one thread
   const uint32_t stg = c.stage, pin = c.pin;
   auto fetch = [&](int sw, bool with_ckpt) {
-    cp_async16(stg, yq + sw * gstride);
-    cp_async16(stg + cstr, yq + sw * gstride + T);
+    const uint32_t gi = (uint32_t)(sw * gstride);
+    cp_async16(stg, at16(yq, gi));
+    cp_async16(stg + cstr, at16(yq, gi + T));
     if (DEC == 0) {
-      cp_async16(stg + 2 * cstr, sysq + sw * gstride);
-      cp_async16(stg + 3 * cstr, sysq + sw * gstride + T);
+      cp_async16(stg + 2 * cstr, at16(sysq, gi));
+      cp_async16(stg + 3 * cstr, at16(sysq, gi + T));
     }
     if (with_ckpt) {
-      cp_async16(stg + 4 * cstr, ckpt4 + sw * cstride);
-      cp_async16(stg + 5 * cstr, ckpt4 + sw * cstride + chalf);
+      const uint32_t ci = (uint32_t)(sw * cstride);
+      cp_async16(stg + 4 * cstr, at16(ckpt4, ci));
+      cp_async16(stg + 5 * cstr, at16(ckpt4, ci + chalf));
     }
     cp_async_commit();
   };
+  // L2 prefetch of the backward sweep: the two (DEC2: one) plane rows of a group and slot are contiguous runs of
+  // 32 T bytes; thread t asks for line t of the first run, thread nl + t for line t of the second
+  const int nl = (T + 3) / 4;                      // 128-byte lines per run
+  const uint4* pf_base = (t < nl) ? (yq - t) + 8 * t : (sysq - t) + 8 * (t - nl);
+  const bool pf_on = t < (DEC == 0 ? 2 * nl : nl) && (t < nl ? 8 * t : 8 * (t - nl)) < 2 * T;
   fetch(nsw - 1, false);
 
   // ---- boundary metrics: all four records are requested at once; the first iteration reads the zeros init_slot wrote
@@ -275,19 +299,27 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
     if (DEC == 0) lds8(stg + 2 * cstr, cstr, Cs);
     pin_store(pin, Cy[kSW - 1]);
     {                                               // checkpoint: thread-private scratch, read back in pass 2
-      uint4* cp = ckpt4 + sw * cstride;
-      cp[0] = make_uint4(b[0], b[1], b[2], b[3]);
-      cp[chalf] = make_uint4(b[4], b[5], b[6], b[7]);
+      const uint32_t ci = (uint32_t)(sw * cstride);
+      *const_cast<uint4*>(at16(ckpt4, ci)) = make_uint4(b[0], b[1], b[2], b[3]);
+      *const_cast<uint4*>(at16(ckpt4, ci + chalf)) = make_uint4(b[4], b[5], b[6], b[7]);
     }
     fetch(sw > 0 ? sw - 1 : 0, sw == 0);            // after group 0: its data and checkpoint again, for the forward sweep
+    // The resident code blocks of all SMs together exceed what the L2 keeps (hit rate 80 %): ask for the lines of the
+    // group three ahead now, so that its copy finds them in L2 instead of waiting for DRAM with nothing to overlap.
+    if (sw >= kL2Ahead && pf_on) asm volatile("prefetch.global.L2 [%0];" ::"l"(at16(pf_base, (uint32_t)((sw - kL2Ahead) * gstride))));
     Cy[kSW - 1] = pin_load(pin);                    // ties the arithmetic below to this point (see pin_store)
     // x of a group: DEC1 systematic + a-priori (natural order, one LDS.32 for both windows); DEC2 the two
     // interleaved positions of the exchange array
     uint32_t x[kSW];
     if (DEC == 0) {
-      const uint32_t* ap = c.Aw + sw * kSW * T + t;
+      if (it) {                                     // a-priori LLRs are zero in the first iteration: nothing to read
+        const uint32_t* ap = c.Aw + sw * kSW * T + t;
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+        for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kSW; i++) x[i] = Cs[i];
+      }
     } else {
       const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
 #pragma unroll
@@ -326,8 +358,13 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
     uint32_t pa[2 * kSW];                           // DEC2: byte offsets of the two interleaved positions per step
     uint32_t* ap = c.Aw + sw * kSW * T + t;
     if (DEC == 0) {
+      if (it) {
 #pragma unroll
-      for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+        for (int i = 0; i < kSW; i++) x[i] = vadd(Cs[i], ap[i * T]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kSW; i++) x[i] = Cs[i];
+      }
     } else {
       const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
 #pragma unroll
@@ -434,8 +471,6 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   auto init_slot = [&]() {
     cbi = g.cb_list ? g.cb_list[cur] : cur;
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
-    // a-priori LLRs start at zero: each thread clears its own column of A
-    for (int i = 0; i < W; i++) c.Aw[i * T + t] = 0u;
     // boundary metrics of the first iteration are all zero: every thread clears exactly the records it will read
     // (read parity 0 of both decoders), so no barrier is needed between a refill and the first pass
     {
@@ -449,14 +484,17 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
         ra[2 * t] = z; ra[2 * t + 1] = z; rb[2 * t + 1] = z; rb[2 * t + 2] = z;
       }
     }
-    // the block comes straight from HBM: request all three planes now (the groups the backward sweep needs
-    // first go first) so that only the first sub-window waits for DRAM
-    const uint4* p0 = c.in4 + t;
-    for (int sw = 2 * nsw - 1; sw >= 0; sw--) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + sw * T));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (plane / 8) + sw * T));
+    // the block comes straight from HBM: request it now, one 128-byte line per prefetch (the rows the backward
+    // sweep of DEC1 needs first -- the ends of the parity-1 and systematic planes -- go first)
+    {
+      const char* base = reinterpret_cast<const char*>(c.in4);
+      const int lines_plane = (plane * 2 + 127) / 128;
+      for (int l = lines_plane - 1 - t; l >= 0; l -= T) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + plane * 2 + (size_t)l * 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
+      }
+      for (int l = lines_plane - 1 - t; l >= 0; l -= T) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + plane * 4 + (size_t)l * 128));
     }
-    for (int sw = 2 * nsw - 1; sw >= 0; sw--) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + 2 * (plane / 8) + sw * T));
   };
   if (have) init_slot();
   if (tid == 0) *s_active = 0;
@@ -477,16 +515,16 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     const bool fin = have && (crc_ok || it + 1 >= g.max_iter);
     if (fin) {
       // ---- de-interleave the hard decisions of this iteration: every thread scatters the 2 x W bits of its
-      // windows (DEC2 order) as 0/1 halfwords to their natural positions in the exchange array, which nobody needs
+      // windows (DEC2 order) as zero / non-zero halfwords to their natural positions in the exchange array, which nobody needs
       // any more ----
       unsigned char* Ab = reinterpret_cast<unsigned char*>(c.Aw);
       for (int sw = 0; sw < nsw; sw++) {
         const uint32_t w = c.bits[sw * T + t];
         const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
 #pragma unroll
-        for (int i = 0; i < kSW; i++) {
-          sts16(Ab, pq[(2 * i) * TS], (w >> (7 - i)) & 1u);
-          sts16(Ab, pq[(2 * i + 1) * TS], (w >> (15 - i)) & 1u);
+        for (int i = 0; i < kSW; i++) {             // any non-zero halfword means "one": the packing below normalises
+          sts16(Ab, pq[(2 * i) * TS], w & (0x80u >> i));
+          sts16(Ab, pq[(2 * i + 1) * TS], w & (0x8000u >> i));
         }
       }
       if (t == 0) {
@@ -506,7 +544,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
       for (int bb = 0; bb < wbytes; bb++) {
         uint32_t v = 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) v = v * 2u + c.Aw[(bb * 8 + q) * T + t];
+        for (int q = 0; q < 8; q++) v = v * 2u + __vminu2(c.Aw[(bb * 8 + q) * T + t], 0x00010001u);
         out[(2 * t) * wbytes + bb] = (uint8_t)v;
         if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)(v >> 16);
       }
