@@ -141,6 +141,10 @@ int srsue_gpu_ofdm_rx_sc16_cfo(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int
 int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t *plan, const int32_t *d_cfo_steps, int32_t cfo_step);
 enum { SRSUE_GPU_IQ_CF32 = 0, SRSUE_GPU_IQ_SC16 = 1 };
 int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t *plan, int format, float scale);
+/* First turbo iteration after which a passing code-block CRC ends the block (default 1: stop as soon as the CRC passes,
+ * what srslte_pdsch_decode_rnti does with the budget of srslte_sch_set_max_noi, phch_worker.cc:88).  min_iter = max_iter
+ * gives a fixed iteration count with the CRC verdicts still reported -- the "fixed 4 iterations" measurement of SURVEY 7.3. */
+int srsue_gpu_pdsch_plan_set_min_iter(srsue_gpu_pdsch_plan_t *plan, int min_iter);
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
 int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
                     float *d_meas, void *stream);

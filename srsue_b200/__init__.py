@@ -177,6 +177,10 @@ class PdschPlan:
         """carrier-offset correction for decode_batch / decode_batch_host of this plan; (None, 0) switches it off"""
         _check(lib().srsue_gpu_pdsch_plan_set_cfo(self.h, _ptr(d_cfo_steps), C.c_int32(cfo_step)), "set_cfo")
 
+    def set_min_iter(self, min_iter):
+        """a passing code-block CRC ends the block only from this turbo iteration on (1 = default, max_iter = fixed count)"""
+        _check(lib().srsue_gpu_pdsch_plan_set_min_iter(self.h, int(min_iter)), "set_min_iter")
+
     def set_iq_format(self, sc16, scale=1.0 / 32768.0):
         """decode_batch / decode_batch_host take int16 {re, im} samples (sc16=True) or complex64 (False, the default)."""
         _check(lib().srsue_gpu_pdsch_plan_set_iq_format(self.h, 1 if sc16 else 0, C.c_float(scale)), "set_iq_format")
@@ -275,14 +279,17 @@ class Batch:
         _check(lib().srsue_gpu_batch_set_iq_format(self.h, 1 if sc16 else 0, C.c_float(scale)), "srsue_gpu_batch_set_iq_format")
 
     def submit_prepared(self, prepared):
-        self._keep = prepared
+        self._keep = None
         _check(lib().srsue_gpu_batch_submit(self.h, prepared[0], len(prepared[0])), "srsue_gpu_batch_submit")
+        self._keep = prepared                 # a refused submission leaves nothing to wait for
 
     def submit(self, items):
         self.submit_prepared(self.prepare(items))
 
     def wait(self):
         _check(lib().srsue_gpu_batch_wait(self.h), "srsue_gpu_batch_wait")
+        if self._keep is None:
+            return []
         descs, payloads, _ = self._keep
         self._keep = None
         return [dict(payload=pl, crc_ok=d.crc_ok, n_iter=d.n_iter, meas=list(d.meas)) for d, pl in zip(descs, payloads)]

@@ -90,7 +90,9 @@ struct srsue_gpu_ctx {
   int device = 0, num_sms = 0, smem_optin = 0, smem_sm = 0;
   std::mutex mu;
   std::map<int, TurboTables> turbo;
-  Scratch scratch;
+  // decoder scratch of the device-pointer srsue_gpu_tdec_* calls, one set per stream: launches on one stream are ordered,
+  // callers on different streams (or threads) never share buffers.  std::map nodes do not move, so the references stay valid.
+  std::map<cudaStream_t, Scratch> scratch;
   int last_grid = 0, last_block = 0, last_smem = 0, last_ncb = 0;
   std::atomic<int> launch_count{0};       // workers on different streams share the context
   std::atomic<bool> attr_set{false};
@@ -103,6 +105,11 @@ struct srsue_gpu_ctx {
 };
 
 namespace {
+
+Scratch& stream_scratch(srsue_gpu_ctx* ctx, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return ctx->scratch[st];
+}
 
 int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -189,7 +196,7 @@ int ensure_scratch(Scratch& s, size_t nii_elems, size_t bits_bytes, size_t tcb_e
 
 // launches the decoder for n_cb code blocks of size K.  cb_list (device) may be null.
 int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long long in_stride, const int32_t* d_cb_list, int n_cb, int K,
-                 int max_iter, int crc_type, uint8_t* d_bits, int out_stride, int32_t* d_status, cudaStream_t st) {
+                 int max_iter, int crc_type, uint8_t* d_bits, int out_stride, int32_t* d_status, cudaStream_t st, int min_iter = 1) {
   if (n_cb <= 0) return 0;
   if (max_iter < 1 || crc_type < 0 || crc_type > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "bad max_iter/crc_type");
   const TurboTables* tt = nullptr;
@@ -213,6 +220,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   a.in = d_in; a.in_stride = in_stride; a.cb_list = d_cb_list; a.n_cb = n_cb;
   a.out_bits = d_bits; a.out_stride = out_stride; a.out_status = d_status;
   a.max_iter = max_iter; a.crc_type = crc_type;
+  a.min_iter = std::max(1, std::min(min_iter, max_iter));
   a.K = g.K; a.W = g.W; a.P = g.P; a.Ppad = g.Ppad; a.T = g.T; a.plane = g.plane;
   a.perm_tab = tt->d_perm;
   a.crc_lin = tt->d_tpos[crc_type == 2 ? 1 : 0];
@@ -257,6 +265,7 @@ struct srsue_gpu_pdsch_plan {
   // staging for the host-pointer call
   float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
   const int32_t* cfo_steps = nullptr; int32_t cfo_step_all = 0;            // carrier-offset correction of the batch calls
+  int min_iter = 1;                                                          // srsue_gpu_pdsch_plan_set_min_iter
   int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what the d_iq / h_iq arguments of the batch calls point at
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
@@ -302,7 +311,7 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
     cudaFree(kv.second.d_perm);
     for (int i = 0; i < 2; i++) cudaFree(kv.second.d_tpos[i]);
   }
-  ctx->scratch.release();
+  for (auto& kv : ctx->scratch) kv.second.release();
   cudaFree(ctx->d_pss_freq); cudaFree(ctx->d_sss);
   for (auto& kv : ctx->sync_tabs) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
   cudaFree(ctx->d_peak_key); cudaFree(ctx->d_power_sum); cudaFree(ctx->d_cexp);
@@ -417,7 +426,7 @@ int srsue_gpu_tdec_decode(srsue_gpu_ctx_t* ctx, const int16_t* d_tcb, int n_cb, 
   if (qpp_index(K) < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "K=%d is not a valid LTE code-block size", K);
   CU_CHECK(cudaSetDevice(ctx->device));
   const TurboGeom g = turbo_geom(K);
-  return launch_turbo(ctx, ctx->scratch, d_tcb, g.cb_elems, nullptr, n_cb, K, max_iter, crc_type, d_bits, K / 8, d_status, (cudaStream_t)stream);
+  return launch_turbo(ctx, stream_scratch(ctx, (cudaStream_t)stream), d_tcb, g.cb_elems, nullptr, n_cb, K, max_iter, crc_type, d_bits, K / 8, d_status, (cudaStream_t)stream);
 }
 
 int srsue_gpu_tdec_run_all(srsue_gpu_ctx_t* ctx, const int16_t* d_triples, int n_cb, int K, int max_iter, int crc_type,
@@ -427,12 +436,13 @@ int srsue_gpu_tdec_run_all(srsue_gpu_ctx_t* ctx, const int16_t* d_triples, int n
   if (n_cb <= 0) return n_cb == 0 ? 0 : fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "negative n_cb");
   const TurboGeom g = turbo_geom(K);
   CU_CHECK(cudaSetDevice(ctx->device));
-  int rc = ensure_scratch(ctx->scratch, 0, 0, (size_t)n_cb * g.cb_elems);
+  Scratch& scr = stream_scratch(ctx, (cudaStream_t)stream);
+  int rc = ensure_scratch(scr, 0, 0, (size_t)n_cb * g.cb_elems);
   if (rc) return rc;
   ctx->launch_count = 0;
-  rc = srsue_gpu_tdec_import(ctx, d_triples, n_cb, K, ctx->scratch.tcb, stream);
+  rc = srsue_gpu_tdec_import(ctx, d_triples, n_cb, K, scr.tcb, stream);
   if (rc) return rc;
-  return srsue_gpu_tdec_decode(ctx, ctx->scratch.tcb, n_cb, K, max_iter, crc_type, d_bits, d_status, stream);
+  return srsue_gpu_tdec_decode(ctx, scr.tcb, n_cb, K, max_iter, crc_type, d_bits, d_status, stream);
 }
 
 int srsue_gpu_tdec_run_all_host(srsue_gpu_ctx_t* ctx, const int16_t* h_triples, int n_cb, int K, int max_iter, int crc_type,
@@ -670,6 +680,12 @@ int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t* p, const int32_t* d_cfo
   return 0;
 }
 
+int srsue_gpu_pdsch_plan_set_min_iter(srsue_gpu_pdsch_plan_t* p, int min_iter) {
+  if (!p || min_iter < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_min_iter: null plan or min_iter < 1");
+  p->min_iter = min_iter;
+  return 0;
+}
+
 int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t* p, int format, float scale) {
   if (!p || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
@@ -768,8 +784,8 @@ namespace {
 int pdcch_tables(srsue_gpu_pdsch_plan_t* p, int ng_x6) {
   if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12 (6 x Ng)");
   if (p->pd_ng == ng_x6) return 0;
+  // only the PDCCH tables depend on Ng; the PBCH tables of the plan (srsue_gpu_pbch_decode) are left alone
   cudaFree(p->d_pd_re4); cudaFree(p->d_pd_src); cudaFree(p->d_pd_scr);
-  cudaFree(p->d_pbch_re); cudaFree(p->d_pbch_scr); cudaFree(p->d_pbch_rm);
   p->d_pd_re4 = nullptr; p->d_pd_src = nullptr; p->d_pd_scr = nullptr; p->pd_ng = -1;
   std::vector<int32_t> re4, src;
   const int n_reg = pdcch_regs(p->cell, p->cfg.cfi, ng_x6, re4);
@@ -1045,10 +1061,10 @@ int srsue_gpu_pdsch_turbo(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t* d_
   cudaStream_t st = (cudaStream_t)stream;
   int rc = 0;
   if (s.Cm) rc = launch_turbo(p->ctx, p->scratch, d_softbuf, p->info.sb_cb_stride, p->d_list_m, n_sf * s.Cm, s.Km, max_iter, crc_type,
-                              p->d_cb_bits, s.Kp / 8, cbst, st);
+                              p->d_cb_bits, s.Kp / 8, cbst, st, p->min_iter);
   if (rc) return rc;
   rc = launch_turbo(p->ctx, p->scratch, d_softbuf, p->info.sb_cb_stride, p->d_list_p, n_sf * s.Cp, s.Kp, max_iter, crc_type, p->d_cb_bits,
-                    s.Kp / 8, cbst, st);
+                    s.Kp / 8, cbst, st, p->min_iter);
   if (rc) return rc;
   TbArgs t{};
   t.cb_bits = p->d_cb_bits; t.cb_status = cbst; t.payload = d_payload; t.tb_status = d_tb_status;

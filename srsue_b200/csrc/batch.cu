@@ -231,9 +231,23 @@ int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t* b, int format, float scale)
   return 0;
 }
 
+static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n);
+
 int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
   if (!b || !descs || n < 0 || n > b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: bad arguments (n=%d)", n);
   if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
+  const int rc = batch_submit_impl(b, descs, n);
+  if (rc) {
+    // Every descriptor is validated before the first launch, so a failure here is a CUDA error in the middle of the
+    // submission: copies and scatter kernels of earlier chunks may still be writing into the callers' payload buffers.
+    // Let them finish before the caller gets its buffers back; nothing is delivered (batch_wait has nothing pending).
+    cudaStreamSynchronize(b->s_copy);
+    cudaStreamSynchronize(b->s_compute);
+  }
+  return rc;
+}
+
+static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
   b->launches = 0;
   b->order.clear();
   b->pl_chunks.clear();
@@ -247,6 +261,8 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
   for (int i = 0; i < n; i++) {
     const srsue_gpu_sf_desc_t& d = descs[i];
     if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptor %d has a null buffer", i);
+    if (!(d.cfo > -1.0f && d.cfo < 1.0f)) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: cfo %g outside (-1, 1) subcarrier spacings", i, (double)d.cfo);
+    if (d.softbuffer_id < 0 && !d.new_data) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: HARQ combining needs a softbuffer_id", i);
     // buckets are launched one after the other, not in arrival order, so one HARQ process may appear only once
     // per submission (its transmissions are 8 ms apart on the air anyway)
     if (d.softbuffer_id >= 0 && !seen.emplace(d.softbuffer_id, i).second)
@@ -260,14 +276,28 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
     if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }
     it->second.push_back(i);
   }
+  // ---- everything that can be refused is refused here, before the first launch: the plan of every bucket exists and
+  // every combine finds an earlier transmission of the same size ------------------------------------------------------
+  for (const std::string& gk : group_order) {
+    const std::vector<int>& idx = groups[gk];
+    PlanEntry* pe = nullptr;
+    const int rc = get_plan(b, gk.substr(0, gk.size() - 1), descs[idx[0]], &pe);   // (looked up again below: with more
+    if (rc) return rc;                                                             // buckets than cached plans it may be evicted)
+    if (gk.back() != 2) continue;
+    for (int i : idx) {
+      auto it = b->softbuffers.find(descs[i].softbuffer_id);
+      if (it == b->softbuffers.end() || !it->second.d)
+        B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: soft buffer %lld has no earlier transmission", i, (long long)descs[i].softbuffer_id);
+      if (it->second.elems != pe->info.sb_sf_stride)
+        B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: soft buffer %lld holds a different transport block size", i, (long long)descs[i].softbuffer_id);
+    }
+  }
   // ---- one chain launch per bucket chunk --------------------------------------------------------------------
   for (const std::string& gk : group_order) {
     const std::vector<int>& idx = groups[gk];
-    const srsue_gpu_sf_desc_t& d0 = descs[idx[0]];
     const int mode = gk.back();                       // 0 untracked, 1 tracked new data, 2 tracked combine
-    if (mode == 0 && !d0.new_data) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: HARQ combining needs a softbuffer_id", idx[0]);
     PlanEntry* pe = nullptr;
-    int rc = get_plan(b, gk.substr(0, gk.size() - 1), d0, &pe);
+    int rc = get_plan(b, gk.substr(0, gk.size() - 1), descs[idx[0]], &pe);
     if (rc) return rc;
     const srsue_gpu_plan_info_t& info = pe->info;
     const size_t cap = (size_t)b->chunk_cap;

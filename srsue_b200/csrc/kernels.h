@@ -20,6 +20,7 @@ struct TurboArgs {
   int out_stride;
   int32_t* out_status;       // [cb] iterations | crc_ok << 8
   int max_iter, crc_type;    // crc_type: 0 none, 1 CRC24A, 2 CRC24B
+  int min_iter;              // a passing CRC stops the block only from this iteration on (1: as srsLTE; = max_iter: fixed count)
   int K, W, P, Ppad, T, plane;
   const uint16_t* perm_tab;  // [W][2][T]: byte offset in the exchange array A of pi((2t + h) * W + i)  (turbo_perm_table)
   const uint32_t* crc_lin;   // [W/2][T][2][2]: x^(K-1-n+24) mod g for n = pi((2t + h) * W + 2 q + i), 0 in padding columns

@@ -298,15 +298,16 @@ int srslte_dci_msg_pack_pdsch(srslte_ra_dl_dci_t* d, srslte_dci_format_t format,
 }
 
 // ---- CQI reporting helpers (phch_worker.cc:504-527) ------------------------------------------------------------------
-// Wideband CQI from the channel estimator's SNR in dB: a ladder of about 2 dB per CQI step from -6.5 dB (CQI 1, QPSK
-// rate 0.08) to 21 dB (CQI 15, 64QAM rate 0.93), the usual AWGN spacing of the 36.213 Table 7.2.3-1 efficiencies.  Not
-// calibrated against this receiver's BLER curves; srsLTE's own table lives in its un-vendored lib/phch/cqi.c and may
-// differ by a fraction of a dB per step.
+// Wideband CQI from the channel estimator's SNR in dB.  [UPSTREAM-RECALL] srsLTE's lib/phch/cqi.c keeps the SNR at which
+// each CQI index becomes usable (1.95 dB for CQI 1 ... 29 dB for CQI 15) and reports the number of entries below the
+// measured SNR; the table is recalled, not readable offline (srsLTE is not vendored).  At the reference's call site
+// (phch_worker.cc:504-527) this is the value the eNodeB's link adaptation sees, so the thresholds must not be optimistic:
+// an earlier ladder here (-6.5 ... 21 dB) reported several CQI steps more than srsLTE for the same SNR.
 uint8_t srslte_cqi_from_snr(float snr_db) {
-  static const float thr[15] = {-6.5f, -4.5f, -2.5f, -0.5f, 1.5f, 3.5f, 5.5f, 7.5f, 9.5f, 11.5f, 13.5f, 15.0f, 17.0f, 19.0f, 21.0f};
-  uint8_t cqi = 0;
-  for (int i = 0; i < 15; i++) if (snr_db >= thr[i]) cqi = (uint8_t)(i + 1);
-  return cqi;
+  static const float cqi_to_snr[15] = {1.95f, 4.f, 6.f, 8.f, 10.f, 11.95f, 14.05f, 16.f, 17.9f, 19.9f, 21.5f, 23.45f, 25.0f, 27.30f, 29.f};
+  int idx = 0;
+  while (idx < 15 && cqi_to_snr[idx] < snr_db) idx++;
+  return (uint8_t)idx;
 }
 
 // 36.213 Table 7.2.2-1A (FDD): does a periodic CQI/PMI report with configuration index I_cqi_pmi fall on this tti?

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) pss_corr_kernel(const SyncArgs a) {
   for (int i = tid; i < N; i += 256) s_t[i] = a.pss_time[u * N + i];
   __syncthreads();
   const int p = p0 + tid;
-  if (p >= n_pos) return;
+  const bool active = p < n_pos;                     // no early return: every lane takes part in the warp reduction below
   float c1r = 0.f, c1i = 0.f, c2r = 0.f, c2i = 0.f;
 #pragma unroll 8
   for (int n = 0; n < N / 2; n++) {
@@ -44,9 +44,9 @@ __global__ void __launch_bounds__(256) pss_corr_kernel(const SyncArgs a) {
   const float pw = __fadd_rn(__fmul_rn(cr, cr), __fmul_rn(ci, ci));
   // power is non-negative, so its bit pattern orders like its value; ties go to the lowest (root, position)
   const unsigned long long key = ((unsigned long long)__float_as_uint(pw) << 32) | (0xFFFFFFFFu - (uint32_t)(u * n_pos + p));
-  atomicMax(a.peak_key + buf, key);
-  // mean power: block sum in double, one atomic per block (reported figure, not part of any decision)
-  double v = (double)pw;
+  if (active) atomicMax(a.peak_key + buf, key);
+  // mean power: warp sum in double, one atomic per warp; positions past the end contribute exactly zero
+  double v = active ? (double)pw : 0.0;
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
   if ((tid & 31) == 0) atomicAdd(a.power_sum + buf, v);

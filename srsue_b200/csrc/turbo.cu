@@ -512,7 +512,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     }
     __syncthreads();
     const bool crc_ok = crc_on && valid && s_crc[slot] == 0;
-    const bool fin = have && (crc_ok || it + 1 >= g.max_iter);
+    const bool fin = have && ((crc_ok && it + 1 >= g.min_iter) || it + 1 >= g.max_iter);
     if (fin) {
       // ---- de-interleave the hard decisions of this iteration: every thread scatters the 2 x W bits of its
       // windows (DEC2 order) as zero / non-zero halfwords to their natural positions in the exchange array, which nobody needs

@@ -138,6 +138,30 @@ def test_batch_argument_errors(gpu, oracle):
     b.close()
 
 
+def test_batch_is_validated_before_anything_is_launched(gpu, oracle):
+    """a descriptor that must be refused anywhere in the submission -- a combine without an earlier transmission behind
+    valid buckets, a later untracked descriptor with new_data = 0 inside a bucket, a carrier offset out of range -- fails
+    the whole submission before the first launch: nothing is pending, no payload buffer is written, the batch stays usable"""
+    sg, ctx = gpu
+    o = oracle
+    ocell, ocfg, cell, cfg = _pair(sg, o, MIX[0])
+    oc2, og2, c2, g2 = _pair(sg, o, MIX[1])
+    iq = o.gen_subframe(ocell, ocfg, 1, 10.0)[1]
+    iq2 = o.gen_subframe(oc2, og2, 2, 16.0)[1]
+    b = sg.Batch(ctx, 8)
+    good = [dict(cell=cell, cfg=cfg, iq=iq), dict(cell=c2, cfg=g2, iq=iq2)]
+    for bad in (dict(cell=c2, cfg=g2, iq=iq2, softbuffer_id=5, new_data=0),      # no earlier transmission
+                dict(cell=cell, cfg=cfg, iq=iq, new_data=0),                       # same bucket as good[0], not its first entry
+                dict(cell=cell, cfg=cfg, iq=iq, cfo=1.5)):
+        with pytest.raises(sg.GpuError):
+            b.submit(good + [bad])
+        assert b.wait() == []                                                      # nothing was accepted
+        assert b.stats()["launches"] == 0
+        b.submit(good)
+        assert [r["crc_ok"] for r in b.wait()] == [1, 1]
+    b.close()
+
+
 @pytest.mark.parametrize("how", ["host_alloc", "host_register"])
 def test_zero_copy_pinned_rows(gpu, oracle, how):
     """scattered subframes inside pinned regions known to the library are fetched / written by the GPU directly

@@ -484,3 +484,53 @@ def test_srslte_ue_mib_decode_shim(gpu, oracle):
     noise = (np.random.default_rng(1).standard_normal((len(iq), 2)) @ np.array([1, 1j])).astype(np.complex64)
     assert L.srslte_ue_mib_decode(C.byref(q), noise.ctypes.data_as(C.c_void_p), payload, C.byref(nports), C.byref(off)) == 0
     L.srslte_ue_mib_free(C.byref(q))
+
+
+def test_pbch_tables_survive_pdcch_on_the_same_plan(gpu, oracle):
+    """PBCH, then PDCCH, then PBCH again on ONE plan (the natural order on subframe 0): building the PDCCH tables must not
+    release the PBCH tables -- the second MIB decode equals the first and that of a fresh plan"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    prb, ports, cid = 25, 2, 77
+    ocell = o.make_cell(prb, ports, cid)
+    cell = sg.make_cell(prb, ports, cid)
+    sfns = [0, 5, 1022]
+    n = len(sfns)
+    mibs = [o.mib_pack(prb, 0, 6, s) for s in sfns]
+    ocfg = o.make_cfg(ocell, sf_idx=0, cfi=2, qm=2, tbs=104, tm=ports, prbs=[0])
+    iq = np.stack([o.gen_subframe(ocell, ocfg, 7100 + i, 6.0, None, pcfich=True, mib=(mibs[i], s % 4))[1] for i, s in enumerate(sfns)])
+    cfg = sg.make_cfg(cell, sf_idx=0, cfi=2, qm=2, tbs=0, tm=ports)
+
+    def run(plan, with_pdcch):
+        I = plan.info
+        d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+        d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+        d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+        plan.ofdm_rx(n, d_iq, d_sf)
+        plan.chest(n, d_sf, d_ce, d_meas)
+        out = []
+        for rep in range(2):
+            d_res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+            d_mib = torch.zeros((n, 24), dtype=torch.uint8, device="cuda")
+            plan.pbch_decode(n, d_sf, d_ce, d_meas, 0.0, 1, d_res, d_mib)
+            torch.cuda.synchronize()
+            out.append((d_res.cpu().numpy().copy(), d_mib.cpu().numpy().copy()))
+            if with_pdcch and rep == 0:
+                n_reg = plan.pdcch_info(1)[0]
+                d_llr = torch.zeros((n, 8 * n_reg), dtype=torch.int16, device="cuda")
+                plan.pdcch_extract_llr(n, d_sf, d_ce, d_meas, 0.0, 1, d_llr)
+                torch.cuda.synchronize()
+        return out
+
+    p1 = sg.PdschPlan(ctx, cell, cfg, n)
+    first, second = run(p1, True)
+    p1.close()
+    p2 = sg.PdschPlan(ctx, cell, cfg, n)
+    fresh, _ = run(p2, False)
+    p2.close()
+    for res, mib in (first, second, fresh):
+        assert np.all(res[:, 0] == 1) and np.array_equal(res[:, 1], [ports] * n) and np.array_equal(res[:, 2], [s % 4 for s in sfns])
+        assert np.array_equal(mib, np.stack(mibs))
+

@@ -156,6 +156,9 @@ def test_cqi_helpers(L):
     L.srslte_cqi_send.restype = C.c_bool
     cq = [L.srslte_cqi_from_snr(C.c_float(s)) for s in np.arange(-10, 30, 0.25)]
     assert cq[0] == 0 and cq[-1] == 15 and all(b - a in (0, 1) for a, b in zip(cq, cq[1:])) and set(cq) == set(range(16))
+    # the mapping itself (srsLTE's thresholds as recalled in ra.cc): number of table entries below the SNR
+    for snr, want in ((1.9, 0), (2.0, 1), (4.0, 1), (4.1, 2), (10.0, 4), (10.01, 5), (19.9, 9), (20.0, 10), (29.0, 14), (29.1, 15)):
+        assert L.srslte_cqi_from_snr(C.c_float(snr)) == want, snr
     for idx, period, off in ((0, 2, 0), (1, 2, 1), (2, 5, 0), (6, 5, 4), (7, 10, 0), (16, 10, 9), (17, 20, 0), (36, 20, 19),
                              (37, 40, 0), (76, 40, 39), (77, 80, 0), (157, 160, 0), (316, 160, 159), (318, 32, 0), (349, 32, 31),
                              (350, 64, 0), (414, 128, 0), (541, 128, 127)):
