@@ -588,6 +588,40 @@ def main():
     sampler.stop_flag = True
     sampler.join()
 
+    # ---- the library's own multi-GPU dispatcher: ONE process, one handle over all N GPUs ---------------------
+    # (srsue_gpu_batch_create_multi: per-device contexts, streams, pinned staging and host threads inside the library;
+    # rank 0 drives it while the other ranks, done with their own measurement, release their buffers and wait)
+    multi = None
+    if not args.no_legs and WORKLOAD["tm"] == 1:
+        eplan.close()
+        d_iq = d_sf = d_ce = d_sb = None
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            nsub = EB * world
+            p_mpl = lib.srsue_gpu_host_alloc(nsub * I.payload_stride)
+            h_mpl = np.ctypeslib.as_array(C.cast(p_mpl, C.POINTER(C.c_uint8)), shape=(nsub, I.payload_stride))
+            mb = sg.Batch(None, nsub, 0.01, args.noise_mode, args.max_iter, devices=list(range(world)))
+            prepared = sg.Batch.prepare([dict(cell=cell, cfg=cfg, iq=h_iq[i % EB].view(np.complex64), payload=h_mpl[i][:WORKLOAD["tbs"] // 8])
+                                         for i in range(nsub)])
+            for _ in range(2):
+                mb.submit_prepared(prepared)
+                lib.srsue_gpu_batch_wait(mb.h)
+            t0 = time.perf_counter()
+            mbits = 0
+            for _ in range(args.steps):
+                mb.submit_prepared(prepared)
+                lib.srsue_gpu_batch_wait(mb.h)
+                mbits += sum(1 for d in prepared[0] if d.crc_ok == 1) * WORKLOAD["tbs"]
+            mdt = time.perf_counter() - t0
+            ok = bool(np.array_equal(h_mpl[:args.pool % EB or EB, :WORKLOAD["tbs"] // 8], tbs[(np.arange(EB) % args.pool)[:args.pool % EB or EB]]))
+            multi = {"value": mbits / mdt / 1e6, "unit": "Mbit/s", "n_devices": world, "subframes_per_step": nsub,
+                     "shares": [n for n, _ in mb.device_shares()], "verified_bit_exact_payload": ok,
+                     "api": "srsue_gpu_batch_create_multi + srsue_gpu_batch_submit/_wait from ONE process, host buffers (H2D and D2H inside)"}
+            mb.close()
+            lib.srsue_gpu_host_free(p_mpl)
+        barrier()
+
     # ---- reduce over ranks (max time, sum of units) ------------------------------------------------------
     leg_names = sorted(legs)
     vals = torch.tensor([total_ms, e2e_s, sc16_s] + [legs[n]["ms"] for n in leg_names] + [legs[n]["turbo_ms"] for n in leg_names],
@@ -675,6 +709,9 @@ def main():
             "clocks": sampler.summary(),
         }
         out["e2e"]["sc16"] = {k: out["e2e_sc16"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+        if multi:
+            multi["vs_e2e_of_the_rank_per_gpu_path"] = multi["value"] / out["e2e"]["value"]
+            out["multi_gpu_dispatcher"] = multi
         if ncu:
             for st_ in stages:
                 k = {"ofdm_fft": "fft", "chest": "chest", "equalise_demap_dematch": "demap", "turbo_crc_tb": "turbo"}[st_["kernel"]]

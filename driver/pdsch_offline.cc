@@ -141,6 +141,45 @@ int run_batch(const Header& h, cf_t* iq, FILE* out) {
   return 0;
 }
 
+// ---- mode "batch --gpus N": the same subframes as descriptors through ONE multi-GPU handle (srsue_gpu_batch_create_multi):
+// the library splits the submission over devices 0..N-1 by estimated turbo work and gathers the results -- what N
+// phch_workers behind the reference's thread pool do one subframe at a time (thread_pool.cc:206-254, phy.h:118-119)
+int run_batch_multi(const Header& h, cf_t* iq, FILE* out, int n_gpus) {
+  std::vector<int> devs(n_gpus);
+  for (int i = 0; i < n_gpus; i++) devs[i] = i;
+  srsue_gpu_batch_t* b = nullptr;
+  if (srsue_gpu_batch_create_multi(devs.data(), n_gpus, h.n_sf, 0.01f, 0, h.max_iter > 0 ? h.max_iter : 4, &b)) {
+    fprintf(stderr, "%s\n", srsue_gpu_last_error());
+    return 1;
+  }
+  const size_t sf_len = SRSLTE_SF_LEN_PRB(h.nof_prb), pl = (size_t)h.tbs / 8;
+  std::vector<uint8_t> payload((size_t)h.n_sf * pl);
+  std::vector<srsue_gpu_sf_desc_t> d((size_t)h.n_sf);
+  for (int n = 0; n < h.n_sf; n++) {
+    std::memset(&d[n], 0, sizeof(d[n]));
+    d[n].cell = {h.nof_prb, h.nof_ports, h.cell_id};
+    d[n].cfg.sf_idx = h.sf_idx; d[n].cfg.cfi = h.cfi; d[n].cfg.rnti = h.rnti; d[n].cfg.qm = h.qm; d[n].cfg.tbs = h.tbs; d[n].cfg.rv = h.rv;
+    d[n].cfg.tm = h.nof_ports == 1 ? 1 : 2; d[n].cfg.nof_prb_alloc = h.nof_prb;
+    for (int i = 0; i < h.nof_prb; i++) d[n].cfg.prb_mask[i] = 1;
+    d[n].iq = reinterpret_cast<const srsue_gpu_cf_t*>(iq + (size_t)n * sf_len);
+    d[n].payload = payload.data() + (size_t)n * pl;
+    d[n].softbuffer_id = -1;
+    d[n].new_data = 1;
+  }
+  if (srsue_gpu_batch_submit(b, d.data(), h.n_sf) || srsue_gpu_batch_wait(b)) { fprintf(stderr, "%s\n", srsue_gpu_last_error()); return 1; }
+  int nd = 0, share[64];
+  srsue_gpu_batch_device_shares(b, &nd, share, nullptr, 64);
+  for (int i = 0; i < nd; i++) fprintf(stderr, "device %d: %d subframes\n", devs[i], share[i]);
+  for (int n = 0; n < h.n_sf; n++) {
+    const int32_t ack = d[n].crc_ok, n_iter = d[n].n_iter;
+    const float snr = d[n].meas[4];
+    fwrite(&ack, 4, 1, out); fwrite(&n_iter, 4, 1, out); fwrite(&snr, 4, 1, out);
+    fwrite(d[n].payload, 1, pl, out);
+  }
+  srsue_gpu_batch_destroy(b);
+  return 0;
+}
+
 // ---- mode "acquire": what phch_recv does before any subframe reaches a worker (phch_recv.cc:136-264): cell search,
 // MIB search, then subframe synchronisation with the system frame number taken from the MIB of subframes 0.  The
 // "radio" is a capture file at 1.92 Msps that wraps around (in.bin: int32 magic 0x53525355, int32 n_samples, cf_t...).
@@ -217,7 +256,9 @@ int run_acquire(const cf_t* iq, size_t n, FILE* out) {
 }  // namespace
 
 int main(int argc, char** argv) {
-  if (argc != 4) { fprintf(stderr, "usage: %s worker|batch|acquire <in.bin> <out>\n", argv[0]); return 2; }
+  int n_gpus = 0;                                            // "batch <in> <out> --gpus N": the multi-GPU dispatcher
+  if (argc == 6 && std::strcmp(argv[4], "--gpus") == 0) { n_gpus = atoi(argv[5]); argc = 4; }
+  if (argc != 4 || n_gpus < 0 || n_gpus > 64) { fprintf(stderr, "usage: %s worker|batch|acquire <in.bin> <out> [--gpus N (batch only)]\n", argv[0]); return 2; }
   if (std::strcmp(argv[1], "acquire") == 0) {
     FILE* in = fopen(argv[2], "rb");
     if (!in) { perror(argv[2]); return 1; }
@@ -242,7 +283,7 @@ int main(int argc, char** argv) {
   fclose(in);
   FILE* out = fopen(argv[3], "wb");
   if (!out) { perror(argv[3]); return 1; }
-  const int rc = std::strcmp(argv[1], "batch") == 0 ? run_batch(h, iq, out) : run_worker(h, iq, out);
+  const int rc = std::strcmp(argv[1], "batch") == 0 ? (n_gpus ? run_batch_multi(h, iq, out, n_gpus) : run_batch(h, iq, out)) : run_worker(h, iq, out);
   fclose(out);
   srslte_vec_free(iq);
   return rc;

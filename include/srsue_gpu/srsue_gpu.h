@@ -239,6 +239,18 @@ typedef struct {
 /* max_subframes bounds one submission.  noise_est / noise_mode / max_iter as in srsue_gpu_pdsch_decode_batch. */
 int srsue_gpu_batch_create(srsue_gpu_ctx_t *ctx, int max_subframes, float noise_est, int noise_mode, int max_iter,
                            srsue_gpu_batch_t **batch);
+/* The same batching layer over SEVERAL GPUs of one box (north star item 4; the reference's analogue is its pool
+ * of phch_workers behind one object, ue/src/common/thread_pool.cc:206-254, ue/hdr/phy/phy.h:118-119).  The library creates
+ * one context per listed device, each with its own streams, pinned staging, plan cache and resident soft buffers, and
+ * drives each with its own host thread.  srsue_gpu_batch_submit then splits a submission: a soft buffer id stays on the
+ * device that first saw it (HARQ state never moves), everything else is cut into contiguous runs balanced by estimated
+ * turbo work (sum of C * K); the shares run concurrently, srsue_gpu_batch_wait gathers the results on the host.  No
+ * collective, no peer traffic.  Every other srsue_gpu_batch_* call works on the returned handle unchanged. */
+int srsue_gpu_batch_create_multi(const int *devices, int n_devices, int max_subframes, float noise_est, int noise_mode, int max_iter,
+                                 srsue_gpu_batch_t **batch);
+/* multi-GPU handles: how the last submission was split (subframes and estimated work per device, first `cap` entries);
+ * n_devices = 0 for a single-device batch */
+int srsue_gpu_batch_device_shares(const srsue_gpu_batch_t *batch, int *n_devices, int *subframes, double *work, int cap);
 void srsue_gpu_batch_destroy(srsue_gpu_batch_t *batch);
 /* what the `iq` pointer of every descriptor points at from the next submission on: SRSUE_GPU_IQ_CF32 (default) or
  * SRSUE_GPU_IQ_SC16 (int16 {re, im} pairs, sample = (float)v * scale) */

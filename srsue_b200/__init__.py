@@ -246,13 +246,28 @@ class PdschPlan:
 class Batch:
     """srsue_gpu_batch_*: heterogeneous subframe streams.  Keeps the numpy buffers alive until wait()."""
 
-    def __init__(self, ctx, max_subframes, noise_est=0.01, noise_mode=0, max_iter=4):
+    def __init__(self, ctx, max_subframes, noise_est=0.01, noise_mode=0, max_iter=4, devices=None):
+        """ctx: a Context (one device), or None with devices=[...]: srsue_gpu_batch_create_multi -- one handle over several
+        GPUs, the library owns a context, a single-device batch and a host thread per device"""
         self.ctx = ctx
         self.h = C.c_void_p()
         lib().srsue_gpu_batch_softbuffer_release.argtypes = [C.c_void_p, C.c_int64]
-        _check(lib().srsue_gpu_batch_create(ctx.h, max_subframes, C.c_float(noise_est), noise_mode, max_iter, C.byref(self.h)),
-               "srsue_gpu_batch_create")
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib().srsue_gpu_batch_create_multi(arr, len(devices), max_subframes, C.c_float(noise_est), noise_mode, max_iter,
+                                                      C.byref(self.h)), "srsue_gpu_batch_create_multi")
+        else:
+            _check(lib().srsue_gpu_batch_create(ctx.h, max_subframes, C.c_float(noise_est), noise_mode, max_iter, C.byref(self.h)),
+                   "srsue_gpu_batch_create")
         self._keep = None
+
+    def device_shares(self):
+        """multi-GPU handles: [(subframes, estimated work)] per device of the last submission"""
+        n = C.c_int()
+        sf = (C.c_int * 64)()
+        w = (C.c_double * 64)()
+        lib().srsue_gpu_batch_device_shares(self.h, C.byref(n), sf, w, 64)
+        return [(sf[i], w[i]) for i in range(n.value)]
 
     @staticmethod
     def prepare(items):

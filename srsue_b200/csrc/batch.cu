@@ -9,6 +9,10 @@
 // (plans + srsue_gpu_pdsch_decode_batch); the only device code is the row gather/scatter of soft buffers.
 #include <cuda_runtime.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -112,6 +116,28 @@ struct srsue_gpu_batch {
   std::map<int64_t, SoftBuffer> softbuffers;
   int launches = 0, plan_launches = 0;
   int half = 0;
+  // ---- multi-GPU front (srsue_gpu_batch_create_multi): this object then owns no device state of its own.  Every device
+  // has its own context, single-device batch (streams, pinned staging, plan cache, resident soft buffers) and host
+  // thread; a submission is partitioned here, the parts run concurrently, results are gathered in batch_wait.
+  // Reference analogue: N phch_workers behind one thread_pool (thread_pool.cc:206-254, phy.h:118-119).
+  struct Dev {
+    int device = 0;
+    srsue_gpu_ctx_t* ctx = nullptr;
+    srsue_gpu_batch* b = nullptr;
+    std::thread th;
+    std::vector<srsue_gpu_sf_desc_t> descs;       // this device's share of the submission (copies)
+    std::vector<int> index;                       // position of each in the caller's array
+    int rc = 0;
+    std::string err;
+    double work = 0;                              // estimated turbo work of the share (sum of C * K)
+  };
+  std::vector<Dev*> devs;
+  std::map<int64_t, int> affinity;                // soft buffer id -> device that holds it
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t generation = 0;                        // bumped by submit; workers run one submission per generation
+  int running = 0;                                // workers that have not finished the current generation
+  bool quit = false;
 };
 
 namespace {
@@ -207,8 +233,162 @@ int srsue_gpu_batch_create(srsue_gpu_ctx_t* ctx, int max_subframes, float noise_
   return 0;
 }
 
+namespace {
+
+// host thread of one device of a multi-GPU batch: runs its share of every submission through the device's own batch
+void multi_worker(srsue_gpu_batch* front, srsue_gpu_batch::Dev* d) {
+  cudaSetDevice(d->device);
+  uint64_t seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(front->mu);
+      front->cv.wait(lk, [&] { return front->quit || front->generation != seen; });
+      if (front->quit) return;
+      seen = front->generation;
+    }
+    d->rc = 0;
+    d->err.clear();
+    if (!d->descs.empty()) {
+      d->rc = srsue_gpu_batch_submit(d->b, d->descs.data(), (int)d->descs.size());
+      if (!d->rc) d->rc = srsue_gpu_batch_wait(d->b);
+      if (d->rc) d->err = srsue_gpu_last_error();          // the error text is thread-local: hand it to the caller's thread
+    }
+    {
+      std::lock_guard<std::mutex> lk(front->mu);
+      front->running--;
+    }
+    front->cv.notify_all();
+  }
+}
+
+double turbo_work(int tbs) {                                // sum of C * K of a transport block: what the decoder's time follows
+  int seg[8];
+  if (tbs <= 0 || srsue_gpu_host_cbsegm(tbs, seg)) return 1.0;
+  return (double)seg[5] * seg[3] + (double)seg[6] * seg[4] + 1.0;
+}
+
+int multi_submit(srsue_gpu_batch* f, srsue_gpu_sf_desc_t* descs, int n) {
+  const int nd = (int)f->devs.size();
+  for (auto* d : f->devs) { d->descs.clear(); d->index.clear(); d->work = 0; }
+  // HARQ state is device-resident: a soft buffer id stays on the device that first saw it.  Everything else is cut
+  // into contiguous runs (neighbouring host buffers keep merging into single copies) balanced by estimated turbo work.
+  std::vector<int> where(n, -1);
+  double total = 0;
+  for (int i = 0; i < n; i++) {
+    const double w = turbo_work(descs[i].cfg.tbs);
+    total += w;
+    if (descs[i].softbuffer_id < 0) continue;
+    auto it = f->affinity.find(descs[i].softbuffer_id);
+    if (it != f->affinity.end()) { where[i] = it->second; f->devs[it->second]->work += w; }
+  }
+  const double target = total / nd;
+  int cur = 0;
+  for (int i = 0; i < n; i++) {
+    if (where[i] >= 0) continue;
+    const double w = turbo_work(descs[i].cfg.tbs);
+    while (cur + 1 < nd && f->devs[cur]->work + 0.5 * w > target) cur++;
+    where[i] = cur;
+    f->devs[cur]->work += w;
+    if (descs[i].softbuffer_id >= 0) f->affinity[descs[i].softbuffer_id] = cur;
+  }
+  for (int i = 0; i < n; i++) {
+    auto* d = f->devs[where[i]];
+    if ((int)d->descs.size() >= d->b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: share of device %d exceeds max_subframes", d->device);
+    d->descs.push_back(descs[i]);
+    d->index.push_back(i);
+  }
+  {
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->running = nd;
+    f->generation++;
+  }
+  f->cv.notify_all();
+  f->pending = descs;
+  f->n_pending = n;
+  return 0;
+}
+
+int multi_wait(srsue_gpu_batch* f) {
+  if (!f->pending) return 0;
+  {
+    std::unique_lock<std::mutex> lk(f->mu);
+    f->cv.wait(lk, [&] { return f->running == 0; });
+  }
+  int rc = 0;
+  std::string err;
+  f->launches = 0;
+  for (auto* d : f->devs) {
+    if (d->rc && !rc) { rc = d->rc; err = "device " + std::to_string(d->device) + ": " + d->err; }
+    for (size_t k = 0; k < d->descs.size(); k++) {
+      srsue_gpu_sf_desc_t& o = f->pending[d->index[k]];
+      o.crc_ok = d->descs[k].crc_ok;
+      o.n_iter = d->descs[k].n_iter;
+      std::memcpy(o.meas, d->descs[k].meas, sizeof(o.meas));
+    }
+    f->launches += d->b->launches;
+  }
+  f->pending = nullptr;
+  f->n_pending = 0;
+  if (rc) return srsue::internal_fail(rc, err.c_str());
+  return 0;
+}
+
+void multi_destroy(srsue_gpu_batch* f) {
+  {
+    std::lock_guard<std::mutex> lk(f->mu);
+    f->quit = true;
+  }
+  f->cv.notify_all();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto* d : f->devs) {
+    if (d->th.joinable()) d->th.join();
+    cudaSetDevice(d->device);
+    if (d->b) srsue_gpu_batch_destroy(d->b);
+    if (d->ctx) srsue_gpu_ctx_destroy(d->ctx);
+    delete d;
+  }
+  cudaSetDevice(prev);
+  delete f;
+}
+
+}  // namespace
+
+int srsue_gpu_batch_create_multi(const int* devices, int n_devices, int max_subframes, float noise_est, int noise_mode, int max_iter,
+                                 srsue_gpu_batch_t** out) {
+  if (!devices || !out || n_devices < 1 || n_devices > 64 || max_subframes < 1 || max_iter < 1)
+    B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_create_multi: bad arguments");
+  *out = nullptr;
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++)
+      if (devices[i] == devices[j]) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_create_multi: device %d listed twice", devices[i]);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  auto* f = new srsue_gpu_batch();
+  f->max_subframes = max_subframes;
+  int rc = 0;
+  for (int i = 0; i < n_devices && !rc; i++) {
+    auto* d = new srsue_gpu_batch::Dev();
+    d->device = devices[i];
+    f->devs.push_back(d);
+    rc = srsue_gpu_ctx_create(&d->ctx, d->device);            // (sets the current device)
+    // any device may end up with the whole submission (all of it pinned to one device by HARQ affinity)
+    if (!rc) rc = srsue_gpu_batch_create(d->ctx, max_subframes, noise_est, noise_mode, max_iter, &d->b);
+  }
+  cudaSetDevice(prev);
+  if (rc) {
+    const std::string err = srsue_gpu_last_error();
+    multi_destroy(f);
+    return srsue::internal_fail(rc, err.c_str());
+  }
+  for (auto* d : f->devs) d->th = std::thread(multi_worker, f, d);
+  *out = f;
+  return 0;
+}
+
 void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   if (!b) return;
+  if (!b->devs.empty()) { multi_destroy(b); return; }
   cudaStreamSynchronize(b->s_compute);
   cudaStreamSynchronize(b->s_copy);
   for (auto& kv : b->plans) srsue_gpu_pdsch_plan_destroy(kv.second.plan);
@@ -226,6 +406,7 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
 int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t* b, int format, float scale) {
   if (!b || (format != SRSUE_GPU_IQ_CF32 && format != SRSUE_GPU_IQ_SC16) || (format == SRSUE_GPU_IQ_SC16 && !(scale > 0.f)))
     return srsue::internal_fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_set_iq_format: format 0 (cf32) or 1 (sc16 with a positive scale)");
+  for (auto* d : b->devs) srsue_gpu_batch_set_iq_format(d->b, format, scale);
   b->iq_format = format;
   if (format == SRSUE_GPU_IQ_SC16) b->iq16_scale = scale;
   return 0;
@@ -236,6 +417,7 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
 int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
   if (!b || !descs || n < 0 || n > b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: bad arguments (n=%d)", n);
   if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
+  if (!b->devs.empty()) return multi_submit(b, descs, n);
   const int rc = batch_submit_impl(b, descs, n);
   if (rc) {
     // Every descriptor is validated before the first launch, so a failure here is a CUDA error in the middle of the
@@ -441,6 +623,7 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
 
 int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
   if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_wait: null batch");
+  if (!b->devs.empty()) return multi_wait(b);
   if (!b->pending) return 0;
   B_CU(cudaStreamSynchronize(b->s_compute));
   for (const auto& c : b->pl_chunks)
@@ -459,6 +642,19 @@ int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
 
 int srsue_gpu_batch_softbuffer_release(srsue_gpu_batch_t* b, int64_t softbuffer_id) {
   if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "softbuffer_release: null batch");
+  if (!b->devs.empty()) {
+    if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "softbuffer_release: a submission is in flight");
+    auto a = b->affinity.find(softbuffer_id);
+    if (a == b->affinity.end()) return 0;
+    auto* d = b->devs[a->second];
+    b->affinity.erase(a);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d->device);
+    const int rc = srsue_gpu_batch_softbuffer_release(d->b, softbuffer_id);
+    cudaSetDevice(prev);
+    return rc;
+  }
   auto it = b->softbuffers.find(softbuffer_id);
   if (it == b->softbuffers.end()) return 0;
   B_CU(cudaStreamSynchronize(b->s_compute));
@@ -469,9 +665,28 @@ int srsue_gpu_batch_softbuffer_release(srsue_gpu_batch_t* b, int64_t softbuffer_
 
 int srsue_gpu_batch_stats(const srsue_gpu_batch_t* b, int* n_plans, int* n_softbuffers, int* launches) {
   if (!b) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  if (!b->devs.empty()) {
+    int np = 0, ns = 0;
+    for (auto* d : b->devs) { np += (int)d->b->plans.size(); ns += (int)d->b->softbuffers.size(); }
+    if (n_plans) *n_plans = np;
+    if (n_softbuffers) *n_softbuffers = ns;
+    if (launches) *launches = b->launches;
+    return 0;
+  }
   if (n_plans) *n_plans = (int)b->plans.size();
   if (n_softbuffers) *n_softbuffers = (int)b->softbuffers.size();
   if (launches) *launches = b->launches;
+  return 0;
+}
+
+int srsue_gpu_batch_device_shares(const srsue_gpu_batch_t* b, int* n_devices, int* subframes, double* work, int cap) {
+  if (!b) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  const int nd = (int)b->devs.size();
+  if (n_devices) *n_devices = nd;
+  for (int i = 0; i < nd && i < cap; i++) {
+    if (subframes) subframes[i] = (int)b->devs[i]->index.size();
+    if (work) work[i] = b->devs[i]->work;
+  }
   return 0;
 }
 

@@ -124,18 +124,6 @@ __device__ __forceinline__ uint32_t sign_fill(uint32_t w) {
   return r;
 }
 
-__device__ __forceinline__ void ld8(const uint4* p, uint32_t (&v)[8]) {
-  const uint4 a = __ldg(p), b = __ldg(p + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void ldp8(const uint4* p, uint32_t (&v)[8]) {      // plain (coherent) load
-  const uint4 a = p[0], b = p[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void st8(uint4* p, const uint32_t (&v)[8]) {
-  p[0] = make_uint4(v[0], v[1], v[2], v[3]);
-  p[1] = make_uint4(v[4], v[5], v[6], v[7]);
-}
 // Asynchronous 16-byte copy global -> shared (LDGSTS, L2 only).  The channel LLRs and checkpoints of the NEXT group
 // travel this way: a register-destination load would be sunk by ptxas to its first use (observed: zero prefetch
 // distance, a third of all stall samples), a copy with no destination register needs no register to be kept live.

@@ -302,3 +302,86 @@ def test_mixed_stream_of_int16_captures(gpu, oracle):
     b.submit([dict(cell=cell, cfg=cfg, iq=iq)])
     assert np.array_equal(b.wait()[0]["payload"], tb)
     b.close()
+
+
+def _multi_stream(sg, o, n_items, with_harq):
+    items, refs = [], []
+    for i in range(n_items):
+        row = MIX[i % len(MIX)]
+        ocell, ocfg, cell, cfg = _pair(sg, o, row)
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 8100 + i, row[7])
+        it = dict(cell=cell, cfg=cfg, iq=iq)
+        if with_harq and i % 3 == 0:
+            it.update(softbuffer_id=1000 + i, new_data=1)
+        items.append(it)
+        refs.append(tb)
+    return items, refs
+
+
+def test_multi_gpu_handle_on_one_device(gpu, oracle):
+    """srsue_gpu_batch_create_multi with a single device: the same submit / wait / stats calls, the library owns the context
+    and the host thread; results as the single-device batch gives them; errors of a share surface in batch_wait"""
+    sg, ctx = gpu
+    o = oracle
+    items, refs = _multi_stream(sg, o, 24, True)
+    b = sg.Batch(None, 64, devices=[0])
+    for _ in range(2):
+        b.submit(items)
+        res = b.wait()
+        assert all(r["crc_ok"] == 1 and np.array_equal(r["payload"], t) for r, t in zip(res, refs))
+    assert b.device_shares()[0][0] == len(items) and b.stats()["softbuffers"] == 8
+    b.release_softbuffer(1000)
+    assert b.stats()["softbuffers"] == 7
+    ocell, ocfg, cell, cfg = _pair(sg, o, MIX[0])
+    bad = dict(cell=cell, cfg=cfg, iq=items[0]["iq"], softbuffer_id=77, new_data=0)
+    b.submit([items[0], bad])
+    with pytest.raises(sg.GpuError):
+        b.wait()
+    b.submit(items[:4])
+    assert [r["crc_ok"] for r in b.wait()] == [1, 1, 1, 1]
+    b.close()
+
+
+def test_multi_gpu_dispatch_pins_harq_processes(gpu, oracle):
+    """two GPUs behind one handle: the submission is split by estimated turbo work, every HARQ process stays on the device
+    that first saw it (rv 2 finds the soft buffer rv 0 left there), transport blocks equal the oracle's"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sg, ctx = gpu
+    o = oracle
+    row = (25, 1, 6, 11448, 1, 2, 2, 11.0)
+    b = sg.Batch(None, 64, devices=[0, 1])
+    filler, frefs = _multi_stream(sg, o, 16, False)
+    sb_o, verdicts = {}, []
+    for rv in (0, 2):
+        items, refs = [], []
+        for k, sid in enumerate((7, 9, 11, 13)):
+            ocell, ocfg, cell, cfg = _pair(sg, o, row, rv)
+            tb, iq, _ = o.gen_subframe(ocell, ocfg, 420 + k, row[7])
+            items.append(dict(cell=cell, cfg=cfg, iq=iq, softbuffer_id=sid, new_data=1 if rv == 0 else 0))
+            refs.append((sid, ocell, ocfg, iq))
+            items += filler[4 * k:4 * k + 4]
+            refs += [None] * 4
+        b.submit(items)
+        res = b.wait()
+        shares = b.device_shares()
+        assert len(shares) == 2 and all(n > 0 for n, _ in shares) and sum(n for n, _ in shares) == len(items)
+        assert max(w for _, w in shares) < 1.6 * min(w for _, w in shares)
+        fi = 0
+        for r, ref in zip(res, refs):
+            if ref is None:
+                assert r["crc_ok"] == 1 and np.array_equal(r["payload"], frefs[fi])
+                fi += 1
+                continue
+            sid, ocell, ocfg, iq = ref
+            sb_o.setdefault(sid, o.new_softbuf(o.cbsegm(ocfg.tbs).C))
+            sf_o = o.ofdm_rx(row[0], iq)
+            ce_o, _ = o.chest(ocell, row[5], sf_o)
+            rc, pl = o.pdsch_decode(ocell, ocfg, sf_o, ce_o, 0.01, 4, softbuf=sb_o[sid])
+            assert (r["crc_ok"] == 1) == (rc == 0) and np.array_equal(r["payload"], pl)
+            verdicts.append((rv, rc == 0))
+    assert all(ok for rv, ok in verdicts if rv == 2) and not all(ok for rv, ok in verdicts if rv == 0)
+    assert b.stats()["softbuffers"] == 4
+    b.close()
+

@@ -453,9 +453,11 @@ def test_cpp_offline_driver_worker_and_batch(gpu, oracle, tmp_path):
         f.write(struct.pack("<12i", 0x53525355, prb, 1, 1, 1, 1, 0x1234, qm, tbs, 0, n, 4))
         f.write(iq.tobytes())
     ref = [o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 0, 4) for i in range(n)]
-    for mode in ("worker", "batch"):
-        outp = tmp_path / ("out_%s.bin" % mode)
-        subprocess.check_call([exe, mode, str(inp), str(outp)])
+    import torch
+    modes = [("worker", []), ("batch", []), ("batch", ["--gpus", str(min(2, torch.cuda.device_count()))])]   # the last: multi-GPU handle
+    for mode, extra in modes:
+        outp = tmp_path / ("out_%s%s.bin" % (mode, "_multi" if extra else ""))
+        subprocess.check_call([exe, mode, str(inp), str(outp)] + extra)
         raw = open(outp, "rb").read()
         rec = 12 + tbs // 8
         assert len(raw) == n * rec
