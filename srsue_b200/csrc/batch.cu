@@ -482,7 +482,11 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
     int rc = get_plan(b, gk.substr(0, gk.size() - 1), descs[idx[0]], &pe);
     if (rc) return rc;
     const srsue_gpu_plan_info_t& info = pe->info;
-    const size_t cap = (size_t)b->chunk_cap;
+    // chunk size: uploads of chunk c + 1 overlap the decoding of chunk c (two staging halves, two streams), so a large
+    // bucket is cut into pieces of about 24 MB of samples (100 subframes at 20 MHz) instead of going up in one copy
+    // that nothing overlaps; small buckets stay whole (a chunk costs half a dozen launches)
+    const size_t sample_bytes = (size_t)info.sf_len * (b->iq_format == SRSUE_GPU_IQ_SC16 ? 4 : sizeof(srsue_gpu_cf_t));
+    const size_t cap = std::min<size_t>((size_t)b->chunk_cap, std::max<size_t>(32, ((size_t)24 << 20) / sample_bytes));
     for (int i = 0; i < 2; i++) { rc = grow(&b->d_iq[i], &b->iq_elems[i], cap * info.sf_len, b->s_compute); if (rc) return rc; }
     rc = grow(&b->d_payload, &b->payload_bytes, cap * info.payload_stride, b->s_compute);
     if (rc) return rc;
