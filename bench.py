@@ -711,6 +711,18 @@ def main():
             "clocks": sampler.summary(),
         }
         out["e2e"]["sc16"] = {k: out["e2e_sc16"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+        # what the box gives: plain cudaMemcpyAsync from pinned memory to N GPUs at once (tools/h2d_ceiling.cu)
+        try:
+            ceil = json.load(open(os.path.join(ROOT, "profiles", "h2d_ceiling_r02.json")))
+            c = [r["gb_per_s"] for r in ceil["runs"] if r["n_gpus"] == world and r["variant"] == "pinned"]
+            if c:
+                sf_per_s = out["e2e"]["value"] * 1e6 / WORKLOAD["tbs"]
+                out["e2e"]["h2d_gb_per_s"] = sf_per_s * I.sf_len * 8 / 1e9
+                out["e2e"]["h2d_ceiling_gb_per_s"] = c[0]
+                out["e2e"]["frac_of_h2d_ceiling"] = out["e2e"]["h2d_gb_per_s"] / c[0]
+                out["e2e"]["ceiling_source"] = "profiles/h2d_ceiling_r02.json (all N GPUs copying concurrently from pinned host memory)"
+        except Exception:  # noqa: BLE001
+            pass
         if multi:
             multi["vs_e2e_of_the_rank_per_gpu_path"] = multi["value"] / out["e2e"]["value"]
             out["multi_gpu_dispatcher"] = multi

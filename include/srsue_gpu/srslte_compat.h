@@ -208,10 +208,13 @@ SRSLTE_API int srslte_ue_dl_find_dl_dci_type(srslte_ue_dl_t *q, srslte_dci_msg_t
 /* uplink grant search (phch_worker.cc:426): DCI format 0 in the UE-specific space; 1 found / 0 / < 0 */
 /* DCI payload -> unpacked fields -> grant (phch_worker.cc:297).  Formats 1A and 1, FDD; allocation types 0, 1 and 2,
  * localized and distributed (36.211 6.2.3.2: the grant's two slot masks then differ).  Transport-block sizes come from the 27 x 110 table of 36.213
- * 7.1.7.2.1, which the caller installs once per process with srsue_gpu_ra_set_tbs_table(); until then every call that
- * needs a size returns SRSLTE_ERROR with a message.  Returns 0 on success (as srsLTE does). */
+ * 7.1.7.2.1: the caller installs it once per process with srsue_gpu_ra_set_tbs_table(); until then the thirteen built-in
+ * columns serve (srsue_gpu_ra_builtin_tbs_columns) and a call that needs any other size returns SRSLTE_ERROR with a message.  Returns 0 on success (as srsLTE does). */
 SRSLTE_API int srsue_gpu_ra_set_tbs_table(const int32_t *table, uint32_t nof_rows /* 27 */, uint32_t nof_cols /* 110 */);
 SRSLTE_API int srsue_gpu_ra_have_tbs_table(void);
+/* columns of the table this library carries itself (N_PRB = 1..6, 10, 15, 25, 50, 75, 100, 110; tbs_table.inc, written from
+ * memory and checked structurally) -- used until the whole table is installed; returns their number */
+SRSLTE_API int srsue_gpu_ra_builtin_tbs_columns(int32_t *n_prb, int cap);
 SRSLTE_API int srslte_dci_msg_to_dl_grant(srslte_dci_msg_t *msg, uint16_t msg_rnti, uint32_t nof_prb, srslte_ra_dl_dci_t *dl_dci,
                                           srslte_ra_dl_grant_t *grant);
 SRSLTE_API int srslte_dci_msg_unpack_pdsch(srslte_dci_msg_t *msg, srslte_ra_dl_dci_t *data, uint32_t nof_prb, bool crc_is_crnti);

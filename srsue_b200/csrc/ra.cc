@@ -5,9 +5,10 @@
 // 7.1.7.1 (MCS -> modulation, I_TBS) and 7.1.7.2.1 (transport block size).  srsLTE itself is an un-vendored
 // dependency of the reference, so parity is anchored on the reference's call site and on the packer in tests/.
 //
-// The 27 x 110 transport-block-size table (36.213 Table 7.1.7.2.1-1) is published data this tree does not carry; the
-// caller installs it once with srsue_gpu_ra_set_tbs_table() (srsLTE keeps it as tbs_table[27][110] in
-// lib/phch/tbs_tables.h).  Without it every conversion that needs a size fails loudly.
+// The 27 x 110 transport-block-size table (36.213 Table 7.1.7.2.1-1) is published data; this tree carries the thirteen
+// columns it could write down and check structurally (tbs_table.inc), the caller installs the whole table once with
+// srsue_gpu_ra_set_tbs_table() (srsLTE keeps it as tbs_table[27][110] in lib/phch/tbs_tables.h), which takes
+// precedence.  A size that neither source has fails loudly.
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -18,6 +19,8 @@
 #include "srsue_gpu/srslte_compat.h"
 
 namespace {
+
+#include "tbs_table.inc"
 
 std::mutex g_tbs_mu;
 std::vector<int32_t> g_tbs;                 // 27 rows (I_TBS) x 110 columns (N_PRB - 1)
@@ -84,6 +87,12 @@ int srsue_gpu_ra_set_tbs_table(const int32_t* table, uint32_t nof_rows, uint32_t
 
 int srsue_gpu_ra_have_tbs_table(void) { return g_tbs_set.load() ? 1 : 0; }
 
+int srsue_gpu_ra_builtin_tbs_columns(int32_t* n_prb, int cap) {
+  const int n = (int)(sizeof(kTbsBuiltinCols) / sizeof(kTbsBuiltinCols[0]));
+  for (int i = 0; i < n && i < cap && n_prb; i++) n_prb[i] = kTbsBuiltinCols[i];
+  return n;
+}
+
 uint32_t srslte_ra_type0_P(uint32_t nof_prb) { return rbg_size(nof_prb); }
 
 uint32_t srslte_ra_type2_n_rb(uint32_t nof_prb) { return (uint32_t)ceil_log2(nof_prb * (nof_prb + 1) / 2); }
@@ -109,7 +118,10 @@ srslte_mod_t srslte_ra_mod_from_mcs(uint32_t mcs_idx) {
 int srslte_ra_tbs_from_idx(uint32_t tbs_idx, uint32_t n_prb) {
   if (tbs_idx >= 27 || n_prb < 1 || n_prb > 110) return SRSLTE_ERROR;
   if (!g_tbs_set.load()) {
-    fprintf(stderr, "[srsue_gpu] srslte_ra_tbs_from_idx: no transport-block-size table installed (srsue_gpu_ra_set_tbs_table)\n");
+    for (size_t c = 0; c < sizeof(kTbsBuiltinCols) / sizeof(kTbsBuiltinCols[0]); c++)
+      if (kTbsBuiltinCols[c] == (int)n_prb) return kTbsBuiltin[c][tbs_idx];
+    fprintf(stderr, "[srsue_gpu] srslte_ra_tbs_from_idx: N_PRB = %u is not among the built-in columns and no transport-block-size table "
+                    "is installed (srsue_gpu_ra_set_tbs_table)\n", n_prb);
     return SRSLTE_ERROR;
   }
   std::lock_guard<std::mutex> lk(g_tbs_mu);

@@ -141,13 +141,54 @@ def test_retransmission_mcs(L):
 
 
 def test_no_table_fails_loudly():
-    """A fresh process has no size table: conversions that need one return an error and say why."""
+    """A fresh process has only the built-in columns: a size outside them returns an error and says why."""
     import subprocess, sys
     code = ("import ctypes as C, srsue_b200 as sg; L = sg.lib(); "
-            "assert L.srsue_gpu_ra_have_tbs_table() == 0; assert L.srslte_ra_tbs_from_idx(3, 10) < 0")
+            "assert L.srsue_gpu_ra_have_tbs_table() == 0; assert L.srslte_ra_tbs_from_idx(3, 11) < 0; "
+            "assert L.srslte_ra_tbs_from_idx(3, 10) == 568")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
-    assert "no transport-block-size table installed" in r.stderr
+    assert "no transport-block-size table" in r.stderr
+
+
+def test_builtin_tbs_columns_have_the_structure_of_the_standard_table():
+    """36.213 Table 7.1.7.2.1-1 cannot be read offline; the thirteen columns the library carries (tbs_table.inc, written
+    from memory) are checked against every structural property of the real table: multiples of 8, strictly increasing in
+    I_TBS, non-decreasing in N_PRB, and -- the selective one -- TBS + 24 segments into code blocks with zero filler bits
+    (36.212 5.1.2).  Anchors: the sizes BASELINE.md and the reference's configs name."""
+    import subprocess, sys
+    code = r"""
+import ctypes as C, json, srsue_b200 as sg
+L = sg.lib()
+cols = (C.c_int32 * 32)()
+n = L.srsue_gpu_ra_builtin_tbs_columns(cols, 32)
+seg = (C.c_int * 8)()
+out = {}
+for c in list(cols)[:n]:
+    col = []
+    for i in range(27):
+        t = L.srslte_ra_tbs_from_idx(i, c)
+        assert L.srsue_gpu_host_cbsegm(t, seg) == 0
+        col.append((t, seg[7]))
+    out[c] = col
+print(json.dumps(out))
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)      # fresh process: nothing installed
+    assert r.returncode == 0, r.stderr
+    import json
+    tab = {int(k): v for k, v in json.loads(r.stdout).items()}
+    assert sorted(tab) == [1, 2, 3, 4, 5, 6, 10, 15, 25, 50, 75, 100, 110]
+    for n_prb, col in tab.items():
+        sizes = [t for t, _ in col]
+        assert all(t % 8 == 0 and t >= 16 for t in sizes), n_prb
+        assert all(b > a for a, b in zip(sizes, sizes[1:])), n_prb
+        assert all(F == 0 for _, F in col), (n_prb, [t for t, F in col if F])          # no filler bits, ever
+    ns = sorted(tab)
+    for i in range(27):
+        row = [tab[n][i][0] for n in ns]
+        assert all(b >= a for a, b in zip(row, row[1:])), i
+    assert tab[100][26][0] == 75376 and tab[75][26][0] == 55056 and tab[100][15][0] == 30576 and tab[6][0][0] == 152
+    assert tab[25][20][0] == 11448 and tab[110][26][0] == 75376 and tab[1][0][0] == 16 and tab[1][26][0] == 712
 
 
 def test_cqi_helpers(L):
