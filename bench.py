@@ -274,11 +274,27 @@ def run_mixed(args, rank, local_rank, world):
     # ---- inputs of this rank: 4 distinct subframes per shape, tiled, in pinned host memory -------------
     ctx = sg.Context(local_rank)
     shapes, pinned = {}, []
+    tbs_entries = {}
     for m in sorted({batches[i][0] for i in mine}):
         prb, ports, qm, tbs, tm, _ = MIXED[m]
         ocell = o.make_cell(prb, ports, 1)
         ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=tm)
-        gen = [o.gen_subframe(ocell, ocfg, 50000 + 100 * m + i + 1000 * rank, MIXED_SNR[qm]) for i in range(4)]
+        dcis = None
+        if args.blind:
+            # a format 1A DCI for the full-band allocation of this shape in the first UE-specific candidate; its size goes
+            # into the (synthetic, test-style) size table because these shapes are not rows of 36.213 Table 7.1.7.2.1-1
+            from tests.srslte_ctypes import DciMsg, RaDlDci
+            mcs = {2: 5, 4: 12, 6: 22}[qm]
+            tbs_entries[(mcs if mcs < 10 else mcs - 1 if mcs < 17 else mcs - 2, prb)] = tbs
+            sent = RaDlDci()
+            sent.mcs_idx, sent.rv_idx, sent.alloc_type = mcs, 0, 2
+            sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = 0, prb, 1
+            msg = DciMsg()
+            nb = lib.srslte_dci_msg_pack_pdsch(C.byref(sent), 2, C.byref(msg), prb, True)
+            rk, _ = o.pdcch_regs(ocell, 1, 6)
+            ss = o.pdcch_search_space(len(rk) // 9, 1, 0x1234)
+            dcis = [(np.frombuffer(msg.data, np.uint8)[:nb].copy(), 0x1234, ss[0][0], ss[0][1])]
+        gen = [o.gen_subframe(ocell, ocfg, 50000 + 100 * m + i + 1000 * rank, MIXED_SNR[qm], None, pcfich=args.blind, dcis=dcis) for i in range(4)]
         cell = sg.make_cell(prb, ports, 1)
         shapes[m] = dict(ocell=ocell, ocfg=ocfg, cell=cell, cfg=sg.make_cfg(cell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=tm),
                          tb=[g[0] for g in gen], iq=[g[1] for g in gen], tbs=tbs)
@@ -304,7 +320,22 @@ def run_mixed(args, rank, local_rank, world):
     items = [items[i] for i in perm]
     truth = [truth[i] for i in perm]
     batch = sg.Batch(ctx, len(items), 0.01, 0, args.max_iter)
+    if args.blind:
+        from tests.srslte_ctypes import install_tbs_table
+        install_tbs_table(lib, tbs_entries)
+        for it in items:                                  # the library is told the subframe number and the RNTI, nothing else
+            it["cfg"] = sg.make_cfg(it["cell"], sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=0)
     prepared = sg.Batch.prepare(items)
+    pl_cap = max(sh["tbs"] for sh in shapes.values()) // 8
+
+    def submit():
+        if args.blind:
+            batch._keep = None
+            rc = lib.srsue_gpu_batch_submit_blind(batch.h, prepared[0], len(prepared[0]), 6, pl_cap)
+            assert rc == 0, lib.srsue_gpu_last_error()
+            batch._keep, batch._blind = prepared, True
+        else:
+            batch.submit_prepared(prepared)
 
     def barrier():
         torch.cuda.synchronize()
@@ -313,9 +344,9 @@ def run_mixed(args, rank, local_rank, world):
             torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        batch.submit_prepared(prepared)
+        submit()
         res = batch.wait()
-    verified = all(r["crc_ok"] == 1 and np.array_equal(r["payload"], t) for r, t in zip(res, truth))
+    verified = all(r["crc_ok"] == 1 and np.array_equal(r["payload"][:len(t)], t) for r, t in zip(res, truth))
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -323,8 +354,9 @@ def run_mixed(args, rank, local_rank, world):
     bits = 0
     launches = 0
     for _ in range(args.steps):
-        batch.submit_prepared(prepared)
+        submit()
         lib.srsue_gpu_batch_wait(batch.h)
+        batch._keep = None
         launches += batch.stats()["launches"]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -349,7 +381,8 @@ def run_mixed(args, rank, local_rank, world):
                           ", ".join("%dPRB/%dport/Qm%d/TBS%d %.0f%%" % (a, b, c, d, 100 * f) for a, b, c, d, e, f in MIXED),
                           "subframes_per_step": sf_all / args.steps, "batches": len(batches), "max_iter": args.max_iter,
                           "parallelism": "batches assigned to GPUs by estimated turbo work, no collective",
-                          "api": "srsue_gpu_batch_submit/_wait, host buffers"},
+                          "api": ("srsue_gpu_batch_submit_blind/_wait: PCFICH + PDCCH search + DCI -> grant in the library, host buffers"
+                                  if args.blind else "srsue_gpu_batch_submit/_wait, host buffers")},
                "subframes_per_s": sf_all / dt_max, "verified_bit_exact_payload": bool(verified),
                "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": iq_all, "d2h_bytes_per_step": pl_all},
                "gpu_launches": int(launches_all), "clocks": sampler.summary()}
@@ -386,6 +419,8 @@ def main():
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic subframes (tiled to the batch)")
     ap.add_argument("--waterfall-snr", type=float, default=21.5, help="SNR of the waterfall leg (first-transmission BLER about 0.2)")
     ap.add_argument("--no-legs", action="store_true", help="skip the fixed-4-iteration and waterfall legs")
+    ap.add_argument("--blind", action="store_true", help="--workload mixed: the caller supplies no CFI and no grant, the library decodes "
+                                                         "PCFICH and PDCCH for every capture (srsue_gpu_batch_submit_blind)")
     ap.add_argument("--snr", type=float, default=30.0)
     ap.add_argument("--max-iter", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -145,6 +145,10 @@ int srsue_gpu_pdsch_plan_set_iq_format(srsue_gpu_pdsch_plan_t *plan, int format,
  * what srslte_pdsch_decode_rnti does with the budget of srslte_sch_set_max_noi, phch_worker.cc:88).  min_iter = max_iter
  * gives a fixed iteration count with the CRC verdicts still reported -- the "fixed 4 iterations" measurement of SURVEY 7.3. */
 int srsue_gpu_pdsch_plan_set_min_iter(srsue_gpu_pdsch_plan_t *plan, int min_iter);
+/* PDCCH calls of this plan (srsue_gpu_pdcch_extract_llr / _find_dci) skip every subframe i with d_values[i] != want and
+ * report "not found" for it; (NULL, 0) switches the filter off.  A plan's control region belongs to one CFI: a batch
+ * whose subframes carry different CFIs (d_values = the output of srsue_gpu_pcfich_decode) runs each plan on its own rows. */
+int srsue_gpu_pdsch_plan_set_row_filter(srsue_gpu_pdsch_plan_t *plan, const int32_t *d_values, int want);
 /* d_ce [n_sf][ports][14*nsc]; d_meas [n_sf][5] = noise, rsrp, rssi, rsrq, snr */
 int srsue_gpu_chest(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols, srsue_gpu_cf_t *d_ce,
                     float *d_meas, void *stream);
@@ -259,6 +263,15 @@ int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t *batch, int format, float sc
  * buffers must stay valid until srsue_gpu_batch_wait, which also fills the out fields of every descriptor */
 int srsue_gpu_batch_submit(srsue_gpu_batch_t *batch, srsue_gpu_sf_desc_t *descs, int n);
 int srsue_gpu_batch_wait(srsue_gpu_batch_t *batch);
+/* The reference's own sequence for a whole batch (phch_worker.cc:254-297): the caller knows the cell, the subframe number
+ * and the RNTI of every capture, nothing else.  Phase 1 runs FFT + channel estimate + PCFICH (-> CFI) + the PDCCH blind
+ * search for the RNTI (formats 1A then 1 in the UE-specific space, 1A in the common space; SI / RA / P-RNTI: 1A in the
+ * common space) over the whole batch; the DCIs become grants on the host (srslte_dci_msg_to_dl_grant: needs the sizes of
+ * srsue_gpu_ra_set_tbs_table or the built-in columns); phase 2 is the PDSCH chain bucketed by grant, fed from the samples
+ * that are already on the device.  In: cell, cfg.sf_idx, cfg.rnti, iq, payload (payload_cap bytes each).  Out: the rest of
+ * cfg and the usual results after srsue_gpu_batch_wait; no DCI for the RNTI: cfg.tbs = 0, crc_ok = 0.  ng_x6 = 6 x the
+ * PHICH Ng of the cell's MIB.  Subframes are decoded as new transmissions (no soft-buffer ids). */
+int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t *batch, srsue_gpu_sf_desc_t *descs, int n, int ng_x6, int payload_cap);
 /* frees the device soft buffer of one id (a HARQ process that was acknowledged or flushed) */
 int srsue_gpu_batch_softbuffer_release(srsue_gpu_batch_t *batch, int64_t softbuffer_id);
 /* cached plans, resident soft buffers, kernels launched by the last submission */

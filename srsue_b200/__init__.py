@@ -301,12 +301,30 @@ class Batch:
     def submit(self, items):
         self.submit_prepared(self.prepare(items))
 
+    def submit_blind(self, items, ng_x6=6, payload_cap=None):
+        """srsue_gpu_batch_submit_blind: items carry cell, cfg (only sf_idx and rnti are read), iq and a payload buffer of
+        payload_cap bytes; CFI, grant and transport block come back (wait() results gain 'cfg')"""
+        import numpy as np
+        if payload_cap is None:
+            payload_cap = 75376 // 8
+        for it in items:
+            it.setdefault("payload", np.zeros(payload_cap, np.uint8))
+        prepared = self.prepare(items)
+        self._keep = None
+        _check(lib().srsue_gpu_batch_submit_blind(self.h, prepared[0], len(prepared[0]), ng_x6, payload_cap), "srsue_gpu_batch_submit_blind")
+        self._keep = prepared
+        self._blind = True
+
     def wait(self):
         _check(lib().srsue_gpu_batch_wait(self.h), "srsue_gpu_batch_wait")
         if self._keep is None:
             return []
         descs, payloads, _ = self._keep
         self._keep = None
+        if getattr(self, "_blind", False):
+            self._blind = False
+            return [dict(payload=pl[:(d.cfg.tbs + 7) // 8], crc_ok=d.crc_ok, n_iter=d.n_iter, meas=list(d.meas), cfg=d.cfg,
+                         tbs=d.cfg.tbs, cfi=d.cfg.cfi) for d, pl in zip(descs, payloads)]
         return [dict(payload=pl, crc_ok=d.crc_ok, n_iter=d.n_iter, meas=list(d.meas)) for d, pl in zip(descs, payloads)]
 
     def release_softbuffer(self, sid):

@@ -266,6 +266,7 @@ struct srsue_gpu_pdsch_plan {
   float2* d_iq = nullptr; uint8_t* d_payload = nullptr; int32_t* d_tb_status = nullptr;
   const int32_t* cfo_steps = nullptr; int32_t cfo_step_all = 0;            // carrier-offset correction of the batch calls
   int min_iter = 1;                                                          // srsue_gpu_pdsch_plan_set_min_iter
+  const int32_t* row_filter = nullptr; int row_want = 0;                     // srsue_gpu_pdsch_plan_set_row_filter
   int iq_format = SRSUE_GPU_IQ_CF32; float iq16_scale = 1.0f / 32768.0f;   // what the d_iq / h_iq arguments of the batch calls point at
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[8] = {};
@@ -680,6 +681,12 @@ int srsue_gpu_pdsch_plan_set_cfo(srsue_gpu_pdsch_plan_t* p, const int32_t* d_cfo
   return 0;
 }
 
+int srsue_gpu_pdsch_plan_set_row_filter(srsue_gpu_pdsch_plan_t* p, const int32_t* d_values, int want) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  p->row_filter = d_values; p->row_want = want;
+  return 0;
+}
+
 int srsue_gpu_pdsch_plan_set_min_iter(srsue_gpu_pdsch_plan_t* p, int min_iter) {
   if (!p || min_iter < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "set_min_iter: null plan or min_iter < 1");
   p->min_iter = min_iter;
@@ -823,9 +830,11 @@ int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue
   a.re4 = p->d_pd_re4; a.src = p->d_pd_src; a.scramble = p->d_pd_scr; a.llr = d_llr;
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.n_reg = p->pd_nreg; a.noise_mode = noise_mode;
   a.noise_est = noise_est; a.k_sqpsk = (float)(100.0 * std::sqrt(2.0)); a.k_sq2 = (float)std::sqrt(2.0);
+  a.row_filter = p->row_filter; a.row_want = p->row_want;
   for (int done = 0; done < n_sf; done += 65535) {
     const int n = std::min(65535, n_sf - done);
     PdcchLlrArgs b = a;
+    if (b.row_filter) b.row_filter += done;
     b.sf_symbols += (size_t)done * 14 * a.nsc; b.ce += (size_t)done * a.nof_ports * 14 * a.nsc;
     if (b.meas) b.meas += (size_t)done * 5;
     b.llr += (size_t)done * 8 * a.n_reg; b.n_sf = n;
@@ -855,6 +864,7 @@ int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t* p, int n_sf, const int16_t*
   PdcchSearchArgs a{};
   a.llr = d_llr; a.llr_stride = 8LL * p->pd_nreg; a.rm_seq = it->second; a.found = d_found; a.bits = d_bits; a.rem = d_rem;
   a.n_sf = n_sf; a.nof_bits = nof_bits; a.rnti = rnti; a.first_bit = first_bit < 0 ? -1 : (first_bit ? 1 : 0);
+  a.row_filter = p->row_filter; a.row_want = p->row_want;
   a.n_cand = pdcch_search_space(p->pd_nreg / 9, p->cfg.sf_idx, (uint16_t)rnti, common != 0, a.cand_L, a.cand_ncce);
   if (a.n_cand == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdcch_find_dci: empty search space");
   const int per_words = 3 * D + 4 * D + (D + 3) / 4;

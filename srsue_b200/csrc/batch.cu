@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "srsue_gpu/srslte_compat.h"
 #include "srsue_gpu/srsue_gpu.h"
 
 namespace srsue {
@@ -79,6 +80,7 @@ struct PlanEntry {
   srsue_gpu_pdsch_plan_t* plan = nullptr;
   srsue_gpu_plan_info_t info{};
   std::list<std::string>::iterator lru;
+  bool front = false;                             // front-end-only plan (no grant)
 };
 
 struct SoftBuffer { int16_t* d = nullptr; int elems = 0; };
@@ -116,6 +118,19 @@ struct srsue_gpu_batch {
   std::map<int64_t, SoftBuffer> softbuffers;
   int launches = 0, plan_launches = 0;
   int half = 0;
+  // ---- blind submissions (srsue_gpu_batch_submit_blind): the samples of the whole submission stay on the device between
+  // the control-channel phase and the PDSCH phase; phase 2 gathers its chunks from there instead of from host memory
+  bool iq_on_device = false;
+  char* d_biq = nullptr; size_t biq_bytes = 0;
+  srsue_gpu_cf_t* d_bsf = nullptr; size_t bsf_elems = 0;
+  srsue_gpu_cf_t* d_bce = nullptr; size_t bce_elems = 0;
+  int16_t* d_bllr = nullptr; size_t bllr_elems = 0;
+  int32_t* d_bcfi = nullptr; int32_t* d_bfound = nullptr; uint8_t* d_bbits = nullptr;     // [cap], [9][cap][4], [9][cap][64]
+  int32_t* h_bcfi = nullptr; int32_t* h_bfound = nullptr; uint8_t* h_bbits = nullptr;     // pinned mirrors
+  std::vector<srsue_gpu_sf_desc_t> blind_descs;   // phase-2 descriptors (grants filled in, iq = device row)
+  std::vector<int> blind_index;                   // their positions in the caller's array
+  srsue_gpu_sf_desc_t* blind_orig = nullptr;
+  int blind_n = 0;
   // ---- multi-GPU front (srsue_gpu_batch_create_multi): this object then owns no device state of its own.  Every device
   // has its own context, single-device batch (streams, pinned staging, plan cache, resident soft buffers) and host
   // thread; a submission is partitioned here, the parts run concurrently, results are gathered in batch_wait.
@@ -131,6 +146,7 @@ struct srsue_gpu_batch {
     std::string err;
     double work = 0;                              // estimated turbo work of the share (sum of C * K)
   };
+  int multi_blind = 0, multi_blind_run = 0, multi_ng_x6 = 6, multi_payload_cap = 0;   // how the workers submit their share
   std::vector<Dev*> devs;
   std::map<int64_t, int> affinity;                // soft buffer id -> device that holds it
   std::mutex mu;
@@ -159,15 +175,24 @@ int get_plan(srsue_gpu_batch* b, const std::string& key, const srsue_gpu_sf_desc
     *out = &it->second;
     return 0;
   }
-  if ((int)b->plans.size() >= b->max_plans) {
-    // evict the least recently used plan; its work may still be in flight on the compute stream
+  // Two budgets: plans with a grant own per-subframe work buffers (hundreds of MB at 20 MHz) and are limited to max_plans;
+  // front-end-only plans (tbs = 0: tables for FFT, estimate, PCFICH, PDCCH of one (cell, subframe, CFI)) are small and a
+  // blind submission needs three per cell and subframe number, so they get their own, larger budget.
+  const bool front = d.cfg.tbs == 0;
+  int n_kind = 0;
+  for (const auto& kv : b->plans) n_kind += kv.second.front == front;
+  if (n_kind >= (front ? 8 * b->max_plans : b->max_plans)) {
+    // evict the least recently used plan of this kind; its work may still be in flight on the compute stream
     B_CU(cudaStreamSynchronize(b->s_compute));
-    const std::string victim = b->lru.back();
-    b->lru.pop_back();
+    auto it2 = b->lru.end();
+    do { --it2; } while (b->plans[*it2].front != front);
+    const std::string victim = *it2;
+    b->lru.erase(it2);
     srsue_gpu_pdsch_plan_destroy(b->plans[victim].plan);
     b->plans.erase(victim);
   }
   PlanEntry e;
+  e.front = front;
   int rc = srsue_gpu_pdsch_plan_create(b->ctx, &d.cell, &d.cfg, b->chunk_cap, &e.plan);
   if (rc) return rc;
   srsue_gpu_pdsch_plan_info(e.plan, &e.info);
@@ -249,7 +274,8 @@ void multi_worker(srsue_gpu_batch* front, srsue_gpu_batch::Dev* d) {
     d->rc = 0;
     d->err.clear();
     if (!d->descs.empty()) {
-      d->rc = srsue_gpu_batch_submit(d->b, d->descs.data(), (int)d->descs.size());
+      d->rc = front->multi_blind_run ? srsue_gpu_batch_submit_blind(d->b, d->descs.data(), (int)d->descs.size(), front->multi_ng_x6, front->multi_payload_cap)
+                                     : srsue_gpu_batch_submit(d->b, d->descs.data(), (int)d->descs.size());
       if (!d->rc) d->rc = srsue_gpu_batch_wait(d->b);
       if (d->rc) d->err = srsue_gpu_last_error();          // the error text is thread-local: hand it to the caller's thread
     }
@@ -300,6 +326,7 @@ int multi_submit(srsue_gpu_batch* f, srsue_gpu_sf_desc_t* descs, int n) {
   {
     std::lock_guard<std::mutex> lk(f->mu);
     f->running = nd;
+    f->multi_blind_run = f->multi_blind;
     f->generation++;
   }
   f->cv.notify_all();
@@ -323,6 +350,7 @@ int multi_wait(srsue_gpu_batch* f) {
       srsue_gpu_sf_desc_t& o = f->pending[d->index[k]];
       o.crc_ok = d->descs[k].crc_ok;
       o.n_iter = d->descs[k].n_iter;
+      if (f->multi_blind_run) o.cfg = d->descs[k].cfg;
       std::memcpy(o.meas, d->descs[k].meas, sizeof(o.meas));
     }
     f->launches += d->b->launches;
@@ -398,6 +426,8 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   cudaFreeHost(b->h_status); cudaFreeHost(b->h_meas); cudaFreeHost(b->h_rows);
   cudaFreeHost(b->h_iq[0]); cudaFreeHost(b->h_iq[1]); cudaFreeHost(b->h_pl);
   cudaFreeHost(b->h_iq_rows); cudaFreeHost(b->h_pl_rows);
+  cudaFree(b->d_biq); cudaFree(b->d_bsf); cudaFree(b->d_bce); cudaFree(b->d_bllr); cudaFree(b->d_bcfi); cudaFree(b->d_bfound); cudaFree(b->d_bbits);
+  cudaFreeHost(b->h_bcfi); cudaFreeHost(b->h_bfound); cudaFreeHost(b->h_bbits);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(b->ev_up[i]); cudaEventDestroy(b->ev_free[i]); }
   cudaStreamDestroy(b->s_compute); cudaStreamDestroy(b->s_copy);
   delete b;
@@ -503,10 +533,10 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
       auto row_ptr = [&](int r) { return reinterpret_cast<const char*>(descs[idx[off + r]].iq); };
       for (int r = 1; r < m; r++) runs += row_ptr(r) != row_ptr(r - 1) + row_bytes;
       const size_t pos_up = b->order.size();
-      bool zero_copy = runs > 4;
+      bool zero_copy = runs > 4 || b->iq_on_device;
       uintptr_t align_or = 0;
       for (int r = 0; r < m && zero_copy; r++) {
-        zero_copy = srsue::host_region_contains(descs[idx[off + r]].iq, row_bytes);
+        zero_copy = b->iq_on_device || srsue::host_region_contains(descs[idx[off + r]].iq, row_bytes);
         align_or |= reinterpret_cast<uintptr_t>(descs[idx[off + r]].iq);
       }
       if (zero_copy) {
@@ -628,7 +658,10 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
 int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
   if (!b) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_wait: null batch");
   if (!b->devs.empty()) return multi_wait(b);
-  if (!b->pending) return 0;
+  if (!b->pending) {
+    if (b->blind_orig) { b->blind_orig = nullptr; b->blind_n = 0; }       // a blind submission in which no grant was found
+    return 0;
+  }
   B_CU(cudaStreamSynchronize(b->s_compute));
   for (const auto& c : b->pl_chunks)
     for (int r = 0; r < c.rows; r++)
@@ -639,8 +672,209 @@ int srsue_gpu_batch_wait(srsue_gpu_batch_t* b) {
     d.n_iter = b->h_status[pos * 4 + 2];
     std::memcpy(d.meas, b->h_meas + pos * 5, 5 * sizeof(float));
   }
+  if (b->blind_orig && b->pending == b->blind_descs.data()) {
+    // blind submission: hand the results (and the grants that were found) to the caller's descriptors
+    for (size_t k = 0; k < b->blind_index.size(); k++) {
+      srsue_gpu_sf_desc_t& o = b->blind_orig[b->blind_index[k]];
+      const srsue_gpu_sf_desc_t& r = b->blind_descs[k];
+      o.crc_ok = r.crc_ok; o.n_iter = r.n_iter;
+      std::memcpy(o.meas, r.meas, sizeof(o.meas));
+    }
+    b->blind_orig = nullptr;
+    b->blind_n = 0;
+    b->iq_on_device = false;
+  }
   b->pending = nullptr;
   b->n_pending = 0;
+  return 0;
+}
+
+// ---- blind submission: PCFICH -> CFI, PDCCH search for the descriptor's RNTI, DCI -> grant, then the PDSCH chain --------
+// (phch_worker.cc:254-297 for a whole batch).  In: cell, cfg.sf_idx, cfg.rnti, iq, payload (payload_cap bytes).  Out:
+// the rest of cfg (cfi, qm, tbs, rv, tm, prb_mask, nof_prb_alloc) and the usual results; a subframe without a DCI for its
+// RNTI comes back with cfg.tbs = 0, crc_ok = 0, n_iter = 0.
+static int symbol_sz_of(int nof_prb) {          // srslte_symbol_sz: FFT size of a bandwidth
+  static const int lim[6] = {6, 15, 25, 50, 75, 110}, sz[6] = {128, 256, 512, 1024, 1536, 2048};
+  if (nof_prb <= 0) return -1;
+  for (int i = 0; i < 6; i++)
+    if (nof_prb <= lim[i]) return sz[i];
+  return -1;
+}
+
+int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n, int ng_x6, int payload_cap) {
+  if (!b || !descs || n < 0 || n > b->max_subframes || payload_cap < 1) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: bad arguments (n=%d)", n);
+  if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: ng_x6 must be 1, 3, 6 or 12");
+  if (b->pending || b->blind_orig) B_FAIL(SRSUE_GPU_ERROR, "batch_submit_blind: the previous submission has not been waited for");
+  if (!b->devs.empty()) {
+    b->multi_blind = 1; b->multi_ng_x6 = ng_x6; b->multi_payload_cap = payload_cap;
+    const int rc = multi_submit(b, descs, n);
+    b->multi_blind = 0;
+    return rc;
+  }
+  b->launches = 0;
+  cudaStream_t st = b->s_compute;
+  const size_t esz = b->iq_format == SRSUE_GPU_IQ_SC16 ? 4 : sizeof(srsue_gpu_cf_t);
+  // ---- 1. all samples to the device, once (neighbouring host buffers in one copy) -----------------------------------
+  std::vector<size_t> row_off(n + 1, 0);
+  for (int i = 0; i < n; i++) {
+    const srsue_gpu_sf_desc_t& d = descs[i];
+    if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d has a null buffer", i);
+    if (d.cfg.sf_idx < 0 || d.cfg.sf_idx > 9 || d.softbuffer_id >= 0) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d: bad sf_idx, or a soft buffer id (blind subframes are decoded as new transmissions)", i);
+    const int nfft = symbol_sz_of(d.cell.nof_prb);
+    if (nfft <= 0) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d: bad cell", i);
+    row_off[i + 1] = row_off[i] + ((size_t)15 * nfft * esz + 255) / 256 * 256;
+  }
+  { int rc = grow(&b->d_biq, &b->biq_bytes, row_off[n] + 256, st); if (rc) return rc; }
+  for (int i = 0; i < n;) {
+    int e = i + 1;
+    const size_t rb = (size_t)15 * symbol_sz_of(descs[i].cell.nof_prb) * esz;
+    const bool packed = row_off[i + 1] - row_off[i] == rb;      // rows are padded to 256 bytes: merge only when there is no padding
+    while (packed && e < n && descs[e].cell.nof_prb == descs[i].cell.nof_prb &&
+           reinterpret_cast<const char*>(descs[e].iq) == reinterpret_cast<const char*>(descs[e - 1].iq) + rb) e++;
+    B_CU(cudaMemcpyAsync(b->d_biq + row_off[i], descs[i].iq, (size_t)(e - i) * rb, cudaMemcpyHostToDevice, st));
+    i = e;
+  }
+  // ---- 2. control channels, one pass per (cell, subframe number, RNTI) ------------------------------------------------
+  std::map<std::string, std::vector<int>> groups;
+  std::vector<std::string> group_order;
+  for (int i = 0; i < n; i++) {
+    const int v[5] = {descs[i].cell.nof_prb, descs[i].cell.nof_ports, descs[i].cell.cell_id, descs[i].cfg.sf_idx, descs[i].cfg.rnti};
+    std::string k(reinterpret_cast<const char*>(v), sizeof(v));
+    auto it = groups.find(k);
+    if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }
+    it->second.push_back(i);
+  }
+  const size_t cap = (size_t)b->chunk_cap;
+  if (!b->d_bcfi) {
+    B_CU(cudaMalloc((void**)&b->d_bcfi, cap * sizeof(int32_t)));
+    B_CU(cudaMalloc((void**)&b->d_bfound, 9 * cap * 4 * sizeof(int32_t)));
+    B_CU(cudaMalloc((void**)&b->d_bbits, 9 * cap * 64));
+    B_CU(cudaMallocHost((void**)&b->h_bcfi, cap * sizeof(int32_t)));
+    B_CU(cudaMallocHost((void**)&b->h_bfound, 9 * cap * 4 * sizeof(int32_t)));
+    B_CU(cudaMallocHost((void**)&b->h_bbits, 9 * cap * 64));
+  }
+  b->blind_descs.clear();
+  b->blind_index.clear();
+  for (int i = 0; i < n; i++) { descs[i].crc_ok = 0; descs[i].n_iter = 0; descs[i].cfg.tbs = 0; std::memset(descs[i].meas, 0, sizeof(descs[i].meas)); }
+  struct Try { int common, fmt, first_bit; };
+  for (const std::string& gk : group_order) {
+    const std::vector<int>& idx = groups[gk];
+    const srsue_gpu_sf_desc_t& d0 = descs[idx[0]];
+    const int rnti = d0.cfg.rnti, nof_prb = d0.cell.nof_prb;
+    const bool user = rnti >= SRSLTE_CRNTI_START && rnti <= SRSLTE_CRNTI_END;
+    // the searches of srslte_ue_dl_find_dl_dci_type: C-RNTI -- 1A then 1 in the UE-specific space, 1A in the common space;
+    // SI / RA / P-RNTI -- 1A in the common space
+    const Try tries_user[3] = {{0, 0, 1}, {0, 1, -1}, {1, 0, 1}}, tries_bc[1] = {{1, 0, 1}};
+    const Try* tries = user ? tries_user : tries_bc;
+    const int n_tries = user ? 3 : 1;
+    PlanEntry* fp[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int cfi = 1; cfi <= 3; cfi++) {
+      srsue_gpu_sf_desc_t fd = d0;
+      std::memset(&fd.cfg, 0, sizeof(fd.cfg));
+      fd.cfg.sf_idx = d0.cfg.sf_idx; fd.cfg.cfi = cfi; fd.cfg.qm = 2; fd.cfg.tm = d0.cell.nof_ports == 1 ? 1 : 2; fd.cfg.tbs = 0;
+      int rc = get_plan(b, plan_key(fd), fd, &fp[cfi]);
+      if (rc) return rc;
+    }
+    const srsue_gpu_plan_info_t& info = fp[1]->info;
+    const size_t grid = (size_t)14 * info.nsc;
+    int n_reg_max = 0;
+    for (int cfi = 1; cfi <= 3; cfi++) { int nr = 0, nc = 0; if (srsue_gpu_pdcch_info(fp[cfi]->plan, ng_x6, &nr, &nc)) return SRSUE_GPU_ERROR; n_reg_max = std::max(n_reg_max, nr); }
+    int rc = grow(&b->d_iq[0], &b->iq_elems[0], cap * info.sf_len, st); if (rc) return rc;
+    rc = grow(&b->d_bsf, &b->bsf_elems, cap * grid, st); if (rc) return rc;
+    rc = grow(&b->d_bce, &b->bce_elems, cap * grid * d0.cell.nof_ports, st); if (rc) return rc;
+    rc = grow(&b->d_bllr, &b->bllr_elems, 3 * cap * 8 * (size_t)n_reg_max, st); if (rc) return rc;
+    const size_t row_bytes = (size_t)info.sf_len * esz;
+    for (size_t off = 0; off < idx.size(); off += cap) {
+      const int m = (int)std::min(cap, idx.size() - off);
+      for (int r = 0; r < m; r++) b->h_iq_rows[r] = b->d_biq + row_off[idx[off + r]];
+      const int slices = (int)std::max<size_t>(1, row_bytes / (32 * 1024));
+      gather_host_rows_kernel<uint4><<<dim3(m, slices), 256, 0, st>>>(reinterpret_cast<uint4*>(b->d_iq[0]),
+          reinterpret_cast<const uint4* const*>(b->h_iq_rows), (int)(row_bytes / 16));
+      B_CU(cudaGetLastError());
+      srsue_gpu_pdsch_plan_set_iq_format(fp[1]->plan, b->iq_format, b->iq16_scale);
+      srsue_gpu_pdsch_plan_set_cfo(fp[1]->plan, nullptr, 0);
+      if (b->iq_format == SRSUE_GPU_IQ_SC16) rc = srsue_gpu_ofdm_rx_sc16(fp[1]->plan, m, reinterpret_cast<const int16_t*>(b->d_iq[0]), b->iq16_scale, b->d_bsf, st);
+      else rc = srsue_gpu_ofdm_rx(fp[1]->plan, m, b->d_iq[0], b->d_bsf, st);
+      if (!rc) rc = srsue_gpu_chest(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, st);
+      // PCFICH and PDCCH with the channel estimator's noise figure, as srslte_ue_dl_decode does
+      if (!rc) rc = srsue_gpu_pcfich_decode(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, 0.0f, 1, b->d_bcfi, nullptr, st);
+      if (rc) return rc;
+      bool have_try[9] = {};
+      for (int cfi = 1; cfi <= 3; cfi++) {
+        int16_t* llr = b->d_bllr + (size_t)(cfi - 1) * cap * 8 * n_reg_max;
+        srsue_gpu_pdsch_plan_set_row_filter(fp[cfi]->plan, b->d_bcfi, cfi);     // only the subframes whose PCFICH said this CFI
+        rc = srsue_gpu_pdcch_extract_llr(fp[cfi]->plan, m, b->d_bsf, b->d_bce, b->d_meas, 0.0f, 1, ng_x6, llr, st);
+        if (rc) return rc;
+        for (int t = 0; t < n_tries; t++) {
+          const int slot = (cfi - 1) * 3 + t;
+          const int nof_bits = srsue_gpu_host_dci_format_sizeof(tries[t].fmt, nof_prb);
+          const int r2 = srsue_gpu_pdcch_find_dci(fp[cfi]->plan, m, llr, ng_x6, rnti, tries[t].common, nof_bits, tries[t].first_bit,
+                                                  b->d_bfound + (size_t)slot * cap * 4, b->d_bbits + (size_t)slot * cap * 64, nullptr, st);
+          have_try[slot] = r2 >= 0;                       // (< 0: a control region too small for a common search space)
+          if (t == n_tries - 1) srsue_gpu_pdsch_plan_set_row_filter(fp[cfi]->plan, nullptr, 0);
+          if (have_try[slot]) {
+            B_CU(cudaMemcpyAsync(b->h_bfound + (size_t)slot * cap * 4, b->d_bfound + (size_t)slot * cap * 4, (size_t)m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            B_CU(cudaMemcpyAsync(b->h_bbits + (size_t)slot * cap * 64, b->d_bbits + (size_t)slot * cap * 64, (size_t)m * 64, cudaMemcpyDeviceToHost, st));
+          }
+        }
+      }
+      B_CU(cudaMemcpyAsync(b->h_bcfi, b->d_bcfi, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      B_CU(cudaStreamSynchronize(st));
+      b->launches += 2 + 1 + 1 + 3 * (1 + n_tries);
+      // ---- 3. DCI -> grant on the host (ra.cc), descriptor by descriptor ---------------------------------------------
+      for (int r = 0; r < m; r++) {
+        srsue_gpu_sf_desc_t& d = descs[idx[off + r]];
+        const int cfi = b->h_bcfi[r];
+        if (cfi < 1 || cfi > 3) continue;
+        d.cfg.cfi = cfi;
+        for (int t = 0; t < n_tries; t++) {
+          const int slot = (cfi - 1) * 3 + t;
+          if (!have_try[slot] || !b->h_bfound[((size_t)slot * cap + r) * 4]) continue;
+          srslte_dci_msg_t msg;
+          std::memset(&msg, 0, sizeof(msg));
+          const int nof_bits = srsue_gpu_host_dci_format_sizeof(tries[t].fmt, nof_prb);
+          std::memcpy(msg.data, b->h_bbits + ((size_t)slot * cap + r) * 64, (size_t)nof_bits);
+          msg.nof_bits = (uint32_t)nof_bits;
+          msg.format = tries[t].fmt ? SRSLTE_DCI_FORMAT1 : SRSLTE_DCI_FORMAT1A;
+          srslte_ra_dl_dci_t dci;
+          srslte_ra_dl_grant_t grant;
+          if (srslte_dci_msg_to_dl_grant(&msg, (uint16_t)rnti, (uint32_t)nof_prb, &dci, &grant) || grant.mcs.tbs <= 0) break;
+          if ((grant.mcs.tbs + 7) / 8 > payload_cap) break;                    // would not fit the caller's buffer
+          d.cfg.qm = (int)grant.Qm; d.cfg.tbs = grant.mcs.tbs; d.cfg.rv = (int)dci.rv_idx;
+          d.cfg.tm = d.cell.nof_ports == 1 ? 1 : 2;
+          int na = 0;
+          for (int p = 0; p < nof_prb; p++) {
+            const bool s0 = grant.prb_idx[0][p], s1 = grant.prb_idx[1][p];
+            d.cfg.prb_mask[p] = (s0 && s1) ? 1 : (uint8_t)((s0 ? 2 : 0) | (s1 ? 4 : 0));
+            na += s0 ? 1 : 0;
+          }
+          d.cfg.nof_prb_alloc = na;
+          break;
+        }
+        if (d.cfg.tbs > 0) {
+          srsue_gpu_sf_desc_t p2 = d;
+          p2.iq = reinterpret_cast<const srsue_gpu_cf_t*>(b->d_biq + row_off[idx[off + r]]);
+          p2.softbuffer_id = -1; p2.new_data = 1; p2.cfo = 0.f;
+          b->blind_descs.push_back(p2);
+          b->blind_index.push_back(idx[off + r]);
+        }
+      }
+    }
+  }
+  // ---- 4. the PDSCH chain for every subframe with a grant, bucketed by grant as usual ------------------------------------
+  b->blind_orig = descs;
+  b->blind_n = n;
+  if (b->blind_descs.empty()) return 0;
+  const int ctrl_launches = b->launches;
+  b->iq_on_device = true;
+  const int rc = batch_submit_impl(b, b->blind_descs.data(), (int)b->blind_descs.size());
+  if (rc) {
+    cudaStreamSynchronize(b->s_copy);
+    cudaStreamSynchronize(b->s_compute);
+    b->iq_on_device = false; b->blind_orig = nullptr; b->blind_n = 0;
+    return rc;
+  }
+  b->launches += ctrl_launches;
   return 0;
 }
 

@@ -123,6 +123,8 @@ struct PdcchLlrArgs {
   int16_t* llr;              // [n_sf][8 * n_reg]: 72 LLRs per CCE in CCE order
   int n_sf, nsc, nof_ports, n_reg, noise_mode;
   float noise_est, k_sqpsk, k_sq2;
+  const int32_t* row_filter; // optional [n_sf]: subframes whose entry differs from row_want are skipped (blind batches:
+  int row_want;              // the control region of a plan belongs to one CFI, the batch mixes them)
 };
 __global__ void pdcch_llr_kernel(const PdcchLlrArgs a);
 
@@ -137,6 +139,8 @@ struct PdcchSearchArgs {
   int n_sf, n_cand, nof_bits, rnti;
   int first_bit;             // -1: any; 0 / 1: a match also needs this value in payload bit 0 (format 0 / 1A flag)
   int cand_L[kPdcchMaxCand], cand_ncce[kPdcchMaxCand];
+  const int32_t* row_filter; // as in PdcchLlrArgs; skipped subframes report "not found"
+  int row_want;
 };
 __global__ void pdcch_search_kernel(const PdcchSearchArgs a);
 

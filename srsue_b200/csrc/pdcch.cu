@@ -24,6 +24,10 @@ __global__ void __launch_bounds__(32 * kPdcchMaxCand) pdcch_search_kernel(const 
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ int s_rem[kPdcchMaxCand];
   const int sf = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.row_filter && a.row_filter[sf] != a.row_want) {        // whole CTA: this subframe belongs to another control region
+    if (threadIdx.x < 4) a.found[(size_t)sf * 4 + threadIdx.x] = 0;
+    return;
+  }
   const int D = a.nof_bits + 16;
   const int per = 3 * D + 4 * D + (D + 3) / 4;                 // words per candidate
   int32_t* soft = reinterpret_cast<int32_t*>(s_dyn + (size_t)w * per);

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(128) phich_kernel(const PhichArgs a) {
 // them (one 16-byte store) at the quadruplet's place in the de-interleaved PDCCH bit stream.
 __global__ void __launch_bounds__(128) pdcch_llr_kernel(const PdcchLlrArgs a) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x, sf = blockIdx.y;
+  if (a.row_filter && a.row_filter[sf] != a.row_want) return;
   if (m >= a.n_reg) return;
   const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
   const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;

@@ -385,3 +385,59 @@ def test_multi_gpu_dispatch_pins_harq_processes(gpu, oracle):
     assert b.stats()["softbuffers"] == 4
     b.close()
 
+
+def test_blind_submission_finds_every_grant(gpu, oracle):
+    """srsue_gpu_batch_submit_blind: a mixed stream where the caller knows only cell, subframe number and RNTI of each capture.
+    The library decodes the PCFICH, searches the PDCCH for the RNTI, turns the DCI into a grant and decodes the PDSCH --
+    phch_worker.cc:254-297 for a whole batch.  CFI, grant and transport block equal what was sent and what the oracle
+    decodes with the true grant; captures without a DCI for the RNTI come back empty."""
+    import ctypes as C
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import DciMsg, RaDlDci, install_tbs_table
+    # (prb, cfi, sf_idx, rnti, mcs, RB_start, L_crb, tbs, with_dci)
+    cases = [(25, 2, 4, 0x1234, 9, 2, 10, 1544, True), (25, 1, 4, 0x1234, 9, 0, 10, 1544, True), (25, 2, 4, 0x1234, 9, 2, 10, 1544, False),
+             (50, 1, 7, 0x0456, 12, 5, 25, 5736, True), (50, 3, 7, 0x0456, 3, 0, 50, 2856, True), (6, 2, 1, 0x1234, 4, 0, 6, 408, True),
+             (25, 3, 5, 0xFFFF, 5, 1, 4, 296, True), (100, 1, 2, 0x2222, 20, 0, 100, 46888, True), (100, 1, 2, 0x2222, 20, 0, 100, 46888, False)]
+    table = {}
+    for prb, cfi, sf, rnti, mcs, start, ln, tbs, with_dci in cases:
+        itbs = mcs if (mcs < 10 or rnti == 0xFFFF) else mcs - 1 if mcs < 17 else mcs - 2      # 36.213 Table 7.1.7.1-1
+        table[(itbs, 3 if rnti == 0xFFFF else ln)] = tbs
+    install_tbs_table(L, table)
+    items, truth = [], []
+    for k, (prb, cfi, sf, rnti, mcs, start, ln, tbs, with_dci) in enumerate(cases):
+        si = rnti == 0xFFFF
+        ocell = o.make_cell(prb, 1, 1)
+        sent = RaDlDci()
+        sent.mcs_idx, sent.rv_idx, sent.alloc_type = mcs, 0, 2
+        sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
+        m = DciMsg()
+        nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), 2, C.byref(m), prb, not si)
+        assert nb > 0
+        rk, _ = o.pdcch_regs(ocell, cfi, 6)
+        ss = o.pdcch_search_space(len(rk) // 9, sf, rnti) if not si else [(4, 0)]
+        qm = 2 if mcs < 10 else 4 if mcs < 17 else 6
+        prbs = list(range(start, start + ln))
+        ocfg = o.make_cfg(ocell, sf_idx=sf, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs, prbs=prbs)
+        dcis = [(np.frombuffer(m.data, np.uint8)[:nb].copy(), rnti, ss[0][0], ss[0][1])] if with_dci else None
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 9300 + k, 26.0 if qm == 6 else 16.0, None, pcfich=True, dcis=dcis)
+        cell = sg.make_cell(prb, 1, 1)
+        items.append(dict(cell=cell, cfg=sg.make_cfg(cell, sf_idx=sf, cfi=1, rnti=rnti, qm=2, tbs=0), iq=iq))
+        truth.append((ocell, ocfg, iq, tb, cfi, tbs, qm, prbs, with_dci))
+    b = sg.Batch(ctx, 32)
+    for rep in range(2):
+        b.submit_blind(items, ng_x6=6)
+        res = b.wait()
+        for r, (ocell, ocfg, iq, tb, cfi, tbs, qm, prbs, with_dci) in zip(res, truth):
+            assert r["cfi"] == cfi
+            if not with_dci:
+                assert r["tbs"] == 0 and r["crc_ok"] == 0
+                continue
+            assert r["tbs"] == tbs and r["cfg"].qm == qm and r["cfg"].rv == 0
+            assert [i for i in range(ocell.nof_prb) if r["cfg"].prb_mask[i]] == prbs
+            rc_o, pl_o, _, _ = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
+            assert rc_o == 0 and r["crc_ok"] == 1 and np.array_equal(r["payload"], pl_o) and np.array_equal(pl_o, tb)
+    assert b.stats()["launches"] > 0
+    b.close()
+
