@@ -132,7 +132,7 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   return 0;
 }
 
-struct TurboLaunchCfg { int ncb, threads, grid, smem; };
+struct TurboLaunchCfg { int ncb, threads, grid, smem, ngroups, group_threads, group_slots; };
 
 // words between the exchange arrays of consecutive slots: plane/2 plus the skew that lets a warp straddling
 // two slots keep hitting distinct shared-memory banks ((plane/2 + skew) mod 32 == T mod 32)
@@ -144,20 +144,35 @@ int turbo_slot_words(const TurboGeom& g) {
 // stride of the position-table rows in shared memory (template parameter of the kernels)
 int turbo_perm_stride(const TurboGeom& g) { return g.T <= 32 ? 32 : 64; }
 
-// CTAs per SM of the persistent decoder.  Two independent CTAs per SM drift out of phase, which spreads the
-// L2 demand of the load-dominated backward sweeps and halves the width of every barrier.
+int turbo_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// CTAs per SM of the persistent decoder (SRSUE_TURBO_CTAS_PER_SM overrides; 0: choose per code-block size)
 int turbo_ctas_per_sm() {
-  static const int v = [] {
-    const char* e = getenv("SRSUE_TURBO_CTAS_PER_SM");
-    return e ? std::max(1, std::min(4, atoi(e))) : 0;        // 0: choose per code-block size (turbo_launch_cfg)
-  }();
+  static const int v = std::max(0, std::min(4, turbo_env_int("SRSUE_TURBO_CTAS_PER_SM", 0)));
   return v;
+}
+
+// Phase groups of a CTA with ncb slots (turbo.cu): two groups of whole warps when there are at least two slots
+void turbo_groups(const TurboGeom& g, int ncb, int* ngroups, int* group_threads, int* group_slots) {
+  static const int want = std::max(1, std::min(2, turbo_env_int("SRSUE_TURBO_GROUPS", 2)));
+  const int ng = (ncb >= 2) ? want : 1;
+  *ngroups = ng;
+  *group_slots = (ncb + ng - 1) / ng;
+  *group_threads = ((*group_slots * g.T + 31) / 32) * 32;
+}
+int turbo_threads(const TurboGeom& g, int ncb) {
+  int ng, gt, gs;
+  turbo_groups(g, ncb, &ng, &gt, &gs);
+  return ng * gt;
 }
 
 // Shared memory of one decoder CTA with ncb slots: position table, flags, per slot the exchange array and the decision
 // bits of the current iteration (one per trellis step), per thread six 16-byte staging chunks and a scratch word
 int turbo_smem_bytes(const TurboGeom& g, int ncb) {
-  const int threads = ((ncb * g.T + 31) / 32) * 32;
+  const int threads = turbo_threads(g, ncb);
   const int slot_bytes = turbo_slot_words(g) * 4 + (g.W / 8) * g.T * 2;
   return g.W * turbo_perm_stride(g) * 4 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes + 16 + threads * 100;
 }
@@ -168,8 +183,9 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   // SRSUE_TURBO_CTAS_PER_SM overrides
   auto slots_for = [&](int per_sm) {
     const int budget = std::min((ctx->smem_sm - per_sm * 1024) / per_sm, ctx->smem_optin);
-    int ncb = std::min(kTurboMaxThreads / per_sm, 1024) / g.T;
-    while (ncb > 0 && turbo_smem_bytes(g, ncb) > budget) ncb--;
+    const int max_threads = std::min(kTurboMaxThreads / per_sm, 1024);
+    int ncb = max_threads / g.T;
+    while (ncb > 0 && (turbo_smem_bytes(g, ncb) > budget || turbo_threads(g, ncb) > max_threads)) ncb--;
     return ncb;
   };
   int per_sm = turbo_ctas_per_sm();
@@ -181,7 +197,8 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   ncb = std::max(ncb, 1);
   TurboLaunchCfg c;
   c.ncb = ncb;
-  c.threads = ((ncb * g.T + 31) / 32) * 32;
+  turbo_groups(g, ncb, &c.ngroups, &c.group_threads, &c.group_slots);
+  c.threads = c.ngroups * c.group_threads;
   c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms * per_sm);
   c.smem = turbo_smem_bytes(g, ncb);
   return c;
@@ -233,6 +250,14 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   CU_CHECK(cudaMemsetAsync(scr.counter, 0, sizeof(int), st));
   a.work_counter = scr.counter;
   a.work_base = lc.grid * lc.ncb;
+  a.ones = 0xFFFFFFFFu;
+  a.ngroups = lc.ngroups; a.group_threads = lc.group_threads; a.group_slots = lc.group_slots;
+  // the second phase group starts about a third of a MAP pass late (a pass costs roughly 60 SM clocks per trellis step
+  // of a window with all slots busy); SRSUE_TURBO_PHASE_DELAY (clocks) overrides
+  {
+    static const int env_delay = turbo_env_int("SRSUE_TURBO_PHASE_DELAY", -1);
+    a.phase_delay = lc.ngroups > 1 ? (env_delay >= 0 ? env_delay : 170 * g.W) : 0;
+  }
   const bool wide = turbo_perm_stride(g) == 64;
   if (crc_type) (wide ? turbo_decode_crc_wide_kernel : turbo_decode_crc_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   else (wide ? turbo_decode_wide_kernel : turbo_decode_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);

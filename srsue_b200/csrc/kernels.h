@@ -30,6 +30,11 @@ struct TurboArgs {
   uint4* ckpt;               // [grid][W/8][2][ncb_cta][T]  beta checkpoints (two 16-byte halves per thread)
   int* work_counter;         // dynamic work items handed out so far (zeroed before the launch)
   int work_base;             // first dynamically assigned code block = grid * ncb_cta
+  uint32_t ones;             // 0xFFFFFFFF, opaque to the compiler (turbo.cu: vnot)
+  int ngroups;               // phase groups per CTA (1 or 2): slots of different groups only meet at named barriers of their own
+  int group_threads;         // threads per phase group (multiple of 32); blockDim.x = ngroups * group_threads
+  int group_slots;           // code-block slots per phase group
+  int phase_delay;           // SM clocks the second group waits before its first block (puts the groups out of phase)
 };
 
 __global__ void turbo_decode_kernel(const TurboArgs g);        // fixed iteration count

@@ -83,10 +83,12 @@ __device__ __forceinline__ void alpha_step(uint32_t (&a)[8], uint32_t x, uint32_
 // the kernel adds ~m(0) = -m(0) - 1 instead: every metric of the vector ends up ONE LOWER than the oracle's, m(0) = -1.
 // The extrinsic max(...) - max(...) and the decision only see differences inside one alpha and one beta vector, so the
 // outputs are unchanged; the no-wrap bound of SPEC 7.6 has a margin of 1284, the offset costs 2 of it.
-// `m1` is the constant (-1, -1) held in a register the compiler cannot see through (it would otherwise re-materialise it
-// with an ALU-pipe PRMT at every use).
+// `m1` is the constant (-1, -1) = 0xFFFFFFFF read from the kernel parameters, so that neither nvcc nor ptxas knows its
+// value: the bitwise NOT is then written v * m1 + m1 = -v - 1 = ~v, ONE IMAD on the FMA pipe instead of a LOP3 on the ALU
+// pipe, which is the pipe this kernel saturates (a literal constant is folded back into LOP3 / IADD3).
+__device__ __forceinline__ uint32_t vnot(uint32_t v, uint32_t m1) { return v * m1 + m1; }
 __device__ __forceinline__ void normalise(uint32_t (&m)[8], uint32_t m1) {
-  const uint32_t n0 = ~m[0];
+  const uint32_t n0 = vnot(m[0], m1);
 #pragma unroll
   for (int s = 1; s < 8; s++) m[s] = vadd(m[s], n0);
   m[0] = m1;
@@ -214,8 +216,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   const int chalf = g.ncb_cta * T;
   uint4* ckpt4 = g.ckpt + (size_t)blockIdx.x * (size_t)(nsw * cstride) + slot_in_cta * T + t;
   unsigned char* Ab = reinterpret_cast<unsigned char*>(c.Aw);
-  uint32_t m1;                                     // (-1, -1), see normalise()
-  asm volatile("mov.b32 %0, 0xFFFFFFFF;" : "=r"(m1));
+  const uint32_t m1 = g.ones;                      // (-1, -1), see normalise()
 
   // The channel LLRs (and, forward, the checkpoint) of a group reach the thread through its private staging chunks in
   // shared memory: requested with cp.async at the top of the previous group (a whole group of issue slots ahead), read
@@ -244,12 +245,17 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   const bool pf_on = t < (DEC == 0 ? 2 * nl : nl) && (t < nl ? 8 * t : 8 * (t - nl)) < 2 * T;
   fetch(nsw - 1, false);
 
-  // ---- boundary metrics: all four records are requested at once; the first iteration reads the zeros init_slot wrote
+  // ---- boundary metrics: all four records are requested at once
   uint32_t b[8], a[8];
   {
-    const uint4 ra0 = nii_a_rd[j0], ra1 = nii_a_rd[j0 + 1], rb0 = nii_b_rd[j0 + 1], rb1 = nii_b_rd[j0 + 2];
-    nii_unpack(ra0, ra1, a);
-    nii_unpack(rb0, rb1, b);
+    if (it) {
+      const uint4 ra0 = nii_a_rd[j0], ra1 = nii_a_rd[j0 + 1], rb0 = nii_b_rd[j0 + 1], rb1 = nii_b_rd[j0 + 2];
+      nii_unpack(ra0, ra1, a);
+      nii_unpack(rb0, rb1, b);
+    } else {                                        // first iteration: all boundary metrics are zero, nothing to read
+#pragma unroll
+      for (int s = 0; s < 8; s++) a[s] = b[s] = 0u;
+    }
     if (j0 == 0) {                                  // trellis start: alpha_0 = (0, -INF, ...)
       a[0] &= 0xFFFF0000u;
 #pragma unroll
@@ -380,7 +386,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
       // extrinsic = l1 - l0 without a packed subtraction (-l0 = ~l0 + 1): q = l1 + ~l0 = ext - 1, exact in 16 bits
       uint32_t l1, l0;
       ext_parts(a, B[i], Cy[i], l1, l0);
-      const uint32_t q = vadd(l1, ~l0);
+      const uint32_t q = vadd(l1, vnot(l0, m1));
       const uint32_t r = vclamp2E(q, kEp1Pair);                // clamp(ext, -E, E) + E
       if (DEC == 0) {
         ap[i * T] = vadd(vadd(Cs[i], kNegEPair), r);
@@ -417,8 +423,16 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int T = g.T, W = g.W, P = g.P, plane = g.plane, nsw = W / kSW;
   const int tid = threadIdx.x;
-  const int slot = tid / T, t = tid - slot * T;
-  const bool valid = slot < g.ncb_cta;
+  // Phase groups: the slots of a CTA are split into g.ngroups groups of whole warps that only synchronise among themselves
+  // (named barriers).  The second group starts late, so while one group is in a load-dominated backward sweep, at a
+  // boundary-metric exchange or refilling slots, the other one is in an arithmetic-bound forward sweep and takes the
+  // issue slots the first cannot use.
+  const int grp = tid / g.group_threads, lt = tid - grp * g.group_threads;
+  const int ls = lt / T, t = lt - ls * T;
+  const int slot = grp * g.group_slots + ls;
+  const bool valid = ls < g.group_slots && slot < g.ncb_cta;
+  const int bar_id = 1 + grp, bar_n = g.group_threads;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory"); };
   constexpr bool crc_on = CRC;
   const int nflag = (g.ncb_cta + 3) & ~3;
 
@@ -426,7 +440,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   uint32_t* s_crc = s_permw + W * TS;                        // per slot: CRC accumulator
   int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
   uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words (+ skew)
-  int* s_active = s_next + nflag;
+  int* s_active = s_next + nflag + grp;                      // per phase group: slots with work
   uint16_t* s_bits = reinterpret_cast<uint16_t*>(s_slots + (size_t)g.ncb_cta * g.slot_words);   // per slot: nsw * T x u16
   // staging chunks of all threads, 16-byte aligned: [6][blockDim.x] uint4, then [blockDim.x] scratch words
   uint4* s_stage = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_bits + (size_t)g.ncb_cta * nsw * T) + 15) & ~(uintptr_t)15);
@@ -459,19 +473,6 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   auto init_slot = [&]() {
     cbi = g.cb_list ? g.cb_list[cur] : cur;
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
-    // boundary metrics of the first iteration are all zero: every thread clears exactly the records it will read
-    // (read parity 0 of both decoders), so no barrier is needed between a refill and the first pass
-    {
-      const int NP = g.Ppad + 2;
-      uint4* nii = g.nii + (size_t)c.gslot * (size_t)(2 * 2 * 2 * NP);
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int dec = 0; dec < 2; dec++) {
-        uint4* ra = nii + (dec * 4 + 0) * NP;
-        uint4* rb = nii + (dec * 4 + 1) * NP;
-        ra[2 * t] = z; ra[2 * t + 1] = z; rb[2 * t + 1] = z; rb[2 * t + 2] = z;
-      }
-    }
     // the block comes straight from HBM: request it now, one 128-byte line per prefetch (the rows the backward
     // sweep of DEC1 needs first -- the ends of the parity-1 and systematic planes -- go first)
     {
@@ -484,21 +485,25 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
       for (int l = lines_plane - 1 - t; l >= 0; l -= T) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + plane * 4 + (size_t)l * 128));
     }
   };
-  if (have) init_slot();
-  if (tid == 0) *s_active = 0;
+  if (lt == 0) *s_active = 0;
   __syncthreads();
   if (have && t == 0) atomicAdd(s_active, 1);
   __syncthreads();
+  if (grp && g.phase_delay > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)g.phase_delay) __nanosleep(500);
+  }
+  if (have) init_slot();
 
-  while (*s_active > 0) {
+  while (*reinterpret_cast<volatile int*>(s_active) > 0) {
     if (valid && t == 0) s_crc[slot] = 0;
     if (have) map_pass<0, CRC, TS>(g, c, perm_t, t, it);
-    __syncthreads();
+    group_sync();
     if (have) {
       const uint32_t part = map_pass<1, CRC, TS>(g, c, perm_t, t, it);
       if (crc_on) atomicXor(&s_crc[slot], part);
     }
-    __syncthreads();
+    group_sync();
     const bool crc_ok = crc_on && valid && s_crc[slot] == 0;
     const bool fin = have && ((crc_ok && it + 1 >= g.min_iter) || it + 1 >= g.max_iter);
     if (fin) {
@@ -524,7 +529,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     } else if (have) {
       it++;
     }
-    __syncthreads();
+    group_sync();
     if (fin) {
       // ---- pack, MSB first, natural order: word i*T + t holds the bits of step i of windows 2t and 2t+1 ----
       uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
