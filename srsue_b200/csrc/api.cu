@@ -49,6 +49,7 @@ cudaError_t upload(T** d, const std::vector<T>& h) {
 struct TurboTables {
   TurboGeom g{};
   uint16_t* d_perm = nullptr;
+  uint16_t* d_deint = nullptr;                // [K] turbo_deint_table
   uint32_t* d_tpos[2] = {nullptr, nullptr};   // [0] CRC24A, [1] CRC24B
 };
 
@@ -121,6 +122,8 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   std::vector<uint16_t> pos;
   turbo_perm_table(t.g, pos);
   CU_CHECK(upload(&t.d_perm, pos));
+  turbo_deint_table(t.g, pos);
+  CU_CHECK(upload(&t.d_deint, pos));
   const uint32_t polys[2] = {kCrc24A, kCrc24B};
   for (int i = 0; i < 2; i++) {
     std::vector<uint32_t> tpos;
@@ -169,11 +172,11 @@ int turbo_threads(const TurboGeom& g, int ncb) {
   return ng * gt;
 }
 
-// Shared memory of one decoder CTA with ncb slots: position table, flags, per slot the exchange array and the decision
-// bits of the current iteration (one per trellis step), per thread six 16-byte staging chunks and a scratch word
+// Shared memory of one decoder CTA with ncb slots: position table, flags, per slot the exchange array, per thread six
+// 16-byte staging chunks and a scratch word
 int turbo_smem_bytes(const TurboGeom& g, int ncb) {
   const int threads = turbo_threads(g, ncb);
-  const int slot_bytes = turbo_slot_words(g) * 4 + (g.W / 8) * g.T * 2;
+  const int slot_bytes = turbo_slot_words(g) * 4;
   return g.W * turbo_perm_stride(g) * 4 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes + 16 + threads * 100;
 }
 
@@ -222,7 +225,9 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   const TurboGeom& g = tt->g;
   const TurboLaunchCfg lc = turbo_launch_cfg(ctx, g, n_cb, crc_type != 0);
   const size_t slots = (size_t)lc.grid * lc.ncb;
-  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), 0, 0);
+  const int row_bytes = g.plane / 8;                                  // decisions of one block in DEC2 order
+  const int dbits_stride = (row_bytes + 15) & ~15;
+  rc = ensure_scratch(scr, slots * (size_t)(2 * 2 * 2 * 8 * (g.Ppad + 2)), (size_t)n_cb * dbits_stride, 0);
   if (rc) return rc;
   const size_t ckpt_bytes = slots * (size_t)(g.W / 8) * g.T * 32;
   if (ckpt_bytes > scr.ckpt_bytes) { cudaFree(scr.ckpt); CU_CHECK(cudaMalloc((void**)&scr.ckpt, ckpt_bytes)); scr.ckpt_bytes = ckpt_bytes; }
@@ -235,7 +240,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   }
   TurboArgs a{};
   a.in = d_in; a.in_stride = in_stride; a.cb_list = d_cb_list; a.n_cb = n_cb;
-  a.out_bits = d_bits; a.out_stride = out_stride; a.out_status = d_status;
+  a.dbits = scr.bits; a.dbits_stride = dbits_stride; a.out_status = d_status;
   a.max_iter = max_iter; a.crc_type = crc_type;
   a.min_iter = std::max(1, std::min(min_iter, max_iter));
   a.K = g.K; a.W = g.W; a.P = g.P; a.Ppad = g.Ppad; a.T = g.T; a.plane = g.plane;
@@ -262,6 +267,14 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   if (crc_type) (wide ? turbo_decode_crc_wide_kernel : turbo_decode_crc_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   else (wide ? turbo_decode_wide_kernel : turbo_decode_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   CU_CHECK(cudaGetLastError());
+  {
+    // decisions: DEC2 order -> natural-order bytes (persistent CTAs, the table of this K in shared memory)
+    const int dsmem = ((g.K + 7) & ~7) * 2 + row_bytes * 8;
+    const int dgrid = std::min(n_cb, ctx->num_sms * 6);
+    tdec_deinterleave_kernel<<<dgrid, 256, dsmem, st>>>(scr.bits, dbits_stride, tt->d_deint, d_cb_list, n_cb, d_bits, out_stride, g.K, row_bytes);
+    CU_CHECK(cudaGetLastError());
+    ctx->launch_count++;
+  }
   ctx->last_grid = lc.grid; ctx->last_block = lc.threads; ctx->last_smem = lc.smem; ctx->last_ncb = lc.ncb;
   ctx->launch_count++;
   return 0;
@@ -334,7 +347,7 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->turbo) {
-    cudaFree(kv.second.d_perm);
+    cudaFree(kv.second.d_perm); cudaFree(kv.second.d_deint);
     for (int i = 0; i < 2; i++) cudaFree(kv.second.d_tpos[i]);
   }
   for (auto& kv : ctx->scratch) kv.second.release();

@@ -16,8 +16,8 @@ struct TurboArgs {
   long long in_stride;       // int16 elements between consecutive code blocks
   const int32_t* cb_list;    // optional indirection (nullptr: code block i is entry i)
   int n_cb;
-  uint8_t* out_bits;         // [cb][out_stride] hard bits, packed MSB first
-  int out_stride;
+  uint8_t* dbits;            // [launch-local cb][dbits_stride] hard decisions in DEC2 order (tdec_deinterleave_kernel reads them)
+  int dbits_stride;          // bytes, even
   int32_t* out_status;       // [cb] iterations | crc_ok << 8
   int max_iter, crc_type;    // crc_type: 0 none, 1 CRC24A, 2 CRC24B
   int min_iter;              // a passing CRC stops the block only from this iteration on (1: as srsLTE; = max_iter: fixed count)
@@ -41,6 +41,8 @@ __global__ void turbo_decode_kernel(const TurboArgs g);        // fixed iteratio
 __global__ void turbo_decode_crc_kernel(const TurboArgs g);    // CRC accumulated on the fly, early stop
 __global__ void turbo_decode_wide_kernel(const TurboArgs g);       // the same for code blocks with more than 32 threads (T > 32)
 __global__ void turbo_decode_crc_wide_kernel(const TurboArgs g);
+__global__ void tdec_deinterleave_kernel(const uint8_t* dbits, int dbits_stride, const uint16_t* deint, const int32_t* cb_list,
+                                         int n_cb, uint8_t* out, int out_stride, int K, int row_bytes);
 __global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
                                       int n_cb, TurboGeomDev g);
 __global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,

@@ -199,6 +199,21 @@ void turbo_perm_table(const TurboGeom& g, std::vector<uint16_t>& tab) {
     }
 }
 
+// For natural bit n of a code block: where its hard decision lies in the decoder's DEC2-order output row
+// (turbo.cu: [W/8][T] x u16, low byte window 2t, high byte window 2t+1, step i of a group at bit 7 - i%8), as
+// 8 * byte + bit with the bit counted from the LSB.
+void turbo_deint_table(const TurboGeom& g, std::vector<uint16_t>& tab) {
+  int f1 = 0, f2 = 0;
+  qpp_params(g.K, &f1, &f2);
+  tab.assign((size_t)g.K, 0);
+  for (int j = 0; j < g.P; j++)
+    for (int i = 0; i < g.W; i++) {
+      const int64_t k = (int64_t)j * g.W + i;
+      const int n = (int)((f1 * k + (int64_t)f2 * k * k) % g.K);
+      const int byte = ((i / 8) * g.T + j / 2) * 2 + (j & 1);
+      tab[n] = (uint16_t)(byte * 8 + (7 - i % 8));
+    }
+}
 void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tlin) {
   int f1 = 0, f2 = 0;
   qpp_params(g.K, &f1, &f2);

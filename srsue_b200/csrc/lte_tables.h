@@ -101,6 +101,7 @@ void turbo_perm_table(const TurboGeom& g, std::vector<uint16_t>& tab);
 // CRC contribution of the hard bit decided at every DEC2 trellis step, [W/2][T][2][2] entries (one 16-byte chunk per
 // thread and pair of steps, chunks of consecutive threads contiguous): the CRC of the K decoded bits is the XOR over the set bits n of x^(K-1-n+24) mod g (zero
 // initial state, no final xor); entry (q, t, i, h) belongs to n = pi((2t + h) * W + 2 q + i), 0 in padding columns
+void turbo_deint_table(const TurboGeom& g, std::vector<uint16_t>& tab);   // [K]: natural bit -> source bit of the decoder's DEC2-order row
 void turbo_crc_table(const TurboGeom& g, uint32_t poly, std::vector<uint32_t>& tlin);
 
 // Rate de-matching gather table for one (K, F, rv): for every element m of the tcb buffer

@@ -169,7 +169,7 @@ __device__ __forceinline__ void sts16(unsigned char* base, uint32_t off, uint32_
 struct SlotCtx {
   const uint4* in4;       // code block in tcb layout (global)
   uint32_t* Aw;           // shared: extrinsic exchange array [W][Ppad] as packed pairs, word i*T + t
-  uint16_t* bits;         // shared: hard decisions of the slot, [W/8][T] x (byte of window 2t | byte of window 2t+1 << 8)
+  uint16_t* bits;         // global: hard decisions of the block in DEC2 order, [W/8][T] x (byte of window 2t | byte of window 2t+1 << 8)
   uint32_t pin;           // shared-window address of this thread's scratch word (pin_store / pin_load)
   uint32_t stage;         // shared-window address of this thread's staging chunks: chunk k (16 bytes) at stage + k * 16 * blockDim.x
                           // (y: 0,1  sys: 2,3  checkpoint: 4,5)
@@ -441,9 +441,8 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
   uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words (+ skew)
   int* s_active = s_next + nflag + grp;                      // per phase group: slots with work
-  uint16_t* s_bits = reinterpret_cast<uint16_t*>(s_slots + (size_t)g.ncb_cta * g.slot_words);   // per slot: nsw * T x u16
   // staging chunks of all threads, 16-byte aligned: [6][blockDim.x] uint4, then [blockDim.x] scratch words
-  uint4* s_stage = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_bits + (size_t)g.ncb_cta * nsw * T) + 15) & ~(uintptr_t)15);
+  uint4* s_stage = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_slots + (size_t)g.ncb_cta * g.slot_words) + 15) & ~(uintptr_t)15);
 
   {
     // position table: global [W][2][T] -> shared [W][2][TS] (rows padded to the warp-friendly stride)
@@ -458,7 +457,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   // slot stride = plane/2 words plus a skew that makes consecutive slots continue the bank sequence
   // (base(s+1) = base(s) + T mod 32): a warp that straddles two slots then stays conflict-free
   c.Aw = s_slots + (size_t)(valid ? slot : 0) * g.slot_words;
-  c.bits = s_bits + (size_t)(valid ? slot : 0) * (nsw * T);
+  c.bits = nullptr;
   c.stage = (uint32_t)__cvta_generic_to_shared(s_stage + tid);
   c.pin = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(s_stage + 6 * blockDim.x) + tid);
   c.gslot = blockIdx.x * g.ncb_cta + (valid ? slot : 0);
@@ -473,6 +472,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   auto init_slot = [&]() {
     cbi = g.cb_list ? g.cb_list[cur] : cur;
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
+    c.bits = reinterpret_cast<uint16_t*>(g.dbits + (size_t)cur * g.dbits_stride);
     // the block comes straight from HBM: request it now, one 128-byte line per prefetch (the rows the backward
     // sweep of DEC1 needs first -- the ends of the parity-1 and systematic planes -- go first)
     {
@@ -507,19 +507,8 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     const bool crc_ok = crc_on && valid && s_crc[slot] == 0;
     const bool fin = have && ((crc_ok && it + 1 >= g.min_iter) || it + 1 >= g.max_iter);
     if (fin) {
-      // ---- de-interleave the hard decisions of this iteration: every thread scatters the 2 x W bits of its
-      // windows (DEC2 order) as zero / non-zero halfwords to their natural positions in the exchange array, which nobody needs
-      // any more ----
-      unsigned char* Ab = reinterpret_cast<unsigned char*>(c.Aw);
-      for (int sw = 0; sw < nsw; sw++) {
-        const uint32_t w = c.bits[sw * T + t];
-        const uint16_t* pq = perm_t + sw * (2 * kSW) * TS;
-#pragma unroll
-        for (int i = 0; i < kSW; i++) {             // any non-zero halfword means "one": the packing below normalises
-          sts16(Ab, pq[(2 * i) * TS], w & (0x80u >> i));
-          sts16(Ab, pq[(2 * i + 1) * TS], w & (0x8000u >> i));
-        }
-      }
+      // The hard decisions of this iteration already lie in global memory in DEC2 order (the forward sweep stores them
+      // group by group); tdec_deinterleave_kernel turns them into natural-order bytes after this kernel.
       if (t == 0) {
         g.out_status[cbi] = (it + 1) | ((crc_ok ? 1 : 0) << 8);
         const int nxt = g.work_base + atomicAdd(g.work_counter, 1);
@@ -531,16 +520,6 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     }
     group_sync();
     if (fin) {
-      // ---- pack, MSB first, natural order: word i*T + t holds the bits of step i of windows 2t and 2t+1 ----
-      uint8_t* out = g.out_bits + cbi * (long long)g.out_stride;
-      const int wbytes = W / 8;
-      for (int bb = 0; bb < wbytes; bb++) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) v = v * 2u + __vminu2(c.Aw[(bb * 8 + q) * T + t], 0x00010001u);
-        out[(2 * t) * wbytes + bb] = (uint8_t)v;
-        if (2 * t + 1 < P) out[(2 * t + 1) * wbytes + bb] = (uint8_t)(v >> 16);
-      }
       cur = s_next[slot];
       have = cur < g.n_cb;
       it = 0;
@@ -555,6 +534,51 @@ __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const
 __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32>(g); }
 __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64>(g); }
 __global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64>(g); }
+
+// ---- hard decisions: DEC2 order -> natural order ------------------------------------------------------
+// The decoder leaves the decisions of a code block as it produced them: one bit per trellis step of the second
+// constituent decoder, [W/8][T] x (byte of window 2t | byte of window 2t+1 << 8), step i of a group at bit 7 - i.  This
+// kernel applies the inverse QPP permutation at full occupancy (inside the decoder the same work ran at 12 warps per SM
+// and held three barriers): a CTA keeps the per-K table `deint` (for natural bit n the index of its source bit, counted
+// LSB first within each source byte) in shared memory, spreads the row of a code block to one byte per bit and
+// gathers the K / 8 output bytes, MSB first.  cb_list maps launch-local rows to output rows as in the decoder.
+__global__ void __launch_bounds__(256) tdec_deinterleave_kernel(const uint8_t* __restrict__ dbits, int dbits_stride,
+                                                                const uint16_t* __restrict__ deint, const int32_t* __restrict__ cb_list,
+                                                                int n_cb, uint8_t* __restrict__ out, int out_stride, int K, int row_bytes) {
+  extern __shared__ __align__(16) uint32_t dsm[];
+  uint16_t* s_tab = reinterpret_cast<uint16_t*>(dsm);                        // K entries (K is a multiple of 8)
+  uint2* s_bit = reinterpret_cast<uint2*>(s_tab + ((K + 7) & ~7));           // row_bytes x 8 bytes: one byte per bit
+  const unsigned char* s_bitb = reinterpret_cast<const unsigned char*>(s_bit);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(deint);
+    uint4* dst = reinterpret_cast<uint4*>(s_tab);
+    for (int e = threadIdx.x; e < K / 8; e += blockDim.x) dst[e] = __ldg(src + e);
+  }
+  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+    __syncthreads();                                                         // table loaded / previous row consumed
+    const uint8_t* row = dbits + (size_t)cb * dbits_stride;
+    for (int e = threadIdx.x; e < row_bytes; e += blockDim.x) {
+      const uint32_t b = row[e];
+      // nibble * 0x00204081 puts bit q of the nibble at bit 8 q
+      s_bit[e] = make_uint2(((b & 15u) * 0x00204081u) & 0x01010101u, ((b >> 4) * 0x00204081u) & 0x01010101u);
+    }
+    __syncthreads();
+    const long long cbi = cb_list ? cb_list[cb] : cb;
+    uint8_t* o = out + cbi * (long long)out_stride;
+    for (int e = threadIdx.x; e < K / 8; e += blockDim.x) {
+      const uint4 q = reinterpret_cast<const uint4*>(s_tab)[e];
+      uint32_t v = s_bitb[q.x & 0xFFFFu];
+      v = v * 2u + s_bitb[q.x >> 16];
+      v = v * 2u + s_bitb[q.y & 0xFFFFu];
+      v = v * 2u + s_bitb[q.y >> 16];
+      v = v * 2u + s_bitb[q.z & 0xFFFFu];
+      v = v * 2u + s_bitb[q.z >> 16];
+      v = v * 2u + s_bitb[q.w & 0xFFFFu];
+      v = v * 2u + s_bitb[q.w >> 16];
+      o[e] = (uint8_t)v;
+    }
+  }
+}
 
 // ---- layout conversion at the API edge -----------------------------------------------------------
 // srsLTE decoder-input order (3K+12 interleaved triples) -> tcb layout, clamping to +-C (SPEC 7.2)
