@@ -266,7 +266,12 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   const bool wide = turbo_perm_stride(g) == 64;
   if (crc_type) (wide ? turbo_decode_crc_wide_kernel : turbo_decode_crc_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   else (wide ? turbo_decode_wide_kernel : turbo_decode_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
-  CU_CHECK(cudaGetLastError());
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return fail(SRSUE_GPU_ERROR, "turbo decoder launch failed: %s (K=%d grid=%d threads=%d smem=%d slots=%d)", cudaGetErrorString(e), K, lc.grid,
+                  lc.threads, lc.smem, lc.ncb);
+  }
   {
     // decisions: DEC2 order -> natural-order bytes (persistent CTAs, the table of this K in shared memory)
     const int dsmem = ((g.K + 7) & ~7) * 2 + row_bytes * 8;

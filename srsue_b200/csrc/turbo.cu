@@ -37,7 +37,7 @@ namespace srsue {
 namespace {
 
 constexpr int kSW = 8;                 // sub-window: beta values re-created in registers
-constexpr int kL2Ahead = 3;            // backward sweep: groups between an L2 prefetch and the copy that needs the lines
+constexpr int kL2Ahead = 3;   // backward sweep: groups between an L2 prefetch and the copy that needs the lines
 constexpr uint32_t kNegInfPair = ((uint32_t)(uint16_t)(-kTdInf) << 16) | (uint16_t)(-kTdInf);
 constexpr uint32_t pair16(int v) { return ((uint32_t)(uint16_t)v << 16) | (uint32_t)(uint16_t)v; }
 constexpr uint32_t k2EPair = pair16(2 * kTdE), kNegEPair = pair16(-kTdE), kEp1Pair = pair16(kTdE + 1);
@@ -473,17 +473,9 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
     cbi = g.cb_list ? g.cb_list[cur] : cur;
     c.in4 = reinterpret_cast<const uint4*>(g.in + cbi * g.in_stride);
     c.bits = reinterpret_cast<uint16_t*>(g.dbits + (size_t)cur * g.dbits_stride);
-    // the block comes straight from HBM: request it now, one 128-byte line per prefetch (the rows the backward
-    // sweep of DEC1 needs first -- the ends of the parity-1 and systematic planes -- go first)
-    {
-      const char* base = reinterpret_cast<const char*>(c.in4);
-      const int lines_plane = (plane * 2 + 127) / 128;
-      for (int l = lines_plane - 1 - t; l >= 0; l -= T) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + plane * 2 + (size_t)l * 128));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
-      }
-      for (int l = lines_plane - 1 - t; l >= 0; l -= T) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + plane * 4 + (size_t)l * 128));
-    }
+    // No prefetch of the new block here: asking the L2 for all of it at once (or for its head one pass early) measured
+    // SLOWER -- the resident blocks of all SMs already overflow the L2, and lines that arrive long before their use push
+    // out lines that are needed sooner.  The backward sweep asks for its groups kL2Ahead groups ahead instead.
   };
   if (lt == 0) *s_active = 0;
   __syncthreads();

@@ -11,24 +11,18 @@ run() {  # label, env..., -- args
   env "${envs[@]}" python tools/perf_turbo.py "$@" >> $out 2>>gpurun_out/perf_variants.err || echo "null" >> $out
   sed -i '$ s/$/}/' $out
 }
-for mode in "4 2 2.0" "4 2 30.0" "4 0 2.0"; do
+export SRSUE_TURBO_PHASE_DELAY=40000
+for mode in "4 2 30.0" "4 2 2.0" "4 0 2.0"; do
   tag=$(echo $mode | tr ' ' '_')
-  for v in "$@"; do :; done
-  run "g1_$tag" SRSUE_TURBO_GROUPS=1 -- 5824 53248 $mode
-  run "g2_d40k_$tag" SRSUE_TURBO_GROUPS=2 SRSUE_TURBO_PHASE_DELAY=40000 -- 5824 53248 $mode
-  run "g2_d80k_$tag" SRSUE_TURBO_GROUPS=2 SRSUE_TURBO_PHASE_DELAY=80000 -- 5824 53248 $mode
+  run "base_$tag" A=1 -- 5824 53248 $mode
+  for v in ef1 ef2 ahead2 ahead4; do
+    run "${v}_$tag" SRSUE_GPU_LIB=build/variants/libsrsue_gpu_$v.so -- 5824 53248 $mode
+  done
 done
-run "K40" A=1 -- 40 1000000 4 0 2.0
-run "K512" A=1 -- 512 200000 4 0 2.0
-run "K6144" A=1 -- 6144 53248 4 0 2.0
-python - <<'P'
-import json,sys
-for l in open(sys.argv[1] if len(sys.argv)>1 else "/dev/stdin"):
-    pass
-P
 python -c "
 import json
 for l in open('$out'):
     d=json.loads(l); r=d['r']
     print(d['label'], None if r is None else (round(r['ms'],3), round(r['avg_iters'],3), round(r['int16_tops'],2), r['launch']))
 "
+tail -2 gpurun_out/perf_variants.err
