@@ -231,11 +231,12 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   if (rc) return rc;
   const size_t ckpt_bytes = slots * (size_t)(g.W / 8) * g.T * 32;
   if (ckpt_bytes > scr.ckpt_bytes) { cudaFree(scr.ckpt); CU_CHECK(cudaMalloc((void**)&scr.ckpt, ckpt_bytes)); scr.ckpt_bytes = ckpt_bytes; }
+  typedef void (*TurboKernel)(const TurboArgs);
+  static const TurboKernel kernels[4][2] = {{turbo_decode_kernel, turbo_decode_crc_kernel}, {turbo_decode_wide_kernel, turbo_decode_crc_wide_kernel},
+                                            {turbo_decode_t26_kernel, turbo_decode_crc_t26_kernel}, {turbo_decode_t24_kernel, turbo_decode_crc_t24_kernel}};
   if (!ctx->attr_set) {
-    CU_CHECK(cudaFuncSetAttribute(turbo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
-    CU_CHECK(cudaFuncSetAttribute(turbo_decode_crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
-    CU_CHECK(cudaFuncSetAttribute(turbo_decode_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
-    CU_CHECK(cudaFuncSetAttribute(turbo_decode_crc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+    for (int v = 0; v < 4; v++)
+      for (int c = 0; c < 2; c++) CU_CHECK(cudaFuncSetAttribute(kernels[v][c], cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
     ctx->attr_set = true;
   }
   TurboArgs a{};
@@ -257,15 +258,15 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   a.work_base = lc.grid * lc.ncb;
   a.ones = 0xFFFFFFFFu;
   a.ngroups = lc.ngroups; a.group_threads = lc.group_threads; a.group_slots = lc.group_slots;
-  // the second phase group starts about a third of a MAP pass late (a pass costs roughly 60 SM clocks per trellis step
+  // the second phase group starts a good half of a MAP pass late (a pass costs roughly 600 SM clocks per trellis step
   // of a window with all slots busy); SRSUE_TURBO_PHASE_DELAY (clocks) overrides
   {
     static const int env_delay = turbo_env_int("SRSUE_TURBO_PHASE_DELAY", -1);
-    a.phase_delay = lc.ngroups > 1 ? (env_delay >= 0 ? env_delay : 170 * g.W) : 0;
+    a.phase_delay = lc.ngroups > 1 ? (env_delay >= 0 ? env_delay : 350 * g.W) : 0;
   }
-  const bool wide = turbo_perm_stride(g) == 64;
-  if (crc_type) (wide ? turbo_decode_crc_wide_kernel : turbo_decode_crc_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
-  else (wide ? turbo_decode_wide_kernel : turbo_decode_kernel)<<<lc.grid, lc.threads, lc.smem, st>>>(a);
+  static const bool generic_only = turbo_env_int("SRSUE_TURBO_GENERIC", 0) != 0;      // tuning: skip the T-specific kernels
+  const int variant = turbo_perm_stride(g) == 64 ? 1 : generic_only ? 0 : g.T == 26 ? 2 : g.T == 24 ? 3 : 0;
+  kernels[variant][crc_type ? 1 : 0]<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)

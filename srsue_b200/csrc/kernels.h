@@ -41,6 +41,10 @@ __global__ void turbo_decode_kernel(const TurboArgs g);        // fixed iteratio
 __global__ void turbo_decode_crc_kernel(const TurboArgs g);    // CRC accumulated on the fly, early stop
 __global__ void turbo_decode_wide_kernel(const TurboArgs g);       // the same for code blocks with more than 32 threads (T > 32)
 __global__ void turbo_decode_crc_wide_kernel(const TurboArgs g);
+__global__ void turbo_decode_t26_kernel(const TurboArgs g);        // T = 26 (K = 5824) as a compile-time constant
+__global__ void turbo_decode_crc_t26_kernel(const TurboArgs g);
+__global__ void turbo_decode_t24_kernel(const TurboArgs g);        // T = 24 (K = 6144)
+__global__ void turbo_decode_crc_t24_kernel(const TurboArgs g);
 __global__ void tdec_deinterleave_kernel(const uint8_t* dbits, int dbits_stride, const uint16_t* deint, const int32_t* cb_list,
                                          int n_cb, uint8_t* out, int out_stride, int K, int row_bytes);
 __global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,

@@ -195,9 +195,9 @@ __device__ __forceinline__ void nii_pack(const uint32_t (&m)[8], uint4& lo, uint
 
 // One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.  Returns the
 // thread's CRC contribution of the hard decisions (DEC2 with CRC), else 0.  perm_t = position table + t.
-template <int DEC, bool CRC, int TS>
+template <int DEC, bool CRC, int TS, int TT>
 __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm_t, int t, int it) {
-  const int T = g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
+  const int T = TT ? TT : g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
   const int j0 = 2 * t, j1 = 2 * t + 1;
   const int rd = it & 1, wr = rd ^ 1;
   // records: [slot][dec][parity][kind][NP] uint4
@@ -418,10 +418,12 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   return crc;
 }
 
-template <bool CRC, int TS>
+// TT: threads per code block as a compile-time constant (0: run time).  With T known, every stride of the exchange array,
+// the channel-LLR planes and the checkpoints is an immediate of the load / store that uses it.
+template <bool CRC, int TS, int TT>
 __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int T = g.T, W = g.W, P = g.P, plane = g.plane, nsw = W / kSW;
+  const int T = TT ? TT : g.T, W = g.W, P = g.P, plane = g.plane, nsw = W / kSW;
   const int tid = threadIdx.x;
   // Phase groups: the slots of a CTA are split into g.ngroups groups of whole warps that only synchronise among themselves
   // (named barriers).  The second group starts late, so while one group is in a load-dominated backward sweep, at a
@@ -489,10 +491,10 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
   while (*reinterpret_cast<volatile int*>(s_active) > 0) {
     if (valid && t == 0) s_crc[slot] = 0;
-    if (have) map_pass<0, CRC, TS>(g, c, perm_t, t, it);
+    if (have) map_pass<0, CRC, TS, TT>(g, c, perm_t, t, it);
     group_sync();
     if (have) {
-      const uint32_t part = map_pass<1, CRC, TS>(g, c, perm_t, t, it);
+      const uint32_t part = map_pass<1, CRC, TS, TT>(g, c, perm_t, t, it);
       if (crc_on) atomicXor(&s_crc[slot], part);
     }
     group_sync();
@@ -522,10 +524,15 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false, 32>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 0>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 0>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64, 0>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64, 0>(g); }
+// the two largest code-block sizes carry most of the bits of a wide-band transport block: K = 5824 (T = 26), K = 6144 (T = 24)
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t26_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 26>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t26_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 26>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t24_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 24>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t24_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 24>(g); }
 
 // ---- hard decisions: DEC2 order -> natural order ------------------------------------------------------
 // The decoder leaves the decisions of a code block as it produced them: one bit per trellis step of the second

@@ -41,7 +41,7 @@ if "--json" in sys.argv:
         i = hdr.index(k)
         return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
 
-    tags = (("ofdm_rx", "fft"), ("chest_kernel", "chest"), ("pdsch_llr_dematch", "demap"), ("turbo_decode", "turbo"), ("tb_assemble", "tb"))
+    tags = (("ofdm_rx", "fft"), ("chest_kernel", "chest"), ("pdsch_llr_dematch", "demap"), ("turbo_decode", "turbo"), ("tb_assemble", "tb"), ("tdec_deinterleave", "deint"))
     out = {"source": "profiles/%s (ncu --set full --clock-control none; regenerate with tools/ncu_chain_summary.py)" %
                      path.split("/")[-1].replace(".json", ".ncu.txt"), "batch": batch}
     for r in rows[2:]:
