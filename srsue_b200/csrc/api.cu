@@ -787,7 +787,14 @@ static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t
     // single exchange buffer (8 CTAs per SM) wherever the CTA has exactly N/8 threads; SRSUE_FFT_INPLACE=0 selects the
     // two-buffer kernel for comparison
     static const int inplace = getenv("SRSUE_FFT_INPLACE") ? atoi(getenv("SRSUE_FFT_INPLACE")) : 1;
-    if (b.iq16 && rotate) {
+    // N = 2048 without rotation: radix 16 x 16 x 8 with 16 points per thread (two exchanges instead of three, per-pass
+    // twiddle tables); SRSUE_FFT_R16=0 selects the radix-8 kernel for comparison
+    static const int r16 = getenv("SRSUE_FFT_R16") ? atoi(getenv("SRSUE_FFT_R16")) : 1;
+    if (r16 && a.nfft == 2048 && !rotate) {
+      const int smem16 = (2048 + 2048 / 16) * (int)sizeof(float2);
+      if (b.iq16) ofdm_rx_r16_iq16_kernel<<<dim3(14, n), 128, smem16, (cudaStream_t)stream>>>(b);
+      else ofdm_rx_r16_kernel<<<dim3(14, n), 128, smem16, (cudaStream_t)stream>>>(b);
+    } else if (b.iq16 && rotate) {
       if (b.cfo_steps) b.cfo_steps += done;
       ofdm_rx_cfo_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
     } else if (b.iq16) {

@@ -69,6 +69,8 @@ struct OfdmArgs {
   float iq16_scale;
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
+__global__ void ofdm_rx_r16_kernel(const OfdmArgs a);          // N = 2048 only: radix 16 x 16 x 8, 128 threads (ofdm.cu)
+__global__ void ofdm_rx_r16_iq16_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_cfo_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_inplace_iq16_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_iq16_kernel(const OfdmArgs a);

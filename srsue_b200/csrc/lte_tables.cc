@@ -284,6 +284,24 @@ void fft_twiddles(int n, std::vector<float>& tw) {
     if ((4 * k) % n == 0) { re = (4 * k / n == 0) ? 1.0f : 0.0f; im = (4 * k / n == 0) ? 0.0f : -1.0f; }
     tw[2 * k] = re; tw[2 * k + 1] = im;
   }
+  if (n == 2048) {
+    // Per-pass copies for the radix 16 x 16 x 8 kernel (ofdm.cu, fft2048_r16), laid out [twiddle of the pass][k] so that
+    // consecutive k are consecutive entries.  Same values as above: twiddle j of a pass that combines sub-transforms of
+    // length L at index k is w_n^((k + c_j L) n / (2^s L)) with s the stage (1..4) and c_j the offset of its butterfly group.
+    auto entry = [&](int idx) { return std::pair<float, float>(tw[2 * idx], tw[2 * idx + 1]); };
+    auto append = [&](int L, int stages, int nk) {
+      for (int j = 0; j < (1 << stages) - 1; j++) {
+        int s = 1, c = j;                                        // j = 2^(s-1) - 1 + c, c < 2^(s-1)
+        while (c >= (1 << (s - 1))) { c -= 1 << (s - 1); s++; }
+        for (int k = 0; k < nk; k++) {
+          const auto e = entry((k + c * L) * (n / ((1 << s) * L)));
+          tw.push_back(e.first); tw.push_back(e.second);
+        }
+      }
+    };
+    append(16, 4, 16);     // pass 2: 15 x 16
+    append(256, 3, 256);   // pass 3:  7 x 256
+  }
 }
 
 // Quadruplet i of the PCFICH sits in the resource-element group starting at kbar + floor(i N_RB / 2) * 6 with

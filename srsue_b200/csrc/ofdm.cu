@@ -298,6 +298,177 @@ __device__ __forceinline__ void fft_symbol_inplace(const float2* __restrict__ gi
   }
 }
 
+// ---- N = 2048 in three passes: radix 16, radix 16, radix 8 -------------------------------------------------------
+// The kernels above are bound by the L1/shared-memory pipe (l1tex 90 % busy, DRAM 40 %): three exchanges through shared
+// memory and twiddle loads whose lanes hit 4 to 8 different cache lines.  This variant keeps 16 points per thread
+// (128 threads per symbol), so the 11 radix-2 stages need only TWO exchanges, and reads its twiddles from tables laid out
+// per pass ([twiddle of the pass][k], fft_twiddles appends them for N = 2048) so that the lanes of a warp read
+// consecutive entries.  The butterflies, their order inside a stage and the twiddle values are those of SPEC.md 2, so
+// the bins are bit-identical to the radix-8 kernels.
+//   pass 1 (L = 1,   radix 16): thread b holds x[b + 128 r]; all twiddles are warp-uniform (w_16^j)
+//   pass 2 (L = 16,  radix 16): k = b / 8, n' = b % 8; reads k 128 + n' + 8 r, writes b + 128 u
+//   pass 3 (L = 256, radix 8, two butterflies per thread: k = b, b + 128): reads 8 k + r, writes bin k + 256 u
+// Shared memory: one buffer of 2048 + 127 skewed points, used in place (barrier between the reads and the writes of pass 2).
+namespace {
+
+// radix-16 combine of sub-transforms of length L at index k: stages A..D of radix-2 DIT butterflies with the twiddles
+// T[j * KS + k]: j = 0 (stage A), 1 + h (B), 3 + h + 2q (C), 7 + h + 2q + 4p (D).  Afterwards element h*8 + q*4 + p*2 + s
+// holds output u = h + 2q + 4p + 8s (index k + u L).
+template <int KS>
+__device__ __forceinline__ void combine16(float2 (&v)[16], const float2* __restrict__ T) {
+  {
+    const float2 w = __ldg(T);
+#pragma unroll
+    for (int r = 0; r < 8; r++) bfly(v[r], v[r + 8], w);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const float2 w = __ldg(T + (1 + h) * KS);
+#pragma unroll
+    for (int r = 0; r < 4; r++) bfly(v[h * 8 + r], v[h * 8 + r + 4], w);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const float2 w = __ldg(T + (3 + h + 2 * q) * KS);
+#pragma unroll
+      for (int r = 0; r < 2; r++) bfly(v[h * 8 + q * 4 + r], v[h * 8 + q * 4 + r + 2], w);
+    }
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int pp = 0; pp < 2; pp++)
+        bfly(v[h * 8 + q * 4 + pp * 2], v[h * 8 + q * 4 + pp * 2 + 1], __ldg(T + (7 + h + 2 * q + 4 * pp) * KS));
+}
+
+// the first pass (L = 1, k = 0): the same with the exact twiddles 1 and -i taken as such (no products); tw = the N/2 table
+template <int N>
+__device__ __forceinline__ void combine_first16(float2 (&v)[16], const float2* __restrict__ tw) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) bfly_one(v[r], v[r + 8]);                                     // A: w = 1
+#pragma unroll
+  for (int r = 0; r < 4; r++) { bfly_one(v[r], v[r + 4]); bfly_mj(v[8 + r], v[8 + r + 4]); }   // B: 1, -i
+  const float2 w8_1 = __ldg(tw + N / 8), w8_3 = __ldg(tw + 3 * (N / 8));
+#pragma unroll
+  for (int r = 0; r < 2; r++) {                                                              // C: w_8^(h + 2q)
+    bfly_one(v[r], v[r + 2]);                    // h = 0, q = 0
+    bfly_mj(v[4 + r], v[4 + r + 2]);             // h = 0, q = 1: w_8^2 = -i
+    bfly(v[8 + r], v[8 + r + 2], w8_1);          // h = 1, q = 0
+    bfly(v[12 + r], v[12 + r + 2], w8_3);        // h = 1, q = 1
+  }
+  // D: w_16^(h + 2q + 4p) on elements h*8 + q*4 + p*2
+  bfly_one(v[0], v[1]);                                             // j = 0
+  bfly_mj(v[2], v[3]);                                              // j = 4 (p = 1)
+  bfly(v[4], v[5], w8_1);                                           // j = 2 (q = 1): w_16^2 = w_8^1
+  bfly(v[6], v[7], w8_3);                                           // j = 6
+  bfly(v[8], v[9], __ldg(tw + N / 16));                             // j = 1 (h = 1)
+  bfly(v[10], v[11], __ldg(tw + 5 * (N / 16)));                     // j = 5
+  bfly(v[12], v[13], __ldg(tw + 3 * (N / 16)));                     // j = 3
+  bfly(v[14], v[15], __ldg(tw + 7 * (N / 16)));                     // j = 7
+}
+
+__host__ __device__ constexpr int reg_of_u16(int u) { return (u & 1) * 8 + ((u >> 1) & 1) * 4 + ((u >> 2) & 1) * 2 + (u >> 3); }
+
+template <bool IQ16>
+__device__ __forceinline__ void fft2048_r16(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s0,
+                                            const float2* __restrict__ tw, int nsc, float scale, float iq16_scale) {
+  constexpr int N = 2048;
+  const int b = threadIdx.x;                        // 128 threads
+  const float2* T2 = tw + N / 2;                    // [15][16]
+  const float2* T3 = tw + N / 2 + 15 * 16;          // [7][256]
+  float2 v[16];
+  // ---- pass 1
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    if (IQ16) {
+      const short2 q = __ldg(reinterpret_cast<const short2*>(gin) + b + 128 * r);
+      v[r] = make_float2(__fmul_rn((float)q.x, iq16_scale), __fmul_rn((float)q.y, iq16_scale));
+    } else {
+      v[r] = __ldg(gin + b + 128 * r);
+    }
+  }
+  combine_first16<N>(v, tw);
+  {
+    float2* p = s0 + b + (b >> 4);
+#pragma unroll
+    for (int u = 0; u < 16; u++) p[136 * u] = v[reg_of_u16(u)];
+  }
+  __syncthreads();
+  // ---- pass 2
+  {
+    const int k = b >> 3, np = b & 7;
+    const float2* p = s0 + 136 * k + np;
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = p[8 * r + (r >> 1)];
+    __syncthreads();
+    combine16<16>(v, T2 + k);
+    float2* q = s0 + b + (b >> 4);
+#pragma unroll
+    for (int u = 0; u < 16; u++) q[136 * u] = v[reg_of_u16(u)];
+  }
+  __syncthreads();
+  // ---- pass 3: two radix-8 butterflies, k = b and b + 128
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int k = b + 128 * half;
+    const float2* p = s0 + 8 * k + (k >> 1);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[half * 8 + r] = p[r];
+  }
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int k = b + 128 * half;
+    const float2* T = T3 + k;
+    float2* w = v + half * 8;
+    {
+      const float2 t = __ldg(T);
+#pragma unroll
+      for (int r = 0; r < 4; r++) bfly(w[r], w[r + 4], t);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float2 t = __ldg(T + (1 + h) * 256);
+#pragma unroll
+      for (int r = 0; r < 2; r++) bfly(w[h * 4 + r], w[h * 4 + r + 2], t);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) bfly(w[h * 4 + q * 2], w[h * 4 + q * 2 + 1], __ldg(T + (3 + h + 2 * q) * 256));
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int kp = k + u * 256;
+      int ko = -1;
+      if (kp >= 1 && kp <= nsc / 2) ko = kp - 1 + nsc / 2;
+      else if (kp >= N - nsc / 2) ko = kp - (N - nsc / 2);
+      if (ko >= 0) gout[ko] = mul2(w[reg_of_u<3>(u)], make_float2(scale, scale));
+    }
+  }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128, 8) ofdm_rx_r16_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  constexpr int N = 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + 160 + 6 * 144) + ls * N + 160 + ls * 144;
+  fft2048_r16<false>(a.iq + (size_t)sf * 15 * N + start, a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc, s_fft, a.tw, a.nsc, a.scale, 0.f);
+}
+__global__ void __launch_bounds__(128, 8) ofdm_rx_r16_iq16_kernel(const OfdmArgs a) {
+  extern __shared__ __align__(16) float2 s_fft[];
+  const int l = blockIdx.x, sf = blockIdx.y;
+  constexpr int N = 2048;
+  const int slot = l / 7, ls = l % 7;
+  const int start = slot * (7 * N + 160 + 6 * 144) + ls * N + 160 + ls * 144;
+  fft2048_r16<true>(reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start), a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc, s_fft,
+                    a.tw, a.nsc, a.scale, a.iq16_scale);
+}
+
 __global__ void __launch_bounds__(256, 7) ofdm_rx_inplace_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;

@@ -423,7 +423,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 template <bool CRC, int TS, int TT>
 __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int T = TT ? TT : g.T, W = g.W, P = g.P, plane = g.plane, nsw = W / kSW;
+  const int T = TT ? TT : g.T, W = g.W;
   const int tid = threadIdx.x;
   // Phase groups: the slots of a CTA are split into g.ngroups groups of whole warps that only synchronise among themselves
   // (named barriers).  The second group starts late, so while one group is in a load-dominated backward sweep, at a
