@@ -12,6 +12,7 @@
  *   srsue_gpu_pdsch_decode_batch[_host]   srslte_ue_dl_decode (the wrapper the north star names) and the
  *                                         thread_pool hand-off it replaces   ue/src/common/thread_pool.cc:72-82
  *   srsue_gpu_tdec_*                      srslte_tdec_run_all & co (turbo sweep, BASELINE config 4)
+ *   srsue_gpu_ulsch_*                     srslte_ue_ul_pusch_encode_rnti_softbuffer's bit chain   phch_worker.cc:545-590
  *   tb_status / meas read-back            srslte_pdsch_last_noi, srslte_chest_dl_get_*  phch_worker.cc:359-360,799-848
  *
  * There is NO CPU fallback: every entry point fails (negative return, message in
@@ -305,6 +306,31 @@ int srsue_gpu_host_rm_sequence(int K, int F, int rv, int32_t *seq);
 int srsue_gpu_host_qpp(int K, uint16_t *pi);
 /* n bits of the Gold sequence with the given c_init, one per byte */
 int srsue_gpu_host_gold(uint32_t c_init, int n, uint8_t *c);
+
+/* ---- uplink shared-channel encoder ------------------------------------------------
+ * The bit chain of srslte_ue_ul_pusch_encode_rnti_softbuffer (ue/src/phy/phch_worker.cc:545-590: srslte_ulsch_encode and
+ * the scrambling of srslte_pusch_encode) for a batch of transport blocks of one grant: CRC24A, segmentation + CRC24B,
+ * turbo ENCODER, rate matching for redundancy version rv over the whole circular buffer, concatenation, channel
+ * interleaver (36.212 5.2.2.8; no control information multiplexed), scrambling (36.211 5.3.1).  The caller's modulation
+ * mapper, DFT precoding and SC-FDMA generation stay where they are.  n_symb = PUSCH symbols per subframe: 12 with the
+ * normal cyclic prefix, 11 when the last one gives way to SRS (10 / 9 with the extended prefix). */
+typedef struct {
+  int tbs;        /* transport-block size in bits (multiple of 8) */
+  int qm;         /* 2, 4, 6 */
+  int nof_prb;    /* L_prb of the grant */
+  int n_symb;
+  int rv;
+  int rnti, sf_idx, cell_id;
+} srsue_gpu_ulsch_cfg_t;
+typedef struct srsue_gpu_ulsch_plan srsue_gpu_ulsch_plan_t;
+int srsue_gpu_ulsch_plan_create(srsue_gpu_ctx_t *ctx, const srsue_gpu_ulsch_cfg_t *cfg, int max_batch, srsue_gpu_ulsch_plan_t **plan);
+void srsue_gpu_ulsch_plan_destroy(srsue_gpu_ulsch_plan_t *plan);
+/* G = 12 nof_prb n_symb qm coded bits per transport block; C code blocks of sizes Km (the first ones) and Kp */
+int srsue_gpu_ulsch_plan_info(const srsue_gpu_ulsch_plan_t *plan, int *G, int *C, int *Kp, int *Km);
+/* d_payload [n_tb][tbs / 8]; d_bits [n_tb][G / 8], packed MSB first (bit 0 of the codeword is bit 7 of byte 0) */
+int srsue_gpu_ulsch_encode(srsue_gpu_ulsch_plan_t *plan, int n_tb, const uint8_t *d_payload, uint8_t *d_bits, void *stream);
+/* host-pointer convenience of the same (copies in and out, synchronises) */
+int srsue_gpu_ulsch_encode_host(srsue_gpu_ulsch_plan_t *plan, int n_tb, const uint8_t *h_payload, uint8_t *h_bits);
 
 /* ---- pinned host memory helpers (so callers need not link the CUDA runtime) ------------------- */
 void *srsue_gpu_host_alloc(uint64_t bytes);

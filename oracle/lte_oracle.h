@@ -86,6 +86,9 @@ int  lteo_rm_sequence(int K, int F, int rv, int32_t *seq);              /* retur
 int  lteo_rm_tx(const uint8_t *d, int K, int F, int E, int rv, uint8_t *e);
 int  lteo_pdsch_encode_bits(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
                             const uint8_t *tb_bytes, uint8_t *e_bits, int *G_out);
+/* uplink UL-SCH coding without control information + PUSCH scrambling; returns G or < 0 (lteo_tx.c) */
+int  lteo_ulsch_encode(int tbs, int qm, int nof_prb, int n_symb, int rv, int rnti, int sf_idx, int cell_id,
+                       const uint8_t *tb_bytes, uint8_t *out_bits /* 12 nof_prb n_symb qm */);
 int  lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
                         const uint8_t *tb_bytes, lteo_cd_t *grid /* [ports][14][12*nof_prb] */);
 void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq /* 15*nfft samples */);

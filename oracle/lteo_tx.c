@@ -116,6 +116,51 @@ int lteo_pdsch_encode_bits(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
   return (wp == G) ? 0 : -2;
 }
 
+/* ---- uplink: UL-SCH coding of srslte_ue_ul_pusch_encode_rnti_softbuffer (phch_worker.cc:545-590 -> srslte_pusch_encode ->
+ * srslte_ulsch_encode), no control information multiplexed (36.212 5.2.2: 5.2.2.1 CRC24A, 5.2.2.2 segmentation + CRC24B,
+ * 5.2.2.3 turbo coding, 5.2.2.4 rate matching with the whole circular buffer, 5.2.2.5 concatenation, 5.2.2.8 channel
+ * interleaver: Qm-bit groups written row by row into a matrix with n_symb columns, read column by column) followed by the
+ * PUSCH scrambling of 36.211 5.3.1 (c_init = rnti 2^14 + sf_idx 2^9 + cell_id).  out_bits: G = 12 nof_prb n_symb qm bits.
+ * n_symb = 12 (normal CP) or 11 (last symbol punctured for SRS). */
+int lteo_ulsch_encode(int tbs, int qm, int nof_prb, int n_symb, int rv, int rnti, int sf_idx, int cell_id,
+                      const uint8_t *tb_bytes, uint8_t *out_bits) {
+  lteo_cbsegm_t s;
+  if (lteo_cbsegm(tbs, &s)) return -1;
+  const int rows = 12 * nof_prb, G = rows * n_symb * qm;
+  uint8_t *b = (uint8_t *)malloc(s.B), *g = (uint8_t *)malloc(G);
+  bytes_to_bits(tb_bytes, tbs, b);
+  uint32_t crc = lteo_crc_bits(b, tbs, LTEO_CRC24A, 24);
+  for (int i = 0; i < 24; i++) b[tbs + i] = (crc >> (23 - i)) & 1;
+  uint8_t *cb = (uint8_t *)malloc(LTEO_MAX_K), *d = (uint8_t *)malloc(3 * (LTEO_MAX_K + 4));
+  int rp = 0, wp = 0;
+  for (int r = 0; r < s.C; r++) {
+    int K = lteo_cb_len(&s, r), F = (r == 0) ? s.F : 0, L = (s.C > 1) ? 24 : 0, n = 0;
+    for (int i = 0; i < F; i++) cb[n++] = 0;
+    while (n < K - L) cb[n++] = b[rp++];
+    if (L) {
+      uint32_t c24 = lteo_crc_bits(cb, K - L, LTEO_CRC24B, 24);
+      for (int i = 0; i < 24; i++) cb[n++] = (c24 >> (23 - i)) & 1;
+    }
+    lteo_turbo_encode(cb, K, d);
+    int E = lteo_cb_E(&s, G, qm, 1, r);
+    lteo_rm_tx(d, K, F, E, rv, g + wp);
+    wp += E;
+  }
+  free(b); free(cb); free(d);
+  if (wp != G) { free(g); return -2; }
+  /* channel interleaver: symbol k = row * n_symb + col of the input is symbol col * rows + row of the output */
+  for (int col = 0; col < n_symb; col++)
+    for (int row = 0; row < rows; row++)
+      for (int q = 0; q < qm; q++) out_bits[(col * rows + row) * qm + q] = g[(row * n_symb + col) * qm + q];
+  free(g);
+  uint32_t c_init = ((uint32_t)rnti << 14) | ((uint32_t)sf_idx << 9) | (uint32_t)cell_id;
+  uint8_t *c = (uint8_t *)malloc(G);
+  lteo_gold(c_init, G, c);
+  for (int i = 0; i < G; i++) out_bits[i] ^= c[i];
+  free(c);
+  return G;
+}
+
 /* 36.211 7.1 modulation mapper */
 static lteo_cd_t modulate(const uint8_t *b, int qm) {
   lteo_cd_t s;

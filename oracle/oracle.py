@@ -176,6 +176,16 @@ def turbo_encode(c):
     return d
 
 
+def ulsch_encode(tbs, qm, nof_prb, tb_bytes, rv=0, rnti=0x1234, sf_idx=0, cell_id=1, n_symb=12):
+    """UL-SCH coding (no control information) + PUSCH scrambling -> G = 12 nof_prb n_symb qm bits (one per byte)."""
+    tb = np.ascontiguousarray(tb_bytes, dtype=np.uint8)
+    out = np.zeros(12 * nof_prb * n_symb * qm, np.uint8)
+    G = lib().lteo_ulsch_encode(int(tbs), int(qm), int(nof_prb), int(n_symb), int(rv), int(rnti), int(sf_idx), int(cell_id), _p(tb), _p(out))
+    if G < 0:
+        raise ValueError("lteo_ulsch_encode failed (%d)" % G)
+    return out
+
+
 def pdsch_tx_grid(cell, cfg, tb_bytes):
     nsc = 12 * cell.nof_prb
     grid = np.zeros((cell.nof_ports, 14, nsc), np.complex128)

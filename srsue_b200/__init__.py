@@ -243,6 +243,36 @@ class PdschPlan:
                "pdsch_decode_batch_host")
 
 
+class UlschCfg(C.Structure):
+    """srsue_gpu_ulsch_cfg_t"""
+    _fields_ = [(n, C.c_int) for n in ("tbs", "qm", "nof_prb", "n_symb", "rv", "rnti", "sf_idx", "cell_id")]
+
+
+class UlschPlan:
+    """Uplink shared-channel encoder (srsue_gpu_ulsch_*): transport blocks -> interleaved, scrambled PUSCH bits."""
+
+    def __init__(self, ctx, tbs, qm, nof_prb, rv=0, rnti=0x1234, sf_idx=0, cell_id=1, n_symb=12, max_batch=64):
+        self.ctx = ctx
+        self.cfg = UlschCfg(tbs, qm, nof_prb, n_symb, rv, rnti, sf_idx, cell_id)
+        self.h = C.c_void_p()
+        _check(lib().srsue_gpu_ulsch_plan_create(ctx.h, C.byref(self.cfg), max_batch, C.byref(self.h)), "srsue_gpu_ulsch_plan_create")
+        G, Cb, Kp, Km = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().srsue_gpu_ulsch_plan_info(self.h, C.byref(G), C.byref(Cb), C.byref(Kp), C.byref(Km)), "srsue_gpu_ulsch_plan_info")
+        self.G, self.C, self.Kp, self.Km = G.value, Cb.value, Kp.value, Km.value
+
+    def close(self):
+        if self.h:
+            lib().srsue_gpu_ulsch_plan_destroy.argtypes = [C.c_void_p]
+            lib().srsue_gpu_ulsch_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def encode(self, n_tb, d_payload, d_bits):
+        _check(lib().srsue_gpu_ulsch_encode(self.h, n_tb, _ptr(d_payload), _ptr(d_bits), _stream()), "srsue_gpu_ulsch_encode")
+
+    def encode_host(self, n_tb, h_payload, h_bits):
+        _check(lib().srsue_gpu_ulsch_encode_host(self.h, n_tb, _ptr(h_payload), _ptr(h_bits)), "srsue_gpu_ulsch_encode_host")
+
+
 class Batch:
     """srsue_gpu_batch_*: heterogeneous subframe streams.  Keeps the numpy buffers alive until wait()."""
 

@@ -1284,3 +1284,136 @@ int srsue_gpu_host_unregister(void* p) {
 }
 
 }  // extern "C"
+
+// ---- uplink shared-channel encoder (ulsch.cu) -------------------------------------------------------
+struct srsue_gpu_ulsch_plan {
+  srsue_gpu_ctx* ctx = nullptr;
+  srsue_gpu_ulsch_cfg_t cfg{};
+  CbSegm seg{};
+  int G = 0, max_batch = 0, threads = 0;
+  int32_t* d_cbtab = nullptr; int32_t* d_seq_len = nullptr; uint16_t* d_perm = nullptr; uint16_t* d_seq = nullptr;
+  uint32_t* d_crcshift = nullptr; uint8_t* d_scramble = nullptr; uint8_t* d_tbcrc = nullptr; uint8_t* d_ebits = nullptr;
+  uint8_t* d_payload = nullptr; uint8_t* d_out = nullptr;          // staging of the host-pointer call
+};
+
+int srsue_gpu_ulsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_ulsch_cfg_t* cfg, int max_batch, srsue_gpu_ulsch_plan_t** plan) {
+  if (!ctx || !cfg || !plan || max_batch < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch_plan_create: bad arguments");
+  if (cfg->qm != 2 && cfg->qm != 4 && cfg->qm != 6) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch: qm=%d", cfg->qm);
+  if (cfg->nof_prb < 1 || cfg->nof_prb > 110 || (cfg->n_symb != 12 && cfg->n_symb != 11 && cfg->n_symb != 10 && cfg->n_symb != 9))
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch: nof_prb=%d n_symb=%d", cfg->nof_prb, cfg->n_symb);
+  if (cfg->tbs < 8 || cfg->tbs % 8 || cfg->rv < 0 || cfg->rv > 3 || cfg->sf_idx < 0 || cfg->sf_idx > 9)
+    return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch: tbs=%d rv=%d sf_idx=%d", cfg->tbs, cfg->rv, cfg->sf_idx);
+  CU_CHECK(cudaSetDevice(ctx->device));
+  auto* p = new srsue_gpu_ulsch_plan;
+  p->ctx = ctx; p->cfg = *cfg; p->max_batch = max_batch;
+  if (!cbsegm(cfg->tbs, &p->seg)) { delete p; return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch: tbs=%d cannot be segmented", cfg->tbs); }
+  const CbSegm& s = p->seg;
+  const int rows = 12 * cfg->nof_prb, G = rows * cfg->n_symb * cfg->qm;
+  p->G = G;
+  std::vector<int32_t> cbtab(8 * s.C), seq_len(s.C);
+  std::vector<uint16_t> perm, seq, one;
+  std::vector<uint32_t> shift((size_t)(1 + s.C) * 32, 0u);
+  // TB CRC24A: lane l of the warp takes bytes [l chunk, (l + 1) chunk) of the payload
+  {
+    const int nb = cfg->tbs / 8, chunk = (nb + 31) / 32;
+    for (int l = 0; l < 32; l++) shift[l] = crc_xpow(kCrc24A, (uint64_t)8 * (nb - std::min(nb, (l + 1) * chunk)));
+  }
+  std::map<int, int> perm_of_K;
+  std::map<std::pair<int, int>, std::pair<int, int>> seq_of;      // (K, F) -> (offset, length)
+  int e_start = 0, pos = 0, maxK = 0;
+  for (int r = 0; r < s.C; r++) {
+    const int K = cb_len(s, r), F = (r == 0) ? s.F : 0, E = cb_E(s, G, cfg->qm, 1, r);
+    const int nbs = K / 8 - F / 8 - (s.C > 1 ? 3 : 0);
+    if (!perm_of_K.count(K)) {
+      int f1 = 0, f2 = 0;
+      qpp_params(K, &f1, &f2);
+      perm_of_K[K] = (int)perm.size();
+      for (int64_t i = 0; i < K; i++) perm.push_back((uint16_t)((f1 * i + (int64_t)f2 * i * i) % K));
+    }
+    if (!seq_of.count({K, F})) {
+      rm_tx_sequence(K, F, cfg->rv, one);
+      seq_of[{K, F}] = {(int)seq.size(), (int)one.size()};
+      seq.insert(seq.end(), one.begin(), one.end());
+    }
+    const int32_t row[8] = {K, F, E, e_start, pos, nbs, perm_of_K[K], seq_of[{K, F}].first};
+    std::copy(row, row + 8, cbtab.begin() + 8 * r);
+    seq_len[r] = seq_of[{K, F}].second;
+    if (s.C > 1) {
+      const int nbc = K / 8 - 3, chunk = (nbc + 31) / 32;
+      for (int l = 0; l < 32; l++) shift[(size_t)(1 + r) * 32 + l] = crc_xpow(kCrc24B, (uint64_t)8 * (nbc - std::min(nbc, (l + 1) * chunk)));
+    }
+    e_start += E; pos += nbs; maxK = std::max(maxK, K);
+  }
+  if (e_start != G || pos != (cfg->tbs + 24) / 8) { delete p; return fail(SRSUE_GPU_ERROR, "internal: uplink rate-matching sizes do not add up"); }
+  p->threads = ((maxK / 8 + 31) / 32) * 32;
+  std::vector<uint8_t> gold(G), scr(G / 8, 0);
+  gold_bits(((uint32_t)cfg->rnti << 14) | ((uint32_t)cfg->sf_idx << 9) | (uint32_t)cfg->cell_id, G, gold.data());
+  for (int i = 0; i < G; i++) scr[i >> 3] |= (uint8_t)(gold[i] << (7 - (i & 7)));
+  bool ok = upload(&p->d_cbtab, cbtab) == cudaSuccess && upload(&p->d_seq_len, seq_len) == cudaSuccess &&
+            upload(&p->d_perm, perm) == cudaSuccess && upload(&p->d_seq, seq) == cudaSuccess &&
+            upload(&p->d_crcshift, shift) == cudaSuccess && upload(&p->d_scramble, scr) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_tbcrc, (size_t)max_batch * 4) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&p->d_ebits, (size_t)max_batch * G) == cudaSuccess;
+  if (!ok) { srsue_gpu_ulsch_plan_destroy(p); return fail(SRSUE_GPU_ERROR, "ulsch_plan_create: device allocation failed"); }
+  *plan = p;
+  return 0;
+}
+
+void srsue_gpu_ulsch_plan_destroy(srsue_gpu_ulsch_plan_t* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaFree(p->d_cbtab); cudaFree(p->d_seq_len); cudaFree(p->d_perm); cudaFree(p->d_seq); cudaFree(p->d_crcshift);
+  cudaFree(p->d_scramble); cudaFree(p->d_tbcrc); cudaFree(p->d_ebits); cudaFree(p->d_payload); cudaFree(p->d_out);
+  delete p;
+}
+
+int srsue_gpu_ulsch_plan_info(const srsue_gpu_ulsch_plan_t* p, int* G, int* C, int* Kp, int* Km) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  if (G) *G = p->G;
+  if (C) *C = p->seg.C;
+  if (Kp) *Kp = p->seg.Kp;
+  if (Km) *Km = p->seg.Km;
+  return 0;
+}
+
+int srsue_gpu_ulsch_encode(srsue_gpu_ulsch_plan_t* p, int n_tb, const uint8_t* d_payload, uint8_t* d_bits, void* stream) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  if (n_tb < 0 || n_tb > p->max_batch) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "n_tb=%d outside [0, max_batch=%d]", n_tb, p->max_batch);
+  if (n_tb == 0) return 0;
+  if (!d_payload || !d_bits) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch_encode: null buffer");
+  CU_CHECK(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  UlschArgs a{};
+  a.payload = d_payload; a.payload_stride = p->cfg.tbs / 8; a.tbcrc = p->d_tbcrc; a.ebits = p->d_ebits; a.out = d_bits;
+  a.out_stride = p->G / 8; a.n_tb = n_tb; a.tbs = p->cfg.tbs; a.C = p->seg.C; a.G = p->G; a.qm = p->cfg.qm;
+  a.rows = 12 * p->cfg.nof_prb; a.n_symb = p->cfg.n_symb;
+  a.cbtab = p->d_cbtab; a.seq_len = p->d_seq_len; a.perm = p->d_perm; a.seq = p->d_seq; a.crcshift = p->d_crcshift; a.scramble = p->d_scramble;
+  for (int done = 0; done < n_tb; done += 65535) {
+    const int n = std::min(65535, n_tb - done);
+    UlschArgs b = a;
+    b.payload += (size_t)done * a.payload_stride; b.tbcrc += (size_t)done * 4; b.ebits += (size_t)done * a.G; b.out += (size_t)done * a.out_stride;
+    b.n_tb = n;
+    ulsch_tbcrc_kernel<<<n, 32, 0, st>>>(b);
+    ulsch_encode_kernel<<<dim3(a.C, n), p->threads, 0, st>>>(b);
+    ulsch_interleave_kernel<<<dim3((a.G / 8 + 255) / 256, n), 256, 0, st>>>(b);
+    p->ctx->launch_count += 3;
+  }
+  CU_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int srsue_gpu_ulsch_encode_host(srsue_gpu_ulsch_plan_t* p, int n_tb, const uint8_t* h_payload, uint8_t* h_bits) {
+  if (!p) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "null plan");
+  if (n_tb < 0 || n_tb > p->max_batch) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "n_tb=%d outside [0, max_batch=%d]", n_tb, p->max_batch);
+  if (n_tb == 0) return 0;
+  if (!h_payload || !h_bits) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ulsch_encode_host: null buffer");
+  CU_CHECK(cudaSetDevice(p->ctx->device));
+  const size_t pb = (size_t)p->cfg.tbs / 8, ob = (size_t)p->G / 8;
+  if (!p->d_payload) CU_CHECK(cudaMalloc((void**)&p->d_payload, (size_t)p->max_batch * pb));
+  if (!p->d_out) CU_CHECK(cudaMalloc((void**)&p->d_out, (size_t)p->max_batch * ob));
+  CU_CHECK(cudaMemcpy(p->d_payload, h_payload, (size_t)n_tb * pb, cudaMemcpyHostToDevice));
+  const int rc = srsue_gpu_ulsch_encode(p, n_tb, p->d_payload, p->d_out, nullptr);
+  if (rc) return rc;
+  CU_CHECK(cudaMemcpy(h_bits, p->d_out, (size_t)n_tb * ob, cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -52,6 +52,27 @@ __global__ void triples_to_tcb_kernel(const int16_t* in, long long in_stride, in
 __global__ void tcb_to_triples_kernel(const int16_t* in, long long in_stride, int16_t* out, long long out_stride,
                                       int n_cb, TurboGeomDev g);
 
+// ---- uplink shared-channel encoder (ulsch.cu) ---------------------------------------------------------
+struct UlschArgs {
+  const uint8_t* payload;    // [n_tb][payload_stride] transport blocks, tbs / 8 bytes each
+  int payload_stride;
+  uint8_t* tbcrc;            // [n_tb][4] scratch: the CRC24A bytes of every transport block
+  uint8_t* ebits;            // [n_tb][G] scratch: the codeword before the channel interleaver, one bit per byte
+  uint8_t* out;              // [n_tb][out_stride] interleaved, scrambled bits, packed MSB first
+  int out_stride;
+  int n_tb, tbs, C, G, qm, rows, n_symb;      // rows = 12 nof_prb
+  const int32_t* cbtab;      // [C][8]: K, F, E, first bit of the block in the codeword, first stream byte, stream bytes,
+                             //         offset of its QPP table in perm, offset of its read order in seq
+  const int32_t* seq_len;    // [C] entries of the block's read order (circular buffer without <NULL>)
+  const uint16_t* perm;      // QPP tables pi(i) of the code-block sizes in use
+  const uint16_t* seq;       // circular-buffer read orders: (index k of the triple << 2) | stream
+  const uint32_t* crcshift;  // [1 + C][32]: x^(8 * bytes after lane's chunk) mod g for the TB CRC24A, then every block's CRC24B
+  const uint8_t* scramble;   // [G / 8] Gold sequence packed MSB first
+};
+__global__ void ulsch_tbcrc_kernel(const UlschArgs a);
+__global__ void ulsch_encode_kernel(const UlschArgs a);
+__global__ void ulsch_interleave_kernel(const UlschArgs a);
+
 // ---- front end -------------------------------------------------------------------------------------
 struct OfdmArgs {
   const float2* iq;          // [n_sf][15 * nfft]

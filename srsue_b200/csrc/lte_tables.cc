@@ -263,6 +263,26 @@ int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& ta
   return n;
 }
 
+// Transmit side of the same circular buffer (uplink encoder, ulsch.cu): the order in which the non-<NULL> elements are read
+// for redundancy version rv, as (k << 2) | stream with k the index of the triple d(0..2)_k, k < K + 4.
+void rm_tx_sequence(int K, int F, int rv, std::vector<uint16_t>& seq) {
+  static const uint8_t colperm[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                      1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+  const int D = K + 4, R = (D + 31) / 32, Kpi = 32 * R, ND = Kpi - D, Kw = 3 * Kpi;
+  const int k0 = R * (2 * ((Kw + 8 * R - 1) / (8 * R)) * rv + 2);
+  seq.clear();
+  for (int step = 0; step < Kw; step++) {
+    const int j = (k0 + step) % Kw;
+    int stream, col_pos;
+    if (j < Kpi) { stream = 0; col_pos = j; } else { stream = 1 + ((j - Kpi) & 1); col_pos = (j - Kpi) >> 1; }
+    const int row = col_pos % R, col = col_pos / R;
+    const int y = (stream < 2) ? row * 32 + colperm[col] : (colperm[col] + 32 * row + 1) % Kpi;
+    const int d = y - ND;
+    if (d < 0 || (stream < 2 && d < F)) continue;
+    seq.push_back((uint16_t)((d << 2) | stream));
+  }
+}
+
 void fft_twiddles(int n, std::vector<float>& tw) {
   if (n % 3 == 0) {
     // n = 3 m (1536): the table of the three m-point transforms, then the full-circle twiddles w1 = w_n^k and

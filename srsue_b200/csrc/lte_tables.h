@@ -112,6 +112,7 @@ int rm_gather_table(const TurboGeom& g, int F, int rv, std::vector<uint16_t>& ta
 // offset of decoder-input element (srsLTE triples index 3k+stream, k < K+4) inside the tcb buffer
 int tcb_offset(const TurboGeom& g, int triple_index);
 
+void rm_tx_sequence(int K, int F, int rv, std::vector<uint16_t>& seq);   // (k << 2) | stream in circular-buffer read order
 void fft_twiddles(int n, std::vector<float>& tw /* re,im pairs, n/2 entries */);
 // CFO correction (SPEC.md 14): 4096-entry unit circle and the 2^-32-turn phase step per sample
 constexpr int kCfoTableLog2 = 12;

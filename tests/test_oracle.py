@@ -596,3 +596,35 @@ def test_pdcch_transmission_equals_standard_description(oracle):
             assert len(ks) == 4
             want[0, rl[j], ks] = sym[4 * src[j]:4 * src[j] + 4]
         assert np.allclose(grid, want, atol=1e-12)
+
+
+# ---- uplink shared-channel encoder (lteo_ulsch_encode): pinned by the receive-side functions above, which are themselves
+# pinned by the 36.212 constructions of this file: undo scrambling and the channel interleaver, de-match every code block,
+# decode it, and the transport block with a good CRC24A must come back, for every redundancy version
+@pytest.mark.parametrize("tbs,qm,nof_prb,rv,n_symb", [(152, 2, 6, 0, 12), (2216, 4, 15, 1, 12), (11448, 6, 25, 2, 11), (30576, 4, 100, 3, 12)])
+def test_ulsch_encoder_round_trip_through_the_receive_side(oracle, tbs, qm, nof_prb, rv, n_symb):
+    o = oracle
+    rng = np.random.default_rng(tbs)
+    tb = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    rnti, sf_idx, cell_id = 0x77, 4, 300
+    h = o.ulsch_encode(tbs, qm, nof_prb, tb, rv=rv, rnti=rnti, sf_idx=sf_idx, cell_id=cell_id, n_symb=n_symb)
+    rows, G = 12 * nof_prb, 12 * nof_prb * n_symb * qm
+    assert len(h) == G
+    # 36.211 5.3.1 scrambling, then the inverse of the 36.212 5.2.2.8 interleaver written as a matrix transpose
+    b = h ^ o.gold((rnti << 14) | (sf_idx << 9) | cell_id, G)
+    g = b.reshape(n_symb, rows, qm).transpose(1, 0, 2).reshape(-1)
+    llr = (1 - 2 * g.astype(np.int16)) * -40            # bit 1 -> positive LLR, the receive chain's convention
+    s = o.cbsegm(tbs)
+    stream, pos = [], 0
+    for r in range(s.C):
+        K, F, E = o.cb_len(s, r), (s.F if r == 0 else 0), o.cb_E(s, G, qm, 1, r)
+        w = o.rm_rx(llr[pos:pos + E], K, F, rv)
+        pos += E
+        bits, it, ok = o.tdec(w, K, 4, 2 if s.C > 1 else 1)[:3]
+        assert ok, "code block %d: CRC failed" % r
+        stream.append(bits[F:K - (24 if s.C > 1 else 0)])
+    assert pos == G
+    stream = np.concatenate(stream)
+    assert len(stream) == tbs + 24
+    assert np.array_equal(np.packbits(stream[:tbs]), tb)
+    assert o.crc_bits(stream, o.CRC24A) == 0
