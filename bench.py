@@ -241,7 +241,7 @@ def run_harq(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_mixed(args, rank, local_rank, world):
+def run_mixed(args, rank, local_rank, world, embedded=False):
     """A stream of heterogeneous batches (mixed 1.4-20 MHz bandwidths) through the batching layer with HOST buffers:
     the global stream is world x 20 batches, assigned to ranks by estimated turbo work (srsue_b200.shard), each rank
     packs its share with srsue_gpu_batch_submit / _wait.  Every number here is end to end (H2D + D2H inside)."""
@@ -252,10 +252,10 @@ def run_mixed(args, rank, local_rank, world):
     from srsue_b200.shard import balance_by_work
     from oracle import oracle as o
     from srsue_b200.shard import bind_rank_to_gpu_numa
-    if world > 1:
+    if world > 1 and not embedded:
         bind_rank_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = sg.lib()
     # ---- the global stream: batches of one shape each, sizes from the shares; identical on every rank ----
@@ -370,6 +370,7 @@ def run_mixed(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    result = None
     if rank == 0:
         dt_max = vals.item()
         bits_all, sf_all, launches_all, iq_all, pl_all = sums.tolist()
@@ -386,7 +387,7 @@ def run_mixed(args, rank, local_rank, world):
                "subframes_per_s": sf_all / dt_max, "verified_bit_exact_payload": bool(verified),
                "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": iq_all, "d2h_bytes_per_step": pl_all},
                "gpu_launches": int(launches_all), "clocks": sampler.summary()}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not embedded:
             cores = os.cpu_count() or 1
             build_kind, restore = cpu_arm(o)
             t0 = time.perf_counter()
@@ -400,12 +401,22 @@ def run_mixed(args, rank, local_rank, world):
             restore()
             out["cpu_baseline"] = {"value": cbits / cdt / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "port",
                                    "sample": "same shape mix, %d threads, CPU restatement of the srsLTE path: %s" % (cores, build_kind)}
-        print(json.dumps(out))
+        if embedded:
+            result = {"value": val, "unit": "Mbit/s", "metric": out["metric"], "subframes_per_s": out["subframes_per_s"],
+                      "ms_per_step": out["ms_per_step"], "steps": args.steps, "workload": out["config"]["workload"],
+                      "subframes_per_step": out["config"]["subframes_per_step"], "api": out["config"]["api"],
+                      "h2d_bytes_per_step": iq_all, "d2h_bytes_per_step": pl_all, "verified_bit_exact_payload": bool(verified),
+                      "note": "BASELINE configs[4]: end to end from pinned host buffers through srsue_gpu_batch_submit / _wait, "
+                              "batches assigned to the ranks by estimated turbo work, no collective"}
+        else:
+            print(json.dumps(out))
     batch.close()
+    ctx.close()
     for p in pinned:
         lib.srsue_gpu_host_free(p)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.destroy_process_group()
+    return result
 
 
 def main():
@@ -674,6 +685,15 @@ def main():
     leg_ms, leg_turbo_ms = vals.tolist()[3:3 + nl], vals.tolist()[3 + nl:3 + 2 * nl]
     leg_ok, leg_iters = sums.tolist()[4:4 + nl], sums.tolist()[4 + nl:4 + 2 * nl]
 
+    # BASELINE configs[4] as a leg of the same line, so that the driver's 1/2/4/8-GPU runs carry it: the mixed-bandwidth
+    # stream through the batching layer, host buffers (every rank takes part)
+    mixed_leg = None
+    if not args.no_legs and WORKLOAD["tm"] == 1:
+        import copy
+        margs = copy.copy(args)
+        margs.batch, margs.steps, margs.warmup, margs.blind = 1024, 5, 3, False
+        mixed_leg = run_mixed(margs, rank, local_rank, world, embedded=True)
+
     if rank == 0:
         value = ok_bits_all / (total_ms_max * 1e-3) / 1e6
         peaks = {}
@@ -776,6 +796,8 @@ def main():
                       "roofline": {"achieved": tops, "peak": alu_peak_tops, "unit": "Tint16op/s", "frac": tops / alu_peak_tops}}
             if "passing_equal_sent" in legs[n]:
                 out[n]["passing_blocks_equal_sent"] = legs[n]["passing_equal_sent"]
+        if mixed_leg:
+            out["mixed_stream"] = mixed_leg
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             build_kind, restore = cpu_arm(o)

@@ -263,6 +263,7 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   {
     static const int env_delay = turbo_env_int("SRSUE_TURBO_PHASE_DELAY", -1);
     a.phase_delay = lc.ngroups > 1 ? (env_delay >= 0 ? env_delay : 350 * g.W) : 0;
+    if ((long long)n_cb < 2LL * lc.grid * lc.ncb) a.phase_delay = 0;      // short launches: latency matters more than overlap
   }
   static const bool generic_only = turbo_env_int("SRSUE_TURBO_GENERIC", 0) != 0;      // tuning: skip the T-specific kernels
   const int variant = turbo_perm_stride(g) == 64 ? 1 : generic_only ? 0 : g.T == 26 ? 2 : g.T == 24 ? 3 : 0;
