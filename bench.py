@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="subframes per step and per GPU (device-resident)")
-    ap.add_argument("--e2e-batch", type=int, default=1024, help="subframes per step for the host-buffer measurement")
+    ap.add_argument("--e2e-batch", type=int, default=4096, help="subframes per step for the host-buffer measurement")
     ap.add_argument("--pool", type=int, default=512, help="distinct synthetic subframes (tiled to the batch)")
     ap.add_argument("--waterfall-snr", type=float, default=21.5, help="SNR of the waterfall leg (first-transmission BLER about 0.2)")
     ap.add_argument("--no-legs", action="store_true", help="skip the fixed-4-iteration and waterfall legs")
