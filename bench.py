@@ -479,6 +479,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # a host-side group for the one place where ranks must wait WITHOUT touching their GPU: while rank 0 drives all
+    # devices through the library's own dispatcher, an NCCL barrier would park a spinning kernel on every other GPU
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     # ---- inputs -------------------------------------------------------------------------------------
     ocell, ocfg, tbs, iqs = gen_pool(o, args.pool, args.snr, 1000 * rank)
@@ -644,7 +647,7 @@ def main():
         torch.cuda.empty_cache()
         barrier()
         if rank == 0:
-            nsub = EB * world
+            nsub = min(EB, 1024) * world
             p_mpl = lib.srsue_gpu_host_alloc(nsub * I.payload_stride)
             h_mpl = np.ctypeslib.as_array(C.cast(p_mpl, C.POINTER(C.c_uint8)), shape=(nsub, I.payload_stride))
             mb = sg.Batch(None, nsub, 0.01, args.noise_mode, args.max_iter, devices=list(range(world)))
@@ -668,7 +671,9 @@ def main():
                      "api": "srsue_gpu_batch_create_multi + srsue_gpu_batch_submit/_wait from ONE process, host buffers (H2D and D2H inside)"}
             mb.close()
             lib.srsue_gpu_host_free(p_mpl)
-        barrier()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)           # the other ranks wait on the host, their GPUs stay idle for rank 0
 
     # ---- reduce over ranks (max time, sum of units) ------------------------------------------------------
     leg_names = sorted(legs)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# ad-hoc: time the turbo kernel under several tuning knobs (one JSON line each), K = 5824, 53 248 blocks
+# ad-hoc: time the turbo kernel under several tuning knobs / build variants (one JSON line each), K = 5824, 53 248 blocks
 out=${1:-gpurun_out/perf_variants.jsonl}
 : > $out
 run() {  # label, env..., -- args
@@ -11,16 +11,13 @@ run() {  # label, env..., -- args
   env "${envs[@]}" python tools/perf_turbo.py "$@" >> $out 2>>gpurun_out/perf_variants.err || echo "null" >> $out
   sed -i '$ s/$/}/' $out
 }
-export SRSUE_TURBO_PHASE_DELAY=40000
 for mode in "4 2 30.0" "4 2 2.0" "4 0 2.0"; do
   tag=$(echo $mode | tr ' ' '_')
-  run "generic_$tag" SRSUE_TURBO_GENERIC=1 -- 5824 53248 $mode
-  run "t26_$tag" A=1 -- 5824 53248 $mode
-  run "t26_d60k_$tag" SRSUE_TURBO_PHASE_DELAY=60000 -- 5824 53248 $mode
-  run "t26_d30k_$tag" SRSUE_TURBO_PHASE_DELAY=30000 -- 5824 53248 $mode
+  run "base_$tag" A=1 -- 5824 53248 $mode
+  for v in $VARIANTS; do
+    run "${v}_$tag" SRSUE_GPU_LIB=build/variants/libsrsue_gpu_$v.so -- 5824 53248 $mode
+  done
 done
-run "K6144" A=1 -- 6144 53248 4 0 2.0
-run "K40" A=1 -- 40 1000000 4 0 2.0
 python -c "
 import json
 for l in open('$out'):
