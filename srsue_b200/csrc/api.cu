@@ -1039,7 +1039,7 @@ static int chest_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_
   a.pilots = reinterpret_cast<float2*>(d_pilots);
   a.crs_sign = p->d_crs; a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_prb = p->cell.nof_prb; a.nof_ports = p->cell.nof_ports;
   std::memcpy(a.crs_off, p->crs_off, sizeof(a.crs_off));
-  const int smem = 2 * p->cell.nof_ports * 4 * 2 * p->cell.nof_prb * (int)sizeof(float2);
+  const int smem = 2 * p->cell.nof_ports * 4 * 2 * p->cell.nof_prb * (int)sizeof(float2) + 4 * p->info.nsc * (int)sizeof(float);
   // 128 threads measured best on B200 (0.19 ms vs 0.26 ms per 4096 subframes with 512): the kernel is bound by its
   // three ordered reduction warps, smaller CTAs pack more of them per SM.  Needs >= 3 warps.
   static const int chest_threads = std::min(128, std::max(96, getenv("SRSUE_CHEST_THREADS") ? atoi(getenv("SRSUE_CHEST_THREADS")) : 128));

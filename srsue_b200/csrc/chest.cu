@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
   const int nsc = a.nsc, M = 2 * a.nof_prb, np = a.nof_ports;
   float2* s_ls = s_ch;                    // [np][4][M]
   float2* s_sm = s_ch + np * 4 * M;       // [np][4][M]
+  float* s_pw = reinterpret_cast<float*>(s_ch + 2 * np * 4 * M);   // [4][nsc]: |y|^2 of the four CRS symbols (RSSI)
   const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
   const int crs_l[4] = {0, 4, 7, 11};
   const float isq2 = (float)(1.0 / sqrt(2.0));
@@ -48,6 +49,10 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
     const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
     s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
   }
+  // ---- RSSI inputs: the ordered sum below is one warp walking 4 nsc values (SPEC 3.5 fixes its order), which as a chain
+  // of dependent global loads kept every CTA resident for tens of microseconds; here all threads fetch the values at once
+  for (int si = 0; si < 4; si++)
+    for (int k = tid; k < nsc; k += nt) s_pw[si * nsc + k] = abs2_rn(y[crs_l[si] * nsc + k]);
   // ---- least squares at the pilots ------------------------------------------------------------------
   for (int i = tid; i < np * 4 * M; i += nt) {
     const int m = i % M, si = (i / M) % 4, p = i / (4 * M);
@@ -110,10 +115,7 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
     const float s = warp_sum_ordered(n_rsrp, lane, [&](int i) { return abs2_rn(s_ls[i]); });   // port 0 first
     if (lane == 0) s_red[1] = __fdiv_rn(s, (float)n_rsrp);
   } else if (warp == 2) {
-    const float s = warp_sum_ordered(n_rssi, lane, [&](int i) {
-      const int si = i / nsc, k = i - si * nsc;
-      return abs2_rn(y[crs_l[si] * nsc + k]);
-    });
+    const float s = warp_sum_ordered(n_rssi, lane, [&](int i) { return s_pw[i]; });
     if (lane == 0) s_red[2] = __fdiv_rn(s, (float)n_rssi);
   }
   __syncthreads();
