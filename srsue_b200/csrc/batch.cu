@@ -57,14 +57,36 @@ __global__ void __launch_bounds__(256) softbuffer_rows_kernel(int16_t* packed, i
 }
 
 // Zero-copy gather of scattered subframes: rows[i] points into pinned host memory (UVA), the GPU pulls each row over
-// PCIe into the packed device array.  gridDim = (rows, slices); VEC = 16 or 8 bytes per access.
+// PCIe into the packed device array.  V = 16 or 8 bytes per access.  The kernel is bound by the PCIe round trip, not
+// by the SMs, and it runs NEXT TO the decoding chain of the previous chunk -- whose turbo decoder needs whole SMs (all
+// registers of an SM per CTA).  So it is a small persistent grid (a few dozen CTAs walking the (row, slice) items with eight
+// loads per thread in flight: enough bytes on the wire to fill the link) instead of one CTA per row and slice, which put
+// long-lived CTAs on every SM and kept the decoder waiting (11.9 vs 15.4 Gbit/s against the copy-engine path).
 template <typename V>
-__global__ void __launch_bounds__(256) gather_host_rows_kernel(V* __restrict__ packed, const V* const* __restrict__ rows, int row_vecs) {
-  const V* __restrict__ src = rows[blockIdx.x];
-  V* dst = packed + (size_t)blockIdx.x * row_vecs;
-  const int per = (row_vecs + gridDim.y - 1) / gridDim.y;
-  const int lo = blockIdx.y * per, hi = min(row_vecs, lo + per);
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+__global__ void __launch_bounds__(256) gather_host_rows_kernel(V* __restrict__ packed, const V* const* __restrict__ rows, int n_rows,
+                                                               int row_vecs, int slices) {
+  const int per = (row_vecs + slices - 1) / slices;
+  for (int item = blockIdx.x; item < n_rows * slices; item += gridDim.x) {
+    const int row = item / slices, sl = item - row * slices;
+    const V* __restrict__ src = rows[row];
+    V* dst = packed + (size_t)row * row_vecs;
+    const int lo = sl * per, hi = min(row_vecs, lo + per);
+    constexpr int U = 8;                                  // loads in flight per thread
+    for (int i = lo + threadIdx.x; i < hi; i += U * blockDim.x) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (i + u * (int)blockDim.x < hi) v[u] = src[i + u * blockDim.x];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (i + u * (int)blockDim.x < hi) dst[i + u * blockDim.x] = v[u];
+    }
+  }
+}
+// CTAs of the gather grid (SRSUE_GATHER_CTAS overrides)
+static int gather_ctas(int items) {
+  static const int want = getenv("SRSUE_GATHER_CTAS") ? std::max(1, atoi(getenv("SRSUE_GATHER_CTAS"))) : 48;
+  return std::max(1, std::min(items, want));
 }
 
 // Zero-copy scatter of the payload rows into the callers' pinned buffers.  WORD = 4 when every row and pointer is
@@ -548,11 +570,11 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
         B_CU(cudaStreamWaitEvent(b->s_copy, b->ev_free[h], 0));
         const int slices = (int)std::max<size_t>(1, row_bytes / (32 * 1024));
         if ((align_or & 15) == 0)
-          gather_host_rows_kernel<uint4><<<dim3(m, slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint4*>(b->d_iq[h]),
-              reinterpret_cast<const uint4* const*>(b->h_iq_rows + pos_up), (int)(row_bytes / 16));
+          gather_host_rows_kernel<uint4><<<gather_ctas(m * slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint4*>(b->d_iq[h]),
+              reinterpret_cast<const uint4* const*>(b->h_iq_rows + pos_up), m, (int)(row_bytes / 16), slices);
         else
-          gather_host_rows_kernel<uint2><<<dim3(m, slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint2*>(b->d_iq[h]),
-              reinterpret_cast<const uint2* const*>(b->h_iq_rows + pos_up), (int)(row_bytes / 8));
+          gather_host_rows_kernel<uint2><<<gather_ctas(m * slices), 256, 0, b->s_copy>>>(reinterpret_cast<uint2*>(b->d_iq[h]),
+              reinterpret_cast<const uint2* const*>(b->h_iq_rows + pos_up), m, (int)(row_bytes / 8), slices);
         B_CU(cudaGetLastError());
         b->launches++;
       } else if (runs > 4 && row_bytes <= kGatherRowBytes) {
@@ -792,8 +814,9 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
       const int m = (int)std::min(cap, idx.size() - off);
       for (int r = 0; r < m; r++) b->h_iq_rows[r] = b->d_biq + row_off[idx[off + r]];
       const int slices = (int)std::max<size_t>(1, row_bytes / (32 * 1024));
-      gather_host_rows_kernel<uint4><<<dim3(m, slices), 256, 0, st>>>(reinterpret_cast<uint4*>(b->d_iq[0]),
-          reinterpret_cast<const uint4* const*>(b->h_iq_rows), (int)(row_bytes / 16));
+      // (device-to-device here: the rows are the samples phase 1 left on the device; every SM may take part)
+      gather_host_rows_kernel<uint4><<<std::min(m * slices, 148 * 8), 256, 0, st>>>(reinterpret_cast<uint4*>(b->d_iq[0]),
+          reinterpret_cast<const uint4* const*>(b->h_iq_rows), m, (int)(row_bytes / 16), slices);
       B_CU(cudaGetLastError());
       srsue_gpu_pdsch_plan_set_iq_format(fp[1]->plan, b->iq_format, b->iq16_scale);
       srsue_gpu_pdsch_plan_set_cfo(fp[1]->plan, nullptr, 0);

@@ -22,7 +22,8 @@ for r in range(n):
     h_iq[r] = gen[r % 8][1]
 ctx = None if devices else sg.Context(0)
 batch = sg.Batch(ctx, n, 0.01, 0, 4, devices=devices)
-prep = sg.Batch.prepare([dict(cell=cell, cfg=cfg, iq=h_iq[r], payload=h_pl[r]) for r in range(n)])
+order = np.random.default_rng(1).permutation(n) if os.environ.get("PERMUTE") else np.arange(n)      # scattered rows: zero-copy gather
+prep = sg.Batch.prepare([dict(cell=cell, cfg=cfg, iq=h_iq[r], payload=h_pl[r]) for r in order])
 for _ in range(3):
     batch.submit_prepared(prep)
     lib.srsue_gpu_batch_wait(batch.h)
@@ -34,6 +35,6 @@ for _ in range(5):
     lib.srsue_gpu_batch_wait(batch.h)
     t2 = time.perf_counter()
     ts.append(t1 - t0); tw.append(t2 - t1)
-ok = all(np.array_equal(h_pl[r], gen[r % 8][0]) for r in range(0, n, 97))
+ok = all(np.array_equal(h_pl[r], gen[r % 8][0]) for r in range(0, n, 97))   # payload row r belongs to IQ row r in both orders
 tot = np.mean(ts) + np.mean(tw)
 print(dict(n=n, devices=devices, submit_ms=1e3 * np.mean(ts), wait_ms=1e3 * np.mean(tw), gbit_s=n * 75376 / tot / 1e9, ok=ok, stats=batch.stats()))
