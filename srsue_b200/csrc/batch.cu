@@ -152,7 +152,7 @@ struct srsue_gpu_batch {
   std::vector<srsue_gpu_sf_desc_t> blind_descs;   // phase-2 descriptors (grants filled in, iq = device row)
   std::vector<int> blind_index;                   // their positions in the caller's array
   srsue_gpu_sf_desc_t* blind_orig = nullptr;
-  int blind_n = 0;
+  int blind_n = 0, blind_rows_used = 0;
   // ---- multi-GPU front (srsue_gpu_batch_create_multi): this object then owns no device state of its own.  Every device
   // has its own context, single-device batch (streams, pinned staging, plan cache, resident soft buffers) and host
   // thread; a submission is partitioned here, the parts run concurrently, results are gathered in batch_wait.
@@ -738,29 +738,16 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
     return rc;
   }
   b->launches = 0;
+  b->blind_rows_used = 0;
   cudaStream_t st = b->s_compute;
   const size_t esz = b->iq_format == SRSUE_GPU_IQ_SC16 ? 4 : sizeof(srsue_gpu_cf_t);
-  // ---- 1. all samples to the device, once (neighbouring host buffers in one copy) -----------------------------------
-  std::vector<size_t> row_off(n + 1, 0);
+  // ---- 1. control channels run once per (cell, subframe number, RNTI): group the descriptors first ------------------
   for (int i = 0; i < n; i++) {
     const srsue_gpu_sf_desc_t& d = descs[i];
     if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d has a null buffer", i);
     if (d.cfg.sf_idx < 0 || d.cfg.sf_idx > 9 || d.softbuffer_id >= 0) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d: bad sf_idx, or a soft buffer id (blind subframes are decoded as new transmissions)", i);
-    const int nfft = symbol_sz_of(d.cell.nof_prb);
-    if (nfft <= 0) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d: bad cell", i);
-    row_off[i + 1] = row_off[i] + ((size_t)15 * nfft * esz + 255) / 256 * 256;
+    if (symbol_sz_of(d.cell.nof_prb) <= 0) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit_blind: descriptor %d: bad cell", i);
   }
-  { int rc = grow(&b->d_biq, &b->biq_bytes, row_off[n] + 256, st); if (rc) return rc; }
-  for (int i = 0; i < n;) {
-    int e = i + 1;
-    const size_t rb = (size_t)15 * symbol_sz_of(descs[i].cell.nof_prb) * esz;
-    const bool packed = row_off[i + 1] - row_off[i] == rb;      // rows are padded to 256 bytes: merge only when there is no padding
-    while (packed && e < n && descs[e].cell.nof_prb == descs[i].cell.nof_prb &&
-           reinterpret_cast<const char*>(descs[e].iq) == reinterpret_cast<const char*>(descs[e - 1].iq) + rb) e++;
-    B_CU(cudaMemcpyAsync(b->d_biq + row_off[i], descs[i].iq, (size_t)(e - i) * rb, cudaMemcpyHostToDevice, st));
-    i = e;
-  }
-  // ---- 2. control channels, one pass per (cell, subframe number, RNTI) ------------------------------------------------
   std::map<std::string, std::vector<int>> groups;
   std::vector<std::string> group_order;
   for (int i = 0; i < n; i++) {
@@ -769,6 +756,48 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
     auto it = groups.find(k);
     if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }
     it->second.push_back(i);
+  }
+  // ---- 2. all samples to the device, once, group by group: the rows of a group are packed one after the other, so the
+  // control pass reads them in place.  Scattered rows in pinned memory the library knows are pulled by the GPU (one
+  // kernel per group instead of one copy per subframe); neighbouring rows go up in one copy. ---------------------------
+  std::vector<size_t> row_off(n + 1, 0);
+  {
+    size_t pos = 0;
+    for (const std::string& gk : group_order) {
+      const std::vector<int>& idx = groups[gk];
+      const size_t rb = (size_t)15 * symbol_sz_of(descs[idx[0]].cell.nof_prb) * esz;
+      pos = (pos + 255) / 256 * 256;
+      for (int i : idx) { row_off[i] = pos; pos += rb; }
+    }
+    int rc = grow(&b->d_biq, &b->biq_bytes, pos + 256, st); if (rc) return rc;
+  }
+  for (const std::string& gk : group_order) {
+    const std::vector<int>& idx = groups[gk];
+    const int m = (int)idx.size();
+    const size_t rb = (size_t)15 * symbol_sz_of(descs[idx[0]].cell.nof_prb) * esz;
+    auto row_ptr = [&](int r) { return reinterpret_cast<const char*>(descs[idx[r]].iq); };
+    int runs = 1;
+    for (int r = 1; r < m; r++) runs += row_ptr(r) != row_ptr(r - 1) + rb;
+    bool pull = runs > 4 && rb % 16 == 0 && m <= b->max_subframes;
+    for (int r = 0; r < m && pull; r++) pull = srsue::host_region_contains(descs[idx[r]].iq, rb) && (reinterpret_cast<uintptr_t>(descs[idx[r]].iq) & 15) == 0;
+    if (pull) {
+      // (the pointer table lives in pinned memory the GPU reads directly; one table region per group)
+      const void** tab = b->h_iq_rows + b->blind_rows_used;
+      for (int r = 0; r < m; r++) tab[r] = descs[idx[r]].iq;
+      b->blind_rows_used += m;
+      const int slices = (int)std::max<size_t>(1, rb / (32 * 1024));
+      gather_host_rows_kernel<uint4><<<gather_ctas(m * slices), 256, 0, st>>>(reinterpret_cast<uint4*>(b->d_biq + row_off[idx[0]]),
+          reinterpret_cast<const uint4* const*>(tab), m, (int)(rb / 16), slices);
+      B_CU(cudaGetLastError());
+      b->launches++;
+    } else {
+      for (int r = 0; r < m;) {
+        int e = r + 1;
+        while (e < m && row_ptr(e) == row_ptr(e - 1) + rb) e++;
+        B_CU(cudaMemcpyAsync(b->d_biq + row_off[idx[r]], descs[idx[r]].iq, (size_t)(e - r) * rb, cudaMemcpyHostToDevice, st));
+        r = e;
+      }
+    }
   }
   const size_t cap = (size_t)b->chunk_cap;
   if (!b->d_bcfi) {
@@ -805,23 +834,17 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
     const size_t grid = (size_t)14 * info.nsc;
     int n_reg_max = 0;
     for (int cfi = 1; cfi <= 3; cfi++) { int nr = 0, nc = 0; if (srsue_gpu_pdcch_info(fp[cfi]->plan, ng_x6, &nr, &nc)) return SRSUE_GPU_ERROR; n_reg_max = std::max(n_reg_max, nr); }
-    int rc = grow(&b->d_iq[0], &b->iq_elems[0], cap * info.sf_len, st); if (rc) return rc;
-    rc = grow(&b->d_bsf, &b->bsf_elems, cap * grid, st); if (rc) return rc;
+    int rc = grow(&b->d_bsf, &b->bsf_elems, cap * grid, st); if (rc) return rc;
     rc = grow(&b->d_bce, &b->bce_elems, cap * grid * d0.cell.nof_ports, st); if (rc) return rc;
     rc = grow(&b->d_bllr, &b->bllr_elems, 3 * cap * 8 * (size_t)n_reg_max, st); if (rc) return rc;
-    const size_t row_bytes = (size_t)info.sf_len * esz;
     for (size_t off = 0; off < idx.size(); off += cap) {
       const int m = (int)std::min(cap, idx.size() - off);
-      for (int r = 0; r < m; r++) b->h_iq_rows[r] = b->d_biq + row_off[idx[off + r]];
-      const int slices = (int)std::max<size_t>(1, row_bytes / (32 * 1024));
-      // (device-to-device here: the rows are the samples phase 1 left on the device; every SM may take part)
-      gather_host_rows_kernel<uint4><<<std::min(m * slices, 148 * 8), 256, 0, st>>>(reinterpret_cast<uint4*>(b->d_iq[0]),
-          reinterpret_cast<const uint4* const*>(b->h_iq_rows), m, (int)(row_bytes / 16), slices);
-      B_CU(cudaGetLastError());
+      // the rows of this group lie packed in d_biq in group order: the FFT reads them in place
+      const srsue_gpu_cf_t* rows_in = reinterpret_cast<const srsue_gpu_cf_t*>(b->d_biq + row_off[idx[off]]);
       srsue_gpu_pdsch_plan_set_iq_format(fp[1]->plan, b->iq_format, b->iq16_scale);
       srsue_gpu_pdsch_plan_set_cfo(fp[1]->plan, nullptr, 0);
-      if (b->iq_format == SRSUE_GPU_IQ_SC16) rc = srsue_gpu_ofdm_rx_sc16(fp[1]->plan, m, reinterpret_cast<const int16_t*>(b->d_iq[0]), b->iq16_scale, b->d_bsf, st);
-      else rc = srsue_gpu_ofdm_rx(fp[1]->plan, m, b->d_iq[0], b->d_bsf, st);
+      if (b->iq_format == SRSUE_GPU_IQ_SC16) rc = srsue_gpu_ofdm_rx_sc16(fp[1]->plan, m, reinterpret_cast<const int16_t*>(rows_in), b->iq16_scale, b->d_bsf, st);
+      else rc = srsue_gpu_ofdm_rx(fp[1]->plan, m, rows_in, b->d_bsf, st);
       if (!rc) rc = srsue_gpu_chest(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, st);
       // PCFICH and PDCCH with the channel estimator's noise figure, as srslte_ue_dl_decode does
       if (!rc) rc = srsue_gpu_pcfich_decode(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, 0.0f, 1, b->d_bcfi, nullptr, st);
@@ -847,7 +870,7 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
       }
       B_CU(cudaMemcpyAsync(b->h_bcfi, b->d_bcfi, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       B_CU(cudaStreamSynchronize(st));
-      b->launches += 2 + 1 + 1 + 3 * (1 + n_tries);
+      b->launches += 1 + 1 + 1 + 3 * (1 + n_tries);
       // ---- 3. DCI -> grant on the host (ra.cc), descriptor by descriptor ---------------------------------------------
       for (int r = 0; r < m; r++) {
         srsue_gpu_sf_desc_t& d = descs[idx[off + r]];
