@@ -1104,7 +1104,7 @@ static int llr_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
     if (b.dbg_e) b.dbg_e += (size_t)done * p->info.G;
     b.n_sf = n;
     // 128 threads measured best on B200 (0.68 ms vs 0.85 ms per 4096 subframes with 512): finer occupancy granularity
-    static const int demod_threads = std::min(256, std::max(32, getenv("SRSUE_DEMOD_THREADS") ? atoi(getenv("SRSUE_DEMOD_THREADS")) : 160));
+    static const int demod_threads = std::min(160, std::max(32, getenv("SRSUE_DEMOD_THREADS") ? atoi(getenv("SRSUE_DEMOD_THREADS")) : 160));
     pdsch_llr_dematch_kernel<<<dim3(a.C, n), demod_threads, smem, (cudaStream_t)stream>>>(b);
     p->ctx->launch_count++;
   }
