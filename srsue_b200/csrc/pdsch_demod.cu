@@ -20,6 +20,9 @@
 #define SRSUE_DEMOD_MAX_THREADS 160
 #define SRSUE_DEMOD_MIN_CTAS 10
 #endif
+#ifndef SRSUE_DEMOD_U2
+#define SRSUE_DEMOD_U2 2
+#endif
 
 namespace srsue {
 
@@ -212,23 +215,28 @@ __global__ void __launch_bounds__(SRSUE_DEMOD_MAX_THREADS, SRSUE_DEMOD_MIN_CTAS)
     // every soft-buffer element takes at most one LLR: branch-free gather, 8 elements (16 bytes) per thread
     const uint4* gt4 = reinterpret_cast<const uint4*>(gt);
     uint4* w4 = reinterpret_cast<uint4*>(w);
-    for (int m8a = threadIdx.x; m8a < cb_elems / 8; m8a += 2 * blockDim.x) {
-     const bool two = m8a + (int)blockDim.x < cb_elems / 8;
-     const uint4 gia = __ldg(gt4 + m8a), gib = __ldg(gt4 + (two ? m8a + blockDim.x : m8a));
-     uint4 olda = make_uint4(0u, 0u, 0u, 0u), oldb = olda;
-     if (a.accumulate) { olda = w4[m8a]; oldb = w4[two ? m8a + blockDim.x : m8a]; }
+    constexpr int U2 = SRSUE_DEMOD_U2;                 // table vectors per thread and trip, all requested before the first use
+    const int n8 = cb_elems / 8;
+    for (int m8a = threadIdx.x; m8a < n8; m8a += U2 * blockDim.x) {
+     uint4 giv[U2], oldv[U2];
 #pragma unroll
-     for (int half = 0; half < 2; half++) {
-      if (half && !two) break;
-      const int m8 = half ? m8a + blockDim.x : m8a;
-      const uint4 gi = half ? gib : gia;
+     for (int u = 0; u < U2; u++) {
+       const int mm = m8a + u * blockDim.x;
+       giv[u] = __ldg(gt4 + (mm < n8 ? mm : m8a));
+       if (a.accumulate) oldv[u] = w4[mm < n8 ? mm : m8a];
+     }
+#pragma unroll
+     for (int half = 0; half < U2; half++) {
+      const int m8 = m8a + half * blockDim.x;
+      if (m8 >= n8) break;
+      const uint4 gi = giv[half];
       const uint32_t g[4] = {gi.x, gi.y, gi.z, gi.w};
       uint32_t o[4];
 #pragma unroll
       for (int q = 0; q < 4; q++)
         o[q] = (uint32_t)(uint16_t)s_e[g[q] & 0xFFFFu] | ((uint32_t)(uint16_t)s_e[g[q] >> 16] << 16);
       if (a.accumulate) {
-        const uint4 old = half ? oldb : olda;
+        const uint4 old = oldv[half];
         // |old| <= C: clamp_C(old + v) == clamp_C(old + clamp_2C(v)), and the packed 16-bit add of values
         // bounded by C and 2C cannot wrap
         o[0] = clamp_pair<kTdC>(__vadd2(old.x, clamp_pair<2 * kTdC>(o[0])));
