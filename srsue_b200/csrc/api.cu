@@ -276,8 +276,9 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
   }
   {
     // decisions: DEC2 order -> natural-order bytes (persistent CTAs, the table of this K in shared memory)
-    const int dsmem = ((g.K + 7) & ~7) * 2 + row_bytes * 8;
-    const int dgrid = std::min(n_cb, ctx->num_sms * 6);
+    const int dsmem = ((g.K + 7) & ~7) * 2 + row_bytes * 8 + ((row_bytes + 15) & ~15);
+    static const int deint_ctas = std::max(1, turbo_env_int("SRSUE_DEINT_CTAS_PER_SM", 8));
+    const int dgrid = std::min(n_cb, ctx->num_sms * deint_ctas);
     tdec_deinterleave_kernel<<<dgrid, 256, dsmem, st>>>(scr.bits, dbits_stride, tt->d_deint, d_cb_list, n_cb, d_bits, out_stride, g.K, row_bytes);
     CU_CHECK(cudaGetLastError());
     ctx->launch_count++;

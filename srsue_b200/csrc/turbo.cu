@@ -548,21 +548,39 @@ __global__ void __launch_bounds__(256) tdec_deinterleave_kernel(const uint8_t* _
   uint16_t* s_tab = reinterpret_cast<uint16_t*>(dsm);                        // K entries (K is a multiple of 8)
   uint2* s_bit = reinterpret_cast<uint2*>(s_tab + ((K + 7) & ~7));           // row_bytes x 8 bytes: one byte per bit
   const unsigned char* s_bitb = reinterpret_cast<const unsigned char*>(s_bit);
+  uint4* s_row = reinterpret_cast<uint4*>(s_bit + row_bytes);                // the row as it came (16-byte pieces)
   {
     const uint4* src = reinterpret_cast<const uint4*>(deint);
     uint4* dst = reinterpret_cast<uint4*>(s_tab);
     for (int e = threadIdx.x; e < K / 8; e += blockDim.x) dst[e] = __ldg(src + e);
   }
+  // The row of the NEXT code block travels while this one is processed (rows are 16-byte aligned, a thread carries at most
+  // one 16-byte piece: row_bytes <= 16 * blockDim.x): without it every block started with an exposed L2 / HBM round trip.
+  const int row16 = (row_bytes + 15) / 16;
+  uint4 piece = make_uint4(0u, 0u, 0u, 0u);
+  long long cbi_next = 0;
+  if ((int)blockIdx.x < n_cb) {
+    if ((int)threadIdx.x < row16) piece = reinterpret_cast<const uint4*>(dbits + (size_t)blockIdx.x * dbits_stride)[threadIdx.x];
+    cbi_next = cb_list ? cb_list[blockIdx.x] : (long long)blockIdx.x;
+  }
   for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
     __syncthreads();                                                         // table loaded / previous row consumed
-    const uint8_t* row = dbits + (size_t)cb * dbits_stride;
+    if ((int)threadIdx.x < row16) s_row[threadIdx.x] = piece;
+    __syncthreads();
     for (int e = threadIdx.x; e < row_bytes; e += blockDim.x) {
-      const uint32_t b = row[e];
+      const uint32_t b = reinterpret_cast<const unsigned char*>(s_row)[e];
       // nibble * 0x00204081 puts bit q of the nibble at bit 8 q
       s_bit[e] = make_uint2(((b & 15u) * 0x00204081u) & 0x01010101u, ((b >> 4) * 0x00204081u) & 0x01010101u);
     }
+    const long long cbi = cbi_next;
+    {
+      const int nx = cb + gridDim.x;
+      if (nx < n_cb) {
+        if ((int)threadIdx.x < row16) piece = reinterpret_cast<const uint4*>(dbits + (size_t)nx * dbits_stride)[threadIdx.x];
+        cbi_next = cb_list ? cb_list[nx] : (long long)nx;
+      }
+    }
     __syncthreads();
-    const long long cbi = cb_list ? cb_list[cb] : cb;
     uint8_t* o = out + cbi * (long long)out_stride;
     for (int e = threadIdx.x; e < K / 8; e += blockDim.x) {
       const uint4 q = reinterpret_cast<const uint4*>(s_tab)[e];
