@@ -135,7 +135,7 @@ int get_turbo_tables(srsue_gpu_ctx* ctx, int K, const TurboTables** out) {
   return 0;
 }
 
-struct TurboLaunchCfg { int ncb, threads, grid, smem, ngroups, group_threads, group_slots; };
+struct TurboLaunchCfg { int ncb, threads, grid, smem, ngroups, group_threads, group_slots, bwd_two; };
 
 // words between the exchange arrays of consecutive slots: plane/2 plus the skew that lets a warp straddling
 // two slots keep hitting distinct shared-memory banks ((plane/2 + skew) mod 32 == T mod 32)
@@ -173,11 +173,11 @@ int turbo_threads(const TurboGeom& g, int ncb) {
 }
 
 // Shared memory of one decoder CTA with ncb slots: position table, flags, per slot the exchange array, per thread six
-// 16-byte staging chunks and a scratch word
-int turbo_smem_bytes(const TurboGeom& g, int ncb) {
+// (eight with two groups in flight in the backward sweep) 16-byte staging chunks and a scratch word
+int turbo_smem_bytes(const TurboGeom& g, int ncb, int chunks = 6) {
   const int threads = turbo_threads(g, ncb);
   const int slot_bytes = turbo_slot_words(g) * 4;
-  return g.W * turbo_perm_stride(g) * 4 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes + 16 + threads * 100;
+  return g.W * turbo_perm_stride(g) * 4 + 2 * ((ncb + 3) & ~3) * 4 + 16 + ncb * slot_bytes + 16 + threads * (16 * chunks + 4);
 }
 
 TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, int n_cb, bool crc) {
@@ -203,7 +203,12 @@ TurboLaunchCfg turbo_launch_cfg(const srsue_gpu_ctx* ctx, const TurboGeom& g, in
   turbo_groups(g, ncb, &c.ngroups, &c.group_threads, &c.group_slots);
   c.threads = c.ngroups * c.group_threads;
   c.grid = std::min((n_cb + ncb - 1) / ncb, ctx->num_sms * per_sm);
-  c.smem = turbo_smem_bytes(g, ncb);
+  // the K = 5824 kernels keep two groups of channel LLRs in flight in the backward sweep (eight staging chunks per thread,
+  // which fit next to its 14 slots; K = 6144 and the small sizes would lose a slot to them, which costs more than it gains)
+  static const bool generic_only = turbo_env_int("SRSUE_TURBO_GENERIC", 0) != 0;      // tuning: skip the T-specific kernels
+  const int budget = std::min((ctx->smem_sm - per_sm * 1024) / per_sm, ctx->smem_optin);
+  c.bwd_two = (!generic_only && g.T == 26 && turbo_perm_stride(g) == 32 && turbo_smem_bytes(g, ncb, 8) <= budget) ? 1 : 0;
+  c.smem = turbo_smem_bytes(g, ncb, c.bwd_two ? 8 : 6);
   return c;
 }
 
@@ -265,8 +270,8 @@ int launch_turbo(srsue_gpu_ctx* ctx, Scratch& scr, const int16_t* d_in, long lon
     a.phase_delay = lc.ngroups > 1 ? (env_delay >= 0 ? env_delay : 350 * g.W) : 0;
     if ((long long)n_cb < 2LL * lc.grid * lc.ncb) a.phase_delay = 0;      // short launches: latency matters more than overlap
   }
-  static const bool generic_only = turbo_env_int("SRSUE_TURBO_GENERIC", 0) != 0;      // tuning: skip the T-specific kernels
-  const int variant = turbo_perm_stride(g) == 64 ? 1 : generic_only ? 0 : g.T == 26 ? 2 : g.T == 24 ? 3 : 0;
+  static const bool generic_only = turbo_env_int("SRSUE_TURBO_GENERIC", 0) != 0;
+  const int variant = turbo_perm_stride(g) == 64 ? 1 : generic_only ? 0 : (g.T == 26 && lc.bwd_two) ? 2 : g.T == 24 ? 3 : 0;
   kernels[variant][crc_type ? 1 : 0]<<<lc.grid, lc.threads, lc.smem, st>>>(a);
   {
     const cudaError_t e = cudaGetLastError();

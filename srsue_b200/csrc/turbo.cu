@@ -143,6 +143,7 @@ __device__ __forceinline__ const uint4* at16(const uint4* base, uint32_t idx) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void lds8(uint32_t saddr, uint32_t stride, uint32_t (&v)[8]) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr) : "memory");
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(saddr + stride) : "memory");
@@ -172,7 +173,7 @@ struct SlotCtx {
   uint16_t* bits;         // global: hard decisions of the block in DEC2 order, [W/8][T] x (byte of window 2t | byte of window 2t+1 << 8)
   uint32_t pin;           // shared-window address of this thread's scratch word (pin_store / pin_load)
   uint32_t stage;         // shared-window address of this thread's staging chunks: chunk k (16 bytes) at stage + k * 16 * blockDim.x
-                          // (y: 0,1  sys: 2,3  checkpoint: 4,5)
+                          // (forward sweep: y 0,1  sys 2,3  checkpoint 4,5; backward sweep: two sets 0..3 / 4..7)
   uint32_t gslot;         // global slot number: selects the NII / checkpoint scratch
 };
 
@@ -195,7 +196,7 @@ __device__ __forceinline__ void nii_pack(const uint32_t (&m)[8], uint4& lo, uint
 
 // One max-log-MAP pass of constituent decoder DEC (0 or 1) for the two windows of this thread.  Returns the
 // thread's CRC contribution of the hard decisions (DEC2 with CRC), else 0.  perm_t = position table + t.
-template <int DEC, bool CRC, int TS, int TT>
+template <int DEC, bool CRC, int TS, int TT, bool TWO>
 __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& c, const uint16_t* perm_t, int t, int it) {
   const int T = TT ? TT : g.T, W = g.W, P = g.P, NP = g.Ppad + 2, nsw = W / kSW, plane = g.plane;
   const int j0 = 2 * t, j1 = 2 * t + 1;
@@ -243,7 +244,21 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   const int nl = (T + 3) / 4;                      // 128-byte lines per run
   const uint4* pf_base = (t < nl) ? (yq - t) + 8 * t : (sysq - t) + 8 * (t - nl);
   const bool pf_on = t < (DEC == 0 ? 2 * nl : nl) && (t < nl ? 8 * t : 8 * (t - nl)) < 2 * T;
-  fetch(nsw - 1, false);
+  // Backward sweep: TWO groups in flight (its trip is a third as long as the forward sweep's, one group of distance did not
+  // cover an L2 miss).  Two sets of chunks alternate: {0..3} and {4..7} (y at +0, +1; systematic at +2, +3).
+  auto fetch_bwd = [&](int sw, uint32_t base) {
+    const uint32_t gi = (uint32_t)(sw * gstride);
+    cp_async16(base, at16(yq, gi));
+    cp_async16(base + cstr, at16(yq, gi + T));
+    if (DEC == 0) {
+      cp_async16(base + 2 * cstr, at16(sysq, gi));
+      cp_async16(base + 3 * cstr, at16(sysq, gi + T));
+    }
+    cp_async_commit();
+  };
+  constexpr bool two = TWO;                         // (one group in flight where the eight chunks would cost a code-block slot)
+  fetch_bwd(nsw - 1, stg);
+  if (two) fetch_bwd(nsw - 2, stg + 4 * cstr);
 
   // ---- boundary metrics: all four records are requested at once
   uint32_t b[8], a[8];
@@ -288,16 +303,19 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
   // ---- pass 1: backward sweep, checkpoint beta every kSW steps -----------------------------------
 #pragma unroll 1
   for (int sw = nsw - 1; sw >= 0; sw--) {
-    cp_async_wait_all();
-    lds8(stg, cstr, Cy);
-    if (DEC == 0) lds8(stg + 2 * cstr, cstr, Cs);
+    const uint32_t cur = stg + ((two && ((nsw - 1 - sw) & 1)) ? 4 * cstr : 0u);
+    if (two && sw) cp_async_wait_but_one(); else cp_async_wait_all();
+    lds8(cur, cstr, Cy);
+    if (DEC == 0) lds8(cur + 2 * cstr, cstr, Cs);
     pin_store(pin, Cy[kSW - 1]);
     {                                               // checkpoint: thread-private scratch, read back in pass 2
       const uint32_t ci = (uint32_t)(sw * cstride);
       *const_cast<uint4*>(at16(ckpt4, ci)) = make_uint4(b[0], b[1], b[2], b[3]);
       *const_cast<uint4*>(at16(ckpt4, ci + chalf)) = make_uint4(b[4], b[5], b[6], b[7]);
     }
-    fetch(sw > 0 ? sw - 1 : 0, sw == 0);            // after group 0: its data and checkpoint again, for the forward sweep
+    if (sw == 0) fetch(0, true);                    // after group 0: its data and checkpoint again, for the forward sweep
+    else if (!two) fetch_bwd(sw - 1, stg);
+    else if (sw >= 2) fetch_bwd(sw - 2, cur);       // into the set just read
     // The resident code blocks of all SMs together exceed what the L2 keeps (hit rate 80 %): ask for the lines of the
     // group three ahead now, so that its copy finds them in L2 instead of waiting for DRAM with nothing to overlap.
     if (sw >= kL2Ahead && pf_on) asm volatile("prefetch.global.L2 [%0];" ::"l"(at16(pf_base, (uint32_t)((sw - kL2Ahead) * gstride))));
@@ -420,7 +438,7 @@ __device__ __forceinline__ uint32_t map_pass(const TurboArgs& g, const SlotCtx& 
 
 // TT: threads per code block as a compile-time constant (0: run time).  With T known, every stride of the exchange array,
 // the channel-LLR planes and the checkpoints is an immediate of the load / store that uses it.
-template <bool CRC, int TS, int TT>
+template <bool CRC, int TS, int TT, bool TWO>
 __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int T = TT ? TT : g.T, W = g.W;
@@ -443,7 +461,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   int* s_next = reinterpret_cast<int*>(s_crc + nflag);       // per slot: next work item; [nflag]: slots with work
   uint32_t* s_slots = s_crc + 2 * nflag + 4;                 // per slot: A, plane/2 words (+ skew)
   int* s_active = s_next + nflag + grp;                      // per phase group: slots with work
-  // staging chunks of all threads, 16-byte aligned: [6][blockDim.x] uint4, then [blockDim.x] scratch words
+  // staging chunks of all threads, 16-byte aligned: [8][blockDim.x] uint4, then [blockDim.x] scratch words
   uint4* s_stage = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_slots + (size_t)g.ncb_cta * g.slot_words) + 15) & ~(uintptr_t)15);
 
   {
@@ -461,7 +479,7 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
   c.Aw = s_slots + (size_t)(valid ? slot : 0) * g.slot_words;
   c.bits = nullptr;
   c.stage = (uint32_t)__cvta_generic_to_shared(s_stage + tid);
-  c.pin = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(s_stage + 6 * blockDim.x) + tid);
+  c.pin = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(s_stage + (TWO ? 8 : 6) * blockDim.x) + tid);
   c.gslot = blockIdx.x * g.ncb_cta + (valid ? slot : 0);
   c.in4 = nullptr;
   const uint16_t* perm_t = reinterpret_cast<const uint16_t*>(s_permw) + t;
@@ -491,10 +509,10 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
   while (*reinterpret_cast<volatile int*>(s_active) > 0) {
     if (valid && t == 0) s_crc[slot] = 0;
-    if (have) map_pass<0, CRC, TS, TT>(g, c, perm_t, t, it);
+    if (have) map_pass<0, CRC, TS, TT, TWO>(g, c, perm_t, t, it);
     group_sync();
     if (have) {
-      const uint32_t part = map_pass<1, CRC, TS, TT>(g, c, perm_t, t, it);
+      const uint32_t part = map_pass<1, CRC, TS, TT, TWO>(g, c, perm_t, t, it);
       if (crc_on) atomicXor(&s_crc[slot], part);
     }
     group_sync();
@@ -524,15 +542,16 @@ __device__ __forceinline__ void turbo_decode_body(const TurboArgs& g) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 0>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 0>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64, 0>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64, 0>(g); }
-// the two largest code-block sizes carry most of the bits of a wide-band transport block: K = 5824 (T = 26), K = 6144 (T = 24)
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t26_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 26>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t26_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 26>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t24_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 24>(g); }
-__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t24_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 24>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 0, false>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 0, false>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_wide_kernel(const TurboArgs g) { turbo_decode_body<false, 64, 0, false>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_wide_kernel(const TurboArgs g) { turbo_decode_body<true, 64, 0, false>(g); }
+// the two largest code-block sizes carry most of the bits of a wide-band transport block: K = 5824 (T = 26; its 14 slots leave
+// room for the eight staging chunks of a backward sweep with two groups in flight), K = 6144 (T = 24)
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t26_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 26, true>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t26_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 26, true>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_t24_kernel(const TurboArgs g) { turbo_decode_body<false, 32, 24, false>(g); }
+__global__ void __launch_bounds__(kTurboMaxThreads, 1) turbo_decode_crc_t24_kernel(const TurboArgs g) { turbo_decode_body<true, 32, 24, false>(g); }
 
 // ---- hard decisions: DEC2 order -> natural order ------------------------------------------------------
 // The decoder leaves the decisions of a code block as it produced them: one bit per trellis step of the second
