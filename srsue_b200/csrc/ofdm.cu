@@ -16,6 +16,10 @@
 
 #include "kernels.h"
 
+#ifndef SRSUE_FFT16_MIN_CTAS
+#define SRSUE_FFT16_MIN_CTAS 9     // 56 registers: 0.270 ms per 4096 subframes; 8 CTAs (64 registers) 0.276, 10 (48) 0.282
+#endif
+
 namespace srsue {
 
 namespace {
@@ -451,7 +455,7 @@ __device__ __forceinline__ void fft2048_r16(const float2* __restrict__ gin, floa
 
 }  // namespace
 
-__global__ void __launch_bounds__(128, 8) ofdm_rx_r16_kernel(const OfdmArgs a) {
+__global__ void __launch_bounds__(128, SRSUE_FFT16_MIN_CTAS) ofdm_rx_r16_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   constexpr int N = 2048;
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(128, 8) ofdm_rx_r16_kernel(const OfdmArgs a) {
   const int start = slot * (7 * N + 160 + 6 * 144) + ls * N + 160 + ls * 144;
   fft2048_r16<false>(a.iq + (size_t)sf * 15 * N + start, a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc, s_fft, a.tw, a.nsc, a.scale, 0.f);
 }
-__global__ void __launch_bounds__(128, 8) ofdm_rx_r16_iq16_kernel(const OfdmArgs a) {
+__global__ void __launch_bounds__(128, SRSUE_FFT16_MIN_CTAS) ofdm_rx_r16_iq16_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   constexpr int N = 2048;
