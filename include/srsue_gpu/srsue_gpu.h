@@ -38,7 +38,10 @@ typedef struct { float re, im; } srsue_gpu_cf_t;        /* layout of srsLTE's cf
 typedef struct {
   int nof_prb;      /* 6, 15, 25, 50, 75, 100 */
   int nof_ports;    /* 1 or 2 */
-  int cell_id;      /* physical cell id, normal cyclic prefix */
+  int cell_id;      /* physical cell id */
+  int cp;           /* cyclic prefix: 0 = normal (srsLTE's SRSLTE_CP_NORM), 1 = extended (SRSLTE_CP_EXT): 12 symbols per
+                     * subframe, CRS in symbols 0 and 3 of each slot.  Device grids (sf_symbols, ce) keep a stride of 14
+                     * symbols per subframe and port either way; with the extended prefix rows 12 and 13 are unused. */
 } srsue_gpu_cell_t;
 
 typedef struct {

@@ -43,8 +43,13 @@ typedef struct { double re, im; } lteo_cd_t;
 typedef struct {
   int nof_prb;      /* 6,15,25,50,75,100 */
   int nof_ports;    /* 1 or 2 */
-  int cell_id;      /* 0..503, normal CP */
+  int cell_id;      /* 0..503 */
+  int cp;           /* 0 = normal cyclic prefix (7 symbols per slot), 1 = extended (6 symbols per slot, SPEC.md 15) */
 } lteo_cell_t;
+/* Grids (sf_symbols, ce, TX grids) always have a stride of 14 symbols per port; with the extended cyclic prefix only
+ * rows 0..11 are used. */
+#define LTEO_NSYMB(cp) ((cp) ? 12 : 14)
+#define LTEO_NSLOT(cp) ((cp) ? 6 : 7)
 
 typedef struct {
   int sf_idx;       /* 0..9 */
@@ -68,6 +73,7 @@ void     lteo_qpp_perm(int K, uint16_t *pi);                 /* pi[i] = (f1 i + 
 int      lteo_window_len(int K);                             /* W(K), SPEC.md 7.3               */
 int      lteo_symbol_sz(int nof_prb);
 int      lteo_cp_len(int nfft, int symbol_in_slot);
+int      lteo_cp_len_x(int nfft, int symbol_in_slot, int cp);   /* cp = 1: 512 samples at 2048 for every symbol */
 uint32_t lteo_crc_bits(const uint8_t *bits, int n, uint32_t poly, int order);
 void     lteo_gold(uint32_t c_init, int n, uint8_t *c);
 int      lteo_cbsegm(int tbs, lteo_cbsegm_t *s);
@@ -92,12 +98,14 @@ int  lteo_ulsch_encode(int tbs, int qm, int nof_prb, int n_symb, int rv, int rnt
 int  lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg,
                         const uint8_t *tb_bytes, lteo_cd_t *grid /* [ports][14][12*nof_prb] */);
 void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq /* 15*nfft samples */);
+void lteo_ofdm_tx_cp(int nof_prb, int cp, const lteo_cd_t *grid, lteo_cd_t *iq);
 /* adds the PCFICH of `cfi` (1..3) to a grid built by lteo_pdsch_tx_grid (symbol 0; TX diversity with 2 ports) */
 void lteo_pcfich_tx(const lteo_cell_t *cell, int sf_idx, int cfi, lteo_cd_t *grid);
 
 /* ---- RX side (the restated hot path) ---------------------------------------------------- */
 void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n);
 void lteo_ofdm_rx(int nof_prb, const lteo_cf_t *iq, lteo_cf_t *sf_symbols);
+void lteo_ofdm_rx_cp(int nof_prb, int cp, const lteo_cf_t *iq, lteo_cf_t *sf_symbols);
 /* meas[5] = noise, rsrp, rssi, rsrq, snr */
 void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf_symbols,
                 lteo_cf_t *ce /* [ports][14*nsc] */, float *meas);

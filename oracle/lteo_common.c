@@ -241,6 +241,8 @@ int lteo_symbol_sz(int nof_prb) {
 }
 
 int lteo_cp_len(int nfft, int l) { return ((l % 7) == 0 ? 160 : 144) * nfft / 2048; }
+/* 36.211 6.12: extended cyclic prefix = 512 samples at 30.72 Msps for each of the 6 symbols of a slot */
+int lteo_cp_len_x(int nfft, int l, int cp) { return cp ? 512 * nfft / 2048 : lteo_cp_len(nfft, l); }
 
 /* bitwise CRC, zero initial state, no final xor (36.212 5.1.1) */
 uint32_t lteo_crc_bits(const uint8_t *bits, int n, uint32_t poly, int order) {
@@ -309,11 +311,12 @@ int lteo_cb_E(const lteo_cbsegm_t *s, int G, int qm, int nl, int r) {
   return nl * qm * ((Gp + s->C - 1) / s->C);
 }
 
-/* CRS positions of antenna port `port` in OFDM symbol l (0..13): 2*nof_prb subcarrier indices,
- * or 0 if the symbol carries no CRS for this port (ports 0/1, normal CP; 36.211 6.10.1.2) */
+/* CRS positions of antenna port `port` in OFDM symbol l (0..13, or 0..11 with the extended cyclic prefix): 2*nof_prb
+ * subcarrier indices, or 0 if the symbol carries no CRS for this port (ports 0/1: symbols 0 and N_symb - 3 of each slot;
+ * 36.211 6.10.1.2) */
 int lteo_crs_positions(const lteo_cell_t *cell, int port, int l, int32_t *k_out) {
-  int ls = l % 7;
-  if (ls != 0 && ls != 4) return 0;
+  int nslot = LTEO_NSLOT(cell->cp), ls = l % nslot;
+  if (ls != 0 && ls != nslot - 3) return 0;
   int v = (port == 0) ? (ls == 0 ? 0 : 3) : (ls == 0 ? 3 : 0);
   int off = (v + cell->cell_id % 6) % 6;
   for (int m = 0; m < 2 * cell->nof_prb; m++) k_out[m] = 6 * m + off;
@@ -346,8 +349,9 @@ void lteo_pcfich_bits(const lteo_cell_t *cell, int sf_idx, int cfi, uint8_t *b32
 /* CRS symbol values for symbol l of subframe sf_idx: r(m') = (re_sign + j im_sign)/sqrt(2),
  * m' = m + 110 - nof_prb, m = 0..2*nof_prb-1 (same sequence for both ports) */
 void lteo_crs_values(const lteo_cell_t *cell, int sf_idx, int l, int8_t *re_sign, int8_t *im_sign) {
-  int ns = 2 * sf_idx + l / 7, ls = l % 7;
-  uint32_t c_init = 1024u * (7 * (ns + 1) + ls + 1) * (2 * cell->cell_id + 1) + 2 * cell->cell_id + 1;
+  int nslot = LTEO_NSLOT(cell->cp), ns = 2 * sf_idx + l / nslot, ls = l % nslot;
+  /* 36.211 6.10.1.1: c_init = 2^10 (7 (n_s + 1) + l + 1)(2 N_ID + 1) + 2 N_ID + N_CP, N_CP = 1 normal / 0 extended */
+  uint32_t c_init = 1024u * (7 * (ns + 1) + ls + 1) * (2 * cell->cell_id + 1) + 2 * cell->cell_id + (cell->cp ? 0 : 1);
   uint8_t c[440];
   lteo_gold(c_init, 440, c);
   for (int m = 0; m < 2 * cell->nof_prb; m++) {
@@ -364,8 +368,9 @@ int lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int
   int nsc = 12 * cell->nof_prb, n = 0;
   int lstart = cfg->cfi + (cell->nof_prb <= 10 ? 1 : 0);
   int c_lo = nsc / 2 - 36, c_hi = nsc / 2 + 36;       /* central 72 subcarriers */
-  for (int l = lstart; l < 14; l++) {
-    int ls = l % 7, crs = (ls == 0 || ls == 4);
+  const int nslot = LTEO_NSLOT(cell->cp);
+  for (int l = lstart; l < 2 * nslot; l++) {
+    int ls = l % nslot, crs = (ls == 0 || ls == nslot - 3);
     int o0 = -1, o1 = -1;
     if (crs) {
       int v0 = (ls == 0) ? 0 : 3;
@@ -373,11 +378,11 @@ int lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int
       if (cell->nof_ports > 1) o1 = (o0 + 3) % 6;
     }
     int sync = 0;
-    if ((cfg->sf_idx == 0 || cfg->sf_idx == 5) && (l == 5 || l == 6)) sync = 1;   /* SSS, PSS */
-    if (cfg->sf_idx == 0 && l >= 7 && l <= 10) sync = 1;                           /* PBCH    */
+    if ((cfg->sf_idx == 0 || cfg->sf_idx == 5) && (l == nslot - 2 || l == nslot - 1)) sync = 1;   /* SSS, PSS */
+    if (cfg->sf_idx == 0 && l >= nslot && l <= nslot + 3) sync = 1;                                /* PBCH    */
     for (int prb = 0; prb < cell->nof_prb; prb++) {
       uint8_t pm = cfg->prb_mask[prb];                 /* bit 0: both slots, bit 1: slot 0 only, bit 2: slot 1 only */
-      if (!((pm & 1) || (pm & (l >= 7 ? 4 : 2)))) continue;
+      if (!((pm & 1) || (pm & (l >= nslot ? 4 : 2)))) continue;
       for (int k = 12 * prb; k < 12 * prb + 12; k++) {
         if (crs && (k % 6 == o0 || k % 6 == o1)) continue;
         /* with a single configured port only port-0 CRS REs are reserved */

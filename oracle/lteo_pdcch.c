@@ -15,14 +15,17 @@
 /* number of OFDM symbols of the control region */
 int lteo_ctrl_symbols(int nof_prb, int cfi) { return cfi + (nof_prb <= 10 ? 1 : 0); }
 
-/* number of PHICH groups, normal CP: ceil(Ng * N_RB / 8) with Ng = ng_x6 / 6 (1/6, 1/2, 1, 2) */
+/* number of PHICH groups, normal CP: ceil(Ng * N_RB / 8) with Ng = ng_x6 / 6 (1/6, 1/2, 1, 2).  With the extended cyclic
+ * prefix there are twice as many groups but two share one mapping unit of three REGs (36.211 6.9.3), so this is also the
+ * number of PHICH mapping units the control region reserves there. */
 int lteo_phich_groups(int nof_prb, int ng_x6) { return (ng_x6 * nof_prb + 47) / 48; }
 
 /*
  * Resource-element groups of the control region that carry PDCCH, in the mapping order of 36.211 6.8.5
  * (subcarrier k' ascending, then symbol l'): reg_k/reg_l = first subcarrier and symbol of each.  Symbol 0 holds
  * 2 REGs of 6 REs per PRB (4 data REs, the CRS positions of ports 0/1 skipped), the other control symbols 3 REGs
- * of 4 REs per PRB (1 or 2 antenna ports).  The 4 PCFICH REGs and the 3 REGs of every PHICH group (normal PHICH
+ * of 4 REs per PRB (1 or 2 antenna ports) -- except symbol 3 under the extended cyclic prefix (a four-symbol control
+ * region at <= 10 PRB), which carries CRS and is laid out like symbol 0.  The 4 PCFICH REGs and the 3 REGs of every PHICH group (normal PHICH
  * duration: all in symbol 0, 36.211 6.9.3) are excluded.  Returns the number of REGs.
  */
 int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k, int32_t *reg_l) {
@@ -44,6 +47,7 @@ int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k,
   for (int k = 0; k < nsc; k += 2) {         /* REG starts are multiples of 6 (symbol 0) or 4 (others) */
     for (int l = 0; l < nsym; l++) {
       if (l == 0) { if (k % 6 == 0 && !used[k / 6]) { reg_k[n] = k; reg_l[n] = 0; n++; } }
+      else if (cell->cp && l == 3) { if (k % 6 == 0) { reg_k[n] = k; reg_l[n] = l; n++; } }
       else if (k % 4 == 0) { reg_k[n] = k; reg_l[n] = l; n++; }
     }
   }
@@ -53,7 +57,7 @@ int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k,
 
 /* the 4 data subcarriers of a REG */
 void lteo_reg_res(const lteo_cell_t *cell, int k0, int l, int32_t *k4) {
-  if (l == 0) { for (int j = 0, n = 0; j < 6; j++) if ((k0 + j) % 3 != cell->cell_id % 3) k4[n++] = k0 + j; }
+  if (l == 0 || (cell->cp && l == 3)) { for (int j = 0, n = 0; j < 6; j++) if ((k0 + j) % 3 != cell->cell_id % 3) k4[n++] = k0 + j; }
   else for (int j = 0; j < 4; j++) k4[j] = k0 + j;
 }
 

@@ -135,12 +135,15 @@ void lteo_fft(const lteo_cf_t *in, lteo_cf_t *out, int n) {
   free(f);
 }
 
-void lteo_ofdm_rx(int nof_prb, const lteo_cf_t *iq, lteo_cf_t *sf_symbols) {
+void lteo_ofdm_rx(int nof_prb, const lteo_cf_t *iq, lteo_cf_t *sf_symbols) { lteo_ofdm_rx_cp(nof_prb, 0, iq, sf_symbols); }
+
+/* cp = 1: 12 symbols behind 512-sample (at 2048) prefixes; rows 12 and 13 of the grid are left untouched */
+void lteo_ofdm_rx_cp(int nof_prb, int cp, const lteo_cf_t *iq, lteo_cf_t *sf_symbols) {
   int n = lteo_symbol_sz(nof_prb), nsc = 12 * nof_prb, pos = 0;
   lteo_cf_t *x = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * n);
   const float sc = (float)(1.0 / sqrt((double)n));
-  for (int l = 0; l < 14; l++) {
-    pos += lteo_cp_len(n, l);
+  for (int l = 0; l < LTEO_NSYMB(cp); l++) {
+    pos += lteo_cp_len_x(n, l, cp);
     lteo_fft(iq + pos, x, n);
     pos += n;
     for (int k = 0; k < nsc; k++) {
@@ -167,11 +170,12 @@ static float lane_reduce(const float *v, int n) {
   return p[0];
 }
 
-static const int crs_syms[4] = {0, 4, 7, 11};
+static const int crs_syms_cp[2][4] = {{0, 4, 7, 11}, {0, 3, 6, 9}};
 
 void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf, lteo_cf_t *ce, float *meas) {
   const int nsc = 12 * cell->nof_prb, M = 2 * cell->nof_prb, np = cell->nof_ports;
   const float isq2 = (float)(1.0 / sqrt(2.0)), w = 0.1f, c = 0.8f;
+  const int *crs_syms = crs_syms_cp[cell->cp ? 1 : 0], nslot = LTEO_NSLOT(cell->cp);
   float ftab[17];                                   /* ftab[t + 5] = (float)(t / 6), t = -5..11 */
   for (int t = -5; t <= 11; t++) ftab[t + 5] = (float)((double)t / 6.0);
   lteo_cf_t *ls = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * M);
@@ -213,9 +217,10 @@ void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf, lteo_c
         hs[si * nsc + k].im = a.im + (b.im - a.im) * f;
       }
     }
-    /* time interpolation between CRS symbols 0,4,7,11; symbols 12,13 extrapolate from (7,11) */
-    for (int l = 0; l < 14; l++) {
-      int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+    /* time interpolation between CRS symbols 0,4,7,11; symbols 12,13 extrapolate from (7,11)
+     * (extended cyclic prefix: 0,3,6,9; symbols 10,11 extrapolate from (6,9)) */
+    for (int l = 0; l < 2 * nslot; l++) {
+      int s0 = (l < crs_syms[1]) ? 0 : (l < nslot) ? 1 : 2;
       int l0 = crs_syms[s0], l1 = crs_syms[s0 + 1];
       float f = (float)((double)(l - l0) / (double)(l1 - l0));
       for (int k = 0; k < nsc; k++) {
@@ -665,7 +670,7 @@ int lteo_ue_dl_decode(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, cons
   lteo_cf_t *ce = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * 14 * nsc * cell->nof_ports);
   float mm[5];
   int iters[32];
-  lteo_ofdm_rx(cell->nof_prb, iq, sf);
+  lteo_ofdm_rx_cp(cell->nof_prb, cell->cp, iq, sf);
   lteo_chest(cell, cfg->sf_idx, sf, ce, mm);
   if (meas) memcpy(meas, mm, sizeof(mm));
   int rc = lteo_pdsch_decode(cell, cfg, sf, ce, noise_mode ? mm[0] : noise_est, max_iter, softbuf, payload, 0, 0,

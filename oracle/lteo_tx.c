@@ -207,7 +207,7 @@ int lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, con
   int32_t kk[220];
   double a = 1.0 / sqrt(2.0);
   for (int p = 0; p < np; p++)
-    for (int l = 0; l < 14; l++) {
+    for (int l = 0; l < LTEO_NSYMB(cell->cp); l++) {
       int n = lteo_crs_positions(cell, p, l, kk);
       if (!n) continue;
       lteo_crs_values(cell, cfg->sf_idx, l, rs, is);
@@ -304,21 +304,23 @@ static void fft_d(lteo_cd_t *x, int n, int inverse, const lteo_cd_t *tab, int nt
   free(t);
 }
 
-/* OFDM modulation of one port's grid: unitary IFFT (scale 1/sqrt(N)), normal CP */
-void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq) {
+/* OFDM modulation of one port's grid: unitary IFFT (scale 1/sqrt(N)) */
+void lteo_ofdm_tx(int nof_prb, const lteo_cd_t *grid, lteo_cd_t *iq) { lteo_ofdm_tx_cp(nof_prb, 0, grid, iq); }
+
+void lteo_ofdm_tx_cp(int nof_prb, int cpx, const lteo_cd_t *grid, lteo_cd_t *iq) {
   int n = lteo_symbol_sz(nof_prb), nsc = 12 * nof_prb, pos = 0;
   lteo_cd_t *x = (lteo_cd_t *)malloc(sizeof(lteo_cd_t) * n);
   lteo_cd_t *tab = (lteo_cd_t *)malloc(sizeof(lteo_cd_t) * n);
   for (int i = 0; i < n; i++) { tab[i].re = cos(-2.0 * M_PI * i / n); tab[i].im = sin(-2.0 * M_PI * i / n); }
   double sc = 1.0 / sqrt((double)n);
-  for (int l = 0; l < 14; l++) {
+  for (int l = 0; l < LTEO_NSYMB(cpx); l++) {
     memset(x, 0, sizeof(lteo_cd_t) * n);
     for (int k = 0; k < nsc; k++) {
       int bin = (k < nsc / 2) ? (n - nsc / 2 + k) : (k - nsc / 2 + 1);
       x[bin] = grid[l * nsc + k];
     }
     fft_d(x, n, 1, tab, n);
-    int cp = lteo_cp_len(n, l);
+    int cp = lteo_cp_len_x(n, l, cpx);
     for (int i = 0; i < cp; i++) { iq[pos].re = x[n - cp + i].re * sc; iq[pos].im = x[n - cp + i].im * sc; pos++; }
     for (int i = 0; i < n; i++) { iq[pos].re = x[i].re * sc; iq[pos].im = x[i].im * sc; pos++; }
   }

@@ -29,7 +29,8 @@ def build(force=False):
 
 
 class Cell(C.Structure):
-    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int)]
+    # cp: 0 = normal cyclic prefix, 1 = extended (12 symbols per subframe; grids keep their 14-row stride)
+    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int), ("cp", C.c_int)]
 
 
 class PdschCfg(C.Structure):
@@ -83,8 +84,8 @@ def _p(a, t=C.c_void_p):
     return a.ctypes.data_as(t)
 
 
-def make_cell(nof_prb, nof_ports=1, cell_id=1):
-    return Cell(nof_prb, nof_ports, cell_id)
+def make_cell(nof_prb, nof_ports=1, cell_id=1, cp=0):
+    return Cell(nof_prb, nof_ports, cell_id, cp)
 
 
 def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None, prbs_slot1=None):
@@ -196,11 +197,11 @@ def pdsch_tx_grid(cell, cfg, tb_bytes):
     return grid
 
 
-def ofdm_tx(nof_prb, grid):
+def ofdm_tx(nof_prb, grid, cp=0):
     n = lib().lteo_symbol_sz(nof_prb)
     grid = np.ascontiguousarray(grid, np.complex128)
     iq = np.zeros(15 * n, np.complex128)
-    lib().lteo_ofdm_tx(nof_prb, _p(grid), _p(iq))
+    lib().lteo_ofdm_tx_cp(nof_prb, cp, _p(grid), _p(iq))
     return iq
 
 
@@ -212,10 +213,10 @@ def fft(x):
     return out
 
 
-def ofdm_rx(nof_prb, iq):
+def ofdm_rx(nof_prb, iq, cp=0):
     iq = np.ascontiguousarray(iq, np.complex64)
     sf = np.zeros(14 * 12 * nof_prb, np.complex64)
-    lib().lteo_ofdm_rx(nof_prb, _p(iq), _p(sf))
+    lib().lteo_ofdm_rx_cp(nof_prb, cp, _p(iq), _p(sf))
     return sf
 
 
@@ -517,7 +518,7 @@ def gen_subframe(cell, cfg, seed, snr_db=30.0, taps=None, pcfich=False, dcis=Non
             t = np.asarray(taps[p], np.complex128)
             h = (t[None, :] * np.exp(-2j * np.pi * np.outer(bins, np.arange(len(t))) / n)).sum(1)
         rx += grid[p] * h[None, :]
-    iq = ofdm_tx(cell.nof_prb, rx)
+    iq = ofdm_tx(cell.nof_prb, rx, cell.cp)
     # unitary (I)FFT on both sides: a unit-power RE stays unit power and the per-RE noise variance
     # equals the per-sample one, so snr_db is Es/N0 per resource element
     sigma2 = 10.0 ** (-snr_db / 10.0)

@@ -12,7 +12,8 @@ LIB_PATH = os.environ.get("SRSUE_GPU_LIB", os.path.join(_HERE, "libsrsue_gpu.so"
 
 
 class Cell(C.Structure):
-    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int)]
+    # cp: 0 = normal cyclic prefix, 1 = extended (srsue_gpu_cell_t, include/srsue_gpu/srsue_gpu.h)
+    _fields_ = [("nof_prb", C.c_int), ("nof_ports", C.c_int), ("cell_id", C.c_int), ("cp", C.c_int)]
 
 
 class PdschCfg(C.Structure):
@@ -371,8 +372,8 @@ class Batch:
             self.h = C.c_void_p()
 
 
-def make_cell(nof_prb, nof_ports=1, cell_id=1):
-    return Cell(nof_prb, nof_ports, cell_id)
+def make_cell(nof_prb, nof_ports=1, cell_id=1, cp=0):
+    return Cell(nof_prb, nof_ports, cell_id, cp)
 
 
 def make_cfg(cell, sf_idx=1, cfi=1, rnti=0x1234, qm=2, tbs=152, rv=0, tm=1, prbs=None, prbs_slot1=None):

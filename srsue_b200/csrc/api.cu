@@ -547,7 +547,7 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
   CU_CHECK(cudaSetDevice(ctx->device));
   auto* p = new srsue_gpu_pdsch_plan();
   p->ctx = ctx;
-  p->cell = CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id};
+  p->cell = CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0};
   static_assert(sizeof(PdschCfg) == sizeof(srsue_gpu_pdsch_cfg_t), "config layouts must match");
   std::memcpy(&p->cfg, cfg, sizeof(PdschCfg));
   if (cfg->tbs == 0) {
@@ -556,7 +556,7 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
     const int nsc0 = 12 * cell->nof_prb;
     p->info.nfft = nfft; p->info.nsc = nsc0; p->info.sf_len = 15 * nfft; p->info.max_batch = max_batch;
     std::vector<int8_t> crs0(4 * 2 * 2 * cell->nof_prb), rs0, is0;
-    const int crs_l0[4] = {0, 4, 7, 11};
+    const int crs_l0[4] = {0, p->cell.cp ? 3 : 4, p->cell.cp ? 6 : 7, p->cell.cp ? 9 : 11};
     for (int si = 0; si < 4; si++) {
       crs_signs(p->cell, cfg->sf_idx, crs_l0[si], rs0, is0);
       const int M = 2 * cell->nof_prb;
@@ -631,7 +631,7 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
   gold_packed(((uint32_t)cfg->rnti << 14) | ((uint32_t)cfg->sf_idx << 9) | (uint32_t)cell->cell_id, G, scr);
   scr.push_back(0u);      // the kernel reads bit groups with a two-word funnel shift
   std::vector<int8_t> crs(4 * 2 * 2 * cell->nof_prb), rs, is;
-  const int crs_l[4] = {0, 4, 7, 11};
+  const int crs_l[4] = {0, p->cell.cp ? 3 : 4, p->cell.cp ? 6 : 7, p->cell.cp ? 9 : 11};
   for (int si = 0; si < 4; si++) {
     crs_signs(p->cell, cfg->sf_idx, crs_l[si], rs, is);
     const int M = 2 * cell->nof_prb;
@@ -778,7 +778,8 @@ static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t
   }
   a.iq = reinterpret_cast<const float2*>(d_iq); a.sf_symbols = reinterpret_cast<float2*>(d_sf);
   a.tw = reinterpret_cast<const float2*>(p->d_tw);
-  a.nfft = p->info.nfft; a.nsc = p->info.nsc; a.n_sf = n_sf;
+  a.nfft = p->info.nfft; a.nsc = p->info.nsc; a.n_sf = n_sf; a.cp_ext = p->cell.cp;
+  const int nsym = nof_symb(p->cell.cp);     // grid x: one CTA per OFDM symbol
   a.log2n = 0; while ((1 << a.log2n) < a.nfft) a.log2n++;
   a.scale = (float)(1.0 / std::sqrt((double)a.nfft));
   a.c3 = (float)(std::sqrt(3.0) / 2.0);
@@ -799,19 +800,19 @@ static int ofdm_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t
     static const int r16 = getenv("SRSUE_FFT_R16") ? atoi(getenv("SRSUE_FFT_R16")) : 1;
     if (r16 && a.nfft == 2048 && !rotate) {
       const int smem16 = (2048 + 2048 / 16) * (int)sizeof(float2);
-      if (b.iq16) ofdm_rx_r16_iq16_kernel<<<dim3(14, n), 128, smem16, (cudaStream_t)stream>>>(b);
-      else ofdm_rx_r16_kernel<<<dim3(14, n), 128, smem16, (cudaStream_t)stream>>>(b);
+      if (b.iq16) ofdm_rx_r16_iq16_kernel<<<dim3(nsym, n), 128, smem16, (cudaStream_t)stream>>>(b);
+      else ofdm_rx_r16_kernel<<<dim3(nsym, n), 128, smem16, (cudaStream_t)stream>>>(b);
     } else if (b.iq16 && rotate) {
       if (b.cfo_steps) b.cfo_steps += done;
-      ofdm_rx_cfo_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+      ofdm_rx_cfo_iq16_kernel<<<dim3(nsym, n), threads, smem, (cudaStream_t)stream>>>(b);
     } else if (b.iq16) {
-      if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_iq16_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
-      else ofdm_rx_iq16_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+      if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_iq16_kernel<<<dim3(nsym, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
+      else ofdm_rx_iq16_kernel<<<dim3(nsym, n), threads, smem, (cudaStream_t)stream>>>(b);
     } else if (rotate) {
       if (b.cfo_steps) b.cfo_steps += done;
-      ofdm_rx_cfo_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
-    } else if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(14, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
-    else ofdm_rx_kernel<<<dim3(14, n), threads, smem, (cudaStream_t)stream>>>(b);
+      ofdm_rx_cfo_kernel<<<dim3(nsym, n), threads, smem, (cudaStream_t)stream>>>(b);
+    } else if (inplace && a.nfft != 1536 && a.nfft >= 256) ofdm_rx_inplace_kernel<<<dim3(nsym, n), threads, smem / 2, (cudaStream_t)stream>>>(b);
+    else ofdm_rx_kernel<<<dim3(nsym, n), threads, smem, (cudaStream_t)stream>>>(b);
     p->ctx->launch_count++;
   }
   CU_CHECK(cudaGetLastError());
@@ -943,6 +944,7 @@ int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_
   PLAN_CHECK(p, n_sf);
   if (!d_sf || !d_ce || !d_ack || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: null buffer");
   if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12");
+  if (p->cell.cp) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: spreading factor 2 of the extended cyclic prefix is not built");
   if (n_group < 0 || n_group >= phich_groups(p->cell.nof_prb, ng_x6) || n_seq < 0 || n_seq > 7)
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: group %d / sequence %d out of range", n_group, n_seq);
   PhichArgs a{};
@@ -963,6 +965,7 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
   PLAN_CHECK(p, n_sf);
   if (!d_sf || !d_ce || !d_result || !d_mib || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: null buffer");
   if (p->cfg.sf_idx != 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: the PBCH is in subframe 0 (plan has sf_idx %d)", p->cfg.sf_idx);
+  if (p->cell.cp) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: the 216-element PBCH of the extended cyclic prefix is not built");
   if (!p->d_pbch_re) {
     std::vector<int32_t> re(240), seq;
     pbch_res(p->cell, re.data());
@@ -985,8 +988,8 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
 }
 
 int srsue_gpu_host_pbch_res(const srsue_gpu_cell_t* cell, int32_t* g240) {
-  if (!cell || !g240 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;
-  pbch_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, g240);
+  if (!cell || !g240 || cell->nof_prb < 6 || cell->cp) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  pbch_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, g240);
   return 0;
 }
 
@@ -997,15 +1000,15 @@ int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs,
 }
 
 int srsue_gpu_host_phich_res(const srsue_gpu_cell_t* cell, int n_group, int32_t* k12) {
-  if (!cell || !k12 || n_group < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
-  phich_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, n_group, k12);
+  if (!cell || !k12 || n_group < 0 || cell->cp) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  phich_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, n_group, k12);
   return 0;
 }
 
 int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t* cell, int cfi, int ng_x6, int32_t* re4) {
   if (!cell || cfi < 1 || cfi > 3) return SRSUE_GPU_ERROR_INVALID_INPUTS;
   std::vector<int32_t> v;
-  const int n = pdcch_regs(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, cfi, ng_x6, v);
+  const int n = pdcch_regs(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, cfi, ng_x6, v);
   if (re4) std::copy(v.begin(), v.end(), re4);
   return n;
 }
@@ -1027,7 +1030,7 @@ int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb) { return (fmt == 0 ||
 
 int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t* cell, int32_t* k16) {
   if (!cell || !k16 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;
-  pcfich_re(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id}, k16);
+  pcfich_re(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, k16);
   return 0;
 }
 
@@ -1049,7 +1052,8 @@ static int chest_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_
   // 128 threads measured best on B200 (0.19 ms vs 0.26 ms per 4096 subframes with 512): the kernel is bound by its
   // three ordered reduction warps, smaller CTAs pack more of them per SM.  Needs >= 3 warps.
   static const int chest_threads = std::min(128, std::max(96, getenv("SRSUE_CHEST_THREADS") ? atoi(getenv("SRSUE_CHEST_THREADS")) : 128));
-  chest_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
+  if (p->cell.cp) chest_ext_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
+  else chest_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
   return 0;
@@ -1082,7 +1086,7 @@ static int llr_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
   if (noise_mode && !d_meas) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: noise_mode 1 needs d_meas");
   DemodArgs a{};
   a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
-  a.pilots = reinterpret_cast<const float2*>(d_pilots); a.nof_prb = p->cell.nof_prb;
+  a.pilots = reinterpret_cast<const float2*>(d_pilots); a.nof_prb = p->cell.nof_prb; a.cp_ext = p->cell.cp;
   std::memcpy(a.crs_off, p->crs_off, sizeof(a.crs_off));
   a.softbuf = d_softbuf; a.re_idx = p->d_re; a.scramble = p->d_scr; a.gather = p->d_gather;
   a.cb_e_start = p->d_e_start; a.cb_geom = p->d_cb_geom;
@@ -1225,7 +1229,7 @@ int srsue_gpu_host_cbsegm(int tbs, int* out) {
 
 int srsue_gpu_host_pdsch_re(const srsue_gpu_cell_t* cell, const srsue_gpu_pdsch_cfg_t* cfg, int32_t* re_idx) {
   if (!cell || !cfg) return SRSUE_GPU_ERROR_INVALID_INPUTS;
-  CellCfg c{cell->nof_prb, cell->nof_ports, cell->cell_id};
+  CellCfg c{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0};
   PdschCfg pc;
   std::memcpy(&pc, cfg, sizeof(pc));
   std::vector<int32_t> re;

@@ -182,7 +182,7 @@ namespace {
 
 std::string plan_key(const srsue_gpu_sf_desc_t& d) {
   // explicit fields only (struct padding must not split buckets)
-  const int v[10] = {d.cell.nof_prb, d.cell.nof_ports, d.cell.cell_id, d.cfg.sf_idx, d.cfg.cfi, d.cfg.rnti, d.cfg.qm, d.cfg.tbs, d.cfg.rv, d.cfg.tm};
+  const int v[11] = {d.cell.nof_prb, d.cell.nof_ports, d.cell.cell_id, d.cell.cp ? 1 : 0, d.cfg.sf_idx, d.cfg.cfi, d.cfg.rnti, d.cfg.qm, d.cfg.tbs, d.cfg.rv, d.cfg.tm};
   std::string k(reinterpret_cast<const char*>(v), sizeof(v));
   for (int i = 0; i < 110; i++) k.push_back((char)(d.cfg.prb_mask[i] & 7));
   return k;
@@ -751,7 +751,7 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
   std::map<std::string, std::vector<int>> groups;
   std::vector<std::string> group_order;
   for (int i = 0; i < n; i++) {
-    const int v[5] = {descs[i].cell.nof_prb, descs[i].cell.nof_ports, descs[i].cell.cell_id, descs[i].cfg.sf_idx, descs[i].cfg.rnti};
+    const int v[6] = {descs[i].cell.nof_prb, descs[i].cell.nof_ports, descs[i].cell.cell_id, descs[i].cell.cp ? 1 : 0, descs[i].cfg.sf_idx, descs[i].cfg.rnti};
     std::string k(reinterpret_cast<const char*>(v), sizeof(v));
     auto it = groups.find(k);
     if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }

@@ -29,7 +29,10 @@ __device__ __forceinline__ float warp_sum_ordered(int n, int lane, F elem) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
+// EXT = extended cyclic prefix: 12 symbols, CRS in symbols 0, 3, 6, 9 (36.211 6.10.1.2: symbols 0 and N_symb - 3 of a slot),
+// symbols 10 and 11 extrapolated from (6, 9) as 12 and 13 are from (7, 11); same operations otherwise (SPEC.md 15)
+template <bool EXT>
+__device__ __forceinline__ void chest_body(const ChestArgs& a) {
   extern __shared__ __align__(16) float2 s_ch[];
   __shared__ float s_ftab[17];
   __shared__ float s_ttab[14];
@@ -40,13 +43,14 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
   float2* s_sm = s_ch + np * 4 * M;       // [np][4][M]
   float* s_pw = reinterpret_cast<float*>(s_ch + 2 * np * 4 * M);   // [4][nsc]: |y|^2 of the four CRS symbols (RSSI)
   const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
-  const int crs_l[4] = {0, 4, 7, 11};
+  constexpr int NSYM = EXT ? 12 : 14, C1 = EXT ? 3 : 4, C2 = EXT ? 6 : 7, C3 = EXT ? 9 : 11;
+  const int crs_l[4] = {0, C1, C2, C3};
   const float isq2 = (float)(1.0 / sqrt(2.0));
 
   if (tid < 17) s_ftab[tid] = (float)((double)(tid - 5) / 6.0);
-  if (tid >= 32 && tid < 46) {
+  if (tid >= 32 && tid < 32 + NSYM) {
     const int l = tid - 32;
-    const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+    const int s0 = (l < C1) ? 0 : (l < C2) ? 1 : 2;
     s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
   }
   // ---- RSSI inputs: the ordered sum below is one warp walking 4 nsc values (SPEC 3.5 fixes its order), which as a chain
@@ -91,10 +95,10 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
         h[si] = make_float2(lerp_rn(v0.x, v1.x, f), lerp_rn(v0.y, v1.y, f));
       }
 #pragma unroll
-      for (int l = 0; l < 14; l++) {
-        const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+      for (int l = 0; l < NSYM; l++) {
+        const int s0 = (l < C1) ? 0 : (l < C2) ? 1 : 2;
         float2 o;
-        if (l == 0 || l == 4 || l == 7 || l == 11) o = h[l == 0 ? 0 : l == 4 ? 1 : l == 7 ? 2 : 3];
+        if (l == 0 || l == C1 || l == C2 || l == C3) o = h[l == 0 ? 0 : l == C1 ? 1 : l == C2 ? 2 : 3];
         else { const float f = s_ttab[l]; o = make_float2(lerp_rn(h[s0].x, h[s0 + 1].x, f), lerp_rn(h[s0].y, h[s0 + 1].y, f)); }
         ce[l * nsc + k] = o;
       }
@@ -126,5 +130,8 @@ __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) {
     o[4] = __fdiv_rn(s_red[1], s_red[0]);
   }
 }
+
+__global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) { chest_body<false>(a); }
+__global__ void __launch_bounds__(128, 10) chest_ext_kernel(const ChestArgs a) { chest_body<true>(a); }
 
 }  // namespace srsue

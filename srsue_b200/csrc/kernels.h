@@ -88,6 +88,7 @@ struct OfdmArgs {
   // int16 {re, im} input (ofdm_rx_*iq16_kernel only): sample = (float)v * iq16_scale
   const short2* iq16;
   float iq16_scale;
+  int cp_ext;                // 1: extended cyclic prefix (grid x = 12 symbols; rows 12, 13 of every grid stay untouched)
 };
 __global__ void ofdm_rx_kernel(const OfdmArgs a);
 __global__ void ofdm_rx_r16_kernel(const OfdmArgs a);          // N = 2048 only: radix 16 x 16 x 8, 128 threads (ofdm.cu)
@@ -107,13 +108,15 @@ struct ChestArgs {
   int n_sf, nsc, nof_prb, nof_ports;
   int crs_off[2][4];         // first pilot subcarrier per port and CRS symbol
 };
-__global__ void chest_kernel(const ChestArgs a);
+__global__ void chest_kernel(const ChestArgs a);       // normal cyclic prefix: CRS in symbols 0, 4, 7, 11 of 14
+__global__ void chest_ext_kernel(const ChestArgs a);   // extended cyclic prefix: CRS in symbols 0, 3, 6, 9 of 12
 
 struct DemodArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc]
   const float2* ce;          // [n_sf][ports][14 * nsc] (unused when pilots != nullptr)
   const float2* pilots;      // optional [n_sf][ports][4][2 * nof_prb]: interpolate the channel on the fly
   int nof_prb;
+  int cp_ext;                // fused interpolation only: CRS symbols 0, 3, 6, 9 instead of 0, 4, 7, 11
   int crs_off[2][4];         // first pilot subcarrier per port and CRS symbol
   const float* meas;         // [n_sf][5] (noise estimate when noise_mode == 1)
   int16_t* softbuf;          // [n_sf][C][sb_stride] tcb layout

@@ -145,15 +145,16 @@ int cb_E(const CbSegm& s, int G, int qm, int nl, int r) {
 }
 
 int crs_offset(const CellCfg& cell, int port, int l) {
-  const int ls = l % 7;
-  if (ls != 0 && ls != 4) return -1;
+  const int nslot = slot_symb(cell.cp), ls = l % nslot;
+  if (ls != 0 && ls != nslot - 3) return -1;            // ports 0/1: symbols 0 and N_symb - 3 of a slot (36.211 6.10.1.2)
   const int v = ((ls == 0) == (port == 0)) ? 0 : 3;
   return (v + cell.cell_id % 6) % 6;
 }
 
 void crs_signs(const CellCfg& cell, int sf_idx, int l, std::vector<int8_t>& re_sign, std::vector<int8_t>& im_sign) {
-  const int ns = 2 * sf_idx + l / 7, ls = l % 7, M = 2 * cell.nof_prb;
-  const uint32_t c_init = 1024u * (7u * (ns + 1) + ls + 1) * (2u * cell.cell_id + 1) + 2u * cell.cell_id + 1u;
+  const int nslot = slot_symb(cell.cp), ns = 2 * sf_idx + l / nslot, ls = l % nslot, M = 2 * cell.nof_prb;
+  // 36.211 6.10.1.1: ... + 2 N_ID + N_CP with N_CP = 1 (normal) or 0 (extended cyclic prefix)
+  const uint32_t c_init = 1024u * (7u * (ns + 1) + ls + 1) * (2u * cell.cell_id + 1) + 2u * cell.cell_id + (cell.cp ? 0u : 1u);
   std::vector<uint8_t> c(440);
   gold_bits(c_init, 440, c.data());
   re_sign.resize(M); im_sign.resize(M);
@@ -169,13 +170,15 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
   const int nsc = 12 * cell.nof_prb;
   const int first = cfg.cfi + (cell.nof_prb <= 10 ? 1 : 0);
   const int mid_lo = nsc / 2 - 36, mid_hi = nsc / 2 + 36;
-  for (int l = first; l < 14; l++) {
+  const int nslot = slot_symb(cell.cp);
+  for (int l = first; l < 2 * nslot; l++) {
     const int o0 = crs_offset(cell, 0, l);
     const int o1 = (cell.nof_ports > 1) ? crs_offset(cell, 1, l) : -1;
-    bool central_reserved = ((cfg.sf_idx == 0 || cfg.sf_idx == 5) && (l == 5 || l == 6)) ||
-                            (cfg.sf_idx == 0 && l >= 7 && l <= 10);
+    // SSS and PSS close slot 0 of subframes 0 and 5, the PBCH opens slot 1 of subframe 0
+    bool central_reserved = ((cfg.sf_idx == 0 || cfg.sf_idx == 5) && (l == nslot - 2 || l == nslot - 1)) ||
+                            (cfg.sf_idx == 0 && l >= nslot && l <= nslot + 3);
     for (int prb = 0; prb < cell.nof_prb; prb++) {
-      if (!prb_in_slot(cfg.prb_mask[prb], l / 7)) continue;
+      if (!prb_in_slot(cfg.prb_mask[prb], l / nslot)) continue;
       for (int k = 12 * prb; k < 12 * prb + 12; k++) {
         if (o0 >= 0 && (k % 6 == o0 || k % 6 == o1)) continue;
         if (central_reserved && k >= mid_lo && k < mid_hi) continue;
@@ -368,6 +371,9 @@ int pdcch_regs(const CellCfg& cell, int cfi, int ng_x6, std::vector<int32_t>& re
       if (l == 0) {
         if (k % 6 || taken[k / 6]) continue;
         for (int j = 0; j < 6; j++) if ((k + j) % 3 != cell.cell_id % 3) re4.push_back(k + j);
+      } else if (cell.cp && l == 3) {        // extended cyclic prefix: the fourth control symbol (<= 10 PRB) carries CRS
+        if (k % 6) continue;
+        for (int j = 0; j < 6; j++) if ((k + j) % 3 != cell.cell_id % 3) re4.push_back(l * nsc + k + j);
       } else {
         if (k % 4) continue;
         for (int j = 0; j < 4; j++) re4.push_back(l * nsc + k + j);

@@ -15,7 +15,11 @@ constexpr int kTdE = 2047;      // clamp of extrinsic LLRs
 constexpr int kTdInf = 10000;   // finite minus-infinity of known trellis states
 constexpr uint32_t kCrc24A = 0x1864CFBu, kCrc24B = 0x1800063u;
 
-struct CellCfg { int nof_prb, nof_ports, cell_id; };
+// cp: 0 = normal cyclic prefix (7 symbols per slot), 1 = extended (6).  Subframe grids keep a stride of 14 symbols per port
+// in either case; with the extended prefix rows 12 and 13 are never touched.
+struct CellCfg { int nof_prb, nof_ports, cell_id, cp = 0; };
+inline int nof_symb(int cp) { return cp ? 12 : 14; }
+inline int slot_symb(int cp) { return cp ? 6 : 7; }
 
 struct PdschCfg {
   int sf_idx, cfi, rnti, qm, tbs, rv, tm, nof_prb_alloc;
@@ -44,6 +48,7 @@ int window_len(int K);
 TurboGeom turbo_geom(int K);
 int symbol_sz(int nof_prb);
 inline int cp_len(int nfft, int l) { return ((l % 7) == 0 ? 160 : 144) * nfft / 2048; }
+inline int cp_len_x(int nfft, int l, int cp) { return cp ? 512 * nfft / 2048 : cp_len(nfft, l); }
 
 uint32_t crc_bits(const uint8_t* bits, int n, uint32_t poly, int order);
 // x^e mod g(x) for the 24-bit CRC polynomials

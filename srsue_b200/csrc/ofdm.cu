@@ -453,22 +453,28 @@ __device__ __forceinline__ void fft2048_r16(const float2* __restrict__ gin, floa
   }
 }
 
+// sample offset of symbol l inside its subframe: the cyclic prefixes of symbols 0..l plus l full symbols.  Normal prefix:
+// 160 samples (at N = 2048) for the first symbol of a slot, 144 for the six others; extended: 512 for each of the six
+__device__ __forceinline__ int symbol_start(int N, int l, int cp_ext) {
+  if (cp_ext) return (l + 1) * (N / 4) + l * N;
+  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
+  const int slot = l / 7, ls = l % 7;
+  return slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+}
 }  // namespace
 
 __global__ void __launch_bounds__(128, SRSUE_FFT16_MIN_CTAS) ofdm_rx_r16_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   constexpr int N = 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + 160 + 6 * 144) + ls * N + 160 + ls * 144;
+  const int start = symbol_start(N, l, a.cp_ext);
   fft2048_r16<false>(a.iq + (size_t)sf * 15 * N + start, a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc, s_fft, a.tw, a.nsc, a.scale, 0.f);
 }
 __global__ void __launch_bounds__(128, SRSUE_FFT16_MIN_CTAS) ofdm_rx_r16_iq16_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   constexpr int N = 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + 160 + 6 * 144) + ls * N + 160 + ls * 144;
+  const int start = symbol_start(N, l, a.cp_ext);
   fft2048_r16<true>(reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start), a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc, s_fft,
                     a.tw, a.nsc, a.scale, a.iq16_scale);
 }
@@ -477,9 +483,7 @@ __global__ void __launch_bounds__(256, 7) ofdm_rx_inplace_kernel(const OfdmArgs 
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = a.iq + (size_t)sf * 15 * N + start;
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   switch (a.log2n) {
@@ -495,10 +499,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  // sample offset of symbol l: CPs of symbols 0..l plus l full symbols
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = a.iq + (size_t)sf * 15 * N + start;
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   float2* s0 = s_fft;
@@ -520,9 +521,7 @@ __global__ void __launch_bounds__(256, 7) ofdm_rx_inplace_iq16_kernel(const Ofdm
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   switch (a.log2n) {
@@ -538,9 +537,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_iq16_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   float2* s0 = s_fft;
@@ -561,9 +558,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_cfo_iq16_kernel(const OfdmArgs a)
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = reinterpret_cast<const float2*>(a.iq16 + (size_t)sf * 15 * N + start);
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   float2* s0 = s_fft;
@@ -585,9 +580,7 @@ __global__ void __launch_bounds__(256) ofdm_rx_cfo_kernel(const OfdmArgs a) {
   extern __shared__ __align__(16) float2 s_fft[];
   const int l = blockIdx.x, sf = blockIdx.y;
   const int N = a.nfft;
-  const int cp0 = 160 * N / 2048, cp1 = 144 * N / 2048;
-  const int slot = l / 7, ls = l % 7;
-  const int start = slot * (7 * N + cp0 + 6 * cp1) + ls * N + cp0 + ls * cp1;
+  const int start = symbol_start(N, l, a.cp_ext);
   const float2* gin = a.iq + (size_t)sf * 15 * N + start;
   float2* gout = a.sf_symbols + ((size_t)sf * 14 + l) * a.nsc;
   float2* s0 = s_fft;

@@ -89,6 +89,7 @@ struct ChanInterp {
   const float* s_ftab;     // [17]
   const float* s_ttab;     // [14]
   int nsc, M;
+  int c1, c2, c3;          // CRS symbols after symbol 0: 4, 7, 11 (normal cyclic prefix) or 3, 6, 9 (extended)
   int off[2][4];
   __device__ __forceinline__ float2 freq(int p, int si, int k) const {
     const int o = off[p][si];
@@ -101,10 +102,10 @@ struct ChanInterp {
   __device__ __forceinline__ float2 at(int p, int g) const {
     const int l = g / nsc, k = g - l * nsc;
     if (l == 0) return freq(p, 0, k);
-    if (l == 4) return freq(p, 1, k);
-    if (l == 7) return freq(p, 2, k);
-    if (l == 11) return freq(p, 3, k);
-    const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+    if (l == c1) return freq(p, 1, k);
+    if (l == c2) return freq(p, 2, k);
+    if (l == c3) return freq(p, 3, k);
+    const int s0 = (l < c1) ? 0 : (l < c2) ? 1 : 2;
     const float2 h0 = freq(p, s0, k), h1 = freq(p, s0 + 1, k);
     const float f = s_ttab[l];
     return make_float2(lerp_rn(h0.x, h1.x, f), lerp_rn(h0.y, h1.y, f));
@@ -185,11 +186,12 @@ __global__ void __launch_bounds__(SRSUE_DEMOD_MAX_THREADS, SRSUE_DEMOD_MIN_CTAS)
     if (threadIdx.x < 17) s_ftab[threadIdx.x] = (float)((double)((int)threadIdx.x - 5) / 6.0);
     if (threadIdx.x >= 32 && threadIdx.x < 46) {
       const int l = threadIdx.x - 32;
-      const int crs_l[4] = {0, 4, 7, 11};
-      const int s0 = (l < 4) ? 0 : (l < 7) ? 1 : 2;
+      const int crs_l[4] = {0, a.cp_ext ? 3 : 4, a.cp_ext ? 6 : 7, a.cp_ext ? 9 : 11};
+      const int s0 = (l < crs_l[1]) ? 0 : (l < crs_l[2]) ? 1 : 2;
       s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
     }
     ci.s_pil = s_pil; ci.s_ftab = s_ftab; ci.s_ttab = s_ttab; ci.nsc = a.nsc; ci.M = M;
+    ci.c1 = a.cp_ext ? 3 : 4; ci.c2 = a.cp_ext ? 6 : 7; ci.c3 = a.cp_ext ? 9 : 11;
 #pragma unroll
     for (int p = 0; p < 2; p++)
 #pragma unroll

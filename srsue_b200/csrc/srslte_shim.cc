@@ -157,13 +157,14 @@ void srslte_vec_free(void* p) { free(p); }
 int srslte_ue_dl_init(srslte_ue_dl_t* q, srslte_cell_t cell) {
   if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
   std::memset(q, 0, sizeof(*q));
-  if (symbol_sz((int)cell.nof_prb) < 0 || cell.nof_ports < 1 || cell.nof_ports > 2 || cell.cp != SRSLTE_CP_NORM)
+  if (symbol_sz((int)cell.nof_prb) < 0 || cell.nof_ports < 1 || cell.nof_ports > 2 ||
+      (cell.cp != SRSLTE_CP_NORM && cell.cp != SRSLTE_CP_EXT))
     return SRSLTE_ERROR_INVALID_INPUTS;
   srsue_gpu_ctx_t* ctx = shared_ctx();
   if (!ctx) return SRSLTE_ERROR;
   auto* u = new UeDlGpu();
   u->ctx = ctx;
-  u->cell = srsue_gpu_cell_t{(int)cell.nof_prb, (int)cell.nof_ports, (int)cell.id};
+  u->cell = srsue_gpu_cell_t{(int)cell.nof_prb, (int)cell.nof_ports, (int)cell.id, cell.cp == SRSLTE_CP_EXT ? 1 : 0};
   u->ng_x6 = ng_x6_of(cell);
   u->nsc = 12 * (int)cell.nof_prb;
   u->sf_len = 15 * symbol_sz((int)cell.nof_prb);
@@ -232,6 +233,7 @@ int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf
   srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, 1);
   if (!fp) return SRSLTE_ERROR;
   const size_t grid = (size_t)14 * u->nsc;
+  const size_t glen = (size_t)nof_symb(u->cell.cp) * u->nsc;   // what the caller's buffers hold (12 symbols with the extended prefix)
   // the IQ buffer is reused by the caller right after we return (phch_worker.cc:254 vs :559,610,641):
   // it is fully consumed (H2D) before the synchronise below
   if (cudaMemcpyAsync(u->d_iq, input, u->sf_len * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream) != cudaSuccess) return SRSLTE_ERROR;
@@ -245,9 +247,9 @@ int srslte_ue_dl_decode_fft_estimate(srslte_ue_dl_t* q, cf_t* input, uint32_t sf
     if (srsue_gpu_pcfich_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, u->d_cfi, u->d_cfi + 1, u->stream)) return SRSLTE_ERROR;
     cudaMemcpyAsync(&cfi_dec, u->d_cfi, sizeof(cfi_dec), cudaMemcpyDeviceToHost, u->stream);
   }
-  cudaMemcpyAsync(q->sf_symbols, u->d_sf, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
+  cudaMemcpyAsync(q->sf_symbols, u->d_sf, glen * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
   for (int p = 0; p < u->cell.nof_ports; p++)
-    cudaMemcpyAsync(q->ce[p], u->d_ce + (size_t)p * grid, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
+    cudaMemcpyAsync(q->ce[p], u->d_ce + (size_t)p * grid, glen * sizeof(srsue_gpu_cf_t), cudaMemcpyDeviceToHost, u->stream);
   cudaMemcpyAsync(meas, u->d_meas, sizeof(meas), cudaMemcpyDeviceToHost, u->stream);
   if (cudaStreamSynchronize(u->stream) != cudaSuccess) return SRSLTE_ERROR;
   q->chest.noise_estimate = meas[0]; q->chest.rsrp = meas[1]; q->chest.rssi = meas[2]; q->chest.rsrq = meas[3];
@@ -264,8 +266,8 @@ int srslte_ue_dl_cfg_grant(srslte_ue_dl_t* q, srslte_ra_dl_grant_t* grant, uint3
   c->rv = rvidx;
   c->sf_idx = sf_idx;
   c->nbits.lstart = cfi + (q->cell.nof_prb <= 10 ? 1 : 0);
-  c->nbits.nof_symb = 14 - c->nbits.lstart;
-  CellCfg cell{(int)q->cell.nof_prb, (int)q->cell.nof_ports, (int)q->cell.id};
+  c->nbits.nof_symb = (q->cell.cp == SRSLTE_CP_EXT ? 12 : 14) - c->nbits.lstart;
+  CellCfg cell{(int)q->cell.nof_prb, (int)q->cell.nof_ports, (int)q->cell.id, q->cell.cp == SRSLTE_CP_EXT ? 1 : 0};
   PdschCfg pc{};
   pc.sf_idx = (int)sf_idx; pc.cfi = (int)cfi;
   for (uint32_t i = 0; i < q->cell.nof_prb; i++) pc.prb_mask[i] = slot_mask(grant->prb_idx[0][i], grant->prb_idx[1][i]);
@@ -303,15 +305,16 @@ int srslte_pdsch_decode_rnti(srslte_pdsch_t* q, srslte_pdsch_cfg_t* cfg, srslte_
   srsue_gpu_pdsch_plan_info(p, &info);
   if ((size_t)info.sb_sf_stride > sh->elems || info.payload_stride > 19200) return SRSLTE_ERROR;
   const size_t grid = (size_t)14 * u->nsc;
+  const size_t glen = (size_t)nof_symb(u->cell.cp) * u->nsc;   // what the caller's buffers hold (12 symbols with the extended prefix)
   // reuse the device copies of this subframe's grid when the caller hands back our own mirrors
   // (phch_worker.cc:347-348 passes ue_dl.sf_symbols / ue_dl.ce), otherwise upload what we were given
   bool own = u->dev_valid && sf_symbols == u->h_sf;
   for (int pt = 0; pt < u->cell.nof_ports; pt++) own = own && (ce[pt] == u->h_ce[pt]);
   if (!own) {
     u->dev_valid = false;
-    cudaMemcpyAsync(u->d_sf, sf_symbols, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+    cudaMemcpyAsync(u->d_sf, sf_symbols, glen * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
     for (int pt = 0; pt < u->cell.nof_ports; pt++)
-      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], glen * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
   }
   const int accumulate = (sh->valid_tbs == c.tbs) ? 1 : 0;
   if (srsue_gpu_pdsch_llr(p, 1, u->d_sf, u->d_ce, u->d_meas, noise_estimate, 0, accumulate, sh->d_buf, nullptr, nullptr, u->stream))
@@ -336,13 +339,14 @@ int srslte_pdcch_extract_llr(srslte_pdcch_t* q, cf_t* sf_symbols, cf_t* ce[SRSLT
   srsue_gpu_pdsch_plan_t* fp = front_plan(u, nsubframe, cfi);
   if (!fp) return SRSLTE_ERROR;
   const size_t grid = (size_t)14 * u->nsc;
+  const size_t glen = (size_t)nof_symb(u->cell.cp) * u->nsc;   // what the caller's buffers hold (12 symbols with the extended prefix)
   bool own = u->dev_valid && sf_symbols == u->h_sf;
   for (int pt = 0; pt < u->cell.nof_ports; pt++) own = own && (ce[pt] == u->h_ce[pt]);
   if (!own) {
     u->dev_valid = false;
-    cudaMemcpyAsync(u->d_sf, sf_symbols, grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+    cudaMemcpyAsync(u->d_sf, sf_symbols, glen * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
     for (int pt = 0; pt < u->cell.nof_ports; pt++)
-      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], grid * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
+      cudaMemcpyAsync(u->d_ce + (size_t)pt * grid, ce[pt], glen * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, u->stream);
   }
   int n_reg = 0, n_cce = 0;
   if (srsue_gpu_pdcch_info(fp, u->ng_x6, &n_reg, &n_cce)) return SRSLTE_ERROR;
