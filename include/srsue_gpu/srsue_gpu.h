@@ -84,6 +84,7 @@ typedef struct {
   float mean_power;     /* mean of |correlation|^2 over all roots and positions (peak / mean_power = peak-to-side ratio) */
   float cfo;            /* carrier frequency offset in units of the 15 kHz subcarrier spacing */
   float sss_corr;
+  int32_t cp;           /* cyclic prefix the SSS was found with: 0 normal, 1 extended (srsue_gpu_cell_search_cp) */
 } srsue_gpu_sync_result_t;
 /* d_iq: n_bufs buffers of n_samples (typically a 5 ms half frame = 75 * nfft), `stride` samples apart, at the sampling
  * rate whose OFDM symbol has nfft samples (128 = 1.92 Msps, the cell-search rate; up to 2048 = 30.72 Msps for tracking at
@@ -92,6 +93,11 @@ typedef struct {
  * to the buffer start.  Cell id = 3 * n_id_1 + n_id_2. */
 int srsue_gpu_cell_search(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride, int nfft,
                           int force_n_id_2, int first_pos, srsue_gpu_sync_result_t *d_result, void *stream);
+/* The same with the cyclic prefix as a parameter (what srslte_ue_cellsearch_scan reports in found_cells[].cp,
+ * phch_recv.cc:189): cp_mode 0 looks for the SSS behind a normal prefix (= srsue_gpu_cell_search), 1 behind an extended
+ * one (160 nfft / 128 samples before the PSS), 2 tries both and reports the better one in result.cp. */
+int srsue_gpu_cell_search_cp(srsue_gpu_ctx_t *ctx, const srsue_gpu_cf_t *d_iq, int n_bufs, int n_samples, long long stride, int nfft,
+                             int force_n_id_2, int first_pos, int cp_mode, srsue_gpu_sync_result_t *d_result, void *stream);
 
 /* ---- turbo decoder (device pointers; `stream` is a cudaStream_t passed as void*) ------------ */
 /* geometry of the windowed decoder for code-block size K: window length, windows, tcb elements */
@@ -184,7 +190,8 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gp
                           const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode,
                           int32_t *d_result, uint8_t *d_mib, void *stream);
 /* PHICH (srslte_ue_dl_decode_phich, phch_worker.cc:381): HARQ indicator of (n_group, n_seq) in every subframe of the
- * batch; d_ack [n_sf] = 1 for ACK, d_metric optional [n_sf] (ACK iff < 0).  Normal CP, normal PHICH duration. */
+ * batch; d_ack [n_sf] = 1 for ACK, d_metric optional [n_sf] (ACK iff < 0).  Normal PHICH duration; with the extended
+ * cyclic prefix (spreading factor 2) n_group runs to twice the mapping units and n_seq to 3. */
 int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
                            const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode, int ng_x6,
                            int n_group, int n_seq, int32_t *d_ack, float *d_metric, void *stream);
@@ -294,11 +301,14 @@ int srsue_gpu_host_pdcch_regs(const srsue_gpu_cell_t *cell, int cfi, int ng_x6, 
 int srsue_gpu_host_pdcch_quad_perm(int n_quad, int cell_id, int32_t *src);
 int srsue_gpu_host_pdcch_search_space(int nof_cce, int sf_idx, int rnti, int common, int32_t *cand_L, int32_t *cand_ncce);
 int srsue_gpu_host_dci_format_sizeof(int fmt, int nof_prb);
-/* grid indices (l * nsc + k) of the 240 PBCH resource elements of a subframe 0 */
+/* grid indices (l * nsc + k) of the 240 PBCH resource elements of a subframe 0; with the extended cyclic prefix there
+ * are 216 and g240[216..239] = -1 */
 int srsue_gpu_host_pbch_res(const srsue_gpu_cell_t *cell, int32_t *g240);
 /* PHICH bookkeeping: (group, sequence) answering an uplink transmission with lowest PRB I_lowest and DMRS cyclic shift
  * n_dmrs (36.213 9.1.2); the 12 subcarriers of a group in OFDM symbol 0 */
 int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
+/* the same for either cyclic prefix (cp = 1: twice the groups, n_seq modulo 4; 36.213 9.1.2) */
+int srsue_gpu_host_phich_index_cp(int nof_prb, int ng_x6, int cp, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
 int srsue_gpu_host_phich_res(const srsue_gpu_cell_t *cell, int n_group, int32_t *k12);
 /* subcarriers (in OFDM symbol 0) of the 16 PCFICH symbols d(0..15) */
 int srsue_gpu_host_pcfich_re(const srsue_gpu_cell_t *cell, int32_t *k16);

@@ -146,6 +146,8 @@ void  lteo_pss_time_n(int n_id_2, int nfft, lteo_cf_t *t);
 float lteo_pss_search_n(const lteo_cf_t *x, int n_samples, int nfft, int force_n_id_2, int first_pos, int *peak_pos, int *n_id_2,
                         float *cfo, float *mean_power);
 int   lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr);
+/* cp_mode 0: normal prefix, 1: extended, 2: try both and report the better one in *cp (SPEC.md 15.4) */
+int   lteo_sss_detect_cp(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int cp_mode, int *sf5, float *corr, int *cp);
 /* CFO correction (SPEC.md 14): y[n] = x[n] * T[(n * step mod 2^32) >> 20], T = 4096-entry unit circle */
 #define LTEO_CFO_TABLE_LOG2 12
 #define LTEO_CFO_TABLE (1 << LTEO_CFO_TABLE_LOG2)
@@ -155,6 +157,7 @@ void  lteo_cfo_correct(const lteo_cf_t *in, lteo_cf_t *out, int n_samples, int32
 /* ---- PBCH / MIB (SPEC.md 12) ---- */
 uint16_t lteo_viterbi_crc16(const int32_t *soft, int nof_bits, uint8_t *bits_out);
 void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240);
+int  lteo_pbch_res_n(const lteo_cell_t *cell, int32_t *g240);           /* returns 240, or 216 with the extended prefix */
 void lteo_pbch_tx(const lteo_cell_t *cell, const uint8_t *mib24, int frame_idx, lteo_cd_t *grid);
 void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce, float noise_est,
                    int16_t *llr480);
@@ -163,6 +166,7 @@ int  lteo_pbch_decode(const lteo_cell_t *cell, const lteo_cf_t *sf_symbols, cons
 /* ---- PHICH (SPEC.md 11) ---- */
 void lteo_phich_res(const lteo_cell_t *cell, int ng_x6, int n_group, int32_t *k12);
 void lteo_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
+void lteo_phich_index_cp(int nof_prb, int ng_x6, int cp, int I_lowest, int n_dmrs, int *n_group, int *n_seq);
 void lteo_phich_tx(const lteo_cell_t *cell, int sf_idx, int ng_x6, int n_group, int n_seq, int ack, lteo_cd_t *grid);
 int  lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo_cf_t *sf_symbols, const lteo_cf_t *ce,
                        float noise_est, int n_group, int n_seq, float *metric);

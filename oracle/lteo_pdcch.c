@@ -277,9 +277,11 @@ int lteo_pdcch_find_dci(const int16_t *llr, int nof_cce, int sf_idx, uint16_t rn
 /* ------------------------------------------------------------------------------------------------
  * PHICH (36.211 6.9; srslte_ue_dl_decode_phich, phch_worker.cc:381).  SPEC.md 11.
  * ---------------------------------------------------------------------------------------------- */
-/* the 12 subcarriers (OFDM symbol 0) of PHICH group n_group: 3 REGs x 4 data REs, normal PHICH duration */
+/* the 12 subcarriers (OFDM symbol 0) of PHICH group n_group: 3 REGs x 4 data REs, normal PHICH duration.  With the
+ * extended cyclic prefix groups 2m' and 2m'+1 share mapping unit m' (36.211 6.9.3). */
 void lteo_phich_res(const lteo_cell_t *cell, int ng_x6, int n_group, int32_t *k12) {
   int nrb = cell->nof_prb, n0 = 2 * nrb;
+  if (cell->cp) n_group /= 2;
   uint8_t *used = (uint8_t *)calloc(n0, 1);
   int32_t k16[16];
   lteo_pcfich_re(cell, k16);
@@ -300,6 +302,19 @@ void lteo_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int *n_g
   int ngroups = lteo_phich_groups(nof_prb, ng_x6);
   *n_group = (I_lowest + n_dmrs) % ngroups;
   *n_seq = (I_lowest / ngroups + n_dmrs) % 8;
+}
+
+/* the same for either cyclic prefix: N_group = 2 ceil(Ng N_RB / 8) and n_seq modulo 2 N_SF = 4 with the extended one */
+void lteo_phich_index_cp(int nof_prb, int ng_x6, int cp, int I_lowest, int n_dmrs, int *n_group, int *n_seq) {
+  int ngroups = (cp ? 2 : 1) * lteo_phich_groups(nof_prb, ng_x6);
+  *n_group = (I_lowest + n_dmrs) % ngroups;
+  *n_seq = (I_lowest / ngroups + n_dmrs) % (cp ? 4 : 8);
+}
+
+/* extended cyclic prefix (36.211 Table 6.9.1-2, N_SF = 2): [+1 +1], [+1 -1], [+j +j], [+j -j] */
+static void phich_w2(int n_seq, int i, int *re, int *im) {
+  int v = ((n_seq & 1) && i) ? -1 : 1;
+  if (n_seq < 2) { *re = v; *im = 0; } else { *re = 0; *im = v; }
 }
 
 /* orthogonal sequence element w(i), i < 4, of sequence n_seq < 8 as (re, im) in {0, +-1} */
@@ -324,6 +339,19 @@ void lteo_phich_tx(const lteo_cell_t *cell, int sf_idx, int ng_x6, int n_group, 
     double z = (ack ? -1.0 : 1.0) * a * (c[i] ? -1.0 : 1.0);     /* BPSK: z (1 + j), real factor z */
     /* w * z(1+j): (wr + j wi)(1 + j) = (wr - wi) + j (wr + wi) */
     d[i].re = z * (wr - wi); d[i].im = z * (wr + wi);
+  }
+  if (cell->cp) {
+    /* N_SF = 2: six symbols d(i) = w(i mod 2)(1 - 2 c(i)) z; resource-group alignment (36.211 6.9.2): an even group
+     * fills the first two elements of each quadruplet, an odd one the last two */
+    lteo_cd_t d6[6];
+    for (int i = 0; i < 6; i++) {
+      int wr, wi;
+      phich_w2(n_seq, i % 2, &wr, &wi);
+      double z = (ack ? -1.0 : 1.0) * a * (c[i] ? -1.0 : 1.0);
+      d6[i].re = z * (wr - wi); d6[i].im = z * (wr + wi);
+    }
+    memset(d, 0, sizeof(d));
+    for (int i = 0; i < 3; i++) { d[4 * i + 2 * (n_group & 1)] = d6[2 * i]; d[4 * i + 2 * (n_group & 1) + 1] = d6[2 * i + 1]; }
   }
   lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
   if (cell->nof_ports == 2) {
@@ -370,16 +398,24 @@ int lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo
     }
   }
   float metric = 0.0f;
+  int first = 1;
   for (int i = 0; i < 12; i++) {
-    int wr, wi;
+    int wr, wi, ci = i;
+    if (cell->cp) {
+      /* the group's half of every quadruplet: element q = 2 (i / 4) + i % 2 of the six spread symbols */
+      if (((i >> 1) & 1) != (n_group & 1)) continue;
+      ci = 2 * (i / 4) + (i & 1);
+      phich_w2(n_seq, i & 1, &wr, &wi);
+    } else
     phich_w(n_seq, i % 4, &wr, &wi);
     /* d * conj(w): w = +-1 -> +-d;  w = +-j -> d * (-+j) = (+-d.im, -+d.re) */
     float tr, ti;
     if (wi == 0) { tr = wr > 0 ? d[i].re : -d[i].re; ti = wr > 0 ? d[i].im : -d[i].im; }
     else { tr = wi > 0 ? d[i].im : -d[i].im; ti = wi > 0 ? -d[i].re : d[i].re; }
-    if (c[i]) { tr = -tr; ti = -ti; }
+    if (c[ci]) { tr = -tr; ti = -ti; }
     float m = tr + ti;
-    metric = (i == 0) ? m : metric + m;
+    metric = first ? m : metric + m;
+    first = 0;
   }
   if (metric_out) *metric_out = metric;
   return metric < 0.0f;
@@ -390,13 +426,19 @@ int lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo
  * ---------------------------------------------------------------------------------------------- */
 /* grid indices (l * nsc + k) of the 240 PBCH resource elements of subframe 0: slot 1, symbols 0..3, the 72 central
  * subcarriers, k first then l; the CRS positions of antenna ports 0..3 are always left out (symbols 0 and 1) */
-void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240) {
-  int nsc = 12 * cell->nof_prb, k0 = nsc / 2 - 36, n = 0;
+void lteo_pbch_res(const lteo_cell_t *cell, int32_t *g240) { (void)lteo_pbch_res_n(cell, g240); }
+
+/* the same for either cyclic prefix; returns the number of resource elements: 240, or 216 with the extended prefix, where
+ * symbol 3 of the slot carries CRS as well (36.211 6.6.4: the reference signals of ports 0..3 are always left out) and
+ * the coded block is E = 1728 bits, 432 per radio frame */
+int lteo_pbch_res_n(const lteo_cell_t *cell, int32_t *g240) {
+  int nsc = 12 * cell->nof_prb, k0 = nsc / 2 - 36, n = 0, nslot = LTEO_NSLOT(cell->cp);
   for (int l = 0; l < 4; l++)
     for (int k = 0; k < 72; k++) {
-      if (l < 2 && (k0 + k) % 3 == cell->cell_id % 3) continue;
-      g240[n++] = (7 + l) * nsc + k0 + k;
+      if ((l < 2 || (cell->cp && l == 3)) && (k0 + k) % 3 == cell->cell_id % 3) continue;
+      g240[n++] = (nslot + l) * nsc + k0 + k;
     }
+  return n;
 }
 
 /* the 16-bit CRC mask that signals the number of transmit antenna ports */
@@ -412,16 +454,16 @@ void lteo_pbch_tx(const lteo_cell_t *cell, const uint8_t *mib24, int frame_idx, 
   for (int i = 0; i < 16; i++) c[24 + i] = (uint8_t)((crc >> (15 - i)) & 1);
   lteo_conv_encode(c, 40, d);
   lteo_cc_rm_sequence(40, seq);
-  for (int k = 0; k < 1920; k++) e[k] = d[seq[k % 120]];
-  lteo_gold((uint32_t)cell->cell_id, 1920, scr);
-  lteo_pbch_res(cell, g);
+  const int nre = lteo_pbch_res_n(cell, g), nb = 2 * nre;      /* 480 bits per radio frame, 432 with the extended prefix */
+  for (int k = 0; k < 4 * nb; k++) e[k] = d[seq[k % 120]];
+  lteo_gold((uint32_t)cell->cell_id, 4 * nb, scr);
   double a = 1.0 / sqrt(2.0);
   lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
-  for (int i = 0; i < 240; i += 2) {
+  for (int i = 0; i < nre; i += 2) {
     lteo_cd_t x[2];
     for (int j = 0; j < 2; j++) {
-      int b0 = e[480 * frame_idx + 2 * (i + j)] ^ scr[480 * frame_idx + 2 * (i + j)];
-      int b1 = e[480 * frame_idx + 2 * (i + j) + 1] ^ scr[480 * frame_idx + 2 * (i + j) + 1];
+      int b0 = e[nb * frame_idx + 2 * (i + j)] ^ scr[nb * frame_idx + 2 * (i + j)];
+      int b1 = e[nb * frame_idx + 2 * (i + j) + 1] ^ scr[nb * frame_idx + 2 * (i + j) + 1];
       x[j].re = (b0 ? -a : a); x[j].im = (b1 ? -a : a);
     }
     if (cell->nof_ports == 2) {
@@ -441,11 +483,11 @@ void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf, 
   int nsc = 12 * cell->nof_prb;
   int32_t g[240];
   lteo_cf_t d[240];
-  lteo_pbch_res(cell, g);
+  const int nre = lteo_pbch_res_n(cell, g);
   if (hyp_ports == 2) {
     const float sq2 = (float)sqrt(2.0);
     const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
-    for (int i = 0; i < 240; i += 2) {
+    for (int i = 0; i < nre; i += 2) {
       lteo_cf_t r0 = sf[g[i]], r1 = sf[g[i + 1]], h0 = ce0[g[i]], h1 = ce1[g[i]];
       float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
       float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
@@ -456,14 +498,14 @@ void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf, 
       d[i + 1].re = ((c_re - e_re) * sq2) / den; d[i + 1].im = ((c_im - e_im) * sq2) / den;
     }
   } else {
-    for (int i = 0; i < 240; i++) {
+    for (int i = 0; i < nre; i++) {
       lteo_cf_t y = sf[g[i]], h = ce[g[i]];
       float den = (h.re * h.re + h.im * h.im) + n0;
       d[i].re = (y.re * h.re + y.im * h.im) / den;
       d[i].im = (y.im * h.re - y.re * h.im) / den;
     }
   }
-  lteo_demod(d, 240, 2, llr480);
+  lteo_demod(d, nre, 2, llr480);
 }
 
 /* Blind MIB decode from one subframe 0: port hypotheses 1 then 2 (2 only when the estimator ran with two ports), for
@@ -474,17 +516,18 @@ void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf, 
 int lteo_pbch_decode(const lteo_cell_t *cell, const lteo_cf_t *sf, const lteo_cf_t *ce, float n0, uint8_t *mib24,
                      int *nof_ports, int *sfn_offset) {
   uint8_t scr[1920];
-  lteo_gold((uint32_t)cell->cell_id, 1920, scr);
+  const int nb = cell->cp ? 432 : 480;
+  lteo_gold((uint32_t)cell->cell_id, 4 * nb, scr);
   for (int hyp = 1; hyp <= (cell->nof_ports >= 2 ? 2 : 1); hyp++) {
     int16_t llr[480], des[480];
     lteo_pbch_llr(cell, hyp, sf, ce, n0, llr);
     for (int q = 0; q < 4; q++) {
-      for (int k = 0; k < 480; k++) des[k] = scr[480 * q + k] ? (int16_t)-llr[k] : llr[k];
+      for (int k = 0; k < nb; k++) des[k] = scr[nb * q + k] ? (int16_t)-llr[k] : llr[k];
       /* the PDCCH candidate decoder with E = 480 = 4 x 120: L such that 72 L = 480 does not exist, so call the pieces */
       int32_t seq[120], soft[120];
       lteo_cc_rm_sequence(40, seq);
       memset(soft, 0, sizeof(soft));
-      for (int k = 0; k < 480; k++) soft[seq[k % 120]] += des[k];
+      for (int k = 0; k < nb; k++) soft[seq[(nb * q + k) % 120]] += des[k];     /* the frame's place in the 4 nb-bit block */
       uint8_t bits[40];
       uint16_t rem = lteo_viterbi_crc16(soft, 24, bits);
       if (rem == pbch_crc_mask(hyp)) {

@@ -57,9 +57,10 @@ void lteo_sync_tx(const lteo_cell_t *cell, int sf_idx, lteo_cd_t *grid) {
   int8_t s[62];
   lteo_pss_seq(cell->cell_id % 3, p);
   lteo_sss_seq(cell->cell_id / 3, cell->cell_id % 3, sf_idx == 5, s);
+  const int lp = LTEO_NSLOT(cell->cp) - 1;          /* PSS: last symbol of slot 0 (6 or 5), SSS: the one before */
   for (int n = 0; n < 62; n++) {
-    grid[6 * nsc + k0 + n] = p[n];
-    grid[5 * nsc + k0 + n].re = s[n]; grid[5 * nsc + k0 + n].im = 0.0;
+    grid[lp * nsc + k0 + n] = p[n];
+    grid[(lp - 1) * nsc + k0 + n].re = s[n]; grid[(lp - 1) * nsc + k0 + n].im = 0.0;
   }
 }
 
@@ -148,11 +149,37 @@ int lteo_sss_detect(const lteo_cf_t *x, int peak_pos, int n_id_2, int *sf5, floa
 }
 
 /* the same at any LTE sampling rate: nfft-point transforms, the SSS symbol nfft + 9 nfft / 128 samples before the PSS */
+static int sss_detect_gap(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int gap, int *sf5, float *corr_out);
 int lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr_out) {
+  return sss_detect_gap(x, peak_pos, n_id_2, nfft, nfft + 9 * nfft / 128, sf5, corr_out);
+}
+
+/* Cyclic-prefix detection (SPEC.md 15.4; srsLTE's srslte_sync_detect_cp, reported at phch_recv.cc:189): the SSS symbol
+ * lies nfft + 9 nfft / 128 samples before the PSS with the normal prefix and nfft + nfft / 4 with the extended one.
+ * cp_mode 0 / 1 look at that one place; 2 tries both (each only if it lies inside the buffer) and keeps the larger
+ * metric, the normal prefix on a tie.  Returns N_id_1, or -1 if no hypothesis could be tested. */
+int lteo_sss_detect_cp(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int cp_mode, int *sf5, float *corr_out, int *cp_out) {
+  int bn = -1, b5 = 0, bcp = 0;
+  float best = 0.0f;
+  for (int hyp = 0; hyp < 2; hyp++) {
+    if (cp_mode != 2 && hyp != cp_mode) continue;
+    int gap = nfft + (hyp ? nfft / 4 : 9 * nfft / 128), s5 = 0;
+    float corr = 0.0f;
+    if (peak_pos < gap) continue;
+    int n1 = sss_detect_gap(x, peak_pos, n_id_2, nfft, gap, &s5, &corr);
+    if (bn < 0 || corr > best) { bn = n1; b5 = s5; best = corr; bcp = hyp; }
+  }
+  if (sf5) *sf5 = b5;
+  if (corr_out) *corr_out = best;
+  if (cp_out) *cp_out = bcp;
+  return bn;
+}
+
+static int sss_detect_gap(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int gap, int *sf5, float *corr_out) {
   lteo_cf_t *yp = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * 2 * nfft), *ys = yp + nfft;
   lteo_cd_t d[62];
   lteo_fft(x + peak_pos, yp, nfft);
-  lteo_fft(x + peak_pos - (nfft + 9 * nfft / 128), ys, nfft);
+  lteo_fft(x + peak_pos - gap, ys, nfft);
   lteo_pss_seq(n_id_2, d);
   float zr[62], zi[62];
   for (int i = 0; i < 62; i++) {

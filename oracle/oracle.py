@@ -405,9 +405,9 @@ def pdcch_find_dci(llr, nof_cce, sf_idx, rnti, nof_bits, common=False):
     return found, out, L.value, n.value
 
 
-def phich_index(nof_prb, I_lowest, n_dmrs, ng_x6=6):
+def phich_index(nof_prb, I_lowest, n_dmrs, ng_x6=6, cp=0):
     g, q = C.c_int(), C.c_int()
-    lib().lteo_phich_index(nof_prb, ng_x6, I_lowest, n_dmrs, C.byref(g), C.byref(q))
+    lib().lteo_phich_index_cp(nof_prb, ng_x6, cp, I_lowest, n_dmrs, C.byref(g), C.byref(q))
     return g.value, q.value
 
 
@@ -458,6 +458,15 @@ def sss_detect(x, peak_pos, n_id_2, nfft=128):
     corr = C.c_float()
     n1 = lib().lteo_sss_detect_n(_p(x), peak_pos, n_id_2, nfft, C.byref(sf5), C.byref(corr))
     return n1, sf5.value, np.float32(corr.value)
+
+
+def sss_detect_cp(x, peak_pos, n_id_2, nfft=128, cp_mode=2):
+    """cp_mode 0 / 1: normal / extended prefix only, 2: both; returns (n_id_1, sf5, corr, cp)"""
+    x = np.ascontiguousarray(x, np.complex64)
+    sf5, cp = C.c_int(), C.c_int()
+    corr = C.c_float()
+    n1 = lib().lteo_sss_detect_cp(_p(x), peak_pos, n_id_2, nfft, cp_mode, C.byref(sf5), C.byref(corr), C.byref(cp))
+    return n1, sf5.value, np.float32(corr.value), cp.value
 
 
 def mib_pack(nof_prb, phich_ext, ng_x6, sfn):

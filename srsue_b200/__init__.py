@@ -42,7 +42,7 @@ class SfDesc(C.Structure):
 class SyncResult(C.Structure):
     """srsue_gpu_sync_result_t"""
     _fields_ = [("peak_pos", C.c_int32), ("n_id_2", C.c_int32), ("n_id_1", C.c_int32), ("sf5", C.c_int32), ("valid", C.c_int32),
-                ("peak", C.c_float), ("mean_power", C.c_float), ("cfo", C.c_float), ("sss_corr", C.c_float)]
+                ("peak", C.c_float), ("mean_power", C.c_float), ("cfo", C.c_float), ("sss_corr", C.c_float), ("cp", C.c_int32)]
 
 
 class GpuError(RuntimeError):
@@ -130,11 +130,12 @@ class Context:
         _check(lib().srsue_gpu_tdec_run_all_host(self.h, _ptr(h_triples), n_cb, K, max_iter, crc_type, _ptr(h_bits),
                                                  _ptr(h_status)), "tdec_run_all_host")
 
-    def cell_search(self, d_iq, n_bufs, n_samples, stride, d_result, force_n_id_2=-1, first_pos=0, nfft=128):
-        lib().srsue_gpu_cell_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                                C.c_void_p]
-        _check(lib().srsue_gpu_cell_search(self.h, _ptr(d_iq), n_bufs, n_samples, stride, nfft, force_n_id_2, first_pos, _ptr(d_result),
-                                           _stream()),
+    def cell_search(self, d_iq, n_bufs, n_samples, stride, d_result, force_n_id_2=-1, first_pos=0, nfft=128, cp_mode=0):
+        """cp_mode 0: SSS behind a normal cyclic prefix, 1: extended, 2: both, the better one reported in result.cp"""
+        lib().srsue_gpu_cell_search_cp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_void_p]
+        _check(lib().srsue_gpu_cell_search_cp(self.h, _ptr(d_iq), n_bufs, n_samples, stride, nfft, force_n_id_2, first_pos, cp_mode,
+                                              _ptr(d_result), _stream()),
                "cell_search")
 
     def tdec_last_launch(self):

@@ -327,6 +327,7 @@ struct srsue_gpu_pdsch_plan {
   int32_t* d_pd_re4 = nullptr; int32_t* d_pd_src = nullptr; uint32_t* d_pd_scr = nullptr;
   std::map<int, int32_t*> d_pd_rm;   // D -> rate-matching order
   int32_t* d_pbch_re = nullptr; uint32_t* d_pbch_scr = nullptr; int32_t* d_pbch_rm = nullptr;   // PBCH tables, built on first use
+  int pbch_nre = 240;
 };
 
 extern "C" {
@@ -372,8 +373,14 @@ void srsue_gpu_ctx_destroy(srsue_gpu_ctx_t* ctx) {
 
 int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int n_bufs, int n_samples, long long stride, int nfft,
                           int force_n_id_2, int first_pos, srsue_gpu_sync_result_t* d_result, void* stream) {
+  return srsue_gpu_cell_search_cp(ctx, d_iq, n_bufs, n_samples, stride, nfft, force_n_id_2, first_pos, 0, d_result, stream);
+}
+
+int srsue_gpu_cell_search_cp(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int n_bufs, int n_samples, long long stride, int nfft,
+                             int force_n_id_2, int first_pos, int cp_mode, srsue_gpu_sync_result_t* d_result, void* stream) {
+  if (cp_mode < 0 || cp_mode > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "cell_search: cp_mode must be 0 (normal), 1 (extended) or 2 (detect)");
   const bool pow2 = nfft >= 128 && nfft <= 2048 && (nfft & (nfft - 1)) == 0;
-  if (!ctx || !d_iq || !d_result || n_bufs < 1 || !pow2 || n_samples < 2 * nfft + 9 * nfft / 128 || stride < n_samples ||
+  if (!ctx || !d_iq || !d_result || n_bufs < 1 || !pow2 || n_samples < 2 * nfft + (cp_mode ? nfft / 4 : 9 * nfft / 128) || stride < n_samples ||
       force_n_id_2 > 2 || first_pos < 0 || first_pos >= n_samples - (nfft - 1))
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "cell_search: bad arguments (nfft must be 128, 256, 512, 1024 or 2048)");
   static_assert(sizeof(srsue_gpu_sync_result_t) == sizeof(srsue_sync_result), "result layouts must match");
@@ -413,7 +420,7 @@ int srsue_gpu_cell_search(srsue_gpu_ctx_t* ctx, const srsue_gpu_cf_t* d_iq, int 
   a.iq = reinterpret_cast<const float2*>(d_iq); a.stride = stride; a.n_samples = n_samples; a.n_bufs = n_bufs;
   a.nfft = nfft; a.log2n = 0; while ((1 << a.log2n) < nfft) a.log2n++;
   a.force_n_id_2 = force_n_id_2 < 0 ? -1 : force_n_id_2;
-  a.first_pos = first_pos;
+  a.first_pos = first_pos; a.cp_mode = cp_mode;
   a.pss_time = it->second.first; a.pss_freq = ctx->d_pss_freq; a.sss = ctx->d_sss; a.tw = it->second.second;
   a.peak_key = ctx->d_peak_key; a.power_sum = ctx->d_power_sum; a.result = reinterpret_cast<srsue_sync_result*>(d_result);
   const int n_pos = n_samples - (nfft - 1);
@@ -944,8 +951,7 @@ int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_
   PLAN_CHECK(p, n_sf);
   if (!d_sf || !d_ce || !d_ack || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: null buffer");
   if (ng_x6 != 1 && ng_x6 != 3 && ng_x6 != 6 && ng_x6 != 12) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "ng_x6 must be 1, 3, 6 or 12");
-  if (p->cell.cp) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: spreading factor 2 of the extended cyclic prefix is not built");
-  if (n_group < 0 || n_group >= phich_groups(p->cell.nof_prb, ng_x6) || n_seq < 0 || n_seq > 7)
+  if (n_group < 0 || n_group >= (p->cell.cp ? 2 : 1) * phich_groups(p->cell.nof_prb, ng_x6) || n_seq < 0 || n_seq > (p->cell.cp ? 3 : 7))
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "phich_decode: group %d / sequence %d out of range", n_group, n_seq);
   PhichArgs a{};
   a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
@@ -954,6 +960,7 @@ int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_
   a.scramble = pcfich_scramble(p->cell, p->cfg.sf_idx) & 0xFFFu;     // the same c_init as the PCFICH (36.211 6.9.1)
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.n_seq = n_seq; a.noise_mode = noise_mode;
   a.noise_est = noise_est; a.k_sq2 = (float)std::sqrt(2.0);
+  a.ext = p->cell.cp; a.odd = n_group & 1;
   phich_kernel<<<(n_sf + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
@@ -965,12 +972,12 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
   PLAN_CHECK(p, n_sf);
   if (!d_sf || !d_ce || !d_result || !d_mib || (noise_mode && !d_meas)) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: null buffer");
   if (p->cfg.sf_idx != 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: the PBCH is in subframe 0 (plan has sf_idx %d)", p->cfg.sf_idx);
-  if (p->cell.cp) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pbch_decode: the 216-element PBCH of the extended cyclic prefix is not built");
   if (!p->d_pbch_re) {
     std::vector<int32_t> re(240), seq;
-    pbch_res(p->cell, re.data());
+    p->pbch_nre = pbch_res(p->cell, re.data());
+    re.resize(p->pbch_nre);
     std::vector<uint32_t> scr;
-    gold_packed((uint32_t)p->cell.cell_id, 1920, scr);
+    gold_packed((uint32_t)p->cell.cell_id, 8 * p->pbch_nre, scr);
     cc_rm_sequence(40, seq);
     CU_CHECK(upload(&p->d_pbch_re, re));
     CU_CHECK(upload(&p->d_pbch_scr, scr));
@@ -978,7 +985,7 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
   }
   PbchArgs a{};
   a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
-  a.re = p->d_pbch_re; a.scramble = p->d_pbch_scr; a.rm_seq = p->d_pbch_rm; a.result = d_result; a.mib = d_mib;
+  a.re = p->d_pbch_re; a.scramble = p->d_pbch_scr; a.rm_seq = p->d_pbch_rm; a.result = d_result; a.mib = d_mib; a.n_re = p->pbch_nre;
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.noise_mode = noise_mode; a.noise_est = noise_est;
   a.k_sqpsk = (float)(100.0 * std::sqrt(2.0)); a.k_sq2 = (float)std::sqrt(2.0);
   pbch_kernel<<<n_sf, 256, 0, (cudaStream_t)stream>>>(a);
@@ -988,8 +995,9 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
 }
 
 int srsue_gpu_host_pbch_res(const srsue_gpu_cell_t* cell, int32_t* g240) {
-  if (!cell || !g240 || cell->nof_prb < 6 || cell->cp) return SRSUE_GPU_ERROR_INVALID_INPUTS;
-  pbch_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, g240);
+  if (!cell || !g240 || cell->nof_prb < 6) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  const int n = pbch_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, g240);
+  for (int i = n; i < 240; i++) g240[i] = -1;       // extended cyclic prefix: 216 elements, the rest marked unused
   return 0;
 }
 
@@ -999,8 +1007,14 @@ int srsue_gpu_host_phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs,
   return 0;
 }
 
+int srsue_gpu_host_phich_index_cp(int nof_prb, int ng_x6, int cp, int I_lowest, int n_dmrs, int* n_group, int* n_seq) {
+  if (!n_group || !n_seq || nof_prb < 6 || I_lowest < 0 || n_dmrs < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  phich_index(nof_prb, ng_x6, I_lowest, n_dmrs, n_group, n_seq, cp ? 1 : 0);
+  return 0;
+}
+
 int srsue_gpu_host_phich_res(const srsue_gpu_cell_t* cell, int n_group, int32_t* k12) {
-  if (!cell || !k12 || n_group < 0 || cell->cp) return SRSUE_GPU_ERROR_INVALID_INPUTS;
+  if (!cell || !k12 || n_group < 0) return SRSUE_GPU_ERROR_INVALID_INPUTS;
   phich_res(CellCfg{cell->nof_prb, cell->nof_ports, cell->cell_id, cell->cp ? 1 : 0}, n_group, k12);
   return 0;
 }

@@ -191,6 +191,8 @@ struct PhichArgs {
   uint32_t scramble;         // 12 scrambling bits, LSB first
   int n_sf, nsc, nof_ports, n_seq, noise_mode;
   float noise_est, k_sq2;
+  int ext;                   // extended cyclic prefix: spreading factor 2, the group owns one half of every quadruplet
+  int odd;                   // ext: n_group & 1 (the second half)
 };
 __global__ void phich_kernel(const PhichArgs a);
 
@@ -198,8 +200,9 @@ struct PbchArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc] grids of subframes 0
   const float2* ce;          // [n_sf][ports][14 * nsc]
   const float* meas;         // [n_sf][5]
-  const int32_t* re;         // [240] grid index of the PBCH resource elements
-  const uint32_t* scramble;  // 1920 scrambling bits, packed LSB first
+  const int32_t* re;         // [n_re] grid index of the PBCH resource elements
+  const uint32_t* scramble;  // 8 n_re scrambling bits (four radio frames), packed LSB first
+  int n_re;                  // 240, or 216 with the extended cyclic prefix
   const int32_t* rm_seq;     // [120] rate-matching order for D = 40
   int32_t* result;           // [n_sf][4]: found, transmit ports, frame number mod 4, 0
   uint8_t* mib;              // [n_sf][24] MIB bits, one per byte
@@ -209,7 +212,7 @@ struct PbchArgs {
 __global__ void pbch_kernel(const PbchArgs a);
 
 // result of the cell search on one buffer (mirrors srsue_gpu_sync_result_t of the C ABI)
-struct srsue_sync_result { int32_t peak_pos, n_id_2, n_id_1, sf5, valid; float peak, mean_power, cfo, sss_corr; };
+struct srsue_sync_result { int32_t peak_pos, n_id_2, n_id_1, sf5, valid; float peak, mean_power, cfo, sss_corr; int32_t cp; };
 struct SyncArgs {
   const float2* iq;          // [n_bufs][stride] samples at 1.92 Msps
   long long stride;
@@ -217,6 +220,7 @@ struct SyncArgs {
   int nfft, log2n;           // samples per OFDM symbol at the buffer's sampling rate (128 at 1.92 Msps ... 2048)
   int force_n_id_2;          // -1: search the three roots, else only this one
   int first_pos;             // first sample offset searched (137 guarantees that the SSS symbol lies inside the buffer)
+  int cp_mode;               // SSS position: 0 normal cyclic prefix, 1 extended, 2 both (the better one is reported)
   const float2* pss_time;    // [3][nfft]
   const float2* pss_freq;    // [3][62]
   const int8_t* sss;         // [3][2][168][62]

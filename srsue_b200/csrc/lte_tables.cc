@@ -462,6 +462,7 @@ int phich_groups(int nof_prb, int ng_x6) { return (ng_x6 * nof_prb + 47) / 48; }
 
 void phich_res(const CellCfg& cell, int n_group, int32_t* k12) {
   const int n0 = 2 * cell.nof_prb;
+  if (cell.cp) n_group /= 2;       // extended cyclic prefix: groups 2m' and 2m'+1 share mapping unit m' (36.211 6.9.3)
   std::vector<uint8_t> taken(n0, 0);
   int32_t pc[16];
   pcfich_re(cell, pc);
@@ -475,21 +476,24 @@ void phich_res(const CellCfg& cell, int n_group, int32_t* k12) {
   }
 }
 
-void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq) {
-  const int g = phich_groups(nof_prb, ng_x6);
+void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq, int cp) {
+  // 36.213 9.1.2: N_group doubles and the sequence index is taken modulo 2 N_SF = 4 with the extended cyclic prefix
+  const int g = (cp ? 2 : 1) * phich_groups(nof_prb, ng_x6);
   *n_group = (I_lowest + n_dmrs) % g;
-  *n_seq = (I_lowest / g + n_dmrs) % 8;
+  *n_seq = (I_lowest / g + n_dmrs) % (cp ? 4 : 8);
 }
 
 // slot 1, symbols 0..3, the 72 central subcarriers, k first then l; CRS positions of ports 0..3 left out (symbols 0, 1)
-void pbch_res(const CellCfg& cell, int32_t* g240) {
-  const int nsc = 12 * cell.nof_prb, k0 = nsc / 2 - 36;
+// Returns the number of elements: 240, or 216 with the extended cyclic prefix (symbol 3 of the slot carries CRS too).
+int pbch_res(const CellCfg& cell, int32_t* g240) {
+  const int nsc = 12 * cell.nof_prb, k0 = nsc / 2 - 36, first = slot_symb(cell.cp);
   int n = 0;
   for (int l = 0; l < 4; l++)
     for (int k = 0; k < 72; k++) {
-      if (l < 2 && (k0 + k) % 3 == cell.cell_id % 3) continue;
-      g240[n++] = (7 + l) * nsc + k0 + k;
+      if ((l < 2 || (cell.cp && l == 3)) && (k0 + k) % 3 == cell.cell_id % 3) continue;
+      g240[n++] = (first + l) * nsc + k0 + k;
     }
+  return n;
 }
 
 // ---- synchronisation signals.  Replace the sequence generators behind srslte_ue_cellsearch_scan

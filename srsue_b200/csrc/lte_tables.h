@@ -80,13 +80,13 @@ void pss_freq(int n_id_2, float* d62x2);
 void pss_time(int n_id_2, float* t128x2);
 void pss_time_n(int n_id_2, int nfft, float* tx2);   // the same replica at any LTE sampling rate
 void sss_seq(int n_id_1, int n_id_2, int sf5, int8_t* d62);
-// PBCH (36.211 6.6.4): grid indices of the 240 resource elements in a subframe 0
-void pbch_res(const CellCfg& cell, int32_t* g240);
-// PHICH (36.211 6.9, 36.213 9.1.2; normal CP and duration): number of groups, the 12 subcarriers of a group in symbol 0,
+// PBCH (36.211 6.6.4): grid indices of the 240 (extended cyclic prefix: 216) resource elements in a subframe 0
+int pbch_res(const CellCfg& cell, int32_t* g240);
+// PHICH (36.211 6.9, 36.213 9.1.2; normal duration): number of groups (of mapping units with the extended prefix), the 12 subcarriers of a group in symbol 0,
 // and (group, sequence) of the indicator that answers an uplink transmission
 int phich_groups(int nof_prb, int ng_x6);
 void phich_res(const CellCfg& cell, int n_group, int32_t* k12);
-void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq);
+void phich_index(int nof_prb, int ng_x6, int I_lowest, int n_dmrs, int* n_group, int* n_seq, int cp = 0);
 // payload size of DCI format 1A (fmt = 0) or 1 (fmt = 1) for FDD, including the padding rules of 36.212 5.3.3.1
 int dci_format_sizeof(int fmt, int nof_prb);
 

@@ -355,7 +355,8 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
   const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
   const int n_hyp = a.nof_ports >= 2 ? 2 : 1;
   // hypothesis 1: every thread below 240 equalises one RE; hypothesis 2: every thread below 120 one Alamouti pair
-  if (tid < 240) {
+  const int nb = 2 * a.n_re;                     // coded bits per radio frame: 480, or 432 with the extended cyclic prefix
+  if (tid < a.n_re) {
     const int g = a.re[tid];
     const float2 r = y[g], h = h0p[g];
     const float den = __fadd_rn(dot_rn(h.x, h.x, h.y, h.y), n0);
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
     s_llr[0][2 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.x));
     s_llr[0][2 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.y));
   }
-  if (n_hyp == 2 && tid < 120) {
+  if (n_hyp == 2 && tid < a.n_re / 2) {
     const float2* h1p = h0p + 14 * a.nsc;
     const int g0 = a.re[2 * tid], g1 = a.re[2 * tid + 1];
     const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
@@ -385,10 +386,10 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
     int32_t* soft = s_soft[w];
     for (int i = lane; i < 120; i += 32) soft[i] = 0;
     __syncwarp();
-    for (int k = lane; k < 480; k += 32) {
-      const int bit = 480 * q + k;
+    for (int k = lane; k < nb; k += 32) {
+      const int bit = nb * q + k;                // place in the block of 4 nb bits: the circular buffer of 120 continues across frames
       const int v = s_llr[hyp][k];
-      atomicAdd(&soft[a.rm_seq[k % 120]], ((a.scramble[bit >> 5] >> (bit & 31)) & 1u) ? -v : v);
+      atomicAdd(&soft[a.rm_seq[bit % 120]], ((a.scramble[bit >> 5] >> (bit & 31)) & 1u) ? -v : v);
     }
     __syncwarp();
     const int rem = viterbi_crc16_warp(soft, 24, &s_surv[w][0][0], s_dec[w], lane);
@@ -440,15 +441,26 @@ __global__ void __launch_bounds__(128) phich_kernel(const PhichArgs a) {
 #pragma unroll
     for (int j = 0; j < 2; j++) {
       const int q = (i + j) & 3;
-      // w(q) of sequence n_seq & 3: {1,1,1,1}, {1,-1,1,-1}, {1,1,-1,-1}, {1,-1,-1,1}; sequences 4..7 are j times these
-      const int s = a.n_seq & 3;
-      const bool neg_w = (s == 1 && (q & 1)) || (s == 2 && (q & 2)) || (s == 3 && (q == 1 || q == 2));
       float tr, ti;
-      if (a.n_seq < 4) { tr = d[j].x; ti = d[j].y; } else { tr = d[j].y; ti = -d[j].x; }      // d * conj(j) = (im, -re)
-      const bool neg = neg_w != (((a.scramble >> (i + j)) & 1u) != 0);
+      bool neg, first;
+      if (a.ext) {
+        // N_SF = 2 (36.211 Table 6.9.1-2): [1 1], [1 -1], j [1 1], j [1 -1]; six spread symbols, element 2 (i / 4) + q % 2
+        if ((q >> 1) != a.odd) continue;
+        const int e = 2 * ((i + j) >> 2) + (q & 1);
+        if (a.n_seq < 2) { tr = d[j].x; ti = d[j].y; } else { tr = d[j].y; ti = -d[j].x; }
+        neg = ((a.n_seq & 1) && (q & 1)) != (((a.scramble >> e) & 1u) != 0);
+        first = (i + j) == 2 * a.odd;
+      } else {
+        // w(q) of sequence n_seq & 3: {1,1,1,1}, {1,-1,1,-1}, {1,1,-1,-1}, {1,-1,-1,1}; sequences 4..7 are j times these
+        const int s = a.n_seq & 3;
+        const bool neg_w = (s == 1 && (q & 1)) || (s == 2 && (q & 2)) || (s == 3 && (q == 1 || q == 2));
+        if (a.n_seq < 4) { tr = d[j].x; ti = d[j].y; } else { tr = d[j].y; ti = -d[j].x; }      // d * conj(j) = (im, -re)
+        neg = neg_w != (((a.scramble >> (i + j)) & 1u) != 0);
+        first = (i + j) == 0;
+      }
       if (neg) { tr = -tr; ti = -ti; }
       const float m = __fadd_rn(tr, ti);
-      metric = (i + j == 0) ? m : __fadd_rn(metric, m);
+      metric = first ? m : __fadd_rn(metric, m);
     }
   }
   a.ack[sf] = metric < 0.0f;

@@ -429,7 +429,7 @@ bool srslte_ue_dl_decode_phich(srslte_ue_dl_t* q, uint32_t sf_idx, uint32_t n_pr
   srsue_gpu_pdsch_plan_t* fp = front_plan(u, sf_idx, 1);
   if (!fp) return false;
   int n_group = 0, n_seq = 0;
-  phich_index(u->cell.nof_prb, u->ng_x6, (int)n_prb_lowest, (int)n_dmrs, &n_group, &n_seq);
+  phich_index(u->cell.nof_prb, u->ng_x6, (int)n_prb_lowest, (int)n_dmrs, &n_group, &n_seq, u->cell.cp);
   if (!u->d_cfi && cudaMalloc((void**)&u->d_cfi, 4 * sizeof(int32_t)) != cudaSuccess) return false;
   // srsLTE decodes the PHICH with the channel estimator's noise figure
   if (srsue_gpu_phich_decode(fp, 1, u->d_sf, u->d_ce, u->d_meas, 0.0f, 1, u->ng_x6, n_group, n_seq, u->d_cfi + 2, nullptr, u->stream)) return false;
@@ -472,7 +472,8 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
     agc_process(&q->ue_sync.agc, g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame);
   }
   if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_cell_search(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, 128, force, 0, g->d_res, g->stream)) return SRSLTE_ERROR;
+  // the SSS is looked for behind both cyclic-prefix lengths; every frame reports the better one (SPEC.md 15.4)
+  if (srsue_gpu_cell_search_cp(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, 128, force, 0, 2, g->d_res, g->stream)) return SRSLTE_ERROR;
   std::vector<srsue_gpu_sync_result_t> res(nf);
   cudaMemcpyAsync(res.data(), g->d_res, nf * sizeof(srsue_gpu_sync_result_t), cudaMemcpyDeviceToHost, g->stream);
   if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
@@ -485,11 +486,12 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
   for (const auto& kv : votes) if (kv.second > best_votes) { best_votes = kv.second; best_id = kv.first; }
   if (best_id < 0) return 0;
   double psr = 0, cfo = 0;
+  int ext_votes = 0;
   for (const auto& r : res)
-    if (r.valid && 3 * r.n_id_1 + r.n_id_2 == best_id && r.peak / r.mean_power >= q->detect_threshold) { psr += r.peak / r.mean_power; cfo += r.cfo; }
+    if (r.valid && 3 * r.n_id_1 + r.n_id_2 == best_id && r.peak / r.mean_power >= q->detect_threshold) { psr += r.peak / r.mean_power; cfo += r.cfo; ext_votes += r.cp ? 1 : 0; }
   std::memset(out, 0, sizeof(*out));
   out->cell_id = (uint32_t)best_id;
-  out->cp = SRSLTE_CP_NORM;
+  out->cp = 2 * ext_votes > best_votes ? SRSLTE_CP_EXT : SRSLTE_CP_NORM;      // the prefix most detections of this cell agree on
   out->peak = out->psr = (float)(psr / best_votes);
   out->mode = (float)best_votes / (float)nf;
   out->cfo = (float)(cfo / best_votes * 15000.0);
@@ -564,6 +566,7 @@ struct UeSyncGpu {
   int (*recv)(void*, void*, uint32_t, srslte_timestamp_t*) = nullptr;
   void* handler = nullptr;
   uint32_t cell_id = 0;
+  int cp = 0;                          // the cell's cyclic prefix: where the SSS lies in front of the PSS
   int nfft = 0, sf_len = 0, off_pss = 0, win = 0;
   bool tracking = false, sss_on_track = true;
   uint32_t sf_idx = 0;
@@ -583,7 +586,7 @@ struct UeSyncGpu {
 // one cell search on host samples: upload, search root n_id_2 from first_pos on, read the result back
 int sync_search(UeSyncGpu* g, const srsue_gpu_cf_t* x, int n_samples, int first_pos, srsue_gpu_sync_result_t* r) {
   if (cudaMemcpyAsync(g->d_iq, x, (size_t)n_samples * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
-  if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, n_samples, n_samples, g->nfft, (int)(g->cell_id % 3), first_pos, g->d_res, g->stream)) return SRSLTE_ERROR;
+  if (srsue_gpu_cell_search_cp(g->ctx, g->d_iq, 1, n_samples, n_samples, g->nfft, (int)(g->cell_id % 3), first_pos, g->cp, g->d_res, g->stream)) return SRSLTE_ERROR;
   cudaMemcpyAsync(r, g->d_res, sizeof(*r), cudaMemcpyDeviceToHost, g->stream);
   return cudaStreamSynchronize(g->stream) == cudaSuccess ? SRSLTE_SUCCESS : SRSLTE_ERROR;
 }
@@ -655,14 +658,14 @@ int sync_track(srslte_ue_sync_t* q, UeSyncGpu* g, srsue_gpu_cf_t* buf) {
 
 int srslte_ue_sync_init(srslte_ue_sync_t* q, srslte_cell_t cell, int (*recv_callback)(void*, void*, uint32_t, srslte_timestamp_t*),
                         void* stream_handler) {
-  if (!q || !recv_callback || cell.id > 503 || cell.cp != SRSLTE_CP_NORM) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (!q || !recv_callback || cell.id > 503 || (cell.cp != SRSLTE_CP_NORM && cell.cp != SRSLTE_CP_EXT)) return SRSLTE_ERROR_INVALID_INPUTS;
   const int n = symbol_sz((int)cell.nof_prb);
   if (n < 0 || n == 1536) return SRSLTE_ERROR_INVALID_INPUTS;      // the synchroniser needs a power-of-two symbol size
   std::memset(q, 0, sizeof(*q));
   srsue_gpu_ctx_t* ctx = shared_ctx();
   if (!ctx) return SRSLTE_ERROR;
   auto* g = new UeSyncGpu();
-  g->ctx = ctx; g->recv = recv_callback; g->handler = stream_handler; g->cell_id = cell.id;
+  g->ctx = ctx; g->recv = recv_callback; g->handler = stream_handler; g->cell_id = cell.id; g->cp = cell.cp == SRSLTE_CP_EXT ? 1 : 0;
   g->nfft = n; g->sf_len = 15 * n; g->off_pss = 832 * n / 128; g->win = n / 8;
   g->window.assign((size_t)10 * g->sf_len, srsue_gpu_cf_t{0.f, 0.f});
   g->tail.assign((size_t)g->win, srsue_gpu_cf_t{0.f, 0.f});
@@ -727,12 +730,13 @@ struct MibSyncGpu {
   int (*recv)(void*, void*, uint32_t, srslte_timestamp_t*) = nullptr;
   void* handler = nullptr;
   std::vector<srsue_gpu_cf_t> win; // two consecutive 5 ms frames
+  int cp = 0;
 };
 }  // namespace
 
 int srslte_ue_mib_sync_init(srslte_ue_mib_sync_t* q, uint32_t cell_id, srslte_cp_t cp,
                             int (*recv_callback)(void*, void*, uint32_t, srslte_timestamp_t*), void* stream_handler) {
-  if (!q || !recv_callback || cell_id > 503 || cp != SRSLTE_CP_NORM) return SRSLTE_ERROR_INVALID_INPUTS;
+  if (!q || !recv_callback || cell_id > 503 || (cp != SRSLTE_CP_NORM && cp != SRSLTE_CP_EXT)) return SRSLTE_ERROR_INVALID_INPUTS;
   std::memset(q, 0, sizeof(*q));
   auto* m = new MibSyncGpu();
   srslte_cell_t c{};
@@ -743,7 +747,7 @@ int srslte_ue_mib_sync_init(srslte_ue_mib_sync_t* q, uint32_t cell_id, srslte_cp
     delete m;
     return SRSLTE_ERROR;
   }
-  m->recv = recv_callback; m->handler = stream_handler;
+  m->recv = recv_callback; m->handler = stream_handler; m->cp = cp == SRSLTE_CP_EXT ? 1 : 0;
   m->win.resize(2 * kHalfFrame);
   q->cell_id = cell_id;
   q->gpu = m;
@@ -780,13 +784,14 @@ int srslte_ue_mib_sync_decode(srslte_ue_mib_sync_t* q, uint32_t max_frames_timeo
     agc_process(&q->ue_sync.agc, m->handler, m->win.data() + kHalfFrame, kHalfFrame);
     if (cudaMemcpyAsync(g->d_iq, m->win.data(), (size_t)2 * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
     // exactly one PSS period, starting at offset 832: the subframe that contains a candidate then begins inside the window
-    if (srsue_gpu_cell_search(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, 128, (int)(q->cell_id % 3), 832, g->d_res, g->stream)) return SRSLTE_ERROR;
+    if (srsue_gpu_cell_search_cp(g->ctx, g->d_iq, 1, 832 + kHalfFrame + 127, 2 * kHalfFrame, 128, (int)(q->cell_id % 3), 832, m->cp, g->d_res, g->stream)) return SRSLTE_ERROR;
     srsue_gpu_sync_result_t r;
     cudaMemcpyAsync(&r, g->d_res, sizeof(r), cudaMemcpyDeviceToHost, g->stream);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return SRSLTE_ERROR;
     if (!r.valid || 3 * r.n_id_1 + r.n_id_2 != (int)q->cell_id || r.sf5) continue;      // not our cell, or the PSS of subframe 5
     if (r.mean_power <= 0.f || r.peak / r.mean_power < 10.0f) continue;
-    // subframe 0 starts 832 samples before the PSS symbol body: CP 10 + 128, five more symbols of 9 + 128, CP 9
+    // subframe 0 starts 832 samples before the PSS symbol body, the last 128 samples of the 960-sample slot with either
+    // prefix (normal: CP 10 + 128, five more symbols of 9 + 128, CP 9)
     const int start = r.peak_pos - 832;
     if (start < 0 || start + 1920 > 2 * kHalfFrame) continue;
     const int rc = srslte_ue_mib_decode(&m->mib, reinterpret_cast<cf_t*>(m->win.data() + start), bch_payload, nof_tx_ports, sfn_offset);

@@ -58,7 +58,10 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
   __shared__ float2 s_z[62];
   __shared__ float s_best[128];
   __shared__ int s_idx[128];
-  const int N = a.nfft, gap = N + 9 * N / 128;                  // the SSS symbol starts one symbol + one cyclic prefix earlier
+  // the SSS symbol starts one symbol + one cyclic prefix before the PSS: 9 N / 128 samples of normal prefix, N / 4 of extended.
+  // cp_mode 0 / 1 look at that one place, 2 tries both and keeps the larger metric (SPEC.md 15.4; normal prefix on a tie)
+  const int N = a.nfft, gap_n = N + 9 * N / 128, gap_x = N + N / 4;
+  const int gap = a.cp_mode == 1 ? gap_x : gap_n;               // the smallest lead-in that allows a verdict
   float2* s_f0 = s_sync;
   float2* s_f1 = s_sync + N;
   const int buf = blockIdx.x, tid = threadIdx.x;
@@ -83,15 +86,21 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
     r->mean_power = (float)(a.power_sum[buf] / ((a.force_n_id_2 >= 0 ? 1.0 : 3.0) * (double)(n_pos - a.first_pos)));
     r->cfo = (float)(atan2((double)im, (double)re) / 3.14159265358979323846);
     r->valid = pos >= gap;
-    if (pos < gap) { r->n_id_1 = -1; r->sf5 = 0; r->sss_corr = 0.f; }
+    if (pos < gap) { r->n_id_1 = -1; r->sf5 = 0; r->sss_corr = 0.f; r->cp = 0; }
   }
   if (pos < gap) return;
+  float best_all = 0.f; int bc_all = -1, cp_all = 0;            // thread 0 only
+  for (int hyp = 0; hyp < 2; hyp++) {
+    if (a.cp_mode != 2 && hyp != a.cp_mode) continue;
+    const int gap_h = hyp ? gap_x : gap_n;
+    if (pos < gap_h) continue;                                  // uniform over the CTA
+    __syncthreads();
   // radix-2 decimation-in-time FFTs (SPEC.md 2) of the PSS symbol (s_f0) and the SSS symbol (s_f1), both by all threads
   const int shift = 32 - a.log2n;
   for (int i = tid; i < N; i += 128) {
     const int rv = (int)(__brev((unsigned)i) >> shift);
     s_f0[rv] = x[pos + i];
-    s_f1[rv] = x[pos - gap + i];
+    s_f1[rv] = x[pos - gap_h + i];
   }
   __syncthreads();
   for (int m = 2; m <= N; m <<= 1) {
@@ -136,8 +145,10 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
     float bv = s_best[0]; int bc = s_idx[0];
     for (int t = 1; t < 128; t++)
       if (s_idx[t] >= 0 && (s_best[t] > bv || (s_best[t] == bv && s_idx[t] < bc))) { bv = s_best[t]; bc = s_idx[t]; }
-    r->n_id_1 = bc % 168; r->sf5 = bc / 168; r->sss_corr = bv;
+    if (bc_all < 0 || bv > best_all) { best_all = bv; bc_all = bc; cp_all = hyp; }
   }
+  }
+  if (tid == 0) { r->n_id_1 = bc_all % 168; r->sf5 = bc_all / 168; r->sss_corr = best_all; r->cp = cp_all; }
 }
 
 }  // namespace srsue

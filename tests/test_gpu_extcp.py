@@ -265,3 +265,213 @@ def test_srslte_worker_sequence_extended_prefix(gpu, oracle):
     assert L.srslte_pdsch_last_noi(C.byref(q.pdsch)) == avg
     L.srslte_softbuffer_rx_free(C.byref(sb))
     L.srslte_ue_dl_free(C.byref(q))
+
+
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (25, 2, 77), (50, 1, 301), (100, 2, 0)])
+def test_phich_matches_oracle_extended_prefix(gpu, oracle, prb, ports, cid):
+    """spreading factor 2 (36.211 Table 6.9.1-2): two groups share a mapping unit, four sequences per group; decision
+    and float metric (bit-identical) for indicators in both halves of a unit, present and absent"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    ocell = o.make_cell(prb, ports, cid, cp=1)
+    cell = sg.make_cell(prb, ports, cid, cp=1)
+    sf_idx = cid % 10
+    units = (6 * prb + 47) // 48
+    sent = [(0, 0, 1), (0, 3, 0), (1, 2, 1), (1, 1, 0), (2 * units - 1, 0, 1), (2 * units - 2, 2, 0)]
+    probe = sent + [(0, 1, None), (1, 3, None)]
+    n = 3
+    iq = []
+    for i in range(n):
+        ocfg = o.make_cfg(ocell, sf_idx=sf_idx, cfi=2, qm=2, tbs=104 if prb == 6 else 1000, tm=ports)
+        iq.append(o.gen_subframe(ocell, ocfg, 8100 + i, 10.0 if i < 2 else -4.0, None, pcfich=True, phichs=sent)[1])
+    iq = np.stack(iq)
+    cfg = sg.make_cfg(cell, sf_idx=sf_idx, cfi=2, qm=2, tbs=0, tm=ports)
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+    d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((n, ports * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+    plan.ofdm_rx(n, d_iq, d_sf)
+    plan.chest(n, d_sf, d_ce, d_meas)
+    for g, q, ack in probe:
+        d_ack = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_met = torch.zeros(n, dtype=torch.float32, device="cuda")
+        plan.phich_decode(n, d_sf, d_ce, d_meas, 0.0, 1, g, q, d_ack, d_met)
+        torch.cuda.synchronize()
+        for i in range(n):
+            sf_o = o.ofdm_rx(prb, iq[i], cp=1)
+            ce_o, meas_o = o.chest(ocell, sf_idx, sf_o)
+            a_o, m_o = o.phich_decode(ocell, sf_idx, sf_o, ce_o, g, q, float(meas_o[0]))
+            assert int(d_ack[i]) == a_o and np.float32(d_met[i].item()) == m_o
+            if i < 2 and ack is not None:
+                assert a_o == ack
+    # (group, sequence) of an uplink grant, both prefixes (36.213 9.1.2)
+    L = sg.lib()
+    for I_low, dmrs in ((0, 0), (7, 3), (prb - 1, 5)):
+        g, q = C.c_int(), C.c_int()
+        assert L.srsue_gpu_host_phich_index_cp(prb, 6, 1, I_low, dmrs, C.byref(g), C.byref(q)) == 0
+        assert (g.value, q.value) == o.phich_index(prb, I_low, dmrs, 6, cp=1) == ((I_low + dmrs) % (2 * units), (I_low // (2 * units) + dmrs) % 4)
+    with pytest.raises(Exception):
+        plan.phich_decode(n, d_sf, d_ce, d_meas, 0.0, 1, 2 * units, 0, d_ack, d_met)
+    with pytest.raises(Exception):
+        plan.phich_decode(n, d_sf, d_ce, d_meas, 0.0, 1, 0, 4, d_ack, d_met)
+    plan.close()
+
+
+@pytest.mark.parametrize("prb,ports,cid", [(6, 1, 1), (6, 2, 77), (25, 2, 300), (100, 1, 503)])
+def test_pbch_matches_oracle_extended_prefix(gpu, oracle, prb, ports, cid):
+    """the 216-element PBCH: E = 1728 coded bits, 432 per radio frame, the circular buffer of 120 running on across the
+    four frames; MIB, port count and frame position equal the oracle's and what was sent"""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    ocell = o.make_cell(prb, ports, cid, cp=1)
+    cell = sg.make_cell(prb, 2, cid, cp=1)                 # the receiver estimates two ports and tries both hypotheses
+    ocell_rx = o.make_cell(prb, 2, cid, cp=1)
+    n = 5
+    iq, mibs = [], []
+    for i in range(n):
+        ocfg = o.make_cfg(ocell, sf_idx=0, cfi=2, qm=2, tbs=56 if prb == 6 else 1000, tm=ports)
+        mib = o.mib_pack(prb, 0, 6, 400 + i)
+        iq.append(o.gen_subframe(ocell, ocfg, 8200 + i, 9.0 if i < 4 else -8.0, None, pcfich=True, mib=(mib, i % 4))[1])
+        mibs.append(mib)
+    iq = np.stack(iq)
+    cfg = sg.make_cfg(cell, sf_idx=0, cfi=2, qm=2, tbs=0, tm=2)
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    d_iq = torch.from_numpy(iq.view(np.float32).reshape(n, -1)).cuda()
+    d_sf = torch.zeros((n, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((n, 2 * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((n, 5), dtype=torch.float32, device="cuda")
+    d_res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    d_mib = torch.zeros((n, 24), dtype=torch.uint8, device="cuda")
+    plan.ofdm_rx(n, d_iq, d_sf)
+    plan.chest(n, d_sf, d_ce, d_meas)
+    plan.pbch_decode(n, d_sf, d_ce, d_meas, 0.0, 1, d_res, d_mib)
+    torch.cuda.synchronize()
+    res, mib_g = d_res.cpu().numpy(), d_mib.cpu().numpy()
+    for i in range(n):
+        sf_o = o.ofdm_rx(prb, iq[i], cp=1)
+        ce_o, meas_o = o.chest(ocell_rx, 0, sf_o)
+        f, bits, p, q = o.pbch_decode(ocell_rx, sf_o, ce_o, float(meas_o[0]))
+        assert res[i, 0] == f
+        if f:
+            assert (res[i, 1], res[i, 2]) == (p, q) and np.array_equal(mib_g[i], bits)
+        if i < 4:
+            assert f == 1 and p == ports and q == i % 4 and np.array_equal(bits, mibs[i])
+    g = np.zeros(240, np.int32)
+    assert sg.lib().srsue_gpu_host_pbch_res(C.byref(cell), g.ctypes.data_as(C.c_void_p)) == 0
+    k = np.zeros(240, np.int32)
+    assert o.lib().lteo_pbch_res_n(C.byref(ocell), k.ctypes.data_as(C.c_void_p)) == 216
+    assert np.array_equal(g[:216], k[:216]) and (g[216:] == -1).all()
+    plan.close()
+
+
+def _half_frame(o, cell, first_sf, seed, snr, cfo, shift):
+    out = []
+    for i in range(5):
+        cfg = o.make_cfg(cell, sf_idx=first_sf + i, cfi=2, qm=2, tbs=56, tm=cell.nof_ports)
+        out.append(o.gen_subframe(cell, cfg, seed + i, snr, None, pcfich=True, sync=True)[1])
+    x = np.concatenate(out)
+    x = x * np.exp(2j * np.pi * cfo * np.arange(len(x)) / 128)
+    return np.roll(x, shift).astype(np.complex64)
+
+
+def test_cell_search_detects_the_cyclic_prefix(gpu, oracle):
+    """srsue_gpu_cell_search_cp: with cp_mode 2 the SSS is looked for behind both prefix lengths and the better metric
+    wins -- cells of both kinds, random timing and carrier offsets; every field equals the oracle's, and the prefix found
+    is the one transmitted at usable SNRs.  cp_mode 0 / 1 look at one place only."""
+    import torch
+    sg, ctx = gpu
+    o = oracle
+    rng = np.random.default_rng(12)
+    cases = []
+    for cid in (0, 1, 77, 150, 301, 503):
+        for cp in (0, 1):
+            cases.append((cid, cp, 5 * int(rng.integers(0, 2)), float(rng.choice([12.0, 4.0])), float(rng.uniform(-0.3, 0.3)),
+                          int(rng.integers(200, 8000))))
+    cases.append((33, 1, 0, -25.0, 0.0, 300))
+    bufs = np.stack([_half_frame(o, o.make_cell(6, 1 + (cid % 2), cid, cp=cp), first, 100 * cid + first, snr, cfo, shift)
+                     for cid, cp, first, snr, cfo, shift in cases])
+    n, ns = bufs.shape
+    d_iq = torch.from_numpy(bufs.view(np.float32).reshape(n, -1)).cuda()
+    for mode in (2, 0, 1):
+        d_res = torch.zeros(n * C.sizeof(sg.SyncResult), dtype=torch.uint8, device="cuda")
+        ctx.cell_search(d_iq, n, ns, ns, d_res, cp_mode=mode)
+        torch.cuda.synchronize()
+        res = (sg.SyncResult * n).from_buffer_copy(d_res.cpu().numpy().tobytes())
+        for i, (cid, cp, first, snr, cfo, shift) in enumerate(cases):
+            r, ref = res[i], o.pss_search(bufs[i])
+            assert (r.peak_pos, r.n_id_2) == (ref["pos"], ref["n_id_2"]) and np.float32(r.peak) == ref["peak"]
+            n1, sf5, corr, cp_o = o.sss_detect_cp(bufs[i], ref["pos"], ref["n_id_2"], 128, mode)
+            if n1 < 0:
+                assert r.valid == 0 and r.n_id_1 == -1
+                continue
+            assert r.valid == 1 and (r.n_id_1, r.sf5, r.cp) == (n1, sf5, cp_o) and np.float32(r.sss_corr) == corr
+            if snr > 0 and mode == 2:
+                assert r.cp == cp and 3 * r.n_id_1 + r.n_id_2 == cid and r.sf5 == (first == 5)
+
+
+def test_init_cell_sequence_extended_prefix(gpu, oracle):
+    """phch_recv::init_cell (phch_recv.cc:136-226) on an extended-prefix cell: the scan reports cp = SRSLTE_CP_EXT
+    (:189), srslte_ue_mib_sync_decode with that prefix finds a subframe 0 and decodes the 216-element PBCH"""
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import Cell
+    from tests.test_gpu_sync import UeSync
+    cid, ports, sfn0, cfo, shift = 218, 2, 406, 0.05, 6100
+    cell = o.make_cell(6, ports, cid, cp=1)
+    stream = []
+    for half in range(8):
+        sfn = sfn0 + half // 2
+        for i in range(5):
+            sf = 5 * (half % 2) + i
+            cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=56, tm=ports)
+            mib = (o.mib_pack(50, 0, 6, sfn), sfn % 4) if sf == 0 else None
+            stream.append(o.gen_subframe(cell, cfg, 1000 * half + i, 9.0, None, pcfich=True, sync=True, mib=mib)[1])
+    x = np.concatenate(stream)
+    x = np.roll(x * np.exp(2j * np.pi * cfo * np.arange(len(x)) / 128), shift).astype(np.complex64)
+    state = {"pos": 0}
+    RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p)
+
+    def recv(handler, data, nsamples, ts):
+        idx = (state["pos"] + np.arange(nsamples)) % len(x)
+        buf = np.ascontiguousarray(x[idx])
+        state["pos"] += nsamples
+        C.memmove(data, buf.ctypes.data, buf.nbytes)
+        return nsamples
+
+    cb = RECV(recv)
+
+    class Result(C.Structure):
+        _fields_ = [("cell_id", C.c_uint32), ("cp", C.c_int), ("peak", C.c_float), ("mode", C.c_float), ("psr", C.c_float), ("cfo", C.c_float)]
+
+    class CellSearch(C.Structure):
+        _fields_ = [("ue_sync", UeSync), ("nof_frames_to_scan", C.c_uint32), ("detect_threshold", C.c_float), ("gpu", C.c_void_p)]
+
+    class MibSync(C.Structure):
+        _fields_ = [("ue_sync", UeSync), ("cell_id", C.c_uint32), ("gpu", C.c_void_p)]
+
+    cs = CellSearch()
+    assert L.srslte_ue_cellsearch_init(C.byref(cs), cb, None) == 0
+    L.srslte_ue_cellsearch_set_nof_frames_to_scan(C.byref(cs), 6)
+    L.srslte_ue_cellsearch_set_threshold.argtypes = [C.c_void_p, C.c_float]
+    L.srslte_ue_cellsearch_set_threshold(C.byref(cs), 15.0)
+    found = (Result * 3)()
+    best = C.c_uint32(0)
+    assert L.srslte_ue_cellsearch_scan(C.byref(cs), found, C.byref(best)) > 0
+    assert found[best.value].cell_id == cid and found[best.value].cp == 1          # SRSLTE_CP_EXT
+    L.srslte_ue_cellsearch_free(C.byref(cs))
+    ms = MibSync()
+    assert L.srslte_ue_mib_sync_init(C.byref(ms), found[best.value].cell_id, found[best.value].cp, cb, None) == 0
+    payload = (C.c_uint8 * 24)()
+    nports, off = C.c_uint32(0), C.c_uint32(0)
+    assert L.srslte_ue_mib_sync_decode(C.byref(ms), 12, payload, C.byref(nports), C.byref(off)) == 1
+    L.srslte_ue_mib_sync_free(C.byref(ms))
+    out_cell, sfn = Cell(), C.c_uint32(0)
+    L.srslte_pbch_mib_unpack(payload, C.byref(out_cell), C.byref(sfn))
+    assert nports.value == ports and out_cell.nof_prb == 50 and out_cell.phich_resources == 2
+    assert sfn0 <= sfn.value + off.value <= sfn0 + 3
