@@ -44,7 +44,7 @@ typedef struct {
   int nof_prb;      /* 6,15,25,50,75,100 */
   int nof_ports;    /* 1 or 2 */
   int cell_id;      /* 0..503 */
-  int cp;           /* 0 = normal cyclic prefix (7 symbols per slot), 1 = extended (6 symbols per slot, SPEC.md 15) */
+  int cp;           /* 0 = normal cyclic prefix (7 symbols per slot), 1 = extended (6 symbols per slot, SPEC.md 15b) */
 } lteo_cell_t;
 /* Grids (sf_symbols, ce, TX grids) always have a stride of 14 symbols per port; with the extended cyclic prefix only
  * rows 0..11 are used. */
@@ -146,7 +146,7 @@ void  lteo_pss_time_n(int n_id_2, int nfft, lteo_cf_t *t);
 float lteo_pss_search_n(const lteo_cf_t *x, int n_samples, int nfft, int force_n_id_2, int first_pos, int *peak_pos, int *n_id_2,
                         float *cfo, float *mean_power);
 int   lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int *sf5, float *corr);
-/* cp_mode 0: normal prefix, 1: extended, 2: try both and report the better one in *cp (SPEC.md 15.4) */
+/* cp_mode 0: normal prefix, 1: extended, 2: try both and report the better one in *cp (SPEC.md 15b.7) */
 int   lteo_sss_detect_cp(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, int cp_mode, int *sf5, float *corr, int *cp);
 /* CFO correction (SPEC.md 14): y[n] = x[n] * T[(n * step mod 2^32) >> 20], T = 4096-entry unit circle */
 #define LTEO_CFO_TABLE_LOG2 12

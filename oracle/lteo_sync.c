@@ -154,7 +154,7 @@ int lteo_sss_detect_n(const lteo_cf_t *x, int peak_pos, int n_id_2, int nfft, in
   return sss_detect_gap(x, peak_pos, n_id_2, nfft, nfft + 9 * nfft / 128, sf5, corr_out);
 }
 
-/* Cyclic-prefix detection (SPEC.md 15.4; srsLTE's srslte_sync_detect_cp, reported at phch_recv.cc:189): the SSS symbol
+/* Cyclic-prefix detection (SPEC.md 15b.7; srsLTE's srslte_sync_detect_cp, reported at phch_recv.cc:189): the SSS symbol
  * lies nfft + 9 nfft / 128 samples before the PSS with the normal prefix and nfft + nfft / 4 with the extended one.
  * cp_mode 0 / 1 look at that one place; 2 tries both (each only if it lies inside the buffer) and keeps the larger
  * metric, the normal prefix on a tie.  Returns N_id_1, or -1 if no hypothesis could be tested. */

@@ -30,7 +30,7 @@ __device__ __forceinline__ float warp_sum_ordered(int n, int lane, F elem) {
 }  // namespace
 
 // EXT = extended cyclic prefix: 12 symbols, CRS in symbols 0, 3, 6, 9 (36.211 6.10.1.2: symbols 0 and N_symb - 3 of a slot),
-// symbols 10 and 11 extrapolated from (6, 9) as 12 and 13 are from (7, 11); same operations otherwise (SPEC.md 15)
+// symbols 10 and 11 extrapolated from (6, 9) as 12 and 13 are from (7, 11); same operations otherwise (SPEC.md 15b)
 template <bool EXT>
 __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   extern __shared__ __align__(16) float2 s_ch[];

@@ -472,7 +472,7 @@ int cellsearch_run(srslte_ue_cellsearch_t* q, int force, srslte_ue_cellsearch_re
     agc_process(&q->ue_sync.agc, g->handler, g->h_iq + (size_t)f * kHalfFrame, kHalfFrame);
   }
   if (cudaMemcpyAsync(g->d_iq, g->h_iq, (size_t)nf * kHalfFrame * sizeof(srsue_gpu_cf_t), cudaMemcpyHostToDevice, g->stream) != cudaSuccess) return SRSLTE_ERROR;
-  // the SSS is looked for behind both cyclic-prefix lengths; every frame reports the better one (SPEC.md 15.4)
+  // the SSS is looked for behind both cyclic-prefix lengths; every frame reports the better one (SPEC.md 15b.7)
   if (srsue_gpu_cell_search_cp(g->ctx, g->d_iq, (int)nf, kHalfFrame, kHalfFrame, 128, force, 0, 2, g->d_res, g->stream)) return SRSLTE_ERROR;
   std::vector<srsue_gpu_sync_result_t> res(nf);
   cudaMemcpyAsync(res.data(), g->d_res, nf * sizeof(srsue_gpu_sync_result_t), cudaMemcpyDeviceToHost, g->stream);

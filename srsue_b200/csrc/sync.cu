@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) sss_detect_kernel(const SyncArgs a) {
   __shared__ float s_best[128];
   __shared__ int s_idx[128];
   // the SSS symbol starts one symbol + one cyclic prefix before the PSS: 9 N / 128 samples of normal prefix, N / 4 of extended.
-  // cp_mode 0 / 1 look at that one place, 2 tries both and keeps the larger metric (SPEC.md 15.4; normal prefix on a tie)
+  // cp_mode 0 / 1 look at that one place, 2 tries both and keeps the larger metric (SPEC.md 15b.7; normal prefix on a tie)
   const int N = a.nfft, gap_n = N + 9 * N / 128, gap_x = N + N / 4;
   const int gap = a.cp_mode == 1 ? gap_x : gap_n;               // the smallest lead-in that allows a verdict
   float2* s_f0 = s_sync;

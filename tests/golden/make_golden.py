@@ -105,9 +105,41 @@ def cfo():
     print("cfo: steps", steps)
 
 
+EXT = dict(prb=6, ports=2, cid=77, cfi=2, rnti=0x1234, qm=2, tbs=56, sfn=413, phich=((0, 1, 1), (1, 2, 0), (1, 3, 1)))
+
+
+def extcp():
+    """extended cyclic prefix (SPEC.md 15b): a subframe 0 of a 1.4 MHz two-port cell with PSS / SSS, the 216-element PBCH,
+    PCFICH, three HARQ indicators in the two groups of one mapping unit and a PDSCH, behind 300 samples of lead-in"""
+    c = EXT
+    cell = o.make_cell(c["prb"], c["ports"], c["cid"], cp=1)
+    cfg = o.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    mib = o.mib_pack(25, 0, 6, c["sfn"])
+    tb, iq, _ = o.gen_subframe(cell, cfg, 1515, 9.0, None, pcfich=True, sync=True, mib=(mib, c["sfn"] % 4), phichs=list(c["phich"]))
+    sf = o.ofdm_rx(c["prb"], iq, cp=1)
+    ce, meas = o.chest(cell, 0, sf)
+    cfi, corr = o.pcfich_decode(cell, 0, sf, ce, meas[0])
+    ph = [o.phich_decode(cell, 0, sf, ce, g, q, float(meas[0])) for g, q, _ in c["phich"]]
+    f, bits, ports, off = o.pbch_decode(cell, sf, ce, float(meas[0]))
+    rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, float(meas[0]), 4, want=True)
+    x = np.concatenate([iq[-300:], iq])
+    pk = o.pss_search(x)
+    n1, sf5, scorr, cp = o.sss_detect_cp(x, pk["pos"], pk["n_id_2"], 128, 2)
+    nre = len(o.pdsch_re_list(cell, cfg))
+    np.savez_compressed(os.path.join(OUT, "extcp.npz"), iq=iq, tb=tb, sf=sf[:12 * 72], ce=ce[:, :12 * 72], meas=meas, cfi=np.array([cfi]),
+                        corr=corr, phich_ack=np.array([a for a, _ in ph], np.int32), phich_metric=np.array([m for _, m in ph], np.float32),
+                        pbch=np.array([f, ports, off], np.int32), mib=bits, mib_sent=mib, e=dbg["e"][:nre * c["qm"]], payload=pl,
+                        rc=np.array([rc]), sync=np.array([pk["pos"], pk["n_id_2"], n1, sf5, cp], np.int32),
+                        sync_f=np.array([pk["peak"], scorr], np.float32))
+    print("extcp: cfi", cfi, "phich", ph, "pbch", f, ports, off, "rc", rc, "sync", pk["pos"], pk["n_id_2"], n1, sf5, cp)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfo":
         cfo()
+    elif len(sys.argv) > 1 and sys.argv[1] == "extcp":
+        extcp()
     else:
         main()
         cfo()
+        extcp()

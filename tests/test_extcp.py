@@ -2,7 +2,7 @@
 initialised with carries it, phch_worker.cc:74): the oracle's geometry against independent constructions written from
 36.211 (6 symbols per slot, 512-sample prefixes, CRS in symbols 0 and 3 of a slot, N_CP = 0 in the CRS c_init,
 PSS/SSS/PBCH positions, the four-symbol control region with CRS in symbol 3), TX -> RX round trips, and the library's
-host-side tables against the oracle.  SPEC.md section 15.  CPU only."""
+host-side tables against the oracle.  SPEC.md section 15b.  CPU only."""
 import ctypes as C
 
 import numpy as np

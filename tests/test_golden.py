@@ -201,3 +201,88 @@ def test_gpu_reproduces_pdsch_golden(gpu):
     assert np.array_equal(t.cpu().numpy(), pv["cfg1_softbuf"])
     assert np.array_equal(d_pl.cpu().numpy()[0], pv["cfg1_payload"]) and d_st.cpu().numpy()[0, 0] == 1
     plan.close()
+
+
+EXT = dict(prb=6, ports=2, cid=77, cfi=2, rnti=0x1234, qm=2, tbs=56, phich=((0, 1), (1, 2), (1, 3)))
+
+
+def test_oracle_reproduces_extended_prefix_golden(oracle):
+    """tests/golden/extcp.npz (make_golden.py extcp): one subframe 0 of an extended-prefix cell through every stage"""
+    o = oracle
+    v = np.load(os.path.join(G, "extcp.npz"))
+    c = EXT
+    cell = o.make_cell(c["prb"], c["ports"], c["cid"], cp=1)
+    cfg = o.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    sf = o.ofdm_rx(c["prb"], v["iq"], cp=1)
+    ce, meas = o.chest(cell, 0, sf)
+    assert np.array_equal(sf[:12 * 72], v["sf"]) and np.array_equal(ce[:, :12 * 72], v["ce"]) and np.array_equal(meas, v["meas"])
+    cfi, corr = o.pcfich_decode(cell, 0, sf, ce, meas[0])
+    assert cfi == int(v["cfi"][0]) == c["cfi"] and np.array_equal(corr, v["corr"])
+    for i, (g, q) in enumerate(c["phich"]):
+        a, m = o.phich_decode(cell, 0, sf, ce, g, q, float(meas[0]))
+        assert a == v["phich_ack"][i] and m == v["phich_metric"][i]
+    f, bits, ports, off = o.pbch_decode(cell, sf, ce, float(meas[0]))
+    assert [f, ports, off] == v["pbch"].tolist() and np.array_equal(bits, v["mib"]) and np.array_equal(bits, v["mib_sent"])
+    rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, float(meas[0]), 4, want=True)
+    assert rc == int(v["rc"][0]) == 0 and np.array_equal(pl, v["payload"]) and np.array_equal(pl, v["tb"])
+    assert np.array_equal(dbg["e"][:len(v["e"])], v["e"])
+    x = np.concatenate([v["iq"][-300:], v["iq"]])
+    pk = o.pss_search(x)
+    n1, sf5, scorr, cp = o.sss_detect_cp(x, pk["pos"], pk["n_id_2"], 128, 2)
+    assert [pk["pos"], pk["n_id_2"], n1, sf5, cp] == v["sync"].tolist() and cp == 1 and 3 * n1 + pk["n_id_2"] == c["cid"]
+    assert pk["peak"] == v["sync_f"][0] and scorr == v["sync_f"][1]
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_extended_prefix_golden(gpu):
+    import ctypes as C
+    import torch
+    sg, ctx = gpu
+    v = np.load(os.path.join(G, "extcp.npz"))
+    c = EXT
+    cell = sg.make_cell(c["prb"], c["ports"], c["cid"], cp=1)
+    cfg = sg.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    plan = sg.PdschPlan(ctx, cell, cfg, 1)
+    I = plan.info
+    d_iq = torch.from_numpy(v["iq"].view(np.float32).reshape(1, -1)).cuda()
+    d_sf = torch.zeros((1, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((1, 2 * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((1, 5), dtype=torch.float32, device="cuda")
+    d_cfi = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_corr = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    d_sb = torch.zeros((1, I.sb_sf_stride), dtype=torch.int16, device="cuda")
+    d_e = torch.zeros((1, I.G), dtype=torch.int16, device="cuda")
+    d_res = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    d_mib = torch.zeros((1, 24), dtype=torch.uint8, device="cuda")
+    d_pl = torch.zeros((1, I.payload_stride), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    plan.ofdm_rx(1, d_iq, d_sf)
+    plan.chest(1, d_sf, d_ce, d_meas)
+    plan.pcfich_decode(1, d_sf, d_ce, d_meas, 0.0, 1, d_cfi, d_corr)
+    plan.pbch_decode(1, d_sf, d_ce, d_meas, 0.0, 1, d_res, d_mib)
+    plan.pdsch_llr(1, d_sf, d_ce, d_meas, 0.0, 1, 0, d_sb, None, d_e)
+    plan.decode_batch(1, d_iq, 0.0, 1, 4, d_pl, d_st)
+    torch.cuda.synchronize()
+    sf_g = d_sf.cpu().numpy().view(np.complex64)[0]
+    ce_g = d_ce.cpu().numpy().view(np.complex64).reshape(2, -1)
+    assert np.array_equal(sf_g[:12 * 72], v["sf"]) and np.array_equal(ce_g[:, :12 * 72], v["ce"])
+    assert np.allclose(d_meas.cpu().numpy()[0], v["meas"], rtol=1e-5)
+    assert int(d_cfi.cpu()[0]) == int(v["cfi"][0]) and np.array_equal(d_corr.cpu().numpy()[0], v["corr"])
+    assert d_res.cpu().numpy()[0, :3].tolist() == v["pbch"].tolist() and np.array_equal(d_mib.cpu().numpy()[0], v["mib"])
+    assert np.array_equal(d_e.cpu().numpy()[0, :len(v["e"])], v["e"])
+    assert int(d_st.cpu()[0, 0]) == 1 and np.array_equal(d_pl.cpu().numpy()[0, :len(v["payload"])], v["payload"])
+    for i, (g, q) in enumerate(c["phich"]):
+        d_ack = torch.zeros(1, dtype=torch.int32, device="cuda")
+        d_met = torch.zeros(1, dtype=torch.float32, device="cuda")
+        plan.phich_decode(1, d_sf, d_ce, d_meas, 0.0, 1, g, q, d_ack, d_met)
+        torch.cuda.synchronize()
+        assert int(d_ack[0]) == v["phich_ack"][i] and np.float32(d_met[0].item()) == v["phich_metric"][i]
+    x = np.concatenate([v["iq"][-300:], v["iq"]])
+    d_x = torch.from_numpy(x.view(np.float32).reshape(1, -1)).cuda()
+    d_sr = torch.zeros(C.sizeof(sg.SyncResult), dtype=torch.uint8, device="cuda")
+    ctx.cell_search(d_x, 1, len(x), len(x), d_sr, cp_mode=2)
+    torch.cuda.synchronize()
+    r = sg.SyncResult.from_buffer_copy(d_sr.cpu().numpy().tobytes())
+    assert [r.peak_pos, r.n_id_2, r.n_id_1, r.sf5, r.cp] == v["sync"].tolist()
+    assert np.float32(r.peak) == v["sync_f"][0] and np.float32(r.sss_corr) == v["sync_f"][1]
+    plan.close()

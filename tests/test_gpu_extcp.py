@@ -1,4 +1,4 @@
-"""Extended cyclic prefix on the device (SPEC.md 15): OFDM demodulation, channel estimate, equaliser / demapper / rate
+"""Extended cyclic prefix on the device (SPEC.md 15b): OFDM demodulation, channel estimate, equaliser / demapper / rate
 de-matcher, the whole PDSCH chain, PCFICH + PDCCH search, the batching layer and the srsLTE-shaped worker sequence on
 cells with cp = SRSLTE_CP_EXT -- every stage against the CPU oracle, floats bit-identical, integers bit-exact.
 The cell's prefix reaches the worker at /root/reference/ue/src/phy/phch_worker.cc:74 (srslte_ue_dl_init(&ue_dl, cell))

@@ -229,8 +229,10 @@ def test_pss_sss_at_the_cells_own_rate(gpu, oracle, prb, nfft):
         assert abs(r.peak_pos - exp) <= 2 and 3 * r.n_id_1 + r.n_id_2 == cid and r.sf5 == i and abs(r.cfo - 0.07) < 0.06
 
 
-def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle):
-    """srslte_ue_sync_zerocopy (phch_recv.cc:322) on a continuous 5 MHz stream that starts at an arbitrary sample, loses
+@pytest.mark.parametrize("cp", [0, 1])
+def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle, cp):
+    """(both cyclic prefixes: the SSS check of the tracker looks where the cell's prefix puts it)
+    srslte_ue_sync_zerocopy (phch_recv.cc:322) on a continuous 5 MHz stream that starts at an arbitrary sample, loses
     two samples at one point and repeats one at another (sampling-clock drift): 0 while searching, then exactly one aligned
     subframe per call with the right subframe index, re-aligned within a few subframes after each slip"""
     sg, ctx = gpu
@@ -239,7 +241,7 @@ def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle):
     from tests.srslte_ctypes import Cell
     prb, nfft, cid = 25, 512, 183
     sf_len = 15 * nfft
-    cell = o.make_cell(prb, 1, cid)
+    cell = o.make_cell(prb, 1, cid, cp=cp)
     sfs = []
     for sf in range(10):
         cfg = o.make_cfg(cell, sf_idx=sf, cfi=2, qm=2, tbs=1000, tm=1)
@@ -265,7 +267,7 @@ def test_ue_sync_finds_tracks_and_follows_timing_slips(gpu, oracle):
 
     cb = RECV(recv)
     q = UeSync()
-    c = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=cid, cp=0, phich_length=0, phich_resources=2)
+    c = Cell(nof_prb=prb, nof_ports=1, bw_idx=0, id=cid, cp=cp, phich_length=0, phich_resources=2)
     assert L.srslte_ue_sync_init(C.byref(q), c, cb, None) == 0
     buf = np.zeros(sf_len, np.complex64)
     delivered, zeros = [], 0
