@@ -42,12 +42,16 @@ typedef struct { double re, im; } lteo_cd_t;
 
 typedef struct {
   int nof_prb;      /* 6,15,25,50,75,100 */
-  int nof_ports;    /* 1 or 2 */
+  int nof_ports;    /* 1, 2 or 4 */
   int cell_id;      /* 0..503 */
   int cp;           /* 0 = normal cyclic prefix (7 symbols per slot), 1 = extended (6 symbols per slot, SPEC.md 15b) */
 } lteo_cell_t;
 /* Grids (sf_symbols, ce, TX grids) always have a stride of 14 symbols per port; with the extended cyclic prefix only
  * rows 0..11 are used. */
+/* Transmit diversity (36.211 6.3.4.3): Alamouti pair number `pair` of a mapped sequence goes out on ports (0, 1) of a
+ * two-port cell; with four ports even pairs use ports (0, 2) and odd pairs ports (1, 3) (SFBC-FSTD).  SPEC.md 15c. */
+#define LTEO_DIV_PA(np, pair) ((np) == 4 ? ((pair) & 1) : 0)
+#define LTEO_DIV_PB(np, pair) ((np) == 4 ? 2 + ((pair) & 1) : 1)
 #define LTEO_NSYMB(cp) ((cp) ? 12 : 14)
 #define LTEO_NSLOT(cp) ((cp) ? 6 : 7)
 

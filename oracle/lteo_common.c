@@ -316,8 +316,14 @@ int lteo_cb_E(const lteo_cbsegm_t *s, int G, int qm, int nl, int r) {
  * 36.211 6.10.1.2) */
 int lteo_crs_positions(const lteo_cell_t *cell, int port, int l, int32_t *k_out) {
   int nslot = LTEO_NSLOT(cell->cp), ls = l % nslot;
-  if (ls != 0 && ls != nslot - 3) return 0;
-  int v = (port == 0) ? (ls == 0 ? 0 : 3) : (ls == 0 ? 3 : 0);
+  int v;
+  if (port >= 2) {                     /* ports 2 / 3: symbol 1 of each slot, v = 3 (n_s mod 2) and 3 + 3 (n_s mod 2) */
+    if (ls != 1) return 0;
+    v = (3 * (l / nslot) + (port == 3 ? 3 : 0)) % 6;
+  } else {
+    if (ls != 0 && ls != nslot - 3) return 0;
+    v = (port == 0) ? (ls == 0 ? 0 : 3) : (ls == 0 ? 3 : 0);
+  }
   int off = (v + cell->cell_id % 6) % 6;
   for (int m = 0; m < 2 * cell->nof_prb; m++) k_out[m] = 6 * m + off;
   return 2 * cell->nof_prb;
@@ -370,10 +376,10 @@ int lteo_pdsch_re_list(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, int
   int c_lo = nsc / 2 - 36, c_hi = nsc / 2 + 36;       /* central 72 subcarriers */
   const int nslot = LTEO_NSLOT(cell->cp);
   for (int l = lstart; l < 2 * nslot; l++) {
-    int ls = l % nslot, crs = (ls == 0 || ls == nslot - 3);
+    int ls = l % nslot, crs = (ls == 0 || ls == nslot - 3 || (cell->nof_ports == 4 && ls == 1));
     int o0 = -1, o1 = -1;
     if (crs) {
-      int v0 = (ls == 0) ? 0 : 3;
+      int v0 = (ls == 0) ? 0 : 3;          /* symbol 1 (ports 2 / 3): both offsets v and v + 3 are taken, so v0 does not matter */
       o0 = (v0 + cell->cell_id % 6) % 6;
       if (cell->nof_ports > 1) o1 = (o0 + 3) % 6;
     }

@@ -25,7 +25,7 @@ int lteo_phich_groups(int nof_prb, int ng_x6) { return (ng_x6 * nof_prb + 47) / 
  * (subcarrier k' ascending, then symbol l'): reg_k/reg_l = first subcarrier and symbol of each.  Symbol 0 holds
  * 2 REGs of 6 REs per PRB (4 data REs, the CRS positions of ports 0/1 skipped), the other control symbols 3 REGs
  * of 4 REs per PRB (1 or 2 antenna ports) -- except symbol 3 under the extended cyclic prefix (a four-symbol control
- * region at <= 10 PRB), which carries CRS and is laid out like symbol 0.  The 4 PCFICH REGs and the 3 REGs of every PHICH group (normal PHICH
+ * region at <= 10 PRB) and symbol 1 of a four-port cell (CRS of ports 2 / 3), which are laid out like symbol 0.  The 4 PCFICH REGs and the 3 REGs of every PHICH group (normal PHICH
  * duration: all in symbol 0, 36.211 6.9.3) are excluded.  Returns the number of REGs.
  */
 int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k, int32_t *reg_l) {
@@ -47,7 +47,7 @@ int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k,
   for (int k = 0; k < nsc; k += 2) {         /* REG starts are multiples of 6 (symbol 0) or 4 (others) */
     for (int l = 0; l < nsym; l++) {
       if (l == 0) { if (k % 6 == 0 && !used[k / 6]) { reg_k[n] = k; reg_l[n] = 0; n++; } }
-      else if (cell->cp && l == 3) { if (k % 6 == 0) { reg_k[n] = k; reg_l[n] = l; n++; } }
+      else if ((cell->cp && l == 3) || (cell->nof_ports == 4 && l == 1)) { if (k % 6 == 0) { reg_k[n] = k; reg_l[n] = l; n++; } }
       else if (k % 4 == 0) { reg_k[n] = k; reg_l[n] = l; n++; }
     }
   }
@@ -57,7 +57,7 @@ int lteo_pdcch_regs(const lteo_cell_t *cell, int cfi, int ng_x6, int32_t *reg_k,
 
 /* the 4 data subcarriers of a REG */
 void lteo_reg_res(const lteo_cell_t *cell, int k0, int l, int32_t *k4) {
-  if (l == 0 || (cell->cp && l == 3)) { for (int j = 0, n = 0; j < 6; j++) if ((k0 + j) % 3 != cell->cell_id % 3) k4[n++] = k0 + j; }
+  if (l == 0 || (cell->cp && l == 3) || (cell->nof_ports == 4 && l == 1)) { for (int j = 0, n = 0; j < 6; j++) if ((k0 + j) % 3 != cell->cell_id % 3) k4[n++] = k0 + j; }
   else for (int j = 0; j < 4; j++) k4[j] = k0 + j;
 }
 
@@ -167,9 +167,11 @@ int lteo_pdcch_extract_llr(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_
     int32_t k4[4];
     lteo_cf_t d[4];
     lteo_reg_res(cell, rk[m], rl[m], k4);
-    const lteo_cf_t *y = sf + rl[m] * nsc, *h0p = ce + rl[m] * nsc, *h1p = ce + 14 * nsc + rl[m] * nsc;
-    if (cell->nof_ports == 2) {
+    const lteo_cf_t *y = sf + rl[m] * nsc, *h0p = ce + rl[m] * nsc, *h1p;
+    if (cell->nof_ports >= 2) {
       for (int i = 0; i < 4; i += 2) {
+        h0p = ce + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc + rl[m] * nsc;
+        h1p = ce + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc + rl[m] * nsc;
         lteo_cf_t r0 = y[k4[i]], r1 = y[k4[i + 1]], h0 = h0p[k4[i]], h1 = h1p[k4[i]];
         float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
         float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
@@ -354,8 +356,12 @@ void lteo_phich_tx(const lteo_cell_t *cell, int sf_idx, int ng_x6, int n_group, 
     for (int i = 0; i < 3; i++) { d[4 * i + 2 * (n_group & 1)] = d6[2 * i]; d[4 * i + 2 * (n_group & 1) + 1] = d6[2 * i + 1]; }
   }
   lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
-  if (cell->nof_ports == 2) {
+  if (cell->nof_ports >= 2) {
     for (int i = 0; i < 12; i += 2) {
+      /* four ports (36.211 6.9.2): quadruplet i / 4 goes out on ports (0, 2) or (1, 3) as a whole, alternating with
+       * i / 4 + n_group (normal prefix) or i / 4 + n_group / 2 (extended) */
+      const int par = i / 4 + (cell->cp ? n_group / 2 : n_group);
+      g0 = grid + (size_t)LTEO_DIV_PA(cell->nof_ports, par) * 14 * nsc; g1 = grid + (size_t)LTEO_DIV_PB(cell->nof_ports, par) * 14 * nsc;
       g0[k[i]].re += d[i].re * a;          g0[k[i]].im += d[i].im * a;
       g1[k[i]].re += -d[i + 1].re * a;     g1[k[i]].im += d[i + 1].im * a;
       g0[k[i + 1]].re += d[i + 1].re * a;  g0[k[i + 1]].im += d[i + 1].im * a;
@@ -376,10 +382,11 @@ int lteo_phich_decode(const lteo_cell_t *cell, int sf_idx, int ng_x6, const lteo
   lteo_cf_t d[12];
   lteo_phich_res(cell, ng_x6, n_group, k);
   lteo_gold(((uint32_t)(sf_idx + 1) * (uint32_t)(2 * cell->cell_id + 1) << 9) + (uint32_t)cell->cell_id, 12, c);
-  if (cell->nof_ports == 2) {
+  if (cell->nof_ports >= 2) {
     const float sq2 = (float)sqrt(2.0);
-    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
     for (int i = 0; i < 12; i += 2) {
+      const int par = i / 4 + (cell->cp ? n_group / 2 : n_group);
+      const lteo_cf_t *ce0 = ce + (size_t)LTEO_DIV_PA(cell->nof_ports, par) * 14 * nsc, *ce1 = ce + (size_t)LTEO_DIV_PB(cell->nof_ports, par) * 14 * nsc;
       lteo_cf_t r0 = sf[k[i]], r1 = sf[k[i + 1]], h0 = ce0[k[i]], h1 = ce1[k[i]];
       float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
       float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
@@ -466,7 +473,8 @@ void lteo_pbch_tx(const lteo_cell_t *cell, const uint8_t *mib24, int frame_idx, 
       int b1 = e[nb * frame_idx + 2 * (i + j) + 1] ^ scr[nb * frame_idx + 2 * (i + j) + 1];
       x[j].re = (b0 ? -a : a); x[j].im = (b1 ? -a : a);
     }
-    if (cell->nof_ports == 2) {
+    if (cell->nof_ports >= 2) {
+      g0 = grid + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc; g1 = grid + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc;
       g0[g[i]].re = x[0].re * a;      g0[g[i]].im = x[0].im * a;
       g1[g[i]].re = -x[1].re * a;     g1[g[i]].im = x[1].im * a;
       g0[g[i + 1]].re = x[1].re * a;  g0[g[i + 1]].im = x[1].im * a;
@@ -484,10 +492,10 @@ void lteo_pbch_llr(const lteo_cell_t *cell, int hyp_ports, const lteo_cf_t *sf, 
   int32_t g[240];
   lteo_cf_t d[240];
   const int nre = lteo_pbch_res_n(cell, g);
-  if (hyp_ports == 2) {
+  if (hyp_ports >= 2) {
     const float sq2 = (float)sqrt(2.0);
-    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
     for (int i = 0; i < nre; i += 2) {
+      const lteo_cf_t *ce0 = ce + (size_t)LTEO_DIV_PA(hyp_ports, i / 2) * 14 * nsc, *ce1 = ce + (size_t)LTEO_DIV_PB(hyp_ports, i / 2) * 14 * nsc;
       lteo_cf_t r0 = sf[g[i]], r1 = sf[g[i + 1]], h0 = ce0[g[i]], h1 = ce1[g[i]];
       float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
       float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;
@@ -518,7 +526,7 @@ int lteo_pbch_decode(const lteo_cell_t *cell, const lteo_cf_t *sf, const lteo_cf
   uint8_t scr[1920];
   const int nb = cell->cp ? 432 : 480;
   lteo_gold((uint32_t)cell->cell_id, 4 * nb, scr);
-  for (int hyp = 1; hyp <= (cell->nof_ports >= 2 ? 2 : 1); hyp++) {
+  for (int hyp = 1; hyp <= cell->nof_ports; hyp *= 2) {      /* 1, 2, 4 transmit ports, as far as the estimator ran */
     int16_t llr[480], des[480];
     lteo_pbch_llr(cell, hyp, sf, ce, n0, llr);
     for (int q = 0; q < 4; q++) {

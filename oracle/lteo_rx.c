@@ -181,15 +181,19 @@ void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf, lteo_c
   lteo_cf_t *ls = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * M);
   lteo_cf_t *sm = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * M);
   lteo_cf_t *hs = (lteo_cf_t *)malloc(sizeof(lteo_cf_t) * 4 * nsc);
-  float *v_noise = (float *)malloc(sizeof(float) * np * 4 * M);
+  float *v_noise = (float *)malloc(sizeof(float) * np * 4 * M);      /* ports 2 / 3 fill half of theirs */
   float *v_rsrp = (float *)malloc(sizeof(float) * 4 * M);
   float *v_rssi = (float *)malloc(sizeof(float) * 4 * nsc);
   int n_noise = 0, n_rsrp = 0, n_rssi = 0;
   int8_t rs[220], is[220];
   int32_t kk[220];
   for (int p = 0; p < np; p++) {
-    for (int si = 0; si < 4; si++) {
-      int l = crs_syms[si];
+    /* ports 2 / 3 carry pilots in symbol 1 of each slot only: two pilot symbols, one time segment (SPEC.md 15c) */
+    const int psyms[2] = {1, nslot + 1};
+    const int nsi = p < 2 ? 4 : 2;
+    const int *syms = p < 2 ? crs_syms : psyms;
+    for (int si = 0; si < nsi; si++) {
+      int l = syms[si];
       lteo_crs_positions(cell, p, l, kk);
       lteo_crs_values(cell, sf_idx, l, rs, is);
       for (int m = 0; m < M; m++) {
@@ -220,8 +224,8 @@ void lteo_chest(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf, lteo_c
     /* time interpolation between CRS symbols 0,4,7,11; symbols 12,13 extrapolate from (7,11)
      * (extended cyclic prefix: 0,3,6,9; symbols 10,11 extrapolate from (6,9)) */
     for (int l = 0; l < 2 * nslot; l++) {
-      int s0 = (l < crs_syms[1]) ? 0 : (l < nslot) ? 1 : 2;
-      int l0 = crs_syms[s0], l1 = crs_syms[s0 + 1];
+      int s0 = (p >= 2) ? 0 : (l < crs_syms[1]) ? 0 : (l < nslot) ? 1 : 2;
+      int l0 = syms[s0], l1 = syms[s0 + 1];
       float f = (float)((double)(l - l0) / (double)(l1 - l0));
       for (int k = 0; k < nsc; k++) {
         lteo_cf_t a = hs[s0 * nsc + k], b = hs[(s0 + 1) * nsc + k];
@@ -257,10 +261,10 @@ void lteo_equalize(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, const l
   int nsc = 12 * cell->nof_prb;
   int32_t *re = (int32_t *)malloc(sizeof(int32_t) * 14 * nsc);
   int nre = lteo_pdsch_re_list(cell, cfg, re);
-  if (cfg->tm == 2 && cell->nof_ports == 2) {
+  if (cfg->tm == 2 && cell->nof_ports >= 2) {
     const float sq2 = (float)sqrt(2.0);
-    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
     for (int i = 0; i + 1 < nre; i += 2) {
+      const lteo_cf_t *ce0 = ce + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc, *ce1 = ce + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc;
       lteo_cf_t r0 = sf[re[i]], r1 = sf[re[i + 1]], h0 = ce0[re[i]], h1 = ce1[re[i]];
       float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
       float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;   /* conj(h0) r0 */
@@ -359,10 +363,10 @@ int lteo_pcfich_decode(const lteo_cell_t *cell, int sf_idx, const lteo_cf_t *sf,
   lteo_cf_t d[16];
   int16_t llr[32];
   lteo_pcfich_re(cell, k);
-  if (cell->nof_ports == 2) {
+  if (cell->nof_ports >= 2) {
     const float sq2 = (float)sqrt(2.0);
-    const lteo_cf_t *ce0 = ce, *ce1 = ce + 14 * nsc;
     for (int i = 0; i < 16; i += 2) {          /* the Alamouti combiner of lteo_equalize */
+      const lteo_cf_t *ce0 = ce + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc, *ce1 = ce + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc;
       lteo_cf_t r0 = sf[k[i]], r1 = sf[k[i + 1]], h0 = ce0[k[i]], h1 = ce1[k[i]];
       float den = ((h0.re * h0.re + h0.im * h0.im) + (h1.re * h1.re + h1.im * h1.im)) + n0;
       float a_re = h0.re * r0.re + h0.im * r0.im, a_im = h0.re * r0.im - h0.im * r0.re;

@@ -189,11 +189,11 @@ int lteo_pdsch_tx_grid(const lteo_cell_t *cell, const lteo_pdsch_cfg_t *cfg, con
   uint8_t *e = (uint8_t *)malloc(nre * cfg->qm + 8);
   int G, rc = lteo_pdsch_encode_bits(cell, cfg, tb_bytes, e, &G);
   if (rc) { free(re); free(e); return rc; }
-  if (cfg->tm == 2 && np == 2) {
+  if (cfg->tm == 2 && np >= 2) {
     double a = 1.0 / sqrt(2.0);
     for (int i = 0; i + 1 < nre; i += 2) {
       lteo_cd_t x0 = modulate(e + i * cfg->qm, cfg->qm), x1 = modulate(e + (i + 1) * cfg->qm, cfg->qm);
-      lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
+      lteo_cd_t *g0 = grid + (size_t)LTEO_DIV_PA(np, i / 2) * 14 * nsc, *g1 = grid + (size_t)LTEO_DIV_PB(np, i / 2) * 14 * nsc;
       g0[re[i]].re = x0.re * a;      g0[re[i]].im = x0.im * a;
       g1[re[i]].re = -x1.re * a;     g1[re[i]].im = x1.im * a;      /* -conj(x1) */
       g0[re[i + 1]].re = x1.re * a;  g0[re[i + 1]].im = x1.im * a;
@@ -226,10 +226,10 @@ void lteo_pcfich_tx(const lteo_cell_t *cell, int sf_idx, int cfi, lteo_cd_t *gri
   uint8_t b[32];
   lteo_pcfich_re(cell, k);
   lteo_pcfich_bits(cell, sf_idx, cfi, b);
-  if (cell->nof_ports == 2) {
+  if (cell->nof_ports >= 2) {
     double a = 1.0 / sqrt(2.0);
-    lteo_cd_t *g0 = grid, *g1 = grid + 14 * nsc;
     for (int i = 0; i < 16; i += 2) {
+      lteo_cd_t *g0 = grid + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc, *g1 = grid + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc;
       lteo_cd_t x0 = modulate(b + 2 * i, 2), x1 = modulate(b + 2 * i + 2, 2);
       g0[k[i]].re = x0.re * a;      g0[k[i]].im = x0.im * a;
       g1[k[i]].re = -x1.re * a;     g1[k[i]].im = x1.im * a;
@@ -267,8 +267,10 @@ int lteo_pdcch_tx(const lteo_cell_t *cell, int sf_idx, int cfi, int ng_x6, int n
     lteo_cd_t x[4];
     for (int i = 0; i < 4; i++) x[i] = modulate(q + 2 * i, 2);
     lteo_cd_t *g0 = grid + rl[m] * nsc, *g1 = grid + 14 * nsc + rl[m] * nsc;
-    if (cell->nof_ports == 2) {
+    if (cell->nof_ports >= 2) {
       for (int i = 0; i < 4; i += 2) {
+        g0 = grid + (size_t)LTEO_DIV_PA(cell->nof_ports, i / 2) * 14 * nsc + rl[m] * nsc;
+        g1 = grid + (size_t)LTEO_DIV_PB(cell->nof_ports, i / 2) * 14 * nsc + rl[m] * nsc;
         g0[k4[i]].re = x[i].re * a;          g0[k4[i]].im = x[i].im * a;
         g1[k4[i]].re = -x[i + 1].re * a;     g1[k4[i]].im = x[i + 1].im * a;
         g0[k4[i + 1]].re = x[i + 1].re * a;  g0[k4[i + 1]].im = x[i + 1].im * a;
