@@ -304,7 +304,7 @@ struct srsue_gpu_pdsch_plan {
   CbSegm seg{};
   srsue_gpu_plan_info_t info{};
   TurboGeom gp{}, gm{};
-  int crs_off[2][4]{};
+  int crs_off[4][4]{};     // ports 2 / 3 (four-port cells): two pilot symbols, columns 0 and 1
   int max_E = 0, gather_stride = 0, direct = 0;
   // device tables
   int32_t* d_re = nullptr; uint32_t* d_scr = nullptr; uint16_t* d_gather = nullptr;
@@ -539,15 +539,33 @@ int srsue_gpu_tdec_last_launch(srsue_gpu_ctx_t* ctx, int* grid, int* block, int*
 int srsue_gpu_last_launch_count(srsue_gpu_ctx_t* ctx) { return ctx ? ctx->launch_count.load() : 0; }
 
 // ---- PDSCH plan -------------------------------------------------------------------------------------
+// +-1 signs of the CRS of the plan's subframe, [row][re, im][2 nof_prb]: rows 0..3 = the four CRS symbols of ports 0 / 1
+// (one sequence per symbol, shared by the ports), rows 4, 5 = symbol 1 of each slot (ports 2 / 3 of a four-port cell);
+// and the first pilot subcarrier of every (port, pilot symbol)
+static void build_crs_tables(srsue_gpu_pdsch_plan_t* p, int sf_idx, std::vector<int8_t>& crs) {
+  const int M = 2 * p->cell.nof_prb, cp = p->cell.cp, rows = p->cell.nof_ports == 4 ? 6 : 4;
+  const int crs_l[6] = {0, cp ? 3 : 4, cp ? 6 : 7, cp ? 9 : 11, 1, slot_symb(cp) + 1};
+  crs.assign((size_t)rows * 2 * M, 0);
+  std::vector<int8_t> rs, is;
+  for (int r = 0; r < rows; r++) {
+    crs_signs(p->cell, sf_idx, crs_l[r], rs, is);
+    std::copy(rs.begin(), rs.end(), crs.begin() + (r * 2 + 0) * M);
+    std::copy(is.begin(), is.end(), crs.begin() + (r * 2 + 1) * M);
+    if (r < 4) for (int port = 0; port < 2; port++) p->crs_off[port][r] = crs_offset(p->cell, port, crs_l[r]);
+    else for (int port = 2; port < 4; port++) p->crs_off[port][r - 4] = crs_offset(p->cell, port, crs_l[r]);
+  }
+}
+
 int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* cell, const srsue_gpu_pdsch_cfg_t* cfg,
                                 int max_batch, srsue_gpu_pdsch_plan_t** out) {
   if (!ctx || !cell || !cfg || !out || max_batch < 1) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "plan_create: bad arguments");
   *out = nullptr;
   const int nfft = symbol_sz(cell->nof_prb);
   if (nfft < 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_prb=%d is not an LTE bandwidth", cell->nof_prb);
-  if (cell->nof_ports < 1 || cell->nof_ports > 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_ports must be 1 or 2");
+  if (cell->nof_ports != 1 && cell->nof_ports != 2 && cell->nof_ports != 4) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "nof_ports must be 1, 2 or 4");
   if (cfg->qm != 2 && cfg->qm != 4 && cfg->qm != 6) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "qm must be 2, 4 or 6");
-  if (cfg->tm == 2 && cell->nof_ports != 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "transmit diversity needs 2 ports");
+  if (cfg->tm == 2 && cell->nof_ports < 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "transmit diversity needs 2 or 4 ports");
+  if (cfg->tm == 1 && cell->nof_ports == 4 && cfg->tbs != 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "a four-port cell transmits with diversity (tm 2)");
   if (cfg->tm != 1 && cfg->tm != 2) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "tm must be 1 or 2");
   if (cfg->rv < 0 || cfg->rv > 3 || cfg->sf_idx < 0 || cfg->sf_idx > 9 || cfg->cfi < 1 || cfg->cfi > 3)
     return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "rv/sf_idx/cfi out of range");
@@ -562,15 +580,8 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
     // (what srslte_ue_dl_decode_fft_estimate needs before the DCI is known, phch_worker.cc:254)
     const int nsc0 = 12 * cell->nof_prb;
     p->info.nfft = nfft; p->info.nsc = nsc0; p->info.sf_len = 15 * nfft; p->info.max_batch = max_batch;
-    std::vector<int8_t> crs0(4 * 2 * 2 * cell->nof_prb), rs0, is0;
-    const int crs_l0[4] = {0, p->cell.cp ? 3 : 4, p->cell.cp ? 6 : 7, p->cell.cp ? 9 : 11};
-    for (int si = 0; si < 4; si++) {
-      crs_signs(p->cell, cfg->sf_idx, crs_l0[si], rs0, is0);
-      const int M = 2 * cell->nof_prb;
-      std::copy(rs0.begin(), rs0.end(), crs0.begin() + (si * 2 + 0) * M);
-      std::copy(is0.begin(), is0.end(), crs0.begin() + (si * 2 + 1) * M);
-      for (int port = 0; port < 2; port++) p->crs_off[port][si] = crs_offset(p->cell, port, crs_l0[si]);
-    }
+    std::vector<int8_t> crs0;
+    build_crs_tables(p, cfg->sf_idx, crs0);
     std::vector<float> tw0;
     fft_twiddles(nfft, tw0);
     if (upload(&p->d_crs, crs0) != cudaSuccess || upload(&p->d_tw, tw0) != cudaSuccess) {
@@ -637,15 +648,8 @@ int srsue_gpu_pdsch_plan_create(srsue_gpu_ctx_t* ctx, const srsue_gpu_cell_t* ce
   std::vector<uint32_t> scr;
   gold_packed(((uint32_t)cfg->rnti << 14) | ((uint32_t)cfg->sf_idx << 9) | (uint32_t)cell->cell_id, G, scr);
   scr.push_back(0u);      // the kernel reads bit groups with a two-word funnel shift
-  std::vector<int8_t> crs(4 * 2 * 2 * cell->nof_prb), rs, is;
-  const int crs_l[4] = {0, p->cell.cp ? 3 : 4, p->cell.cp ? 6 : 7, p->cell.cp ? 9 : 11};
-  for (int si = 0; si < 4; si++) {
-    crs_signs(p->cell, cfg->sf_idx, crs_l[si], rs, is);
-    const int M = 2 * cell->nof_prb;
-    std::copy(rs.begin(), rs.end(), crs.begin() + (si * 2 + 0) * M);
-    std::copy(is.begin(), is.end(), crs.begin() + (si * 2 + 1) * M);
-    for (int port = 0; port < 2; port++) p->crs_off[port][si] = crs_offset(p->cell, port, crs_l[si]);
-  }
+  std::vector<int8_t> crs;
+  build_crs_tables(p, cfg->sf_idx, crs);
   std::vector<float> tw;
   fft_twiddles(nfft, tw);
   std::vector<int32_t> list_m((size_t)max_batch * s.Cm), list_p((size_t)max_batch * s.Cp);
@@ -960,7 +964,7 @@ int srsue_gpu_phich_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_
   a.scramble = pcfich_scramble(p->cell, p->cfg.sf_idx) & 0xFFFu;     // the same c_init as the PCFICH (36.211 6.9.1)
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.n_seq = n_seq; a.noise_mode = noise_mode;
   a.noise_est = noise_est; a.k_sq2 = (float)std::sqrt(2.0);
-  a.ext = p->cell.cp; a.odd = n_group & 1;
+  a.ext = p->cell.cp; a.odd = n_group & 1; a.par0 = p->cell.cp ? n_group / 2 : n_group;
   phich_kernel<<<(n_sf + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
@@ -988,7 +992,7 @@ int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_c
   a.re = p->d_pbch_re; a.scramble = p->d_pbch_scr; a.rm_seq = p->d_pbch_rm; a.result = d_result; a.mib = d_mib; a.n_re = p->pbch_nre;
   a.n_sf = n_sf; a.nsc = p->info.nsc; a.nof_ports = p->cell.nof_ports; a.noise_mode = noise_mode; a.noise_est = noise_est;
   a.k_sqpsk = (float)(100.0 * std::sqrt(2.0)); a.k_sq2 = (float)std::sqrt(2.0);
-  pbch_kernel<<<n_sf, 256, 0, (cudaStream_t)stream>>>(a);
+  pbch_kernel<<<n_sf, p->cell.nof_ports == 4 ? 384 : 256, 0, (cudaStream_t)stream>>>(a);      // four warps per transmit-port hypothesis
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
   return 0;
@@ -1066,7 +1070,16 @@ static int chest_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_
   // 128 threads measured best on B200 (0.19 ms vs 0.26 ms per 4096 subframes with 512): the kernel is bound by its
   // three ordered reduction warps, smaller CTAs pack more of them per SM.  Needs >= 3 warps.
   static const int chest_threads = std::min(128, std::max(96, getenv("SRSUE_CHEST_THREADS") ? atoi(getenv("SRSUE_CHEST_THREADS")) : 128));
-  if (p->cell.cp) chest_ext_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
+  if (p->cell.nof_ports == 4) {
+    if (d_pilots) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "chest_pilots: the fused interpolation serves one and two ports");
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(chest_p4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(chest_ext_p4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    });
+    if (p->cell.cp) chest_ext_p4_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
+    else chest_p4_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
+  } else if (p->cell.cp) chest_ext_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
   else chest_kernel<<<n_sf, chest_threads, smem, (cudaStream_t)stream>>>(a);
   p->ctx->launch_count++;
   CU_CHECK(cudaGetLastError());
@@ -1098,10 +1111,11 @@ static int llr_launch(srsue_gpu_pdsch_plan_t* p, int n_sf, const srsue_gpu_cf_t*
   if (!d_sf || !d_softbuf) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: null buffer");
   if (p->info.C == 0) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: front-end-only plan (tbs == 0)");
   if (noise_mode && !d_meas) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr: noise_mode 1 needs d_meas");
+  if (d_pilots && p->cell.nof_ports == 4) return fail(SRSUE_GPU_ERROR_INVALID_INPUTS, "pdsch_llr_fused: the fused interpolation serves one and two ports");
   DemodArgs a{};
   a.sf_symbols = reinterpret_cast<const float2*>(d_sf); a.ce = reinterpret_cast<const float2*>(d_ce); a.meas = d_meas;
   a.pilots = reinterpret_cast<const float2*>(d_pilots); a.nof_prb = p->cell.nof_prb; a.cp_ext = p->cell.cp;
-  std::memcpy(a.crs_off, p->crs_off, sizeof(a.crs_off));
+  std::memcpy(a.crs_off, p->crs_off, sizeof(a.crs_off));       // ports 0 and 1 (the fused interpolation's)
   a.softbuf = d_softbuf; a.re_idx = p->d_re; a.scramble = p->d_scr; a.gather = p->d_gather;
   a.cb_e_start = p->d_e_start; a.cb_geom = p->d_cb_geom;
   a.dbg_d = reinterpret_cast<float2*>(d_dbg_d); a.dbg_e = d_dbg_e;

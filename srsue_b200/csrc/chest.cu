@@ -31,11 +31,15 @@ __device__ __forceinline__ float warp_sum_ordered(int n, int lane, F elem) {
 
 // EXT = extended cyclic prefix: 12 symbols, CRS in symbols 0, 3, 6, 9 (36.211 6.10.1.2: symbols 0 and N_symb - 3 of a slot),
 // symbols 10 and 11 extrapolated from (6, 9) as 12 and 13 are from (7, 11); same operations otherwise (SPEC.md 15b)
-template <bool EXT>
+// P4 = four-port cell: ports 2 / 3 carry pilots in symbol 1 of each slot only (36.211 6.10.1.2), so they have two pilot
+// symbols (rows 0, 1 of their [4][M] block; sign rows 4, 5) and one time segment (1, NSLOT + 1) that every symbol
+// interpolates or extrapolates from (SPEC.md 15c).  Ports 0 / 1 are computed exactly as in a two-port cell.
+template <bool EXT, bool P4>
 __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   extern __shared__ __align__(16) float2 s_ch[];
   __shared__ float s_ftab[17];
   __shared__ float s_ttab[14];
+  __shared__ float s_ttab2[14];           // ports 2 / 3: (l - 1) / NSLOT
   __shared__ float s_red[3];
   const int sf = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int nsc = a.nsc, M = 2 * a.nof_prb, np = a.nof_ports;
@@ -43,7 +47,7 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   float2* s_sm = s_ch + np * 4 * M;       // [np][4][M]
   float* s_pw = reinterpret_cast<float*>(s_ch + 2 * np * 4 * M);   // [4][nsc]: |y|^2 of the four CRS symbols (RSSI)
   const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
-  constexpr int NSYM = EXT ? 12 : 14, C1 = EXT ? 3 : 4, C2 = EXT ? 6 : 7, C3 = EXT ? 9 : 11;
+  constexpr int NSYM = EXT ? 12 : 14, C1 = EXT ? 3 : 4, C2 = EXT ? 6 : 7, C3 = EXT ? 9 : 11, NSLOT = EXT ? 6 : 7;
   const int crs_l[4] = {0, C1, C2, C3};
   const float isq2 = (float)(1.0 / sqrt(2.0));
 
@@ -52,6 +56,7 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
     const int l = tid - 32;
     const int s0 = (l < C1) ? 0 : (l < C2) ? 1 : 2;
     s_ttab[l] = (float)((double)(l - crs_l[s0]) / (double)(crs_l[s0 + 1] - crs_l[s0]));
+    if (P4) s_ttab2[l] = (float)((double)(l - 1) / (double)NSLOT);
   }
   // ---- RSSI inputs: the ordered sum below is one warp walking 4 nsc values (SPEC 3.5 fixes its order), which as a chain
   // of dependent global loads kept every CTA resident for tens of microseconds; here all threads fetch the values at once
@@ -60,8 +65,10 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   // ---- least squares at the pilots ------------------------------------------------------------------
   for (int i = tid; i < np * 4 * M; i += nt) {
     const int m = i % M, si = (i / M) % 4, p = i / (4 * M);
-    const float2 v = y[crs_l[si] * nsc + a.crs_off[p][si] + 6 * m];
-    const int rs = a.crs_sign[(si * 2 + 0) * M + m], is = a.crs_sign[(si * 2 + 1) * M + m];
+    if (P4 && p >= 2 && si >= 2) { s_ls[i] = make_float2(0.f, 0.f); continue; }      // ports 2 / 3 have two pilot symbols
+    const int lsym = (P4 && p >= 2) ? (si ? NSLOT + 1 : 1) : crs_l[si], srow = (P4 && p >= 2) ? 4 + si : si;
+    const float2 v = y[lsym * nsc + a.crs_off[p][si] + 6 * m];
+    const int rs = a.crs_sign[(srow * 2 + 0) * M + m], is = a.crs_sign[(srow * 2 + 1) * M + m];
     const float tre = __fadd_rn(rs > 0 ? v.x : -v.x, is > 0 ? v.y : -v.y);
     const float tim = __fsub_rn(rs > 0 ? v.y : -v.y, is > 0 ? v.x : -v.x);
     s_ls[i] = make_float2(__fmul_rn(tre, isq2), __fmul_rn(tim, isq2));
@@ -83,6 +90,29 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   // ---- frequency + time interpolation ---------------------------------------------------------------
   for (int p = 0; p < np && a.ce != nullptr; p++) {
     float2* ce = a.ce + ((size_t)sf * np + p) * 14 * nsc;
+    if (P4 && p >= 2) {
+      for (int k = tid; k < nsc; k += nt) {
+        float2 h[2];
+#pragma unroll
+        for (int si = 0; si < 2; si++) {
+          const int off = a.crs_off[p][si];
+          int m = (k >= off) ? (k - off) / 6 : 0;
+          if (m > M - 2) m = M - 2;
+          const float f = s_ftab[k - (6 * m + off) + 5];
+          const float2 v0 = s_sm[(p * 4 + si) * M + m], v1 = s_sm[(p * 4 + si) * M + m + 1];
+          h[si] = make_float2(lerp_rn(v0.x, v1.x, f), lerp_rn(v0.y, v1.y, f));
+        }
+#pragma unroll
+        for (int l = 0; l < NSYM; l++) {
+          float2 o;
+          if (l == 1) o = h[0];
+          else if (l == NSLOT + 1) o = h[1];
+          else { const float f = s_ttab2[l]; o = make_float2(lerp_rn(h[0].x, h[1].x, f), lerp_rn(h[0].y, h[1].y, f)); }
+          ce[l * nsc + k] = o;
+        }
+      }
+      continue;
+    }
     for (int k = tid; k < nsc; k += nt) {
       float2 h[4];
 #pragma unroll
@@ -106,10 +136,12 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   }
   // ---- measurements: three warps, one quantity each -------------------------------------------------
   const int warp = tid >> 5, lane = tid & 31;
-  const int n_noise = np * 4 * (M - 2), n_rsrp = 4 * M, n_rssi = 4 * nsc;
+  const int n_noise = (P4 ? 12 : np * 4) * (M - 2), n_rsrp = 4 * M, n_rssi = 4 * nsc;
   if (warp == 0) {
     const float s = warp_sum_ordered(n_noise, lane, [&](int i) {
-      const int m = i % (M - 2) + 1, q = i / (M - 2);       // q = p*4 + si
+      const int m = i % (M - 2) + 1;
+      int q = i / (M - 2);                                  // q = p*4 + si; ports 2 / 3 own rows 8, 9 and 12, 13
+      if (P4 && q >= 8) q = 8 + 4 * ((q - 8) >> 1) + ((q - 8) & 1);
       const float2 l = s_ls[q * M + m], t = s_sm[q * M + m];
       const float dr = __fsub_rn(l.x, t.x), di = __fsub_rn(l.y, t.y);
       return __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
@@ -131,7 +163,9 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) { chest_body<false>(a); }
-__global__ void __launch_bounds__(128, 10) chest_ext_kernel(const ChestArgs a) { chest_body<true>(a); }
+__global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) { chest_body<false, false>(a); }
+__global__ void __launch_bounds__(128, 10) chest_ext_kernel(const ChestArgs a) { chest_body<true, false>(a); }
+__global__ void __launch_bounds__(128) chest_p4_kernel(const ChestArgs a) { chest_body<false, true>(a); }
+__global__ void __launch_bounds__(128) chest_ext_p4_kernel(const ChestArgs a) { chest_body<true, true>(a); }
 
 }  // namespace srsue

@@ -104,12 +104,14 @@ struct ChestArgs {
   float2* ce;                // [n_sf][ports][14 * nsc]; nullptr: skip the interpolation (fused path)
   float2* pilots;            // optional [n_sf][ports][4][2 * nof_prb] smoothed pilot estimates
   float* meas;               // [n_sf][5]  noise, rsrp, rssi, rsrq, snr
-  const int8_t* crs_sign;    // [4 crs symbols][2 (re, im)][2 * nof_prb]
+  const int8_t* crs_sign;    // [4 crs symbols (+ the 2 of ports 2 / 3 in a four-port cell)][2 (re, im)][2 * nof_prb]
   int n_sf, nsc, nof_prb, nof_ports;
-  int crs_off[2][4];         // first pilot subcarrier per port and CRS symbol
+  int crs_off[4][4];         // first pilot subcarrier per port and CRS symbol (ports 2 / 3: two symbols)
 };
 __global__ void chest_kernel(const ChestArgs a);       // normal cyclic prefix: CRS in symbols 0, 4, 7, 11 of 14
 __global__ void chest_ext_kernel(const ChestArgs a);   // extended cyclic prefix: CRS in symbols 0, 3, 6, 9 of 12
+__global__ void chest_p4_kernel(const ChestArgs a);    // four-port cells (ports 2 / 3: symbol 1 of each slot)
+__global__ void chest_ext_p4_kernel(const ChestArgs a);
 
 struct DemodArgs {
   const float2* sf_symbols;  // [n_sf][14 * nsc]
@@ -193,6 +195,7 @@ struct PhichArgs {
   float noise_est, k_sq2;
   int ext;                   // extended cyclic prefix: spreading factor 2, the group owns one half of every quadruplet
   int odd;                   // ext: n_group & 1 (the second half)
+  int par0;                  // four ports: quadruplet i uses ports (0, 2) when i + par0 is even, else (1, 3); par0 = n_group (ext: n_group / 2)
 };
 __global__ void phich_kernel(const PhichArgs a);
 

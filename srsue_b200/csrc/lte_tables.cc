@@ -146,6 +146,10 @@ int cb_E(const CbSegm& s, int G, int qm, int nl, int r) {
 
 int crs_offset(const CellCfg& cell, int port, int l) {
   const int nslot = slot_symb(cell.cp), ls = l % nslot;
+  if (port >= 2) {                                      // ports 2/3: symbol 1 of each slot, v = 3 (n_s mod 2) [+ 3 for port 3]
+    if (ls != 1) return -1;
+    return (3 * (l / nslot) + (port == 3 ? 3 : 0) + cell.cell_id % 6) % 6;
+  }
   if (ls != 0 && ls != nslot - 3) return -1;            // ports 0/1: symbols 0 and N_symb - 3 of a slot (36.211 6.10.1.2)
   const int v = ((ls == 0) == (port == 0)) ? 0 : 3;
   return (v + cell.cell_id % 6) % 6;
@@ -172,8 +176,9 @@ void pdsch_re_list(const CellCfg& cell, const PdschCfg& cfg, std::vector<int32_t
   const int mid_lo = nsc / 2 - 36, mid_hi = nsc / 2 + 36;
   const int nslot = slot_symb(cell.cp);
   for (int l = first; l < 2 * nslot; l++) {
-    const int o0 = crs_offset(cell, 0, l);
-    const int o1 = (cell.nof_ports > 1) ? crs_offset(cell, 1, l) : -1;
+    int o0 = crs_offset(cell, 0, l);
+    int o1 = (cell.nof_ports > 1) ? crs_offset(cell, 1, l) : -1;
+    if (cell.nof_ports == 4 && o0 < 0) { o0 = crs_offset(cell, 2, l); o1 = crs_offset(cell, 3, l); }     // symbol 1 of a slot
     // SSS and PSS close slot 0 of subframes 0 and 5, the PBCH opens slot 1 of subframe 0
     bool central_reserved = ((cfg.sf_idx == 0 || cfg.sf_idx == 5) && (l == nslot - 2 || l == nslot - 1)) ||
                             (cfg.sf_idx == 0 && l >= nslot && l <= nslot + 3);
@@ -371,7 +376,8 @@ int pdcch_regs(const CellCfg& cell, int cfi, int ng_x6, std::vector<int32_t>& re
       if (l == 0) {
         if (k % 6 || taken[k / 6]) continue;
         for (int j = 0; j < 6; j++) if ((k + j) % 3 != cell.cell_id % 3) re4.push_back(k + j);
-      } else if (cell.cp && l == 3) {        // extended cyclic prefix: the fourth control symbol (<= 10 PRB) carries CRS
+      } else if ((cell.cp && l == 3) || (cell.nof_ports == 4 && l == 1)) {
+        // extended cyclic prefix: the fourth control symbol (<= 10 PRB) carries CRS; four ports: symbol 1 does (ports 2 / 3)
         if (k % 6) continue;
         for (int j = 0; j < 6; j++) if ((k + j) % 3 != cell.cell_id % 3) re4.push_back(l * nsc + k + j);
       } else {

@@ -82,6 +82,15 @@ __device__ __forceinline__ void emit_re(const DemodArgs& a, int sf, int re, int 
 
 __device__ __forceinline__ float lerp_rn(float a, float b, float f) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), f)); }
 
+// Transmit diversity (36.211 6.3.4.3): Alamouti pair number `pair` of a mapped sequence arrives over ports (0, 1) of a
+// two-port cell; with four ports even pairs use ports (0, 2) and odd pairs ports (1, 3) (SFBC-FSTD).  `grid` = 14 nsc, the
+// distance between the estimates of two ports.
+__device__ __forceinline__ void div_ports(const float2* h0p, int np, int pair, int grid, const float2*& ha, const float2*& hb) {
+  const int odd = (np == 4) ? (pair & 1) : 0;
+  ha = h0p + (size_t)odd * grid;
+  hb = h0p + (size_t)(np == 4 ? 2 + odd : 1) * grid;
+}
+
 // Channel estimate of port p at grid index g (= l*nsc + k) from the smoothed pilots in shared memory: the
 // same frequency and time interpolation, operation for operation, as chest_kernel (SPEC.md 3.3-3.4).
 struct ChanInterp {
@@ -118,13 +127,14 @@ __device__ __forceinline__ void llr_stage(const DemodArgs& a, const ChanInterp& 
   const float2* y = a.sf_symbols + (size_t)sf * 14 * nsc;
   const float2* h0p = FUSED ? nullptr : a.ce + (size_t)sf * a.nof_ports * 14 * nsc;
   const int re0 = e0 / QM, re1 = e1 / QM;
-  if (a.tm == 2 && a.nof_ports == 2) {
-    const float2* h1p = FUSED ? nullptr : h0p + 14 * nsc;
+  if (a.tm == 2 && a.nof_ports >= 2) {
     const float sq2 = a.k_sq2;
     for (int i = re0 + 2 * threadIdx.x; i < re1; i += 2 * blockDim.x) {
       const int g0 = __ldg(a.re_idx + i), g1 = __ldg(a.re_idx + i + 1);
       const float2 r0 = y[g0], r1 = y[g1];
-      const float2 h0 = FUSED ? ci.at(0, g0) : h0p[g0], h1 = FUSED ? ci.at(1, g0) : h1p[g0];
+      const float2 *hap = nullptr, *hbp = nullptr;
+      if (!FUSED) div_ports(h0p, a.nof_ports, i >> 1, 14 * nsc, hap, hbp);     // code blocks start at even REs (E_r is a multiple of 2 Qm)
+      const float2 h0 = FUSED ? ci.at(0, g0) : hap[g0], h1 = FUSED ? ci.at(1, g0) : hbp[g0];
       const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
       const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
       const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
@@ -292,10 +302,11 @@ __global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
   int c0 = 0, c1 = 0, c2 = 0;
   if (lane < 16) {
     float2 d;
-    if (a.nof_ports == 2) {
-      const float2* h1p = h0p + 14 * a.nsc;
+    if (a.nof_ports >= 2) {
+      const float2 *hap, *hbp;
+      div_ports(h0p, a.nof_ports, lane >> 1, 14 * a.nsc, hap, hbp);
       const int g0 = a.re[lane & ~1], g1 = a.re[lane | 1];
-      const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
+      const float2 r0 = y[g0], r1 = y[g1], h0 = hap[g0], h1 = hbp[g0];
       const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
       if ((lane & 1) == 0) {
         const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
@@ -343,17 +354,17 @@ __global__ void __launch_bounds__(128) pcfich_kernel(const PcfichArgs a) {
 // turn the 240 resource elements into 480 LLRs under both transmit-port hypotheses; warp w then decodes hypothesis
 // w / 4 (1 or 2 ports) at frame position w % 4 of the 40 ms BCH period: descrambling with that quarter of the sequence,
 // exact integer soft combining onto the 120 coded bits, tail-biting Viterbi, CRC16 against the antenna mask.
-__global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
-  __shared__ int16_t s_llr[2][480];
-  __shared__ int32_t s_soft[8][120];
-  __shared__ uint32_t s_surv[8][80][2];
-  __shared__ uint8_t s_dec[8][40];
-  __shared__ int s_rem[8];
+__global__ void __launch_bounds__(384) pbch_kernel(const PbchArgs a) {
+  __shared__ int16_t s_llr[3][480];
+  __shared__ int32_t s_soft[12][120];
+  __shared__ uint32_t s_surv[12][80][2];
+  __shared__ uint8_t s_dec[12][40];
+  __shared__ int s_rem[12];
   const int sf = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const float2* y = a.sf_symbols + (size_t)sf * 14 * a.nsc;
   const float2* h0p = a.ce + (size_t)sf * a.nof_ports * 14 * a.nsc;
   const float n0 = a.noise_mode ? a.meas[(size_t)sf * 5] : a.noise_est;
-  const int n_hyp = a.nof_ports >= 2 ? 2 : 1;
+  const int n_hyp = a.nof_ports == 4 ? 3 : a.nof_ports == 2 ? 2 : 1;     // 1, 2 and 4 transmit ports (4 warps each: 256 / 384 threads)
   // hypothesis 1: every thread below 240 equalises one RE; hypothesis 2: every thread below 120 one Alamouti pair
   const int nb = 2 * a.n_re;                     // coded bits per radio frame: 480, or 432 with the extended cyclic prefix
   if (tid < a.n_re) {
@@ -364,10 +375,11 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
     s_llr[0][2 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.x));
     s_llr[0][2 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d.y));
   }
-  if (n_hyp == 2 && tid < a.n_re / 2) {
-    const float2* h1p = h0p + 14 * a.nsc;
+  for (int hy = 1; hy < n_hyp; hy++) if (tid < a.n_re / 2) {
+    const float2 *hap, *hbp;
+    div_ports(h0p, hy == 2 ? 4 : 2, tid, 14 * a.nsc, hap, hbp);
     const int g0 = a.re[2 * tid], g1 = a.re[2 * tid + 1];
-    const float2 r0 = y[g0], r1 = y[g1], h0 = h0p[g0], h1 = h1p[g0];
+    const float2 r0 = y[g0], r1 = y[g1], h0 = hap[g0], h1 = hbp[g0];
     const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
     const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
     const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
@@ -375,10 +387,10 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
     const float e_re = dot_rn(h1.x, r0.x, h1.y, r0.y), e_im = det_rn(h1.y, r0.x, h1.x, r0.y);
     const float2 d0 = make_float2(__fdiv_rn(__fmul_rn(__fadd_rn(a_re, b_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fadd_rn(a_im, b_im), a.k_sq2), den));
     const float2 d1 = make_float2(__fdiv_rn(__fmul_rn(__fsub_rn(c_re, e_re), a.k_sq2), den), __fdiv_rn(__fmul_rn(__fsub_rn(c_im, e_im), a.k_sq2), den));
-    s_llr[1][4 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.x));
-    s_llr[1][4 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.y));
-    s_llr[1][4 * tid + 2] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.x));
-    s_llr[1][4 * tid + 3] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.y));
+    s_llr[hy][4 * tid] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.x));
+    s_llr[hy][4 * tid + 1] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d0.y));
+    s_llr[hy][4 * tid + 2] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.x));
+    s_llr[hy][4 * tid + 3] = (int16_t)q16(-__fmul_rn(a.k_sqpsk, d1.y));
   }
   __syncthreads();
   const int hyp = w >> 2, q = w & 3;
@@ -393,16 +405,16 @@ __global__ void __launch_bounds__(256) pbch_kernel(const PbchArgs a) {
     }
     __syncwarp();
     const int rem = viterbi_crc16_warp(soft, 24, &s_surv[w][0][0], s_dec[w], lane);
-    if (lane == 0) s_rem[w] = (rem == (hyp == 0 ? 0x0000 : 0xFFFF)) ? 1 : 0;
+    if (lane == 0) s_rem[w] = (rem == (hyp == 0 ? 0x0000 : hyp == 1 ? 0xFFFF : 0x5555)) ? 1 : 0;
   } else if (lane == 0) {
     s_rem[w] = 0;
   }
   __syncthreads();
   if (tid == 0) {
     int hit = -1;
-    for (int c = 0; c < 8 && hit < 0; c++) if (s_rem[c]) hit = c;
+    for (int c = 0; c < 4 * n_hyp && hit < 0; c++) if (s_rem[c]) hit = c;
     int32_t* o = a.result + (size_t)sf * 4;
-    o[0] = hit >= 0; o[1] = hit >= 0 ? (hit >> 2) + 1 : 0; o[2] = hit >= 0 ? (hit & 3) : 0; o[3] = 0;
+    o[0] = hit >= 0; o[1] = hit >= 0 ? 1 << (hit >> 2) : 0; o[2] = hit >= 0 ? (hit & 3) : 0; o[3] = 0;
     if (hit >= 0) for (int i = 0; i < 24; i++) a.mib[(size_t)sf * 24 + i] = s_dec[hit][i];
   }
 }
@@ -420,9 +432,11 @@ __global__ void __launch_bounds__(128) phich_kernel(const PhichArgs a) {
 #pragma unroll
   for (int i = 0; i < 12; i += 2) {
     float2 d[2];
-    if (a.nof_ports == 2) {
-      const float2* h1p = h0p + 14 * a.nsc;
-      const float2 r0 = y[a.re[i]], r1 = y[a.re[i + 1]], h0 = h0p[a.re[i]], h1 = h1p[a.re[i]];
+    if (a.nof_ports >= 2) {
+      // four ports (36.211 6.9.2): a whole quadruplet uses ports (0, 2) or (1, 3), alternating with quadruplet + group
+      const float2 *hap, *hbp;
+      div_ports(h0p, a.nof_ports, (i >> 2) + a.par0, 14 * a.nsc, hap, hbp);
+      const float2 r0 = y[a.re[i]], r1 = y[a.re[i + 1]], h0 = hap[a.re[i]], h1 = hbp[a.re[i]];
       const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
       const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
       const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);
@@ -480,11 +494,12 @@ __global__ void __launch_bounds__(128) pdcch_llr_kernel(const PdcchLlrArgs a) {
   const int4 g = *reinterpret_cast<const int4*>(a.re4 + 4 * m);
   const int gi[4] = {g.x, g.y, g.z, g.w};
   float2 d[4];
-  if (a.nof_ports == 2) {
-    const float2* h1p = h0p + 14 * a.nsc;
+  if (a.nof_ports >= 2) {
 #pragma unroll
     for (int i = 0; i < 4; i += 2) {
-      const float2 r0 = y[gi[i]], r1 = y[gi[i + 1]], h0 = h0p[gi[i]], h1 = h1p[gi[i]];
+      const float2 *hap, *hbp;
+      div_ports(h0p, a.nof_ports, i >> 1, 14 * a.nsc, hap, hbp);
+      const float2 r0 = y[gi[i]], r1 = y[gi[i + 1]], h0 = hap[gi[i]], h1 = hbp[gi[i]];
       const float den = __fadd_rn(__fadd_rn(dot_rn(h0.x, h0.x, h0.y, h0.y), dot_rn(h1.x, h1.x, h1.y, h1.y)), n0);
       const float a_re = dot_rn(h0.x, r0.x, h0.y, r0.y), a_im = det_rn(h0.x, r0.y, h0.y, r0.x);
       const float b_re = dot_rn(h1.x, r1.x, h1.y, r1.y), b_im = det_rn(h1.y, r1.x, h1.x, r1.y);

@@ -157,7 +157,7 @@ void srslte_vec_free(void* p) { free(p); }
 int srslte_ue_dl_init(srslte_ue_dl_t* q, srslte_cell_t cell) {
   if (!q) return SRSLTE_ERROR_INVALID_INPUTS;
   std::memset(q, 0, sizeof(*q));
-  if (symbol_sz((int)cell.nof_prb) < 0 || cell.nof_ports < 1 || cell.nof_ports > 2 ||
+  if (symbol_sz((int)cell.nof_prb) < 0 || (cell.nof_ports != 1 && cell.nof_ports != 2 && cell.nof_ports != 4) ||
       (cell.cp != SRSLTE_CP_NORM && cell.cp != SRSLTE_CP_EXT))
     return SRSLTE_ERROR_INVALID_INPUTS;
   srsue_gpu_ctx_t* ctx = shared_ctx();
@@ -856,7 +856,7 @@ int srslte_ue_mib_init(srslte_ue_mib_t* q, srslte_cell_t cell) {
   std::memset(q, 0, sizeof(*q));
   auto* m = new MibGpu();
   srslte_cell_t c2 = cell;
-  c2.nof_ports = 2;
+  c2.nof_ports = 4;            // the estimator runs for all four ports; the PBCH decoder tries 1, 2 and 4 (CRC mask)
   if (srslte_ue_dl_init(&m->ue_dl, c2) != SRSLTE_SUCCESS ||
       cudaMalloc((void**)&m->d_result, 4 * sizeof(int32_t)) != cudaSuccess || cudaMalloc((void**)&m->d_mib, 24) != cudaSuccess) {
     srslte_ue_dl_free(&m->ue_dl);
