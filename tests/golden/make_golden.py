@@ -134,12 +134,54 @@ def extcp():
     print("extcp: cfi", cfi, "phich", ph, "pbch", f, ports, off, "rc", rc, "sync", pk["pos"], pk["n_id_2"], n1, sf5, cp)
 
 
+P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, sfn=822, phich=((0, 1, 1), (1, 5, 0)))
+
+
+def _taps4():
+    rng = np.random.default_rng(44)
+    t = (rng.standard_normal((4, 5)) + 1j * rng.standard_normal((4, 5))) * np.array([1, .6, .4, .2, .1])
+    return t / np.sqrt((abs(t) ** 2).sum(1, keepdims=True))
+
+
+def fourports():
+    """four-port cell (SPEC.md 15c): a subframe 0 of a 1.4 MHz cell over four independent channels with PBCH (CRC mask
+    0x5555), PCFICH, a PDCCH in the common search space, two HARQ indicators and a 16QAM PDSCH"""
+    c = P4
+    cell = o.make_cell(c["prb"], 4, c["cid"])
+    cfg = o.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    mib = o.mib_pack(6, 0, 6, c["sfn"])
+    nb = 21
+    bits = np.random.default_rng(4).integers(0, 2, nb, dtype=np.uint8)
+    rk, _ = o.pdcch_regs(cell, c["cfi"], 6)
+    ss = o.pdcch_search_space(len(rk) // 9, 0, c["rnti"])
+    tb, iq, _ = o.gen_subframe(cell, cfg, 1616, 14.0, _taps4(), pcfich=True, mib=(mib, c["sfn"] % 4), phichs=list(c["phich"]),
+                               dcis=[(bits, c["rnti"]) + ss[0]])
+    sf = o.ofdm_rx(c["prb"], iq)
+    ce, meas = o.chest(cell, 0, sf)
+    cfi, corr = o.pcfich_decode(cell, 0, sf, ce, meas[0])
+    ph = [o.phich_decode(cell, 0, sf, ce, g, q, float(meas[0])) for g, q, _ in c["phich"]]
+    f, mbits, ports, off = o.pbch_decode(cell, sf, ce, float(meas[0]))
+    llr, nc = o.pdcch_extract_llr(cell, 0, cfi, sf, ce, meas[0])
+    fd, out, L1, n1 = o.pdcch_find_dci(llr, nc, 0, c["rnti"], nb)
+    rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, float(meas[0]), 4, want=True)
+    nre = len(o.pdsch_re_list(cell, cfg))
+    np.savez_compressed(os.path.join(OUT, "fourports.npz"), iq=iq, tb=tb, sf=sf, ce=ce, meas=meas, cfi=np.array([cfi]), corr=corr,
+                        phich_ack=np.array([a for a, _ in ph], np.int32), phich_metric=np.array([m for _, m in ph], np.float32),
+                        pbch=np.array([f, ports, off], np.int32), mib=mbits, mib_sent=mib, llr=llr[:8 * len(rk)],
+                        dci=np.array([fd, L1, n1], np.int32), dci_bits=out, dci_sent=bits, e=dbg["e"][:nre * c["qm"]], payload=pl,
+                        rc=np.array([rc]))
+    print("fourports: cfi", cfi, "phich", ph, "pbch", f, ports, off, "dci", fd, L1, n1, "rc", rc)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfo":
         cfo()
     elif len(sys.argv) > 1 and sys.argv[1] == "extcp":
         extcp()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fourports":
+        fourports()
     else:
         main()
         cfo()
         extcp()
+        fourports()

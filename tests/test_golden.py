@@ -286,3 +286,86 @@ def test_gpu_reproduces_extended_prefix_golden(gpu):
     assert [r.peak_pos, r.n_id_2, r.n_id_1, r.sf5, r.cp] == v["sync"].tolist()
     assert np.float32(r.peak) == v["sync_f"][0] and np.float32(r.sss_corr) == v["sync_f"][1]
     plan.close()
+
+
+P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, phich=((0, 1), (1, 5)), nb=21)
+
+
+def test_oracle_reproduces_four_port_golden(oracle):
+    """tests/golden/fourports.npz (make_golden.py fourports): one subframe 0 of a four-port cell through every stage"""
+    o = oracle
+    v = np.load(os.path.join(G, "fourports.npz"))
+    c = P4
+    cell = o.make_cell(c["prb"], 4, c["cid"])
+    cfg = o.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    sf = o.ofdm_rx(c["prb"], v["iq"])
+    ce, meas = o.chest(cell, 0, sf)
+    assert np.array_equal(sf, v["sf"]) and np.array_equal(ce, v["ce"]) and np.array_equal(meas, v["meas"])
+    cfi, corr = o.pcfich_decode(cell, 0, sf, ce, meas[0])
+    assert cfi == int(v["cfi"][0]) == c["cfi"] and np.array_equal(corr, v["corr"])
+    for i, (g, q) in enumerate(c["phich"]):
+        a, m = o.phich_decode(cell, 0, sf, ce, g, q, float(meas[0]))
+        assert a == v["phich_ack"][i] and m == v["phich_metric"][i]
+    assert v["phich_ack"].tolist() == [1, 0]
+    f, bits, ports, off = o.pbch_decode(cell, sf, ce, float(meas[0]))
+    assert [f, ports, off] == v["pbch"].tolist() and ports == 4 and np.array_equal(bits, v["mib"]) and np.array_equal(bits, v["mib_sent"])
+    llr, nc = o.pdcch_extract_llr(cell, 0, cfi, sf, ce, meas[0])
+    assert np.array_equal(llr[:len(v["llr"])], v["llr"])
+    fd, out, L1, n1 = o.pdcch_find_dci(llr, nc, 0, c["rnti"], c["nb"])
+    assert [fd, L1, n1] == v["dci"].tolist() and fd == 1 and np.array_equal(out, v["dci_bits"]) and np.array_equal(out, v["dci_sent"])
+    rc, pl, dbg = o.pdsch_decode(cell, cfg, sf, ce, float(meas[0]), 4, want=True)
+    assert rc == int(v["rc"][0]) == 0 and np.array_equal(pl, v["payload"]) and np.array_equal(pl, v["tb"])
+    assert np.array_equal(dbg["e"][:len(v["e"])], v["e"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_four_port_golden(gpu):
+    import torch
+    sg, ctx = gpu
+    v = np.load(os.path.join(G, "fourports.npz"))
+    c = P4
+    cell = sg.make_cell(c["prb"], 4, c["cid"])
+    cfg = sg.make_cfg(cell, sf_idx=0, cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=c["tbs"], tm=2)
+    plan = sg.PdschPlan(ctx, cell, cfg, 1)
+    I = plan.info
+    n_reg, nc = plan.pdcch_info(6)
+    d_iq = torch.from_numpy(v["iq"].view(np.float32).reshape(1, -1)).cuda()
+    d_sf = torch.zeros((1, 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_ce = torch.zeros((1, 4 * 14 * I.nsc * 2), dtype=torch.float32, device="cuda")
+    d_meas = torch.zeros((1, 5), dtype=torch.float32, device="cuda")
+    d_cfi = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_corr = torch.zeros((1, 3), dtype=torch.int32, device="cuda")
+    d_sb = torch.zeros((1, I.sb_sf_stride), dtype=torch.int16, device="cuda")
+    d_e = torch.zeros((1, I.G), dtype=torch.int16, device="cuda")
+    d_res = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    d_mib = torch.zeros((1, 24), dtype=torch.uint8, device="cuda")
+    d_pl = torch.zeros((1, I.payload_stride), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    d_llr = torch.zeros((1, 8 * n_reg), dtype=torch.int16, device="cuda")
+    d_found = torch.zeros((1, 4), dtype=torch.int32, device="cuda")
+    d_bits = torch.zeros((1, 64), dtype=torch.uint8, device="cuda")
+    plan.ofdm_rx(1, d_iq, d_sf)
+    plan.chest(1, d_sf, d_ce, d_meas)
+    plan.pcfich_decode(1, d_sf, d_ce, d_meas, 0.0, 1, d_cfi, d_corr)
+    plan.pbch_decode(1, d_sf, d_ce, d_meas, 0.0, 1, d_res, d_mib)
+    plan.pdcch_extract_llr(1, d_sf, d_ce, d_meas, 0.0, 1, d_llr)
+    plan.pdcch_find_dci(1, d_llr, c["rnti"], c["nb"], d_found, d_bits, None)
+    plan.pdsch_llr(1, d_sf, d_ce, d_meas, 0.0, 1, 0, d_sb, None, d_e)
+    plan.decode_batch(1, d_iq, 0.0, 1, 4, d_pl, d_st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sf.cpu().numpy().view(np.complex64)[0], v["sf"])
+    assert np.array_equal(d_ce.cpu().numpy().view(np.complex64).reshape(v["ce"].shape), v["ce"])
+    assert np.allclose(d_meas.cpu().numpy()[0], v["meas"], rtol=1e-5)
+    assert int(d_cfi.cpu()[0]) == int(v["cfi"][0]) and np.array_equal(d_corr.cpu().numpy()[0], v["corr"])
+    assert d_res.cpu().numpy()[0, :3].tolist() == v["pbch"].tolist() and np.array_equal(d_mib.cpu().numpy()[0], v["mib"])
+    assert np.array_equal(d_llr.cpu().numpy()[0], v["llr"])
+    assert d_found.cpu().numpy()[0, :3].tolist() == v["dci"].tolist() and np.array_equal(d_bits.cpu().numpy()[0, :c["nb"]], v["dci_bits"])
+    assert np.array_equal(d_e.cpu().numpy()[0, :len(v["e"])], v["e"])
+    assert int(d_st.cpu()[0, 0]) == 1 and np.array_equal(d_pl.cpu().numpy()[0, :len(v["payload"])], v["payload"])
+    for i, (g, q) in enumerate(c["phich"]):
+        d_ack = torch.zeros(1, dtype=torch.int32, device="cuda")
+        d_met = torch.zeros(1, dtype=torch.float32, device="cuda")
+        plan.phich_decode(1, d_sf, d_ce, d_meas, 0.0, 1, g, q, d_ack, d_met)
+        torch.cuda.synchronize()
+        assert int(d_ack[0]) == v["phich_ack"][i] and np.float32(d_met[0].item()) == v["phich_metric"][i]
+    plan.close()
