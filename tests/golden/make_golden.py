@@ -134,7 +134,7 @@ def extcp():
     print("extcp: cfi", cfi, "phich", ph, "pbch", f, ports, off, "rc", rc, "sync", pk["pos"], pk["n_id_2"], n1, sf5, cp)
 
 
-P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, sfn=822, phich=((0, 1, 1), (1, 5, 0)))
+P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, sfn=822, phich=((0, 1, 1), (0, 5, 0)))
 
 
 def _taps4():

@@ -288,7 +288,7 @@ def test_gpu_reproduces_extended_prefix_golden(gpu):
     plan.close()
 
 
-P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, phich=((0, 1), (1, 5)), nb=21)
+P4 = dict(prb=6, cid=101, cfi=2, rnti=0x2345, qm=4, tbs=208, phich=((0, 1), (0, 5)), nb=21)
 
 
 def test_oracle_reproduces_four_port_golden(oracle):
