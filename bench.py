@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, cfi=1, sf_idx=1, rnti=0x1234, cell_id=1)
+WORKLOAD = dict(prb=100, ports=1, qm=6, tbs=75376, tm=1, cfi=1, sf_idx=1, rnti=0x1234, cell_id=1, cp=0)
 METRIC = "pdsch_decoded_mbit_per_s_20mhz_mcs28_tm1"
 
 
@@ -31,11 +31,13 @@ def channel_taps():
     """fixed frequency-selective channel of BASELINE configs[2]: 6 sample-spaced taps per TX port, seed 77"""
     rng = np.random.default_rng(77)
     taps = (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])
+    if WORKLOAD["ports"] == 4:          # --ports 4: two more independent channels (the first two stay those of configs[2])
+        taps = np.concatenate([taps, (rng.standard_normal((2, 6)) + 1j * rng.standard_normal((2, 6))) * np.array([1, .7, .5, .3, .2, .1])])
     return taps / np.sqrt((abs(taps) ** 2).sum(1, keepdims=True))
 
 
 def gen_pool(o, pool, snr_db, seed0):
-    ocell = o.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"])
+    ocell = o.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"], cp=WORKLOAD["cp"])
     ocfg = o.make_cfg(ocell, sf_idx=WORKLOAD["sf_idx"], cfi=WORKLOAD["cfi"], rnti=WORKLOAD["rnti"], qm=WORKLOAD["qm"],
                       tbs=WORKLOAD["tbs"], tm=WORKLOAD["tm"])
     tbs, iqs = [], []
@@ -440,6 +442,11 @@ def main():
                          "frequency-selective channel, MMSE with the estimated noise); mixed: configs[4], heterogeneous stream "
                          "through the batching layer; harq: MCS 28 at a BLER operating point with rv 2 retransmissions combined in "
                          "device-resident soft buffers")
+    ap.add_argument("--ports", type=int, default=0, choices=[0, 2, 4],
+                    help="--workload tm2: 4 = a four-port cell (SFBC-FSTD, CRS of ports 2 / 3; SPEC 15c); not a BASELINE config")
+    ap.add_argument("--cp", default="norm", choices=["norm", "ext"],
+                    help="mcs28 / tm2: ext = extended cyclic prefix (12 symbols; SPEC 15b; MCS 28 becomes TBS 61664, the largest "
+                         "that fits 11 data symbols); not a BASELINE config")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     global METRIC
@@ -451,6 +458,21 @@ def main():
     args.noise_mode = 1 if WORKLOAD["tm"] == 2 else 0
     args.label = ("20MHz 100PRB TM2 2-port 16QAM MCS16 TBS30576, 6-tap channel + AWGN %gdB (BASELINE configs[2])" if WORKLOAD["tm"] == 2
                   else "20MHz 100PRB TM1 64QAM MCS28 TBS75376 AWGN %gdB (BASELINE configs[1])") % args.snr
+    if args.workload in ("mcs28", "tm2") and (args.ports == 4 or args.cp == "ext"):       # other cell shapes of the same path
+        if args.ports == 4:
+            if args.workload != "tm2":
+                ap.error("--ports 4 goes with --workload tm2 (a four-port cell transmits with diversity)")
+            WORKLOAD.update(ports=4)
+            METRIC += "_4port"
+            if args.snr == 15.0:       # ports 2 / 3 have half the pilots: the waterfall of this grant sits about 2 dB higher
+                args.snr = 19.0
+        if args.cp == "ext":
+            WORKLOAD.update(cp=1)
+            WORKLOAD.update(tbs=61664 if args.workload == "mcs28" else 22920)      # 11 data symbols: the next smaller sizes
+            METRIC += "_extcp"
+        args.label = "20MHz 100PRB %s %d-port %s TBS%d %s cyclic prefix, %s AWGN %gdB (cell shape beyond BASELINE's configs)" % (
+            "TM2" if WORKLOAD["tm"] == 2 else "TM1", WORKLOAD["ports"], "16QAM" if WORKLOAD["qm"] == 4 else "64QAM", WORKLOAD["tbs"],
+            "extended" if WORKLOAD["cp"] else "normal", "6-tap channels +" if WORKLOAD["tm"] == 2 else "", args.snr)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -488,7 +510,7 @@ def main():
     B = args.batch
     idx = np.arange(B) % args.pool
     ctx = sg.Context(local_rank)
-    cell = sg.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"])
+    cell = sg.make_cell(WORKLOAD["prb"], WORKLOAD["ports"], WORKLOAD["cell_id"], cp=WORKLOAD["cp"])
     cfg = sg.make_cfg(cell, sf_idx=WORKLOAD["sf_idx"], cfi=WORKLOAD["cfi"], rnti=WORKLOAD["rnti"], qm=WORKLOAD["qm"],
                       tbs=WORKLOAD["tbs"], tm=WORKLOAD["tm"])
     plan = sg.PdschPlan(ctx, cell, cfg, B)
@@ -729,7 +751,8 @@ def main():
         np_ = WORKLOAD["ports"]
         # channel estimate: credited with what it moves (the 4 CRS symbols in, every estimate out), not with SURVEY's
         # whole-grid read (268 800 B for cfg2)
-        alg_bytes = {"ofdm_fft": I.sf_len * 8 + 14 * I.nsc * 8, "chest": 4 * I.nsc * 8 + 14 * I.nsc * 8 * np_ + 20,
+        nsym, npil = (12 if WORKLOAD["cp"] else 14), (6 if np_ == 4 else 4)        # symbols per subframe, pilot symbols read
+        alg_bytes = {"ofdm_fft": I.sf_len * 8 + nsym * I.nsc * 8, "chest": npil * I.nsc * 8 + nsym * I.nsc * 8 * np_ + 20,
                      "equalise_demap_dematch": I.nof_re * 8 * (1 + np_) + I.C * (3 * I.Kp + 12) * 2,
                      "turbo_crc_tb": I.C * (3 * I.Kp + 12) * 2 + I.payload_stride + 4 * I.C}
         # cfg2: 380 160 / 172 820 / 694 584 / 464 058 bytes per subframe (channel estimate as moved)
