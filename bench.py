@@ -753,7 +753,7 @@ def main():
         # whole-grid read (268 800 B for cfg2)
         nsym, npil = (12 if WORKLOAD["cp"] else 14), (6 if np_ == 4 else 4)        # symbols per subframe, pilot symbols read
         alg_bytes = {"ofdm_fft": I.sf_len * 8 + nsym * I.nsc * 8, "chest": npil * I.nsc * 8 + nsym * I.nsc * 8 * np_ + 20,
-                     "equalise_demap_dematch": I.nof_re * 8 * (1 + np_) + I.C * (3 * I.Kp + 12) * 2,
+                     "equalise_demap_dematch": I.nof_re * 8 * (1 + min(np_, 2)) + I.C * (3 * I.Kp + 12) * 2,     # an RE is combined with two ports' estimates
                      "turbo_crc_tb": I.C * (3 * I.Kp + 12) * 2 + I.payload_stride + 4 * I.C}
         # cfg2: 380 160 / 172 820 / 694 584 / 464 058 bytes per subframe (channel estimate as moved)
         stages = []
