@@ -410,3 +410,54 @@ def test_init_cell_sequence_four_ports(gpu, oracle):
     L.srslte_pbch_mib_unpack(payload, C.byref(out_cell), C.byref(sfn))
     assert nports.value == 4 and out_cell.nof_prb == 50
     assert sfn0 <= sfn.value + off.value <= sfn0 + 3
+
+
+def test_blind_batch_other_cell_shapes(gpu, oracle):
+    """srsue_gpu_batch_submit_blind (phch_worker.cc:254-297 for a whole batch) on four-port and extended-prefix cells: the
+    caller knows cell, subframe number and RNTI; CFI, grant and transport block equal what was sent"""
+    sg, ctx = gpu
+    o = oracle
+    L = sg.lib()
+    from tests.srslte_ctypes import DciMsg, RaDlDci, install_tbs_table
+    # (prb, ports, cp, cfi, sf_idx, rnti, mcs, RB_start, L_crb, tbs, with_dci)
+    cases = [(25, 4, 0, 2, 4, 0x1234, 9, 2, 10, 1544, True), (25, 4, 1, 1, 4, 0x1234, 9, 0, 10, 1544, True), (25, 4, 0, 2, 4, 0x1234, 9, 2, 10, 1544, False),
+             (50, 4, 0, 1, 7, 0x0456, 12, 5, 25, 5736, True), (6, 4, 0, 2, 1, 0x1234, 4, 0, 6, 408, True), (50, 2, 1, 3, 7, 0x0456, 3, 0, 50, 2856, True),
+             (100, 4, 0, 1, 2, 0x2222, 20, 0, 100, 46888, True), (100, 1, 1, 1, 2, 0x2222, 20, 0, 100, 46888, True)]
+    table = {}
+    for prb, ports, cp, cfi, sf, rnti, mcs, start, ln, tbs, with_dci in cases:
+        itbs = mcs if mcs < 10 else mcs - 1 if mcs < 17 else mcs - 2      # 36.213 Table 7.1.7.1-1
+        table[(itbs, ln)] = tbs
+    install_tbs_table(L, table)
+    items, truth = [], []
+    for k, (prb, ports, cp, cfi, sf, rnti, mcs, start, ln, tbs, with_dci) in enumerate(cases):
+        ocell = o.make_cell(prb, ports, 1, cp=cp)
+        tm = 1 if ports == 1 else 2
+        sent = RaDlDci()
+        sent.mcs_idx, sent.rv_idx, sent.alloc_type = mcs, 0, 2
+        sent.type2_alloc.RB_start, sent.type2_alloc.L_crb, sent.type2_alloc.n_prb1a = start, ln, 1
+        m = DciMsg()
+        nb = L.srslte_dci_msg_pack_pdsch(C.byref(sent), 2, C.byref(m), prb, True)
+        assert nb > 0
+        rk, _ = o.pdcch_regs(ocell, cfi, 6)
+        ss = o.pdcch_search_space(len(rk) // 9, sf, rnti)
+        qm = 2 if mcs < 10 else 4 if mcs < 17 else 6
+        prbs = list(range(start, start + ln))
+        ocfg = o.make_cfg(ocell, sf_idx=sf, cfi=cfi, rnti=rnti, qm=qm, tbs=tbs, prbs=prbs, tm=tm)
+        dcis = [(np.frombuffer(m.data, np.uint8)[:nb].copy(), rnti, ss[0][0], ss[0][1])] if with_dci else None
+        tb, iq, _ = o.gen_subframe(ocell, ocfg, 9400 + k, 28.0 if qm == 6 else 18.0, _taps4(k)[:ports], pcfich=True, dcis=dcis)
+        cell = sg.make_cell(prb, ports, 1, cp=cp)
+        items.append(dict(cell=cell, cfg=sg.make_cfg(cell, sf_idx=sf, cfi=1, rnti=rnti, qm=2, tbs=0, tm=tm), iq=iq))
+        truth.append((ocell, ocfg, iq, tb, cfi, tbs, qm, prbs, with_dci))
+    b = sg.Batch(ctx, 32)
+    b.submit_blind(items, ng_x6=6)
+    res = b.wait()
+    for r, (ocell, ocfg, iq, tb, cfi, tbs, qm, prbs, with_dci) in zip(res, truth):
+        assert r["cfi"] == cfi
+        if not with_dci:
+            assert r["tbs"] == 0 and r["crc_ok"] == 0
+            continue
+        assert r["tbs"] == tbs and r["cfg"].qm == qm and r["cfg"].rv == 0
+        assert [i for i in range(ocell.nof_prb) if r["cfg"].prb_mask[i]] == prbs
+        rc_o, pl_o, _, _ = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
+        assert rc_o == 0 and r["crc_ok"] == 1 and np.array_equal(r["payload"], pl_o) and np.array_equal(pl_o, tb)
+    b.close()
