@@ -10,8 +10,8 @@
 //
 //   pdsch_offline worker|batch <in.bin> <out.bin>
 //   pdsch_offline acquire <capture.bin> <out.txt>     cell search -> MIB -> subframe synchronisation on a 1.92 Msps capture
-// in.bin : 12 int32 {magic 0x53525355, nof_prb, nof_ports, cell_id, sf_idx, cfi, rnti, qm, tbs, rv, n_sf, max_iter}
-//          followed by n_sf * SRSLTE_SF_LEN_PRB(nof_prb) cf_t samples
+// in.bin : 12 int32 {magic 0x53525355 (normal cyclic prefix) or 0x53525345 (extended), nof_prb, nof_ports (1, 2, 4), cell_id, sf_idx,
+//          cfi, rnti, qm, tbs, rv, n_sf, max_iter} followed by n_sf * SRSLTE_SF_LEN_PRB(nof_prb) cf_t samples
 // out.bin: per subframe {int32 ack, int32 n_iter, float snr} followed by tbs/8 payload bytes
 #include <cstdint>
 #include <cstdio>
@@ -26,6 +26,8 @@
 namespace {
 
 struct Header { int32_t magic, nof_prb, nof_ports, cell_id, sf_idx, cfi, rnti, qm, tbs, rv, n_sf, max_iter; };
+constexpr int32_t kMagicNorm = 0x53525355, kMagicExt = 0x53525345;
+inline int header_cp(const Header& h) { return h.magic == kMagicExt ? 1 : 0; }
 
 // what mac->new_grant_dl() hands back to the worker (mac_interface.h:62-74), reduced to the fields the DL path reads
 struct tb_action_dl_t {
@@ -60,7 +62,7 @@ class mac_stub {   // one HARQ process: owns the soft buffer and the PDU buffer
 int run_worker(const Header& h, cf_t* iq, FILE* out) {
   srslte_cell_t cell;
   std::memset(&cell, 0, sizeof(cell));
-  cell.nof_prb = h.nof_prb; cell.nof_ports = h.nof_ports; cell.id = h.cell_id; cell.cp = SRSLTE_CP_NORM;
+  cell.nof_prb = h.nof_prb; cell.nof_ports = h.nof_ports; cell.id = h.cell_id; cell.cp = header_cp(h) ? SRSLTE_CP_EXT : SRSLTE_CP_NORM;
   srslte_ue_dl_t ue_dl;
   if (srslte_ue_dl_init(&ue_dl, cell)) { fprintf(stderr, "Initiating UE DL: %s\n", srsue_gpu_last_error()); return 1; }
   srslte_ue_dl_set_rnti(&ue_dl, (uint16_t)h.rnti);
@@ -112,7 +114,7 @@ int run_worker(const Header& h, cf_t* iq, FILE* out) {
 int run_batch(const Header& h, cf_t* iq, FILE* out) {
   srsue_gpu_ctx_t* ctx = nullptr;
   if (srsue_gpu_ctx_create(&ctx, 0)) { fprintf(stderr, "%s\n", srsue_gpu_last_error()); return 1; }
-  srsue_gpu_cell_t cell = {h.nof_prb, h.nof_ports, h.cell_id};
+  srsue_gpu_cell_t cell = {h.nof_prb, h.nof_ports, h.cell_id, header_cp(h)};
   srsue_gpu_pdsch_cfg_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.sf_idx = h.sf_idx; cfg.cfi = h.cfi; cfg.rnti = h.rnti; cfg.qm = h.qm; cfg.tbs = h.tbs; cfg.rv = h.rv;
@@ -157,7 +159,7 @@ int run_batch_multi(const Header& h, cf_t* iq, FILE* out, int n_gpus) {
   std::vector<srsue_gpu_sf_desc_t> d((size_t)h.n_sf);
   for (int n = 0; n < h.n_sf; n++) {
     std::memset(&d[n], 0, sizeof(d[n]));
-    d[n].cell = {h.nof_prb, h.nof_ports, h.cell_id};
+    d[n].cell = {h.nof_prb, h.nof_ports, h.cell_id, header_cp(h)};
     d[n].cfg.sf_idx = h.sf_idx; d[n].cfg.cfi = h.cfi; d[n].cfg.rnti = h.rnti; d[n].cfg.qm = h.qm; d[n].cfg.tbs = h.tbs; d[n].cfg.rv = h.rv;
     d[n].cfg.tm = h.nof_ports == 1 ? 1 : 2; d[n].cfg.nof_prb_alloc = h.nof_prb;
     for (int i = 0; i < h.nof_prb; i++) d[n].cfg.prb_mask[i] = 1;
@@ -276,7 +278,7 @@ int main(int argc, char** argv) {
   FILE* in = fopen(argv[2], "rb");
   if (!in) { perror(argv[2]); return 1; }
   Header h;
-  if (fread(&h, sizeof(h), 1, in) != 1 || h.magic != 0x53525355) { fprintf(stderr, "bad header\n"); return 1; }
+  if (fread(&h, sizeof(h), 1, in) != 1 || (h.magic != kMagicNorm && h.magic != kMagicExt)) { fprintf(stderr, "bad header\n"); return 1; }
   const size_t n = (size_t)h.n_sf * SRSLTE_SF_LEN_PRB(h.nof_prb);
   cf_t* iq = (cf_t*)srslte_vec_malloc((uint32_t)(n * sizeof(cf_t)));
   if (!iq || fread(iq, sizeof(cf_t), n, in) != n) { fprintf(stderr, "short read\n"); return 1; }

@@ -461,3 +461,39 @@ def test_blind_batch_other_cell_shapes(gpu, oracle):
         rc_o, pl_o, _, _ = o.ue_dl_decode(ocell, ocfg, iq, 0.01, 0, 4)
         assert rc_o == 0 and r["crc_ok"] == 1 and np.array_equal(r["payload"], pl_o) and np.array_equal(pl_o, tb)
     b.close()
+
+
+def test_cpp_offline_driver_on_a_four_port_extended_prefix_capture(gpu, oracle, tmp_path):
+    """driver/pdsch_offline.cc (worker = phch_worker's call sequence, batch = the batching layer) on a capture of a four-port
+    cell with the extended cyclic prefix (header magic 0x53525345): transport blocks, verdicts, iterations and SNR of the oracle"""
+    import os, struct, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "pdsch_offline")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "driver", "pdsch_offline.cc"), "-L" + os.path.join(root, "srsue_b200"),
+                           "-lsrsue_gpu", "-Wl,-rpath," + os.path.join(root, "srsue_b200")])
+    o = oracle
+    for cp, magic in ((1, 0x53525345), (0, 0x53525355)):
+        prb, qm, tbs, n = 50, 4, 6200, 4
+        ocell = o.make_cell(prb, 4, 1, cp=cp)
+        ocfg = o.make_cfg(ocell, sf_idx=1, cfi=1, qm=qm, tbs=tbs, tm=2)
+        iq = np.stack([o.gen_subframe(ocell, ocfg, 700 + i, 18.0 if i != 2 else 0.0, _taps4())[1] for i in range(n)])
+        inp = tmp_path / ("in%d.bin" % cp)
+        with open(inp, "wb") as f:
+            f.write(struct.pack("<12i", magic, prb, 4, 1, 1, 1, 0x1234, qm, tbs, 0, n, 4))
+            f.write(iq.tobytes())
+        ref = [o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 0, 4) for i in range(n)]
+        for mode in ("worker", "batch"):
+            outp = tmp_path / ("out_%s%d.bin" % (mode, cp))
+            subprocess.check_call([exe, mode, str(inp), str(outp)])
+            raw = open(outp, "rb").read()
+            rec = 12 + tbs // 8
+            assert len(raw) == n * rec
+            for i in range(n):
+                ack, n_iter, snr = struct.unpack_from("<iif", raw, i * rec)
+                payload = np.frombuffer(raw, np.uint8, tbs // 8, i * rec + 12)
+                rc, pl, meas, avg = ref[i]
+                assert ack == int(rc == 0) and n_iter == avg, (mode, i)
+                assert np.array_equal(payload, pl), (mode, i)
+                assert abs(snr - meas[4]) <= 1e-4 * meas[4]
+        assert ref[2][0] != 0 and ref[0][0] == 0      # the noisy subframe fails, the others decode
