@@ -37,7 +37,7 @@ typedef struct { float re, im; } srsue_gpu_cf_t;        /* layout of srsLTE's cf
 
 typedef struct {
   int nof_prb;      /* 6, 15, 25, 50, 75, 100 */
-  int nof_ports;    /* 1 or 2 */
+  int nof_ports;    /* 1, 2 or 4 (four: CRS of ports 2 / 3 in symbol 1 of each slot, PDSCH and control channels in SFBC-FSTD; tm 2 only) */
   int cell_id;      /* physical cell id */
   int cp;           /* cyclic prefix: 0 = normal (srsLTE's SRSLTE_CP_NORM), 1 = extended (SRSLTE_CP_EXT): 12 symbols per
                      * subframe, CRS in symbols 0 and 3 of each slot.  Device grids (sf_symbols, ce) keep a stride of 14
@@ -183,8 +183,8 @@ int srsue_gpu_pdcch_extract_llr(srsue_gpu_pdsch_plan_t *plan, int n_sf, const sr
 int srsue_gpu_pdcch_find_dci(srsue_gpu_pdsch_plan_t *plan, int n_sf, const int16_t *d_llr, int ng_x6, int rnti, int common,
                              int nof_bits, int first_bit, int32_t *d_found, uint8_t *d_bits, uint16_t *d_rem, void *stream);
 /* PBCH / MIB (srslte_ue_mib_decode, phch_recv.cc:247): blind decode of the master information block from subframes 0
- * (plan with sf_idx 0): transmit-port hypotheses 1 and 2 (2 only when the plan's cell has two ports, i.e. both were
- * estimated) x the four positions in the 40 ms BCH period.  d_result [n_sf][4] = {found, ports, frame number mod 4, 0},
+ * (plan with sf_idx 0): transmit-port hypotheses 1, 2 and 4 (as many as the plan's cell has ports, i.e. as were
+ * estimated; CRC masks 0x0000 / 0xFFFF / 0x5555) x the four positions in the 40 ms BCH period.  d_result [n_sf][4] = {found, ports, frame number mod 4, 0},
  * d_mib [n_sf][24] one bit per byte (dl-Bandwidth 3, phich-Duration 1, phich-Resource 2, SFN/4 8, spare 10). */
 int srsue_gpu_pbch_decode(srsue_gpu_pdsch_plan_t *plan, int n_sf, const srsue_gpu_cf_t *d_sf_symbols,
                           const srsue_gpu_cf_t *d_ce, const float *d_meas, float noise_est, int noise_mode,
