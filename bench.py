@@ -442,7 +442,7 @@ def main():
                          "frequency-selective channel, MMSE with the estimated noise); mixed: configs[4], heterogeneous stream "
                          "through the batching layer; harq: MCS 28 at a BLER operating point with rv 2 retransmissions combined in "
                          "device-resident soft buffers")
-    ap.add_argument("--multi-batch", type=int, default=1024, help="subframes per device and step of the one-process dispatcher leg")
+    ap.add_argument("--multi-batch", type=int, default=4096, help="subframes per device and step of the one-process dispatcher leg (as many as the e2e leg by default)")
     ap.add_argument("--ports", type=int, default=0, choices=[0, 2, 4],
                     help="--workload tm2: 4 = a four-port cell (SFBC-FSTD, CRS of ports 2 / 3; SPEC 15c); not a BASELINE config")
     ap.add_argument("--cp", default="norm", choices=["norm", "ext"],

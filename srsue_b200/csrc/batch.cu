@@ -180,6 +180,14 @@ struct srsue_gpu_batch {
 
 namespace {
 
+// same launch shape, field for field (what plan_key() below strings together); false negatives only cost the slow path
+bool same_shape(const srsue_gpu_sf_desc_t& a, const srsue_gpu_sf_desc_t& b) {
+  return a.cell.nof_prb == b.cell.nof_prb && a.cell.nof_ports == b.cell.nof_ports && a.cell.cell_id == b.cell.cell_id &&
+         (a.cell.cp ? 1 : 0) == (b.cell.cp ? 1 : 0) && a.cfg.sf_idx == b.cfg.sf_idx && a.cfg.cfi == b.cfg.cfi && a.cfg.rnti == b.cfg.rnti &&
+         a.cfg.qm == b.cfg.qm && a.cfg.tbs == b.cfg.tbs && a.cfg.rv == b.cfg.rv && a.cfg.tm == b.cfg.tm &&
+         std::memcmp(a.cfg.prb_mask, b.cfg.prb_mask, sizeof(a.cfg.prb_mask)) == 0;
+}
+
 std::string plan_key(const srsue_gpu_sf_desc_t& d) {
   // explicit fields only (struct padding must not split buckets)
   const int v[11] = {d.cell.nof_prb, d.cell.nof_ports, d.cell.cell_id, d.cell.cp ? 1 : 0, d.cfg.sf_idx, d.cfg.cfi, d.cfg.rnti, d.cfg.qm, d.cfg.tbs, d.cfg.rv, d.cfg.tm};
@@ -317,13 +325,17 @@ double turbo_work(int tbs) {                                // sum of C * K of a
 
 int multi_submit(srsue_gpu_batch* f, srsue_gpu_sf_desc_t* descs, int n) {
   const int nd = (int)f->devs.size();
-  for (auto* d : f->devs) { d->descs.clear(); d->index.clear(); d->work = 0; }
+  for (auto* d : f->devs) { d->descs.clear(); d->index.clear(); d->work = 0; d->descs.reserve((size_t)n / nd + 64); d->index.reserve((size_t)n / nd + 64); }
   // HARQ state is device-resident: a soft buffer id stays on the device that first saw it.  Everything else is cut
   // into contiguous runs (neighbouring host buffers keep merging into single copies) balanced by estimated turbo work.
   std::vector<int> where(n, -1);
+  std::vector<double> work((size_t)n);
   double total = 0;
+  int memo_tbs = -1;
+  double memo_w = 0;
   for (int i = 0; i < n; i++) {
-    const double w = turbo_work(descs[i].cfg.tbs);
+    if (descs[i].cfg.tbs != memo_tbs) { memo_tbs = descs[i].cfg.tbs; memo_w = turbo_work(memo_tbs); }     // runs of one size
+    const double w = work[i] = memo_w;
     total += w;
     if (descs[i].softbuffer_id < 0) continue;
     auto it = f->affinity.find(descs[i].softbuffer_id);
@@ -333,7 +345,7 @@ int multi_submit(srsue_gpu_batch* f, srsue_gpu_sf_desc_t* descs, int n) {
   int cur = 0;
   for (int i = 0; i < n; i++) {
     if (where[i] >= 0) continue;
-    const double w = turbo_work(descs[i].cfg.tbs);
+    const double w = work[i];
     while (cur + 1 < nd && f->devs[cur]->work + 0.5 * w > target) cur++;
     where[i] = cur;
     f->devs[cur]->work += w;
@@ -492,6 +504,8 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
   std::map<std::string, std::vector<int>> groups;
   std::vector<std::string> group_order;
   std::map<int64_t, int> seen;
+  std::vector<int>* last_bucket = nullptr;
+  char last_mode = 0;
   for (int i = 0; i < n; i++) {
     const srsue_gpu_sf_desc_t& d = descs[i];
     if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptor %d has a null buffer", i);
@@ -502,13 +516,19 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
     if (d.softbuffer_id >= 0 && !seen.emplace(d.softbuffer_id, i).second)
       B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptors %d and %d use soft buffer %lld in one submission",
              seen[d.softbuffer_id], i, (long long)d.softbuffer_id);
-    std::string k = plan_key(d);
     // new transmissions and HARQ combines use different launches (reset vs accumulate), as do tracked and
     // untracked soft buffers
-    k.push_back(d.softbuffer_id >= 0 ? (d.new_data ? 1 : 2) : 0);
+    const char mode = d.softbuffer_id >= 0 ? (d.new_data ? 1 : 2) : 0;
+    // streams come in runs of one shape: a descriptor shaped like its predecessor joins that bucket without building a key
+    // (150 bytes of key + a map lookup per descriptor were 0.2 us each: 8 % of a 20 MHz step before the first copy started)
+    if (last_bucket && mode == last_mode && same_shape(d, descs[i - 1])) { last_bucket->push_back(i); continue; }
+    std::string k = plan_key(d);
+    k.push_back(mode);
     auto it = groups.find(k);
     if (it == groups.end()) { group_order.push_back(k); it = groups.emplace(k, std::vector<int>()).first; }
     it->second.push_back(i);
+    last_bucket = &it->second;          // (std::map nodes do not move)
+    last_mode = mode;
   }
   // ---- everything that can be refused is refused here, before the first launch: the plan of every bucket exists and
   // every combine finds an earlier transmission of the same size ------------------------------------------------------
