@@ -115,6 +115,7 @@ struct srsue_gpu_batch {
   float noise_est = 0.01f;
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_up[2] = {}, ev_free[2] = {};
+  std::vector<cudaEvent_t> ev_blind;               // blind submissions: samples of group g are on the device
   // plan cache keyed by the bytes of (cell, cfg)
   std::map<std::string, PlanEntry> plans;
   std::list<std::string> lru;
@@ -463,6 +464,7 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   cudaFree(b->d_biq); cudaFree(b->d_bsf); cudaFree(b->d_bce); cudaFree(b->d_bllr); cudaFree(b->d_bcfi); cudaFree(b->d_bfound); cudaFree(b->d_bbits);
   cudaFreeHost(b->h_bcfi); cudaFreeHost(b->h_bfound); cudaFreeHost(b->h_bbits);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(b->ev_up[i]); cudaEventDestroy(b->ev_free[i]); }
+  for (cudaEvent_t e : b->ev_blind) cudaEventDestroy(e);
   cudaStreamDestroy(b->s_compute); cudaStreamDestroy(b->s_copy);
   delete b;
 }
@@ -801,7 +803,17 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
     }
     int rc = grow(&b->d_biq, &b->biq_bytes, pos + 256, st); if (rc) return rc;
   }
+  // The uploads go out on the copy stream, group by group, each followed by an event; the control pass of a group (compute
+  // stream, below) waits for its own event only, so it runs next to the uploads of the groups behind it.
+  while (b->ev_blind.size() < group_order.size()) {
+    cudaEvent_t e;
+    B_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    b->ev_blind.push_back(e);
+  }
+  size_t g_no = 0;
   for (const std::string& gk : group_order) {
+    cudaStream_t st = b->s_copy;                          // (shadows the compute stream inside this loop)
+    struct Mark { srsue_gpu_batch* b; size_t g; ~Mark() { cudaEventRecord(b->ev_blind[g], b->s_copy); } } mark{b, g_no++};
     const std::vector<int>& idx = groups[gk];
     const int m = (int)idx.size();
     const size_t rb = (size_t)15 * symbol_sz_of(descs[idx[0]].cell.nof_prb) * esz;
@@ -842,7 +854,9 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
   b->blind_index.clear();
   for (int i = 0; i < n; i++) { descs[i].crc_ok = 0; descs[i].n_iter = 0; descs[i].cfg.tbs = 0; std::memset(descs[i].meas, 0, sizeof(descs[i].meas)); }
   struct Try { int common, fmt, first_bit; };
+  g_no = 0;
   for (const std::string& gk : group_order) {
+    B_CU(cudaStreamWaitEvent(st, b->ev_blind[g_no++], 0));
     const std::vector<int>& idx = groups[gk];
     const srsue_gpu_sf_desc_t& d0 = descs[idx[0]];
     const int rnti = d0.cfg.rnti, nof_prb = d0.cell.nof_prb;
