@@ -116,6 +116,10 @@ struct srsue_gpu_batch {
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_up[2] = {}, ev_free[2] = {};
   std::vector<cudaEvent_t> ev_blind;               // blind submissions: samples of group g are on the device
+  cudaStream_t s_aux = nullptr;                    // blind submissions: the "copy" stream of the PDSCH phase (device-side gathers), next to the uploads on s_copy
+  cudaStream_t s_ctrl = nullptr;                   // blind submissions: the control-channel passes (the host waits for each; the PDSCH chains of earlier groups run next to them)
+  float* d_bmeas = nullptr;                        // their measurements (d_meas belongs to the PDSCH chains)
+  size_t pl_off = 0;                               // payload staging used by the chunks submitted so far
   // plan cache keyed by the bytes of (cell, cfg)
   std::map<std::string, PlanEntry> plans;
   std::list<std::string> lru;
@@ -466,6 +470,9 @@ void srsue_gpu_batch_destroy(srsue_gpu_batch_t* b) {
   for (int i = 0; i < 2; i++) { cudaEventDestroy(b->ev_up[i]); cudaEventDestroy(b->ev_free[i]); }
   for (cudaEvent_t e : b->ev_blind) cudaEventDestroy(e);
   cudaStreamDestroy(b->s_compute); cudaStreamDestroy(b->s_copy);
+  if (b->s_aux) cudaStreamDestroy(b->s_aux);
+  if (b->s_ctrl) cudaStreamDestroy(b->s_ctrl);
+  cudaFree(b->d_bmeas);
   delete b;
 }
 
@@ -478,12 +485,13 @@ int srsue_gpu_batch_set_iq_format(srsue_gpu_batch_t* b, int format, float scale)
   return 0;
 }
 
-static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n);
+static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n, int first = 0);
 
 int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
   if (!b || !descs || n < 0 || n > b->max_subframes) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: bad arguments (n=%d)", n);
   if (b->pending) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: the previous submission has not been waited for");
   if (!b->devs.empty()) return multi_submit(b, descs, n);
+  b->launches = 0;
   const int rc = batch_submit_impl(b, descs, n);
   if (rc) {
     // Every descriptor is validated before the first launch, so a failure here is a CUDA error in the middle of the
@@ -495,12 +503,18 @@ int srsue_gpu_batch_submit(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int
   return rc;
 }
 
-static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n) {
-  b->launches = 0;
-  b->order.clear();
-  b->pl_chunks.clear();
-  size_t pl_total = 0, pl_off = 0;
-  for (int i = 0; i < n; i++) pl_total += (size_t)(descs[i].cfg.tbs + 7) / 8;
+// descs[first .. n) join the submission (first > 0: a blind submission feeding its PDSCH phase group by group; the payload
+// staging was sized for the whole submission by the caller, nothing that is in flight may move)
+static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, int n, int first) {
+  if (first == 0) {
+    b->order.clear();
+    b->pl_chunks.clear();
+    b->pl_off = 0;
+  }
+  size_t& pl_off = b->pl_off;
+  size_t pl_total = pl_off;
+  for (int i = first; i < n; i++) pl_total += (size_t)(descs[i].cfg.tbs + 7) / 8;
+  if (pl_total > b->h_pl_bytes && first) B_FAIL(SRSUE_GPU_ERROR, "batch_submit: payload staging too small for an appended group");
   { int rc = grow_pinned(&b->h_pl, &b->h_pl_bytes, pl_total, b->s_compute); if (rc) return rc; }
   // ---- bucket the descriptors by launch shape, keeping arrival order inside a bucket -----------------------
   std::map<std::string, std::vector<int>> groups;
@@ -509,7 +523,7 @@ static int batch_submit_impl(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* descs, i
   struct Recent { int rep; std::vector<int>* bucket; char mode; };
   Recent recent[8];
   int n_recent = 0;
-  for (int i = 0; i < n; i++) {
+  for (int i = first; i < n; i++) {
     const srsue_gpu_sf_desc_t& d = descs[i];
     if (!d.iq || !d.payload) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "batch_submit: descriptor %d has a null buffer", i);
     if (!(d.cfo > -1.0f && d.cfo < 1.0f)) B_FAIL(SRSUE_GPU_ERROR_INVALID_INPUTS, "descriptor %d: cfo %g outside (-1, 1) subcarrier spacings", i, (double)d.cfo);
@@ -771,7 +785,9 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
   }
   b->launches = 0;
   b->blind_rows_used = 0;
-  cudaStream_t st = b->s_compute;
+  if (!b->s_ctrl) B_CU(cudaStreamCreateWithFlags(&b->s_ctrl, cudaStreamNonBlocking));
+  if (!b->d_bmeas) B_CU(cudaMalloc((void**)&b->d_bmeas, (size_t)b->chunk_cap * 5 * sizeof(float)));
+  cudaStream_t st = b->s_ctrl;
   const size_t esz = b->iq_format == SRSUE_GPU_IQ_SC16 ? 4 : sizeof(srsue_gpu_cf_t);
   // ---- 1. control channels run once per (cell, subframe number, RNTI): group the descriptors first ------------------
   for (int i = 0; i < n; i++) {
@@ -851,7 +867,30 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
     B_CU(cudaMallocHost((void**)&b->h_bbits, 9 * cap * 64));
   }
   b->blind_descs.clear();
+  b->blind_descs.reserve((size_t)n);            // (the PDSCH phase keeps a pointer into it while later groups are appended)
   b->blind_index.clear();
+  // The PDSCH phase of a group starts as soon as its grants are known (step 4 below), while the samples of later groups are still
+  // on their way: its device-side gathers use a stream of their own (they would queue up behind every upload on s_copy), and
+  // the payload staging is sized now for the whole submission because nothing in flight may move later.
+  if (!b->s_aux) B_CU(cudaStreamCreateWithFlags(&b->s_aux, cudaStreamNonBlocking));
+  { const int rc = grow_pinned(&b->h_pl, &b->h_pl_bytes, (size_t)n * (size_t)payload_cap, st); if (rc) return rc; }
+  b->blind_orig = descs;
+  b->blind_n = n;
+  size_t fed = 0;
+  auto feed = [&]() -> int {                     // hands blind_descs[fed ..) to the PDSCH chain
+    if (b->blind_descs.size() == fed) return 0;
+    cudaStream_t keep = b->s_copy;
+    b->s_copy = b->s_aux;
+    b->iq_on_device = true;
+    const int rc = batch_submit_impl(b, b->blind_descs.data(), (int)b->blind_descs.size(), (int)fed);
+    b->s_copy = keep;
+    fed = b->blind_descs.size();
+    if (rc) {
+      cudaStreamSynchronize(b->s_copy); cudaStreamSynchronize(b->s_aux); cudaStreamSynchronize(b->s_compute);
+      b->iq_on_device = false; b->blind_orig = nullptr; b->blind_n = 0; b->pending = nullptr; b->n_pending = 0;
+    }
+    return rc;
+  };
   for (int i = 0; i < n; i++) { descs[i].crc_ok = 0; descs[i].n_iter = 0; descs[i].cfg.tbs = 0; std::memset(descs[i].meas, 0, sizeof(descs[i].meas)); }
   struct Try { int common, fmt, first_bit; };
   g_no = 0;
@@ -889,15 +928,15 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
       srsue_gpu_pdsch_plan_set_cfo(fp[1]->plan, nullptr, 0);
       if (b->iq_format == SRSUE_GPU_IQ_SC16) rc = srsue_gpu_ofdm_rx_sc16(fp[1]->plan, m, reinterpret_cast<const int16_t*>(rows_in), b->iq16_scale, b->d_bsf, st);
       else rc = srsue_gpu_ofdm_rx(fp[1]->plan, m, rows_in, b->d_bsf, st);
-      if (!rc) rc = srsue_gpu_chest(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, st);
+      if (!rc) rc = srsue_gpu_chest(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_bmeas, st);
       // PCFICH and PDCCH with the channel estimator's noise figure, as srslte_ue_dl_decode does
-      if (!rc) rc = srsue_gpu_pcfich_decode(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_meas, 0.0f, 1, b->d_bcfi, nullptr, st);
+      if (!rc) rc = srsue_gpu_pcfich_decode(fp[1]->plan, m, b->d_bsf, b->d_bce, b->d_bmeas, 0.0f, 1, b->d_bcfi, nullptr, st);
       if (rc) return rc;
       bool have_try[9] = {};
       for (int cfi = 1; cfi <= 3; cfi++) {
         int16_t* llr = b->d_bllr + (size_t)(cfi - 1) * cap * 8 * n_reg_max;
         srsue_gpu_pdsch_plan_set_row_filter(fp[cfi]->plan, b->d_bcfi, cfi);     // only the subframes whose PCFICH said this CFI
-        rc = srsue_gpu_pdcch_extract_llr(fp[cfi]->plan, m, b->d_bsf, b->d_bce, b->d_meas, 0.0f, 1, ng_x6, llr, st);
+        rc = srsue_gpu_pdcch_extract_llr(fp[cfi]->plan, m, b->d_bsf, b->d_bce, b->d_bmeas, 0.0f, 1, ng_x6, llr, st);
         if (rc) return rc;
         for (int t = 0; t < n_tries; t++) {
           const int slot = (cfi - 1) * 3 + t;
@@ -954,21 +993,9 @@ int srsue_gpu_batch_submit_blind(srsue_gpu_batch_t* b, srsue_gpu_sf_desc_t* desc
         }
       }
     }
+    // ---- 4. the PDSCH chain for the subframes of this group that have a grant, bucketed by grant as usual ----------------
+    { const int rc4 = feed(); if (rc4) return rc4; }
   }
-  // ---- 4. the PDSCH chain for every subframe with a grant, bucketed by grant as usual ------------------------------------
-  b->blind_orig = descs;
-  b->blind_n = n;
-  if (b->blind_descs.empty()) return 0;
-  const int ctrl_launches = b->launches;
-  b->iq_on_device = true;
-  const int rc = batch_submit_impl(b, b->blind_descs.data(), (int)b->blind_descs.size());
-  if (rc) {
-    cudaStreamSynchronize(b->s_copy);
-    cudaStreamSynchronize(b->s_compute);
-    b->iq_on_device = false; b->blind_orig = nullptr; b->blind_n = 0;
-    return rc;
-  }
-  b->launches += ctrl_launches;
   return 0;
 }
 
