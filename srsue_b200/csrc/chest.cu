@@ -165,7 +165,7 @@ __device__ __forceinline__ void chest_body(const ChestArgs& a) {
 
 __global__ void __launch_bounds__(128, 10) chest_kernel(const ChestArgs a) { chest_body<false, false>(a); }
 __global__ void __launch_bounds__(128, 10) chest_ext_kernel(const ChestArgs a) { chest_body<true, false>(a); }
-__global__ void __launch_bounds__(128) chest_p4_kernel(const ChestArgs a) { chest_body<false, true>(a); }
-__global__ void __launch_bounds__(128) chest_ext_p4_kernel(const ChestArgs a) { chest_body<true, true>(a); }
+__global__ void __launch_bounds__(512) chest_p4_kernel(const ChestArgs a) { chest_body<false, true>(a); }
+__global__ void __launch_bounds__(512) chest_ext_p4_kernel(const ChestArgs a) { chest_body<true, true>(a); }
 
 }  // namespace srsue
