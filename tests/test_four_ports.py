@@ -184,3 +184,23 @@ def test_host_tables_four_ports_agree_with_oracle(oracle):
                     lo.lteo_reg_res(C.byref(ocell), k0, l, k4.ctypes.data_as(C.c_void_p))
                     exp += [l * 12 * prb + int(k) for k in k4]
                 assert re4[:4 * m].tolist() == exp
+
+
+def test_host_tables_four_ports_all_shifts(oracle):
+    """the PDSCH RE list and the control-region REGs of the library against the oracle for every CRS frequency shift
+    (cell id mod 6), every bandwidth, both prefixes and the subframes with synchronisation signals / PBCH"""
+    import srsue_b200 as sg
+    lib = sg.lib()
+    for cp in (0, 1):
+        for prb in (6, 15, 25, 50, 75, 100):
+            for cid in (0, 1, 2, 3, 4, 5, 503):
+                for sf, cfi in ((0, 1), (5, 2), (9, 3)):
+                    cell, ocell = sg.make_cell(prb, 4, cid, cp=cp), oracle.make_cell(prb, 4, cid, cp=cp)
+                    cfg, ocfg = sg.make_cfg(cell, sf_idx=sf, cfi=cfi, tm=2), oracle.make_cfg(ocell, sf_idx=sf, cfi=cfi, tm=2)
+                    re = np.zeros(14 * 12 * prb, np.int32)
+                    n = lib.srsue_gpu_host_pdsch_re(C.byref(cell), C.byref(cfg), re.ctypes.data_as(C.c_void_p))
+                    ref = oracle.pdsch_re_list(ocell, ocfg)
+                    assert n == len(ref) and np.array_equal(re[:n], ref), (cp, prb, cid, sf, cfi)
+                    rk, rl = oracle.pdcch_regs(ocell, cfi, 6)
+                    re4 = np.zeros(4 * 12 * prb, np.int32)
+                    assert lib.srsue_gpu_host_pdcch_regs(C.byref(cell), cfi, 6, re4.ctypes.data_as(C.c_void_p)) == len(rk)
