@@ -497,3 +497,60 @@ def test_cpp_offline_driver_on_a_four_port_extended_prefix_capture(gpu, oracle, 
                 assert np.array_equal(payload, pl), (mode, i)
                 assert abs(snr - meas[4]) <= 1e-4 * meas[4]
         assert ref[2][0] != 0 and ref[0][0] == 0      # the noisy subframe fails, the others decode
+
+
+def _random_cases4(n, seed):
+    """random four-port cells / grants: every bandwidth, both prefixes, all modulations, partial and scattered allocations,
+    every subframe number and CFI, random cell ids and RNTIs, code rates 0.1 .. 0.85"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        prb = int(rng.choice([6, 15, 25, 50, 75, 100]))
+        nalloc = int(rng.integers(max(1, prb // 8), prb + 1))
+        if rng.random() < 0.5:
+            prbs = sorted(int(x) for x in rng.choice(prb, nalloc, replace=False))
+        else:
+            start = int(rng.integers(0, prb - nalloc + 1))
+            prbs = list(range(start, start + nalloc))
+        out.append(dict(prb=prb, cp=int(rng.integers(0, 2)), qm=int(rng.choice([2, 4, 6])), cid=int(rng.integers(0, 504)), sf=int(rng.integers(0, 10)),
+                        cfi=int(rng.integers(1, 4)), prbs=prbs, rnti=int(rng.integers(1, 65520)), rate=float(rng.uniform(0.1, 0.85)),
+                        seed=int(rng.integers(1, 1 << 30))))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases4(16, 20261019), ids=lambda c: "%dprb_cp%d_qm%d_sf%d_cfi%d_n%d" % (
+    c["prb"], c["cp"], c["qm"], c["sf"], c["cfi"], len(c["prbs"])))
+def test_random_grants_match_oracle_four_ports(gpu, oracle, case):
+    """whole chain on randomly drawn four-port cells and grants over four independent channels, noise around the decoding
+    threshold so that both CRC verdicts occur: payload, verdict, iterations and measurements equal the oracle's"""
+    sg, ctx = gpu
+    o = oracle
+    c = case
+    ocell = o.make_cell(c["prb"], 4, c["cid"], cp=c["cp"])
+    probe = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=40, tm=2, prbs=c["prbs"])
+    nre = len(o.pdsch_re_list(ocell, probe))
+    nre -= nre % 2
+    if nre * c["qm"] < 200:
+        pytest.skip("allocation swallowed by the synchronisation signals")
+    tbs = min(max(40, int(c["rate"] * nre * c["qm"]) // 8 * 8 - 24), 75376)
+    ocfg = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=2, prbs=c["prbs"])
+    cell = sg.make_cell(c["prb"], 4, c["cid"], cp=c["cp"])
+    cfg = sg.make_cfg(cell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=2, prbs=c["prbs"])
+    base = 10 * np.log10(2 ** (tbs / max(nre, 1)) - 1) + 3.5
+    n = 3
+    iq = np.stack([o.gen_subframe(ocell, ocfg, c["seed"] + i, base + d, _taps4(c["seed"] % 1000) if i == 1 else None)[1]
+                   for i, d in enumerate((7.0, 2.0, -4.0))])
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    assert I.nof_re == len(o.pdsch_re_list(ocell, ocfg))
+    h_pl = np.zeros((n, I.payload_stride), np.uint8)
+    h_st = np.zeros((n, 4), np.int32)
+    h_meas = np.zeros((n, 5), np.float32)
+    plan.decode_batch_host(n, iq, 0.01, 1, 5, h_pl, h_st, h_meas)
+    for i in range(n):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 1, 5)
+        assert (h_st[i, 0] == 1) == (rc == 0), "CRC verdict differs (sf %d)" % i
+        assert np.array_equal(h_pl[i], pl), "transport block differs (sf %d)" % i
+        assert h_st[i, 2] == avg
+        assert np.allclose(h_meas[i], meas, rtol=1e-4)
+    plan.close()
