@@ -475,3 +475,48 @@ def test_init_cell_sequence_extended_prefix(gpu, oracle):
     L.srslte_pbch_mib_unpack(payload, C.byref(out_cell), C.byref(sfn))
     assert nports.value == ports and out_cell.nof_prb == 50 and out_cell.phich_resources == 2
     assert sfn0 <= sfn.value + off.value <= sfn0 + 3
+
+
+def _random_ext_cases():
+    from tests.test_gpu_chain import _random_cases
+    return _random_cases(12, 20261020)
+
+
+@pytest.mark.parametrize("case", _random_ext_cases(), ids=lambda c: "%dprb_%dp_qm%d_sf%d_cfi%d_n%d" % (
+    c["prb"], c["ports"], c["qm"], c["sf"], c["cfi"], len(c["prbs"])))
+def test_random_grants_match_oracle_extended_prefix(gpu, oracle, case):
+    """whole chain on randomly drawn extended-prefix cells and grants (1 and 2 ports, scattered allocations, every subframe
+    number and CFI), noise around the decoding threshold: payload, verdict, iterations and measurements equal the oracle's"""
+    sg, ctx = gpu
+    o = oracle
+    c = case
+    tm = 1 if c["ports"] == 1 else 2
+    ocell = o.make_cell(c["prb"], c["ports"], c["cid"], cp=1)
+    probe = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=40, tm=tm, prbs=c["prbs"])
+    nre = len(o.pdsch_re_list(ocell, probe))
+    if tm == 2:
+        nre -= nre % 2
+    if nre * c["qm"] < 200:
+        pytest.skip("allocation swallowed by the synchronisation signals")
+    tbs = min(max(40, int(min(c["rate"], 0.85) * nre * c["qm"]) // 8 * 8 - 24), 61664)
+    ocfg = o.make_cfg(ocell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=tm, prbs=c["prbs"])
+    cell = sg.make_cell(c["prb"], c["ports"], c["cid"], cp=1)
+    cfg = sg.make_cfg(cell, sf_idx=c["sf"], cfi=c["cfi"], rnti=c["rnti"], qm=c["qm"], tbs=tbs, tm=tm, prbs=c["prbs"])
+    base = 10 * np.log10(2 ** (tbs / max(nre, 1)) - 1) + 2.5
+    n = 3
+    iq = np.stack([o.gen_subframe(ocell, ocfg, c["seed"] + i, base + d, _taps() if (tm == 2 and i == 1) else None)[1]
+                   for i, d in enumerate((6.0, 1.0, -4.0))])
+    plan = sg.PdschPlan(ctx, cell, cfg, n)
+    I = plan.info
+    assert I.nof_re == len(o.pdsch_re_list(ocell, ocfg))
+    h_pl = np.zeros((n, I.payload_stride), np.uint8)
+    h_st = np.zeros((n, 4), np.int32)
+    h_meas = np.zeros((n, 5), np.float32)
+    plan.decode_batch_host(n, iq, 0.01, 1, 5, h_pl, h_st, h_meas)
+    for i in range(n):
+        rc, pl, meas, avg = o.ue_dl_decode(ocell, ocfg, iq[i], 0.01, 1, 5)
+        assert (h_st[i, 0] == 1) == (rc == 0), "CRC verdict differs (sf %d)" % i
+        assert np.array_equal(h_pl[i], pl), "transport block differs (sf %d)" % i
+        assert h_st[i, 2] == avg
+        assert np.allclose(h_meas[i], meas, rtol=1e-4)
+    plan.close()
